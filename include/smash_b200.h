@@ -1,0 +1,194 @@
+/*
+ * smash_b200.h -- C ABI of libsmash_b200.so, the B200 (sm_100a) replacement for the
+ * f90wrap-exposed solver entry points of DassHydro-dev/smash v0.5.0.
+ *
+ * Every entry point below names the reference interface it replaces (paths relative to
+ * /root/reference/smash/solver/).  All arrays are caller-owned HOST memory in the reference's
+ * own layout: Fortran order, real(sp) = float, integer(4) = int32_t, and 1-BASED index values
+ * in `path`, `gauge_pos`, `rowcol_to_ind_sparse` and `ind_parameters_states` (what the Fortran
+ * side holds in memory; the f90wrap Python layer shows them 0-based, _f90wrap_decorator.py:72-106).
+ *   (nrow,ncol)       a[(row-1) + (col-1)*nrow]
+ *   (nrow,ncol,T)     a[(row-1) + (col-1)*nrow + t*nrow*ncol]
+ *   (nac,T) sparse    a[k + nac*t]        k = rowcol_to_ind_sparse(row,col) - 1
+ *   path(2,nrow*ncol) path[2*i] = row, path[2*i+1] = col
+ *   gauge_pos(ng,2)   gauge_pos[g] = row, gauge_pos[g+ng] = col
+ *   qsim(ng,T)        qsim[g + ng*t]
+ *
+ * Return value: 0 on success, non-zero on error (message via smash_b200_last_error()).  There is
+ * no CPU fallback: without a CUDA device every compute entry point fails with SMASH_B200_ENODEV.
+ * Only the gr-a structure is implemented (the structure named by BASELINE.json's configs).
+ */
+#ifndef SMASH_B200_H
+#define SMASH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMASH_B200_GNP 16 /* global/md_constant.f90:32 */
+#define SMASH_B200_GNS 8  /* global/md_constant.f90:33 */
+
+enum { SMASH_B200_OK = 0, SMASH_B200_EINVAL = 1, SMASH_B200_ENODEV = 2, SMASH_B200_ECUDA = 3,
+       SMASH_B200_EUNSUPPORTED = 4, SMASH_B200_ENOMEM = 5 };
+
+/* setup%structure (derived_type/mwd_setup.f90:113) */
+enum { SMASH_STRUCTURE_GR_A = 1, SMASH_STRUCTURE_GR_B = 2, SMASH_STRUCTURE_GR_C = 3, SMASH_STRUCTURE_GR_D = 4,
+       SMASH_STRUCTURE_VIC_A = 5 };
+/* setup%optimize%jobs_fun(:) (optimize/mwd_cost.f90:98-131) */
+enum { SMASH_JOBS_NSE = 1, SMASH_JOBS_KGE = 2, SMASH_JOBS_KGE2 = 3, SMASH_JOBS_SE = 4, SMASH_JOBS_RMSE = 5,
+       SMASH_JOBS_LOGARITHMIC = 6 };
+/* setup%optimize%jreg_fun(:) (optimize/mwd_cost.f90:200-240) */
+enum { SMASH_JREG_PRIOR = 1, SMASH_JREG_SMOOTHING = 2, SMASH_JREG_HARD_SMOOTHING = 3 };
+/* setup%optimize%mapping (routine/mwd_parameters_manipulation.f90:330-342) */
+enum { SMASH_MAPPING_NONE = 0, SMASH_MAPPING_HYPER_LINEAR = 1, SMASH_MAPPING_HYPER_POLYNOMIAL = 2 };
+
+/* Index of each field inside SmashParameters.v / SmashStates.v = position in GPARAMETERS_NAME /
+ * GSTATES_NAME (global/md_constant.f90:35-69). */
+enum { SMASH_P_CI = 0, SMASH_P_CP, SMASH_P_BETA, SMASH_P_CFT, SMASH_P_CST, SMASH_P_ALPHA, SMASH_P_EXC, SMASH_P_B,
+       SMASH_P_CUSL1, SMASH_P_CUSL2, SMASH_P_CLSL, SMASH_P_KS, SMASH_P_DS, SMASH_P_DSM, SMASH_P_WS, SMASH_P_LR };
+enum { SMASH_S_HI = 0, SMASH_S_HP, SMASH_S_HFT, SMASH_S_HST, SMASH_S_HUSL1, SMASH_S_HUSL2, SMASH_S_HLSL, SMASH_S_HLR };
+
+/* SetupDT + Optimize_SetupDT (derived_type/mwd_setup.f90:57-157): the fields the solver reads. */
+typedef struct SmashSetup {
+    int32_t structure;
+    float dt;
+    int32_t ntime_step;
+    int32_t nd;
+    int32_t ncpu; /* accepted for signature fidelity; members run on the GPU */
+    int32_t sparse_storage, save_qsim_domain, save_net_prcp_domain;
+    /* setup%optimize */
+    int32_t njf;
+    const int32_t *jobs_fun; /* (njf) SMASH_JOBS_* */
+    const float *wjobs_fun;  /* (njf) */
+    int32_t njr;
+    const int32_t *jreg_fun; /* (njr) SMASH_JREG_* */
+    const float *wjreg_fun;  /* (njr) */
+    float wjreg;
+    int32_t mapping, denormalize_forward, nhyper;
+    int32_t optimize_start_step; /* 1-based */
+    int32_t optim_parameters[SMASH_B200_GNP];
+    int32_t optim_states[SMASH_B200_GNS];
+    float lb_parameters[SMASH_B200_GNP], ub_parameters[SMASH_B200_GNP];
+    float lb_states[SMASH_B200_GNS], ub_states[SMASH_B200_GNS];
+    const float *wgauge; /* (ng) */
+} SmashSetup;
+
+/* MeshDT (derived_type/mwd_mesh.f90:45-72) */
+typedef struct SmashMesh {
+    float dx;
+    int32_t nrow, ncol, ng, nac;
+    const int32_t *flwdir, *flwacc, *active_cell; /* (nrow,ncol) */
+    const int32_t *local_active_cell;             /* (nrow,ncol) or NULL = all 1 */
+    const int32_t *path;                          /* (2,nrow*ncol) */
+    const int32_t *gauge_pos;                     /* (ng,2) */
+    const int32_t *rowcol_to_ind_sparse;          /* (nrow,ncol), used when sparse_storage */
+    const float *area;                            /* (ng) */
+} SmashMesh;
+
+/* Input_DataDT (derived_type/mwd_input_data.f90:32-50) */
+typedef struct SmashInputData {
+    const float *qobs;                    /* (ng,T) */
+    const float *prcp, *pet;              /* (nrow,ncol,T)  when !sparse_storage */
+    const float *sparse_prcp, *sparse_pet; /* (nac,T)       when  sparse_storage */
+    const float *descriptor;              /* (nrow,ncol,nd) */
+    /* 0 = forcing is re-uploaded on every call (reference semantics: arrays may change between
+     * calls).  Non-zero = caller's promise that (pointer, version) identifies immutable content,
+     * so the device-resident [block][tick][cell] copy is reused. */
+    uint64_t forcing_version;
+} SmashInputData;
+
+/* ParametersDT / StatesDT (derived_type/mwd_parameters.f90:58-78, mwd_states.f90:49-60): one
+ * (nrow,ncol) plane per field; Hyper_* variants hold (nhyper,1) planes. */
+typedef struct SmashParameters { float *v[SMASH_B200_GNP]; } SmashParameters;
+typedef struct SmashStates { float *v[SMASH_B200_GNS]; } SmashStates;
+
+/* OutputDT (derived_type/mwd_output.f90:36-57); any pointer may be NULL = not wanted. */
+typedef struct SmashOutput {
+    float *qsim;                                         /* (ng,T) */
+    float *qsim_domain, *sparse_qsim_domain;             /* (nrow,ncol,T) / (nac,T) */
+    float *net_prcp_domain, *sparse_net_prcp_domain;     /* (nrow,ncol,T) / (nac,T) */
+    float cost, cost_jobs, cost_jreg;
+    SmashStates fstates;
+} SmashOutput;
+
+/* ---- drop-in entry points --------------------------------------------------------------------- */
+
+/* replaces mw_forward::forward (forward/mw_forward.f90:18-39 -> base_forward forward/forward.f90:1-80) */
+int smash_b200_forward(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *input_data,
+                       SmashParameters *parameters, const SmashParameters *parameters_bgd, SmashStates *states,
+                       const SmashStates *states_bgd, SmashOutput *output, float *cost);
+
+/* replaces mw_forward::forward_b (forward/mw_forward.f90:41-68 -> BASE_FORWARD_B forward/forward_db.f90:10648-10936).
+ * parameters_b / states_b are overwritten (zero, then accumulate); *cost_b is the seed (callers pass 1).
+ * parameters_bgd_b, states_bgd_b and output_b of the Fortran signature carry no information and are omitted. */
+int smash_b200_forward_b(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *input_data,
+                         SmashParameters *parameters, SmashParameters *parameters_b,
+                         const SmashParameters *parameters_bgd, SmashStates *states, SmashStates *states_b,
+                         const SmashStates *states_bgd, SmashOutput *output, float *cost, float *cost_b);
+
+/* replaces mw_forward::hyper_forward (forward/mw_forward.f90:99-123 -> base_hyper_forward forward/forward.f90:82-157) */
+int smash_b200_hyper_forward(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *input_data,
+                             SmashParameters *parameters, const SmashParameters *hyper_parameters,
+                             const SmashParameters *hyper_parameters_bgd, SmashStates *states,
+                             const SmashStates *hyper_states, const SmashStates *hyper_states_bgd,
+                             SmashOutput *output, float *cost);
+
+/* replaces mw_forward::hyper_forward_b (forward/mw_forward.f90:125-152 -> BASE_HYPER_FORWARD_B forward_db.f90:11231-11554) */
+int smash_b200_hyper_forward_b(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *input_data,
+                               SmashParameters *parameters, const SmashParameters *hyper_parameters,
+                               SmashParameters *hyper_parameters_b, SmashStates *states,
+                               const SmashStates *hyper_states, SmashStates *hyper_states_b, SmashOutput *output,
+                               float *cost, float *cost_b);
+
+/* replaces mw_multiple_run::compute_multiple_run (routine/mw_multiple_run.f90:68-119).
+ * sample F(nvar,ns); ind_parameters_states (nvar) 1-based into the 16+8 stacked fields;
+ * res_cost (ns); res_qsim F(ng,T,ns) or NULL (the reference's size-0 array, :113). */
+int smash_b200_compute_multiple_run(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *input_data,
+                                    const SmashParameters *parameters, const SmashStates *states, SmashOutput *output,
+                                    const float *sample, const int32_t *ind_parameters_states, int32_t nvar, int32_t ns,
+                                    float *res_cost, float *res_qsim);
+
+/* ---- library services ------------------------------------------------------------------------- */
+const char *smash_b200_last_error(void);
+const char *smash_b200_version(void);
+int smash_b200_device_count(void);           /* number of CUDA devices, 0 if none / no driver */
+int smash_b200_set_device(int device);       /* device used by subsequent calls of this thread */
+void smash_b200_clear_cache(void);           /* drop cached mesh plans and device-resident forcing */
+/* tuning knobs (also readable from the environment as SMASH_B200_<NAME>): "math" 0 = IEEE division/sqrt +
+ * libm tanhf (default), 1 = MUFU reciprocal/rsqrt approximations; "block" = cells per CTA (0 = automatic);
+ * "member_budget_mb" = device memory per ensemble launch. */
+int smash_b200_set_option(const char *name, long long value);
+
+/* ---- device-resident plan API (bench / advanced callers) --------------------------------------
+ * A plan owns the level-ordered topology of one mesh and every device buffer; run_* launch the
+ * kernels only (inputs already in HBM) and return the device time measured with CUDA events on the
+ * plan's stream. */
+typedef struct SmashPlan SmashPlan;
+
+int smash_b200_plan_create(const SmashSetup *setup, const SmashMesh *mesh, int32_t nmember, SmashPlan **plan);
+void smash_b200_plan_destroy(SmashPlan *plan);
+/* upload + re-layout forcing ([block][tick][prcp|pet][cell]); qobs too if present */
+int smash_b200_plan_set_forcing(SmashPlan *plan, const SmashSetup *setup, const SmashInputData *input_data);
+/* member-major parameter / state values: uniform_sample F(nvar,nmember) applied on top of the planes */
+int smash_b200_plan_set_fields(SmashPlan *plan, const SmashParameters *parameters, const SmashStates *states,
+                               const float *sample, const int32_t *ind_parameters_states, int32_t nvar);
+int smash_b200_plan_run_forward(SmashPlan *plan, float *elapsed_ms);
+int smash_b200_plan_run_gradient(SmashPlan *plan, float *elapsed_ms_forward, float *elapsed_ms_reverse);
+int smash_b200_plan_get_qsim(SmashPlan *plan, float *qsim /* F(ng,T,nmember) */, float *cost /* (nmember) */);
+int smash_b200_plan_get_gradient(SmashPlan *plan, SmashParameters *parameters_b, SmashStates *states_b);
+/* sum of the device-resident q of the last run over all active cell-steps (size-independent checksum) */
+int smash_b200_plan_checksum(SmashPlan *plan, double *sum_q);
+/* topology facts: [0]=ncell_active [1]=nblocks [2]=block_size [3]=max in-block skew [4]=total ticks over blocks
+ * [5]=cross-block edges [6]=pit pairs [7]=kernel launches of the last run_* call */
+int smash_b200_plan_info(const SmashPlan *plan, int64_t info[8]);
+
+/* level ordering exposed for the bit-exact mesh tests: order[k] = 0-based flat (row + col*nrow) index of the
+ * k-th cell in device order, block_of/offset_of its block and in-block skew (n = number of active cells) */
+int smash_b200_plan_order(const SmashPlan *plan, int32_t *order, int32_t *block_of, int32_t *offset_of);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMASH_B200_H */

@@ -1,0 +1,1003 @@
+// api.cu -- C ABI of libsmash_b200.so (include/smash_b200.h): plan cache, host<->device plumbing and the
+// O(nrow*ncol) host-side pieces of base_forward / BASE_FORWARD_B that are not worth a kernel
+// ((de)normalisation, regularisation term and its adjoint, hyper-parameter mapping).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/smash_b200.h"
+#include "kernels.cuh"
+#include "topology.hpp"
+
+using namespace smash;
+
+// ------------------------------------------------------------------------------------------------
+// error handling
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            return fail(e_ == cudaErrorMemoryAllocation ? SMASH_B200_ENOMEM : SMASH_B200_ECUDA, "%s: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                      \
+    } while (0)
+#define TRY(call)                \
+    do {                         \
+        int rc_ = (call);        \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+static std::map<std::string, long long> &options() {
+    static std::map<std::string, long long> o;
+    return o;
+}
+static long long option(const char *name, long long dflt) {
+    auto it = options().find(name);
+    if (it != options().end()) return it->second;
+    std::string env = std::string("SMASH_B200_") + name;
+    for (auto &ch : env) ch = (char)toupper(ch);
+    const char *v = getenv(env.c_str());
+    return v ? atoll(v) : dflt;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device buffer helper
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    ~DBuf() { if (p) cudaFree(p); }
+    int ensure(size_t count) {
+        if (count <= n) return 0;
+        if (p) { cudaFree(p); p = nullptr; n = 0; }
+        if (count == 0) return 0;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(SMASH_B200_ENOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); }
+        n = count;
+        return 0;
+    }
+    int upload(const std::vector<T> &v, cudaStream_t s) {
+        TRY(ensure(v.size() ? v.size() : 1));
+        if (v.size()) CU(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+        return 0;
+    }
+};
+
+struct SmashPlan {
+    Topology tp;
+    DeviceTopology dtp{};
+    int nmember = 0;
+    float dt = 0, dx = 0;
+    int ncell = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    int launches = 0;
+    // topology on device
+    DBuf<int32_t> d_cell, d_off, d_flwacc, d_up_begin, d_down_kind, d_down_lane, d_gfirst, d_gnext, d_hmax, d_sparse_k;
+    DBuf<uint8_t> d_late, d_early, d_bflags;
+    DBuf<UpEntry> d_up;
+    DBuf<ExtRef> d_ext, d_rext;
+    DBuf<int64_t> d_tick_base;
+    // data
+    DBuf<float> d_forcing, d_raw_prcp, d_raw_pet, d_planes, d_fields, d_fstates, d_qsim, d_qdom, d_netp, d_tape, d_qsim_b,
+        d_wdom, d_grad, d_cost_jobs, d_qobs, d_area, d_wgauge, d_sample, d_out;
+    DBuf<int32_t> d_gauge_flwacc, d_sample_field;
+    DBuf<int> d_prog, d_rprog;
+    DBuf<unsigned int> d_ticket;
+    DBuf<double> d_sum;
+    bool need_qdom = false;
+    bool have_forcing = false, have_qobs = false, have_tape = false;
+    const void *forcing_ptr = nullptr;
+    uint64_t forcing_version = 0;
+    int forcing_sparse = -1;
+    std::vector<int32_t> gauge_flwacc;
+
+    ~SmashPlan() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (ev2) cudaEventDestroy(ev2);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+static std::mutex g_mu;
+static std::map<std::string, std::unique_ptr<SmashPlan>> g_plans;
+
+static int check_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return fail(SMASH_B200_ENODEV, "no CUDA device available (%s): libsmash_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+static int pick_block(int nactive) {
+    long long b = option("block", 0);
+    if (b > 0) return (int)b;
+    if (nactive <= 512) return std::max(32, ((nactive + 31) / 32) * 32);
+    return 256;
+}
+
+static int plan_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, int nmember) {
+    if (!setup || !mesh) return fail(SMASH_B200_EINVAL, "setup / mesh is NULL");
+    if (setup->structure != SMASH_STRUCTURE_GR_A)
+        return fail(SMASH_B200_EUNSUPPORTED, "structure %d: only gr-a is implemented on the device", setup->structure);
+    if (!mesh->flwdir || !mesh->flwacc || !mesh->active_cell || !mesh->path) return fail(SMASH_B200_EINVAL, "mesh arrays missing");
+    if (mesh->ng > 0 && (!mesh->gauge_pos || !mesh->area)) return fail(SMASH_B200_EINVAL, "mesh.gauge_pos / area missing");
+    // count computed cells to pick the block size
+    int nact = 0;
+    const int ncell = mesh->nrow * mesh->ncol;
+    for (int c = 0; c < ncell; c++)
+        if (mesh->active_cell[c] == 1 && (!mesh->local_active_cell || mesh->local_active_cell[c] == 1)) nact++;
+    const int B = pick_block(nact);
+    std::string err = build_topology(pl.tp, mesh->nrow, mesh->ncol, mesh->ng, setup->ntime_step, mesh->flwdir, mesh->flwacc,
+                                     mesh->active_cell, mesh->local_active_cell, mesh->path, mesh->gauge_pos, B);
+    if (!err.empty()) return fail(SMASH_B200_EINVAL, "%s", err.c_str());
+    pl.dt = setup->dt; pl.dx = mesh->dx; pl.ncell = ncell; pl.nmember = 0;
+    Topology &tp = pl.tp;
+    CU(cudaStreamCreateWithFlags(&pl.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&pl.ev0)); CU(cudaEventCreate(&pl.ev1)); CU(cudaEventCreate(&pl.ev2));
+    cudaStream_t s = pl.stream;
+    TRY(pl.d_cell.upload(tp.cell, s)); TRY(pl.d_off.upload(tp.off, s)); TRY(pl.d_flwacc.upload(tp.flwacc, s));
+    TRY(pl.d_late.upload(tp.late, s)); TRY(pl.d_early.upload(tp.early, s)); TRY(pl.d_up_begin.upload(tp.up_begin, s));
+    TRY(pl.d_up.upload(tp.up, s)); TRY(pl.d_ext.upload(tp.ext, s)); TRY(pl.d_rext.upload(tp.rext, s));
+    TRY(pl.d_down_kind.upload(tp.down_kind, s)); TRY(pl.d_down_lane.upload(tp.down_lane, s));
+    TRY(pl.d_gfirst.upload(tp.gauge_first, s)); TRY(pl.d_gnext.upload(tp.gauge_next, s));
+    TRY(pl.d_hmax.upload(tp.hmax, s)); TRY(pl.d_tick_base.upload(tp.tick_base, s)); TRY(pl.d_bflags.upload(tp.flags, s));
+    TRY(pl.d_sparse_k.upload(tp.sparse_k, s));
+    TRY(pl.d_ticket.ensure(1)); TRY(pl.d_sum.ensure(1));
+    DeviceTopology &d = pl.dtp;
+    d.T = tp.T; d.B = tp.B; d.nblocks = tp.nblocks; d.nslots = tp.nslots; d.ng = tp.ng; d.total_ticks = tp.total_ticks;
+    d.cell = pl.d_cell.p; d.off = pl.d_off.p; d.flwacc = pl.d_flwacc.p; d.late = pl.d_late.p; d.early = pl.d_early.p;
+    d.up_begin = pl.d_up_begin.p; d.up = pl.d_up.p; d.ext = pl.d_ext.p; d.rext = pl.d_rext.p;
+    d.down_kind = pl.d_down_kind.p; d.down_lane = pl.d_down_lane.p; d.gauge_first = pl.d_gfirst.p; d.gauge_next = pl.d_gnext.p;
+    d.hmax = pl.d_hmax.p; d.tick_base = pl.d_tick_base.p; d.bflags = pl.d_bflags.p;
+    pl.need_qdom = false;
+    for (auto f : tp.flags) if (f & BLK_PUBLISH) pl.need_qdom = true;
+    pl.gauge_flwacc.assign(std::max(1, mesh->ng), 1);
+    if (mesh->ng > 0) {
+        std::vector<float> area(mesh->area, mesh->area + mesh->ng);
+        for (int g = 0; g < mesh->ng; g++)
+            pl.gauge_flwacc[g] = mesh->flwacc[(mesh->gauge_pos[g] - 1) + (size_t)(mesh->gauge_pos[g + mesh->ng] - 1) * mesh->nrow];
+        TRY(pl.d_area.upload(area, s));
+        TRY(pl.d_gauge_flwacc.upload(pl.gauge_flwacc, s));
+    }
+    TRY(pl.d_planes.ensure((size_t)NFIELD * ncell));
+    CU(cudaStreamSynchronize(s));
+    (void)nmember;
+    return 0;
+}
+
+static int plan_members(SmashPlan &pl, int nmember, bool save_q, bool save_netp, bool gradient) {
+    const Topology &tp = pl.tp;
+    const size_t nm = (size_t)nmember;
+    TRY(pl.d_fields.ensure(nm * NFIELD * tp.nslots));
+    TRY(pl.d_fstates.ensure(nm * 3 * tp.nslots));
+    TRY(pl.d_qsim.ensure(std::max<size_t>(1, nm * tp.T * tp.ng)));
+    TRY(pl.d_cost_jobs.ensure(nm));
+    TRY(pl.d_prog.ensure(nm * tp.nblocks));
+    if (pl.need_qdom || save_q || gradient) TRY(pl.d_qdom.ensure(nm * tp.total_ticks * tp.B));
+    if (save_netp) TRY(pl.d_netp.ensure(nm * tp.total_ticks * tp.B));
+    if (gradient) {
+        TRY(pl.d_tape.ensure(nm * tp.total_ticks * 4 * tp.B));
+        TRY(pl.d_qsim_b.ensure(std::max<size_t>(1, nm * tp.T * tp.ng)));
+        TRY(pl.d_wdom.ensure(nm * tp.total_ticks * tp.B));
+        TRY(pl.d_grad.ensure(nm * NFIELD * tp.nslots));
+        TRY(pl.d_rprog.ensure(nm * tp.nblocks));
+    }
+    pl.nmember = nmember;
+    return 0;
+}
+
+static SolverArgs solver_args(SmashPlan &pl, bool save_q, bool save_netp, bool tape) {
+    SolverArgs a{};
+    a.tp = pl.dtp; a.nmember = pl.nmember; a.dt = pl.dt; a.dx = pl.dx;
+    a.save_q = save_q ? 1 : 0; a.save_netp = save_netp ? 1 : 0; a.tape_on = tape ? 1 : 0;
+    a.forcing = pl.d_forcing.p; a.fields = pl.d_fields.p; a.fstates = pl.d_fstates.p; a.qsim = pl.d_qsim.p;
+    a.qdom = pl.d_qdom.p; a.netp = pl.d_netp.p; a.tape = pl.d_tape.p; a.prog = pl.d_prog.p; a.ticket = pl.d_ticket.p;
+    a.qsim_b = pl.d_qsim_b.p; a.wdom = pl.d_wdom.p; a.grad = pl.d_grad.p; a.rprog = pl.d_rprog.p;
+    return a;
+}
+
+// ---- forcing ------------------------------------------------------------------------------------
+static int plan_set_forcing(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in) {
+    if (!in) return fail(SMASH_B200_EINVAL, "input_data is NULL");
+    const Topology &tp = pl.tp;
+    const bool sparse = setup->sparse_storage != 0;
+    const float *prcp = sparse ? in->sparse_prcp : in->prcp;
+    const float *pet = sparse ? in->sparse_pet : in->pet;
+    if (!prcp || !pet) return fail(SMASH_B200_EINVAL, "input_data.%sprcp / pet is NULL", sparse ? "sparse_" : "");
+    if (pl.have_forcing && in->forcing_version != 0 && pl.forcing_version == in->forcing_version && pl.forcing_ptr == prcp &&
+        pl.forcing_sparse == (int)sparse)
+        return 0;
+    const int64_t stride = sparse ? mesh->nac : (int64_t)mesh->nrow * mesh->ncol;
+    const size_t nraw = (size_t)stride * tp.T;
+    TRY(pl.d_raw_prcp.ensure(nraw)); TRY(pl.d_raw_pet.ensure(nraw));
+    TRY(pl.d_forcing.ensure((size_t)tp.total_ticks * 2 * tp.B));
+    CU(cudaMemcpyAsync(pl.d_raw_prcp.p, prcp, nraw * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+    CU(cudaMemcpyAsync(pl.d_raw_pet.p, pet, nraw * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+    CU(launch_relayout_forcing(pl.dtp, sparse ? pl.d_sparse_k.p : pl.d_cell.p, pl.d_raw_prcp.p, pl.d_raw_pet.p, stride,
+                               pl.d_forcing.p, pl.stream));
+    pl.launches++;
+    pl.have_forcing = true; pl.forcing_ptr = prcp; pl.forcing_version = in->forcing_version; pl.forcing_sparse = (int)sparse;
+    if (mesh->ng > 0 && in->qobs) {
+        TRY(pl.d_qobs.ensure((size_t)mesh->ng * tp.T));
+        CU(cudaMemcpyAsync(pl.d_qobs.p, in->qobs, (size_t)mesh->ng * tp.T * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+        pl.have_qobs = true;
+    }
+    return 0;
+}
+
+// ---- fields -------------------------------------------------------------------------------------
+static const int FIELD_PARAM[4] = {SMASH_P_CP, SMASH_P_CFT, SMASH_P_EXC, SMASH_P_LR};
+static const int FIELD_STATE[3] = {SMASH_S_HP, SMASH_S_HFT, SMASH_S_HLR};
+
+// stacked index (1-based, 16 parameters then 8 states) -> device field or -1
+static int stacked_to_field(int ind1) {
+    const int k = ind1 - 1;
+    if (k < SMASH_B200_GNP) { for (int f = 0; f < 4; f++) if (FIELD_PARAM[f] == k) return f; return -1; }
+    for (int f = 0; f < 3; f++) if (FIELD_STATE[f] == k - SMASH_B200_GNP) return 4 + f;
+    return -1;
+}
+
+static int plan_set_fields(SmashPlan &pl, const SmashParameters *par, const SmashStates *st, const float *sample,
+                           const int32_t *ind, int nvar, int nmember) {
+    const size_t nc = (size_t)pl.ncell;
+    for (int f = 0; f < 4; f++) {
+        if (!par->v[FIELD_PARAM[f]]) return fail(SMASH_B200_EINVAL, "parameters plane %d is NULL", FIELD_PARAM[f]);
+        CU(cudaMemcpyAsync(pl.d_planes.p + f * nc, par->v[FIELD_PARAM[f]], nc * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+    }
+    for (int f = 0; f < 3; f++) {
+        if (!st->v[FIELD_STATE[f]]) return fail(SMASH_B200_EINVAL, "states plane %d is NULL", FIELD_STATE[f]);
+        CU(cudaMemcpyAsync(pl.d_planes.p + (4 + f) * nc, st->v[FIELD_STATE[f]], nc * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+    }
+    int nv = 0;
+    if (sample && nvar > 0) {
+        std::vector<int32_t> sf(nvar);
+        for (int j = 0; j < nvar; j++) sf[j] = stacked_to_field(ind[j]);  // -1: field unused by gr-a, no effect on the run
+        TRY(pl.d_sample_field.upload(sf, pl.stream));
+        TRY(pl.d_sample.ensure((size_t)nvar * nmember));
+        CU(cudaMemcpyAsync(pl.d_sample.p, sample, (size_t)nvar * nmember * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+        nv = nvar;
+    }
+    CU(launch_gather_fields(pl.dtp, nmember, pl.d_planes.p, (int64_t)nc, nv ? pl.d_sample.p : nullptr, pl.d_sample_field.p, nv,
+                            pl.d_fields.p, pl.stream));
+    pl.launches++;
+    return 0;
+}
+
+// ---- cost ---------------------------------------------------------------------------------------
+static int make_cost_args(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, float jobs_b, bool adjoint, CostArgs &c) {
+    c = CostArgs{};
+    c.T = pl.tp.T; c.ng = mesh->ng; c.nmember = pl.nmember; c.start = setup->optimize_start_step - 1;
+    if (c.start < 0 || c.start >= c.T) return fail(SMASH_B200_EINVAL, "optimize_start_step %d out of range", setup->optimize_start_step);
+    c.dt = setup->dt; c.dx = mesh->dx;
+    c.qsim = pl.d_qsim.p; c.qobs = pl.d_qobs.p; c.area = pl.d_area.p; c.wgauge = pl.d_wgauge.p; c.gauge_flwacc = pl.d_gauge_flwacc.p;
+    c.njf = setup->njf;
+    if (c.njf > 8) return fail(SMASH_B200_EUNSUPPORTED, "more than 8 objective functions");
+    for (int j = 0; j < c.njf; j++) {
+        c.jobs_fun[j] = setup->jobs_fun[j]; c.wjobs_fun[j] = setup->wjobs_fun[j];
+        if (c.jobs_fun[j] < SMASH_JOBS_NSE || c.jobs_fun[j] > SMASH_JOBS_LOGARITHMIC)
+            return fail(SMASH_B200_EUNSUPPORTED, "jobs_fun code %d (signature-based objectives are host-side, not implemented)", c.jobs_fun[j]);
+    }
+    c.jobs_b = jobs_b; c.cost_jobs = pl.d_cost_jobs.p; c.qsim_b = adjoint ? pl.d_qsim_b.p : nullptr;
+    return 0;
+}
+
+static int run_cost(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, float jobs_b, bool adjoint) {
+    if (mesh->ng <= 0) {
+        CU(cudaMemsetAsync(pl.d_cost_jobs.p, 0, sizeof(float) * pl.nmember, pl.stream));
+        return 0;
+    }
+    if (!pl.have_qobs) return fail(SMASH_B200_EINVAL, "input_data.qobs is NULL");
+    if (!setup->wgauge) return fail(SMASH_B200_EINVAL, "setup.optimize.wgauge is NULL");
+    std::vector<float> wg(setup->wgauge, setup->wgauge + mesh->ng);
+    TRY(pl.d_wgauge.upload(wg, pl.stream));
+    CostArgs c;
+    TRY(make_cost_args(pl, setup, mesh, jobs_b, adjoint, c));
+    CU(launch_cost(c, pl.stream));
+    pl.launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side pieces of base_forward: (de)normalisation, Jreg and its adjoint, hyper mapping
+// (compiled with -ffp-contract=off on the host side: plain float arithmetic in the reference's order)
+// ------------------------------------------------------------------------------------------------
+static void normalize_planes(float *const *v, int nplanes, size_t nc, const float *lb, const float *ub, bool inverse) {
+    for (int i = 0; i < nplanes; i++) {
+        if (!v[i]) continue;
+        const float l = lb[i], u = ub[i];
+        if (!inverse) for (size_t c = 0; c < nc; c++) v[i][c] = (v[i][c] - l) / (u - l);   // mwd_parameters_manipulation.f90:154-179
+        else for (size_t c = 0; c < nc; c++) v[i][c] = v[i][c] * (u - l) + l;               // :181-206
+    }
+}
+
+struct JregCtx {
+    const SmashSetup *setup;
+    const SmashMesh *mesh;
+};
+
+// reg_prior mwd_cost.f90:1180-1221 / REG_PRIOR_B forward_db.f90:5756-5799
+static float reg_prior(const JregCtx &jc, const int32_t *optim, int nplanes, float *const *mat, float *const *bgd, float *const *mat_b, float res_b) {
+    const size_t nc = (size_t)jc.mesh->nrow * jc.mesh->ncol;
+    float res = 0.0f;
+    for (int i = 0; i < nplanes; i++)
+        if (optim[i] > 0 && mat[i] && bgd[i])
+            for (size_t c = 0; c < nc; c++) { const float d = mat[i][c] - bgd[i][c]; res = res + d * d; }
+    if (mat_b)
+        for (int i = nplanes - 1; i >= 0; i--)
+            if (optim[i] > 0 && mat[i] && bgd[i] && mat_b[i])
+                for (size_t c = nc; c-- > 0;) mat_b[i][c] = mat_b[i][c] + 2.0f * (mat[i][c] - bgd[i][c]) * res_b;
+    return res;
+}
+
+// reg_smoothing mwd_cost.f90:1100-1178 / REG_SMOOTHING_B forward_db.f90:5504-5657
+static float reg_smoothing(const JregCtx &jc, const int32_t *optim, int nplanes, float *const *matrix, float *const *bgd,
+                           bool rel_to_bgd, float *const *matrix_b, float res_b) {
+    const int nrow = jc.mesh->nrow, ncol = jc.mesh->ncol;
+    const int32_t *act = jc.mesh->active_cell;
+    float res = 0.0f;
+    std::vector<float> mat((size_t)nrow * ncol);
+    auto at = [&](int r, int c) -> size_t { return (size_t)(r - 1) + (size_t)(c - 1) * nrow; };
+    for (int i = 0; i < nplanes; i++) {
+        if (!(optim[i] > 0) || !matrix[i]) continue;
+        for (size_t c = 0; c < mat.size(); c++) mat[c] = rel_to_bgd ? matrix[i][c] - bgd[i][c] : matrix[i][c];
+        for (int col = 1; col <= ncol; col++)
+            for (int row = 1; row <= nrow; row++) {
+                if (act[at(row, col)] != 1) continue;
+                int min_col = std::max(1, col - 1), max_col = std::min(ncol, col + 1);
+                int min_row = std::max(1, row - 1), max_row = std::min(nrow, row + 1);
+                if (act[at(row, min_col)] == 0) min_col = col;
+                if (act[at(row, max_col)] == 0) max_col = col;
+                if (act[at(min_row, col)] == 0) min_row = row;
+                if (act[at(max_row, col)] == 0) max_row = row;
+                const float dr = mat[at(max_row, col)] - 2.0f * mat[at(row, col)] + mat[at(min_row, col)];
+                const float dc = mat[at(row, max_col)] - 2.0f * mat[at(row, col)] + mat[at(row, min_col)];
+                res = res + (dr * dr + dc * dc);
+                if (matrix_b && matrix_b[i]) {
+                    const float tb = 2.0f * dr * res_b, tb0 = 2.0f * dc * res_b;
+                    float *mb = matrix_b[i];
+                    mb[at(row, max_col)] += tb0; mb[at(row, col)] -= 2.0f * tb0; mb[at(row, min_col)] += tb0;
+                    mb[at(max_row, col)] += tb; mb[at(row, col)] -= 2.0f * tb; mb[at(min_row, col)] += tb;
+                }
+            }
+    }
+    return res;
+}
+
+// compute_jreg mwd_cost.f90:159-245 (+ COMPUTE_JREG_B forward_db.f90:2927-3092 when *_b given; they accumulate)
+static int compute_jreg(const JregCtx &jc, float *const *par, float *const *par_bgd, float *const *st, float *const *st_bgd,
+                        float *const *par_b, float *const *st_b, float jreg_b, float *jreg) {
+    const SmashSetup *s = jc.setup;
+    float pj = 0.0f, sj = 0.0f;
+    for (int i = 0; i < s->njr; i++) {
+        const float w = s->wjreg_fun[i];
+        switch (s->jreg_fun[i]) {
+            case SMASH_JREG_PRIOR:
+                pj = pj + w * reg_prior(jc, s->optim_parameters, SMASH_B200_GNP, par, par_bgd, par_b, w * jreg_b);
+                sj = sj + w * reg_prior(jc, s->optim_states, SMASH_B200_GNS, st, st_bgd, st_b, w * jreg_b);
+                break;
+            case SMASH_JREG_SMOOTHING:
+            case SMASH_JREG_HARD_SMOOTHING: {
+                const bool rel = s->jreg_fun[i] == SMASH_JREG_SMOOTHING;
+                const float w2 = powf(w, 2.0f);
+                pj = pj + w2 * reg_smoothing(jc, s->optim_parameters, SMASH_B200_GNP, par, par_bgd, rel, par_b, w2 * jreg_b);
+                sj = sj + w2 * reg_smoothing(jc, s->optim_states, SMASH_B200_GNS, st, st_bgd, rel, st_b, w2 * jreg_b);
+            } break;
+            default:
+                return fail(SMASH_B200_EUNSUPPORTED, "jreg_fun code %d is not implemented", s->jreg_fun[i]);
+        }
+    }
+    *jreg = pj + sj;
+    return 0;
+}
+
+// hyper_parameters_to_parameters mwd_parameters_manipulation.f90:304-362 (+ states twin mwd_states_manipulation.f90:271-329)
+static void hyper_to_planes(const SmashSetup *s, const SmashMesh *m, const float *desc, float *const *hyper, float *const *planes,
+                            int nplanes, const float *lb, const float *ub) {
+    const size_t nc = (size_t)m->nrow * m->ncol;
+    for (int i = 0; i < nplanes; i++) {
+        if (!planes[i] || !hyper[i]) continue;
+        float *f = planes[i];
+        const float *h = hyper[i];
+        for (size_t c = 0; c < nc; c++) f[c] = h[0];
+        for (int j = 1; j <= s->nd; j++) {
+            const float *d = desc + (size_t)(j - 1) * nc;
+            float a, b;
+            if (s->mapping == SMASH_MAPPING_HYPER_LINEAR) { a = h[j]; b = 1.0f; }
+            else { a = h[2 * j - 1]; b = h[2 * j]; }
+            for (size_t c = 0; c < nc; c++) f[c] = f[c] + a * powf(d[c], b);
+        }
+        for (size_t c = 0; c < nc; c++) f[c] = (ub[i] - lb[i]) * (1.0f / (1.0f + expf(-f[c]))) + lb[i];
+    }
+}
+
+// HYPER_PARAMETERS_TO_PARAMETERS_B forward_db.f90:1434-1537 (+ states twin :2272-2369); planes_b is consumed
+static void hyper_to_planes_b(const SmashSetup *s, const SmashMesh *m, const float *desc, float *const *hyper, float *const *hyper_b,
+                              std::vector<std::vector<float>> &planes_b, int nplanes, const float *lb, const float *ub) {
+    const size_t nc = (size_t)m->nrow * m->ncol;
+    const int nh = s->nhyper;
+    std::vector<float> z(nc);
+    for (int i = nplanes - 1; i >= 0; i--) {
+        if (!hyper[i] || !hyper_b[i]) continue;
+        const float *h = hyper[i];
+        float *hb = hyper_b[i];
+        for (int k = 0; k < nh; k++) hb[k] = 0.0f;
+        std::vector<float> &fb = planes_b[i];
+        if (fb.empty()) continue;
+        for (size_t c = 0; c < nc; c++) z[c] = h[0];
+        for (int j = 1; j <= s->nd; j++) {
+            const float *d = desc + (size_t)(j - 1) * nc;
+            float a, b;
+            if (s->mapping == SMASH_MAPPING_HYPER_LINEAR) { a = h[j]; b = 1.0f; }
+            else { a = h[2 * j - 1]; b = h[2 * j]; }
+            for (size_t c = 0; c < nc; c++) z[c] = z[c] + a * powf(d[c], b);
+        }
+        for (size_t c = 0; c < nc; c++) {
+            const float e = expf(-z[c]);
+            const float temp = e + 1.0f;
+            fb[c] = e * (ub[i] - lb[i]) * fb[c] / (temp * temp);
+        }
+        for (int j = s->nd; j >= 1; j--) {
+            const float *d = desc + (size_t)(j - 1) * nc;
+            float a, b;
+            if (s->mapping == SMASH_MAPPING_HYPER_LINEAR) { a = h[j]; b = 1.0f; }
+            else { a = h[2 * j - 1]; b = h[2 * j]; }
+            float a_b = 0.0f, b_b = 0.0f;
+            for (size_t c = 0; c < nc; c++) a_b = a_b + powf(d[c], b) * fb[c];
+            if (s->mapping == SMASH_MAPPING_HYPER_LINEAR) hb[j] += a_b;
+            else {
+                for (size_t c = 0; c < nc; c++)
+                    if (!(d[c] <= 0.0f)) b_b = b_b + powf(d[c], b) * logf(d[c]) * (a * fb[c]);
+                hb[2 * j] += b_b; hb[2 * j - 1] += a_b;
+            }
+        }
+        float sum = 0.0f;
+        for (size_t c = 0; c < nc; c++) sum = sum + fb[c];
+        hb[0] += sum;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan cache
+// ------------------------------------------------------------------------------------------------
+static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **out) {
+    if (!setup || !mesh) return fail(SMASH_B200_EINVAL, "setup / mesh is NULL");
+    TRY(check_device());
+    const uint64_t h = hash_mesh(mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
+                                 mesh->local_active_cell, mesh->path, mesh->gauge_pos);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    char key[160];
+    snprintf(key, sizeof key, "%016llx:%d:%d:%g:%g:%lld", (unsigned long long)h, dev, setup->ntime_step, (double)setup->dt,
+             (double)mesh->dx, option("block", 0));
+    auto it = g_plans.find(key);
+    if (it == g_plans.end()) {
+        std::unique_ptr<SmashPlan> pl(new SmashPlan());
+        TRY(plan_build(*pl, setup, mesh, 1));
+        it = g_plans.emplace(key, std::move(pl)).first;
+    }
+    *out = it->second.get();
+    return 0;
+}
+
+static int download(SmashPlan &pl, void *dst, const void *src, size_t bytes) {
+    CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, pl.stream));
+    return 0;
+}
+
+// qsim_domain / net_prcp_domain in the reference's layout
+static int export_domain(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, const float *skewed, float *dense, float *sparse) {
+    const Topology &tp = pl.tp;
+    if (setup->sparse_storage) {
+        if (!sparse) return 0;
+        const size_t n = (size_t)mesh->nac * tp.T;
+        TRY(pl.d_out.ensure(n));
+        CU(cudaMemsetAsync(pl.d_out.p, 0, n * sizeof(float), pl.stream));
+        CU(launch_unskew(pl.dtp, pl.d_sparse_k.p, skewed, mesh->nac, 0.0f, pl.d_out.p, pl.stream));
+        pl.launches++;
+        CU(cudaMemcpyAsync(sparse, pl.d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, pl.stream));
+    } else {
+        if (!dense) return 0;
+        // only active cells are written by the reference (md_forward_structure.f90:164-194): read-modify-write
+        const size_t n = (size_t)pl.ncell * tp.T;
+        TRY(pl.d_out.ensure(n));
+        CU(cudaMemcpyAsync(pl.d_out.p, dense, n * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+        CU(launch_unskew(pl.dtp, pl.d_cell.p, skewed, pl.ncell, 0.0f, pl.d_out.p, pl.stream));
+        pl.launches++;
+        CU(cudaMemcpyAsync(dense, pl.d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, pl.stream));
+    }
+    return 0;
+}
+
+static void scatter_sorted(const SmashPlan &pl, const float *sorted, float *plane) {
+    const Topology &tp = pl.tp;
+    for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) plane[tp.cell[s]] = sorted[s];
+}
+
+static int math_mode() { return (int)option("math", 0); }
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, SmashParameters *par,
+                          SmashStates *st, SmashOutput *out, SmashPlan **plan_out, float *jobs_out, bool restore_states) {
+    SmashPlan *pl;
+    TRY(get_plan(setup, mesh, &pl));
+    *plan_out = pl;
+    pl->launches = 0;
+    const Topology &tp = pl->tp;
+    const bool save_q = setup->save_qsim_domain && out && (setup->sparse_storage ? out->sparse_qsim_domain : out->qsim_domain);
+    const bool save_n = setup->save_net_prcp_domain && out && (setup->sparse_storage ? out->sparse_net_prcp_domain : out->net_prcp_domain);
+    TRY(plan_members(*pl, 1, save_q, save_n, false));
+    TRY(plan_set_forcing(*pl, setup, mesh, in));
+    TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
+    SolverArgs a = solver_args(*pl, save_q, save_n, false);
+    CU(launch_forward(a, math_mode(), pl->stream));
+    pl->launches++;
+    TRY(run_cost(*pl, setup, mesh, 0.0f, false));
+    std::vector<float> fs((size_t)3 * tp.nslots);
+    float jobs = 0.0f;
+    TRY(download(*pl, fs.data(), pl->d_fstates.p, fs.size() * sizeof(float)));
+    TRY(download(*pl, &jobs, pl->d_cost_jobs.p, sizeof(float)));
+    if (out && out->qsim && mesh->ng > 0) TRY(download(*pl, out->qsim, pl->d_qsim.p, (size_t)mesh->ng * tp.T * sizeof(float)));
+    if (save_q) TRY(export_domain(*pl, setup, mesh, pl->d_qdom.p, out->qsim_domain, out->sparse_qsim_domain));
+    if (save_n) TRY(export_domain(*pl, setup, mesh, pl->d_netp.p, out->net_prcp_domain, out->sparse_net_prcp_domain));
+    CU(cudaStreamSynchronize(pl->stream));
+    const size_t nc = (size_t)pl->ncell;
+    // output%fstates = states (forward.f90:71): every plane is copied, the three prognostic ones hold final values
+    if (out)
+        for (int i = 0; i < SMASH_B200_GNS; i++)
+            if (out->fstates.v[i] && st->v[i]) memcpy(out->fstates.v[i], st->v[i], nc * sizeof(float));
+    for (int f = 0; f < 3; f++) {
+        float *dst = restore_states ? (out ? out->fstates.v[FIELD_STATE[f]] : nullptr) : st->v[FIELD_STATE[f]];
+        if (dst) scatter_sorted(*pl, fs.data() + (size_t)f * tp.nslots, dst);
+        if (!restore_states && out && out->fstates.v[FIELD_STATE[f]]) memcpy(out->fstates.v[FIELD_STATE[f]], st->v[FIELD_STATE[f]], nc * sizeof(float));
+    }
+    *jobs_out = jobs;
+    return 0;
+}
+
+extern "C" int smash_b200_forward(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, SmashParameters *par,
+                                  const SmashParameters *par_bgd, SmashStates *st, const SmashStates *st_bgd, SmashOutput *out,
+                                  float *cost) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!setup || !mesh || !par || !st) return fail(SMASH_B200_EINVAL, "NULL argument");
+    const size_t nc = (size_t)mesh->nrow * mesh->ncol;
+    if (setup->denormalize_forward) {                                   // forward.f90:33-38
+        normalize_planes(par->v, SMASH_B200_GNP, nc, setup->lb_parameters, setup->ub_parameters, true);
+        normalize_planes(st->v, SMASH_B200_GNS, nc, setup->lb_states, setup->ub_states, true);
+    }
+    SmashPlan *pl;
+    float jobs = 0.0f;
+    TRY(forward_common(setup, mesh, in, par, st, out, &pl, &jobs, true));
+    // compute_cost mwd_cost.f90:247-306
+    float jreg = 0.0f;
+    if (setup->denormalize_forward) {
+        normalize_planes(par->v, SMASH_B200_GNP, nc, setup->lb_parameters, setup->ub_parameters, false);
+        normalize_planes(st->v, SMASH_B200_GNS, nc, setup->lb_states, setup->ub_states, false);
+    }
+    if (setup->njr > 0) {
+        if (!par_bgd || !st_bgd) return fail(SMASH_B200_EINVAL, "parameters_bgd / states_bgd required by the regularisation term");
+        JregCtx jc{setup, mesh};
+        TRY(compute_jreg(jc, par->v, par_bgd->v, st->v, st_bgd->v, nullptr, nullptr, 0.0f, &jreg));
+    }
+    if (setup->denormalize_forward) {
+        normalize_planes(par->v, SMASH_B200_GNP, nc, setup->lb_parameters, setup->ub_parameters, true);
+        normalize_planes(st->v, SMASH_B200_GNS, nc, setup->lb_states, setup->ub_states, true);
+    }
+    const float c = jobs + setup->wjreg * jreg;
+    if (out) { out->cost = c; out->cost_jobs = jobs; out->cost_jreg = jreg; }
+    if (cost) *cost = c;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward_b
+// ------------------------------------------------------------------------------------------------
+static int gradient_common(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, SmashParameters *par,
+                           SmashStates *st, SmashOutput *out, float cost_b, SmashPlan **plan_out, float *jobs_out,
+                           std::vector<float> &grad) {
+    SmashPlan *pl;
+    TRY(get_plan(setup, mesh, &pl));
+    *plan_out = pl;
+    pl->launches = 0;
+    const Topology &tp = pl->tp;
+    TRY(plan_members(*pl, 1, false, false, true));
+    TRY(plan_set_forcing(*pl, setup, mesh, in));
+    TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
+    SolverArgs a = solver_args(*pl, false, false, true);
+    CU(launch_forward(a, math_mode(), pl->stream));
+    pl->launches++;
+    if (mesh->ng > 0) TRY(run_cost(*pl, setup, mesh, cost_b, true));
+    else CU(cudaMemsetAsync(pl->d_cost_jobs.p, 0, sizeof(float), pl->stream));
+    CU(launch_reverse(a, math_mode(), pl->stream));
+    pl->launches++;
+    grad.resize((size_t)NFIELD * tp.nslots);
+    float jobs = 0.0f;
+    TRY(download(*pl, grad.data(), pl->d_grad.p, grad.size() * sizeof(float)));
+    TRY(download(*pl, &jobs, pl->d_cost_jobs.p, sizeof(float)));
+    if (out && out->qsim && mesh->ng > 0) TRY(download(*pl, out->qsim, pl->d_qsim.p, (size_t)mesh->ng * tp.T * sizeof(float)));
+    CU(cudaStreamSynchronize(pl->stream));
+    *jobs_out = jobs;
+    return 0;
+}
+
+extern "C" int smash_b200_forward_b(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, SmashParameters *par,
+                                    SmashParameters *par_b, const SmashParameters *par_bgd, SmashStates *st, SmashStates *st_b,
+                                    const SmashStates *st_bgd, SmashOutput *out, float *cost, float *cost_b) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!setup || !mesh || !par || !st || !par_b || !st_b) return fail(SMASH_B200_EINVAL, "NULL argument");
+    const size_t nc = (size_t)mesh->nrow * mesh->ncol;
+    const float seed = cost_b ? *cost_b : 1.0f;
+    if (setup->denormalize_forward) {                                   // forward_db.f90:10697-10703
+        normalize_planes(par->v, SMASH_B200_GNP, nc, setup->lb_parameters, setup->ub_parameters, true);
+        normalize_planes(st->v, SMASH_B200_GNS, nc, setup->lb_states, setup->ub_states, true);
+    }
+    SmashPlan *pl;
+    float jobs = 0.0f;
+    std::vector<float> grad;
+    TRY(gradient_common(setup, mesh, in, par, st, out, seed, &pl, &jobs, grad));
+    const Topology &tp = pl->tp;
+    for (int i = 0; i < SMASH_B200_GNP; i++) if (par_b->v[i]) memset(par_b->v[i], 0, nc * sizeof(float));   // :10869
+    for (int i = 0; i < SMASH_B200_GNS; i++) if (st_b->v[i]) memset(st_b->v[i], 0, nc * sizeof(float));     // :10870
+    // COMPUTE_COST_B :3252-3353: Jreg and its adjoint act on normalised copies, the caller's arrays stay denormalised
+    float jreg = 0.0f;
+    if (setup->njr > 0) {
+        if (!par_bgd || !st_bgd) return fail(SMASH_B200_EINVAL, "parameters_bgd / states_bgd required by the regularisation term");
+        std::vector<std::vector<float>> pc(SMASH_B200_GNP), sc(SMASH_B200_GNS);
+        float *pv[SMASH_B200_GNP], *sv[SMASH_B200_GNS];
+        for (int i = 0; i < SMASH_B200_GNP; i++) { pv[i] = nullptr; if (par->v[i]) { pc[i].assign(par->v[i], par->v[i] + nc); pv[i] = pc[i].data(); } }
+        for (int i = 0; i < SMASH_B200_GNS; i++) { sv[i] = nullptr; if (st->v[i]) { sc[i].assign(st->v[i], st->v[i] + nc); sv[i] = sc[i].data(); } }
+        if (setup->denormalize_forward) {
+            normalize_planes(pv, SMASH_B200_GNP, nc, setup->lb_parameters, setup->ub_parameters, false);
+            normalize_planes(sv, SMASH_B200_GNS, nc, setup->lb_states, setup->ub_states, false);
+        }
+        JregCtx jc{setup, mesh};
+        TRY(compute_jreg(jc, pv, par_bgd->v, sv, st_bgd->v, par_b->v, st_b->v, setup->wjreg * seed, &jreg));
+        if (setup->denormalize_forward) {                               // NORMALIZE_*_B :809-889, :1877-1900
+            for (int i = 0; i < SMASH_B200_GNS; i++) if (st_b->v[i]) for (size_t c = 0; c < nc; c++) st_b->v[i][c] = st_b->v[i][c] / (setup->ub_states[i] - setup->lb_states[i]);
+            for (int i = 0; i < SMASH_B200_GNP; i++) if (par_b->v[i]) for (size_t c = 0; c < nc; c++) par_b->v[i][c] = par_b->v[i][c] / (setup->ub_parameters[i] - setup->lb_parameters[i]);
+        }
+    }
+    // GR_A_FORWARD_B accumulates on top (:10885)
+    for (int f = 0; f < 4; f++) {
+        float *dst = par_b->v[FIELD_PARAM[f]];
+        if (!dst) continue;
+        const float *g = grad.data() + (size_t)f * tp.nslots;
+        for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) dst[tp.cell[s]] += g[s];
+    }
+    for (int f = 0; f < 3; f++) {
+        float *dst = st_b->v[FIELD_STATE[f]];
+        if (!dst) continue;
+        const float *g = grad.data() + (size_t)(4 + f) * tp.nslots;
+        for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) dst[tp.cell[s]] += g[s];
+    }
+    if (setup->denormalize_forward) {                                   // :10931-10935
+        for (int i = 0; i < SMASH_B200_GNS; i++) if (st_b->v[i]) for (size_t c = 0; c < nc; c++) st_b->v[i][c] = (setup->ub_states[i] - setup->lb_states[i]) * st_b->v[i][c];
+        for (int i = 0; i < SMASH_B200_GNP; i++) if (par_b->v[i]) for (size_t c = 0; c < nc; c++) par_b->v[i][c] = (setup->ub_parameters[i] - setup->lb_parameters[i]) * par_b->v[i][c];
+    }
+    const float c = jobs + setup->wjreg * jreg;
+    if (out) { out->cost = c; out->cost_jobs = jobs; out->cost_jreg = jreg; }
+    if (cost) *cost = c;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// hyper_forward / hyper_forward_b
+// ------------------------------------------------------------------------------------------------
+static int hyper_check(const SmashSetup *setup, const SmashInputData *in) {
+    if (setup->mapping != SMASH_MAPPING_HYPER_LINEAR && setup->mapping != SMASH_MAPPING_HYPER_POLYNOMIAL)
+        return fail(SMASH_B200_EINVAL, "hyper_forward needs mapping hyper-linear or hyper-polynomial");
+    const int want = setup->mapping == SMASH_MAPPING_HYPER_LINEAR ? 1 + setup->nd : 1 + 2 * setup->nd;
+    if (setup->nhyper != want) return fail(SMASH_B200_EINVAL, "nhyper = %d, expected %d", setup->nhyper, want);
+    if (setup->nd > 0 && (!in || !in->descriptor)) return fail(SMASH_B200_EINVAL, "input_data.descriptor is NULL");
+    return 0;
+}
+
+extern "C" int smash_b200_hyper_forward(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in,
+                                        SmashParameters *par, const SmashParameters *hyper_par, const SmashParameters *hyper_par_bgd,
+                                        SmashStates *st, const SmashStates *hyper_st, const SmashStates *hyper_st_bgd,
+                                        SmashOutput *out, float *cost) {
+    (void)hyper_par_bgd; (void)hyper_st_bgd;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!setup || !mesh || !par || !st || !hyper_par || !hyper_st) return fail(SMASH_B200_EINVAL, "NULL argument");
+    TRY(hyper_check(setup, in));
+    hyper_to_planes(setup, mesh, in->descriptor, hyper_par->v, par->v, SMASH_B200_GNP, setup->lb_parameters, setup->ub_parameters);
+    hyper_to_planes(setup, mesh, in->descriptor, hyper_st->v, st->v, SMASH_B200_GNS, setup->lb_states, setup->ub_states);
+    SmashPlan *pl;
+    float jobs = 0.0f;
+    TRY(forward_common(setup, mesh, in, par, st, out, &pl, &jobs, false));   // states keep their final values (forward.f90:145)
+    const float c = jobs + setup->wjreg * 0.0f;                          // hyper_compute_cost mwd_cost.f90:309-348
+    if (out) { out->cost = c; out->cost_jobs = jobs; }
+    if (cost) *cost = c;
+    return 0;
+}
+
+extern "C" int smash_b200_hyper_forward_b(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in,
+                                          SmashParameters *par, const SmashParameters *hyper_par, SmashParameters *hyper_par_b,
+                                          SmashStates *st, const SmashStates *hyper_st, SmashStates *hyper_st_b, SmashOutput *out,
+                                          float *cost, float *cost_b) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!setup || !mesh || !par || !st || !hyper_par || !hyper_st || !hyper_par_b || !hyper_st_b)
+        return fail(SMASH_B200_EINVAL, "NULL argument");
+    TRY(hyper_check(setup, in));
+    const size_t nc = (size_t)mesh->nrow * mesh->ncol;
+    const float seed = cost_b ? *cost_b : 1.0f;
+    hyper_to_planes(setup, mesh, in->descriptor, hyper_par->v, par->v, SMASH_B200_GNP, setup->lb_parameters, setup->ub_parameters);
+    hyper_to_planes(setup, mesh, in->descriptor, hyper_st->v, st->v, SMASH_B200_GNS, setup->lb_states, setup->ub_states);
+    SmashPlan *pl;
+    float jobs = 0.0f;
+    std::vector<float> grad;
+    TRY(gradient_common(setup, mesh, in, par, st, out, seed, &pl, &jobs, grad));
+    const Topology &tp = pl->tp;
+    std::vector<std::vector<float>> pb(SMASH_B200_GNP), sb(SMASH_B200_GNS);
+    for (int i = 0; i < SMASH_B200_GNP; i++) if (i != SMASH_P_BETA && i != SMASH_P_ALPHA) pb[i].assign(nc, 0.0f);   // forward_db.f90:1489-1490
+    for (int i = 0; i < SMASH_B200_GNS; i++) sb[i].assign(nc, 0.0f);
+    for (int f = 0; f < 4; f++) { const float *g = grad.data() + (size_t)f * tp.nslots; for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) pb[FIELD_PARAM[f]][tp.cell[s]] = g[s]; }
+    for (int f = 0; f < 3; f++) { const float *g = grad.data() + (size_t)(4 + f) * tp.nslots; for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) sb[FIELD_STATE[f]][tp.cell[s]] = g[s]; }
+    hyper_to_planes_b(setup, mesh, in->descriptor, hyper_st->v, hyper_st_b->v, sb, SMASH_B200_GNS, setup->lb_states, setup->ub_states);
+    hyper_to_planes_b(setup, mesh, in->descriptor, hyper_par->v, hyper_par_b->v, pb, SMASH_B200_GNP, setup->lb_parameters, setup->ub_parameters);
+    if (hyper_par_b->v[SMASH_P_BETA]) for (int k = 0; k < setup->nhyper; k++) hyper_par_b->v[SMASH_P_BETA][k] = 0.0f;
+    if (hyper_par_b->v[SMASH_P_ALPHA]) for (int k = 0; k < setup->nhyper; k++) hyper_par_b->v[SMASH_P_ALPHA][k] = 0.0f;
+    if (out) { out->cost = jobs; out->cost_jobs = jobs; }
+    if (cost) *cost = jobs;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// compute_multiple_run
+// ------------------------------------------------------------------------------------------------
+extern "C" int smash_b200_compute_multiple_run(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in,
+                                               const SmashParameters *par, const SmashStates *st, SmashOutput *out,
+                                               const float *sample, const int32_t *ind, int32_t nvar, int32_t ns,
+                                               float *res_cost, float *res_qsim) {
+    (void)out;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!setup || !mesh || !par || !st || !sample || !ind || !res_cost) return fail(SMASH_B200_EINVAL, "NULL argument");
+    if (ns <= 0) return 0;
+    if (setup->denormalize_forward) return fail(SMASH_B200_EUNSUPPORTED, "compute_multiple_run with denormalize_forward");
+    for (int j = 0; j < nvar; j++)
+        if (ind[j] < 1 || ind[j] > SMASH_B200_GNP + SMASH_B200_GNS) return fail(SMASH_B200_EINVAL, "ind_parameters_states[%d] = %d out of range", j, ind[j]);
+    SmashPlan *pl;
+    TRY(get_plan(setup, mesh, &pl));
+    pl->launches = 0;
+    const Topology &tp = pl->tp;
+    // members per launch bounded by a memory budget
+    const size_t per_member = ((size_t)NFIELD + 3) * tp.nslots * 4 + (size_t)tp.T * tp.ng * 4 + (pl->need_qdom ? (size_t)tp.total_ticks * tp.B * 4 : 0) + 64;
+    const size_t budget = (size_t)option("member_budget_mb", 16384) << 20;
+    int chunk = (int)std::min<size_t>((size_t)ns, std::max<size_t>(1, budget / per_member));
+    TRY(plan_set_forcing(*pl, setup, mesh, in));
+    const size_t nq = (size_t)mesh->ng * tp.T;
+    std::vector<float> jobs(chunk);
+    for (int m0 = 0; m0 < ns; m0 += chunk) {
+        const int nm = std::min(chunk, ns - m0);
+        TRY(plan_members(*pl, nm, false, false, false));
+        TRY(plan_set_fields(*pl, par, st, sample + (size_t)m0 * nvar, ind, nvar, nm));
+        SolverArgs a = solver_args(*pl, false, false, false);
+        CU(launch_forward(a, math_mode(), pl->stream));
+        pl->launches++;
+        TRY(run_cost(*pl, setup, mesh, 0.0f, false));
+        TRY(download(*pl, jobs.data(), pl->d_cost_jobs.p, (size_t)nm * sizeof(float)));
+        if (res_qsim && nq) TRY(download(*pl, res_qsim + (size_t)m0 * nq, pl->d_qsim.p, (size_t)nm * nq * sizeof(float)));
+        CU(cudaStreamSynchronize(pl->stream));
+        for (int m = 0; m < nm; m++) res_cost[m0 + m] = jobs[m];
+    }
+    // regularisation term of each member (uniform planes against the caller's background), mwd_cost.f90:280-303
+    if (setup->njr > 0 && setup->wjreg != 0.0f) {
+        const size_t nc = (size_t)mesh->nrow * mesh->ncol;
+        std::vector<std::vector<float>> pc(SMASH_B200_GNP), sc(SMASH_B200_GNS);
+        float *pv[SMASH_B200_GNP], *sv[SMASH_B200_GNS];
+        JregCtx jc{setup, mesh};
+        for (int m = 0; m < ns; m++) {
+            for (int i = 0; i < SMASH_B200_GNP; i++) { pv[i] = nullptr; if (par->v[i]) { pc[i].assign(par->v[i], par->v[i] + nc); pv[i] = pc[i].data(); } }
+            for (int i = 0; i < SMASH_B200_GNS; i++) { sv[i] = nullptr; if (st->v[i]) { sc[i].assign(st->v[i], st->v[i] + nc); sv[i] = sc[i].data(); } }
+            for (int j = 0; j < nvar; j++) {
+                const int k = ind[j] - 1;
+                float *plane = k < SMASH_B200_GNP ? pv[k] : sv[k - SMASH_B200_GNP];
+                if (plane) std::fill(plane, plane + nc, sample[(size_t)m * nvar + j]);
+            }
+            float jreg = 0.0f;
+            TRY(compute_jreg(jc, pv, par->v, sv, st->v, nullptr, nullptr, 0.0f, &jreg));
+            res_cost[m] = res_cost[m] + setup->wjreg * jreg;
+        }
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// services
+// ------------------------------------------------------------------------------------------------
+extern "C" const char *smash_b200_last_error(void) { return g_err.c_str(); }
+extern "C" const char *smash_b200_version(void) { return "smash_b200 0.1.0 (sm_100a; reference smash v0.5.0 solver ABI)"; }
+extern "C" int smash_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int smash_b200_set_device(int device) {
+    TRY(check_device());
+    CU(cudaSetDevice(device));
+    return 0;
+}
+extern "C" void smash_b200_clear_cache(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_plans.clear();
+}
+extern "C" int smash_b200_set_option(const char *name, long long value) {
+    if (!name) return fail(SMASH_B200_EINVAL, "option name is NULL");
+    std::lock_guard<std::mutex> lk(g_mu);
+    options()[name] = value;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-resident plan API
+// ------------------------------------------------------------------------------------------------
+extern "C" int smash_b200_plan_create(const SmashSetup *setup, const SmashMesh *mesh, int32_t nmember, SmashPlan **plan) {
+    if (!plan) return fail(SMASH_B200_EINVAL, "plan is NULL");
+    TRY(check_device());
+    std::unique_ptr<SmashPlan> pl(new SmashPlan());
+    TRY(plan_build(*pl, setup, mesh, nmember));
+    pl->nmember = nmember > 0 ? nmember : 1;
+    *plan = pl.release();
+    return 0;
+}
+extern "C" void smash_b200_plan_destroy(SmashPlan *plan) { delete plan; }
+
+struct PlanSetupCopy { SmashSetup setup; SmashMesh mesh; };
+
+extern "C" int smash_b200_plan_set_forcing(SmashPlan *plan, const SmashSetup *setup, const SmashInputData *in) {
+    if (!plan || !setup) return fail(SMASH_B200_EINVAL, "NULL argument");
+    SmashMesh m{};
+    m.nrow = plan->tp.nrow; m.ncol = plan->tp.ncol; m.ng = plan->tp.ng;
+    int nac = 0;
+    for (int s = 0; s < plan->tp.nslots; s++) nac = std::max(nac, plan->tp.sparse_k[s] + 1);
+    m.nac = nac;
+    SmashInputData i2 = *in;
+    i2.forcing_version = 0;
+    TRY(plan_set_forcing(*plan, setup, &m, &i2));
+    CU(cudaStreamSynchronize(plan->stream));
+    return 0;
+}
+
+extern "C" int smash_b200_plan_set_fields(SmashPlan *plan, const SmashParameters *par, const SmashStates *st, const float *sample,
+                                          const int32_t *ind, int32_t nvar) {
+    if (!plan || !par || !st) return fail(SMASH_B200_EINVAL, "NULL argument");
+    const int nm = plan->nmember > 0 ? plan->nmember : 1;
+    TRY(plan_members(*plan, nm, true, false, false));
+    TRY(plan_set_fields(*plan, par, st, sample, ind, nvar, nm));
+    CU(cudaStreamSynchronize(plan->stream));
+    return 0;
+}
+
+static int plan_cost_setup(SmashPlan *plan) {
+    // plans created through the plan API evaluate NSE with unit weight on every gauge that has observations
+    (void)plan;
+    return 0;
+}
+
+extern "C" int smash_b200_plan_run_forward(SmashPlan *plan, float *elapsed_ms) {
+    if (!plan) return fail(SMASH_B200_EINVAL, "plan is NULL");
+    if (!plan->have_forcing) return fail(SMASH_B200_EINVAL, "plan has no forcing");
+    TRY(plan_cost_setup(plan));
+    plan->launches = 0;
+    SolverArgs a = solver_args(*plan, plan->d_qdom.p != nullptr, false, false);
+    CU(cudaEventRecord(plan->ev0, plan->stream));
+    CU(launch_forward(a, math_mode(), plan->stream));
+    CU(cudaEventRecord(plan->ev1, plan->stream));
+    plan->launches++;
+    CU(cudaEventSynchronize(plan->ev1));
+    if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, plan->ev0, plan->ev1));
+    return 0;
+}
+
+extern "C" int smash_b200_plan_run_gradient(SmashPlan *plan, float *ms_fwd, float *ms_rev) {
+    if (!plan) return fail(SMASH_B200_EINVAL, "plan is NULL");
+    if (!plan->have_forcing) return fail(SMASH_B200_EINVAL, "plan has no forcing");
+    const int nm = plan->nmember > 0 ? plan->nmember : 1;
+    TRY(plan_members(*plan, nm, true, false, true));
+    plan->launches = 0;
+    SolverArgs a = solver_args(*plan, true, false, true);
+    const Topology &tp = plan->tp;
+    CU(cudaEventRecord(plan->ev0, plan->stream));
+    CU(launch_forward(a, math_mode(), plan->stream));
+    CU(cudaEventRecord(plan->ev1, plan->stream));
+    plan->launches++;
+    if (tp.ng > 0 && plan->have_qobs) {
+        // NSE on every gauge, weight 1/ng (Optimize_SetupDT default wgauge, mwd_setup.f90:172)
+        std::vector<float> wg(tp.ng, 1.0f / tp.ng);
+        TRY(plan->d_wgauge.upload(wg, plan->stream));
+        CostArgs c{};
+        c.T = tp.T; c.ng = tp.ng; c.nmember = nm; c.start = 0; c.dt = plan->dt; c.dx = plan->dx;
+        c.qsim = plan->d_qsim.p; c.qobs = plan->d_qobs.p; c.area = plan->d_area.p; c.wgauge = plan->d_wgauge.p;
+        c.gauge_flwacc = plan->d_gauge_flwacc.p; c.njf = 1; c.jobs_fun[0] = SMASH_JOBS_NSE; c.wjobs_fun[0] = 1.0f;
+        c.jobs_b = 1.0f; c.cost_jobs = plan->d_cost_jobs.p; c.qsim_b = plan->d_qsim_b.p;
+        CU(launch_cost(c, plan->stream));
+        plan->launches++;
+    } else {
+        CU(cudaMemsetAsync(plan->d_qsim_b.p, 0, sizeof(float) * std::max<size_t>(1, (size_t)nm * tp.T * tp.ng), plan->stream));
+    }
+    CU(launch_reverse(a, math_mode(), plan->stream));
+    CU(cudaEventRecord(plan->ev2, plan->stream));
+    plan->launches++;
+    CU(cudaEventSynchronize(plan->ev2));
+    if (ms_fwd) CU(cudaEventElapsedTime(ms_fwd, plan->ev0, plan->ev1));
+    if (ms_rev) CU(cudaEventElapsedTime(ms_rev, plan->ev1, plan->ev2));
+    return 0;
+}
+
+extern "C" int smash_b200_plan_get_qsim(SmashPlan *plan, float *qsim, float *cost) {
+    if (!plan) return fail(SMASH_B200_EINVAL, "plan is NULL");
+    const int nm = plan->nmember > 0 ? plan->nmember : 1;
+    if (qsim && plan->tp.ng > 0) TRY(download(*plan, qsim, plan->d_qsim.p, (size_t)nm * plan->tp.T * plan->tp.ng * sizeof(float)));
+    if (cost) TRY(download(*plan, cost, plan->d_cost_jobs.p, (size_t)nm * sizeof(float)));
+    CU(cudaStreamSynchronize(plan->stream));
+    return 0;
+}
+
+extern "C" int smash_b200_plan_get_gradient(SmashPlan *plan, SmashParameters *par_b, SmashStates *st_b) {
+    if (!plan || !par_b || !st_b) return fail(SMASH_B200_EINVAL, "NULL argument");
+    const Topology &tp = plan->tp;
+    std::vector<float> grad((size_t)NFIELD * tp.nslots);
+    TRY(download(*plan, grad.data(), plan->d_grad.p, grad.size() * sizeof(float)));
+    CU(cudaStreamSynchronize(plan->stream));
+    for (int f = 0; f < 4; f++) if (par_b->v[FIELD_PARAM[f]]) scatter_sorted(*plan, grad.data() + (size_t)f * tp.nslots, par_b->v[FIELD_PARAM[f]]);
+    for (int f = 0; f < 3; f++) if (st_b->v[FIELD_STATE[f]]) scatter_sorted(*plan, grad.data() + (size_t)(4 + f) * tp.nslots, st_b->v[FIELD_STATE[f]]);
+    return 0;
+}
+
+extern "C" int smash_b200_plan_checksum(SmashPlan *plan, double *sum_q) {
+    if (!plan || !sum_q) return fail(SMASH_B200_EINVAL, "NULL argument");
+    if (!plan->d_qdom.p) return fail(SMASH_B200_EINVAL, "plan keeps no domain discharge");
+    CU(launch_checksum(plan->dtp, plan->d_qdom.p, plan->d_sum.p, plan->stream));
+    CU(cudaMemcpyAsync(sum_q, plan->d_sum.p, sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
+    CU(cudaStreamSynchronize(plan->stream));
+    return 0;
+}
+
+extern "C" int smash_b200_plan_info(const SmashPlan *plan, int64_t info[8]) {
+    if (!plan || !info) return fail(SMASH_B200_EINVAL, "NULL argument");
+    const Topology &tp = plan->tp;
+    info[0] = tp.nactive; info[1] = tp.nblocks; info[2] = tp.B; info[3] = tp.max_skew; info[4] = tp.total_ticks;
+    info[5] = tp.n_cross_edges; info[6] = tp.n_pairs; info[7] = plan->launches;
+    return 0;
+}
+
+extern "C" int smash_b200_plan_order(const SmashPlan *plan, int32_t *order, int32_t *block_of, int32_t *offset_of) {
+    if (!plan) return fail(SMASH_B200_EINVAL, "plan is NULL");
+    const Topology &tp = plan->tp;
+    int k = 0;
+    for (int s = 0; s < tp.nslots; s++) {
+        if (tp.cell[s] < 0) continue;
+        if (order) order[k] = tp.cell[s];
+        if (block_of) block_of[k] = s / tp.B;
+        if (offset_of) offset_of[k] = tp.off[s];
+        k++;
+    }
+    return 0;
+}

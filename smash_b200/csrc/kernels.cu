@@ -1,0 +1,872 @@
+// kernels.cu -- hand-written sm_100a kernels of the smash gr-a forward / adjoint solver.
+//
+// Execution model: one CTA per block of B consecutive cells of the post-ordered
+// drainage forest, one thread per cell, the whole time loop inside the kernel.  Reservoir states hp, hft,
+// hlr live in registers.  At tick d a cell works on time step t = d - off (in-block skew), so every
+// in-block inflow was produced exactly one tick earlier and is exchanged through a double buffer in shared
+// memory with one __syncthreads per tick; inflows from other blocks come from HBM/L2 behind per-block
+// progress flags (blocks only ever wait for lower-numbered blocks, numbering by an atomic ticket).
+// Forcing rows [block][tick][prcp|pet][B] (and tape rows in the reverse sweep) are streamed by TMA 1-D
+// bulk copies (cp.async.bulk, SASS UBLKCP) into an mbarrier-guarded shared-memory ring.
+//
+// Reference statements are cited as file:line under /root/reference/smash/solver/.
+#include "kernels.cuh"
+
+#include <cstdio>
+
+namespace smash {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// scalar math.  FAST = 0: IEEE division / sqrt, libm tanhf.  FAST = 1: MUFU reciprocal / rsqrt.
+// The reference's real exponents are all of the form +-4, +-1/4, 3.5, 2.5 (md_gr_operator.f90:62,77,96,104),
+// so powf is replaced by products and square roots (<= 2 ulp, like libm's powf).
+// ------------------------------------------------------------------------------------------------
+template <int FAST> __device__ __forceinline__ float fdiv(float a, float b) {
+    if (FAST) return __fdividef(a, b);
+    return a / b;
+}
+template <int FAST> __device__ __forceinline__ float frcp(float a) {
+    if (FAST) return __frcp_rn(a);
+    return 1.0f / a;
+}
+template <int FAST> __device__ __forceinline__ float pow_m025(float x) {  // x ** (-0.25)
+    if (FAST) return rsqrtf(sqrtf(x));
+    return 1.0f / sqrtf(sqrtf(x));
+}
+template <int FAST> __device__ __forceinline__ float pow_m125(float x) {  // x ** (-1.25)
+    return pow_m025<FAST>(x) * frcp<FAST>(x);
+}
+__device__ __forceinline__ float pow4(float x) { float x2 = x * x; return x2 * x2; }
+template <int FAST> __device__ __forceinline__ float pow_m4(float x) { return frcp<FAST>(pow4(x)); }
+__device__ __forceinline__ float pow_3p5(float x) { return (x * x) * x * sqrtf(x); }
+__device__ __forceinline__ float pow_2p5(float x) { return (x * x) * sqrtf(x); }
+template <int FAST> __device__ __forceinline__ float ftanh(float x) {
+    if (FAST) {
+        // x >= 0 here (pn, en >= 0 and cp > 0).  tanh x = 1 - 2/(e^{2x}+1); odd series below 0.04.
+        if (x < 0.04f) { float x2 = x * x; return x * (1.0f + x2 * (-0.33333334f + x2 * 0.13333334f)); }
+        float e = __expf(2.0f * x);
+        return 1.0f - __fdividef(2.0f, e + 1.0f);
+    }
+    return tanhf(x);
+}
+
+struct CellConst {
+    float cp, inv_cp, cft, cft_m4, exc, lr, E, fa1, den;  // den = 0.001*dx*dx*(flwacc-1)
+};
+
+// One gr-a cell-step WITHOUT routing (md_forward_structure.f90:106-144).  Updates hp, hft; returns qt and
+// the intermediates the adjoint needs.
+struct StepOut { float qt, prr, prd, l, pn, en; bool nogap; };
+
+template <int FAST>
+__device__ __forceinline__ StepOut vertical_step(const CellConst &k, float prcp, float pet, float &hp, float &hft) {
+    StepOut o;
+    float pr = 0.0f, perc = 0.0f, l = 0.0f;
+    o.pn = 0.0f; o.en = 0.0f;
+    o.nogap = (prcp >= 0.0f) && (pet >= 0.0f);                        // :106
+    if (o.nogap) {
+        float ei = fminf(pet, prcp);                                 // :112
+        float pn = fmaxf(0.0f, prcp - ei);                           // :114
+        float en = pet - ei;                                         // :116
+        o.pn = pn; o.en = en;
+        // gr_production md_gr_operator.f90:36-67.  One of pn, en is exactly 0, tanh(0) = 0, so only the
+        // non-zero branch of (ps, es) is evaluated; the other is exactly 0.
+        bool wet = pn > 0.0f;
+        float th = ftanh<FAST>((wet ? pn : en) * k.inv_cp);
+        float num = wet ? (k.cp * (1.0f - hp * hp)) * th : ((hp * k.cp) * (2.0f - hp)) * th;   // :52, :55
+        float den = wet ? 1.0f + hp * th : 1.0f + (1.0f - hp) * th;
+        float r = fdiv<FAST>(num, den);
+        float hp_imd = hp + (wet ? r : -r) * k.inv_cp;               // :58
+        if (wet) pr = pn - (hp_imd - hp) * k.cp;                     // :60-62
+        float w = 1.0f + pow4(hp_imd * 0.001f);                      // :66 (beta = 1000, :122 of caller)
+        float pw = (w == 1.0f) ? 1.0f : pow_m025<FAST>(w);
+        perc = (hp_imd * k.cp) * (1.0f - pw);
+        hp = hp_imd - perc * k.inv_cp;                               // :68
+        // gr_exchange md_gr_operator.f90:69-79
+        l = (k.exc == 0.0f) ? 0.0f : k.exc * pow_3p5(hft);
+    }
+    o.prr = 0.9f * (pr + perc) + l;                                  // :137
+    o.prd = 0.1f * (pr + perc);                                      // :138
+    o.l = l;
+    // gr_transfer(n = 5) md_gr_operator.f90:81-110
+    float pr_imd;
+    if (prcp < 0.0f) {
+        float x = hft * k.cft;
+        pr_imd = pow_m025<0>(pow_m4<0>(x) - k.cft_m4) - x;            // :96 (forcing gap: emptying)
+    } else {
+        pr_imd = o.prr;
+    }
+    float ht_imd = fmaxf(1.e-6f, hft + fdiv<FAST>(pr_imd, k.cft));   // :102
+    float x1 = ht_imd * k.cft;
+    float ht_new = fdiv<FAST>(pow_m025<FAST>(pow_m4<FAST>(x1) + k.cft_m4), k.cft);   // :104
+    float qr = (ht_imd - ht_new) * k.cft;                            // :106
+    hft = ht_new;
+    float qd = fmaxf(0.0f, o.prd + l);                               // :142
+    o.qt = qr + qd;                                                  // :144
+    return o;
+}
+
+__device__ __forceinline__ CellConst make_const(float cp, float cft, float exc, float lr, int flwacc, float dt, float dx) {
+    CellConst k;
+    k.cp = cp; k.inv_cp = 1.0f / cp;                                  // md_gr_operator.f90:47
+    k.cft = cft; k.cft_m4 = 1.0f / pow4(cft);
+    k.exc = exc; k.lr = lr;
+    k.E = expf(-dt / (lr * 60.0f));                                   // md_routing_operator.f90:75
+    k.fa1 = (float)(flwacc - 1);
+    k.den = 0.001f * dx * dx * k.fa1;                                 // md_routing_operator.f90:56
+    return k;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward kernel
+// ------------------------------------------------------------------------------------------------
+template <int FAST, int TAPE>
+__global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const DeviceTopology &tp = a.tp;
+    const int B = tp.B;
+    const int tid = threadIdx.x;
+    float *ring = reinterpret_cast<float *>(smem_raw);                 // [RING_STAGES][2][B]
+    float *qx = ring + RING_STAGES * 2 * B;                            // [2][B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(qx + 2 * B);         // [RING_STAGES]
+    __shared__ unsigned int s_ticket;
+
+    if (tid == 0) {
+        s_ticket = atomicAdd(a.ticket, 1u);
+        for (int s = 0; s < RING_STAGES; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    qx[tid] = 0.0f;
+    qx[B + tid] = 0.0f;
+    __syncthreads();
+    const int vb = (int)s_ticket;
+    const int member = vb / tp.nblocks;
+    const int blk = vb - member * tp.nblocks;
+    const int slot = blk * B + tid;
+    const int nticks = tp.T + tp.hmax[blk];
+    const int64_t row0 = tp.tick_base[blk];
+    const unsigned bf = tp.bflags[blk];
+    const bool has_late = bf & BLK_LATE;
+    const bool publish = (bf & BLK_PUBLISH) || a.save_q;
+    const float *frc = a.forcing + row0 * 2 * B;
+    const uint32_t row_bytes = 2u * B * sizeof(float);
+
+    if (tid == 0) {
+        for (int s = 0; s < RING_STAGES && s < nticks; s++) {
+            mbar_expect_tx(&bars[s], row_bytes);
+            tma_load_1d(ring + (size_t)s * 2 * B, frc + (size_t)s * 2 * B, row_bytes, &bars[s]);
+        }
+    }
+
+    const bool valid = tp.cell[slot] >= 0;
+    const int off = tp.off[slot];
+    const int fa = tp.flwacc[slot];
+    const bool late = tp.late[slot];
+    const int ub = tp.up_begin[slot], ue = tp.up_begin[slot + 1];
+    const int gfirst = tp.gauge_first[slot];
+    const float *fld = a.fields + (size_t)member * NFIELD * tp.nslots + slot;
+    float hp = 0.01f, hft = 0.01f, hlr = 0.0f;
+    CellConst k = make_const(1.0f, 1.0f, 0.0f, 1.0f, 1, a.dt, a.dx);
+    if (valid) {
+        k = make_const(fld[(size_t)F_CP * tp.nslots], fld[(size_t)F_CFT * tp.nslots], fld[(size_t)F_EXC * tp.nslots],
+                       fld[(size_t)F_LR * tp.nslots], fa, a.dt, a.dx);
+        hp = fld[(size_t)F_HP * tp.nslots]; hft = fld[(size_t)F_HFT * tp.nslots]; hlr = fld[(size_t)F_HLR * tp.nslots];
+    }
+    const float c_dx = a.dx, c_dt = a.dt;
+    float *qdom = a.qdom ? a.qdom + ((size_t)member * tp.total_ticks + row0) * B + tid : nullptr;
+    float *netp = (a.save_netp && a.netp) ? a.netp + ((size_t)member * tp.total_ticks + row0) * B + tid : nullptr;
+    float *tape = TAPE ? a.tape + ((size_t)member * tp.total_ticks + row0) * 4 * B + tid : nullptr;
+    float *qsim = a.qsim + (size_t)member * tp.T * tp.ng;
+    const int *prog_m = a.prog + (size_t)member * tp.nblocks;
+
+    for (int d = 0; d < nticks; d++) {
+        const int stage = d % RING_STAGES;
+        mbar_wait(&bars[stage], (d / RING_STAGES) & 1);
+        const float prcp = ring[(size_t)stage * 2 * B + tid];
+        const float pet = ring[(size_t)stage * 2 * B + B + tid];
+        const int t = d - off;
+        const bool act = valid && t >= 0 && t < tp.T;
+        const int cur = d & 1;
+        float q = 0.0f, qt = 0.0f;
+        float xv[8];
+        int nx = 0;
+        if (act) {
+            // cross-block inflows first: their latency hides behind the reservoir arithmetic
+            for (int e = ub; e < ue; e++) {
+                const int ea = tp.up[e].a;
+                if (ea < 0) {
+                    const ExtRef x = tp.ext[-ea - 1];
+                    float v = 0.0f;
+                    if (t - x.lag >= 0) {
+                        const int need = d + x.dtick + 1;
+                        while (ld_acquire(prog_m + x.blk) < need) __nanosleep(40);
+                        v = __ldcg(a.qdom + (size_t)member * tp.total_ticks * B + x.base + (int64_t)d * B);
+                    }
+                    xv[nx & 7] = v;
+                    nx++;
+                }
+            }
+            if (TAPE) { tape[(size_t)d * 4 * B] = hp; tape[(size_t)d * 4 * B + B] = hft; tape[(size_t)d * 4 * B + 2 * B] = hlr; }
+            StepOut o = vertical_step<FAST>(k, prcp, pet, hp, hft);
+            qt = o.qt;
+            if (!late) {
+                // upstream_discharge md_routing_operator.f90:17-60 (neighbour order kept)
+                float qup = 0.0f;
+                if (fa > 1) {
+                    int jx = 0;
+                    for (int e = ub; e < ue; e++) {
+                        const int ea = tp.up[e].a;
+                        qup = qup + (ea >= 0 ? qx[(cur ^ 1) * B + ea] : xv[(jx++) & 7]);
+                    }
+                    qup = fdiv<FAST>(qup * c_dt, k.den);
+                }
+                if (TAPE) tape[(size_t)d * 4 * B + 3 * B] = qup;
+                // linear_routing md_routing_operator.f90:62-79
+                float hr_imd = hlr + qup;
+                hlr = hr_imd * k.E;
+                float qrout = hr_imd - hlr;
+                q = fdiv<FAST>((qt + qrout * k.fa1) * c_dx * c_dx * 0.001f, c_dt);   // md_forward_structure.f90:155
+                qx[cur * B + tid] = q;
+            }
+        }
+        if (has_late) {
+            __syncthreads();
+            if (act && late) {
+                float qup = 0.0f;
+                int jx = 0;
+                for (int e = ub; e < ue; e++) {
+                    const UpEntry u = tp.up[e];
+                    qup = qup + (u.a >= 0 ? qx[(u.cur ? cur : cur ^ 1) * B + u.a] : xv[(jx++) & 7]);
+                }
+                qup = fdiv<FAST>(qup * c_dt, k.den);
+                if (TAPE) tape[(size_t)d * 4 * B + 3 * B] = qup;
+                float hr_imd = hlr + qup;
+                hlr = hr_imd * k.E;
+                float qrout = hr_imd - hlr;
+                q = fdiv<FAST>((qt + qrout * k.fa1) * c_dx * c_dx * 0.001f, c_dt);
+                qx[cur * B + tid] = q;
+            }
+        }
+        if (act) {
+            if (publish) qdom[(size_t)d * B] = q;
+            if (netp) netp[(size_t)d * B] = qt;
+            for (int g = gfirst; g >= 0; g = tp.gauge_next[g]) qsim[(size_t)t * tp.ng + g] = q;   // :206-210
+        }
+        __syncthreads();
+        if (tid == 0) {
+            if (bf & BLK_PUBLISH) { __threadfence(); st_release(a.prog + (size_t)member * tp.nblocks + blk, d + 1); }
+            const int dn = d + RING_STAGES;
+            if (dn < nticks) {
+                mbar_expect_tx(&bars[stage], row_bytes);
+                tma_load_1d(ring + (size_t)stage * 2 * B, frc + (size_t)dn * 2 * B, row_bytes, &bars[stage]);
+            }
+        }
+    }
+    if (valid) {
+        float *fs = a.fstates + (size_t)member * 3 * tp.nslots + slot;
+        fs[0] = hp; fs[(size_t)tp.nslots] = hft; fs[(size_t)2 * tp.nslots] = hlr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reverse (adjoint) kernel: GR_A_FORWARD_B reverse sweep, forward_db.f90:8102-8174, hand-written.
+// Carried backwards per cell: hp_b, hft_b, hlr_b; accumulated: cp_b, cft_b, exc_b, lr_b.
+// Exchange between cells: w = s * qup_b of the downstream cell (UPSTREAM_DISCHARGE_B :6553-6558) read
+// as a GATHER from the single downstream cell -- no atomics.
+// ------------------------------------------------------------------------------------------------
+template <int FAST>
+__global__ void __launch_bounds__(512) reverse_kernel(const SolverArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const DeviceTopology &tp = a.tp;
+    const int B = tp.B;
+    const int tid = threadIdx.x;
+    float *ring = reinterpret_cast<float *>(smem_raw);                 // [RING_STAGES][6][B]: prcp, pet, hp0, hft0, hlr0, qup
+    float *wx = ring + RING_STAGES * 6 * B;                            // [2][B]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(wx + 2 * B);
+    __shared__ unsigned int s_ticket;
+
+    if (tid == 0) {
+        s_ticket = atomicAdd(a.ticket, 1u);
+        for (int s = 0; s < RING_STAGES; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    wx[tid] = 0.0f;
+    wx[B + tid] = 0.0f;
+    __syncthreads();
+    const int vb = (int)s_ticket;
+    const int member = vb / tp.nblocks;
+    const int blk = tp.nblocks - 1 - (vb - member * tp.nblocks);       // reverse block order
+    const int slot = blk * B + tid;
+    const int nticks = tp.T + tp.hmax[blk];
+    const int64_t row0 = tp.tick_base[blk];
+    const unsigned bf = tp.bflags[blk];
+    const bool has_pair = bf & BLK_LATE;
+    const float *frc = a.forcing + row0 * 2 * B;
+    const float *tpe = a.tape + ((size_t)member * tp.total_ticks + row0) * 4 * B;
+    const uint32_t frc_bytes = 2u * B * sizeof(float), tape_bytes = 4u * B * sizeof(float);
+
+    // ring slot j holds tick d = nticks - 1 - j
+    if (tid == 0) {
+        for (int j = 0; j < RING_STAGES && j < nticks; j++) {
+            const int d = nticks - 1 - j;
+            mbar_expect_tx(&bars[j], frc_bytes + tape_bytes);
+            tma_load_1d(ring + (size_t)j * 6 * B, frc + (size_t)d * 2 * B, frc_bytes, &bars[j]);
+            tma_load_1d(ring + (size_t)j * 6 * B + 2 * B, tpe + (size_t)d * 4 * B, tape_bytes, &bars[j]);
+        }
+    }
+
+    const bool valid = tp.cell[slot] >= 0;
+    const int off = tp.off[slot];
+    const int fa = tp.flwacc[slot];
+    const bool early = tp.early[slot];
+    const int dkind = tp.down_kind[slot], dlane = tp.down_lane[slot];
+    const int gfirst = tp.gauge_first[slot];
+    const float *fld = a.fields + (size_t)member * NFIELD * tp.nslots + slot;
+    CellConst k = make_const(1.0f, 1.0f, 0.0f, 1.0f, 1, a.dt, a.dx);
+    if (valid)
+        k = make_const(fld[(size_t)F_CP * tp.nslots], fld[(size_t)F_CFT * tp.nslots], fld[(size_t)F_EXC * tp.nslots],
+                       fld[(size_t)F_LR * tp.nslots], fa, a.dt, a.dx);
+    ExtRef rx = {0, 0, 0, 0, 0};
+    if (dkind == 3) rx = tp.rext[dlane];
+    const float c_dx = a.dx, c_dt = a.dt;
+    const float s_w = (fa > 1) ? c_dt / k.den : 0.0f;                    // forward_db.f90:6547
+    float hp_b = 0.0f, hft_b = 0.0f, hlr_b = 0.0f, cp_b = 0.0f, cft_b = 0.0f, exc_b = 0.0f, lr_b = 0.0f;
+    const float *qsim_b = a.qsim_b + (size_t)member * tp.T * tp.ng;
+    float *wdom = a.wdom + ((size_t)member * tp.total_ticks + row0) * B + tid;
+    const int *rprog_m = a.rprog + (size_t)member * tp.nblocks;
+
+    for (int j = 0; j < nticks; j++) {
+        const int d = nticks - 1 - j;
+        const int stage = j % RING_STAGES;
+        mbar_wait(&bars[stage], (j / RING_STAGES) & 1);
+        const float *rw = ring + (size_t)stage * 6 * B + tid;
+        const float prcp = rw[0], pet = rw[B], hp0 = rw[2 * B], hft0 = rw[3 * B], hlr0 = rw[4 * B], qup = rw[5 * B];
+        const int t = d - off;
+        const bool act = valid && t >= 0 && t < tp.T;
+        const int cur = j & 1;
+        float w_out = 0.0f;
+
+        for (int phase = 0; phase < (has_pair ? 2 : 1); phase++) {
+            if (phase == 1) __syncthreads();
+            if (!(act && ((early && has_pair) ? phase == 1 : phase == 0))) continue;
+            // adjoint of the discharge of this cell-step
+            float q_b = 0.0f;
+            for (int g = gfirst; g >= 0; g = tp.gauge_next[g]) q_b += qsim_b[(size_t)t * tp.ng + g];   // :8104-8108
+            if (dkind == 1) q_b += wx[(cur ^ 1) * B + dlane];
+            else if (dkind == 2) q_b += wx[cur * B + dlane];
+            else if (dkind == 3) {
+                if (t + rx.lag < tp.T) {
+                    const int dp = d + rx.dtick;
+                    while (ld_acquire(rprog_m + rx.blk) > dp) __nanosleep(40);
+                    q_b += __ldcg(a.wdom + (size_t)member * tp.total_ticks * B + rx.base + (int64_t)d * B);
+                }
+            }
+            const float temp_b = fdiv<FAST>(c_dx * c_dx * 0.001f * q_b, c_dt);   // :8114
+            const float qt_b = temp_b;
+            const float qrout_b = k.fa1 * temp_b;                                 // :8118
+            // LINEAR_ROUTING_B :6628-6652
+            float hrb = hlr_b - qrout_b;
+            const float hr_imd_b = qrout_b + k.E * hrb;
+            const float arg1_b = k.E * (hlr0 + qup) * hrb;
+            lr_b += fdiv<FAST>(c_dt * arg1_b, (k.lr * k.lr) * 60.0f);
+            hlr_b = hr_imd_b;
+            w_out = s_w * hr_imd_b;                                               // UPSTREAM_DISCHARGE_B :6547
+            // recompute the forward intermediates of this cell-step from the taped states
+            const bool nogap = (prcp >= 0.0f) && (pet >= 0.0f);
+            float pn = 0.0f, en = 0.0f, pr = 0.0f, perc = 0.0f, l = 0.0f;
+            float tp_ = 0.0f, te_ = 0.0f, ps = 0.0f, es = 0.0f, hp_imd = hp0, pwx1 = 1.0f, pwr1 = 1.0f;
+            if (nogap) {
+                const float ei = fminf(pet, prcp);
+                pn = fmaxf(0.0f, prcp - ei);
+                en = pet - ei;
+                tp_ = (pn > 0.0f) ? ftanh<FAST>(pn * k.inv_cp) : 0.0f;
+                te_ = (en > 0.0f) ? ftanh<FAST>(en * k.inv_cp) : 0.0f;
+                ps = fdiv<FAST>(k.cp * (1.0f - hp0 * hp0) * tp_, 1.0f + hp0 * tp_);
+                es = fdiv<FAST>(hp0 * k.cp * (2.0f - hp0) * te_, 1.0f + (1.0f - hp0) * te_);
+                hp_imd = hp0 + (ps - es) * k.inv_cp;
+                if (pn > 0.0f) pr = pn - (hp_imd - hp0) * k.cp;
+                pwx1 = 1.0f + pow4(hp_imd * 0.001f);
+                pwr1 = (pwx1 == 1.0f) ? 1.0f : pow_m025<FAST>(pwx1);
+                perc = hp_imd * k.cp * (1.0f - pwr1);
+                l = (k.exc == 0.0f) ? 0.0f : k.exc * pow_3p5(hft0);
+            }
+            const float prr = 0.9f * (pr + perc) + l;
+            const float prd = 0.1f * (pr + perc);
+            const float qr_b = qt_b, qd_b = qt_b;
+            float prd_b = 0.0f, l_b = 0.0f;
+            if (0.0f < prd + l) { prd_b = qd_b; l_b = qd_b; }                     // :8128-8137
+            // GR_TRANSFER_B(n = 5) :6275-6412
+            float prr_b;
+            {
+                const float ct = k.cft, ht = hft0;
+                float pr_imd, g_pwx1 = 0.0f, g_pwx3 = 0.0f;
+                const bool gap = prcp < 0.0f;
+                if (gap) {
+                    g_pwx1 = ht * ct;
+                    g_pwx3 = pow_m4<0>(g_pwx1) - k.cft_m4;
+                    pr_imd = pow_m025<0>(g_pwx3) - ht * ct;
+                } else pr_imd = prr;
+                const float hsum = ht + fdiv<FAST>(pr_imd, ct);
+                const bool first = 1.e-6f < hsum;
+                const float ht_imd = first ? hsum : 1.e-6f;
+                const float x1 = ht_imd * ct;
+                const float x3 = pow_m4<FAST>(x1) + k.cft_m4;
+                const float pwr3 = pow_m025<FAST>(x3);
+                const float ht_new = fdiv<FAST>(pwr3, ct);
+                float htb = hft_b - ct * qr_b;
+                const float pwr3_b = fdiv<FAST>(htb, ct);
+                const float x3_b = -0.25f * (pwr3 * frcp<FAST>(x3)) * pwr3_b;               // pwy3*x3**(pwy3-1)
+                const float x1_b = -4.0f * (pow_m4<FAST>(x1) * frcp<FAST>(x1)) * x3_b;      // pwy1*x1**(pwy1-1)
+                const float ht_imd_b = ct * qr_b + ct * x1_b;
+                const float ct2 = ct * ct;
+                cft_b += (ht_imd - ht_new) * qr_b + (-4.0f * (k.cft_m4 * frcp<FAST>(ct))) * x3_b -
+                         fdiv<FAST>(pwr3 * htb, ct2) + ht_imd * x1_b;
+                float pr_imd_b;
+                if (first) {
+                    htb = ht_imd_b;
+                    pr_imd_b = fdiv<FAST>(ht_imd_b, ct);
+                    cft_b -= fdiv<FAST>(pr_imd * ht_imd_b, ct2);
+                } else { htb = 0.0f; pr_imd_b = 0.0f; }
+                if (!gap) prr_b = pr_imd_b;
+                else {
+                    const float gw3_b = (g_pwx3 <= 0.0f) ? 0.0f : -0.25f * pow_m125<0>(g_pwx3) * pr_imd_b;
+                    const float gw1_b = (g_pwx1 <= 0.0f) ? 0.0f : -4.0f * (pow_m4<0>(g_pwx1) / g_pwx1) * gw3_b;
+                    htb = htb + ct * gw1_b - ct * pr_imd_b;
+                    cft_b += (-4.0f * (k.cft_m4 / ct)) * (-gw3_b) - ht * pr_imd_b + ht * gw1_b;
+                    prr_b = 0.0f;
+                }
+                hft_b = htb;
+            }
+            const float pr_b = 0.1f * prd_b + 0.9f * prr_b;                       // :8143
+            float perc_b = pr_b;
+            l_b += prr_b;
+            if (nogap) {
+                // GR_EXCHANGE_B :6147-6157 (pre-transfer hft)
+                if (k.exc != 0.0f || l_b != 0.0f) {
+                    exc_b += pow_3p5(hft0) * l_b;
+                    hft_b += 3.5f * pow_2p5(hft0) * k.exc * l_b;
+                }
+                // GR_PRODUCTION_B :6012-6103
+                const float cp = k.cp, inv_cp = k.inv_cp, hp = hp0;
+                perc_b = perc_b - inv_cp * hp_b;
+                float inv_cp_b = -(perc * hp_b);
+                cp_b += hp_imd * (1.0f - pwr1) * perc_b;
+                const float pwr1_b = -(hp_imd * cp * perc_b);
+                const float pwx1_b = (pwx1 == 1.0f) ? -(0.25f * pwr1_b) : -(0.25f * pow_m125<FAST>(pwx1) * pwr1_b);
+                float hp_imd_b = hp_b + cp * (1.0f - pwr1) * perc_b + 4.0f * (hp_imd * hp_imd * hp_imd) * pwx1_b * 1.0e-12f;
+                float hpb;
+                if (pn > 0.0f) {
+                    hp_imd_b -= cp * pr_b;
+                    hpb = cp * pr_b;
+                    cp_b -= (hp_imd - hp) * pr_b;
+                } else hpb = 0.0f;
+                const float es_b = -(inv_cp * hp_imd_b);
+                const float temp3 = (1.0f - hp) * te_ + 1.0f;
+                const float temp0e = hp * cp * (2.0f - hp);
+                const float temp_b3 = fdiv<FAST>(es_b, temp3);
+                const float temp_be = (2.0f - hp) * te_ * temp_b3;
+                const float temp_b0e = -fdiv<FAST>(temp0e * te_ * temp_b3, temp3);
+                hpb = hpb + hp_imd_b + cp * temp_be - hp * cp * te_ * temp_b3 - te_ * temp_b0e;
+                const float ps_b = inv_cp * hp_imd_b;
+                const float sech_e = 1.0f - te_ * te_;
+                const float temp_b4 = sech_e * temp0e * temp_b3;
+                const float temp_b5 = sech_e * (1.0f - hp) * temp_b0e;
+                cp_b += hp * temp_be;
+                const float temp0p = hp * tp_ + 1.0f;
+                const float temp2 = cp * (1.0f - hp * hp);
+                const float temp_bp = fdiv<FAST>(ps_b, temp0p);
+                const float sech_p = 1.0f - tp_ * tp_;
+                const float temp_b0p = sech_p * temp2 * temp_bp;
+                const float temp_b1 = -fdiv<FAST>(temp2 * tp_ * temp_bp, temp0p);
+                hpb = hpb + tp_ * temp_b1 - 2.0f * hp * cp * tp_ * temp_bp;
+                const float temp_b2 = sech_p * hp * temp_b1;
+                inv_cp_b = inv_cp_b + (ps - es) * hp_imd_b + en * temp_b5 + en * temp_b4 + pn * temp_b2 + pn * temp_b0p;
+                cp_b += (1.0f - hp * hp) * tp_ * temp_bp - fdiv<FAST>(inv_cp_b, cp * cp);
+                hp_b = hpb;
+            }
+            wx[cur * B + tid] = w_out;
+        }
+        if (act && (bf & BLK_RPUBLISH)) wdom[(size_t)d * B] = w_out;
+        __syncthreads();
+        if (tid == 0) {
+            if (bf & BLK_RPUBLISH) { __threadfence(); st_release(a.rprog + (size_t)member * tp.nblocks + blk, d); }
+            const int jn = j + RING_STAGES;
+            if (jn < nticks) {
+                const int dn = nticks - 1 - jn;
+                mbar_expect_tx(&bars[stage], frc_bytes + tape_bytes);
+                tma_load_1d(ring + (size_t)stage * 6 * B, frc + (size_t)dn * 2 * B, frc_bytes, &bars[stage]);
+                tma_load_1d(ring + (size_t)stage * 6 * B + 2 * B, tpe + (size_t)dn * 4 * B, tape_bytes, &bars[stage]);
+            }
+        }
+    }
+    if (valid) {
+        float *g = a.grad + (size_t)member * NFIELD * tp.nslots + slot;
+        g[(size_t)F_CP * tp.nslots] = cp_b; g[(size_t)F_CFT * tp.nslots] = cft_b; g[(size_t)F_EXC * tp.nslots] = exc_b;
+        g[(size_t)F_LR * tp.nslots] = lr_b; g[(size_t)F_HP * tp.nslots] = hp_b; g[(size_t)F_HFT * tp.nslots] = hft_b;
+        g[(size_t)F_HLR * tp.nslots] = hlr_b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// cost kernel: compute_jobs (mwd_cost.f90:37-156) + COMPUTE_JOBS_B (forward_db.f90:2553-2715).
+// One CTA per member, one thread per gauge, sequential sums in the reference's order; no FMA contraction
+// (explicit _rn intrinsics) so that the sums round like the scalar Fortran.
+// ------------------------------------------------------------------------------------------------
+#define FM(a, b) __fmul_rn((a), (b))
+#define FA(a, b) __fadd_rn((a), (b))
+#define FS(a, b) __fsub_rn((a), (b))
+#define FD(a, b) __fdiv_rn((a), (b))
+
+struct Series {
+    const float *qsim, *qobs;
+    int ng, g, start, n;
+    float fs, fo;   // qs = qsim*dt/area*1e3 ; qo = qobs*dt/(flwacc*dx*dx)*1e3
+    float dt, area, dden;
+    __device__ float qs(int i) const { return FM(FD(FM(qsim[(size_t)(start + i) * ng + g], dt), area), 1e3f); }
+    __device__ float qo(int i) const { return FM(FD(FM(qobs[(size_t)(start + i) * ng + g], dt), dden), 1e3f); }
+};
+
+struct Moments { int n; float sum_x, sum_y, sum_xx, sum_yy, sum_xy, se, lg; };
+
+__device__ Moments moments(const Series &s) {
+    Moments m = {0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = 0; i < s.n; i++) {
+        const float x = s.qo(i), y = s.qs(i);
+        if (x >= 0.0f) {
+            m.n++;
+            m.sum_x = FA(m.sum_x, x);
+            m.sum_y = FA(m.sum_y, y);
+            m.sum_xx = FA(m.sum_xx, FM(x, x));
+            m.sum_yy = FA(m.sum_yy, FM(y, y));
+            m.sum_xy = FA(m.sum_xy, FM(x, y));
+            const float df = FS(x, y);
+            m.se = FA(m.se, FM(df, df));
+        }
+        if (x > 0.0f && y > 0.0f) { const float lq = logf(FD(y, x)); m.lg = FA(m.lg, FM(FM(x, lq), lq)); }
+    }
+    return m;
+}
+
+__device__ float nse_of(const Moments &m) {          // mwd_cost.f90:350-401
+    const float mean_x = FD(m.sum_x, (float)m.n);
+    const float num = FA(FS(m.sum_xx, FM(2.0f, m.sum_xy)), m.sum_yy);
+    const float den = FS(m.sum_xx, FM(FM((float)m.n, mean_x), mean_x));
+    return FD(num, den);
+}
+struct Kge { float r, a, b, mean_x, mean_y, var_x, var_y, cov, val; };
+__device__ Kge kge_of(const Moments &m) {            // mwd_cost.f90:403-490
+    Kge k;
+    const float n = (float)m.n;
+    k.mean_x = FD(m.sum_x, n); k.mean_y = FD(m.sum_y, n);
+    k.var_x = FS(FD(m.sum_xx, n), FM(k.mean_x, k.mean_x));
+    k.var_y = FS(FD(m.sum_yy, n), FM(k.mean_y, k.mean_y));
+    k.cov = FS(FD(m.sum_xy, n), FM(k.mean_x, k.mean_y));
+    k.r = FD(FD(k.cov, sqrtf(k.var_x)), sqrtf(k.var_y));
+    k.a = FD(sqrtf(k.var_y), sqrtf(k.var_x));
+    k.b = FD(k.mean_y, k.mean_x);
+    const float r1 = FS(k.r, 1.0f), b1 = FS(k.b, 1.0f), a1 = FS(k.a, 1.0f);
+    k.val = sqrtf(FA(FA(FM(r1, r1), FM(b1, b1)), FM(a1, a1)));
+    return k;
+}
+
+__global__ void cost_kernel(const CostArgs c) {
+    extern __shared__ float sh[];            // [ng] gauge_jobs, [ng] gauge_jobs_b
+    float *gj = sh, *gjb = sh + c.ng;
+    const int m = blockIdx.x;
+    const int n = c.T - c.start;
+    // per gauge adjoint coefficients: y_b(i) = cx*x + cy*y + c0 (+ special terms)
+    for (int g = threadIdx.x; g < c.ng; g += blockDim.x) {
+        float gauge_jobs = 0.0f;
+        const float wg = c.wgauge[g];
+        if (wg > 0.0f || wg < 0.0f) {
+            Series s = {c.qsim + (size_t)m * c.T * c.ng, c.qobs, c.ng, g, c.start, n, 0.f, 0.f, c.dt, c.area[g],
+                        FM(FM((float)c.gauge_flwacc[g], c.dx), c.dx)};
+            const Moments mo = moments(s);
+            float j_imd = 0.0f;
+            for (int j = 0; j < c.njf; j++) {
+                if (mo.n > 0) {
+                    switch (c.jobs_fun[j]) {
+                        case 1: j_imd = nse_of(mo); break;
+                        case 2: j_imd = kge_of(mo).val; break;
+                        case 3: { const float v = kge_of(mo).val; j_imd = FM(v, v); } break;
+                        case 4: j_imd = mo.se; break;
+                        case 5: j_imd = sqrtf(FD(mo.se, (float)mo.n)); break;
+                        case 6: j_imd = mo.lg; break;
+                        default: break;
+                    }
+                }
+                gauge_jobs = FA(gauge_jobs, FM(c.wjobs_fun[j], j_imd));
+            }
+        }
+        gj[g] = gauge_jobs;
+        gjb[g] = 0.0f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // gauge aggregation mwd_cost.f90:139-154 (+ QUANTILE_B for negative weights)
+        float jobs = 0.0f;
+        int nmed = 0;
+        for (int g = 0; g < c.ng; g++) {
+            const float wg = c.wgauge[g];
+            if (wg > 0.0f) { jobs = FA(jobs, FM(wg, gj[g])); gjb[g] = FM(wg, c.jobs_b); }
+            else if (wg < 0.0f) nmed++;
+        }
+        if (nmed > 0) {
+            // median by selection (n is tiny): rank of each value with index tie-break
+            const float frac = FA(FM((float)(nmed - 1), 0.5f), 1.0f);
+            int i1 = (int)frac - 1, i2 = i1 + 1;
+            float w2 = FS(frac, (float)(int)frac);
+            if (nmed == 1 || frac <= 1.0f) { i1 = i2 = 0; w2 = 0.0f; }
+            else if (frac >= (float)nmed) { i1 = i2 = nmed - 1; w2 = 0.0f; }
+            int g1 = -1, g2 = -1;
+            for (int g = 0; g < c.ng; g++) {
+                if (!(c.wgauge[g] < 0.0f)) continue;
+                int rk = 0;
+                for (int h = 0; h < c.ng; h++)
+                    if (c.wgauge[h] < 0.0f && (gj[h] < gj[g] || (gj[h] == gj[g] && h < g))) rk++;
+                if (rk == i1) g1 = g;
+                if (rk == i2) g2 = g;
+            }
+            jobs = FA(gj[g1], FM(FS(gj[g2], gj[g1]), w2));
+            for (int g = 0; g < c.ng; g++) if (c.wgauge[g] < 0.0f) gjb[g] = 0.0f;
+            gjb[g1] = FA(gjb[g1], FM(FS(1.0f, w2), c.jobs_b));
+            gjb[g2] = FA(gjb[g2], FM(w2, c.jobs_b));
+        }
+        c.cost_jobs[m] = jobs;
+    }
+    if (c.qsim_b == nullptr) return;
+    __syncthreads();
+    for (int g = threadIdx.x; g < c.ng; g += blockDim.x) {
+        float *qb = c.qsim_b + (size_t)m * c.T * c.ng;
+        for (int t = 0; t < c.T; t++) qb[(size_t)t * c.ng + g] = 0.0f;
+        const float wg = c.wgauge[g];
+        if (!(wg > 0.0f || wg < 0.0f)) continue;
+        Series s = {c.qsim + (size_t)m * c.T * c.ng, c.qobs, c.ng, g, c.start, n, 0.f, 0.f, c.dt, c.area[g],
+                    FM(FM((float)c.gauge_flwacc[g], c.dx), c.dx)};
+        const Moments mo = moments(s);
+        if (mo.n == 0) continue;
+        const float gauge_jobs_b = gjb[g];
+        // accumulate y_b(i) = cx*x(i) + cy*y(i) + c0 + (se / log terms)
+        float cx = 0.f, cy = 0.f, c0 = 0.f, cse = 0.f, clg = 0.f;
+        for (int j = c.njf - 1; j >= 0; j--) {
+            const float jb = FM(c.wjobs_fun[j], gauge_jobs_b);
+            switch (c.jobs_fun[j]) {
+                case 1: {   // NSE_B forward_db.f90:3505-3545
+                    const float mean_x = FD(mo.sum_x, (float)mo.n);
+                    const float den = FS(mo.sum_xx, FM(FM((float)mo.n, mean_x), mean_x));
+                    const float num_b = FD(jb, den);
+                    cx = FA(cx, -FM(2.0f, num_b)); cy = FA(cy, FM(2.0f, num_b));
+                } break;
+                case 2: case 3: {   // KGE_B :3805-3829 + KGE_COMPONENTS_B :3657-3729
+                    const Kge k = kge_of(mo);
+                    const float res_b = (c.jobs_fun[j] == 3) ? FM(FM(2.0f, k.val), jb) : jb;
+                    const float r1 = FS(k.r, 1.0f), b1 = FS(k.b, 1.0f), a1 = FS(k.a, 1.0f);
+                    const float arg1 = FA(FA(FM(r1, r1), FM(b1, b1)), FM(a1, a1));
+                    const float arg1_b = (arg1 == 0.0f) ? 0.0f : FD(res_b, FM(2.0f, sqrtf(arg1)));
+                    const float r_b = FM(FM(2.0f, r1), arg1_b), b_b = FM(FM(2.0f, b1), arg1_b), a_b = FM(FM(2.0f, a1), arg1_b);
+                    const float sx = sqrtf(k.var_x), sy = sqrtf(k.var_y);
+                    const float result1_b = FD(a_b, sx);
+                    float var_y_b = (k.var_y == 0.0f) ? 0.0f : FD(result1_b, FM(2.0f, sy));
+                    const float temp_b = FD(r_b, FM(sx, sy));
+                    const float cov_b = temp_b;
+                    const float result2_b = -FD(FM(k.cov, temp_b), sy);
+                    if (!(k.var_y == 0.0f)) var_y_b = FA(var_y_b, FD(result2_b, FM(2.0f, sy)));
+                    const float mean_y_b = FS(FS(FD(b_b, k.mean_x), FM(k.mean_x, cov_b)), FM(FM(2.0f, k.mean_y), var_y_b));
+                    const float nn = (float)mo.n;
+                    cx = FA(cx, FD(cov_b, nn)); cy = FA(cy, FM(2.0f, FD(var_y_b, nn))); c0 = FA(c0, FD(mean_y_b, nn));
+                } break;
+                case 4: cse = FA(cse, jb); break;
+                case 5: {
+                    const float sm = FD(mo.se, (float)mo.n);
+                    const float sb = (sm == 0.0f) ? 0.0f : FD(jb, FM(2.0f, sqrtf(sm)));
+                    cse = FA(cse, FD(sb, (float)mo.n));
+                } break;
+                case 6: clg = FA(clg, jb); break;
+                default: break;
+            }
+        }
+        const float scale = FD(FM(c.dt, 1e3f), c.area[g]);       // :2709-2712
+        for (int i = 0; i < n; i++) {
+            const float x = s.qo(i), y = s.qs(i);
+            float yb = 0.0f;
+            if (x >= 0.0f) yb = FA(FA(FM(x, cx), FM(y, cy)), c0) - FM(FM(2.0f, FS(x, y)), cse);
+            if (clg != 0.0f && x > 0.0f && y > 0.0f) yb = FA(yb, FD(FM(FM(FM(2.0f, x), logf(FD(y, x))), clg), y));
+            qb[(size_t)(c.start + i) * c.ng + g] = FM(scale, yb);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void relayout_forcing_kernel(DeviceTopology tp, const int32_t *src, const float *prcp_raw, const float *pet_raw,
+                                        int64_t stride, float *forcing) {
+    const int blk = blockIdx.x;
+    const int B = tp.B;
+    const int nticks = tp.T + tp.hmax[blk];
+    const int64_t row0 = tp.tick_base[blk];
+    for (int lane = threadIdx.x; lane < B; lane += blockDim.x) {
+        const int slot = blk * B + lane;
+        const int sidx = src[slot];
+        const int off = tp.off[slot];
+        for (int d = blockIdx.y; d < nticks; d += gridDim.y) {
+            const int t = d - off;
+            float p = 0.0f, e = 0.0f;
+            if (sidx >= 0 && t >= 0 && t < tp.T) { p = prcp_raw[(int64_t)t * stride + sidx]; e = pet_raw[(int64_t)t * stride + sidx]; }
+            forcing[(row0 + d) * 2 * B + lane] = p;
+            forcing[(row0 + d) * 2 * B + B + lane] = e;
+        }
+    }
+}
+
+__global__ void gather_fields_kernel(DeviceTopology tp, int nmember, const float *planes, int64_t ncell, const float *sample,
+                                     const int32_t *sample_field, int nvar, float *fields) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = (int64_t)nmember * NFIELD * tp.nslots;
+    if (i >= total) return;
+    const int slot = (int)(i % tp.nslots);
+    const int f = (int)((i / tp.nslots) % NFIELD);
+    const int m = (int)(i / ((int64_t)tp.nslots * NFIELD));
+    const int c = tp.cell[slot];
+    float v = (c >= 0) ? planes[(int64_t)f * ncell + c] : 1.0f;
+    for (int j = 0; j < nvar; j++) if (sample_field[j] == f) v = sample[(int64_t)m * nvar + j];
+    fields[i] = v;
+}
+
+__global__ void unskew_kernel(DeviceTopology tp, const int32_t *dst, const float *skewed, int64_t out_stride, float *out) {
+    const int blk = blockIdx.x;
+    const int B = tp.B;
+    const int64_t row0 = tp.tick_base[blk];
+    for (int lane = threadIdx.x; lane < B; lane += blockDim.x) {
+        const int slot = blk * B + lane;
+        const int di = dst[slot];
+        if (di < 0) continue;
+        const int off = tp.off[slot];
+        for (int t = blockIdx.y; t < tp.T; t += gridDim.y) out[(int64_t)t * out_stride + di] = skewed[(row0 + t + off) * B + lane];
+    }
+}
+
+__global__ void checksum_kernel(DeviceTopology tp, const float *skewed, double *out) {
+    const int blk = blockIdx.x;
+    const int B = tp.B;
+    const int64_t row0 = tp.tick_base[blk];
+    double acc = 0.0;
+    for (int lane = threadIdx.x; lane < B; lane += blockDim.x) {
+        const int slot = blk * B + lane;
+        if (tp.cell[slot] < 0) continue;
+        const int off = tp.off[slot];
+        for (int t = blockIdx.y; t < tp.T; t += gridDim.y) acc += (double)skewed[(row0 + t + off) * B + lane];
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers
+// ------------------------------------------------------------------------------------------------
+static size_t fwd_smem(int B) { return (size_t)(RING_STAGES * 2 + 2) * B * sizeof(float) + RING_STAGES * sizeof(uint64_t); }
+static size_t rev_smem(int B) { return (size_t)(RING_STAGES * 6 + 2) * B * sizeof(float) + RING_STAGES * sizeof(uint64_t); }
+
+template <typename K> static cudaError_t launch_solver(K kern, const SolverArgs &a, size_t smem, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), s);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)((size_t)a.tp.nblocks * a.nmember));
+    kern<<<grid, a.tp.B, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_forward(const SolverArgs &a, int math_mode, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(a.prog, 0, sizeof(int) * (size_t)a.tp.nblocks * a.nmember, s);
+    if (e != cudaSuccess) return e;
+    const size_t smem = fwd_smem(a.tp.B);
+    if (a.tape_on) return math_mode ? launch_solver(forward_kernel<1, 1>, a, smem, s) : launch_solver(forward_kernel<0, 1>, a, smem, s);
+    return math_mode ? launch_solver(forward_kernel<1, 0>, a, smem, s) : launch_solver(forward_kernel<0, 0>, a, smem, s);
+}
+
+cudaError_t launch_reverse(const SolverArgs &a, int math_mode, cudaStream_t s) {
+    // rprog starts above every tick index
+    cudaError_t e = cudaMemsetAsync(a.rprog, 0x7f, sizeof(int) * (size_t)a.tp.nblocks * a.nmember, s);
+    if (e != cudaSuccess) return e;
+    const size_t smem = rev_smem(a.tp.B);
+    return math_mode ? launch_solver(reverse_kernel<1>, a, smem, s) : launch_solver(reverse_kernel<0>, a, smem, s);
+}
+
+cudaError_t launch_cost(const CostArgs &c, cudaStream_t s) {
+    if (c.ng <= 0 || c.nmember <= 0) return cudaSuccess;
+    int threads = c.ng < 32 ? 32 : (c.ng > 256 ? 256 : ((c.ng + 31) / 32) * 32);
+    cost_kernel<<<c.nmember, threads, 2 * c.ng * sizeof(float), s>>>(c);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_relayout_forcing(const DeviceTopology &tp, const int32_t *src_index, const float *prcp_raw,
+                                    const float *pet_raw, int64_t raw_stride, float *forcing, cudaStream_t s) {
+    dim3 grid(tp.nblocks, tp.nblocks > 512 ? 8 : 64);
+    relayout_forcing_kernel<<<grid, tp.B > 256 ? 256 : tp.B, 0, s>>>(tp, src_index, prcp_raw, pet_raw, raw_stride, forcing);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_fields(const DeviceTopology &tp, int nmember, const float *planes, int64_t ncell, const float *sample,
+                                 const int32_t *sample_field, int nvar, float *fields, cudaStream_t s) {
+    const int64_t total = (int64_t)nmember * NFIELD * tp.nslots;
+    gather_fields_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(tp, nmember, planes, ncell, sample, sample_field, nvar, fields);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unskew(const DeviceTopology &tp, const int32_t *dst_index, const float *skewed, int64_t out_stride,
+                          float fill, float *out, cudaStream_t s) {
+    (void)fill;
+    dim3 grid(tp.nblocks, tp.nblocks > 512 ? 8 : 64);
+    unskew_kernel<<<grid, tp.B > 256 ? 256 : tp.B, 0, s>>>(tp, dst_index, skewed, out_stride, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_checksum(const DeviceTopology &tp, const float *skewed, double *out, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    dim3 grid(tp.nblocks, tp.nblocks > 512 ? 8 : 64);
+    checksum_kernel<<<grid, 256, 0, s>>>(tp, skewed, out);
+    return cudaGetLastError();
+}
+
+}  // namespace smash

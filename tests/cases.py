@@ -1,0 +1,180 @@
+"""Shared builders for the parity tests: the Cance model rebuilt from tests/golden/*.npz (what
+``smash.Model(*load_dataset("Cance"))`` holds in the reference, smash/tests/test_define_global_vars.py:9-14),
+synthetic forcing and the France mesh."""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+from smash_b200.solver._derived_types import (Hyper_ParametersDT, Hyper_StatesDT, Input_DataDT, MeshDT, Optimize_SetupDT,
+                                              OutputDT, ParametersDT, SetupDT, StatesDT, compute_rowcol_to_ind_sparse)
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# smash/core/_constant.py:49-77
+RATIO_PET_HOURLY = np.array([0, 0, 0, 0, 0, 0, 0, 0.035, 0.062, 0.079, 0.097, 0.11, 0.117, 0.117, 0.11, 0.097, 0.079, 0.062,
+                             0.035, 0, 0, 0, 0, 0], dtype=np.float32)
+
+
+class Model:
+    """The six derived types a reference ``smash.Model`` carries."""
+
+    def __init__(self, setup, mesh, input_data, parameters, states, output):
+        self.setup, self.mesh, self.input_data = setup, mesh, input_data
+        self.parameters, self.states, self.output = parameters, states, output
+
+    def copy(self):
+        return Model(self.setup.copy(), self.mesh, self.input_data, self.parameters.copy(), self.states.copy(),
+                     self.output.copy())
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def set_optimize(setup, mesh, jobs_fun=("nse",), wjobs_fun=None, gauge="downstream", wgauge=None, mapping="...",
+                 jreg_fun=(), wjreg_fun=None, wjreg=0.0, ost=1, denormalize_forward=False):
+    """What _standardize_*_args + reset_optimize_setup (mw_derived_type_update.f90:13-59) leave in setup._optimize."""
+    njf, njr = len(jobs_fun), len(jreg_fun)
+    o = Optimize_SetupDT(setup._ntime_step, setup._nd, mesh.ng, mapping, njf, njr)
+    o.jobs_fun = np.array(list(jobs_fun), dtype="U20")
+    o.wjobs_fun = np.full(njf, 1.0 / njf if njf else 0.0, dtype=np.float32) if wjobs_fun is None else np.asarray(wjobs_fun, np.float32)
+    o.jreg_fun = np.array(list(jreg_fun), dtype="U20")
+    o.wjreg_fun = np.ones(njr, np.float32) if wjreg_fun is None else np.asarray(wjreg_fun, np.float32)
+    o.wjreg = np.float32(wjreg)
+    o.optimize_start_step = int(ost)
+    o.denormalize_forward = bool(denormalize_forward)
+    if mesh.ng > 0:
+        if wgauge is not None:
+            o.wgauge = np.asarray(wgauge, dtype=np.float32)
+        elif gauge == "downstream":  # _standardize.py:308-311,362-363: argmax(area), weight 1
+            w = np.zeros(mesh.ng, np.float32)
+            w[int(np.argmax(mesh.area))] = 1.0
+            o.wgauge = w
+        elif gauge == "all":
+            o.wgauge = np.full(mesh.ng, 1.0 / mesh.ng, np.float32)
+    setup._optimize = o
+    return o
+
+
+def cance(sparse=False, T=None, jobs_fun=("nse",)):
+    d = golden("cance_inputs.npz")
+    nrow, ncol, ng = int(d["nrow"]), int(d["ncol"]), int(d["ng"])
+    Tfull = d["prcp"].shape[0]
+    T = Tfull if T is None else int(T)
+    setup = SetupDT(nd=2, ng=ng)
+    setup.structure = "gr-a"
+    setup.dt = np.float32(d["dt"])
+    setup.sparse_storage = bool(sparse)
+    setup._ntime_step = T
+    setup.descriptor_name = np.array(["slope", "dd"], dtype="U20")
+    mesh = MeshDT(setup, nrow, ncol, ng)
+    mesh.dx = np.float32(d["dx"])
+    mesh.nac = int(d["nac"])
+    mesh.flwdir = np.asfortranarray(d["flwdir"], dtype=np.int32)
+    mesh.flwacc = np.asfortranarray(d["flwacc"], dtype=np.int32)
+    mesh.active_cell = np.asfortranarray(d["active_cell"], dtype=np.int32)
+    mesh.path = np.asfortranarray(d["path"], dtype=np.int32)          # 0-based as stored by save_mesh
+    mesh.gauge_pos = np.asfortranarray(d["gauge_pos"], dtype=np.int32)
+    mesh.area = d["area"].astype(np.float32)
+    mesh.flwdst = np.asfortranarray(d["flwdst"], dtype=np.float32)
+    mesh.code = d["code"].astype("U20")
+    mesh._local_active_cell = np.asfortranarray(mesh.active_cell.copy())
+    compute_rowcol_to_ind_sparse(mesh)
+    inp = Input_DataDT(setup, mesh)
+    prcp = d["prcp"][:T]                                                # (T,nrow,ncol)
+    pet = (d["pet_daily"][d["pet_day"][:T]] * d["pet_ratio"][:T, None, None].astype(np.float64)).astype(np.float32)
+    if sparse:
+        k = mesh._rowcol_to_ind_sparse
+        rr, cc = np.nonzero(k > 0)
+        order = np.argsort(k[rr, cc])
+        rr, cc = rr[order], cc[order]
+        inp.sparse_prcp = np.asfortranarray(prcp[:, rr, cc].T)
+        inp.sparse_pet = np.asfortranarray(pet[:, rr, cc].T)
+    else:
+        inp.prcp = np.asfortranarray(np.moveaxis(prcp, 0, 2))
+        inp.pet = np.asfortranarray(np.moveaxis(pet, 0, 2))
+    inp.qobs = np.asfortranarray(d["qobs"][:, :T], dtype=np.float32)
+    inp.descriptor = np.asfortranarray(d["descriptor"], dtype=np.float32)
+    par = ParametersDT(mesh)
+    par.lr[...] = np.float32(setup.dt) * np.float32(5.0 / 3600.0)       # _build_model.py:257
+    st = StatesDT(mesh)
+    out = OutputDT(setup, mesh)
+    set_optimize(setup, mesh, jobs_fun=jobs_fun)
+    return Model(setup, mesh, inp, par, st, out)
+
+
+# ind_parameters_states of cp, cft, exc, lr in the 16+8 stacked planes (1-based, multiple_run.py:184-200)
+IND_CP_CFT_EXC_LR = np.array([2, 4, 7, 16], dtype=np.int32)
+
+
+def output_cost(model, nse, kge):
+    """smash/tests/core/test_simu.py:319-334"""
+    qo, qs = model.input_data.qobs, model.output.qsim
+    ret = np.zeros(3 * model.mesh.ng, dtype=np.float32)
+    for i in range(model.mesh.ng):
+        ret[3 * i:3 * i + 3] = (model.output.cost, nse(qo[i], qs[i]), kge(qo[i], qs[i]))
+    return ret
+
+
+def normalize_descriptor(model):
+    """optimize_hyper_lbfgsb normalises descriptors to [0,1] over the domain before mapping (mw_optimize.f90:960-980)."""
+    d = model.input_data.descriptor
+    out = np.empty_like(d)
+    for j in range(d.shape[2]):
+        lo, hi = d[..., j].min(), d[..., j].max()
+        out[..., j] = (d[..., j] - lo) / (hi - lo)
+    model.input_data.descriptor = np.asfortranarray(out)
+
+
+def synthetic_forcing(nac, T, seed=0, gap_fraction=0.0):
+    """prcp = Bernoulli(0.15)*Gamma(0.6, 4.0) mm/h, pet = U(1,4) mm/d * RATIO_PET_HOURLY[hour]."""
+    rng = np.random.default_rng(seed)
+    prcp = (rng.random((nac, T), dtype=np.float32) < 0.15) * rng.gamma(0.6, 4.0, (nac, T)).astype(np.float32)
+    pet_day = rng.uniform(1.0, 4.0, nac).astype(np.float32)
+    pet = pet_day[:, None] * RATIO_PET_HOURLY[np.arange(T) % 24][None, :]
+    if gap_fraction > 0:
+        gaps = rng.random((nac, T)) < gap_fraction
+        prcp = np.where(gaps, np.float32(-99.0), prcp)
+    return np.asfortranarray(prcp, dtype=np.float32), np.asfortranarray(pet, dtype=np.float32)
+
+
+def france(T=24, seed=0, sub=None):
+    """France 1 km mesh (mesh_France.hdf5) with synthetic sparse forcing; `sub=(r0,r1,c0,c1)` crops a window
+    (flow directions leaving the window simply drain nowhere, as at the domain edge)."""
+    d = golden("france_mesh.npz")
+    flwdir, flwacc, active = d["flwdir"].astype(np.int32), d["flwacc"], d["active_cell"].astype(np.int32)
+    path = d["path"].astype(np.int32)
+    if sub is not None:
+        r0, r1, c0, c1 = sub
+        flwdir, flwacc, active = flwdir[r0:r1, c0:c1], flwacc[r0:r1, c0:c1], active[r0:r1, c0:c1]
+        keep = (path[0] >= r0) & (path[0] < r1) & (path[1] >= c0) & (path[1] < c1)
+        path = path[:, keep] - np.array([[r0], [c0]], dtype=np.int32)
+    nrow, ncol = flwdir.shape
+    setup = SetupDT(nd=0, ng=0)
+    setup.sparse_storage = True
+    setup._ntime_step = int(T)
+    setup.save_qsim_domain = True                                       # setup_France.yaml:18
+    mesh = MeshDT(setup, nrow, ncol, 0)
+    mesh.dx = np.float32(d["dx"])
+    mesh.flwdir = np.asfortranarray(flwdir)
+    mesh.flwacc = np.asfortranarray(flwacc)
+    mesh.active_cell = np.asfortranarray(active)
+    mesh._local_active_cell = np.asfortranarray(active.copy())
+    full = np.full((2, nrow * ncol), -100, dtype=np.int32)
+    full[:, :path.shape[1]] = path
+    mesh.path = np.asfortranarray(full)
+    mesh.nac = int(active.sum())
+    compute_rowcol_to_ind_sparse(mesh)
+    inp = Input_DataDT(setup, mesh)
+    inp.sparse_prcp, inp.sparse_pet = synthetic_forcing(mesh.nac, T, seed)
+    par = ParametersDT(mesh)
+    st = StatesDT(mesh)
+    out = OutputDT(setup, mesh)
+    set_optimize(setup, mesh, jobs_fun=())
+    return Model(setup, mesh, inp, par, st, out)
+
+
+def hyper_objects(model):
+    return Hyper_ParametersDT(model.setup), Hyper_StatesDT(model.setup)
