@@ -181,12 +181,17 @@ int smash_b200_plan_get_gradient(SmashPlan *plan, SmashParameters *parameters_b,
 /* sum of the device-resident q of the last run over all active cell-steps (size-independent checksum) */
 int smash_b200_plan_checksum(SmashPlan *plan, double *sum_q);
 /* topology facts: [0]=ncell_active [1]=nblocks [2]=block_size [3]=max in-block skew [4]=total ticks over blocks
- * [5]=cross-block edges [6]=pit pairs [7]=kernel launches of the last run_* call */
-int smash_b200_plan_info(const SmashPlan *plan, int64_t info[8]);
+ * [5]=cross-block edges [6]=pit pairs [7]=kernel launches of the last run_* call [8]=critical path over blocks in
+ * ticks [9]=longest chain of dependent blocks [10..11]=reserved */
+int smash_b200_plan_info(const SmashPlan *plan, int64_t info[12]);
 
 /* level ordering exposed for the bit-exact mesh tests: order[k] = 0-based flat (row + col*nrow) index of the
  * k-th cell in device order, block_of/offset_of its block and in-block skew (n = number of active cells) */
 int smash_b200_plan_order(const SmashPlan *plan, int32_t *order, int32_t *block_of, int32_t *offset_of);
+/* same ordering computed on the host only (no CUDA device needed): info as smash_b200_plan_info, block = cells per
+ * CTA (0 = automatic) */
+int smash_b200_mesh_order(const SmashSetup *setup, const SmashMesh *mesh, int32_t block, int64_t info[12],
+                          int32_t *order, int32_t *block_of, int32_t *offset_of);
 
 #ifdef __cplusplus
 }

@@ -312,3 +312,14 @@ def kge(x, y, precision="f32"):
     f = ctx.fn("oracle_kge")
     f.restype = ctx.creal
     return f(ctx.r(x), ctx.r(y), len(x))
+
+
+def compute_jobs(setup, mesh, input_data, qsim, precision="f32", adjoint=False):
+    """compute_jobs (optimize/mwd_cost.f90:37-156) on a given hydrograph array (ng, T)."""
+    ctx = _Ctx(precision)
+    P = _problem(ctx, setup, mesh, input_data)
+    f = ctx.fn("oracle_compute_jobs")
+    f.restype = ctx.creal
+    qb = np.zeros((mesh.ng, setup._ntime_step), dtype=ctx.dtype, order="F") if adjoint else None
+    j = f(C.byref(P), ctx.r(qsim), _ptr(ctx, qb))
+    return (ctx.dtype(j), qb) if adjoint else ctx.dtype(j)

@@ -573,6 +573,11 @@ static void logarithmic_b(const oreal *x, const oreal *y, oreal *y_b, int size, 
         if (x[i] > R(0.0) && y[i] > R(0.0)) y_b[i] = y_b[i] + 2 * x[i] * LOG(y[i] / x[i]) * res_b / y[i];
 }
 
+static oreal compute_jobs(const Prob *P, const oreal *qsim, oreal *qsim_b, oreal jobs_b);
+/* compute_jobs on a given qsim(ng,T) (lets tests check the cost kernel independently of the simulation) */
+oreal OSYM(oracle_compute_jobs)(const Prob *P, const oreal *qsim, oreal *qsim_b) {
+    return compute_jobs(P, qsim, qsim_b, R(1.0));
+}
 oreal OSYM(oracle_nse)(const oreal *x, const oreal *y, int n) { return nse(x, y, n); }
 oreal OSYM(oracle_kge)(const oreal *x, const oreal *y, int n) { return kge(x, y, n); }
 

@@ -117,6 +117,8 @@ int OSYM(oracle_multiple_run)(const OSYM(OProblem) *P, const oreal *parameters, 
 void OSYM(oracle_gr_production)(oreal pn, oreal en, oreal cp, oreal beta, oreal *hp, oreal *pr, oreal *perc);
 void OSYM(oracle_gr_transfer)(oreal n, oreal prcp, oreal pr, oreal ct, oreal *ht, oreal *q);
 oreal OSYM(oracle_nse)(const oreal *x, const oreal *y, int n);
+/* compute_jobs (mwd_cost.f90:37-156) on a given qsim(ng,T); qsim_b (may be NULL) receives COMPUTE_JOBS_B with jobs_b = 1 */
+oreal OSYM(oracle_compute_jobs)(const OSYM(OProblem) *P, const oreal *qsim, oreal *qsim_b);
 oreal OSYM(oracle_kge)(const oreal *x, const oreal *y, int n);
 
 #ifdef __cplusplus

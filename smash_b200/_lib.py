@@ -12,7 +12,7 @@ import numpy as np
 
 GNP, GNS = 16, 8
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsmash_b200.so")
+LIB_PATH = os.environ.get("SMASH_B200_LIB", os.path.join(_HERE, "libsmash_b200.so"))
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int32)
@@ -77,6 +77,7 @@ EXPORTS = [
     "smash_b200_plan_destroy", "smash_b200_plan_set_forcing", "smash_b200_plan_set_fields",
     "smash_b200_plan_run_forward", "smash_b200_plan_run_gradient", "smash_b200_plan_get_qsim",
     "smash_b200_plan_get_gradient", "smash_b200_plan_checksum", "smash_b200_plan_info", "smash_b200_plan_order",
+    "smash_b200_mesh_order",
 ]
 
 _lib = None

@@ -980,17 +980,43 @@ extern "C" int smash_b200_plan_checksum(SmashPlan *plan, double *sum_q) {
     return 0;
 }
 
-extern "C" int smash_b200_plan_info(const SmashPlan *plan, int64_t info[8]) {
+extern "C" int smash_b200_plan_info(const SmashPlan *plan, int64_t info[12]) {
     if (!plan || !info) return fail(SMASH_B200_EINVAL, "NULL argument");
     const Topology &tp = plan->tp;
     info[0] = tp.nactive; info[1] = tp.nblocks; info[2] = tp.B; info[3] = tp.max_skew; info[4] = tp.total_ticks;
-    info[5] = tp.n_cross_edges; info[6] = tp.n_pairs; info[7] = plan->launches;
+    info[5] = tp.n_cross_edges; info[6] = tp.n_pairs; info[7] = plan->launches; info[8] = tp.critical_ticks; info[9] = tp.max_chain_blocks; info[10] = tp.n_clusters; info[11] = tp.cluster_levels;
     return 0;
 }
 
 extern "C" int smash_b200_plan_order(const SmashPlan *plan, int32_t *order, int32_t *block_of, int32_t *offset_of) {
     if (!plan) return fail(SMASH_B200_EINVAL, "plan is NULL");
     const Topology &tp = plan->tp;
+    int k = 0;
+    for (int s = 0; s < tp.nslots; s++) {
+        if (tp.cell[s] < 0) continue;
+        if (order) order[k] = tp.cell[s];
+        if (block_of) block_of[k] = s / tp.B;
+        if (offset_of) offset_of[k] = tp.off[s];
+        k++;
+    }
+    return 0;
+}
+
+// host-only: the device ordering of a mesh without touching CUDA (used by the CPU test-suite)
+extern "C" int smash_b200_mesh_order(const SmashSetup *setup, const SmashMesh *mesh, int32_t block, int64_t info[12],
+                                     int32_t *order, int32_t *block_of, int32_t *offset_of) {
+    if (!setup || !mesh || !info) return fail(SMASH_B200_EINVAL, "NULL argument");
+    int nact = 0;
+    const int ncell = mesh->nrow * mesh->ncol;
+    for (int c = 0; c < ncell; c++)
+        if (mesh->active_cell[c] == 1 && (!mesh->local_active_cell || mesh->local_active_cell[c] == 1)) nact++;
+    Topology tp;
+    std::string err = build_topology(tp, mesh->nrow, mesh->ncol, mesh->ng, setup->ntime_step, mesh->flwdir, mesh->flwacc,
+                                     mesh->active_cell, mesh->local_active_cell, mesh->path, mesh->gauge_pos,
+                                     block > 0 ? block : pick_block(nact));
+    if (!err.empty()) return fail(SMASH_B200_EINVAL, "%s", err.c_str());
+    info[0] = tp.nactive; info[1] = tp.nblocks; info[2] = tp.B; info[3] = tp.max_skew; info[4] = tp.total_ticks;
+    info[5] = tp.n_cross_edges; info[6] = tp.n_pairs; info[7] = 0; info[8] = tp.critical_ticks; info[9] = tp.max_chain_blocks; info[10] = tp.n_clusters; info[11] = tp.cluster_levels;
     int k = 0;
     for (int s = 0; s < tp.nslots; s++) {
         if (tp.cell[s] < 0) continue;

@@ -81,16 +81,25 @@ __device__ __forceinline__ float pow_3p5(float x) { return (x * x) * x * sqrtf(x
 __device__ __forceinline__ float pow_2p5(float x) { return (x * x) * sqrtf(x); }
 template <int FAST> __device__ __forceinline__ float ftanh(float x) {
     if (FAST) {
-        // x >= 0 here (pn, en >= 0 and cp > 0).  tanh x = 1 - 2/(e^{2x}+1); odd series below 0.04.
-        if (x < 0.04f) { float x2 = x * x; return x * (1.0f + x2 * (-0.33333334f + x2 * 0.13333334f)); }
-        float e = __expf(2.0f * x);
+        // x >= 0 here (pn, en >= 0 and cp > 0).  Odd Taylor polynomial below 0.25 (truncation < 3e-9 relative),
+        // 1 - 2/(e^{2x}+1) above (absolute error ~1e-7 on a value >= 0.24).
+        if (x < 0.25f) {
+            const float x2 = x * x;
+            float p = fmaf(x2, 0.021869488f, -0.053968254f);   // 62/2835, -17/315
+            p = fmaf(x2, p, 0.13333334f);                      // 2/15
+            p = fmaf(x2, p, -0.33333334f);                     // -1/3
+            return fmaf(x * x2, p, x);
+        }
+        const float e = __expf(2.0f * x);
         return 1.0f - __fdividef(2.0f, e + 1.0f);
     }
     return tanhf(x);
 }
+__device__ __forceinline__ float fsqrt_fast(float x) { return x * rsqrtf(x); }   // x > 0
 
 struct CellConst {
-    float cp, inv_cp, cft, cft_m4, exc, lr, E, fa1, den;  // den = 0.001*dx*dx*(flwacc-1)
+    float cp, inv_cp, cft, inv_cft, cft_m4, exc, lr, E, fa1, den;  // den = 0.001*dx*dx*(flwacc-1)
+    float s_q, c0;                                                  // dt/den (0 for sources) and dx*dx*0.001/dt
 };
 
 // One gr-a cell-step WITHOUT routing (md_forward_structure.f90:106-144).  Updates hp, hft; returns qt and
@@ -135,10 +144,24 @@ __device__ __forceinline__ StepOut vertical_step(const CellConst &k, float prcp,
     } else {
         pr_imd = o.prr;
     }
-    float ht_imd = fmaxf(1.e-6f, hft + fdiv<FAST>(pr_imd, k.cft));   // :102
-    float x1 = ht_imd * k.cft;
-    float ht_new = fdiv<FAST>(pow_m025<FAST>(pow_m4<FAST>(x1) + k.cft_m4), k.cft);   // :104
-    float qr = (ht_imd - ht_new) * k.cft;                            // :106
+    float ht_imd, ht_new, qr;
+    if (FAST) {
+        // ht = ((ht_imd*ct)^-4 + ct^-4)^(-1/4) / ct  ==  u / s  with u = ht_imd, s = (1 + u^4)^(1/4)   (:104)
+        // q  = (ht_imd - ht)*ct = ct*u*(1 - 1/s), evaluated without the cancellation of the reference's form:
+        //      1 - 1/s = z / (s (s+1) (s^2+1)),  z = u^4.
+        ht_imd = fmaxf(1.e-6f, fmaf(pr_imd, k.inv_cft, hft));       // :102
+        const float z = pow4(ht_imd);
+        const float s2 = fsqrt_fast(1.0f + z), s1 = fsqrt_fast(s2);
+        const float g = __fdividef(z, s1 * (s1 + 1.0f) * (s2 + 1.0f));
+        const float rel = ht_imd * g;
+        qr = rel * k.cft;                                            // :106
+        ht_new = ht_imd - rel;
+    } else {
+        ht_imd = fmaxf(1.e-6f, hft + pr_imd / k.cft);               // :102
+        float x1 = ht_imd * k.cft;
+        ht_new = pow_m025<0>(pow_m4<0>(x1) + k.cft_m4) / k.cft;     // :104
+        qr = (ht_imd - ht_new) * k.cft;                              // :106
+    }
     hft = ht_new;
     float qd = fmaxf(0.0f, o.prd + l);                               // :142
     o.qt = qr + qd;                                                  // :144
@@ -148,17 +171,62 @@ __device__ __forceinline__ StepOut vertical_step(const CellConst &k, float prcp,
 __device__ __forceinline__ CellConst make_const(float cp, float cft, float exc, float lr, int flwacc, float dt, float dx) {
     CellConst k;
     k.cp = cp; k.inv_cp = 1.0f / cp;                                  // md_gr_operator.f90:47
-    k.cft = cft; k.cft_m4 = 1.0f / pow4(cft);
+    k.cft = cft; k.inv_cft = 1.0f / cft; k.cft_m4 = 1.0f / pow4(cft);
     k.exc = exc; k.lr = lr;
     k.E = expf(-dt / (lr * 60.0f));                                   // md_routing_operator.f90:75
     k.fa1 = (float)(flwacc - 1);
     k.den = 0.001f * dx * dx * k.fa1;                                 // md_routing_operator.f90:56
+    k.s_q = (flwacc > 1) ? dt / k.den : 0.0f;
+    k.c0 = dx * dx * 0.001f / dt;                                     // md_forward_structure.f90:155
     return k;
 }
 
 // ------------------------------------------------------------------------------------------------
 // forward kernel
 // ------------------------------------------------------------------------------------------------
+constexpr int QX_PAD = 32;   // qx[buf][B + QX_PAD]; slot B always holds 0 (absent inflow)
+
+// Branch-light cell-step for the common case (no forcing gap in the warp), FAST math only.
+// Same statements as vertical_step<1>; all lanes execute it, the caller commits the state conditionally.
+__device__ __forceinline__ float vertical_step_nogap(const CellConst &k, float prcp, float pet, float &hp, float &hft) {
+    const float ei = fminf(pet, prcp);                                   // md_forward_structure.f90:112
+    const float pn = fmaxf(0.0f, prcp - ei);                             // :114
+    const float en = pet - ei;                                           // :116
+    const bool wet = pn > 0.0f;
+    const float x = (wet ? pn : en) * k.inv_cp;
+    float th;
+    if (__all_sync(0xffffffffu, x < 0.25f)) {                            // warp-uniform: no divergence
+        const float x2 = x * x;
+        float p = fmaf(x2, 0.021869488f, -0.053968254f);
+        p = fmaf(x2, p, 0.13333334f);
+        p = fmaf(x2, p, -0.33333334f);
+        th = fmaf(x * x2, p, x);
+    } else {
+        th = ftanh<1>(x);
+    }
+    const float num = (wet ? k.cp * (1.0f - hp * hp) : (hp * k.cp) * (2.0f - hp)) * th;     // md_gr_operator.f90:52,55
+    const float den = fmaf(wet ? hp : 1.0f - hp, th, 1.0f);
+    const float r = __fdividef(num, den);
+    const float hp_imd = hp + (wet ? r : -r) * k.inv_cp;                 // :58
+    const float pr = wet ? pn - (hp_imd - hp) * k.cp : 0.0f;             // :60-62
+    float perc = 0.0f;
+    if (__any_sync(0xffffffffu, hp_imd > 15.0f)) {                       // below, 1 + (hp_imd/1000)^4 == 1 in float32 (:66)
+        const float w = 1.0f + pow4(hp_imd * 0.001f);
+        perc = (w == 1.0f) ? 0.0f : (hp_imd * k.cp) * (1.0f - pow_m025<1>(w));
+    }
+    hp = hp_imd - perc * k.inv_cp;                                       // :68
+    const float l = k.exc * ((hft * hft) * hft * fsqrt_fast(hft));       // md_gr_operator.f90:77
+    const float prr = fmaf(0.9f, pr + perc, l);                          // md_forward_structure.f90:137
+    const float prd = 0.1f * (pr + perc);                                // :138
+    const float u = fmaxf(1.e-6f, fmaf(prr, k.inv_cft, hft));            // md_gr_operator.f90:102
+    const float z = pow4(u);
+    const float s2 = fsqrt_fast(1.0f + z), s1 = fsqrt_fast(s2);
+    const float g = __fdividef(z, s1 * (s1 + 1.0f) * (s2 + 1.0f));       // 1 - (1+u^4)^(-1/4), cancellation-free (:104)
+    const float rel = u * g;
+    hft = u - rel;
+    return fmaf(rel, k.cft, fmaxf(0.0f, prd + l));                       // qt = qr + qd (:106, md_forward_structure.f90:142-144)
+}
+
 template <int FAST, int TAPE>
 __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -166,17 +234,17 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
     const int B = tp.B;
     const int tid = threadIdx.x;
     float *ring = reinterpret_cast<float *>(smem_raw);                 // [RING_STAGES][2][B]
-    float *qx = ring + RING_STAGES * 2 * B;                            // [2][B]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(qx + 2 * B);         // [RING_STAGES]
+    float *qx = ring + RING_STAGES * 2 * B;                            // [2][B + QX_PAD]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(qx + 2 * (B + QX_PAD));   // [RING_STAGES]
     __shared__ unsigned int s_ticket;
+    const int QS = B + QX_PAD;
 
     if (tid == 0) {
         s_ticket = atomicAdd(a.ticket, 1u);
         for (int s = 0; s < RING_STAGES; s++) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    qx[tid] = 0.0f;
-    qx[B + tid] = 0.0f;
+    for (int i = tid; i < 2 * QS; i += B) qx[i] = 0.0f;
     __syncthreads();
     const int vb = (int)s_ticket;
     const int member = vb / tp.nblocks;
@@ -199,38 +267,54 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
 
     const bool valid = tp.cell[slot] >= 0;
     const int off = tp.off[slot];
-    const int fa = tp.flwacc[slot];
+    const int fa = valid ? tp.flwacc[slot] : 1;
     const bool late = tp.late[slot];
     const int ub = tp.up_begin[slot], ue = tp.up_begin[slot + 1];
     const int gfirst = tp.gauge_first[slot];
     const float *fld = a.fields + (size_t)member * NFIELD * tp.nslots + slot;
     float hp = 0.01f, hft = 0.01f, hlr = 0.0f;
-    CellConst k = make_const(1.0f, 1.0f, 0.0f, 1.0f, 1, a.dt, a.dx);
+    CellConst k = make_const(200.0f, 500.0f, 0.0f, 5.0f, 1, a.dt, a.dx);
     if (valid) {
         k = make_const(fld[(size_t)F_CP * tp.nslots], fld[(size_t)F_CFT * tp.nslots], fld[(size_t)F_EXC * tp.nslots],
                        fld[(size_t)F_LR * tp.nslots], fa, a.dt, a.dx);
         hp = fld[(size_t)F_HP * tp.nslots]; hft = fld[(size_t)F_HFT * tp.nslots]; hlr = fld[(size_t)F_HLR * tp.nslots];
     }
+    // inflow lanes of the common case (<= 3 in-block producers, none in another block, not a pit-pair member):
+    // absent entries point at the zero slot B, so the sum keeps the reference's order without branches
+    int u0 = B, u1 = B, u2 = B;
+    bool simple = !late && (ue - ub) <= 3;
+    for (int e = ub; e < ue; e++) if (tp.up[e].a < 0 || tp.up[e].cur) simple = false;
+    if (simple) {
+        if (ue - ub > 0) u0 = tp.up[ub].a;
+        if (ue - ub > 1) u1 = tp.up[ub + 1].a;
+        if (ue - ub > 2) u2 = tp.up[ub + 2].a;
+    }
     const float c_dx = a.dx, c_dt = a.dt;
+    const int T = tp.T, ng = tp.ng;
     float *qdom = a.qdom ? a.qdom + ((size_t)member * tp.total_ticks + row0) * B + tid : nullptr;
     float *netp = (a.save_netp && a.netp) ? a.netp + ((size_t)member * tp.total_ticks + row0) * B + tid : nullptr;
     float *tape = TAPE ? a.tape + ((size_t)member * tp.total_ticks + row0) * 4 * B + tid : nullptr;
     float *qsim = a.qsim + (size_t)member * tp.T * tp.ng;
     const int *prog_m = a.prog + (size_t)member * tp.nblocks;
+    int *prog_mine = a.prog + (size_t)member * tp.nblocks + blk;
+    const bool do_flag = bf & BLK_PUBLISH;
 
+    int stage = 0;
+    uint32_t parity = 0;
+#pragma unroll 1
     for (int d = 0; d < nticks; d++) {
-        const int stage = d % RING_STAGES;
-        mbar_wait(&bars[stage], (d / RING_STAGES) & 1);
-        const float prcp = ring[(size_t)stage * 2 * B + tid];
-        const float pet = ring[(size_t)stage * 2 * B + B + tid];
+        mbar_wait(&bars[stage], parity);
+        const float prcp = ring[stage * 2 * B + tid];
+        const float pet = ring[stage * 2 * B + B + tid];
         const int t = d - off;
-        const bool act = valid && t >= 0 && t < tp.T;
-        const int cur = d & 1;
-        float q = 0.0f, qt = 0.0f;
+        const bool act = valid && (unsigned)t < (unsigned)T;
+        const float *qprev = qx + ((d & 1) ^ 1) * QS;
+        float *qcur = qx + (d & 1) * QS;
+        float q = 0.0f, qt;
         float xv[8];
-        int nx = 0;
-        if (act) {
+        if (!simple && act) {
             // cross-block inflows first: their latency hides behind the reservoir arithmetic
+            int nx = 0;
             for (int e = ub; e < ue; e++) {
                 const int ea = tp.up[e].a;
                 if (ea < 0) {
@@ -245,61 +329,77 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
                     nx++;
                 }
             }
-            if (TAPE) { tape[(size_t)d * 4 * B] = hp; tape[(size_t)d * 4 * B + B] = hft; tape[(size_t)d * 4 * B + 2 * B] = hlr; }
-            StepOut o = vertical_step<FAST>(k, prcp, pet, hp, hft);
-            qt = o.qt;
-            if (!late) {
-                // upstream_discharge md_routing_operator.f90:17-60 (neighbour order kept)
-                float qup = 0.0f;
-                if (fa > 1) {
-                    int jx = 0;
-                    for (int e = ub; e < ue; e++) {
-                        const int ea = tp.up[e].a;
-                        qup = qup + (ea >= 0 ? qx[(cur ^ 1) * B + ea] : xv[(jx++) & 7]);
-                    }
-                    qup = fdiv<FAST>(qup * c_dt, k.den);
-                }
-                if (TAPE) tape[(size_t)d * 4 * B + 3 * B] = qup;
-                // linear_routing md_routing_operator.f90:62-79
-                float hr_imd = hlr + qup;
-                hlr = hr_imd * k.E;
-                float qrout = hr_imd - hlr;
-                q = fdiv<FAST>((qt + qrout * k.fa1) * c_dx * c_dx * 0.001f, c_dt);   // md_forward_structure.f90:155
-                qx[cur * B + tid] = q;
+        }
+        if (TAPE && act) { tape[0] = hp; tape[B] = hft; tape[2 * B] = hlr; }
+        float hp_n = hp, hft_n = hft;
+        const bool gapless = (prcp >= 0.0f) && (pet >= 0.0f);
+        if (FAST && __all_sync(0xffffffffu, gapless)) {
+            qt = vertical_step_nogap(k, prcp, pet, hp_n, hft_n);
+        } else {
+            qt = vertical_step<FAST>(k, prcp, pet, hp_n, hft_n).qt;
+        }
+        if (act) { hp = hp_n; hft = hft_n; }
+        float qup = 0.0f;
+        if (simple) {
+            qup = (qprev[u0] + qprev[u1]) + qprev[u2];               // upstream_discharge md_routing_operator.f90:37-53
+        } else if (!late) {
+            int jx = 0;
+            for (int e = ub; e < ue; e++) {
+                const int ea = tp.up[e].a;
+                qup = qup + (ea >= 0 ? qprev[ea] : xv[(jx++) & 7]);
+            }
+        }
+        if (!late) {
+            qup = FAST ? qup * k.s_q : ((fa > 1) ? (qup * c_dt) / k.den : 0.0f);    // :55-56
+            // linear_routing md_routing_operator.f90:62-79
+            const float hr_imd = hlr + qup;
+            const float hlr_n = hr_imd * k.E;
+            const float qrout = hr_imd - hlr_n;
+            q = FAST ? fmaf(qrout, k.fa1, qt) * k.c0
+                     : (qt + qrout * k.fa1) * c_dx * c_dx * 0.001f / c_dt;          // md_forward_structure.f90:155
+            if (act) {
+                hlr = hlr_n;
+                qcur[tid] = q;
+                if (TAPE) tape[3 * B] = qup;
             }
         }
         if (has_late) {
             __syncthreads();
             if (act && late) {
-                float qup = 0.0f;
+                qup = 0.0f;
                 int jx = 0;
                 for (int e = ub; e < ue; e++) {
                     const UpEntry u = tp.up[e];
-                    qup = qup + (u.a >= 0 ? qx[(u.cur ? cur : cur ^ 1) * B + u.a] : xv[(jx++) & 7]);
+                    qup = qup + (u.a >= 0 ? (u.cur ? qcur : qprev)[u.a] : xv[(jx++) & 7]);
                 }
-                qup = fdiv<FAST>(qup * c_dt, k.den);
-                if (TAPE) tape[(size_t)d * 4 * B + 3 * B] = qup;
-                float hr_imd = hlr + qup;
+                qup = FAST ? qup * k.s_q : (qup * c_dt) / k.den;
+                if (TAPE) tape[3 * B] = qup;
+                const float hr_imd = hlr + qup;
                 hlr = hr_imd * k.E;
-                float qrout = hr_imd - hlr;
-                q = fdiv<FAST>((qt + qrout * k.fa1) * c_dx * c_dx * 0.001f, c_dt);
-                qx[cur * B + tid] = q;
+                const float qrout = hr_imd - hlr;
+                q = FAST ? fmaf(qrout, k.fa1, qt) * k.c0 : (qt + qrout * k.fa1) * c_dx * c_dx * 0.001f / c_dt;
+                qcur[tid] = q;
             }
         }
         if (act) {
-            if (publish) qdom[(size_t)d * B] = q;
-            if (netp) netp[(size_t)d * B] = qt;
-            for (int g = gfirst; g >= 0; g = tp.gauge_next[g]) qsim[(size_t)t * tp.ng + g] = q;   // :206-210
+            if (publish) qdom[0] = q;
+            if (netp) netp[0] = qt;
+            if (gfirst >= 0)
+                for (int g = gfirst; g >= 0; g = tp.gauge_next[g]) qsim[(size_t)t * ng + g] = q;   // :206-210
         }
+        if (publish) qdom += B;
+        if (netp) netp += B;
+        if (TAPE) tape += 4 * B;
         __syncthreads();
         if (tid == 0) {
-            if (bf & BLK_PUBLISH) { __threadfence(); st_release(a.prog + (size_t)member * tp.nblocks + blk, d + 1); }
+            if (do_flag) { __threadfence(); st_release(prog_mine, d + 1); }
             const int dn = d + RING_STAGES;
             if (dn < nticks) {
                 mbar_expect_tx(&bars[stage], row_bytes);
                 tma_load_1d(ring + (size_t)stage * 2 * B, frc + (size_t)dn * 2 * B, row_bytes, &bars[stage]);
             }
         }
+        if (++stage == RING_STAGES) { stage = 0; parity ^= 1u; }
     }
     if (valid) {
         float *fs = a.fstates + (size_t)member * 3 * tp.nslots + slot;
@@ -803,7 +903,7 @@ __global__ void checksum_kernel(DeviceTopology tp, const float *skewed, double *
 // ------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
-static size_t fwd_smem(int B) { return (size_t)(RING_STAGES * 2 + 2) * B * sizeof(float) + RING_STAGES * sizeof(uint64_t); }
+static size_t fwd_smem(int B) { return (size_t)((RING_STAGES * 2 + 2) * B + 2 * QX_PAD) * sizeof(float) + RING_STAGES * sizeof(uint64_t); }
 static size_t rev_smem(int B) { return (size_t)(RING_STAGES * 6 + 2) * B * sizeof(float) + RING_STAGES * sizeof(uint64_t); }
 
 template <typename K> static cudaError_t launch_solver(K kern, const SolverArgs &a, size_t smem, cudaStream_t s) {

@@ -169,35 +169,112 @@ std::string build_topology(Topology &tp, int nrow, int ncol, int ng, int T, cons
     }
     if ((int)post.size() != n) return "mesh: flow directions contain a cycle longer than two cells";
 
-    // ---- cut into blocks; never separate a pit pair
+    // ---- partition the forest into connected clusters of at most B cells (bottom-up, Kundu-Misra style: when the
+    // residual subtree of a cell exceeds the capacity its heaviest child subtrees are cut off), then pack clusters of
+    // the same depth of the cluster tree into blocks.  Producers of a block are always one cluster-level below, so
+    // blocks ordered by level only ever wait for lower-numbered blocks, and the chain of dependent blocks is as
+    // short as the river network allows (a post-order cut into fixed chunks chains almost every block to its
+    // predecessor).  A pit pair is never separated.
     std::vector<int32_t> slot_rank;  // slot -> rank or -1
-    slot_rank.reserve(n + n / B + B);
-    for (int k = 0; k < n; k++) {
-        int r = post[k];
-        int lane = (int)(slot_rank.size() % B);
-        if (lane == B - 1 && early[r]) slot_rank.push_back(-1);
-        slot_rank.push_back(r);
+    {
+        std::vector<int32_t> w(n, 1);
+        std::vector<uint8_t> cut(n, 0);
+        std::vector<std::pair<int32_t, int32_t>> kids;
+        for (int k = 0; k < n; k++) {
+            const int v = post[k];
+            int64_t tot = 1;
+            for (int e = ch_begin[v]; e < ch_begin[v + 1]; e++) tot += w[ch[e]];
+            const int cap = early[v] ? B - 1 : B;
+            if (tot > cap) {
+                kids.clear();
+                for (int e = ch_begin[v]; e < ch_begin[v + 1]; e++)
+                    if (partner[v] != ch[e]) kids.push_back({w[ch[e]], ch[e]});
+                std::sort(kids.begin(), kids.end(), [](const std::pair<int32_t, int32_t> &x, const std::pair<int32_t, int32_t> &y) {
+                    return x.first != y.first ? x.first > y.first : x.second < y.second;
+                });
+                for (size_t i = 0; i < kids.size() && tot > cap; i++) { cut[kids[i].second] = 1; tot -= kids[i].first; }
+                if (tot > cap) return "internal: cluster capacity exceeded";
+            }
+            w[v] = (int32_t)tot;
+        }
+        // cluster ids, parents first
+        std::vector<int32_t> cid(n, -1), csize, cparent, croot;
+        for (int k = n - 1; k >= 0; k--) {
+            const int v = post[k];
+            if (parent[v] < 0 || cut[v]) {
+                cid[v] = (int32_t)csize.size();
+                csize.push_back(0);
+                croot.push_back(v);
+                cparent.push_back(parent[v] < 0 ? -1 : cid[parent[v]]);
+            } else cid[v] = cid[parent[v]];
+            csize[cid[v]]++;
+        }
+        const int nc = (int)csize.size();
+        std::vector<int32_t> clevel(nc, 0);
+        int maxlevel = 0;
+        for (int c = nc - 1; c >= 0; c--) {   // children clusters have larger ids than their parent cluster
+            if (cparent[c] >= 0) clevel[cparent[c]] = std::max(clevel[cparent[c]], clevel[c] + 1);
+            maxlevel = std::max(maxlevel, clevel[c]);
+        }
+        // member lists in post-order
+        std::vector<int32_t> cbegin(nc + 1, 0), cmem(n);
+        for (int c = 0; c < nc; c++) cbegin[c + 1] = cbegin[c] + csize[c];
+        {
+            std::vector<int32_t> pos(cbegin.begin(), cbegin.end() - 1);
+            for (int k = 0; k < n; k++) cmem[pos[cid[post[k]]]++] = post[k];
+        }
+        // pack level by level, best fit decreasing
+        std::vector<std::vector<int32_t>> by_level(maxlevel + 1);
+        for (int c = 0; c < nc; c++) by_level[clevel[c]].push_back(c);
+        std::vector<std::vector<int32_t>> blocks;   // cluster ids per block
+        for (int lv = 0; lv <= maxlevel; lv++) {
+            auto &cl = by_level[lv];
+            std::sort(cl.begin(), cl.end(), [&](int x, int y) { return csize[x] != csize[y] ? csize[x] > csize[y] : x < y; });
+            std::vector<std::vector<int32_t>> open(B + 1);   // open blocks of this level by remaining capacity
+            for (int c : cl) {
+                int rem = -1;
+                for (int r = csize[c]; r <= B; r++) if (!open[r].empty()) { rem = r; break; }
+                int bi;
+                if (rem < 0) { bi = (int)blocks.size(); blocks.emplace_back(); rem = B; }
+                else { bi = open[rem].back(); open[rem].pop_back(); }
+                blocks[bi].push_back(c);
+                if (rem - csize[c] > 0) open[rem - csize[c]].push_back(bi);
+            }
+        }
+        slot_rank.assign(blocks.size() * (size_t)B, -1);
+        for (size_t bi = 0; bi < blocks.size(); bi++) {
+            size_t lane = 0;
+            for (int c : blocks[bi])
+                for (int e = cbegin[c]; e < cbegin[c + 1]; e++) slot_rank[bi * B + lane++] = cmem[e];
+        }
+        tp.n_clusters = nc;
+        tp.cluster_levels = maxlevel + 1;
     }
-    while (slot_rank.size() % B) slot_rank.push_back(-1);
     tp.nslots = (int)slot_rank.size();
     tp.nblocks = tp.nslots / B;
     std::vector<int32_t> slot_of_rank(n, -1);
     for (int s = 0; s < tp.nslots; s++) if (slot_rank[s] >= 0) slot_of_rank[slot_rank[s]] = s;
 
     // ---- in-block skew
-    std::vector<int32_t> h(tp.nslots, 0);
+    // Every in-block tree is scheduled on its own: its root (the cell whose consumer lives in another block) runs
+    // as early as its own height allows, its descendants one tick ahead per hop.  Offsets relative to the block-wide
+    // maximum would delay the roots of shallow trees for nothing and that delay adds up along chains of blocks.
+    std::vector<int32_t> h(tp.nslots, 0), root(tp.nslots, -1), height(tp.nslots, 0);
     tp.hmax.assign(tp.nblocks, 0);
     for (int s = tp.nslots - 1; s >= 0; s--) {
         int r = slot_rank[s];
         if (r < 0) continue;
+        root[s] = s;
         int p = parent[r];
         if (p >= 0) {
             int ps = slot_of_rank[p];
             if (ps / B == s / B) {
                 if (ps <= s) return "internal: parent does not follow child in post-order";
                 h[s] = h[ps] + parent_delta[r];
+                root[s] = root[ps];
             }
         }
+        height[root[s]] = std::max(height[root[s]], h[s]);
         tp.hmax[s / B] = std::max(tp.hmax[s / B], h[s]);
     }
     tp.tick_base.assign(tp.nblocks + 1, 0);
@@ -216,7 +293,7 @@ std::string build_topology(Topology &tp, int nrow, int ncol, int ng, int T, cons
         if (r < 0) continue;
         int c = computed[r];
         tp.cell[s] = c; tp.sparse_k[s] = sparse_k[c]; tp.flwacc[s] = flwacc[c];
-        tp.off[s] = tp.hmax[s / B] - h[s];
+        tp.off[s] = height[root[s]] - h[s];
         tp.late[s] = late[r]; tp.early[s] = early[r];
         tp.slot_of_cell[c] = s;
         if (late[r]) tp.flags[s / B] |= BLK_LATE;
@@ -272,6 +349,25 @@ std::string build_topology(Topology &tp, int nrow, int ncol, int ng, int T, cons
         }
     }
     tp.up_begin[tp.nslots] = (int32_t)tp.up.size();
+
+    // ---- critical path over blocks: block b may run tick d once every cross-block producer p has finished its
+    // tick d + dtick, i.e. start[b] >= start[p] + dtick + 1 when every block advances one tick per time unit.
+    {
+        std::vector<int64_t> start(tp.nblocks, 0);
+        std::vector<int32_t> depth(tp.nblocks, 1);
+        for (int s = 0; s < tp.nslots; s++)
+            for (int e = tp.up_begin[s]; e < tp.up_begin[s + 1]; e++) {
+                if (tp.up[e].a >= 0) continue;
+                const ExtRef &x = tp.ext[-tp.up[e].a - 1];
+                const int b = s / B;
+                start[b] = std::max(start[b], start[x.blk] + x.dtick + 1);
+                depth[b] = std::max(depth[b], depth[x.blk] + 1);
+            }
+        for (int b = 0; b < tp.nblocks; b++) {
+            tp.critical_ticks = std::max<int64_t>(tp.critical_ticks, start[b] + T + tp.hmax[b]);
+            tp.max_chain_blocks = std::max(tp.max_chain_blocks, depth[b]);
+        }
+    }
 
     // ---- gauges (md_forward_structure.f90:206-210)
     tp.gauge_first.assign(tp.nslots, -1);

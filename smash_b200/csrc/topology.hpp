@@ -38,6 +38,9 @@ struct Topology {
     int64_t total_ticks = 0;   // sum over blocks of (T + hmax)
     int max_skew = 0;
     int n_cross_edges = 0, n_pairs = 0;
+    int64_t critical_ticks = 0; // longest dependency chain over blocks, in ticks (start delay + own ticks)
+    int max_chain_blocks = 0;
+    int n_clusters = 0, cluster_levels = 0;  // connected clusters of the forest partition and depth of the cluster tree   // longest chain of blocks linked by cross-block edges
 
     // per slot (size nslots); cell == -1 marks a padding lane
     std::vector<int32_t> cell;        // 0-based flat rect index row + col*nrow

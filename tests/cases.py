@@ -129,15 +129,33 @@ def normalize_descriptor(model):
 
 
 def synthetic_forcing(nac, T, seed=0, gap_fraction=0.0):
-    """prcp = Bernoulli(0.15)*Gamma(0.6, 4.0) mm/h, pet = U(1,4) mm/d * RATIO_PET_HOURLY[hour]."""
+    """prcp = Bernoulli(0.15)*Gamma(0.6, 4.0) mm/h, pet = U(1,4) mm/d * RATIO_PET_HOURLY[hour].
+    Returns Fortran-ordered (nac, T) float32 arrays (memory [t][k], mwd_input_data.f90:73-80)."""
     rng = np.random.default_rng(seed)
-    prcp = (rng.random((nac, T), dtype=np.float32) < 0.15) * rng.gamma(0.6, 4.0, (nac, T)).astype(np.float32)
+    prcp = np.empty((T, nac), dtype=np.float32)
+    chunks = list(range(0, T, 16))
+    seeds = np.random.SeedSequence(seed).spawn(len(chunks))
+
+    def fill(job):                                  # independent stream per 16-step chunk (NumPy RNGs release the GIL)
+        t0, ss = job
+        r = np.random.default_rng(ss)
+        n = min(16, T - t0)
+        wet = r.random((n, nac), dtype=np.float32) < np.float32(0.15)
+        prcp[t0:t0 + n] = wet * (r.standard_gamma(0.6, (n, nac), dtype=np.float32) * np.float32(4.0))
+        if gap_fraction > 0:
+            gaps = r.random((n, nac), dtype=np.float32) < np.float32(gap_fraction)
+            prcp[t0:t0 + n][gaps] = np.float32(-99.0)
+
+    if T * nac > 50_000_000:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+            list(ex.map(fill, zip(chunks, seeds)))
+    else:
+        for job in zip(chunks, seeds):
+            fill(job)
     pet_day = rng.uniform(1.0, 4.0, nac).astype(np.float32)
-    pet = pet_day[:, None] * RATIO_PET_HOURLY[np.arange(T) % 24][None, :]
-    if gap_fraction > 0:
-        gaps = rng.random((nac, T)) < gap_fraction
-        prcp = np.where(gaps, np.float32(-99.0), prcp)
-    return np.asfortranarray(prcp, dtype=np.float32), np.asfortranarray(pet, dtype=np.float32)
+    pet = RATIO_PET_HOURLY[np.arange(T) % 24][:, None] * pet_day[None, :]
+    return prcp.T, np.ascontiguousarray(pet, dtype=np.float32).T
 
 
 def france(T=24, seed=0, sub=None):
