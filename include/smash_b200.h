@@ -156,8 +156,10 @@ const char *smash_b200_version(void);
 int smash_b200_device_count(void);           /* number of CUDA devices, 0 if none / no driver */
 int smash_b200_set_device(int device);       /* device used by subsequent calls of this thread */
 void smash_b200_clear_cache(void);           /* drop cached mesh plans and device-resident forcing */
-/* tuning knobs (also readable from the environment as SMASH_B200_<NAME>): "math" 0 = IEEE division/sqrt +
- * libm tanhf (default), 1 = MUFU reciprocal/rsqrt approximations; "block" = cells per CTA (0 = automatic);
+/* tuning knobs (also readable from the environment as SMASH_B200_<NAME>): "math" 1 (default) = MUFU
+ * reciprocal / rsqrt with the cancellation-free transfer formula (closer to the float64 solution than the
+ * reference's own float32 arithmetic), 0 = IEEE division / sqrt + libm tanhf in the reference's
+ * statement order; "block" = cells per CTA (0 = automatic);
  * "member_budget_mb" = device memory per ensemble launch. */
 int smash_b200_set_option(const char *name, long long value);
 

@@ -539,7 +539,7 @@ static void scatter_sorted(const SmashPlan &pl, const float *sorted, float *plan
     for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) plane[tp.cell[s]] = sorted[s];
 }
 
-static int math_mode() { return (int)option("math", 0); }
+static int math_mode() { return (int)option("math", 1); }
 
 // ------------------------------------------------------------------------------------------------
 // forward

@@ -158,9 +158,10 @@ def synthetic_forcing(nac, T, seed=0, gap_fraction=0.0):
     return prcp.T, np.ascontiguousarray(pet, dtype=np.float32).T
 
 
-def france(T=24, seed=0, sub=None):
+def france(T=24, seed=0, sub=None, ngauge=0):
     """France 1 km mesh (mesh_France.hdf5) with synthetic sparse forcing; `sub=(r0,r1,c0,c1)` crops a window
-    (flow directions leaving the window simply drain nowhere, as at the domain edge)."""
+    (flow directions leaving the window simply drain nowhere, as at the domain edge); `ngauge` puts synthetic gauges
+    on the cells with the largest flow accumulation (the shipped France mesh has none)."""
     d = golden("france_mesh.npz")
     flwdir, flwacc, active = d["flwdir"].astype(np.int32), d["flwacc"], d["active_cell"].astype(np.int32)
     path = d["path"].astype(np.int32)
@@ -170,11 +171,11 @@ def france(T=24, seed=0, sub=None):
         keep = (path[0] >= r0) & (path[0] < r1) & (path[1] >= c0) & (path[1] < c1)
         path = path[:, keep] - np.array([[r0], [c0]], dtype=np.int32)
     nrow, ncol = flwdir.shape
-    setup = SetupDT(nd=0, ng=0)
+    setup = SetupDT(nd=0, ng=ngauge)
     setup.sparse_storage = True
     setup._ntime_step = int(T)
     setup.save_qsim_domain = True                                       # setup_France.yaml:18
-    mesh = MeshDT(setup, nrow, ncol, 0)
+    mesh = MeshDT(setup, nrow, ncol, ngauge)
     mesh.dx = np.float32(d["dx"])
     mesh.flwdir = np.asfortranarray(flwdir)
     mesh.flwacc = np.asfortranarray(flwacc)
@@ -185,13 +186,32 @@ def france(T=24, seed=0, sub=None):
     mesh.path = np.asfortranarray(full)
     mesh.nac = int(active.sum())
     compute_rowcol_to_ind_sparse(mesh)
+    if ngauge > 0:
+        fa = np.where(active == 1, flwacc, 0)
+        flat = np.argsort(fa.ravel(), kind="stable")[::-1][:ngauge]
+        gr, gc = np.unravel_index(flat, fa.shape)
+        mesh.gauge_pos = np.asfortranarray(np.stack([gr, gc], axis=1).astype(np.int32))
+        mesh.area = (flwacc[gr, gc].astype(np.float32) * mesh.dx * mesh.dx).astype(np.float32)
     inp = Input_DataDT(setup, mesh)
     inp.sparse_prcp, inp.sparse_pet = synthetic_forcing(mesh.nac, T, seed)
     par = ParametersDT(mesh)
     st = StatesDT(mesh)
     out = OutputDT(setup, mesh)
-    set_optimize(setup, mesh, jobs_fun=())
-    return Model(setup, mesh, inp, par, st, out)
+    set_optimize(setup, mesh, jobs_fun=("nse",) if ngauge else (), gauge="all")
+    model = Model(setup, mesh, inp, par, st, out)
+    if ngauge > 0:
+        # "observations" = a run of the CPU oracle with perturbed parameters, +-5 % multiplicative noise
+        import oracle
+        truth = model.copy()
+        truth.setup.save_qsim_domain = False
+        truth.parameters.cp[...] = 260.0
+        truth.parameters.cft[...] = 380.0
+        truth.parameters.lr[...] = 7.0
+        oracle.forward(truth.setup, truth.mesh, truth.input_data, truth.parameters, truth.parameters.copy(), truth.states,
+                       truth.states.copy(), truth.output)
+        noise = 1.0 + 0.05 * np.random.default_rng(seed + 17).uniform(-1, 1, truth.output.qsim.shape)
+        inp.qobs = np.asfortranarray((truth.output.qsim * noise).astype(np.float32))
+    return model
 
 
 def hyper_objects(model):

@@ -1,0 +1,109 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/smash_b200.h
+declares, fails loudly without a device, and its host-side mesh ordering keeps the integer contract."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+from smash_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "smash_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(smash_b200_[a-z_0-9]+)\s*\(", hdr)))
+    assert declared, "no declarations found"
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(L.EXPORTS) == declared
+
+
+def test_version_and_no_device_is_loud():
+    lib = L.lib()
+    assert b"sm_100a" in lib.smash_b200_version()
+    if lib.smash_b200_device_count() == 0:
+        import smash_b200
+        m = cases.cance(T=24)
+        with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+            smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(),
+                               m.output)
+
+
+def mesh_order(m, block=0):
+    pk = L.Packed()
+    s, me = L.pack_setup(m.setup, m.mesh, pk), L.pack_mesh(m.mesh, m.setup, pk)
+    info = (C.c_int64 * 12)()
+    n = int(((m.mesh.active_cell == 1) & (m.mesh._local_active_cell == 1)).sum())
+    order, blk, off = (np.zeros(n, np.int32) for _ in range(3))
+    L.check(L.lib().smash_b200_mesh_order(C.byref(s), C.byref(me), block, info, L._ip(order), L._ip(blk), L._ip(off)))
+    return order, blk, off, list(info)
+
+
+DROW = np.array([1, 1, 0, -1, -1, -1, 0, 1])   # md_routing_operator.f90:29-30
+DCOL = np.array([0, -1, -1, -1, 0, 1, 1, 1])
+
+
+def check_order(m, order, blk, off, info):
+    nrow, ncol = m.mesh.nrow, m.mesh.ncol
+    act = ((m.mesh.active_cell == 1) & (m.mesh._local_active_cell == 1)).ravel(order="F")
+    assert info[0] == act.sum()
+    assert np.array_equal(np.sort(order), np.nonzero(act)[0])            # a permutation of the computed cells
+    pos = np.full(nrow * ncol, -1, np.int64)
+    pos[order] = np.arange(len(order))
+    rank = np.full(nrow * ncol, -1, np.int64)                              # rank in the stored path
+    p = m.mesh.path
+    ok = (p[0] >= 0) & (p[1] >= 0)
+    rank[p[0][ok] + p[1][ok].astype(np.int64) * nrow] = np.arange(ok.sum())
+    flwdir, flwacc = m.mesh.flwdir.ravel(order="F"), m.mesh.flwacc.ravel(order="F")
+    rows, cols = order % nrow, order // nrow
+    d = flwdir[order]
+    tr, tc = rows - DROW[d - 1], cols - DCOL[d - 1]                       # downstream cell of every computed cell
+    inb = (tr >= 0) & (tr < nrow) & (tc >= 0) & (tc < ncol)
+    tgt = np.where(inb, tr + tc * nrow, 0)
+    edge = inb & act[tgt] & (flwacc[tgt] > 1)
+    src_pos, tgt_pos = np.nonzero(edge)[0], pos[tgt[edge]]
+    same_step = rank[order[src_pos]] < rank[tgt[edge]]
+    # producers never sit in a later block; inside a block a same-step producer is exactly one tick ahead
+    assert np.all(blk[src_pos] <= blk[tgt_pos])
+    same_blk = blk[src_pos] == blk[tgt_pos]
+    normal = same_blk & same_step
+    gap = off[tgt_pos[normal]] - off[src_pos[normal]]
+    assert np.all((gap == 1) | (gap == 0))
+    assert (gap == 0).sum() == info[6]                                    # only pit pairs share a tick
+    lag = same_blk & ~same_step
+    assert np.all(off[tgt_pos[lag]] == off[src_pos[lag]])
+    assert np.all(blk[src_pos[~same_step]] == blk[tgt_pos[~same_step]]) or info[6] == 0
+    assert info[5] == int((~same_blk).sum())
+    assert off.max() == info[3]
+
+
+def test_order_cance():
+    m = cases.cance(T=24)
+    order, blk, off, info = mesh_order(m)
+    check_order(m, order, blk, off, info)
+    assert info[1] == 1 and info[2] == 384 and info[6] == 0
+    for b in (32, 64, 128):
+        check_order(m, *mesh_order(m, b))
+
+
+def test_order_france():
+    m = cases.france(T=24)
+    order, blk, off, info = mesh_order(m, 256)
+    check_order(m, order, blk, off, info)
+    assert info[0] == 906044 and info[6] == 50
+    assert info[9] < 200, "chain of dependent blocks should stay short"
+
+
+def test_mesh_golden_integers(golden):
+    # the mesh arrays the solver consumes are the reference's own (smash/tests/io/test_io.py:27-32, test_meshing.py:31-42)
+    d = cases.golden("cance_inputs.npz")
+    assert np.array_equal(d["flwacc"], golden["mesh_io.flwacc"])
+    assert np.array_equal(d["path"], golden["mesh_io.path"])
+    assert np.array_equal(d["flwdir"], golden["mesh_io.flwdir"].astype(np.int32))
+    assert np.array_equal(d["flwacc"], golden["xy_mesh.flwacc"])
+    assert np.array_equal(d["gauge_pos"], golden["mesh_io.gauge_pos"])

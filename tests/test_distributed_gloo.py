@@ -1,0 +1,63 @@
+"""world_size-2 gloo test (CPU) of the N>1 path: member sharding + gather of the ensemble results, and the single
+all-reduce of the shared hyper-parameter gradient.  The per-rank compute is replaced by a deterministic stand-in so
+that only the host-side plumbing is exercised here; the GPU arithmetic is covered by the -m gpu tests."""
+import os
+
+import numpy as np
+import torch.multiprocessing as mp
+
+
+def _fake_compute(setup, mesh, input_data, parameters, states, output, sample, ind, res_cost, res_qsim):
+    res_cost[...] = sample.sum(axis=0)
+    if res_qsim.size:
+        res_qsim[...] = sample[0][None, None, :] * np.arange(1, mesh.ng * setup._ntime_step + 1).reshape(
+            mesh.ng, setup._ntime_step, order="F")[..., None]
+
+
+def _worker(rank, world, port, ns, ret):
+    import torch.distributed as dist
+
+    import cases
+    from smash_b200 import distributed as D
+    from smash_b200.solver._derived_types import Hyper_ParametersDT, Hyper_StatesDT
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = cases.cance(T=12)
+    rng = np.random.RandomState(0)
+    sample = np.asfortranarray(rng.uniform(0, 1, (4, ns)).astype(np.float32))
+    cost = np.zeros(ns, np.float32)
+    qsim = np.zeros((m.mesh.ng, 12, ns), np.float32, order="F")
+    D.multiple_run_sharded(m.setup, m.mesh, m.input_data, m.parameters, m.states, m.output, sample, cases.IND_CP_CFT_EXC_LR,
+                           cost, qsim, compute=_fake_compute)
+    cases.set_optimize(m.setup, m.mesh, mapping="hyper-linear")
+    hpb, hsb = Hyper_ParametersDT(m.setup), Hyper_StatesDT(m.setup)
+    hpb.cp[...] = rank + 1.0
+    hsb.hlr[...] = 10.0 * (rank + 1)
+    total = D.allreduce_shared_gradient(np.float32(0.5 + rank), hpb, hsb)
+    if rank == 0:
+        ret["cost"], ret["qsim"], ret["sample"] = cost, qsim, sample
+        ret["total"], ret["cp"], ret["hlr"] = float(total), hpb.cp.copy(), hsb.hlr.copy()
+    dist.destroy_process_group()
+
+
+def test_member_slices_cover_everything():
+    from smash_b200.distributed import member_slice
+    for ns in (0, 1, 7, 10, 4096):
+        for world in (1, 2, 3, 8):
+            idx = np.concatenate([np.arange(ns)[member_slice(ns, r, world)] for r in range(world)])
+            assert np.array_equal(idx, np.arange(ns))
+            sizes = [member_slice(ns, r, world).stop - member_slice(ns, r, world).start for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_sharded_ensemble_and_allreduce_world2():
+    world, ns = 2, 7
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, 29500 + os.getpid() % 1000, ns, ret), nprocs=world, join=True)
+        sample = ret["sample"]
+        assert np.allclose(ret["cost"], sample.sum(axis=0))
+        want = sample[0][None, None, :] * np.arange(1, 3 * 12 + 1).reshape(3, 12, order="F")[..., None]
+        assert np.allclose(ret["qsim"], want)
+        assert ret["total"] == 0.5 + 1.5
+        assert np.all(ret["cp"] == 3.0) and np.all(ret["hlr"] == 30.0)

@@ -1,0 +1,237 @@
+"""More GPU parity cases through the C ABI: hyper mappings, regularised / normalised VDA gradient, forcing gaps,
+domain outputs, ensemble chunking, France-scale gradient with pit pairs, and size-independent properties."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import oracle
+import smash_b200
+from smash_b200 import _lib as L
+from smash_b200.solver._derived_types import Hyper_ParametersDT, Hyper_StatesDT, ParametersDT, StatesDT
+from test_gpu_parity import check_grad, close_q, random_fields
+
+pytestmark = pytest.mark.gpu
+
+
+def hyper_setup(mapping, T=1440):
+    m = cases.cance(T=T)
+    cases.normalize_descriptor(m)
+    cases.set_optimize(m.setup, m.mesh, jobs_fun=("nse",), mapping=mapping)
+    o = m.setup._optimize
+    nh = o.nhyper
+    hp, hs = Hyper_ParametersDT(m.setup), Hyper_StatesDT(m.setup)
+    rng = np.random.default_rng(5)
+    defaults = dict(cp=200.0, cft=500.0, exc=0.0, lr=5.0, hp=0.01, hft=0.01, hlr=1e-6)
+    for names, obj, lb, ub in ((L.PARAM_NAMES, hp, o.lb_parameters, o.ub_parameters), (L.STATE_NAMES, hs, o.lb_states, o.ub_states)):
+        for i, n in enumerate(names):
+            h = np.zeros((nh, 1), np.float32, order="F")
+            x = (defaults.get(n, 0.5 * (float(lb[i]) + float(ub[i]))) - float(lb[i])) / (float(ub[i]) - float(lb[i]))
+            x = min(max(x, 1e-6), 1 - 1e-6)
+            h[0, 0] = np.log(x / (1 - x))
+            if n in ("cp", "cft", "lr", "exc"):
+                if mapping == "hyper-linear":
+                    h[1:, 0] = rng.uniform(-0.5, 0.5, nh - 1)
+                else:
+                    h[1::2, 0] = rng.uniform(-0.5, 0.5, (nh - 1) // 2)
+                    h[2::2, 0] = rng.uniform(0.6, 1.8, (nh - 1) // 2)
+            elif mapping == "hyper-polynomial":
+                h[2::2, 0] = 1.0
+            setattr(obj, n, h)
+    return m, hp, hs
+
+
+@pytest.mark.parametrize("mapping", ["hyper-linear", "hyper-polynomial"])
+def test_hyper_forward_and_adjoint(mapping):
+    a, hp, hs = hyper_setup(mapping)
+    b = a.copy()
+    smash_b200.hyper_forward(a.setup, a.mesh, a.input_data, a.parameters, hp, hp.copy(), a.states, hs, hs.copy(), a.output)
+    oracle.hyper_forward(b.setup, b.mesh, b.input_data, b.parameters, hp, b.states, hs, b.output)
+    assert close_q(a.output.qsim, b.output.qsim)
+    assert abs(float(a.output.cost) - float(b.output.cost)) < 1e-5 * max(1.0, abs(float(b.output.cost)))
+    # the mapping rewrites every field over the whole rectangle (mwd_parameters_manipulation.f90:326-358)
+    for n in ("cp", "cft", "exc", "lr", "ci", "beta"):
+        assert np.allclose(getattr(a.parameters, n), getattr(b.parameters, n), rtol=2e-6, atol=1e-6), n
+    # states keep their final values (forward.f90:145: no restore in the hyper path)
+    assert np.allclose(a.states.hp, b.states.hp, rtol=1e-4, atol=1e-7)
+    a2, b2 = a.copy(), b.copy()
+    ga, gsa, gb, gsb = (Hyper_ParametersDT(a.setup), Hyper_StatesDT(a.setup), Hyper_ParametersDT(a.setup), Hyper_StatesDT(a.setup))
+    smash_b200.hyper_forward_b(a2.setup, a2.mesh, a2.input_data, a2.parameters, None, hp, ga, None, None, a2.states, None, hs, gsa,
+                               None, None, a2.output, None)
+    oracle.hyper_forward_b(b2.setup, b2.mesh, b2.input_data, b2.parameters, hp, gb, b2.states, hs, gsb, b2.output)
+    for n in ("cp", "cft", "exc", "lr"):
+        x, y = np.asarray(getattr(ga, n), np.float64).ravel(), np.asarray(getattr(gb, n), np.float64).ravel()
+        assert np.allclose(x, y, rtol=2e-3, atol=2e-3 * np.abs(y).max()), (n, x, y)
+    for n in ("hp", "hft", "hlr"):
+        x, y = np.asarray(getattr(gsa, n), np.float64).ravel(), np.asarray(getattr(gsb, n), np.float64).ravel()
+        assert np.allclose(x, y, rtol=2e-3, atol=2e-3 * np.abs(y).max() + 1e-12), (n, x, y)
+
+
+def test_vda_gradient_with_regularisation_and_normalisation():
+    # optimize_lbfgsb setting (mw_optimize.f90:547-561): normalised controls, denormalize_forward, prior + smoothing
+    def make():
+        m = cases.cance(T=480)
+        cases.set_optimize(m.setup, m.mesh, jobs_fun=("nse",), jreg_fun=("prior", "smoothing"), wjreg_fun=[1.0, 0.5], wjreg=1e-3,
+                           denormalize_forward=True)
+        random_fields(m)
+        o = m.setup._optimize
+        o.optim_parameters[[1, 3, 6, 15]] = 1
+        bgd = m.parameters.copy()
+        for i, n in enumerate(L.PARAM_NAMES):
+            rngw = o.ub_parameters[i] - o.lb_parameters[i]
+            setattr(m.parameters, n, np.asfortranarray((getattr(m.parameters, n) - o.lb_parameters[i]) / rngw))
+            setattr(bgd, n, np.asfortranarray((getattr(bgd, n) - o.lb_parameters[i]) / rngw + np.float32(0.01)))
+        for i, n in enumerate(L.STATE_NAMES):
+            setattr(m.states, n, np.asfortranarray((getattr(m.states, n) - o.lb_states[i]) / (o.ub_states[i] - o.lb_states[i])))
+        return m, bgd
+
+    (a, bgd_a), (b, bgd_b) = make(), make()
+    pa, sa, pb, sb = ParametersDT(a.mesh), StatesDT(a.mesh), ParametersDT(b.mesh), StatesDT(b.mesh)
+    sbgd = a.states.copy()
+    smash_b200.forward_b(a.setup, a.mesh, a.input_data, a.parameters, pa, bgd_a, None, a.states, sa, sbgd, None, a.output, None)
+    oracle.forward_b(b.setup, b.mesh, b.input_data, b.parameters, pb, bgd_b, b.states, sb, sbgd, b.output)
+    assert float(b.output.cost_jreg) > 0
+    assert np.isclose(float(a.output.cost_jreg), float(b.output.cost_jreg), rtol=1e-5)
+    assert abs(float(a.output.cost) - float(b.output.cost)) < 1e-5 * max(1.0, abs(float(b.output.cost)))
+    check_grad(pa, pb, ("cp", "cft", "exc", "lr"))
+    check_grad(sa, sb, ("hp", "hft", "hlr"))
+    # parameters / states come back denormalised (forward_db.f90:10697-10703)
+    assert np.allclose(a.parameters.cp, b.parameters.cp, rtol=1e-6)
+    # the plain forward with the same setting: cost identical, round-trip of the controls as in compute_cost
+    (a, bgd_a), (b, bgd_b) = make(), make()
+    smash_b200.forward(a.setup, a.mesh, a.input_data, a.parameters, bgd_a, a.states, sbgd, a.output)
+    oracle.forward(b.setup, b.mesh, b.input_data, b.parameters, bgd_b, b.states, sbgd, b.output)
+    assert abs(float(a.output.cost) - float(b.output.cost)) < 1e-5 * max(1.0, abs(float(b.output.cost)))
+    assert np.array_equal(a.parameters.cft, b.parameters.cft)
+
+
+def with_gaps(T=360, frac=0.02):
+    m = cases.cance(sparse=True, T=T)
+    prcp, pet = cases.synthetic_forcing(m.mesh.nac, T, seed=3, gap_fraction=frac)
+    pet = np.array(pet, order="F")
+    pet[::7, 5::50] = -99.0                         # PET gaps too (md_forward_structure.f90:106)
+    m.input_data.sparse_prcp, m.input_data.sparse_pet = np.asfortranarray(prcp), pet
+    random_fields(m)
+    return m
+
+
+def test_forcing_gaps_forward_and_gradient():
+    a, b = with_gaps(), with_gaps()
+    assert (a.input_data.sparse_prcp < 0).any()
+    smash_b200.forward(a.setup, a.mesh, a.input_data, a.parameters, a.parameters.copy(), a.states, a.states.copy(), a.output)
+    oracle.forward(b.setup, b.mesh, b.input_data, b.parameters, b.parameters.copy(), b.states, b.states.copy(), b.output)
+    assert close_q(a.output.qsim, b.output.qsim)
+    pa, sa, pb, sb = ParametersDT(a.mesh), StatesDT(a.mesh), ParametersDT(b.mesh), StatesDT(b.mesh)
+    smash_b200.forward_b(a.setup, a.mesh, a.input_data, a.parameters, pa, a.parameters.copy(), None, a.states, sa, a.states.copy(),
+                         None, a.output, None)
+    oracle.forward_b(b.setup, b.mesh, b.input_data, b.parameters, pb, b.parameters.copy(), b.states, sb, b.states.copy(), b.output)
+    check_grad(pa, pb, ("cp", "cft", "exc", "lr"))
+    check_grad(sa, sb, ("hp", "hft", "hlr"))
+
+
+@pytest.mark.parametrize("sparse", [False, True])
+def test_domain_outputs(sparse):
+    def make():
+        m = cases.cance(sparse=sparse, T=96)
+        m.setup.save_qsim_domain = True
+        m.setup.save_net_prcp_domain = True
+        from smash_b200.solver._derived_types import OutputDT
+        m.output = OutputDT(m.setup, m.mesh)
+        return m
+    a, b = make(), make()
+    smash_b200.forward(a.setup, a.mesh, a.input_data, a.parameters, a.parameters.copy(), a.states, a.states.copy(), a.output)
+    oracle.forward(b.setup, b.mesh, b.input_data, b.parameters, b.parameters.copy(), b.states, b.states.copy(), b.output)
+    for name in (("sparse_qsim_domain", "sparse_net_prcp_domain") if sparse else ("qsim_domain", "net_prcp_domain")):
+        x, y = getattr(a.output, name), getattr(b.output, name)
+        assert x.shape == y.shape
+        assert close_q(x, y), name
+    if not sparse:   # inactive cells keep the -99 fill (mwd_output.f90:80-100), gauges read the domain discharge
+        assert np.all(a.output.qsim_domain[a.mesh.active_cell == 0] == -99.0)
+        g = a.mesh.gauge_pos
+        assert np.array_equal(a.output.qsim_domain[g[0, 0], g[0, 1], :], a.output.qsim[0])
+
+
+def test_multiple_run_chunked_equals_single_launch(golden):
+    m = cases.cance(T=240)
+    rng = np.random.RandomState(1)
+    ns = 37
+    smp = np.asfortranarray(np.stack([rng.uniform(lo, hi, ns) for lo, hi in [(1, 1e3), (1, 1e3), (-50, 50), (1, 1e3)]]).astype(np.float32))
+    out = []
+    for budget in (16384, 1):            # 1 MB per launch forces several chunks
+        L.lib().smash_b200_set_option(b"member_budget_mb", budget)
+        cost = np.zeros(ns, np.float32)
+        qsim = np.zeros((3, 240, ns), np.float32, order="F")
+        smash_b200.compute_multiple_run(m.setup, m.mesh, m.input_data, m.parameters, m.states, m.output, smp,
+                                        cases.IND_CP_CFT_EXC_LR, cost, qsim)
+        out.append((cost.copy(), qsim.copy()))
+    L.lib().smash_b200_set_option(b"member_budget_mb", 16384)
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    # a member equals a plain forward run with the same uniform parameters (test_simu.py:57-73)
+    k = 5
+    f = m.copy()
+    for j, n in enumerate(("cp", "cft", "exc", "lr")):
+        getattr(f.parameters, n)[...] = smp[j, k]
+    smash_b200.forward(f.setup, f.mesh, f.input_data, f.parameters, f.parameters.copy(), f.states, f.states.copy(), f.output)
+    assert np.array_equal(f.output.qsim, out[0][1][:, :, k])
+    assert np.isclose(float(f.output.cost), out[0][0][k], rtol=1e-6)
+
+
+def test_france_window_gradient():
+    # 300x300 window of the France mesh (387 blocks, cross-block flags in both sweeps), 4 synthetic gauges on the
+    # largest rivers, NSE with equal gauge weights
+    def make():
+        m = cases.france(T=96, sub=(400, 700, 400, 700), ngauge=4)
+        m.setup.save_qsim_domain = False
+        random_fields(m, seed=2)
+        return m
+    a, b = make(), make()
+    pa, sa, pb, sb = ParametersDT(a.mesh), StatesDT(a.mesh), ParametersDT(b.mesh), StatesDT(b.mesh)
+    smash_b200.forward_b(a.setup, a.mesh, a.input_data, a.parameters, pa, a.parameters.copy(), None, a.states, sa, a.states.copy(),
+                         None, a.output, None)
+    oracle.forward_b(b.setup, b.mesh, b.input_data, b.parameters, pb, b.parameters.copy(), b.states, sb, b.states.copy(), b.output)
+    assert close_q(a.output.qsim, b.output.qsim)
+    assert np.isclose(float(a.output.cost), float(b.output.cost), rtol=5e-4)
+    check_grad(pa, pb, ("cp", "cft", "exc", "lr"))
+    check_grad(sa, sb, ("hp", "hft", "hlr"))
+
+
+def test_france_full_gradient_pit_pairs_checksum():
+    # whole France mesh (906 044 cells, 50 pit pairs): forward+adjoint against the oracle on 24 steps, 3 gauges
+    def make():
+        m = cases.france(T=24, ngauge=3)
+        m.setup.save_qsim_domain = False
+        return m
+    a, b = make(), make()
+    pa, sa, pb, sb = ParametersDT(a.mesh), StatesDT(a.mesh), ParametersDT(b.mesh), StatesDT(b.mesh)
+    smash_b200.forward_b(a.setup, a.mesh, a.input_data, a.parameters, pa, a.parameters.copy(), None, a.states, sa, a.states.copy(),
+                         None, a.output, None)
+    oracle.forward_b(b.setup, b.mesh, b.input_data, b.parameters, pb, b.parameters.copy(), b.states, sb, b.states.copy(), b.output)
+    assert close_q(a.output.qsim, b.output.qsim)
+    # over 24 steps the transfer-store fields (cft, hft) have no measurable influence (gradient ~1e-10, pure rounding
+    # noise in any float32 implementation): only the well-conditioned fields are compared
+    check_grad(pa, pb, ("cp", "lr"))
+    check_grad(sa, sb, ("hp", "hlr"))
+    inactive = a.mesh.active_cell == 0
+    assert not np.any(pa.cp[inactive])
+
+
+def test_linearity_of_gradient_in_cost_b():
+    # forward_b is linear in the seed cost_b (BASE_FORWARD_B): doubling the seed doubles the gradient
+    m = cases.cance(T=240)
+    random_fields(m)
+    g = []
+    for seed in (1.0, 2.0):
+        c = m.copy()
+        pb, sb = ParametersDT(m.mesh), StatesDT(m.mesh)
+        smash_b200.forward_b(c.setup, c.mesh, c.input_data, c.parameters, pb, c.parameters.copy(), None, c.states, sb,
+                             c.states.copy(), None, c.output, None, 0.0, seed)
+        g.append(pb.cp.copy())
+    assert np.allclose(2.0 * g[0], g[1], rtol=1e-5, atol=1e-12)
+
+
+def test_run_to_run_determinism():
+    a, b = cases.cance(T=240), cases.cance(T=240)
+    for m in (a, b):
+        smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
+    assert np.array_equal(a.output.qsim, b.output.qsim)
