@@ -27,6 +27,18 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(bar_addr), "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -95,7 +107,9 @@ template <int FAST> __device__ __forceinline__ float ftanh(float x) {
     }
     return tanhf(x);
 }
-__device__ __forceinline__ float fsqrt_fast(float x) { return x * rsqrtf(x); }   // x > 0
+__device__ __forceinline__ float mufu_rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float fsqrt_fast(float x) { return x * mufu_rsq(x); }   // x > 0, normal range
 
 struct CellConst {
     float cp, inv_cp, cft, inv_cft, cft_m4, exc, lr, E, fa1, den;  // den = 0.001*dx*dx*(flwacc-1)
@@ -206,7 +220,7 @@ __device__ __forceinline__ float vertical_step_nogap(const CellConst &k, float p
     }
     const float num = (wet ? k.cp * (1.0f - hp * hp) : (hp * k.cp) * (2.0f - hp)) * th;     // md_gr_operator.f90:52,55
     const float den = fmaf(wet ? hp : 1.0f - hp, th, 1.0f);
-    const float r = __fdividef(num, den);
+    const float r = num * mufu_rcp(den);
     const float hp_imd = hp + (wet ? r : -r) * k.inv_cp;                 // :58
     const float pr = wet ? pn - (hp_imd - hp) * k.cp : 0.0f;             // :60-62
     float perc = 0.0f;
@@ -221,11 +235,18 @@ __device__ __forceinline__ float vertical_step_nogap(const CellConst &k, float p
     const float u = fmaxf(1.e-6f, fmaf(prr, k.inv_cft, hft));            // md_gr_operator.f90:102
     const float z = pow4(u);
     const float s2 = fsqrt_fast(1.0f + z), s1 = fsqrt_fast(s2);
-    const float g = __fdividef(z, s1 * (s1 + 1.0f) * (s2 + 1.0f));       // 1 - (1+u^4)^(-1/4), cancellation-free (:104)
+    const float g = z * mufu_rcp(s1 * (s1 + 1.0f) * (s2 + 1.0f));        // 1 - (1+u^4)^(-1/4), cancellation-free (:104)
     const float rel = u * g;
     hft = u - rel;
     return fmaf(rel, k.cft, fmaxf(0.0f, prd + l));                       // qt = qr + qd (:106, md_forward_structure.f90:142-144)
 }
+
+// Time is processed in chunks of CHF ticks.  Phase V of a chunk runs the reservoir arithmetic of every lane for
+// the chunk's ticks with NO block-wide synchronisation (it has no inter-cell dependency, md_forward_structure.f90:106-144)
+// and parks qt in shared memory; phase R then routes the chunk tick by tick (cheap: a few loads, one FMA chain and one
+// __syncthreads per tick).  Warps therefore only wait for each other on the cheap part.
+constexpr int CHF = 8;                 // ticks per chunk, forward
+constexpr int FRING = 2 * CHF;         // forcing rows resident per CTA (two chunks)
 
 template <int FAST, int TAPE>
 __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
@@ -233,15 +254,16 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
     const DeviceTopology &tp = a.tp;
     const int B = tp.B;
     const int tid = threadIdx.x;
-    float *ring = reinterpret_cast<float *>(smem_raw);                 // [RING_STAGES][2][B]
-    float *qx = ring + RING_STAGES * 2 * B;                            // [2][B + QX_PAD]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(qx + 2 * (B + QX_PAD));   // [RING_STAGES]
-    __shared__ unsigned int s_ticket;
     const int QS = B + QX_PAD;
+    float *ring = reinterpret_cast<float *>(smem_raw);                 // [FRING][2][B]
+    float *qts = ring + FRING * 2 * B;                                 // [CHF][B]  qt of the current chunk
+    float *qx = qts + CHF * B;                                         // [2][B + QX_PAD]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(qx + 2 * QS);        // [FRING]
+    __shared__ unsigned int s_ticket;
 
     if (tid == 0) {
         s_ticket = atomicAdd(a.ticket, 1u);
-        for (int s = 0; s < RING_STAGES; s++) mbar_init(&bars[s], 1);
+        for (int s = 0; s < FRING; s++) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 2 * QS; i += B) qx[i] = 0.0f;
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
     const uint32_t row_bytes = 2u * B * sizeof(float);
 
     if (tid == 0) {
-        for (int s = 0; s < RING_STAGES && s < nticks; s++) {
+        for (int s = 0; s < FRING && s < nticks; s++) {
             mbar_expect_tx(&bars[s], row_bytes);
             tma_load_1d(ring + (size_t)s * 2 * B, frc + (size_t)s * 2 * B, row_bytes, &bars[s]);
         }
@@ -279,16 +301,21 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
                        fld[(size_t)F_LR * tp.nslots], fa, a.dt, a.dx);
         hp = fld[(size_t)F_HP * tp.nslots]; hft = fld[(size_t)F_HFT * tp.nslots]; hlr = fld[(size_t)F_HLR * tp.nslots];
     }
-    // inflow lanes of the common case (<= 3 in-block producers, none in another block, not a pit-pair member):
-    // absent entries point at the zero slot B, so the sum keeps the reference's order without branches
-    int u0 = B, u1 = B, u2 = B;
-    bool simple = !late && (ue - ub) <= 3;
+    // inflow lanes of the common case (<= 6 in-block producers, none in another block, not a pit-pair member), as byte
+    // offsets into the exchange buffer: absent entries point at the zero slot B, so the sum keeps the reference's
+    // order (i = 1..8, md_routing_operator.f90:37-53) without branches
+    int u0 = B * 4, u1 = B * 4, u2 = B * 4, u3 = B * 4, u4 = B * 4, u5 = B * 4;
+    bool simple = !late && (ue - ub) <= 6;
     for (int e = ub; e < ue; e++) if (tp.up[e].a < 0 || tp.up[e].cur) simple = false;
     if (simple) {
-        if (ue - ub > 0) u0 = tp.up[ub].a;
-        if (ue - ub > 1) u1 = tp.up[ub + 1].a;
-        if (ue - ub > 2) u2 = tp.up[ub + 2].a;
+        if (ue - ub > 0) u0 = tp.up[ub].a * 4;
+        if (ue - ub > 1) u1 = tp.up[ub + 1].a * 4;
+        if (ue - ub > 2) u2 = tp.up[ub + 2].a * 4;
+        if (ue - ub > 3) u3 = tp.up[ub + 3].a * 4;
+        if (ue - ub > 4) u4 = tp.up[ub + 4].a * 4;
+        if (ue - ub > 5) u5 = tp.up[ub + 5].a * 4;
     }
+    const bool many = (ue - ub) > 3;
     const float c_dx = a.dx, c_dt = a.dt;
     const int T = tp.T, ng = tp.ng;
     float *qdom = a.qdom ? a.qdom + ((size_t)member * tp.total_ticks + row0) * B + tid : nullptr;
@@ -299,107 +326,145 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
     int *prog_mine = a.prog + (size_t)member * tp.nblocks + blk;
     const bool do_flag = bf & BLK_PUBLISH;
 
-    int stage = 0;
     uint32_t parity = 0;
+    const bool do_net = netp != nullptr;
+    float *qbuf0 = qx, *qbuf1 = qx + QS;       // qbuf0 = buffer written at even ticks
 #pragma unroll 1
-    for (int d = 0; d < nticks; d++) {
-        mbar_wait(&bars[stage], parity);
-        const float prcp = ring[stage * 2 * B + tid];
-        const float pet = ring[stage * 2 * B + B + tid];
-        const int t = d - off;
-        const bool act = valid && (unsigned)t < (unsigned)T;
-        const float *qprev = qx + ((d & 1) ^ 1) * QS;
-        float *qcur = qx + (d & 1) * QS;
-        float q = 0.0f, qt;
-        float xv[8];
-        if (!simple && act) {
-            // cross-block inflows first: their latency hides behind the reservoir arithmetic
-            int nx = 0;
-            for (int e = ub; e < ue; e++) {
-                const int ea = tp.up[e].a;
-                if (ea < 0) {
-                    const ExtRef x = tp.ext[-ea - 1];
-                    float v = 0.0f;
-                    if (t - x.lag >= 0) {
-                        const int need = d + x.dtick + 1;
-                        while (ld_acquire(prog_m + x.blk) < need) __nanosleep(40);
-                        v = __ldcg(a.qdom + (size_t)member * tp.total_ticks * B + x.base + (int64_t)d * B);
+    for (int d0 = 0; d0 < nticks; d0 += CHF) {
+        const int nd = min(CHF, nticks - d0);
+        const int sbase = d0 % FRING;           // d0 is a multiple of CHF and FRING = 2*CHF: 0 or CHF
+        // ---------------- phase V: reservoirs, no block synchronisation
+        {
+            const float *rp = ring + (size_t)sbase * 2 * B + tid;
+            float *qp = qts + tid;
+            float *tv = tape;
+            uint32_t bar_addr = smem_u32(&bars[sbase]);
+            int t = d0 - off;
+#pragma unroll 1
+            for (int i = 0; i < nd; i++) {
+                mbar_wait_addr(bar_addr, parity);
+                const float prcp = rp[0];
+                const float pet = rp[B];
+                const bool act = valid && (unsigned)t < (unsigned)T;
+                if (TAPE && act) { tv[0] = hp; tv[B] = hft; }
+                float hp_n = hp, hft_n = hft, qt;
+                const bool gapless = (prcp >= 0.0f) && (pet >= 0.0f);
+                if (FAST && __all_sync(0xffffffffu, gapless)) qt = vertical_step_nogap(k, prcp, pet, hp_n, hft_n);
+                else qt = vertical_step<FAST>(k, prcp, pet, hp_n, hft_n).qt;
+                if (act) { hp = hp_n; hft = hft_n; }
+                qp[0] = qt;
+                rp += 2 * B; qp += B; bar_addr += 8; t++;
+                if (TAPE) tv += 4 * B;
+            }
+        }
+        // ---------------- phase R: routing, one barrier per tick
+        {
+            const float *qp = qts + tid;
+            float *tr = tape;
+            float *qd = qdom, *np_ = netp;
+            int t = d0 - off;
+#pragma unroll 1
+            for (int i = 0; i < nd; i++) {
+                const int d = d0 + i;
+                const bool act = valid && (unsigned)t < (unsigned)T;
+                const float *qprev = (d & 1) ? qbuf0 : qbuf1;
+                float *qcur = (d & 1) ? qbuf1 : qbuf0;
+                const float qt = qp[0];
+                float q = 0.0f, qup = 0.0f;
+                float xv[8];
+                if (simple) {
+                    const char *qb = reinterpret_cast<const char *>(qprev);
+                    qup = (*reinterpret_cast<const float *>(qb + u0) + *reinterpret_cast<const float *>(qb + u1)) +
+                          *reinterpret_cast<const float *>(qb + u2);          // upstream_discharge md_routing_operator.f90:37-53
+                    if (many)
+                        qup = ((qup + *reinterpret_cast<const float *>(qb + u3)) + *reinterpret_cast<const float *>(qb + u4)) +
+                              *reinterpret_cast<const float *>(qb + u5);
+                } else if (act) {
+                    int nx = 0;
+                    for (int e = ub; e < ue; e++) {                          // cross-block inflows (progress flags in HBM)
+                        const int ea = tp.up[e].a;
+                        if (ea < 0) {
+                            const ExtRef x = tp.ext[-ea - 1];
+                            float v = 0.0f;
+                            if (t - x.lag >= 0) {
+                                const int need = d + x.dtick + 1;
+                                while (ld_acquire(prog_m + x.blk) < need) __nanosleep(40);
+                                v = __ldcg(a.qdom + (size_t)member * tp.total_ticks * B + x.base + (int64_t)d * B);
+                            }
+                            xv[nx & 7] = v;
+                            nx++;
+                        }
                     }
-                    xv[nx & 7] = v;
-                    nx++;
+                    if (!late) {
+                        int jx = 0;
+                        for (int e = ub; e < ue; e++) {
+                            const int ea = tp.up[e].a;
+                            qup = qup + (ea >= 0 ? qprev[ea] : xv[(jx++) & 7]);
+                        }
+                    }
                 }
-            }
-        }
-        if (TAPE && act) { tape[0] = hp; tape[B] = hft; tape[2 * B] = hlr; }
-        float hp_n = hp, hft_n = hft;
-        const bool gapless = (prcp >= 0.0f) && (pet >= 0.0f);
-        if (FAST && __all_sync(0xffffffffu, gapless)) {
-            qt = vertical_step_nogap(k, prcp, pet, hp_n, hft_n);
-        } else {
-            qt = vertical_step<FAST>(k, prcp, pet, hp_n, hft_n).qt;
-        }
-        if (act) { hp = hp_n; hft = hft_n; }
-        float qup = 0.0f;
-        if (simple) {
-            qup = (qprev[u0] + qprev[u1]) + qprev[u2];               // upstream_discharge md_routing_operator.f90:37-53
-        } else if (!late) {
-            int jx = 0;
-            for (int e = ub; e < ue; e++) {
-                const int ea = tp.up[e].a;
-                qup = qup + (ea >= 0 ? qprev[ea] : xv[(jx++) & 7]);
-            }
-        }
-        if (!late) {
-            qup = FAST ? qup * k.s_q : ((fa > 1) ? (qup * c_dt) / k.den : 0.0f);    // :55-56
-            // linear_routing md_routing_operator.f90:62-79
-            const float hr_imd = hlr + qup;
-            const float hlr_n = hr_imd * k.E;
-            const float qrout = hr_imd - hlr_n;
-            q = FAST ? fmaf(qrout, k.fa1, qt) * k.c0
-                     : (qt + qrout * k.fa1) * c_dx * c_dx * 0.001f / c_dt;          // md_forward_structure.f90:155
-            if (act) {
-                hlr = hlr_n;
-                qcur[tid] = q;
-                if (TAPE) tape[3 * B] = qup;
-            }
-        }
-        if (has_late) {
-            __syncthreads();
-            if (act && late) {
-                qup = 0.0f;
-                int jx = 0;
-                for (int e = ub; e < ue; e++) {
-                    const UpEntry u = tp.up[e];
-                    qup = qup + (u.a >= 0 ? (u.cur ? qcur : qprev)[u.a] : xv[(jx++) & 7]);
+                if (!late) {
+                    qup = FAST ? qup * k.s_q : ((fa > 1) ? (qup * c_dt) / k.den : 0.0f);    // :55-56
+                    // linear_routing md_routing_operator.f90:62-79
+                    const float hr_imd = hlr + qup;
+                    const float hlr_n = hr_imd * k.E;
+                    const float qrout = hr_imd - hlr_n;
+                    q = FAST ? fmaf(qrout, k.fa1, qt) * k.c0
+                             : (qt + qrout * k.fa1) * c_dx * c_dx * 0.001f / c_dt;          // md_forward_structure.f90:155
+                    if (act) {
+                        if (TAPE) { tr[2 * B] = hlr; tr[3 * B] = qup; }
+                        hlr = hlr_n;
+                        qcur[tid] = q;
+                    }
                 }
-                qup = FAST ? qup * k.s_q : (qup * c_dt) / k.den;
-                if (TAPE) tape[3 * B] = qup;
-                const float hr_imd = hlr + qup;
-                hlr = hr_imd * k.E;
-                const float qrout = hr_imd - hlr;
-                q = FAST ? fmaf(qrout, k.fa1, qt) * k.c0 : (qt + qrout * k.fa1) * c_dx * c_dx * 0.001f / c_dt;
-                qcur[tid] = q;
+                if (has_late) {
+                    __syncthreads();
+                    if (act && late) {
+                        qup = 0.0f;
+                        int jx = 0;
+                        for (int e = ub; e < ue; e++) {
+                            const UpEntry u = tp.up[e];
+                            qup = qup + (u.a >= 0 ? (u.cur ? qcur : qprev)[u.a] : xv[(jx++) & 7]);
+                        }
+                        qup = FAST ? qup * k.s_q : (qup * c_dt) / k.den;
+                        if (TAPE) { tr[2 * B] = hlr; tr[3 * B] = qup; }
+                        const float hr_imd = hlr + qup;
+                        hlr = hr_imd * k.E;
+                        const float qrout = hr_imd - hlr;
+                        q = FAST ? fmaf(qrout, k.fa1, qt) * k.c0 : (qt + qrout * k.fa1) * c_dx * c_dx * 0.001f / c_dt;
+                        qcur[tid] = q;
+                    }
+                }
+                if (act) {
+                    if (publish) qd[0] = q;
+                    if (do_net) np_[0] = qt;
+                    if (gfirst >= 0)
+                        for (int g = gfirst; g >= 0; g = tp.gauge_next[g]) qsim[(size_t)t * ng + g] = q;   // :206-210
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    if (do_flag) { __threadfence(); st_release(prog_mine, d + 1); }
+                    if (i == 0) {
+                        // every thread is past phase V of this chunk: its forcing rows can be refilled for chunk + 2
+                        for (int r = 0; r < CHF; r++) {
+                            const int dn = d0 + FRING + r;
+                            if (dn < nticks) {
+                                mbar_expect_tx(&bars[sbase + r], row_bytes);
+                                tma_load_1d(ring + (size_t)(sbase + r) * 2 * B, frc + (size_t)dn * 2 * B, row_bytes, &bars[sbase + r]);
+                            }
+                        }
+                    }
+                }
+                qp += B; t++;
+                if (publish) qd += B;
+                if (do_net) np_ += B;
+                if (TAPE) tr += 4 * B;
             }
         }
-        if (act) {
-            if (publish) qdom[0] = q;
-            if (netp) netp[0] = qt;
-            if (gfirst >= 0)
-                for (int g = gfirst; g >= 0; g = tp.gauge_next[g]) qsim[(size_t)t * ng + g] = q;   // :206-210
-        }
-        if (publish) qdom += B;
-        if (netp) netp += B;
-        if (TAPE) tape += 4 * B;
-        __syncthreads();
-        if (tid == 0) {
-            if (do_flag) { __threadfence(); st_release(prog_mine, d + 1); }
-            const int dn = d + RING_STAGES;
-            if (dn < nticks) {
-                mbar_expect_tx(&bars[stage], row_bytes);
-                tma_load_1d(ring + (size_t)stage * 2 * B, frc + (size_t)dn * 2 * B, row_bytes, &bars[stage]);
-            }
-        }
-        if (++stage == RING_STAGES) { stage = 0; parity ^= 1u; }
+        if (publish) qdom += (size_t)CHF * B;
+        if (do_net) netp += (size_t)CHF * B;
+        if (TAPE) tape += (size_t)CHF * 4 * B;
+        if (sbase) parity ^= 1u;
     }
     if (valid) {
         float *fs = a.fstates + (size_t)member * 3 * tp.nslots + slot;
@@ -903,7 +968,7 @@ __global__ void checksum_kernel(DeviceTopology tp, const float *skewed, double *
 // ------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
-static size_t fwd_smem(int B) { return (size_t)((RING_STAGES * 2 + 2) * B + 2 * QX_PAD) * sizeof(float) + RING_STAGES * sizeof(uint64_t); }
+static size_t fwd_smem(int B) { return (size_t)((FRING * 2 + CHF + 2) * B + 2 * QX_PAD) * sizeof(float) + FRING * sizeof(uint64_t); }
 static size_t rev_smem(int B) { return (size_t)(RING_STAGES * 6 + 2) * B * sizeof(float) + RING_STAGES * sizeof(uint64_t); }
 
 template <typename K> static cudaError_t launch_solver(K kern, const SolverArgs &a, size_t smem, cudaStream_t s) {

@@ -9,7 +9,7 @@ from smash_b200 import _lib as L
 
 ap = argparse.ArgumentParser()
 ap.add_argument("mesh"); ap.add_argument("--T", type=int, default=None); ap.add_argument("--block", type=int, default=0)
-ap.add_argument("--math", type=int, default=0); ap.add_argument("--members", type=int, default=1)
+ap.add_argument("--math", type=int, default=1); ap.add_argument("--members", type=int, default=1)
 ap.add_argument("--grad", action="store_true"); ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--opt", action="append", default=[], help="name=value library option")
 a = ap.parse_args()
