@@ -216,6 +216,7 @@ static SolverArgs solver_args(SmashPlan &pl, bool save_q, bool save_netp, bool t
     SolverArgs a{};
     a.tp = pl.dtp; a.nmember = pl.nmember; a.dt = pl.dt; a.dx = pl.dx;
     a.save_q = save_q ? 1 : 0; a.save_netp = save_netp ? 1 : 0; a.tape_on = tape ? 1 : 0;
+    a.debug_nowait = (int)option("debug_nowait", 0);
     a.forcing = pl.d_forcing.p; a.fields = pl.d_fields.p; a.fstates = pl.d_fstates.p; a.qsim = pl.d_qsim.p;
     a.qdom = pl.d_qdom.p; a.netp = pl.d_netp.p; a.tape = pl.d_tape.p; a.prog = pl.d_prog.p; a.ticket = pl.d_ticket.p;
     a.qsim_b = pl.d_qsim_b.p; a.wdom = pl.d_wdom.p; a.grad = pl.d_grad.p; a.rprog = pl.d_rprog.p;
@@ -906,7 +907,7 @@ extern "C" int smash_b200_plan_run_forward(SmashPlan *plan, float *elapsed_ms) {
     if (!plan->have_forcing) return fail(SMASH_B200_EINVAL, "plan has no forcing");
     TRY(plan_cost_setup(plan));
     plan->launches = 0;
-    SolverArgs a = solver_args(*plan, plan->d_qdom.p != nullptr, false, false);
+    SolverArgs a = solver_args(*plan, plan->d_qdom.p != nullptr && !option("debug_nosave", 0), false, false);
     CU(cudaEventRecord(plan->ev0, plan->stream));
     CU(launch_forward(a, math_mode(), plan->stream));
     CU(cudaEventRecord(plan->ev1, plan->stream));

@@ -248,8 +248,9 @@ __device__ __forceinline__ float vertical_step_nogap(const CellConst &k, float p
 constexpr int CHF = 8;                 // ticks per chunk, forward
 constexpr int FRING = 2 * CHF;         // forcing rows resident per CTA (two chunks)
 
-template <int FAST, int TAPE>
-__global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
+// MULTI = 0: the mesh fits one block (small catchments, ensembles): no cross-block code at all.
+template <int FAST, int TAPE, int MULTI>
+__global__ void __launch_bounds__(512, 2) forward_kernel(const SolverArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const DeviceTopology &tp = a.tp;
     const int B = tp.B;
@@ -257,7 +258,9 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
     const int QS = B + QX_PAD;
     float *ring = reinterpret_cast<float *>(smem_raw);                 // [FRING][2][B]
     float *qts = ring + FRING * 2 * B;                                 // [CHF][B]  qt of the current chunk
-    float *qx = qts + CHF * B;                                         // [2][B + QX_PAD]
+    float *xq = qts + CHF * B;                                         // MULTI: [2][CHF][B] prefetched cross-block inflows
+    int *seen_s = reinterpret_cast<int *>(xq + (MULTI ? 2 * CHF * B : 0));   // MULTI: [2][B] cached producer progress
+    float *qx = reinterpret_cast<float *>(seen_s + (MULTI ? 2 * B : 0));     // [2][B + QX_PAD]
     uint64_t *bars = reinterpret_cast<uint64_t *>(qx + 2 * QS);        // [FRING]
     __shared__ unsigned int s_ticket;
 
@@ -267,6 +270,10 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 2 * QS; i += B) qx[i] = 0.0f;
+    if (MULTI) {
+        seen_s[tid] = 0; seen_s[B + tid] = 0;
+        for (int i = 0; i < 2 * CHF; i++) xq[i * B + tid] = 0.0f;
+    }
     __syncthreads();
     const int vb = (int)s_ticket;
     const int member = vb / tp.nblocks;
@@ -304,18 +311,36 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
     // inflow lanes of the common case (<= 6 in-block producers, none in another block, not a pit-pair member), as byte
     // offsets into the exchange buffer: absent entries point at the zero slot B, so the sum keeps the reference's
     // order (i = 1..8, md_routing_operator.f90:37-53) without branches
-    int u0 = B * 4, u1 = B * 4, u2 = B * 4, u3 = B * 4, u4 = B * 4, u5 = B * 4;
-    bool simple = !late && (ue - ub) <= 6;
-    for (int e = ub; e < ue; e++) if (tp.up[e].a < 0 || tp.up[e].cur) simple = false;
-    if (simple) {
-        if (ue - ub > 0) u0 = tp.up[ub].a * 4;
-        if (ue - ub > 1) u1 = tp.up[ub + 1].a * 4;
-        if (ue - ub > 2) u2 = tp.up[ub + 2].a * 4;
-        if (ue - ub > 3) u3 = tp.up[ub + 3].a * 4;
-        if (ue - ub > 4) u4 = tp.up[ub + 4].a * 4;
-        if (ue - ub > 5) u5 = tp.up[ub + 5].a * 4;
+    int u0 = B * 4, u1 = B * 4, u2 = B * 4;
+    unsigned ux = (unsigned)B | ((unsigned)B << 10) | ((unsigned)B << 20);   // entries 4..6, 10 bits each (B <= 512)
+    // One cross-block producer is folded into the fast path when it is the first or the last term of the sum (0 + x
+    // and commutativity keep the reference's result bit for bit); other patterns take the generic loop below.
+    int n_ext = 0, n_in = 0, xmode = 0;   // xmode: 0 none, 1 cross-block term first, 2 last
+    bool simple = !late;
+    {
+        unsigned lanes[6];
+        for (int e = ub; e < ue; e++) {
+            const UpEntry u = tp.up[e];
+            if (u.cur) simple = false;
+            if (u.a < 0) {
+                n_ext++;
+                if (e == ub) xmode = 1; else if (e == ue - 1) xmode = 2; else simple = false;
+            } else {
+                if (n_in < 6) lanes[n_in] = (unsigned)u.a;
+                n_in++;
+            }
+        }
+        if (n_in > 6 || n_ext > 1 || (!MULTI && n_ext > 0)) simple = false;
+        if (simple) {
+            if (n_in > 0) u0 = lanes[0] * 4;
+            if (n_in > 1) u1 = lanes[1] * 4;
+            if (n_in > 2) u2 = lanes[2] * 4;
+            const unsigned a3 = n_in > 3 ? lanes[3] : B, a4 = n_in > 4 ? lanes[4] : B, a5 = n_in > 5 ? lanes[5] : B;
+            ux = a3 | (a4 << 10) | (a5 << 20);
+        }
     }
-    const bool many = (ue - ub) > 3;
+    const bool many = n_in > 3;
+    const bool xfirst = simple && xmode == 1, xlast = simple && xmode == 2;
     const float c_dx = a.dx, c_dt = a.dt;
     const int T = tp.T, ng = tp.ng;
     float *qdom = a.qdom ? a.qdom + ((size_t)member * tp.total_ticks + row0) * B + tid : nullptr;
@@ -324,7 +349,7 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
     float *qsim = a.qsim + (size_t)member * tp.T * tp.ng;
     const int *prog_m = a.prog + (size_t)member * tp.nblocks;
     int *prog_mine = a.prog + (size_t)member * tp.nblocks + blk;
-    const bool do_flag = bf & BLK_PUBLISH;
+    const bool do_flag = MULTI && (bf & BLK_PUBLISH);
 
     uint32_t parity = 0;
     const bool do_net = netp != nullptr;
@@ -358,6 +383,31 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
             }
         }
         // ---------------- phase R: routing, one barrier per tick
+        if (MULTI && n_ext > 0 && valid) {
+            int j = 0;
+#pragma unroll 1
+            for (int e = ub; e < ue && j < 2; e++) {
+                if (tp.up[e].a >= 0) continue;
+                const ExtRef x = tp.ext[-tp.up[e].a - 1];
+                const int i_lo = max(0, off + x.lag - d0);            // first tick of the chunk with t - lag >= 0
+                const int i_hi = min(nd - 1, T - 1 + off - d0);       // last tick of the chunk with t <= T - 1
+                if (i_lo <= i_hi) {
+                    const int need = d0 + i_hi + x.dtick + 1;
+                    int seen = seen_s[j * B + tid];
+                    if (seen < need && !a.debug_nowait) {
+                        do {
+                            seen = ld_acquire(prog_m + x.blk);
+                            if (seen < need) __nanosleep(100);
+                        } while (seen < need);
+                        seen_s[j * B + tid] = seen;
+                    }
+                }
+                const float *src = a.qdom + (size_t)member * tp.total_ticks * B + x.base + (int64_t)d0 * B;
+                for (int i = 0; i < nd; i++)
+                    xq[(j * CHF + i) * B + tid] = (i >= i_lo && i <= i_hi) ? __ldcg(src + (size_t)i * B) : 0.0f;
+                j++;
+            }
+        }
         {
             const float *qp = qts + tid;
             float *tr = tape;
@@ -374,22 +424,28 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
                 float xv[8];
                 if (simple) {
                     const char *qb = reinterpret_cast<const char *>(qprev);
-                    qup = (*reinterpret_cast<const float *>(qb + u0) + *reinterpret_cast<const float *>(qb + u1)) +
+                    const float xval = MULTI ? xq[i * B + tid] : 0.0f;      // prefetched cross-block inflow (0 if none)
+                    qup = ((((MULTI && xfirst) ? xval : 0.0f) + *reinterpret_cast<const float *>(qb + u0)) +
+                           *reinterpret_cast<const float *>(qb + u1)) +
                           *reinterpret_cast<const float *>(qb + u2);          // upstream_discharge md_routing_operator.f90:37-53
                     if (many)
-                        qup = ((qup + *reinterpret_cast<const float *>(qb + u3)) + *reinterpret_cast<const float *>(qb + u4)) +
-                              *reinterpret_cast<const float *>(qb + u5);
+                        qup = ((qup + qprev[ux & 1023u]) + qprev[(ux >> 10) & 1023u]) + qprev[ux >> 20];
+                    if (MULTI && xlast) qup = qup + xval;
                 } else if (act) {
                     int nx = 0;
-                    for (int e = ub; e < ue; e++) {                          // cross-block inflows (progress flags in HBM)
+                    for (int e = ub; e < ue; e++) {                          // cross-block inflows
                         const int ea = tp.up[e].a;
                         if (ea < 0) {
-                            const ExtRef x = tp.ext[-ea - 1];
-                            float v = 0.0f;
-                            if (t - x.lag >= 0) {
-                                const int need = d + x.dtick + 1;
-                                while (ld_acquire(prog_m + x.blk) < need) __nanosleep(40);
-                                v = __ldcg(a.qdom + (size_t)member * tp.total_ticks * B + x.base + (int64_t)d * B);
+                            float v;
+                            if (nx < 2) v = xq[(nx * CHF + i) * B + tid];    // prefetched at the start of phase R
+                            else {                                          // rare: third and later producer, read per tick
+                                const ExtRef x = tp.ext[-ea - 1];
+                                v = 0.0f;
+                                if (t - x.lag >= 0) {
+                                    const int need = d + x.dtick + 1;
+                                    while (ld_acquire(prog_m + x.blk) < need) __nanosleep(40);
+                                    v = __ldcg(a.qdom + (size_t)member * tp.total_ticks * B + x.base + (int64_t)d * B);
+                                }
                             }
                             xv[nx & 7] = v;
                             nx++;
@@ -443,7 +499,7 @@ __global__ void __launch_bounds__(1024) forward_kernel(const SolverArgs a) {
                 }
                 __syncthreads();
                 if (tid == 0) {
-                    if (do_flag) { __threadfence(); st_release(prog_mine, d + 1); }
+                    if (do_flag && i == nd - 1) { __threadfence(); st_release(prog_mine, d + 1); }   // one release per chunk
                     if (i == 0) {
                         // every thread is past phase V of this chunk: its forcing rows can be refilled for chunk + 2
                         for (int r = 0; r < CHF; r++) {
@@ -968,7 +1024,7 @@ __global__ void checksum_kernel(DeviceTopology tp, const float *skewed, double *
 // ------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
-static size_t fwd_smem(int B) { return (size_t)((FRING * 2 + CHF + 2) * B + 2 * QX_PAD) * sizeof(float) + FRING * sizeof(uint64_t); }
+static size_t fwd_smem(int B, bool multi) { return (size_t)((FRING * 2 + CHF + 2 + (multi ? 2 * CHF + 2 : 0)) * B + 2 * QX_PAD) * sizeof(float) + FRING * sizeof(uint64_t); }
 static size_t rev_smem(int B) { return (size_t)(RING_STAGES * 6 + 2) * B * sizeof(float) + RING_STAGES * sizeof(uint64_t); }
 
 template <typename K> static cudaError_t launch_solver(K kern, const SolverArgs &a, size_t smem, cudaStream_t s) {
@@ -984,9 +1040,14 @@ template <typename K> static cudaError_t launch_solver(K kern, const SolverArgs 
 cudaError_t launch_forward(const SolverArgs &a, int math_mode, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(a.prog, 0, sizeof(int) * (size_t)a.tp.nblocks * a.nmember, s);
     if (e != cudaSuccess) return e;
-    const size_t smem = fwd_smem(a.tp.B);
-    if (a.tape_on) return math_mode ? launch_solver(forward_kernel<1, 1>, a, smem, s) : launch_solver(forward_kernel<0, 1>, a, smem, s);
-    return math_mode ? launch_solver(forward_kernel<1, 0>, a, smem, s) : launch_solver(forward_kernel<0, 0>, a, smem, s);
+    const bool multi = a.tp.nblocks > 1;
+    const size_t smem = fwd_smem(a.tp.B, multi);
+    if (multi) {
+        if (a.tape_on) return math_mode ? launch_solver(forward_kernel<1, 1, 1>, a, smem, s) : launch_solver(forward_kernel<0, 1, 1>, a, smem, s);
+        return math_mode ? launch_solver(forward_kernel<1, 0, 1>, a, smem, s) : launch_solver(forward_kernel<0, 0, 1>, a, smem, s);
+    }
+    if (a.tape_on) return math_mode ? launch_solver(forward_kernel<1, 1, 0>, a, smem, s) : launch_solver(forward_kernel<0, 1, 0>, a, smem, s);
+    return math_mode ? launch_solver(forward_kernel<1, 0, 0>, a, smem, s) : launch_solver(forward_kernel<0, 0, 0>, a, smem, s);
 }
 
 cudaError_t launch_reverse(const SolverArgs &a, int math_mode, cudaStream_t s) {

@@ -32,6 +32,7 @@ struct SolverArgs {
     int nmember;
     float dt, dx;
     int save_q, save_netp, tape_on;
+    int debug_nowait;       // timing experiments only: skip the cross-block progress waits (results are then wrong)
     const float *forcing;   // [tick_base[b] + d][2][B]   (shared by all members)
     const float *fields;    // [m][NFIELD][nslots]
     float *fstates;         // [m][3][nslots]

@@ -38,7 +38,7 @@ std::string build_topology(Topology &tp, int nrow, int ncol, int ng, int T, cons
                            const int32_t *path, const int32_t *gauge_pos, int block_size) {
     const int ncell = nrow * ncol;
     if (nrow <= 0 || ncol <= 0 || T <= 0) return "mesh: nrow, ncol and ntime_step must be positive";
-    if (block_size < 32 || block_size > 1024 || block_size % 32) return "block size must be a multiple of 32 in [32,1024]";
+    if (block_size < 32 || block_size > 512 || block_size % 32) return "block size must be a multiple of 32 in [32,512]";
     tp = Topology();
     tp.nrow = nrow; tp.ncol = ncol; tp.ng = ng; tp.T = T; tp.B = block_size;
     const int B = block_size;
