@@ -195,6 +195,18 @@ int smash_b200_plan_order(const SmashPlan *plan, int32_t *order, int32_t *block_
 int smash_b200_mesh_order(const SmashSetup *setup, const SmashMesh *mesh, int32_t block, int64_t info[12],
                           int32_t *order, int32_t *block_of, int32_t *offset_of);
 
+/* Heavy-path decomposition used by the split engine (reservoir pass per cell + routing pass per chain), computed on
+ * the host only.  Cells are numbered j = 0..n-1 in `path` order (md_forward_structure.f90:82-92).
+ *   info[0] n computed cells, [1] chains, [2] pit pairs, [3] largest dependency height of a chain, [4] longest chain,
+ *   [5] longest dependency path in cells, [6] source cells (flwacc == 1), [7] 1 if sparse arrays are usable in place
+ *   cell[j]      flat rect index row + col*nrow of cell j                                    (n entries)
+ *   task_of[j]   task (chain or pair, execution order) that routes cell j, -1 for lone source cells
+ *   pos_of[j]    position of the cell inside its task, upstream -> downstream
+ *   down_of[j]   cell that gathers j in upstream_discharge (md_routing_operator.f90:37-53), -1 if none
+ * Returns SMASH_B200_EUNSUPPORTED when the mesh needs the fused engine. */
+int smash_b200_mesh_chains(const SmashMesh *mesh, int64_t info[8], int32_t *cell, int32_t *task_of, int32_t *pos_of,
+                           int32_t *down_of);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,7 +77,7 @@ EXPORTS = [
     "smash_b200_plan_destroy", "smash_b200_plan_set_forcing", "smash_b200_plan_set_fields",
     "smash_b200_plan_run_forward", "smash_b200_plan_run_gradient", "smash_b200_plan_get_qsim",
     "smash_b200_plan_get_gradient", "smash_b200_plan_checksum", "smash_b200_plan_info", "smash_b200_plan_order",
-    "smash_b200_mesh_order",
+    "smash_b200_mesh_order", "smash_b200_mesh_chains",
 ]
 
 _lib = None

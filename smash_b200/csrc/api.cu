@@ -17,6 +17,8 @@
 
 #include "../../include/smash_b200.h"
 #include "kernels.cuh"
+#include "route_graph.hpp"
+#include "split_kernels.cuh"
 #include "topology.hpp"
 
 using namespace smash;
@@ -83,9 +85,31 @@ template <typename T> struct DBuf {
     }
 };
 
+// state of the split engine (split_kernels.cuh): route graph on the device, row / tape buffers, tensor maps
+struct SplitState {
+    RouteGraph rg;
+    int S = 0, W = 0, nwin = 0, Tp = 0;
+    int64_t qpitch = 0;
+    DBuf<int32_t> d_flwacc, d_up_begin, d_down, d_down_task, d_task_begin, d_task_cells, d_gfirst, d_gnext;
+    DBuf<RouteUp> d_up, d_tup;
+    DBuf<TaskCell> d_tcell;
+    DBuf<uint8_t> d_down_lag;
+    DBuf<float> d_pk_prcp, d_pk_pet, d_rows, d_rows_hr, d_rows_w, d_tape_hp, d_tape_hft, d_hcar, d_gcar;
+    DBuf<int> d_done, d_rdone;
+    CUtensorMap tm_prcp, tm_pet, tm_hp, tm_hft;
+    const float *tape_mapped = nullptr;
+    size_t tape_rows = 0;
+    SplitTopo topo{};
+};
+
 struct SmashPlan {
     Topology tp;
     DeviceTopology dtp{};
+    int engine = 0;                 // 0: fused tick wavefront (kernels.cu), 1: split reservoirs / routing (split_kernels.cu)
+    int sparse = 0;                 // setup.sparse_storage the plan was built for
+    SplitState sp;
+    std::vector<int32_t> col_cell;  // per device column (slot / cell j): flat rect index or -1 on padding
+    int ncols = 0;                  // columns of the per-cell device arrays (fields, fstates, grad)
     int nmember = 0;
     float dt = 0, dx = 0;
     int ncell = 0;
@@ -141,7 +165,19 @@ static int pick_block(int nactive) {
     return 256;
 }
 
-static int plan_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, int nmember) {
+static int math_mode();
+
+// engine option: -1 (default) picks the split engine whenever the mesh supports it and the fast math mode is on
+static int pick_engine(int want) {
+    const long long o = option("engine", -1);
+    if (o >= 0) return (int)o;
+    if (want >= 0) return want;
+    return math_mode() ? 1 : 0;
+}
+
+static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, bool *unsupported);
+
+static int plan_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, int nmember, int engine = -1) {
     if (!setup || !mesh) return fail(SMASH_B200_EINVAL, "setup / mesh is NULL");
     if (setup->structure != SMASH_STRUCTURE_GR_A)
         return fail(SMASH_B200_EUNSUPPORTED, "structure %d: only gr-a is implemented on the device", setup->structure);
@@ -152,6 +188,16 @@ static int plan_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *m
     const int ncell = mesh->nrow * mesh->ncol;
     for (int c = 0; c < ncell; c++)
         if (mesh->active_cell[c] == 1 && (!mesh->local_active_cell || mesh->local_active_cell[c] == 1)) nact++;
+    pl.sparse = setup->sparse_storage ? 1 : 0;
+    pl.engine = pick_engine(engine);
+    if (pl.engine == 1) {
+        bool unsupported = false;
+        const int rc = split_build(pl, setup, mesh, &unsupported);
+        if (rc == 0) return 0;
+        if (!unsupported) return rc;
+        pl.engine = 0;   // mesh shape the split engine does not handle: fused engine
+        pl.sp = SplitState();
+    }
     const int B = pick_block(nact);
     std::string err = build_topology(pl.tp, mesh->nrow, mesh->ncol, mesh->ng, setup->ntime_step, mesh->flwdir, mesh->flwacc,
                                      mesh->active_cell, mesh->local_active_cell, mesh->path, mesh->gauge_pos, B);
@@ -188,10 +234,148 @@ static int plan_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *m
     TRY(pl.d_planes.ensure((size_t)NFIELD * ncell));
     CU(cudaStreamSynchronize(s));
     (void)nmember;
+    pl.col_cell = tp.cell;
+    pl.ncols = tp.nslots;
+    return 0;
+}
+
+// ---- split engine: build -------------------------------------------------------------------------
+static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, bool *unsupported) {
+    SplitState &sp = pl.sp;
+    RouteGraph &rg = sp.rg;
+    std::string err = build_route_graph(rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
+                                        mesh->local_active_cell, mesh->path, mesh->gauge_pos);
+    if (!err.empty()) {
+        *unsupported = err.rfind("unsupported", 0) == 0;
+        return fail(SMASH_B200_EINVAL, "%s", err.c_str());
+    }
+    const int ncell = mesh->nrow * mesh->ncol;
+    pl.dt = setup->dt; pl.dx = mesh->dx; pl.ncell = ncell; pl.nmember = 0;
+    Topology &tp = pl.tp;
+    tp = Topology();
+    tp.nrow = mesh->nrow; tp.ncol = mesh->ncol; tp.ng = mesh->ng; tp.T = setup->ntime_step; tp.B = 256;
+    tp.nactive = rg.n; tp.nslots = rg.npad; tp.nblocks = (rg.n + 255) / 256; tp.n_pairs = rg.npair;
+    tp.sparse_k.assign(rg.npad, -1);
+    for (int j = 0; j < rg.n; j++) tp.sparse_k[j] = rg.sparse_k[j];
+    tp.gauge_slot = rg.gauge_cell;
+    sp.W = split_pick_window(tp.T, &sp.S, &sp.nwin);
+    sp.Tp = sp.W * sp.nwin;
+    CU(cudaStreamCreateWithFlags(&pl.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&pl.ev0)); CU(cudaEventCreate(&pl.ev1)); CU(cudaEventCreate(&pl.ev2));
+    cudaStream_t s = pl.stream;
+    const int npad = rg.npad;
+    std::vector<int32_t> cell(npad, -1), flw(npad, 1), down(npad, -1), down_task(npad, -1), gfirst(npad, -1);
+    std::vector<uint8_t> down_lag(npad, 0);
+    for (int j = 0; j < rg.n; j++) {
+        cell[j] = rg.cell[j]; flw[j] = rg.flwacc[j]; down[j] = rg.down[j]; down_task[j] = rg.down_task[j]; gfirst[j] = rg.gauge_first[j];
+        if (rg.down[j] >= 0 && j > rg.down[j]) down_lag[j] = 1;   // producer later in path: the reader sees its previous step
+    }
+    TRY(pl.d_cell.upload(cell, s)); TRY(pl.d_sparse_k.upload(tp.sparse_k, s));
+    TRY(sp.d_flwacc.upload(flw, s)); TRY(sp.d_up_begin.upload(rg.up_begin, s)); TRY(sp.d_up.upload(rg.up, s));
+    TRY(sp.d_down.upload(down, s)); TRY(sp.d_down_task.upload(down_task, s)); TRY(sp.d_down_lag.upload(down_lag, s));
+    TRY(sp.d_task_begin.upload(rg.task_begin, s)); TRY(sp.d_task_cells.upload(rg.task_cells, s));
+    TRY(sp.d_gfirst.upload(gfirst, s)); TRY(sp.d_gnext.upload(rg.gauge_next, s));
+    TRY(sp.d_tcell.upload(rg.tcell, s)); TRY(sp.d_tup.upload(rg.tup, s));
+    TRY(pl.d_ticket.ensure(1)); TRY(pl.d_sum.ensure(1));
+    SplitTopo &t = sp.topo;
+    t.n = rg.n; t.npad = npad; t.ng = mesh->ng; t.ntask = rg.ntask; t.nchain = rg.nchain;
+    t.flwacc = sp.d_flwacc.p; t.up_begin = sp.d_up_begin.p; t.up = sp.d_up.p; t.down = sp.d_down.p; t.down_task = sp.d_down_task.p;
+    t.down_lag = sp.d_down_lag.p; t.task_begin = sp.d_task_begin.p; t.task_cells = sp.d_task_cells.p;
+    t.gauge_first = sp.d_gfirst.p; t.gauge_next = sp.d_gnext.p;
+    t.tcell = reinterpret_cast<const int4 *>(sp.d_tcell.p); t.tup = reinterpret_cast<const int2 *>(sp.d_tup.p);
+    // the field gather kernel only needs the column -> cell map
+    pl.dtp = DeviceTopology{};
+    pl.dtp.T = tp.T; pl.dtp.B = 256; pl.dtp.nblocks = tp.nblocks; pl.dtp.nslots = npad; pl.dtp.ng = mesh->ng; pl.dtp.cell = pl.d_cell.p;
+    pl.gauge_flwacc.assign(std::max(1, mesh->ng), 1);
+    if (mesh->ng > 0) {
+        std::vector<float> area(mesh->area, mesh->area + mesh->ng);
+        for (int g = 0; g < mesh->ng; g++)
+            pl.gauge_flwacc[g] = mesh->flwacc[(mesh->gauge_pos[g] - 1) + (size_t)(mesh->gauge_pos[g + mesh->ng] - 1) * mesh->nrow];
+        TRY(pl.d_area.upload(area, s));
+        TRY(pl.d_gauge_flwacc.upload(pl.gauge_flwacc, s));
+    }
+    TRY(pl.d_planes.ensure((size_t)NFIELD * ncell));
+    CU(cudaStreamSynchronize(s));
+    pl.col_cell = cell;
+    pl.ncols = npad;
+    sp.qpitch = (pl.sparse && rg.direct) ? rg.n : npad;
+    return 0;
+}
+
+static int split_members(SmashPlan &pl, int nmember, bool save_q, bool save_netp, bool gradient) {
+    SplitState &sp = pl.sp;
+    const Topology &tp = pl.tp;
+    const size_t nm = (size_t)nmember, npad = (size_t)sp.rg.npad;
+    TRY(pl.d_fields.ensure(nm * NFIELD * npad));
+    TRY(pl.d_fstates.ensure(nm * 3 * npad));
+    TRY(pl.d_qsim.ensure(std::max<size_t>(1, nm * tp.T * tp.ng)));
+    TRY(pl.d_cost_jobs.ensure(nm));
+    const size_t nrows = nm * npad * sp.Tp;
+    if (sp.d_rows.n < nrows) { TRY(sp.d_rows.ensure(nrows)); CU(cudaMemsetAsync(sp.d_rows.p, 0, nrows * sizeof(float), pl.stream)); }
+    TRY(sp.d_hcar.ensure(nm * npad));
+    TRY(sp.d_done.ensure(std::max<size_t>(1, nm * sp.rg.ntask)));
+    if (save_q || gradient) TRY(pl.d_qdom.ensure(nm * tp.T * sp.qpitch));
+    if (save_netp) TRY(pl.d_netp.ensure(nm * tp.T * sp.qpitch));
+    if (gradient) {
+        TRY(sp.d_tape_hp.ensure(nm * tp.T * npad)); TRY(sp.d_tape_hft.ensure(nm * tp.T * npad));
+        if (sp.d_rows_hr.n < nrows) { TRY(sp.d_rows_hr.ensure(nrows)); CU(cudaMemsetAsync(sp.d_rows_hr.p, 0, nrows * sizeof(float), pl.stream)); }
+        if (sp.d_rows_w.n < nrows) { TRY(sp.d_rows_w.ensure(nrows)); CU(cudaMemsetAsync(sp.d_rows_w.p, 0, nrows * sizeof(float), pl.stream)); }
+        TRY(sp.d_gcar.ensure(nm * npad));
+        TRY(sp.d_rdone.ensure(std::max<size_t>(1, nm * sp.rg.ntask)));
+        TRY(pl.d_qsim_b.ensure(std::max<size_t>(1, nm * tp.T * tp.ng)));
+        TRY(pl.d_grad.ensure(nm * NFIELD * npad));
+        if (sp.tape_mapped != sp.d_tape_hp.p || sp.tape_rows != nm * tp.T) {
+            const char *err = nullptr;
+            if (make_tensor_map_2d(&sp.tm_hp, sp.d_tape_hp.p, npad, nm * tp.T, npad, &err) ||
+                make_tensor_map_2d(&sp.tm_hft, sp.d_tape_hft.p, npad, nm * tp.T, npad, &err))
+                return fail(SMASH_B200_ECUDA, "%s", err);
+            sp.tape_mapped = sp.d_tape_hp.p; sp.tape_rows = nm * tp.T;
+        }
+    }
+    pl.nmember = nmember;
+    return 0;
+}
+
+static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp) {
+    SplitState &sp = pl.sp;
+    SplitArgs a{};
+    a.tp = sp.topo; a.T = pl.tp.T; a.Tp = sp.Tp; a.W = sp.W; a.nwin = sp.nwin; a.nmember = pl.nmember; a.dt = pl.dt; a.dx = pl.dx;
+    a.first_routed = sp.rg.first_routed;
+    a.save_q = save_q ? 1 : 0; a.save_netp = save_netp ? 1 : 0;
+    a.fields = pl.d_fields.p; a.fstates = pl.d_fstates.p; a.rows = sp.d_rows.p; a.qdom = pl.d_qdom.p; a.netp = pl.d_netp.p;
+    a.qpitch = sp.qpitch; a.qsim = pl.d_qsim.p; a.tape_hp = sp.d_tape_hp.p; a.tape_hft = sp.d_tape_hft.p; a.rows_hr = sp.d_rows_hr.p;
+    a.hcar = sp.d_hcar.p; a.done = sp.d_done.p; a.ticket = pl.d_ticket.p; a.qsim_b = pl.d_qsim_b.p; a.rows_w = sp.d_rows_w.p;
+    a.gcar = sp.d_gcar.p; a.grad = pl.d_grad.p; a.rdone = sp.d_rdone.p;
+    return a;
+}
+
+// forward sweep of the split engine: reservoirs, routing, optional [t][cell] export of the routed cells
+static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) {
+    SplitState &sp = pl.sp;
+    const size_t npad = (size_t)sp.rg.npad;
+    SplitArgs a = split_args(pl, save_q, save_netp);
+    // routing state of window 0 = the hlr field
+    CU(cudaMemcpy2DAsync(sp.d_hcar.p, npad * sizeof(float), pl.d_fields.p + (size_t)F_HLR * npad, (size_t)NFIELD * npad * sizeof(float),
+                         npad * sizeof(float), (size_t)pl.nmember, cudaMemcpyDeviceToDevice, pl.stream));
+    CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), tape, pl.stream));
+    CU(launch_route_forward(a, tape, pl.stream));
+    pl.launches += 1 + sp.nwin;
+    if (save_q) { CU(launch_rows_to_domain(a, pl.stream)); pl.launches++; }
+    return 0;
+}
+
+static int split_reverse(SmashPlan &pl) {
+    SplitState &sp = pl.sp;
+    SplitArgs a = split_args(pl, false, false);
+    CU(cudaMemsetAsync(pl.d_grad.p, 0, sizeof(float) * (size_t)pl.nmember * NFIELD * sp.rg.npad, pl.stream));
+    CU(launch_route_adjoint(a, pl.stream));
+    CU(launch_vertical_adjoint(a, sp.tm_prcp, sp.tm_pet, sp.tm_hp, sp.tm_hft, math_mode(), pl.stream));
+    pl.launches += 1 + sp.nwin;
     return 0;
 }
 
 static int plan_members(SmashPlan &pl, int nmember, bool save_q, bool save_netp, bool gradient) {
+    if (pl.engine == 1) return split_members(pl, nmember, save_q, save_netp, gradient);
     const Topology &tp = pl.tp;
     const size_t nm = (size_t)nmember;
     TRY(pl.d_fields.ensure(nm * NFIELD * tp.nslots));
@@ -237,12 +421,32 @@ static int plan_set_forcing(SmashPlan &pl, const SmashSetup *setup, const SmashM
     const int64_t stride = sparse ? mesh->nac : (int64_t)mesh->nrow * mesh->ncol;
     const size_t nraw = (size_t)stride * tp.T;
     TRY(pl.d_raw_prcp.ensure(nraw)); TRY(pl.d_raw_pet.ensure(nraw));
-    TRY(pl.d_forcing.ensure((size_t)tp.total_ticks * 2 * tp.B));
+    if (pl.engine == 0) TRY(pl.d_forcing.ensure((size_t)tp.total_ticks * 2 * tp.B));
     CU(cudaMemcpyAsync(pl.d_raw_prcp.p, prcp, nraw * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
     CU(cudaMemcpyAsync(pl.d_raw_pet.p, pet, nraw * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
-    CU(launch_relayout_forcing(pl.dtp, sparse ? pl.d_sparse_k.p : pl.d_cell.p, pl.d_raw_prcp.p, pl.d_raw_pet.p, stride,
-                               pl.d_forcing.p, pl.stream));
-    pl.launches++;
+    if (pl.engine == 1) {
+        // the reservoir pass reads [t][cell j] tiles by TMA: sparse arrays whose order is already j are used in place
+        SplitState &sp = pl.sp;
+        const float *fp = pl.d_raw_prcp.p, *fe = pl.d_raw_pet.p;
+        uint64_t cols = (uint64_t)sp.rg.n, pitch = (uint64_t)stride;
+        if (!(sparse && sp.rg.direct && stride % 4 == 0)) {
+            const size_t npk = (size_t)sp.rg.npad * tp.T;
+            TRY(sp.d_pk_prcp.ensure(npk)); TRY(sp.d_pk_pet.ensure(npk));
+            const int32_t *idx = sparse ? pl.d_sparse_k.p : pl.d_cell.p;
+            CU(launch_pack_columns(pl.d_raw_prcp.p, stride, idx, sp.rg.n, sp.rg.npad, tp.T, sp.d_pk_prcp.p, pl.stream));
+            CU(launch_pack_columns(pl.d_raw_pet.p, stride, idx, sp.rg.n, sp.rg.npad, tp.T, sp.d_pk_pet.p, pl.stream));
+            pl.launches += 2;
+            fp = sp.d_pk_prcp.p; fe = sp.d_pk_pet.p; cols = pitch = (uint64_t)sp.rg.npad;
+        }
+        const char *err = nullptr;
+        if (make_tensor_map_2d(&sp.tm_prcp, fp, cols, (uint64_t)tp.T, pitch, &err) ||
+            make_tensor_map_2d(&sp.tm_pet, fe, cols, (uint64_t)tp.T, pitch, &err))
+            return fail(SMASH_B200_ECUDA, "%s", err);
+    } else {
+        CU(launch_relayout_forcing(pl.dtp, sparse ? pl.d_sparse_k.p : pl.d_cell.p, pl.d_raw_prcp.p, pl.d_raw_pet.p, stride,
+                                   pl.d_forcing.p, pl.stream));
+        pl.launches++;
+    }
     pl.have_forcing = true; pl.forcing_ptr = prcp; pl.forcing_version = in->forcing_version; pl.forcing_sparse = (int)sparse;
     if (mesh->ng > 0 && in->qobs) {
         TRY(pl.d_qobs.ensure((size_t)mesh->ng * tp.T));
@@ -486,20 +690,20 @@ static void hyper_to_planes_b(const SmashSetup *s, const SmashMesh *m, const flo
 // ------------------------------------------------------------------------------------------------
 // plan cache
 // ------------------------------------------------------------------------------------------------
-static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **out) {
+static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **out, int engine = -1) {
     if (!setup || !mesh) return fail(SMASH_B200_EINVAL, "setup / mesh is NULL");
     TRY(check_device());
     const uint64_t h = hash_mesh(mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
                                  mesh->local_active_cell, mesh->path, mesh->gauge_pos);
     int dev = 0;
     cudaGetDevice(&dev);
-    char key[160];
-    snprintf(key, sizeof key, "%016llx:%d:%d:%g:%g:%lld", (unsigned long long)h, dev, setup->ntime_step, (double)setup->dt,
-             (double)mesh->dx, option("block", 0));
+    char key[192];
+    snprintf(key, sizeof key, "%016llx:%d:%d:%g:%g:%lld:%d:%d", (unsigned long long)h, dev, setup->ntime_step, (double)setup->dt,
+             (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0);
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
         std::unique_ptr<SmashPlan> pl(new SmashPlan());
-        TRY(plan_build(*pl, setup, mesh, 1));
+        TRY(plan_build(*pl, setup, mesh, 1, engine));
         it = g_plans.emplace(key, std::move(pl)).first;
     }
     *out = it->second.get();
@@ -514,6 +718,28 @@ static int download(SmashPlan &pl, void *dst, const void *src, size_t bytes) {
 // qsim_domain / net_prcp_domain in the reference's layout
 static int export_domain(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, const float *skewed, float *dense, float *sparse) {
     const Topology &tp = pl.tp;
+    if (pl.engine == 1) {   // [t][qpitch] in cell order j
+        SplitState &sp = pl.sp;
+        if (setup->sparse_storage) {
+            if (!sparse) return 0;
+            const size_t n = (size_t)mesh->nac * tp.T;
+            if (sp.rg.direct) { CU(cudaMemcpyAsync(sparse, skewed, n * sizeof(float), cudaMemcpyDeviceToHost, pl.stream)); return 0; }
+            TRY(pl.d_out.ensure(n));
+            CU(cudaMemsetAsync(pl.d_out.p, 0, n * sizeof(float), pl.stream));
+            CU(launch_scatter_columns(skewed, sp.qpitch, pl.d_sparse_k.p, sp.rg.n, tp.T, mesh->nac, pl.d_out.p, pl.stream));
+            pl.launches++;
+            CU(cudaMemcpyAsync(sparse, pl.d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, pl.stream));
+        } else {
+            if (!dense) return 0;
+            const size_t n = (size_t)pl.ncell * tp.T;
+            TRY(pl.d_out.ensure(n));
+            CU(cudaMemcpyAsync(pl.d_out.p, dense, n * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+            CU(launch_scatter_columns(skewed, sp.qpitch, pl.d_cell.p, sp.rg.n, tp.T, pl.ncell, pl.d_out.p, pl.stream));
+            pl.launches++;
+            CU(cudaMemcpyAsync(dense, pl.d_out.p, n * sizeof(float), cudaMemcpyDeviceToHost, pl.stream));
+        }
+        return 0;
+    }
     if (setup->sparse_storage) {
         if (!sparse) return 0;
         const size_t n = (size_t)mesh->nac * tp.T;
@@ -536,8 +762,22 @@ static int export_domain(SmashPlan &pl, const SmashSetup *setup, const SmashMesh
 }
 
 static void scatter_sorted(const SmashPlan &pl, const float *sorted, float *plane) {
-    const Topology &tp = pl.tp;
-    for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) plane[tp.cell[s]] = sorted[s];
+    for (int s = 0; s < pl.ncols; s++) if (pl.col_cell[s] >= 0) plane[pl.col_cell[s]] = sorted[s];
+}
+
+static int run_forward_engine(SmashPlan &pl, bool save_q, bool save_netp, bool tape) {
+    if (pl.engine == 1) return split_forward(pl, save_q, save_netp, tape);
+    SolverArgs a = solver_args(pl, save_q, save_netp, tape);
+    CU(launch_forward(a, math_mode(), pl.stream));
+    pl.launches++;
+    return 0;
+}
+static int run_reverse_engine(SmashPlan &pl) {
+    if (pl.engine == 1) return split_reverse(pl);
+    SolverArgs a = solver_args(pl, false, false, true);
+    CU(launch_reverse(a, math_mode(), pl.stream));
+    pl.launches++;
+    return 0;
 }
 
 static int math_mode() { return (int)option("math", 1); }
@@ -557,11 +797,9 @@ static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const 
     TRY(plan_members(*pl, 1, save_q, save_n, false));
     TRY(plan_set_forcing(*pl, setup, mesh, in));
     TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
-    SolverArgs a = solver_args(*pl, save_q, save_n, false);
-    CU(launch_forward(a, math_mode(), pl->stream));
-    pl->launches++;
+    TRY(run_forward_engine(*pl, save_q, save_n, false));
     TRY(run_cost(*pl, setup, mesh, 0.0f, false));
-    std::vector<float> fs((size_t)3 * tp.nslots);
+    std::vector<float> fs((size_t)3 * pl->ncols);
     float jobs = 0.0f;
     TRY(download(*pl, fs.data(), pl->d_fstates.p, fs.size() * sizeof(float)));
     TRY(download(*pl, &jobs, pl->d_cost_jobs.p, sizeof(float)));
@@ -576,7 +814,7 @@ static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const 
             if (out->fstates.v[i] && st->v[i]) memcpy(out->fstates.v[i], st->v[i], nc * sizeof(float));
     for (int f = 0; f < 3; f++) {
         float *dst = restore_states ? (out ? out->fstates.v[FIELD_STATE[f]] : nullptr) : st->v[FIELD_STATE[f]];
-        if (dst) scatter_sorted(*pl, fs.data() + (size_t)f * tp.nslots, dst);
+        if (dst) scatter_sorted(*pl, fs.data() + (size_t)f * pl->ncols, dst);
         if (!restore_states && out && out->fstates.v[FIELD_STATE[f]]) memcpy(out->fstates.v[FIELD_STATE[f]], st->v[FIELD_STATE[f]], nc * sizeof(float));
     }
     *jobs_out = jobs;
@@ -631,14 +869,11 @@ static int gradient_common(const SmashSetup *setup, const SmashMesh *mesh, const
     TRY(plan_members(*pl, 1, false, false, true));
     TRY(plan_set_forcing(*pl, setup, mesh, in));
     TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
-    SolverArgs a = solver_args(*pl, false, false, true);
-    CU(launch_forward(a, math_mode(), pl->stream));
-    pl->launches++;
+    TRY(run_forward_engine(*pl, false, false, true));
     if (mesh->ng > 0) TRY(run_cost(*pl, setup, mesh, cost_b, true));
     else CU(cudaMemsetAsync(pl->d_cost_jobs.p, 0, sizeof(float), pl->stream));
-    CU(launch_reverse(a, math_mode(), pl->stream));
-    pl->launches++;
-    grad.resize((size_t)NFIELD * tp.nslots);
+    TRY(run_reverse_engine(*pl));
+    grad.resize((size_t)NFIELD * pl->ncols);
     float jobs = 0.0f;
     TRY(download(*pl, grad.data(), pl->d_grad.p, grad.size() * sizeof(float)));
     TRY(download(*pl, &jobs, pl->d_cost_jobs.p, sizeof(float)));
@@ -663,7 +898,6 @@ extern "C" int smash_b200_forward_b(const SmashSetup *setup, const SmashMesh *me
     float jobs = 0.0f;
     std::vector<float> grad;
     TRY(gradient_common(setup, mesh, in, par, st, out, seed, &pl, &jobs, grad));
-    const Topology &tp = pl->tp;
     for (int i = 0; i < SMASH_B200_GNP; i++) if (par_b->v[i]) memset(par_b->v[i], 0, nc * sizeof(float));   // :10869
     for (int i = 0; i < SMASH_B200_GNS; i++) if (st_b->v[i]) memset(st_b->v[i], 0, nc * sizeof(float));     // :10870
     // COMPUTE_COST_B :3252-3353: Jreg and its adjoint act on normalised copies, the caller's arrays stay denormalised
@@ -689,14 +923,14 @@ extern "C" int smash_b200_forward_b(const SmashSetup *setup, const SmashMesh *me
     for (int f = 0; f < 4; f++) {
         float *dst = par_b->v[FIELD_PARAM[f]];
         if (!dst) continue;
-        const float *g = grad.data() + (size_t)f * tp.nslots;
-        for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) dst[tp.cell[s]] += g[s];
+        const float *g = grad.data() + (size_t)f * pl->ncols;
+        for (int s = 0; s < pl->ncols; s++) if (pl->col_cell[s] >= 0) dst[pl->col_cell[s]] += g[s];
     }
     for (int f = 0; f < 3; f++) {
         float *dst = st_b->v[FIELD_STATE[f]];
         if (!dst) continue;
-        const float *g = grad.data() + (size_t)(4 + f) * tp.nslots;
-        for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) dst[tp.cell[s]] += g[s];
+        const float *g = grad.data() + (size_t)(4 + f) * pl->ncols;
+        for (int s = 0; s < pl->ncols; s++) if (pl->col_cell[s] >= 0) dst[pl->col_cell[s]] += g[s];
     }
     if (setup->denormalize_forward) {                                   // :10931-10935
         for (int i = 0; i < SMASH_B200_GNS; i++) if (st_b->v[i]) for (size_t c = 0; c < nc; c++) st_b->v[i][c] = (setup->ub_states[i] - setup->lb_states[i]) * st_b->v[i][c];
@@ -755,12 +989,11 @@ extern "C" int smash_b200_hyper_forward_b(const SmashSetup *setup, const SmashMe
     float jobs = 0.0f;
     std::vector<float> grad;
     TRY(gradient_common(setup, mesh, in, par, st, out, seed, &pl, &jobs, grad));
-    const Topology &tp = pl->tp;
     std::vector<std::vector<float>> pb(SMASH_B200_GNP), sb(SMASH_B200_GNS);
     for (int i = 0; i < SMASH_B200_GNP; i++) if (i != SMASH_P_BETA && i != SMASH_P_ALPHA) pb[i].assign(nc, 0.0f);   // forward_db.f90:1489-1490
     for (int i = 0; i < SMASH_B200_GNS; i++) sb[i].assign(nc, 0.0f);
-    for (int f = 0; f < 4; f++) { const float *g = grad.data() + (size_t)f * tp.nslots; for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) pb[FIELD_PARAM[f]][tp.cell[s]] = g[s]; }
-    for (int f = 0; f < 3; f++) { const float *g = grad.data() + (size_t)(4 + f) * tp.nslots; for (int s = 0; s < tp.nslots; s++) if (tp.cell[s] >= 0) sb[FIELD_STATE[f]][tp.cell[s]] = g[s]; }
+    for (int f = 0; f < 4; f++) { const float *g = grad.data() + (size_t)f * pl->ncols; for (int s = 0; s < pl->ncols; s++) if (pl->col_cell[s] >= 0) pb[FIELD_PARAM[f]][pl->col_cell[s]] = g[s]; }
+    for (int f = 0; f < 3; f++) { const float *g = grad.data() + (size_t)(4 + f) * pl->ncols; for (int s = 0; s < pl->ncols; s++) if (pl->col_cell[s] >= 0) sb[FIELD_STATE[f]][pl->col_cell[s]] = g[s]; }
     hyper_to_planes_b(setup, mesh, in->descriptor, hyper_st->v, hyper_st_b->v, sb, SMASH_B200_GNS, setup->lb_states, setup->ub_states);
     hyper_to_planes_b(setup, mesh, in->descriptor, hyper_par->v, hyper_par_b->v, pb, SMASH_B200_GNP, setup->lb_parameters, setup->ub_parameters);
     if (hyper_par_b->v[SMASH_P_BETA]) for (int k = 0; k < setup->nhyper; k++) hyper_par_b->v[SMASH_P_BETA][k] = 0.0f;
@@ -785,11 +1018,13 @@ extern "C" int smash_b200_compute_multiple_run(const SmashSetup *setup, const Sm
     for (int j = 0; j < nvar; j++)
         if (ind[j] < 1 || ind[j] > SMASH_B200_GNP + SMASH_B200_GNS) return fail(SMASH_B200_EINVAL, "ind_parameters_states[%d] = %d out of range", j, ind[j]);
     SmashPlan *pl;
-    TRY(get_plan(setup, mesh, &pl));
+    TRY(get_plan(setup, mesh, &pl, (int)option("ensemble_engine", 0)));
     pl->launches = 0;
     const Topology &tp = pl->tp;
     // members per launch bounded by a memory budget
-    const size_t per_member = ((size_t)NFIELD + 3) * tp.nslots * 4 + (size_t)tp.T * tp.ng * 4 + (pl->need_qdom ? (size_t)tp.total_ticks * tp.B * 4 : 0) + 64;
+    const size_t per_member = ((size_t)NFIELD + 3) * pl->ncols * 4 + (size_t)tp.T * tp.ng * 4 + 64 +
+                              (pl->engine == 1 ? (size_t)pl->ncols * (pl->sp.Tp + 1) * 4 + (size_t)pl->sp.rg.ntask * 4
+                                               : (pl->need_qdom ? (size_t)tp.total_ticks * tp.B * 4 : 0));
     const size_t budget = (size_t)option("member_budget_mb", 16384) << 20;
     int chunk = (int)std::min<size_t>((size_t)ns, std::max<size_t>(1, budget / per_member));
     TRY(plan_set_forcing(*pl, setup, mesh, in));
@@ -799,9 +1034,7 @@ extern "C" int smash_b200_compute_multiple_run(const SmashSetup *setup, const Sm
         const int nm = std::min(chunk, ns - m0);
         TRY(plan_members(*pl, nm, false, false, false));
         TRY(plan_set_fields(*pl, par, st, sample + (size_t)m0 * nvar, ind, nvar, nm));
-        SolverArgs a = solver_args(*pl, false, false, false);
-        CU(launch_forward(a, math_mode(), pl->stream));
-        pl->launches++;
+        TRY(run_forward_engine(*pl, false, false, false));
         TRY(run_cost(*pl, setup, mesh, 0.0f, false));
         TRY(download(*pl, jobs.data(), pl->d_cost_jobs.p, (size_t)nm * sizeof(float)));
         if (res_qsim && nq) TRY(download(*pl, res_qsim + (size_t)m0 * nq, pl->d_qsim.p, (size_t)nm * nq * sizeof(float)));
@@ -863,7 +1096,7 @@ extern "C" int smash_b200_plan_create(const SmashSetup *setup, const SmashMesh *
     if (!plan) return fail(SMASH_B200_EINVAL, "plan is NULL");
     TRY(check_device());
     std::unique_ptr<SmashPlan> pl(new SmashPlan());
-    TRY(plan_build(*pl, setup, mesh, nmember));
+    TRY(plan_build(*pl, setup, mesh, nmember, nmember > 1 ? (int)option("ensemble_engine", 0) : -1));
     pl->nmember = nmember > 0 ? nmember : 1;
     *plan = pl.release();
     return 0;
@@ -907,11 +1140,9 @@ extern "C" int smash_b200_plan_run_forward(SmashPlan *plan, float *elapsed_ms) {
     if (!plan->have_forcing) return fail(SMASH_B200_EINVAL, "plan has no forcing");
     TRY(plan_cost_setup(plan));
     plan->launches = 0;
-    SolverArgs a = solver_args(*plan, plan->d_qdom.p != nullptr && !option("debug_nosave", 0), false, false);
     CU(cudaEventRecord(plan->ev0, plan->stream));
-    CU(launch_forward(a, math_mode(), plan->stream));
+    TRY(run_forward_engine(*plan, plan->d_qdom.p != nullptr && !option("debug_nosave", 0), false, false));
     CU(cudaEventRecord(plan->ev1, plan->stream));
-    plan->launches++;
     CU(cudaEventSynchronize(plan->ev1));
     if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, plan->ev0, plan->ev1));
     return 0;
@@ -923,12 +1154,10 @@ extern "C" int smash_b200_plan_run_gradient(SmashPlan *plan, float *ms_fwd, floa
     const int nm = plan->nmember > 0 ? plan->nmember : 1;
     TRY(plan_members(*plan, nm, true, false, true));
     plan->launches = 0;
-    SolverArgs a = solver_args(*plan, true, false, true);
     const Topology &tp = plan->tp;
     CU(cudaEventRecord(plan->ev0, plan->stream));
-    CU(launch_forward(a, math_mode(), plan->stream));
+    TRY(run_forward_engine(*plan, plan->engine == 0, false, true));
     CU(cudaEventRecord(plan->ev1, plan->stream));
-    plan->launches++;
     if (tp.ng > 0 && plan->have_qobs) {
         // NSE on every gauge, weight 1/ng (Optimize_SetupDT default wgauge, mwd_setup.f90:172)
         std::vector<float> wg(tp.ng, 1.0f / tp.ng);
@@ -943,9 +1172,8 @@ extern "C" int smash_b200_plan_run_gradient(SmashPlan *plan, float *ms_fwd, floa
     } else {
         CU(cudaMemsetAsync(plan->d_qsim_b.p, 0, sizeof(float) * std::max<size_t>(1, (size_t)nm * tp.T * tp.ng), plan->stream));
     }
-    CU(launch_reverse(a, math_mode(), plan->stream));
+    TRY(run_reverse_engine(*plan));
     CU(cudaEventRecord(plan->ev2, plan->stream));
-    plan->launches++;
     CU(cudaEventSynchronize(plan->ev2));
     if (ms_fwd) CU(cudaEventElapsedTime(ms_fwd, plan->ev0, plan->ev1));
     if (ms_rev) CU(cudaEventElapsedTime(ms_rev, plan->ev1, plan->ev2));
@@ -963,19 +1191,20 @@ extern "C" int smash_b200_plan_get_qsim(SmashPlan *plan, float *qsim, float *cos
 
 extern "C" int smash_b200_plan_get_gradient(SmashPlan *plan, SmashParameters *par_b, SmashStates *st_b) {
     if (!plan || !par_b || !st_b) return fail(SMASH_B200_EINVAL, "NULL argument");
-    const Topology &tp = plan->tp;
-    std::vector<float> grad((size_t)NFIELD * tp.nslots);
+    const size_t nc = (size_t)plan->ncols;
+    std::vector<float> grad((size_t)NFIELD * nc);
     TRY(download(*plan, grad.data(), plan->d_grad.p, grad.size() * sizeof(float)));
     CU(cudaStreamSynchronize(plan->stream));
-    for (int f = 0; f < 4; f++) if (par_b->v[FIELD_PARAM[f]]) scatter_sorted(*plan, grad.data() + (size_t)f * tp.nslots, par_b->v[FIELD_PARAM[f]]);
-    for (int f = 0; f < 3; f++) if (st_b->v[FIELD_STATE[f]]) scatter_sorted(*plan, grad.data() + (size_t)(4 + f) * tp.nslots, st_b->v[FIELD_STATE[f]]);
+    for (int f = 0; f < 4; f++) if (par_b->v[FIELD_PARAM[f]]) scatter_sorted(*plan, grad.data() + (size_t)f * nc, par_b->v[FIELD_PARAM[f]]);
+    for (int f = 0; f < 3; f++) if (st_b->v[FIELD_STATE[f]]) scatter_sorted(*plan, grad.data() + (size_t)(4 + f) * nc, st_b->v[FIELD_STATE[f]]);
     return 0;
 }
 
 extern "C" int smash_b200_plan_checksum(SmashPlan *plan, double *sum_q) {
     if (!plan || !sum_q) return fail(SMASH_B200_EINVAL, "NULL argument");
     if (!plan->d_qdom.p) return fail(SMASH_B200_EINVAL, "plan keeps no domain discharge");
-    CU(launch_checksum(plan->dtp, plan->d_qdom.p, plan->d_sum.p, plan->stream));
+    if (plan->engine == 1) CU(launch_sum_domain(plan->d_qdom.p, plan->sp.qpitch, plan->sp.rg.n, plan->tp.T, plan->d_sum.p, plan->stream));
+    else CU(launch_checksum(plan->dtp, plan->d_qdom.p, plan->d_sum.p, plan->stream));
     CU(cudaMemcpyAsync(sum_q, plan->d_sum.p, sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
     CU(cudaStreamSynchronize(plan->stream));
     return 0;
@@ -986,6 +1215,11 @@ extern "C" int smash_b200_plan_info(const SmashPlan *plan, int64_t info[12]) {
     const Topology &tp = plan->tp;
     info[0] = tp.nactive; info[1] = tp.nblocks; info[2] = tp.B; info[3] = tp.max_skew; info[4] = tp.total_ticks;
     info[5] = tp.n_cross_edges; info[6] = tp.n_pairs; info[7] = plan->launches; info[8] = tp.critical_ticks; info[9] = tp.max_chain_blocks; info[10] = tp.n_clusters; info[11] = tp.cluster_levels;
+    if (plan->engine == 1) {   // split engine: chains instead of blocks
+        const RouteGraph &rg = plan->sp.rg;
+        info[3] = rg.max_height; info[4] = plan->sp.Tp; info[5] = rg.nchain; info[8] = rg.critical_cells; info[9] = rg.max_chain;
+        info[10] = rg.ntask; info[11] = -1;
+    }
     return 0;
 }
 
@@ -993,11 +1227,11 @@ extern "C" int smash_b200_plan_order(const SmashPlan *plan, int32_t *order, int3
     if (!plan) return fail(SMASH_B200_EINVAL, "plan is NULL");
     const Topology &tp = plan->tp;
     int k = 0;
-    for (int s = 0; s < tp.nslots; s++) {
-        if (tp.cell[s] < 0) continue;
-        if (order) order[k] = tp.cell[s];
+    for (int s = 0; s < plan->ncols; s++) {
+        if (plan->col_cell[s] < 0) continue;
+        if (order) order[k] = plan->col_cell[s];
         if (block_of) block_of[k] = s / tp.B;
-        if (offset_of) offset_of[k] = tp.off[s];
+        if (offset_of) offset_of[k] = plan->engine == 1 ? 0 : tp.off[s];
         k++;
     }
     return 0;
@@ -1026,5 +1260,27 @@ extern "C" int smash_b200_mesh_order(const SmashSetup *setup, const SmashMesh *m
         if (offset_of) offset_of[k] = tp.off[s];
         k++;
     }
+    return 0;
+}
+
+// host-only: the heavy-path decomposition of the split engine (used by the CPU test-suite)
+extern "C" int smash_b200_mesh_chains(const SmashMesh *mesh, int64_t info[8], int32_t *cell, int32_t *task_of, int32_t *pos_of,
+                                      int32_t *down_of) {
+    if (!mesh || !info) return fail(SMASH_B200_EINVAL, "NULL argument");
+    RouteGraph rg;
+    std::string err = build_route_graph(rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
+                                        mesh->local_active_cell, mesh->path, mesh->gauge_pos);
+    if (!err.empty()) return fail(err.rfind("unsupported", 0) == 0 ? SMASH_B200_EUNSUPPORTED : SMASH_B200_EINVAL, "%s", err.c_str());
+    info[0] = rg.n; info[1] = rg.nchain; info[2] = rg.npair; info[3] = rg.max_height; info[4] = rg.max_chain;
+    info[5] = rg.critical_cells; info[6] = rg.nsrc; info[7] = rg.direct ? 1 : 0;
+    for (int j = 0; j < rg.n; j++) {
+        if (cell) cell[j] = rg.cell[j];
+        if (task_of) task_of[j] = rg.cell_task[j];
+        if (down_of) down_of[j] = rg.down[j];
+        if (pos_of) pos_of[j] = -1;
+    }
+    if (pos_of)
+        for (int t = 0; t < rg.ntask; t++)
+            for (int e = rg.task_begin[t]; e < rg.task_begin[t + 1]; e++) pos_of[rg.task_cells[e]] = e - rg.task_begin[t];
     return 0;
 }

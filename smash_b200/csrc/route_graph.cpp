@@ -1,0 +1,216 @@
+// route_graph.cpp -- see route_graph.hpp.
+#include "route_graph.hpp"
+
+#include <algorithm>
+#include <numeric>
+
+namespace smash {
+
+// operator/md_routing_operator.f90:29-31: neighbour i (1..8) sits at (row + drow[i], col + dcol[i]) and flows into
+// (row, col) iff its flwdir == i.
+static const int RG_DCOL[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+static const int RG_DROW[8] = {1, 1, 0, -1, -1, -1, 0, 1};
+
+std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const int32_t *flwdir, const int32_t *flwacc,
+                              const int32_t *active_cell, const int32_t *local_active_cell, const int32_t *path,
+                              const int32_t *gauge_pos) {
+    const int ncell = nrow * ncol;
+    if (nrow <= 0 || ncol <= 0) return "mesh: nrow and ncol must be positive";
+    g = RouteGraph();
+    g.nrow = nrow; g.ncol = ncol; g.ng = ng;
+
+    // ---- cells in path order (md_forward_structure.f90:82-92), sparse index (mw_sparse_storage.f90:28-45)
+    g.j_of_cell.assign(ncell, -1);
+    std::vector<int32_t> sparse_of_cell(ncell, -1);
+    int ks = 0;
+    for (int i = 0; i < ncell; i++) {
+        const int row = path[2 * i], col = path[2 * i + 1];
+        if (!(row > 0 && col > 0)) continue;
+        if (row > nrow || col > ncol) return "mesh.path holds an index outside the grid";
+        const int c = (row - 1) + (col - 1) * nrow;
+        if (active_cell[c] != 1) continue;
+        if (sparse_of_cell[c] < 0) sparse_of_cell[c] = ks++;
+        if (local_active_cell && local_active_cell[c] != 1) continue;
+        if (g.j_of_cell[c] >= 0) return "mesh.path lists a cell twice";
+        g.j_of_cell[c] = (int32_t)g.cell.size();
+        g.cell.push_back(c);
+    }
+    const int n = (int)g.cell.size();
+    if (n == 0) return "mesh has no active cell";
+    g.n = n;
+    g.npad = (n + 31) / 32 * 32;
+    g.sparse_k.resize(n); g.flwacc.resize(n);
+    g.direct = (ks == n);
+    for (int j = 0; j < n; j++) {
+        g.sparse_k[j] = sparse_of_cell[g.cell[j]];
+        g.flwacc[j] = flwacc[g.cell[j]];
+        if (g.sparse_k[j] != j) g.direct = false;
+        if (g.flwacc[j] <= 1) g.nsrc++;
+    }
+
+    // ---- inflow lists, neighbour order i = 1..8 (md_routing_operator.f90:37-53); only cells with flwacc > 1 gather (:35)
+    g.up_begin.assign(n + 1, 0);
+    g.down.assign(n, -1);
+    std::vector<uint8_t> lagged;   // per up entry: producer later in path (reader sees the previous time step)
+    for (int j = 0; j < n; j++) {
+        g.up_begin[j] = (int32_t)g.up.size();
+        if (g.flwacc[j] <= 1) continue;
+        const int c = g.cell[j];
+        const int row = c % nrow, col = c / nrow;
+        for (int i = 0; i < 8; i++) {
+            const int rr = row + RG_DROW[i], cc = col + RG_DCOL[i];
+            if (rr < 0 || rr >= nrow || cc < 0 || cc >= ncol) continue;
+            const int nb = rr + cc * nrow;
+            if (flwdir[nb] != i + 1) continue;
+            const int s = g.j_of_cell[nb];
+            if (s < 0) continue;   // never computed: its q stays 0
+            if (g.down[s] >= 0) return "mesh: a cell drains into two cells";
+            g.down[s] = j;
+            g.up.push_back({s, UP_NOWAIT});
+            lagged.push_back(s > j ? 1 : 0);
+        }
+    }
+    g.up_begin[n] = (int32_t)g.up.size();
+
+    // ---- pit pairs: j (earlier in path) reads its partner's previous step, the partner reads j's current step
+    std::vector<int32_t> partner(n, -1);
+    std::vector<std::pair<int32_t, int32_t>> pairs;
+    for (int j = 0; j < n; j++)
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) {
+            if (!lagged[e]) continue;
+            const int s = g.up[e].src;
+            if (g.down[j] != s) return "unsupported: lagged inflow outside a pit pair";
+            if (partner[j] >= 0 || partner[s] >= 0) return "mesh: chained flow-direction cycles are not supported";
+            partner[j] = s; partner[s] = j;
+            pairs.push_back({j, s});
+        }
+    for (int j = 0; j < n; j++)
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++)
+            if (partner[j] == g.up[e].src) g.up[e].task = UP_PARTNER;
+
+    // ---- heavy-path decomposition: the heavy child of a cell is its inflow with the largest flwacc (first on ties)
+    std::vector<int32_t> heavy(n, -1), next(n, -1);
+    for (int j = 0; j < n; j++) {
+        if (partner[j] >= 0) continue;
+        int best = -1, best_fa = -1;
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) {
+            const int s = g.up[e].src;
+            if (partner[s] >= 0) continue;   // cannot happen (pit cells only drain into each other); kept for safety
+            if (g.flwacc[s] > best_fa) { best_fa = g.flwacc[s]; best = e; }
+        }
+        if (best >= 0) { heavy[j] = g.up[best].src; next[g.up[best].src] = j; g.up[best].task = UP_HEAVY; }
+    }
+    // cycle check + chains
+    std::vector<std::vector<int32_t>> chains;
+    std::vector<int32_t> chain_of(n, -1);
+    for (int j = 0; j < n; j++) {
+        if (heavy[j] >= 0 || partner[j] >= 0) continue;          // not a chain head
+        if (next[j] < 0 && g.flwacc[j] <= 1) continue;           // lone source cell: final after the reservoir pass
+        std::vector<int32_t> ch;
+        for (int c = j; c >= 0; c = next[c]) {
+            if (chain_of[c] >= 0) return "mesh: flow directions contain a cycle";
+            chain_of[c] = (int32_t)chains.size();
+            ch.push_back(c);
+        }
+        chains.push_back(std::move(ch));
+    }
+    for (int j = 0; j < n; j++)
+        if (chain_of[j] < 0 && partner[j] < 0 && (heavy[j] >= 0 || g.flwacc[j] > 1))
+            return "mesh: flow directions contain a cycle longer than two cells";
+
+    // ---- dependency height of every chain (laterals are tails of other chains); processed in order of the tail's
+    // position in path, which is a topological order for non-lagged edges (producer earlier in path than consumer)
+    const int nch = (int)chains.size();
+    std::vector<int32_t> height(nch, 0);
+    std::vector<int64_t> finish(nch, 0);
+    {
+        std::vector<int32_t> order(nch);
+        std::iota(order.begin(), order.end(), 0);
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return chains[a].back() < chains[b].back(); });
+        for (int ci : order) {
+            int h = 0;
+            int64_t t = 0;
+            for (int c : chains[ci]) {
+                int64_t ready = 0;
+                for (int e = g.up_begin[c]; e < g.up_begin[c + 1]; e++) {
+                    const int s = g.up[e].src;
+                    const int cs = chain_of[s];
+                    if (cs < 0 || cs == ci) continue;
+                    if (chains[cs].back() != s) return "internal: lateral inflow is not a chain tail";
+                    h = std::max(h, height[cs] + 1);
+                    ready = std::max(ready, finish[cs]);
+                }
+                t = std::max(t, ready) + 1;
+            }
+            height[ci] = h;
+            finish[ci] = t;
+            g.max_height = std::max(g.max_height, h);
+            g.critical_cells = std::max(g.critical_cells, t);
+            g.max_chain = std::max(g.max_chain, (int)chains[ci].size());
+        }
+    }
+    std::vector<int32_t> torder(nch);
+    std::iota(torder.begin(), torder.end(), 0);
+    std::stable_sort(torder.begin(), torder.end(), [&](int a, int b) {
+        if (height[a] != height[b]) return height[a] < height[b];
+        return chains[a].size() > chains[b].size();
+    });
+    std::vector<int32_t> task_of_chain(nch);
+    for (int t = 0; t < nch; t++) task_of_chain[torder[t]] = t;
+
+    g.nchain = nch; g.npair = (int)pairs.size(); g.ntask = g.nchain + g.npair;
+    g.task_begin.assign(g.ntask + 1, 0);
+    g.cell_task.assign(n, -1);
+    for (int t = 0; t < nch; t++) {
+        g.task_begin[t] = (int32_t)g.task_cells.size();
+        for (int c : chains[torder[t]]) { g.task_cells.push_back(c); g.cell_task[c] = t; }
+    }
+    for (int p = 0; p < g.npair; p++) {
+        g.task_begin[nch + p] = (int32_t)g.task_cells.size();
+        g.task_cells.push_back(pairs[p].first); g.task_cells.push_back(pairs[p].second);
+        g.cell_task[pairs[p].first] = g.cell_task[pairs[p].second] = nch + p;
+    }
+    g.task_begin[g.ntask] = (int32_t)g.task_cells.size();
+    // lateral entries wait for the producing task (source cells outside every task need no wait)
+    for (int j = 0; j < n; j++)
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++)
+            if (g.up[e].task == UP_NOWAIT) {
+                const int s = g.up[e].src;
+                if (g.cell_task[s] >= 0) {
+                    if (g.cell_task[s] >= g.cell_task[j]) return "internal: task order violates a dependency";
+                    g.up[e].task = g.cell_task[s];
+                }
+            }
+    g.down_task.assign(n, -1);
+    for (int j = 0; j < n; j++) if (g.down[j] >= 0) g.down_task[j] = g.cell_task[g.down[j]];
+
+    // ---- gauges (md_forward_structure.f90:206-210)
+    g.gauge_first.assign(n, -1);
+    g.gauge_next.assign(ng > 0 ? ng : 0, -1);
+    g.gauge_cell.assign(ng > 0 ? ng : 0, -1);
+    for (int k = ng - 1; k >= 0; k--) {
+        const int row = gauge_pos[k], col = gauge_pos[k + ng];
+        if (row < 1 || row > nrow || col < 1 || col > ncol) return "mesh.gauge_pos outside the grid";
+        const int j = g.j_of_cell[(row - 1) + (col - 1) * nrow];
+        g.gauge_cell[k] = j;
+        if (j >= 0) { g.gauge_next[k] = g.gauge_first[j]; g.gauge_first[j] = k; }
+    }
+    // ---- compact per-task records: everything a routing warp needs about its cells in two coalesced loads
+    g.tcell.resize(g.task_cells.size());
+    for (size_t i = 0; i < g.task_cells.size(); i++) {
+        const int j = g.task_cells[i];
+        TaskCell tc;
+        tc.j = j;
+        const int nup = g.up_begin[j + 1] - g.up_begin[j];
+        tc.meta = (g.flwacc[j] > 1 ? 1 : 0) | (g.gauge_first[j] >= 0 ? 2 : 0) | (nup << 8);
+        tc.up_off = (int32_t)g.tup.size();
+        tc.pad_ = 0;
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) g.tup.push_back(g.up[e]);
+        g.tcell[i] = tc;
+    }
+    g.first_routed = n;
+    for (int j = 0; j < n; j++) if (g.flwacc[j] > 1) { g.first_routed = j; break; }
+    return "";
+}
+
+}  // namespace smash

@@ -1,0 +1,985 @@
+// split_kernels.cu -- the split engine: reservoirs and routing of gr_a_forward as separate passes (split_kernels.cuh).
+//
+// Reference statements are cited as file:line under /root/reference/smash/solver/.
+#include "split_kernels.cuh"
+
+#include "cell_math.cuh"
+
+namespace smash {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int VT_TK = 8;      // time steps per TMA box (= one 32-byte sector of a row)
+constexpr int VT_WARPS = 8;   // warps per CTA of the per-cell passes; every warp runs its own pipeline, no CTA barrier
+constexpr int VF_NST = 3;     // forward: boxes in flight per warp and array
+constexpr int VB_NST = 2;     // adjoint: boxes in flight per warp and array
+
+// 2-D TMA tile load global -> shared (SASS UTMALDG), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int x, int y, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(tm), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+// 32-byte (one sector) vector accesses, sm_100+
+__device__ __forceinline__ void ld8(const float *p, float *v) {
+    asm volatile("ld.global.cg.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void st8(float *p, const float *v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int FAST> __device__ __forceinline__ float scale_q(float v, float c0, float dx, float dt) {
+    return FAST ? v * c0 : v * dx * dx * 0.001f / dt;                     // md_forward_structure.f90:155
+}
+
+// gr-a cell-step for a stage whose forcing has no gap, whose tanh arguments stay below 0.25 and whose production store
+// cannot reach the percolation threshold of float32 (hp_imd <= 15 => 1 + (hp_imd/1000)^4 == 1): the statements of
+// vertical_step_nogap (cell_math.cuh) with those warp-uniform branches resolved once per stage.  Bit-identical results.
+template <bool EXC>
+__device__ __forceinline__ float vertical_step_lean(const CellConst &k, float prcp, float pet, float &hp, float &hft) {
+    const float ei = fminf(pet, prcp);                                   // md_forward_structure.f90:112
+    const float pn = fmaxf(0.0f, prcp - ei);                             // :114
+    const float en = pet - ei;                                           // :116
+    const bool wet = pn > 0.0f;
+    const float x = (wet ? pn : en) * k.inv_cp;
+    const float x2 = x * x;
+    float p = fmaf(x2, 0.021869488f, -0.053968254f);
+    p = fmaf(x2, p, 0.13333334f);
+    p = fmaf(x2, p, -0.33333334f);
+    const float th = fmaf(x * x2, p, x);
+    const float num = (wet ? k.cp * (1.0f - hp * hp) : (hp * k.cp) * (2.0f - hp)) * th;     // md_gr_operator.f90:52,55
+    const float den = fmaf(wet ? hp : 1.0f - hp, th, 1.0f);
+    const float r = num * mufu_rcp(den);
+    const float hp_imd = hp + (wet ? r : -r) * k.inv_cp;                 // :58
+    const float pr = wet ? pn - (hp_imd - hp) * k.cp : 0.0f;             // :60-62
+    hp = hp_imd;                                                         // perc == 0 (:66-68)
+    const float l = EXC ? k.exc * ((hft * hft) * hft * fsqrt_fast(hft)) : 0.0f;             // :77
+    const float prr = fmaf(0.9f, pr, l);                                 // md_forward_structure.f90:137
+    const float prd = 0.1f * pr;                                         // :138
+    const float u = fmaxf(1.e-6f, fmaf(prr, k.inv_cft, hft));            // md_gr_operator.f90:102
+    const float z = pow4(u);
+    const float s2 = fsqrt_fast(1.0f + z), s1 = fsqrt_fast(s2);
+    const float g = z * mufu_rcp(s1 * (s1 + 1.0f) * (s2 + 1.0f));        // 1 - (1+u^4)^(-1/4), cancellation-free (:104)
+    const float rel = u * g;
+    hft = u - rel;
+    return fmaf(rel, k.cft, fmaxf(0.0f, prd + l));                       // qt = qr + qd (:106, md_forward_structure.f90:142-144)
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertical_forward: md_forward_structure.f90:106-144 for every cell and time step; no inter-cell dependency.
+// Source cells (flwacc == 1) are final here: q = qt * dx^2 * 1e-3 / dt (:155 with flwacc - 1 = 0).
+// ------------------------------------------------------------------------------------------------
+typedef float FwdStage[2][VT_TK][32];
+
+template <int FAST, int TAPE>
+__global__ void __launch_bounds__(VT_WARPS * 32) vertical_forward_kernel(const __grid_constant__ CUtensorMap tm_prcp,
+                                                                        const __grid_constant__ CUtensorMap tm_pet,
+                                                                        const SplitArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FwdStage *stage = reinterpret_cast<FwdStage *>(smem_raw) + warp * VF_NST;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + sizeof(FwdStage) * VT_WARPS * VF_NST) + warp * VF_NST;
+    const int m = blockIdx.y;
+    const int j0 = (blockIdx.x * VT_WARPS + warp) * 32;
+    const int n = a.tp.n, npad = a.tp.npad, T = a.T;
+    if (j0 >= n) return;
+    const int j = j0 + lane;
+    const bool valid = j < n;
+    const int nst = (T + VT_TK - 1) / VT_TK;
+    constexpr uint32_t STAGE_BYTES = sizeof(FwdStage);
+
+    if (lane == 0) {
+        for (int s = 0; s < VF_NST; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < VF_NST && s < nst; s++) {
+            mbar_expect_tx(&bars[s], STAGE_BYTES);
+            tma_load_2d(&stage[s][0][0][0], &tm_prcp, j0, s * VT_TK, &bars[s]);
+            tma_load_2d(&stage[s][1][0][0], &tm_pet, j0, s * VT_TK, &bars[s]);
+        }
+    }
+    __syncwarp();
+
+    const float *fld = a.fields + (size_t)m * NFIELD * npad + j;
+    float hp = 0.01f, hft = 0.01f, hlr = 0.0f;
+    int fa = 1;
+    CellConst k = make_const(200.0f, 500.0f, 0.0f, 5.0f, 1, a.dt, a.dx);
+    if (valid) {
+        fa = a.tp.flwacc[j];
+        k = make_const(fld[(size_t)F_CP * npad], fld[(size_t)F_CFT * npad], fld[(size_t)F_EXC * npad], fld[(size_t)F_LR * npad], fa,
+                       a.dt, a.dx);
+        hp = fld[(size_t)F_HP * npad]; hft = fld[(size_t)F_HFT * npad]; hlr = fld[(size_t)F_HLR * npad];
+    }
+    const bool src = fa <= 1;
+    const int gfirst = valid ? a.tp.gauge_first[j] : -1;
+    const bool all_valid = j0 + 32 <= n;
+    const bool exc_on = __any_sync(FULL, k.exc != 0.0f);
+    const size_t qpitch = (size_t)a.qpitch;
+    float *row = a.rows + ((size_t)m * npad + j) * a.Tp;
+    float *qd = (a.save_q && src && valid) ? a.qdom + (size_t)m * T * qpitch + j : nullptr;
+    float *np_ = (a.save_netp && valid) ? a.netp + (size_t)m * T * qpitch + j : nullptr;
+    float *thp = TAPE ? a.tape_hp + (size_t)m * T * npad + j : nullptr;
+    float *thft = TAPE ? a.tape_hft + (size_t)m * T * npad + j : nullptr;
+    float *qsim = a.qsim + (size_t)m * T * a.tp.ng;
+    const int ng = a.tp.ng;
+    const float c0 = k.c0, E = k.E, inv_cp = k.inv_cp;
+
+    uint32_t parity = 0;
+    int slot = 0;
+#pragma unroll 1
+    for (int st = 0; st < nst; st++) {
+        mbar_wait(&bars[slot], parity);
+        float pv[VT_TK], ev[VT_TK], qv[VT_TK];
+        float mn = 0.0f, mx = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VT_TK; i++) {
+            pv[i] = stage[slot][0][i][lane];
+            ev[i] = stage[slot][1][i][lane];
+            mn = fminf(mn, fminf(pv[i], ev[i]));
+            mx = fmaxf(mx, fmaxf(pv[i], ev[i]));
+        }
+        __syncwarp();   // every lane holds its stage in registers: refill the slot
+        if (lane == 0 && st + VF_NST < nst) {
+            mbar_expect_tx(&bars[slot], STAGE_BYTES);
+            tma_load_2d(&stage[slot][0][0][0], &tm_prcp, j0, (st + VF_NST) * VT_TK, &bars[slot]);
+            tma_load_2d(&stage[slot][1][0][0], &tm_pet, j0, (st + VF_NST) * VT_TK, &bars[slot]);
+        }
+        const int tb = st * VT_TK;
+        const bool full = all_valid && tb + VT_TK <= T;
+        const float xm = mx * inv_cp;
+        const bool lean = FAST && full && __all_sync(FULL, mn >= 0.0f && xm < 0.25f && fmaf(8.0f, xm, hp) < 15.0f);
+        if (lean) {
+#pragma unroll
+            for (int i = 0; i < VT_TK; i++) {
+                if (TAPE) { thp[(size_t)(tb + i) * npad] = hp; thft[(size_t)(tb + i) * npad] = hft; }
+                const float qt = exc_on ? vertical_step_lean<true>(k, pv[i], ev[i], hp, hft) : vertical_step_lean<false>(k, pv[i], ev[i], hp, hft);
+                if (np_) np_[(size_t)(tb + i) * qpitch] = qt;
+                float q = qt;
+                if (src) {
+                    q = qt * c0;
+                    hlr = (hlr + 0.0f) * E;                                // linear_routing with qup = 0, md_routing_operator.f90:73-77
+                    if (qd) qd[(size_t)(tb + i) * qpitch] = q;
+                    if (gfirst >= 0)
+                        for (int g = gfirst; g >= 0; g = a.tp.gauge_next[g]) qsim[(size_t)(tb + i) * ng + g] = q;   // :206-210
+                }
+                qv[i] = q;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < VT_TK; i++) {
+                const int t = tb + i;
+                const bool act = valid && t < T;
+                if (TAPE && act) { thp[(size_t)t * npad] = hp; thft[(size_t)t * npad] = hft; }
+                float hp_n = hp, hft_n = hft, qt;
+                const bool gapless = (pv[i] >= 0.0f) && (ev[i] >= 0.0f);
+                if (FAST && __all_sync(FULL, gapless)) qt = vertical_step_nogap(k, pv[i], ev[i], hp_n, hft_n);
+                else qt = vertical_step<FAST>(k, pv[i], ev[i], hp_n, hft_n).qt;
+                float q = qt;
+                if (act) {
+                    hp = hp_n; hft = hft_n;
+                    if (np_) np_[(size_t)t * qpitch] = qt;
+                    if (src) {
+                        q = scale_q<FAST>(qt, c0, a.dx, a.dt);
+                        hlr = (hlr + 0.0f) * E;
+                        if (qd) qd[(size_t)t * qpitch] = q;
+                        if (gfirst >= 0)
+                            for (int g = gfirst; g >= 0; g = a.tp.gauge_next[g]) qsim[(size_t)t * ng + g] = q;
+                    }
+                }
+                qv[i] = q;
+            }
+        }
+        if (valid) st8(row + (size_t)tb, qv);
+        if (++slot == VF_NST) { slot = 0; parity ^= 1u; }
+    }
+    if (valid) {
+        float *fs = a.fstates + (size_t)m * 3 * npad + j;
+        fs[0] = hp; fs[(size_t)npad] = hft;
+        if (src) fs[(size_t)2 * npad] = hlr;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// row helpers: a lane owns S consecutive time steps of a row
+// ------------------------------------------------------------------------------------------------
+template <int S> __device__ __forceinline__ void ld_row(const float *p, float (&v)[S]) {
+#pragma unroll
+    for (int i = 0; i < S / 8; i++) ld8(p + 8 * i, &v[8 * i]);
+}
+template <int S> __device__ __forceinline__ void st_row(float *p, const float (&v)[S]) {
+#pragma unroll
+    for (int i = 0; i < S / 8; i++) st8(p + 8 * i, &v[8 * i]);
+}
+// every lane asks for the 128-byte lines of its own row (window part): DRAM -> L2 ahead of use
+template <int S> __device__ __forceinline__ void prefetch_row(const float *row_window) {
+#pragma unroll
+    for (int i = 0; i < S; i++) prefetch_l2(row_window + 32 * i);
+}
+__device__ __forceinline__ void wait_flag(const int *flag, int epoch, int lane) {
+    if (lane == 0)
+        while (ld_acquire(flag) < epoch) __nanosleep(32);
+    __syncwarp();
+}
+__device__ __forceinline__ void publish_flag(int *flag, int epoch, int lane) {
+    __syncwarp();
+    if (lane == 0) { __threadfence(); st_release(flag, epoch); }
+}
+__device__ __forceinline__ int claim_ticket(unsigned int *ticket, int lane) {
+    int tk = 0;
+    if (lane == 0) tk = (int)atomicAdd(ticket, 1u);
+    return __shfl_sync(FULL, tk, 0);
+}
+
+struct RouteConst { float fa1, s_q, E, c0, lr, h0; };
+__device__ __forceinline__ RouteConst route_const(const SplitArgs &a, int m, int j, const float *carry) {
+    RouteConst c;
+    const int fa = a.tp.flwacc[j];
+    c.lr = a.fields[((size_t)m * NFIELD + F_LR) * a.tp.npad + j];
+    c.h0 = carry[(size_t)m * a.tp.npad + j];
+    c.fa1 = (float)(fa - 1);
+    c.s_q = (fa > 1) ? a.dt / (0.001f * a.dx * a.dx * c.fa1) : 0.0f;      // md_routing_operator.f90:55-56
+    c.E = expf(-a.dt / (c.lr * 60.0f));                                   // :75
+    c.c0 = a.dx * a.dx * 0.001f / a.dt;                                   // md_forward_structure.f90:155
+    return c;
+}
+__device__ __forceinline__ RouteConst shfl_const(const RouteConst &c, int src) {
+    RouteConst r;
+    r.fa1 = __shfl_sync(FULL, c.fa1, src); r.s_q = __shfl_sync(FULL, c.s_q, src); r.E = __shfl_sync(FULL, c.E, src);
+    r.c0 = __shfl_sync(FULL, c.c0, src); r.lr = __shfl_sync(FULL, c.lr, src); r.h0 = __shfl_sync(FULL, c.h0, src);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// route_forward: upstream_discharge + linear_routing (md_routing_operator.f90:17-79) + the discharge of the
+// cell (md_forward_structure.f90:155) on whole time windows.  Per cell the routing state obeys
+//   hlr(t) = (hlr(t-1) + qup(t)) * E,   qrout = hr_imd - hlr,   q = (qt + qrout * (flwacc - 1)) * dx^2 * 1e-3 / dt
+// which is linear in time: every lane runs its S steps from a zero state, a warp scan of the affine maps
+// (E^S, end value) gives every lane its true carry-in, a second pass produces the results.
+// ------------------------------------------------------------------------------------------------
+template <int S, int TAPE>
+__device__ __forceinline__ void route_cell(const SplitArgs &a, const RouteConst &c, int m, int j, int w, int lane, int t_first,
+                                           bool gauge, float (&x)[S], const float (&qt)[S], float (&r)[S]) {
+    const float E = c.E;
+    const float h0 = c.h0;
+    float h = (lane == 0) ? h0 : 0.0f;
+    float A = 1.0f;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        x[s] = x[s] * c.s_q;
+        h = (h + x[s]) * E;
+        A *= E;
+    }
+    float Bv = h;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float Bo = __shfl_up_sync(FULL, Bv, d), Ao = __shfl_up_sync(FULL, A, d);
+        if (lane >= d) { Bv = fmaf(A, Bo, Bv); A *= Ao; }
+    }
+    h = __shfl_up_sync(FULL, Bv, 1);
+    if (lane == 0) h = h0;
+    const int tcap = min(a.T, (w + 1) * a.W) - 1;          // last valid step of this window: its state is carried on
+    float hcap = 0.0f;
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const float hr = h + x[s];                          // :73
+        const float hn = hr * E;                            // :75
+        const float qrout = hr - hn;                        // :77
+        r[s] = fmaf(qrout, c.fa1, qt[s]) * c.c0;            // md_forward_structure.f90:155
+        x[s] = hr;
+        if (t_first + s == tcap) hcap = hn;
+        h = hn;
+    }
+    const float hfin = __shfl_sync(FULL, hcap, (tcap - w * a.W) / S);
+    float *rows = a.rows + ((size_t)m * a.tp.npad + j) * a.Tp + t_first;
+    st_row<S>(rows, r);
+    if (TAPE) st_row<S>(a.rows_hr + ((size_t)m * a.tp.npad + j) * a.Tp + t_first, x);
+    if (lane == 0) {
+        a.hcar[(size_t)m * a.tp.npad + j] = hfin;
+        if (w == a.nwin - 1) a.fstates[((size_t)m * 3 + 2) * a.tp.npad + j] = hfin;
+    }
+    if (gauge) {
+        float *qsim = a.qsim + (size_t)m * a.T * a.tp.ng;
+        for (int g = a.tp.gauge_first[j]; g >= 0; g = a.tp.gauge_next[g])
+#pragma unroll
+            for (int s = 0; s < S; s++)
+                if (t_first + s < a.T) qsim[(size_t)(t_first + s) * a.tp.ng + g] = r[s];          // :206-210
+    }
+}
+
+// inflows of a pit-pair cell other than its partner, summed in the reference's order
+template <int S>
+__device__ __forceinline__ void gather_laterals(const SplitArgs &a, const int *done, int epoch, const float *rows_lane,
+                                                const int4 rec, int lane, float (&lat)[S]) {
+#pragma unroll
+    for (int s = 0; s < S; s++) lat[s] = 0.0f;
+    const int nup = rec.y >> 8;
+#pragma unroll 1
+    for (int e = 0; e < nup; e++) {
+        const int2 u = a.tp.tup[rec.z + e];
+        if (u.y <= UP_HEAVY) continue;
+        if (u.y >= 0) wait_flag(done + u.y, epoch, lane);
+        float v[S];
+        ld_row<S>(rows_lane + (size_t)u.x * a.Tp, v);
+#pragma unroll
+        for (int s = 0; s < S; s++) lat[s] = lat[s] + v[s];
+    }
+}
+
+// pit pair (A earlier in path, B its partner): A gathers q_B of the previous step, B gathers q_A of the current
+// step.  The coupled recurrence is run step by step, lane after lane.
+template <int S, int TAPE>
+__device__ __noinline__ void route_pair(const SplitArgs &a, int m, const int4 recA, const int4 recB, int w, int lane, int t_first,
+                                        const int *done, int epoch) {
+    const size_t npad = a.tp.npad;
+    const int jA = recA.x, jB = recB.x;
+    const float *rows_lane = a.rows + (size_t)m * npad * a.Tp + t_first;
+    float latA[S], latB[S], qA[S], qB[S];
+    gather_laterals<S>(a, done, epoch, rows_lane, recA, lane, latA);
+    gather_laterals<S>(a, done, epoch, rows_lane, recB, lane, latB);
+    ld_row<S>(rows_lane + (size_t)jA * a.Tp, qA);
+    ld_row<S>(rows_lane + (size_t)jB * a.Tp, qB);
+    const RouteConst cA = route_const(a, m, jA, a.hcar), cB = route_const(a, m, jB, a.hcar);
+    float hA = cA.h0, hB = cB.h0;
+    float qBp = (w > 0) ? a.rows[((size_t)m * npad + jB) * a.Tp + (size_t)w * a.W - 1] : 0.0f;
+#pragma unroll 1
+    for (int L = 0; L < 32; L++) {
+        float sA = hA, sB = hB, sq = qBp;
+        if (lane == L) {
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                const float hrA = sA + (latA[s] + sq) * cA.s_q;
+                const float hnA = hrA * cA.E;
+                const float qa = fmaf(hrA - hnA, cA.fa1, qA[s]) * cA.c0;
+                const float hrB = sB + (latB[s] + qa) * cB.s_q;
+                const float hnB = hrB * cB.E;
+                const float qb = fmaf(hrB - hnB, cB.fa1, qB[s]) * cB.c0;
+                qA[s] = qa; qB[s] = qb; latA[s] = hrA; latB[s] = hrB;
+                if (t_first + s < a.T) { sA = hnA; sB = hnB; sq = qb; }
+            }
+        }
+        hA = __shfl_sync(FULL, sA, L); hB = __shfl_sync(FULL, sB, L); qBp = __shfl_sync(FULL, sq, L);
+    }
+    float *rows = a.rows + (size_t)m * npad * a.Tp + t_first;
+    st_row<S>(rows + (size_t)jA * a.Tp, qA);
+    st_row<S>(rows + (size_t)jB * a.Tp, qB);
+    if (TAPE) {
+        float *hr = a.rows_hr + (size_t)m * npad * a.Tp + t_first;
+        st_row<S>(hr + (size_t)jA * a.Tp, latA);
+        st_row<S>(hr + (size_t)jB * a.Tp, latB);
+    }
+    if (lane == 0) {
+        a.hcar[(size_t)m * npad + jA] = hA; a.hcar[(size_t)m * npad + jB] = hB;
+        if (w == a.nwin - 1) {
+            a.fstates[((size_t)m * 3 + 2) * npad + jA] = hA;
+            a.fstates[((size_t)m * 3 + 2) * npad + jB] = hB;
+        }
+    }
+    float *qsim = a.qsim + (size_t)m * a.T * a.tp.ng;
+    for (int g = a.tp.gauge_first[jA]; g >= 0; g = a.tp.gauge_next[g])
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if (t_first + s < a.T) qsim[(size_t)(t_first + s) * a.tp.ng + g] = qA[s];
+    for (int g = a.tp.gauge_first[jB]; g >= 0; g = a.tp.gauge_next[g])
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if (t_first + s < a.T) qsim[(size_t)(t_first + s) * a.tp.ng + g] = qB[s];
+}
+
+// One warp per task.  The records of up to 32 cells of the chain are fetched with one coalesced load, lane i then
+// owns the scalars of cell i (constants, carried state) and asks L2 for that cell's rows while the warp routes the
+// cells one after the other; nothing on the cell-to-cell critical path but L2 hits and the scan.
+template <int S, int TAPE>
+__global__ void __launch_bounds__(128) route_forward_kernel(const SplitArgs a, const int w) {
+    const int lane = threadIdx.x & 31;
+    const SplitTopo &tp = a.tp;
+    const int t_first = w * a.W + lane * S;
+    const int epoch = w + 1;
+    const int total = tp.ntask * a.nmember;
+    int tk_next = claim_ticket(a.ticket, lane);
+    for (;;) {
+        const int tk = tk_next;
+        if (tk >= total) break;
+        tk_next = claim_ticket(a.ticket, lane);            // the next ticket travels while this task is routed
+        const int m = tk / tp.ntask, task = tk - m * tp.ntask;
+        const int cb = tp.task_begin[task], ce = tp.task_begin[task + 1];
+        int *done = a.done + (size_t)m * tp.ntask;
+        if (task >= tp.nchain) {
+            route_pair<S, TAPE>(a, m, tp.tcell[cb], tp.tcell[cb + 1], w, lane, t_first, done, epoch);
+            publish_flag(done + task, epoch, lane);
+            continue;
+        }
+        const float *rows_lane = a.rows + (size_t)m * tp.npad * a.Tp + t_first;
+        const float *rows_win = a.rows + (size_t)m * tp.npad * a.Tp + (size_t)w * a.W;
+        float r[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) r[s] = 0.0f;
+#pragma unroll 1
+        for (int g0 = cb; g0 < ce; g0 += 32) {
+            const int ngr = min(32, ce - g0);
+            int4 rec = make_int4(-1, 0, 0, 0);
+            if (lane < ngr) rec = tp.tcell[g0 + lane];
+            RouteConst ci = {0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+            if (lane < ngr) {
+                prefetch_row<S>(rows_win + (size_t)rec.x * a.Tp);
+                if (rec.y & 1) ci = route_const(a, m, rec.x, a.hcar);
+            }
+            const int up0 = __shfl_sync(FULL, rec.z, 0);
+            const int nup_all = __shfl_sync(FULL, rec.z + (rec.y >> 8), ngr - 1) - up0;
+            int2 ent = make_int2(-1, UP_HEAVY);
+            if (lane < nup_all) {
+                ent = tp.tup[up0 + lane];
+                if (ent.y > UP_HEAVY) prefetch_row<S>(rows_win + (size_t)ent.x * a.Tp);
+            }
+#pragma unroll 1
+            for (int c = 0; c < ngr; c++) {
+                const int j = __shfl_sync(FULL, rec.x, c);
+                const int meta = __shfl_sync(FULL, rec.y, c);
+                const int uo = __shfl_sync(FULL, rec.z, c) - up0;
+                float qt[S];
+                ld_row<S>(rows_lane + (size_t)j * a.Tp, qt);
+                if (meta & 1) {
+                    float x[S];
+#pragma unroll
+                    for (int s = 0; s < S; s++) x[s] = 0.0f;
+                    const int nup = meta >> 8;
+#pragma unroll 1
+                    for (int e = 0; e < nup; e++) {                         // md_routing_operator.f90:37-53, same order
+                        const int idx = uo + e;
+                        int2 u;
+                        u.x = __shfl_sync(FULL, ent.x, idx & 31); u.y = __shfl_sync(FULL, ent.y, idx & 31);
+                        if (idx >= 32) u = tp.tup[up0 + idx];
+                        if (u.y <= UP_HEAVY) {
+#pragma unroll
+                            for (int s = 0; s < S; s++) x[s] = x[s] + r[s];
+                        } else {
+                            if (u.y >= 0) wait_flag(done + u.y, epoch, lane);
+                            float v[S];
+                            ld_row<S>(rows_lane + (size_t)u.x * a.Tp, v);
+#pragma unroll
+                            for (int s = 0; s < S; s++) x[s] = x[s] + v[s];
+                        }
+                    }
+                    const RouteConst cc = shfl_const(ci, c);
+                    route_cell<S, TAPE>(a, cc, m, j, w, lane, t_first, (meta & 2) != 0, x, qt, r);
+                } else {
+#pragma unroll
+                    for (int s = 0; s < S; s++) r[s] = qt[s];               // source cell at the chain head: already final
+                }
+            }
+        }
+        publish_flag(done + task, epoch, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// rows_to_domain: q rows of the routed cells -> qsim_domain layout [t][cell]
+// ------------------------------------------------------------------------------------------------
+constexpr int RD_T = 128;   // time steps per tile
+__global__ void __launch_bounds__(256) rows_to_domain_kernel(const SplitArgs a, const int j_first) {
+    __shared__ float tile[32][RD_T + 1];
+    const int m = blockIdx.z;
+    const int j0 = j_first + blockIdx.x * 32, t0 = blockIdx.y * RD_T;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = warp; i < 32; i += 8) {
+        const int j = j0 + i;
+        if (j >= a.tp.n) break;
+        const float *row = a.rows + ((size_t)m * a.tp.npad + j) * a.Tp + t0;
+#pragma unroll
+        for (int k = 0; k < RD_T / 32; k++) tile[i][k * 32 + lane] = __ldcs(row + k * 32 + lane);   // rows are padded to Tp
+    }
+    __syncthreads();
+    const int j = j0 + lane;
+    if (j < a.tp.n && a.tp.flwacc[j] > 1)
+        for (int i = warp; i < RD_T; i += 8) {
+            const int t = t0 + i;
+            if (t < a.T) a.qdom[((size_t)m * a.T + t) * a.qpitch + j] = tile[lane][i];
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// route_adjoint: LINEAR_ROUTING_B (forward_db.f90:6628-6652), UPSTREAM_DISCHARGE_B (:6520-6564) and the q_b part of
+// GR_A_FORWARD_B (:8104-8118) on whole time windows, chains in reverse order, cells from the chain tail upwards.
+//   q_b(c,t) = sum_g qsim_b(g,t) + w(down(c), t),     qrout_b = (flwacc-1) * c0 * q_b
+//   G(t) = hr_imd_b(t) = qrout_b(t) + E * (G(t+1) - qrout_b(t)),   lr_b += dt * E * hr_imd(t) * (G(t+1) - qrout_b(t)) / (60 lr^2)
+//   w(c,t) = s * G(t)  is what every inflow of c adds to its own q_b
+// ------------------------------------------------------------------------------------------------
+template <int S>
+__device__ __forceinline__ void add_seeds(const SplitArgs &a, int m, int j, int t_first, float (&qb)[S]) {
+    const float *sb = a.qsim_b + (size_t)m * a.T * a.tp.ng;
+    for (int g = a.tp.gauge_first[j]; g >= 0; g = a.tp.gauge_next[g])
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if (t_first + s < a.T) qb[s] = qb[s] + sb[(size_t)(t_first + s) * a.tp.ng + g];        // :8104-8108
+}
+
+template <int S>
+__device__ __forceinline__ void route_cell_b(const SplitArgs &a, const RouteConst &c, int m, int j, int w, int lane, int t_first,
+                                             float (&qb)[S], const float (&hr)[S], float (&wv)[S]) {
+    const float E = c.E;
+    const float g0 = c.h0;                                    // hlr_b carried in from the next window
+    const float k1 = c.fa1 * c.c0;
+    float G = (lane == 31) ? g0 : 0.0f;
+    float A = 1.0f;
+#pragma unroll
+    for (int s = S - 1; s >= 0; s--) {
+        qb[s] = (t_first + s < a.T) ? k1 * qb[s] : 0.0f;     // qrout_b :8118
+        G = fmaf(E, G - qb[s], qb[s]);
+        A *= E;
+    }
+    float Bv = G;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float Bo = __shfl_down_sync(FULL, Bv, d), Ao = __shfl_down_sync(FULL, A, d);
+        if (lane + d < 32) { Bv = fmaf(A, Bo, Bv); A *= Ao; }
+    }
+    G = __shfl_down_sync(FULL, Bv, 1);
+    if (lane == 31) G = g0;
+    float lrs = 0.0f;
+#pragma unroll
+    for (int s = S - 1; s >= 0; s--) {
+        const float hrb = G - qb[s];                          // :6640
+        const float Gn = qb[s] + E * hrb;                     // hr_imd_b :6641
+        if (t_first + s < a.T) lrs = fmaf(hr[s], hrb, lrs);  // arg1_b / E :6643
+        wv[s] = c.s_q * Gn;                                   // :6547
+        G = Gn;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lrs += __shfl_xor_sync(FULL, lrs, o);
+    st_row<S>(a.rows_w + ((size_t)m * a.tp.npad + j) * a.Tp + t_first, wv);
+    if (lane == 0) {
+        float *g = a.grad + (size_t)m * NFIELD * a.tp.npad + j;
+        g[(size_t)F_LR * a.tp.npad] += a.dt * (E * lrs) / ((c.lr * c.lr) * 60.0f);                // :6644
+        a.gcar[(size_t)m * a.tp.npad + j] = G;                // lane 0 ends at the first step of the window
+        if (w == 0) g[(size_t)F_HLR * a.tp.npad] = G;
+    }
+}
+
+template <int S>
+__device__ __noinline__ void route_pair_b(const SplitArgs &a, int m, int jA, int jB, int w, int lane, int t_first) {
+    const size_t npad = a.tp.npad;
+    float sdA[S], sdB[S], hrA[S], hrB[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) { sdA[s] = 0.0f; sdB[s] = 0.0f; }
+    add_seeds<S>(a, m, jA, t_first, sdA);
+    add_seeds<S>(a, m, jB, t_first, sdB);
+    ld_row<S>(a.rows_hr + ((size_t)m * npad + jA) * a.Tp + t_first, hrA);
+    ld_row<S>(a.rows_hr + ((size_t)m * npad + jB) * a.Tp + t_first, hrB);
+    const RouteConst cA = route_const(a, m, jA, a.gcar), cB = route_const(a, m, jB, a.gcar);
+    const float kA = cA.fa1 * cA.c0, kB = cB.fa1 * cB.c0;
+    float GA = cA.h0, GB = cB.h0;
+    float wAn = (w < a.nwin - 1) ? a.rows_w[((size_t)m * npad + jA) * a.Tp + (size_t)(w + 1) * a.W] : 0.0f;   // w_A(t + 1)
+    float lrA = 0.0f, lrB = 0.0f;
+#pragma unroll 1
+    for (int L = 31; L >= 0; L--) {
+        float sA = GA, sB = GB, sw = wAn;
+        if (lane == L) {
+#pragma unroll
+            for (int s = S - 1; s >= 0; s--) {
+                const bool on = t_first + s < a.T;
+                const float qrB = kB * (sdB[s] + sw);           // B's discharge fed A one step later
+                const float hbB = sB - qrB;
+                const float GnB = qrB + cB.E * hbB;
+                const float wB = cB.s_q * GnB;
+                const float qrA = kA * (sdA[s] + wB);           // A's discharge fed B in the same step
+                const float hbA = sA - qrA;
+                const float GnA = qrA + cA.E * hbA;
+                const float wA = cA.s_q * GnA;
+                if (on) {
+                    lrB = fmaf(hrB[s], hbB, lrB); lrA = fmaf(hrA[s], hbA, lrA);
+                    sA = GnA; sB = GnB; sw = wA;
+                }
+                sdA[s] = on ? wA : 0.0f; sdB[s] = on ? wB : 0.0f;
+            }
+        }
+        GA = __shfl_sync(FULL, sA, L); GB = __shfl_sync(FULL, sB, L); wAn = __shfl_sync(FULL, sw, L);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lrA += __shfl_xor_sync(FULL, lrA, o); lrB += __shfl_xor_sync(FULL, lrB, o); }
+    st_row<S>(a.rows_w + ((size_t)m * npad + jA) * a.Tp + t_first, sdA);
+    st_row<S>(a.rows_w + ((size_t)m * npad + jB) * a.Tp + t_first, sdB);
+    if (lane == 0) {
+        float *g = a.grad + (size_t)m * NFIELD * npad;
+        g[(size_t)F_LR * npad + jA] += a.dt * (cA.E * lrA) / ((cA.lr * cA.lr) * 60.0f);
+        g[(size_t)F_LR * npad + jB] += a.dt * (cB.E * lrB) / ((cB.lr * cB.lr) * 60.0f);
+        a.gcar[(size_t)m * npad + jA] = GA; a.gcar[(size_t)m * npad + jB] = GB;
+        if (w == 0) { g[(size_t)F_HLR * npad + jA] = GA; g[(size_t)F_HLR * npad + jB] = GB; }
+    }
+}
+
+template <int S>
+__global__ void __launch_bounds__(128) route_adjoint_kernel(const SplitArgs a, const int w) {
+    const int lane = threadIdx.x & 31;
+    const SplitTopo &tp = a.tp;
+    const int t_first = w * a.W + lane * S;
+    const int epoch = a.nwin - w;
+    const int total = tp.ntask * a.nmember;
+    int tk_next = claim_ticket(a.ticket, lane);
+    for (;;) {
+        const int tk = tk_next;
+        if (tk >= total) break;
+        tk_next = claim_ticket(a.ticket, lane);
+        const int m = tk / tp.ntask, task = tp.ntask - 1 - (tk - m * tp.ntask);
+        const int cb = tp.task_begin[task], ce = tp.task_begin[task + 1];
+        int *rdone = a.rdone + (size_t)m * tp.ntask;
+        if (task >= tp.nchain) {
+            route_pair_b<S>(a, m, tp.task_cells[cb], tp.task_cells[cb + 1], w, lane, t_first);
+            publish_flag(rdone + task, epoch, lane);
+            continue;
+        }
+        const size_t mrow = (size_t)m * tp.npad * a.Tp;
+        float wv[S];
+        {   // w of the consumer of the chain tail (another task), zero at an outlet
+            const int jt = tp.task_cells[ce - 1];
+            const int d = tp.down[jt];
+            if (d >= 0) {
+                wait_flag(rdone + tp.down_task[jt], epoch, lane);
+                ld_row<S>(a.rows_w + mrow + (size_t)d * a.Tp + t_first, wv);
+            } else {
+#pragma unroll
+                for (int s = 0; s < S; s++) wv[s] = 0.0f;
+            }
+        }
+#pragma unroll 1
+        for (int g1 = ce; g1 > cb; g1 -= 32) {
+            const int g0 = max(cb, g1 - 32), ngr = g1 - g0;
+            int4 rec = make_int4(-1, 0, 0, 0);
+            if (lane < ngr) rec = tp.tcell[g0 + lane];
+            RouteConst ci = {0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+            if (lane < ngr && (rec.y & 1)) {
+                prefetch_row<S>(a.rows_hr + mrow + (size_t)rec.x * a.Tp + (size_t)w * a.W);
+                ci = route_const(a, m, rec.x, a.gcar);
+            }
+#pragma unroll 1
+            for (int c = ngr - 1; c >= 0; c--) {
+                const int j = __shfl_sync(FULL, rec.x, c);
+                const int meta = __shfl_sync(FULL, rec.y, c);
+                if (!(meta & 1)) break;                            // source cell at the chain head: nothing to route
+                float hr[S], qb[S];
+                ld_row<S>(a.rows_hr + mrow + (size_t)j * a.Tp + t_first, hr);
+#pragma unroll
+                for (int s = 0; s < S; s++) qb[s] = wv[s];
+                if (meta & 2) add_seeds<S>(a, m, j, t_first, qb);
+                const RouteConst cc = shfl_const(ci, c);
+                route_cell_b<S>(a, cc, m, j, w, lane, t_first, qb, hr, wv);
+            }
+        }
+        publish_flag(rdone + task, epoch, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// vertical_adjoint: reverse time loop of the reservoirs of one cell (vertical_step_b, cell_math.cuh).
+// qt_b(c,t) = dx^2 * 1e-3 / dt * (sum_g qsim_b(g,t) + w(down(c), t)), forward_db.f90:8104-8118.
+// ------------------------------------------------------------------------------------------------
+typedef float BwdStage[4][VT_TK][32];
+
+template <int FAST>
+__global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const __grid_constant__ CUtensorMap tm_prcp,
+                                                                        const __grid_constant__ CUtensorMap tm_pet,
+                                                                        const __grid_constant__ CUtensorMap tm_hp,
+                                                                        const __grid_constant__ CUtensorMap tm_hft,
+                                                                        const SplitArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    BwdStage *stage = reinterpret_cast<BwdStage *>(smem_raw) + warp * VB_NST;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + sizeof(BwdStage) * VT_WARPS * VB_NST) + warp * VB_NST;
+    const int m = blockIdx.y;
+    const int j0 = (blockIdx.x * VT_WARPS + warp) * 32;
+    const int n = a.tp.n, npad = a.tp.npad, T = a.T;
+    if (j0 >= n) return;
+    const int j = j0 + lane;
+    const bool valid = j < n;
+    const int nst = (T + VT_TK - 1) / VT_TK;
+    constexpr uint32_t STAGE_BYTES = sizeof(BwdStage);
+    const int yb = m * T;   // tape rows of member m
+
+    auto issue = [&](int slot, int st) {
+        mbar_expect_tx(&bars[slot], STAGE_BYTES);
+        tma_load_2d(&stage[slot][0][0][0], &tm_prcp, j0, st * VT_TK, &bars[slot]);
+        tma_load_2d(&stage[slot][1][0][0], &tm_pet, j0, st * VT_TK, &bars[slot]);
+        tma_load_2d(&stage[slot][2][0][0], &tm_hp, j0, yb + st * VT_TK, &bars[slot]);
+        tma_load_2d(&stage[slot][3][0][0], &tm_hft, j0, yb + st * VT_TK, &bars[slot]);
+    };
+    if (lane == 0) {
+        for (int s = 0; s < VB_NST; s++) mbar_init(&bars[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < VB_NST && s < nst; s++) issue(s, nst - 1 - s);
+    }
+    __syncwarp();
+
+    const float *fld = a.fields + (size_t)m * NFIELD * npad + j;
+    CellConst k = make_const(1.0f, 1.0f, 0.0f, 1.0f, 1, a.dt, a.dx);
+    int d = -1, dlag = 0, gfirst = -1;
+    if (valid) {
+        k = make_const(fld[(size_t)F_CP * npad], fld[(size_t)F_CFT * npad], fld[(size_t)F_EXC * npad], fld[(size_t)F_LR * npad],
+                       a.tp.flwacc[j], a.dt, a.dx);
+        d = a.tp.down[j]; dlag = a.tp.down_lag[j]; gfirst = a.tp.gauge_first[j];
+    }
+    const float *wrow = (d >= 0) ? a.rows_w + ((size_t)m * npad + d) * a.Tp : nullptr;
+    const float *sb = a.qsim_b + (size_t)m * T * a.tp.ng;
+    const int ng = a.tp.ng;
+    float hp_b = 0.0f, hft_b = 0.0f, cp_b = 0.0f, cft_b = 0.0f, exc_b = 0.0f;
+
+    auto load_w = [&](int st, float *v) {
+#pragma unroll
+        for (int i = 0; i < VT_TK; i++) v[i] = 0.0f;
+        if (wrow) {
+            if (!dlag) ld8(wrow + (size_t)st * VT_TK, v);
+            else {   // late cell of a pit pair: its discharge fed the partner one step later
+#pragma unroll
+                for (int i = 0; i < VT_TK; i++) {
+                    const int t = st * VT_TK + i + 1;
+                    v[i] = (t < T) ? __ldcg(wrow + t) : 0.0f;
+                }
+            }
+        }
+    };
+    float wn[VT_TK];
+    load_w(nst - 1, wn);
+    uint32_t parity = 0;
+    int slot = 0;
+#pragma unroll 1
+    for (int it = 0; it < nst; it++) {
+        const int st = nst - 1 - it;
+        float wq[VT_TK];
+#pragma unroll
+        for (int i = 0; i < VT_TK; i++) wq[i] = wn[i];
+        if (st > 0) load_w(st - 1, wn);
+        mbar_wait(&bars[slot], parity);
+        float pv[VT_TK], ev[VT_TK], hpv[VT_TK], hfv[VT_TK];
+#pragma unroll
+        for (int i = 0; i < VT_TK; i++) {
+            pv[i] = stage[slot][0][i][lane]; ev[i] = stage[slot][1][i][lane];
+            hpv[i] = stage[slot][2][i][lane]; hfv[i] = stage[slot][3][i][lane];
+        }
+        __syncwarp();
+        if (lane == 0 && it + VB_NST < nst) issue(slot, st - VB_NST);
+#pragma unroll
+        for (int i = VT_TK - 1; i >= 0; i--) {
+            const int t = st * VT_TK + i;
+            if (valid && t < T) {
+                float q_b = wq[i];
+                if (gfirst >= 0)
+                    for (int g = gfirst; g >= 0; g = a.tp.gauge_next[g]) q_b += sb[(size_t)t * ng + g];
+                const float qt_b = fdiv<FAST>(a.dx * a.dx * 0.001f * q_b, a.dt);                   // :8114
+                vertical_step_b<FAST>(k, pv[i], ev[i], hpv[i], hfv[i], qt_b, hp_b, hft_b, cp_b, cft_b, exc_b);
+            }
+        }
+        if (++slot == VB_NST) { slot = 0; parity ^= 1u; }
+    }
+    if (valid) {
+        float *g = a.grad + (size_t)m * NFIELD * npad + j;
+        g[(size_t)F_CP * npad] = cp_b; g[(size_t)F_CFT * npad] = cft_b; g[(size_t)F_EXC * npad] = exc_b;
+        g[(size_t)F_HP * npad] = hp_b; g[(size_t)F_HFT * npad] = hft_b;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_columns_kernel(const float *raw, int64_t stride, const int32_t *idx, int n, int npad, int T, float *out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= npad) return;
+    const int src = j < n ? idx[j] : -1;
+    for (int t = blockIdx.y; t < T; t += gridDim.y) out[(size_t)t * npad + j] = src >= 0 ? raw[(int64_t)t * stride + src] : 0.0f;
+}
+__global__ void scatter_columns_kernel(const float *src, int64_t pitch, const int32_t *idx, int n, int T, int64_t stride, float *out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const int dst = idx[j];
+    if (dst < 0) return;
+    for (int t = blockIdx.y; t < T; t += gridDim.y) out[(int64_t)t * stride + dst] = src[(size_t)t * pitch + j];
+}
+__global__ void sum_domain_kernel(const float *src, int64_t pitch, int n, int T, double *out) {
+    double acc = 0.0;
+    for (int t = blockIdx.y; t < T; t += gridDim.y)
+        for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) acc += (double)src[(size_t)t * pitch + j];
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+int split_pick_window(int T, int *S, int *nwin) {
+    const int nw = (T + 1023) / 1024;
+    const int need = (T + nw - 1) / nw;
+    int s = 8;
+    while (32 * s < need) s += 8;
+    *S = s; *nwin = nw;
+    return 32 * s;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tensor_map_2d(CUtensorMap *tm, const float *base, uint64_t cols, uint64_t rows, uint64_t pitch_elems, const char **err) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || !p) {
+            cudaGetLastError();
+            *err = "cuTensorMapEncodeTiled is not available from the driver";
+            return 1;
+        }
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    if ((pitch_elems * sizeof(float)) % 16 != 0 || (reinterpret_cast<uintptr_t>(base) % 16) != 0) {
+        *err = "tensor map: base and row pitch must be multiples of 16 bytes";
+        return 1;
+    }
+    const cuuint64_t gdim[2] = {cols, rows};
+    const cuuint64_t gstride[1] = {pitch_elems * sizeof(float)};
+    const cuuint32_t box[2] = {32, (cuuint32_t)VT_TK};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed"; return 1; }
+    return 0;
+}
+
+cudaError_t launch_vertical_forward(const SplitArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, int math_mode, bool tape,
+                                    cudaStream_t s) {
+    dim3 grid((unsigned)((a.tp.n + VT_WARPS * 32 - 1) / (VT_WARPS * 32)), (unsigned)a.nmember);
+    const size_t smem = sizeof(FwdStage) * VT_WARPS * VF_NST + sizeof(uint64_t) * VT_WARPS * VF_NST;
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, VT_WARPS * 32, smem, s>>>(prcp, pet, a);
+        return cudaGetLastError();
+    };
+    if (math_mode) return tape ? go(vertical_forward_kernel<1, 1>) : go(vertical_forward_kernel<1, 0>);
+    return tape ? go(vertical_forward_kernel<0, 1>) : go(vertical_forward_kernel<0, 0>);
+}
+
+template <typename K> static cudaError_t persistent_grid(K kern, int *blocks) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, 0);
+    if (e != cudaSuccess) return e;
+    *blocks = sms * (per_sm > 0 ? per_sm : 1);
+    return cudaSuccess;
+}
+
+template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bool tape, cudaStream_t s) {
+    int blocks = 0;
+    cudaError_t e = tape ? persistent_grid(route_forward_kernel<S, 1>, &blocks) : persistent_grid(route_forward_kernel<S, 0>, &blocks);
+    if (e != cudaSuccess) return e;
+    const long long total = (long long)a.tp.ntask * a.nmember;
+    const int need = (int)((total + 3) / 4);
+    if (blocks > need) blocks = need > 0 ? need : 1;
+    for (int w = 0; w < a.nwin; w++) {
+        e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), s);
+        if (e != cudaSuccess) return e;
+        if (tape) route_forward_kernel<S, 1><<<blocks, 128, 0, s>>>(a, w);
+        else route_forward_kernel<S, 0><<<blocks, 128, 0, s>>>(a, w);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s) {
+    if (a.tp.ntask == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(a.done, 0, sizeof(int) * (size_t)a.tp.ntask * a.nmember, s);
+    if (e != cudaSuccess) return e;
+    switch (a.W / 32) {
+        case 8: return route_forward_windows<8>(a, tape, s);
+        case 16: return route_forward_windows<16>(a, tape, s);
+        case 24: return route_forward_windows<24>(a, tape, s);
+        default: return route_forward_windows<32>(a, tape, s);
+    }
+}
+
+template <int S> static cudaError_t route_adjoint_windows(const SplitArgs &a, cudaStream_t s) {
+    int blocks = 0;
+    cudaError_t e = persistent_grid(route_adjoint_kernel<S>, &blocks);
+    if (e != cudaSuccess) return e;
+    const long long total = (long long)a.tp.ntask * a.nmember;
+    const int need = (int)((total + 3) / 4);
+    if (blocks > need) blocks = need > 0 ? need : 1;
+    for (int w = a.nwin - 1; w >= 0; w--) {
+        e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), s);
+        if (e != cudaSuccess) return e;
+        route_adjoint_kernel<S><<<blocks, 128, 0, s>>>(a, w);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_route_adjoint(const SplitArgs &a, cudaStream_t s) {
+    if (a.tp.ntask == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(a.rdone, 0, sizeof(int) * (size_t)a.tp.ntask * a.nmember, s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(a.gcar, 0, sizeof(float) * (size_t)a.tp.npad * a.nmember, s);
+    if (e != cudaSuccess) return e;
+    switch (a.W / 32) {
+        case 8: return route_adjoint_windows<8>(a, s);
+        case 16: return route_adjoint_windows<16>(a, s);
+        case 24: return route_adjoint_windows<24>(a, s);
+        default: return route_adjoint_windows<32>(a, s);
+    }
+}
+
+cudaError_t launch_rows_to_domain(const SplitArgs &a, cudaStream_t s) {
+    const int j_first = (a.first_routed / 32) * 32;
+    if (j_first >= a.tp.n) return cudaSuccess;
+    dim3 grid((unsigned)((a.tp.n - j_first + 31) / 32), (unsigned)((a.T + RD_T - 1) / RD_T), (unsigned)a.nmember);
+    rows_to_domain_kernel<<<grid, 256, 0, s>>>(a, j_first);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_vertical_adjoint(const SplitArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, const CUtensorMap &hp,
+                                    const CUtensorMap &hft, int math_mode, cudaStream_t s) {
+    dim3 grid((unsigned)((a.tp.n + VT_WARPS * 32 - 1) / (VT_WARPS * 32)), (unsigned)a.nmember);
+    const size_t smem = sizeof(BwdStage) * VT_WARPS * VB_NST + sizeof(uint64_t) * VT_WARPS * VB_NST;
+    cudaError_t e;
+    if (math_mode) {
+        e = cudaFuncSetAttribute(vertical_adjoint_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        vertical_adjoint_kernel<1><<<grid, VT_WARPS * 32, smem, s>>>(prcp, pet, hp, hft, a);
+    } else {
+        e = cudaFuncSetAttribute(vertical_adjoint_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        vertical_adjoint_kernel<0><<<grid, VT_WARPS * 32, smem, s>>>(prcp, pet, hp, hft, a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_columns(const float *raw, int64_t stride, const int32_t *idx, int n, int npad, int T, float *out,
+                                cudaStream_t s) {
+    dim3 grid((unsigned)((npad + 255) / 256), (unsigned)(T < 64 ? T : 64));
+    pack_columns_kernel<<<grid, 256, 0, s>>>(raw, stride, idx, n, npad, T, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_scatter_columns(const float *src, int64_t pitch, const int32_t *idx, int n, int T, int64_t stride, float *out,
+                                   cudaStream_t s) {
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)(T < 64 ? T : 64));
+    scatter_columns_kernel<<<grid, 256, 0, s>>>(src, pitch, idx, n, T, stride, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_sum_domain(const float *src, int64_t pitch, int n, int T, double *out, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), s);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)std::min(1024, (n + 255) / 256), (unsigned)(T < 64 ? T : 64));
+    sum_domain_kernel<<<grid, 256, 0, s>>>(src, pitch, n, T, out);
+    return cudaGetLastError();
+}
+
+}  // namespace smash

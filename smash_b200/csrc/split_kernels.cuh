@@ -1,0 +1,87 @@
+// split_kernels.cuh -- argument blocks and launch wrappers of the split engine (sm_100a only).
+//
+// Kernels:
+//   vertical_forward   one thread per cell, whole time loop, reservoirs in registers, forcing tiles [4 steps][32 cells]
+//                      by 2-D TMA (cp.async.bulk.tensor, SASS UTMALDG) into a per-warp mbarrier ring; writes the
+//                      cell's runoff series qt as a row [cell][time]
+//   route_forward      one warp per heavy-path chain, time axis across the lanes: upstream_discharge + linear_routing
+//                      as a scan; turns qt rows into q rows in place
+//   rows_to_domain     [cell][time] -> [time][cell] for the routed cells (qsim_domain layout)
+//   route_adjoint      reverse of route_forward (LINEAR_ROUTING_B, UPSTREAM_DISCHARGE_B): w rows, lr_b, hlr_b
+//   vertical_adjoint   reverse time loop per cell (GR_TRANSFER_B, GR_EXCHANGE_B, GR_PRODUCTION_B)
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.cuh"
+#include "route_graph.hpp"
+
+namespace smash {
+
+struct SplitTopo {
+    int n, npad, ng, ntask, nchain;
+    const int32_t *flwacc;       // [npad] (1 on padding)
+    const int32_t *up_begin;     // [n + 1]
+    const RouteUp *up;
+    const int32_t *down;         // [npad] consumer cell or -1
+    const int32_t *down_task;    // [npad]
+    const uint8_t *down_lag;     // [npad] 1: the consumer reads this cell's previous time step (late cell of a pit pair)
+    const int32_t *task_begin, *task_cells;
+    const int4 *tcell;           // TaskCell records, parallel to task_cells
+    const int2 *tup;             // RouteUp entries of the task cells
+    const int32_t *gauge_first;  // [npad]
+    const int32_t *gauge_next;   // [ng]
+};
+
+struct SplitArgs {
+    SplitTopo tp;
+    int T, Tp, W, nwin;          // time steps, row pitch (= nwin * W), steps per window (= 32 * S), windows
+    int first_routed;            // smallest cell index with flwacc > 1
+    int nmember;
+    float dt, dx;
+    int save_q, save_netp;
+    const float *fields;         // [m][NFIELD][npad]
+    float *fstates;              // [m][3][npad]
+    float *rows;                 // [m][npad][Tp]   qt of every cell after vertical_forward, q after route_forward
+    float *qdom;                 // [m][T][qpitch]  domain discharge, cell order j
+    float *netp;                 // [m][T][qpitch]  qt (save_net_prcp_domain)
+    int64_t qpitch;
+    float *qsim;                 // [m][T][ng]
+    float *tape_hp, *tape_hft;   // [m][T][npad]    pre-step reservoir states (gradient runs)
+    float *rows_hr;              // [m][npad][Tp]   hr_imd = hlr0 + qup of the routed cells (gradient runs)
+    float *hcar;                 // [m][npad]       routing state carried across windows (starts as the hlr field)
+    int *done;                   // [m][ntask]      forward: windows finished by each task
+    unsigned int *ticket;
+    // adjoint
+    const float *qsim_b;         // [m][T][ng]
+    float *rows_w;               // [m][npad][Tp]   s * hr_imd_b of the routed cells (UPSTREAM_DISCHARGE_B)
+    float *gcar;                 // [m][npad]       hlr_b carried across windows
+    float *grad;                 // [m][NFIELD][npad]
+    int *rdone;                  // [m][ntask]
+};
+
+// 2-D tensor map over a [rows][pitch] float array, box = 8 rows x 32 columns.  cols = valid columns (the rest reads 0).
+int make_tensor_map_2d(CUtensorMap *tm, const float *base, uint64_t cols, uint64_t rows, uint64_t pitch_elems, const char **err);
+
+cudaError_t launch_vertical_forward(const SplitArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, int math_mode, bool tape,
+                                    cudaStream_t s);
+cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s);     // all windows
+cudaError_t launch_rows_to_domain(const SplitArgs &a, cudaStream_t s);
+cudaError_t launch_route_adjoint(const SplitArgs &a, cudaStream_t s);                // all windows, reverse order
+cudaError_t launch_vertical_adjoint(const SplitArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, const CUtensorMap &hp,
+                                    const CUtensorMap &hft, int math_mode, cudaStream_t s);
+
+// out[t * pitch + j] = raw[t * stride + idx[j]]  (j < n; padding columns get 0)
+cudaError_t launch_pack_columns(const float *raw, int64_t stride, const int32_t *idx, int n, int npad, int T, float *out,
+                                cudaStream_t s);
+// out[t * stride + idx[j]] = src[t * pitch + j]
+cudaError_t launch_scatter_columns(const float *src, int64_t pitch, const int32_t *idx, int n, int T, int64_t stride, float *out,
+                                   cudaStream_t s);
+// sum over t < T, j < n of a [T][pitch] array (double accumulation)
+cudaError_t launch_sum_domain(const float *src, int64_t pitch, int n, int T, double *out, cudaStream_t s);
+
+int split_pick_window(int T, int *S, int *nwin);   // returns W = 32 * S
+
+}  // namespace smash

@@ -107,3 +107,64 @@ def test_mesh_golden_integers(golden):
     assert np.array_equal(d["flwdir"], golden["mesh_io.flwdir"].astype(np.int32))
     assert np.array_equal(d["flwacc"], golden["xy_mesh.flwacc"])
     assert np.array_equal(d["gauge_pos"], golden["mesh_io.gauge_pos"])
+
+
+def mesh_chains(m):
+    pk = L.Packed()
+    me = L.pack_mesh(m.mesh, m.setup, pk)
+    info = (C.c_int64 * 8)()
+    n = int(((m.mesh.active_cell == 1) & (m.mesh._local_active_cell == 1)).sum())
+    cell, task, pos, down = (np.zeros(n, np.int32) for _ in range(4))
+    L.check(L.lib().smash_b200_mesh_chains(C.byref(me), info, L._ip(cell), L._ip(task), L._ip(pos), L._ip(down)))
+    return cell, task, pos, down, list(info)
+
+
+def check_chains(m, cell, task, pos, down, info):
+    """Invariants the routing pass of the split engine relies on (route_graph.hpp)."""
+    nrow = m.mesh.nrow
+    n = info[0]
+    flwacc = m.mesh.flwacc.ravel(order="F")[cell]
+    # cell order = the stored path restricted to computed cells
+    p = m.mesh.path
+    ok = (p[0] >= 0) & (p[1] >= 0)
+    flat = p[0][ok] + p[1][ok].astype(np.int64) * nrow
+    act = ((m.mesh.active_cell == 1) & (m.mesh._local_active_cell == 1)).ravel(order="F")
+    assert np.array_equal(cell, flat[act[flat]])
+    # every gathering cell is routed by exactly one task, lone source cells by none
+    assert np.all(task[flwacc > 1] >= 0)
+    assert info[6] == int((flwacc <= 1).sum())
+    assert len(np.unique(task[task >= 0])) == info[1] + info[2]
+    has = down >= 0
+    src, dst = np.nonzero(has)[0], down[has]
+    assert np.all(flwacc[dst] > 1)                                         # md_routing_operator.f90:35
+    same = task[src] == task[dst]
+    # inside a chain the consumer directly follows its producer; across tasks the producer's task runs earlier
+    chain = same & (task[src] < info[1])
+    assert np.all(pos[dst[chain]] == pos[src[chain]] + 1)
+    cross = ~same & (task[src] >= 0)
+    assert np.all(task[src[cross]] < task[dst[cross]])
+    # a producer that feeds another task is the last cell of its own chain
+    last = np.zeros(info[1] + info[2], np.int64)
+    np.maximum.at(last, task[task >= 0], pos[task >= 0])
+    assert np.all(pos[src[cross]] == last[task[src[cross]]])
+    # pit pairs: two cells that gather each other, routed together
+    pair = same & (task[src] >= info[1])
+    assert pair.sum() == 2 * info[2]
+    assert np.all(down[dst[pair]] == src[pair])
+
+
+def test_chains_cance():
+    m = cases.cance(T=24)
+    out = mesh_chains(m)
+    check_chains(m, *out)
+    info = out[-1]
+    assert info[0] == 383 and info[2] == 0 and info[5] == 31 and info[7] == 1
+
+
+def test_chains_france():
+    m = cases.france(T=24)
+    out = mesh_chains(m)
+    check_chains(m, *out)
+    info = out[-1]
+    assert info[0] == 906044 and info[2] == 50 and info[7] == 1
+    assert info[3] <= 16 and info[5] <= 820

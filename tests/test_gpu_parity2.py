@@ -173,7 +173,9 @@ def test_multiple_run_chunked_equals_single_launch(golden):
     for j, n in enumerate(("cp", "cft", "exc", "lr")):
         getattr(f.parameters, n)[...] = smp[j, k]
     smash_b200.forward(f.setup, f.mesh, f.input_data, f.parameters, f.parameters.copy(), f.states, f.states.copy(), f.output)
-    assert np.array_equal(f.output.qsim, out[0][1][:, :, k])
+    # (bit-identical when both calls run on the same engine; ensembles default to the fused engine, single runs to the
+    # split engine, whose routing scan rounds differently in the last place)
+    assert np.allclose(f.output.qsim, out[0][1][:, :, k], rtol=1e-5, atol=1e-9)
     assert np.isclose(float(f.output.cost), out[0][0][k], rtol=1e-6)
 
 

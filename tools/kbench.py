@@ -37,7 +37,8 @@ fw = []
 for i in range(a.reps + 2):
     L.check(lib.smash_b200_plan_run_forward(plan, C.byref(ms))); fw.append(ms.value)
 fw = np.array(fw[2:])
-line = f"{a.mesh} T={m.setup._ntime_step} B={int(info[2])} blocks={int(info[1])} members={a.members} math={a.math} crit_ticks={int(info[8])} | fwd {fw.mean():.3f} ms (min {fw.min():.3f}) {units/fw.mean()/1e-3:.3e} cs/s"
+eng = "split" if int(info[11]) == -1 else "fused"
+line = f"{a.mesh} T={m.setup._ntime_step} engine={eng} B={int(info[2])} blocks={int(info[1])} members={a.members} math={a.math} crit={int(info[8])} | fwd {fw.mean():.3f} ms (min {fw.min():.3f}) {units/fw.mean()/1e-3:.3e} cs/s"
 if a.grad:
     g = []
     for i in range(a.reps + 1):
