@@ -6,10 +6,13 @@ France 1 km flow-direction mesh (906 044 active cells, mesh_France.hdf5 -> tests
 T = 720 synthetic hourly steps (SURVEY.md 8d recipe), gr-a, default parameters, save_qsim_domain as in
 setup_France.yaml.  One "step" = one forward run over the whole mesh and all T time steps.
 
-  value   active-cell-timesteps/s, forcing already resident in HBM (plan API), kernel launches only
+  value   active-cell-timesteps/s, forcing already resident in HBM (plan API), kernel launches only; the result
+          (domain discharge in the reference's sparse layout [t][k]) stays in HBM
   e2e     same metric through the drop-in call smash_b200.forward(...) with HOST arrays: per step the forcing
           (5.2 GB) goes host->device and the domain discharge (2.6 GB) comes back
-  roofline  forward kernel: algorithmic bytes (12 B per active cell-step: prcp + pet read, q written) / device time
+  roofline  the longest kernel of the step (split engine: vertical_forward / route_forward / rows_to_domain), its
+          algorithmic bytes / its CUDA-event time; "step" = the whole forward step against the
+          12 B per active cell-step of SURVEY.md 8(d) (prcp + pet read, q written)
   cpu_baseline  the C oracle (restatement of the Fortran solver, oracle/) on one host core, bounded sample
   extra   fwd+adjoint gradient on the same mesh, Cance gradient latency, 4096-member Cance ensemble
 
@@ -181,16 +184,19 @@ def main():
     lib.smash_b200_plan_info(plan, info)
 
     ms = C.c_float(0.0)
+    kt = (C.c_float * 5)()
     for _ in range(args.warmup):
         L.check(lib.smash_b200_plan_run_forward(plan, C.byref(ms)))
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
-    kernel_ms = []
+    kernel_ms, per_kernel = [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
         L.check(lib.smash_b200_plan_run_forward(plan, C.byref(ms)))   # returns after cudaEventSynchronize
         kernel_ms.append(ms.value)
+        L.check(lib.smash_b200_plan_kernel_times(plan, kt))           # events recorded inside the run, read after it
+        per_kernel.append([kt[i] for i in range(5)])
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -200,13 +206,40 @@ def main():
     chk = C.c_double(0.0)
     L.check(lib.smash_b200_plan_checksum(plan, C.byref(chk)))
 
-    # ---- roofline of the forward kernel (device events, average launch)
+    # ---- roofline (device events on the launching stream, average over the timed launches)
     peak, peak_src = measured_peaks()
-    alg_bytes = 12.0 * units
-    achieved = alg_bytes / (kms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "forward_kernel<0,0>", "kernel_ms": kms,
-                "algorithmic_bytes_per_launch": alg_bytes}
+    split = int(info[11]) == -1
+    step_bytes = 12.0 * units
+    roofline_step = {"achieved": step_bytes / (kms * 1e-3) / 1e9, "frac": step_bytes / (kms * 1e-3) / 1e9 / peak,
+                     "algorithmic_bytes_per_step": step_bytes, "device_ms": kms}
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+    if split:
+        pk_ms = np.mean(np.array(per_kernel), axis=0)
+        nrt, nedge = float(lib.smash_b200_plan_stat(plan, b"routed_cells")), float(lib.smash_b200_plan_stat(plan, b"inflow_edges"))
+        names = ["vertical_forward_kernel", "route_forward_kernel", "rows_to_domain_kernel"]
+        # algorithmic bytes per launch: reservoir pass 8 B forcing + 4 B series per cell-step;
+        # routing 4 B per routed cell-step in and out + 4 B per inflow edge-step; export 8 B per routed cell-step
+        kbytes = [12.0 * units, 4.0 * T * (2.0 * nrt + nedge), 8.0 * T * nrt]
+        kernels = {names[i]: {"ms": float(pk_ms[i]), "share": float(pk_ms[i] / kms), "algorithmic_bytes": kbytes[i],
+                              "achieved_gbs": kbytes[i] / (pk_ms[i] * 1e-3) / 1e9, "frac": kbytes[i] / (pk_ms[i] * 1e-3) / 1e9 / peak,
+                              "traffic": traffic.get(names[i])} for i in range(3) if pk_ms[i] > 0}
+        top = max(kernels, key=lambda k: kernels[k]["ms"])
+        roofline = {"bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                    "frac": kernels[top]["frac"], "traffic": kernels[top]["traffic"], "peak_source": peak_src, "kernel": top,
+                    "kernel_ms": kernels[top]["ms"], "algorithmic_bytes_per_launch": kernels[top]["algorithmic_bytes"],
+                    "kernels": kernels, "step": roofline_step}
+        launches_per_step = len(kernels)
+    else:
+        roofline = {"bound": "hbm", "achieved": roofline_step["achieved"], "peak": peak, "unit": "GB/s",
+                    "frac": roofline_step["frac"], "traffic": traffic.get("forward_kernel"), "peak_source": peak_src,
+                    "kernel": "forward_kernel", "kernel_ms": kms, "algorithmic_bytes_per_launch": step_bytes,
+                    "step": roofline_step}
+        launches_per_step = 1
 
     extra = {}
     if not args.no_extra:
@@ -266,12 +299,16 @@ def main():
             "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"France 1km mesh forward gr-a, nac={nac}, T={T}, save_qsim_domain (setup_France.yaml)",
-                       "blocks": int(info[1]), "block_size": int(info[2]), "max_skew": int(info[3]),
-                       "cross_block_edges": int(info[5]), "pit_pairs": int(info[6]),
+                       "engine": "split (reservoir pass per cell + routing scan per heavy-path chain)" if split else "fused tick wavefront",
+                       "ctas": int(info[1]), "cta_size": int(info[2]),
+                       **({"chains": int(info[5]), "routing_tasks": int(info[10]), "chain_dependency_height": int(info[3]),
+                           "longest_dependency_path_cells": int(info[8])} if split else
+                          {"max_skew": int(info[3]), "cross_block_edges": int(info[5])}),
+                       "pit_pairs": int(info[6]),
                        "l2": "inputs larger than L2 (5.2 GB forcing streamed once per step)",
                        "parallelism": f"{world} independent domain replica(s), no collective", "checksum_q": chk.value,
                        "model_build_s": t_build},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "extra": extra,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks, "extra": extra,
         }))
     if dist is not None:
         dist.destroy_process_group()

@@ -182,6 +182,11 @@ int smash_b200_plan_get_qsim(SmashPlan *plan, float *qsim /* F(ng,T,nmember) */,
 int smash_b200_plan_get_gradient(SmashPlan *plan, SmashParameters *parameters_b, SmashStates *states_b);
 /* sum of the device-resident q of the last run over all active cell-steps (size-independent checksum) */
 int smash_b200_plan_checksum(SmashPlan *plan, double *sum_q);
+/* device time (ms, CUDA events on the plan's stream) of the kernels of the last run: [0] vertical_forward,
+ * [1] route_forward, [2] rows_to_domain, [3] route_adjoint, [4] vertical_adjoint; -1 where a kernel did not run */
+int smash_b200_plan_kernel_times(SmashPlan *plan, float ms[5]);
+/* named facts about a plan: "engine" (0 fused, 1 split), "routed_cells", "source_cells", "inflow_edges"; -1 if unknown */
+double smash_b200_plan_stat(const SmashPlan *plan, const char *name);
 /* topology facts: [0]=ncell_active [1]=nblocks [2]=block_size [3]=max in-block skew [4]=total ticks over blocks
  * [5]=cross-block edges [6]=pit pairs [7]=kernel launches of the last run_* call [8]=critical path over blocks in
  * ticks [9]=longest chain of dependent blocks [10..11]=reserved */

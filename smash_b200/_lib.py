@@ -77,7 +77,7 @@ EXPORTS = [
     "smash_b200_plan_destroy", "smash_b200_plan_set_forcing", "smash_b200_plan_set_fields",
     "smash_b200_plan_run_forward", "smash_b200_plan_run_gradient", "smash_b200_plan_get_qsim",
     "smash_b200_plan_get_gradient", "smash_b200_plan_checksum", "smash_b200_plan_info", "smash_b200_plan_order",
-    "smash_b200_mesh_order", "smash_b200_mesh_chains",
+    "smash_b200_mesh_order", "smash_b200_mesh_chains", "smash_b200_plan_kernel_times", "smash_b200_plan_stat",
 ]
 
 _lib = None
@@ -98,6 +98,8 @@ def lib():
         L.smash_b200_plan_destroy.restype = None
         L.smash_b200_plan_destroy.argtypes = [C.c_void_p]
         L.smash_b200_clear_cache.restype = None
+        L.smash_b200_plan_stat.restype = C.c_double
+        L.smash_b200_plan_stat.argtypes = [C.c_void_p, C.c_char_p]
         _lib = L
     return _lib
 

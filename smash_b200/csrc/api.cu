@@ -90,7 +90,7 @@ struct SplitState {
     RouteGraph rg;
     int S = 0, W = 0, nwin = 0, Tp = 0;
     int64_t qpitch = 0;
-    DBuf<int32_t> d_flwacc, d_up_begin, d_down, d_down_task, d_task_begin, d_task_cells, d_gfirst, d_gnext;
+    DBuf<int32_t> d_flwacc, d_up_begin, d_down, d_down_task, d_down_need, d_task_begin, d_task_cells, d_gfirst, d_gnext;
     DBuf<RouteUp> d_up, d_tup;
     DBuf<TaskCell> d_tcell;
     DBuf<uint8_t> d_down_lag;
@@ -115,6 +115,8 @@ struct SmashPlan {
     int ncell = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaEvent_t evk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // per-kernel marks
+    int kmark[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 1: evk[i] was recorded in the last run
     int launches = 0;
     // topology on device
     DBuf<int32_t> d_cell, d_off, d_flwacc, d_up_begin, d_down_kind, d_down_lane, d_gfirst, d_gnext, d_hmax, d_sparse_k;
@@ -140,6 +142,7 @@ struct SmashPlan {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
+        for (auto &e : evk) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -206,6 +209,7 @@ static int plan_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *m
     Topology &tp = pl.tp;
     CU(cudaStreamCreateWithFlags(&pl.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&pl.ev0)); CU(cudaEventCreate(&pl.ev1)); CU(cudaEventCreate(&pl.ev2));
+    for (auto &e : pl.evk) CU(cudaEventCreate(&e));
     cudaStream_t s = pl.stream;
     TRY(pl.d_cell.upload(tp.cell, s)); TRY(pl.d_off.upload(tp.off, s)); TRY(pl.d_flwacc.upload(tp.flwacc, s));
     TRY(pl.d_late.upload(tp.late, s)); TRY(pl.d_early.upload(tp.early, s)); TRY(pl.d_up_begin.upload(tp.up_begin, s));
@@ -262,24 +266,35 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     sp.Tp = sp.W * sp.nwin;
     CU(cudaStreamCreateWithFlags(&pl.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&pl.ev0)); CU(cudaEventCreate(&pl.ev1)); CU(cudaEventCreate(&pl.ev2));
+    for (auto &e : pl.evk) CU(cudaEventCreate(&e));
     cudaStream_t s = pl.stream;
     const int npad = rg.npad;
     std::vector<int32_t> cell(npad, -1), flw(npad, 1), down(npad, -1), down_task(npad, -1), gfirst(npad, -1);
     std::vector<uint8_t> down_lag(npad, 0);
+    std::vector<int32_t> down_need(npad, 0xffff), pos_in_task(rg.n, 0);
+    for (int t = 0; t < rg.ntask; t++)
+        for (int e = rg.task_begin[t]; e < rg.task_begin[t + 1]; e++) pos_in_task[rg.task_cells[e]] = e - rg.task_begin[t];
+    for (int j = 0; j < rg.n; j++) {
+        const int d = rg.down[j];
+        if (d >= 0 && rg.down_task[j] >= 0 && rg.down_task[j] < rg.nchain) {
+            const int len = rg.task_begin[rg.down_task[j] + 1] - rg.task_begin[rg.down_task[j]];
+            if (len < 0xffff) down_need[j] = len - pos_in_task[d];   // cells done counted from the tail, d included
+        }
+    }
     for (int j = 0; j < rg.n; j++) {
         cell[j] = rg.cell[j]; flw[j] = rg.flwacc[j]; down[j] = rg.down[j]; down_task[j] = rg.down_task[j]; gfirst[j] = rg.gauge_first[j];
         if (rg.down[j] >= 0 && j > rg.down[j]) down_lag[j] = 1;   // producer later in path: the reader sees its previous step
     }
     TRY(pl.d_cell.upload(cell, s)); TRY(pl.d_sparse_k.upload(tp.sparse_k, s));
     TRY(sp.d_flwacc.upload(flw, s)); TRY(sp.d_up_begin.upload(rg.up_begin, s)); TRY(sp.d_up.upload(rg.up, s));
-    TRY(sp.d_down.upload(down, s)); TRY(sp.d_down_task.upload(down_task, s)); TRY(sp.d_down_lag.upload(down_lag, s));
+    TRY(sp.d_down.upload(down, s)); TRY(sp.d_down_task.upload(down_task, s)); TRY(sp.d_down_need.upload(down_need, s)); TRY(sp.d_down_lag.upload(down_lag, s));
     TRY(sp.d_task_begin.upload(rg.task_begin, s)); TRY(sp.d_task_cells.upload(rg.task_cells, s));
     TRY(sp.d_gfirst.upload(gfirst, s)); TRY(sp.d_gnext.upload(rg.gauge_next, s));
     TRY(sp.d_tcell.upload(rg.tcell, s)); TRY(sp.d_tup.upload(rg.tup, s));
     TRY(pl.d_ticket.ensure(1)); TRY(pl.d_sum.ensure(1));
     SplitTopo &t = sp.topo;
     t.n = rg.n; t.npad = npad; t.ng = mesh->ng; t.ntask = rg.ntask; t.nchain = rg.nchain;
-    t.flwacc = sp.d_flwacc.p; t.up_begin = sp.d_up_begin.p; t.up = sp.d_up.p; t.down = sp.d_down.p; t.down_task = sp.d_down_task.p;
+    t.flwacc = sp.d_flwacc.p; t.up_begin = sp.d_up_begin.p; t.up = sp.d_up.p; t.down = sp.d_down.p; t.down_task = sp.d_down_task.p; t.down_need = sp.d_down_need.p;
     t.down_lag = sp.d_down_lag.p; t.task_begin = sp.d_task_begin.p; t.task_cells = sp.d_task_cells.p;
     t.gauge_first = sp.d_gfirst.p; t.gauge_next = sp.d_gnext.p;
     t.tcell = reinterpret_cast<const int4 *>(sp.d_tcell.p); t.tup = reinterpret_cast<const int2 *>(sp.d_tup.p);
@@ -354,13 +369,19 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
     SplitState &sp = pl.sp;
     const size_t npad = (size_t)sp.rg.npad;
     SplitArgs a = split_args(pl, save_q, save_netp);
+    for (int i = 0; i < 8; i++) pl.kmark[i] = 0;
+    auto mark = [&](int i) { pl.kmark[i] = cudaEventRecord(pl.evk[i], pl.stream) == cudaSuccess; };
+    mark(0);
     // routing state of window 0 = the hlr field
     CU(cudaMemcpy2DAsync(sp.d_hcar.p, npad * sizeof(float), pl.d_fields.p + (size_t)F_HLR * npad, (size_t)NFIELD * npad * sizeof(float),
                          npad * sizeof(float), (size_t)pl.nmember, cudaMemcpyDeviceToDevice, pl.stream));
     CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), tape, pl.stream));
+    mark(1);
     CU(launch_route_forward(a, tape, pl.stream));
+    mark(2);
     pl.launches += 1 + sp.nwin;
     if (save_q) { CU(launch_rows_to_domain(a, pl.stream)); pl.launches++; }
+    mark(3);
     return 0;
 }
 
@@ -368,8 +389,12 @@ static int split_reverse(SmashPlan &pl) {
     SplitState &sp = pl.sp;
     SplitArgs a = split_args(pl, false, false);
     CU(cudaMemsetAsync(pl.d_grad.p, 0, sizeof(float) * (size_t)pl.nmember * NFIELD * sp.rg.npad, pl.stream));
+    auto mark = [&](int i) { pl.kmark[i] = cudaEventRecord(pl.evk[i], pl.stream) == cudaSuccess; };
+    mark(4);
     CU(launch_route_adjoint(a, pl.stream));
+    mark(5);
     CU(launch_vertical_adjoint(a, sp.tm_prcp, sp.tm_pet, sp.tm_hp, sp.tm_hft, math_mode(), pl.stream));
+    mark(6);
     pl.launches += 1 + sp.nwin;
     return 0;
 }
@@ -1283,4 +1308,31 @@ extern "C" int smash_b200_mesh_chains(const SmashMesh *mesh, int64_t info[8], in
         for (int t = 0; t < rg.ntask; t++)
             for (int e = rg.task_begin[t]; e < rg.task_begin[t + 1]; e++) pos_of[rg.task_cells[e]] = e - rg.task_begin[t];
     return 0;
+}
+
+// device time of the kernels of the last plan run (split engine), milliseconds, -1 where a kernel did not run:
+// [0] vertical_forward, [1] route_forward, [2] rows_to_domain, [3] route_adjoint, [4] vertical_adjoint
+extern "C" int smash_b200_plan_kernel_times(SmashPlan *plan, float ms[5]) {
+    if (!plan || !ms) return fail(SMASH_B200_EINVAL, "NULL argument");
+    for (int i = 0; i < 5; i++) ms[i] = -1.0f;
+    if (plan->engine != 1) return 0;
+    CU(cudaStreamSynchronize(plan->stream));
+    const int from[5] = {0, 1, 2, 4, 5}, to[5] = {1, 2, 3, 5, 6};
+    for (int i = 0; i < 5; i++)
+        if (plan->kmark[from[i]] && plan->kmark[to[i]]) CU(cudaEventElapsedTime(&ms[i], plan->evk[from[i]], plan->evk[to[i]]));
+    return 0;
+}
+
+// named integer facts about a plan (bench / diagnostics): "routed_cells", "inflow_edges", "source_cells", "engine"
+extern "C" double smash_b200_plan_stat(const SmashPlan *plan, const char *name) {
+    if (!plan || !name) return -1.0;
+    const std::string n(name);
+    if (n == "engine") return plan->engine;
+    if (plan->engine == 1) {
+        const RouteGraph &rg = plan->sp.rg;
+        if (n == "routed_cells") return (double)(rg.n - rg.nsrc);
+        if (n == "source_cells") return (double)rg.nsrc;
+        if (n == "inflow_edges") return (double)rg.up.size();
+    }
+    return -1.0;
 }

@@ -225,9 +225,11 @@ __device__ __forceinline__ void wait_flag(const int *flag, int epoch, int lane) 
         while (ld_acquire(flag) < epoch) __nanosleep(32);
     __syncwarp();
 }
-__device__ __forceinline__ void publish_flag(int *flag, int epoch, int lane) {
+// the row stores of every lane happen before the barrier, the release store of lane 0 after it: cumulativity makes
+// them visible to whoever acquires the flag (no separate fence.sc, which costs microseconds here)
+__device__ __forceinline__ void publish_flag(int *flag, int value, int lane) {
     __syncwarp();
-    if (lane == 0) { __threadfence(); st_release(flag, epoch); }
+    if (lane == 0) st_release(flag, value);
 }
 __device__ __forceinline__ int claim_ticket(unsigned int *ticket, int lane) {
     int tk = 0;
@@ -276,9 +278,10 @@ __device__ __forceinline__ void route_cell(const SplitArgs &a, const RouteConst 
     }
     float Bv = h;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const float Bo = __shfl_up_sync(FULL, Bv, d), Ao = __shfl_up_sync(FULL, A, d);
-        if (lane >= d) { Bv = fmaf(A, Bo, Bv); A *= Ao; }
+    for (int d = 1; d < 32; d <<= 1) {                     // every lane's map has the same slope E^S: slope of d lanes = A
+        const float Bo = __shfl_up_sync(FULL, Bv, d);
+        if (lane >= d) Bv = fmaf(A, Bo, Bv);
+        A *= A;
     }
     h = __shfl_up_sync(FULL, Bv, 1);
     if (lane == 0) h = h0;
@@ -534,8 +537,9 @@ __device__ __forceinline__ void route_cell_b(const SplitArgs &a, const RouteCons
     float Bv = G;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        const float Bo = __shfl_down_sync(FULL, Bv, d), Ao = __shfl_down_sync(FULL, A, d);
-        if (lane + d < 32) { Bv = fmaf(A, Bo, Bv); A *= Ao; }
+        const float Bo = __shfl_down_sync(FULL, Bv, d);
+        if (lane + d < 32) Bv = fmaf(A, Bo, Bv);
+        A *= A;
     }
     G = __shfl_down_sync(FULL, Bv, 1);
     if (lane == 31) G = g0;
@@ -628,7 +632,7 @@ __global__ void __launch_bounds__(128) route_adjoint_kernel(const SplitArgs a, c
         int *rdone = a.rdone + (size_t)m * tp.ntask;
         if (task >= tp.nchain) {
             route_pair_b<S>(a, m, tp.task_cells[cb], tp.task_cells[cb + 1], w, lane, t_first);
-            publish_flag(rdone + task, epoch, lane);
+            publish_flag(rdone + task, (epoch << 16) | 0xffff, lane);
             continue;
         }
         const size_t mrow = (size_t)m * tp.npad * a.Tp;
@@ -637,13 +641,15 @@ __global__ void __launch_bounds__(128) route_adjoint_kernel(const SplitArgs a, c
             const int jt = tp.task_cells[ce - 1];
             const int d = tp.down[jt];
             if (d >= 0) {
-                wait_flag(rdone + tp.down_task[jt], epoch, lane);
+                // the consumer's chain streams its progress (cells done, counted from its tail)
+                wait_flag(rdone + tp.down_task[jt], (epoch << 16) | tp.down_need[jt], lane);
                 ld_row<S>(a.rows_w + mrow + (size_t)d * a.Tp + t_first, wv);
             } else {
 #pragma unroll
                 for (int s = 0; s < S; s++) wv[s] = 0.0f;
             }
         }
+        int ndone = 0;
 #pragma unroll 1
         for (int g1 = ce; g1 > cb; g1 -= 32) {
             const int g0 = max(cb, g1 - 32), ngr = g1 - g0;
@@ -666,9 +672,10 @@ __global__ void __launch_bounds__(128) route_adjoint_kernel(const SplitArgs a, c
                 if (meta & 2) add_seeds<S>(a, m, j, t_first, qb);
                 const RouteConst cc = shfl_const(ci, c);
                 route_cell_b<S>(a, cc, m, j, w, lane, t_first, qb, hr, wv);
+                if ((++ndone & 7) == 0) publish_flag(rdone + task, (epoch << 16) | ndone, lane);   // tributaries may start
             }
         }
-        publish_flag(rdone + task, epoch, lane);
+        publish_flag(rdone + task, (epoch << 16) | 0xffff, lane);
     }
 }
 

@@ -27,6 +27,7 @@ struct SplitTopo {
     const RouteUp *up;
     const int32_t *down;         // [npad] consumer cell or -1
     const int32_t *down_task;    // [npad]
+    const int32_t *down_need;    // [npad] reverse sweep: cells the consumer's task must have finished (0xffff: all)
     const uint8_t *down_lag;     // [npad] 1: the consumer reads this cell's previous time step (late cell of a pit pair)
     const int32_t *task_begin, *task_cells;
     const int4 *tcell;           // TaskCell records, parallel to task_cells

@@ -37,13 +37,18 @@ fw = []
 for i in range(a.reps + 2):
     L.check(lib.smash_b200_plan_run_forward(plan, C.byref(ms))); fw.append(ms.value)
 fw = np.array(fw[2:])
+kt = (C.c_float * 5)(); lib.smash_b200_plan_kernel_times(plan, kt)
+kf = [kt[i] for i in range(5)]
 eng = "split" if int(info[11]) == -1 else "fused"
 line = f"{a.mesh} T={m.setup._ntime_step} engine={eng} B={int(info[2])} blocks={int(info[1])} members={a.members} math={a.math} crit={int(info[8])} | fwd {fw.mean():.3f} ms (min {fw.min():.3f}) {units/fw.mean()/1e-3:.3e} cs/s"
+if kf[0] >= 0: line += f" [vert {kf[0]:.3f} route {kf[1]:.3f} export {kf[2]:.3f}]"
 if a.grad:
     g = []
     for i in range(a.reps + 1):
         L.check(lib.smash_b200_plan_run_gradient(plan, C.byref(f), C.byref(r))); g.append((f.value, r.value))
     g = np.array(g[1:])
+    lib.smash_b200_plan_kernel_times(plan, kt)
+    if kt[0] >= 0: line += f" | [vert {kt[0]:.3f} route {kt[1]:.3f} route_b {kt[3]:.3f} vert_b {kt[4]:.3f}]"
     line += f" | grad fwd {g[:,0].mean():.3f} rev {g[:,1].mean():.3f} ms {units/g.sum(1).mean()/1e-3:.3e} cs/s"
 print(line, flush=True)
 lib.smash_b200_plan_destroy(plan)
