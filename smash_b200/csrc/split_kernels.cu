@@ -71,6 +71,89 @@ __device__ __forceinline__ float vertical_step_lean(const CellConst &k, float pr
     return fmaf(rel, k.cft, fmaxf(0.0f, prd + l));                       // qt = qr + qd (:106, md_forward_structure.f90:142-144)
 }
 
+// Adjoint of vertical_step_lean (same stage-level preconditions: no gap, tanh arguments below 0.25, hp_imd <= 15 so that
+// perc == 0 and pwx1 == 1): the statements of vertical_step_b (cell_math.cuh) with exactly one of the production /
+// evaporation branches live (pn and en are never both positive), written with selects instead of branches and with the
+// per-cell reciprocals hoisted.  GR_TRANSFER_B forward_db.f90:6275-6412, GR_EXCHANGE_B :6147-6157, GR_PRODUCTION_B :6012-6103.
+template <bool EXC>
+__device__ __forceinline__ void vertical_step_b_lean(const CellConst &k, float inv_cft2, float inv_cp2, float prcp, float pet, float hp,
+                                                     float ht, float qt_b, float &hp_b, float &hft_b, float &cp_b, float &cft_b,
+                                                     float &exc_b) {
+    // forward intermediates from the taped states
+    const float ei = fminf(pet, prcp);
+    const float pn = fmaxf(0.0f, prcp - ei);
+    const float en = pet - ei;
+    const bool wet = pn > 0.0f;
+    const float am = wet ? pn : en;
+    const float x = am * k.inv_cp;
+    const float x2 = x * x;
+    float p = fmaf(x2, 0.021869488f, -0.053968254f);
+    p = fmaf(x2, p, 0.13333334f);
+    p = fmaf(x2, p, -0.33333334f);
+    const float th = fmaf(x * x2, p, x);
+    const float u1 = wet ? hp : 1.0f - hp;
+    const float Nn = wet ? 1.0f - hp * hp : hp * (2.0f - hp);
+    const float N = k.cp * Nn;
+    const float inv_den = mufu_rcp(fmaf(u1, th, 1.0f));
+    const float val = N * th * inv_den;                               // ps (wet) or es (dry), md_gr_operator.f90:52,55
+    const float sval = wet ? val : -val;
+    const float hp_imd = fmaf(sval, k.inv_cp, hp);                    // :58
+    const float pr = wet ? pn - (hp_imd - hp) * k.cp : 0.0f;          // :60-62
+    const float h25 = (ht * ht) * fsqrt_fast(ht);                     // hft^2.5
+    const float l = EXC ? k.exc * (h25 * ht) : 0.0f;                  // :77
+    const float prr = fmaf(0.9f, pr, l);
+    const float prd = 0.1f * pr;
+    // reverse
+    const float qr_b = qt_b;
+    const bool qd_on = 0.0f < prd + l;                                // forward_db.f90:8128-8137
+    const float prd_b = qd_on ? qt_b : 0.0f;
+    float l_b = prd_b;
+    // GR_TRANSFER_B (n = 5), no gap
+    const float ct = k.cft, ict = k.inv_cft;
+    const float hsum = fmaf(prr, ict, ht);
+    const bool first = 1.e-6f < hsum;
+    const float ht_imd = first ? hsum : 1.e-6f;
+    const float x1 = ht_imd * ct;
+    const float ix1 = mufu_rcp(x1);
+    const float x1m4 = pow4(ix1);
+    const float x3 = x1m4 + k.cft_m4;
+    const float pwr3 = mufu_rsq(fsqrt_fast(x3));
+    const float ht_new = pwr3 * ict;
+    const float htb = hft_b - ct * qr_b;
+    const float pwr3_b = htb * ict;
+    const float x3_b = -0.25f * (pwr3 * mufu_rcp(x3)) * pwr3_b;
+    const float x1_b = -4.0f * (x1m4 * ix1) * x3_b;
+    const float ht_imd_b = ct * qr_b + ct * x1_b;
+    cft_b += (ht_imd - ht_new) * qr_b + (-4.0f * (k.cft_m4 * ict)) * x3_b - (pwr3 * htb) * inv_cft2 + ht_imd * x1_b;
+    const float prr_b = first ? ht_imd_b * ict : 0.0f;
+    if (first) cft_b -= (prr * ht_imd_b) * inv_cft2;
+    hft_b = first ? ht_imd_b : 0.0f;
+    const float pr_b = fmaf(0.9f, prr_b, 0.1f * prd_b);               // :8143
+    l_b += prr_b;
+    exc_b = fmaf(h25 * ht, l_b, exc_b);                               // GR_EXCHANGE_B (pre-transfer hft); exc_b is fed even where exc == 0
+    if (EXC) hft_b = fmaf(3.5f * h25 * k.exc, l_b, hft_b);
+    // GR_PRODUCTION_B with perc == 0, pwx1 == 1
+    const float perc_b = pr_b - k.inv_cp * hp_b;
+    const float pwx1_b = 0.25f * (hp_imd * k.cp * perc_b);
+    float hp_imd_b = fmaf(4.0f * (hp_imd * hp_imd * hp_imd) * pwx1_b, 1.0e-12f, hp_b);
+    float hpb = 0.0f;
+    if (wet) {
+        hp_imd_b -= k.cp * pr_b;
+        hpb = k.cp * pr_b;
+        cp_b -= (hp_imd - hp) * pr_b;
+    }
+    const float gb = (wet ? k.inv_cp : -k.inv_cp) * hp_imd_b;         // ps_b or es_b
+    const float tb = gb * inv_den;
+    const float dden = -(N * th * tb) * inv_den;
+    const float dNdhp = wet ? -2.0f * hp * k.cp : k.cp * (2.0f - 2.0f * hp);
+    hpb = hpb + hp_imd_b + dNdhp * th * tb + (wet ? th : -th) * dden;
+    const float sech = 1.0f - th * th;
+    const float d_th = sech * N * tb, d_u = sech * u1 * dden;
+    const float inv_cp_b = sval * hp_imd_b + am * d_u + am * d_th;
+    cp_b += Nn * th * tb - inv_cp_b * inv_cp2;
+    hp_b = hpb;
+}
+
 // ------------------------------------------------------------------------------------------------
 // vertical_forward: md_forward_structure.f90:106-144 for every cell and time step; no inter-cell dependency.
 // Source cells (flwacc == 1) are final here: q = qt * dx^2 * 1e-3 / dt (:155 with flwacc - 1 = 0).
@@ -731,6 +814,10 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const _
     const float *sb = a.qsim_b + (size_t)m * T * a.tp.ng;
     const int ng = a.tp.ng;
     float hp_b = 0.0f, hft_b = 0.0f, cp_b = 0.0f, cft_b = 0.0f, exc_b = 0.0f;
+    const bool all_valid = j0 + 32 <= n;
+    const bool exc_on = __any_sync(FULL, k.exc != 0.0f);
+    const float inv_cft2 = k.inv_cft * k.inv_cft, inv_cp2 = k.inv_cp * k.inv_cp;
+    const float c0 = k.c0;
 
     auto load_w = [&](int st, float *v) {
 #pragma unroll
@@ -766,6 +853,24 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const _
         }
         __syncwarp();
         if (lane == 0 && it + VB_NST < nst) issue(slot, st - VB_NST);
+        float mn = 0.0f, mx = 0.0f, hmx = 0.0f;
+#pragma unroll
+        for (int i = 0; i < VT_TK; i++) {
+            mn = fminf(mn, fminf(pv[i], ev[i]));
+            mx = fmaxf(mx, fmaxf(pv[i], ev[i]));
+            hmx = fmaxf(hmx, hpv[i]);
+        }
+        const float xm = mx * k.inv_cp;
+        const bool lean = FAST && all_valid && (st + 1) * VT_TK <= T &&      // warp-uniform part first: every lane votes
+                          __all_sync(FULL, gfirst < 0 && mn >= 0.0f && xm < 0.25f && hmx + xm < 15.0f);
+        if (lean) {
+#pragma unroll
+            for (int i = VT_TK - 1; i >= 0; i--) {
+                const float qt_b = c0 * wq[i];                                                     // :8114
+                if (exc_on) vertical_step_b_lean<true>(k, inv_cft2, inv_cp2, pv[i], ev[i], hpv[i], hfv[i], qt_b, hp_b, hft_b, cp_b, cft_b, exc_b);
+                else vertical_step_b_lean<false>(k, inv_cft2, inv_cp2, pv[i], ev[i], hpv[i], hfv[i], qt_b, hp_b, hft_b, cp_b, cft_b, exc_b);
+            }
+        } else
 #pragma unroll
         for (int i = VT_TK - 1; i >= 0; i--) {
             const int t = st * VT_TK + i;
