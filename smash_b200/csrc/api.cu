@@ -102,6 +102,33 @@ struct SplitState {
     SplitTopo topo{};
 };
 
+// Large caller-owned host arrays (forcing in, domain series out) are page-locked in place the first time they are seen
+// (cudaHostRegister), so that the copies run at PCIe speed and asynchronously; the registration is remembered by address.
+// Arrays below the threshold, or ranges the driver refuses, stay pageable.
+static std::map<uintptr_t, size_t> &pinned_ranges() {
+    static std::map<uintptr_t, size_t> m;
+    return m;
+}
+static void pin_host(const void *ptr, size_t bytes) {
+    if (!ptr || bytes < ((size_t)option("pin_min_mb", 64) << 20) || !option("pin_host", 1)) return;
+    const uintptr_t page = 4096, lo = reinterpret_cast<uintptr_t>(ptr) & ~(page - 1);
+    const uintptr_t hi = (reinterpret_cast<uintptr_t>(ptr) + bytes + page - 1) & ~(page - 1);
+    auto &m = pinned_ranges();
+    auto it = m.find(lo);
+    if (it != m.end()) {
+        if (it->second >= hi - lo) return;
+        cudaHostUnregister(reinterpret_cast<void *>(lo));
+        m.erase(it);
+    }
+    if (cudaHostRegister(reinterpret_cast<void *>(lo), hi - lo, cudaHostRegisterDefault) == cudaSuccess) m[lo] = hi - lo;
+    else cudaGetLastError();
+}
+static void unpin_all() {
+    for (auto &kv : pinned_ranges()) cudaHostUnregister(reinterpret_cast<void *>(kv.first));
+    cudaGetLastError();
+    pinned_ranges().clear();
+}
+
 struct SmashPlan {
     Topology tp;
     DeviceTopology dtp{};
@@ -447,6 +474,7 @@ static int plan_set_forcing(SmashPlan &pl, const SmashSetup *setup, const SmashM
     const size_t nraw = (size_t)stride * tp.T;
     TRY(pl.d_raw_prcp.ensure(nraw)); TRY(pl.d_raw_pet.ensure(nraw));
     if (pl.engine == 0) TRY(pl.d_forcing.ensure((size_t)tp.total_ticks * 2 * tp.B));
+    pin_host(prcp, nraw * sizeof(float)); pin_host(pet, nraw * sizeof(float));
     CU(cudaMemcpyAsync(pl.d_raw_prcp.p, prcp, nraw * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
     CU(cudaMemcpyAsync(pl.d_raw_pet.p, pet, nraw * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
     if (pl.engine == 1) {
@@ -748,6 +776,7 @@ static int export_domain(SmashPlan &pl, const SmashSetup *setup, const SmashMesh
         if (setup->sparse_storage) {
             if (!sparse) return 0;
             const size_t n = (size_t)mesh->nac * tp.T;
+            pin_host(sparse, n * sizeof(float));
             if (sp.rg.direct) { CU(cudaMemcpyAsync(sparse, skewed, n * sizeof(float), cudaMemcpyDeviceToHost, pl.stream)); return 0; }
             TRY(pl.d_out.ensure(n));
             CU(cudaMemsetAsync(pl.d_out.p, 0, n * sizeof(float), pl.stream));
@@ -1106,6 +1135,7 @@ extern "C" int smash_b200_set_device(int device) {
 extern "C" void smash_b200_clear_cache(void) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_plans.clear();
+    unpin_all();
 }
 extern "C" int smash_b200_set_option(const char *name, long long value) {
     if (!name) return fail(SMASH_B200_EINVAL, "option name is NULL");
