@@ -160,7 +160,10 @@ void smash_b200_clear_cache(void);           /* drop cached mesh plans and devic
  * reciprocal / rsqrt with the cancellation-free transfer formula (closer to the float64 solution than the
  * reference's own float32 arithmetic), 0 = IEEE division / sqrt + libm tanhf in the reference's
  * statement order; "block" = cells per CTA (0 = automatic);
- * "member_budget_mb" = device memory per ensemble launch. */
+ * "member_budget_mb" = device memory per ensemble launch; "engine" 1 = split engine (reservoir pass per cell + routing
+ * scan per chain, default with math = 1), 0 = fused tick wavefront; "pin_host" 1 = page-lock large caller-owned host
+ * arrays in place on first use (PCIe-speed copies) -- the caller must then call smash_b200_clear_cache() before freeing
+ * them; off by default. */
 int smash_b200_set_option(const char *name, long long value);
 
 /* ---- device-resident plan API (bench / advanced callers) --------------------------------------
@@ -203,7 +206,8 @@ int smash_b200_mesh_order(const SmashSetup *setup, const SmashMesh *mesh, int32_
 /* Heavy-path decomposition used by the split engine (reservoir pass per cell + routing pass per chain), computed on
  * the host only.  Cells are numbered j = 0..n-1 in `path` order (md_forward_structure.f90:82-92).
  *   info[0] n computed cells, [1] chains, [2] pit pairs, [3] largest dependency height of a chain, [4] longest chain,
- *   [5] longest dependency path in cells, [6] source cells (flwacc == 1), [7] 1 if sparse arrays are usable in place
+ *   [5] longest dependency path in cells, [6] source cells (flwacc == 1), [7] bit 0: sparse arrays are usable in place, bits 1..: number of longest
+ *   chains that run on dedicated warps (they are the last chain tasks and may feed tasks with a smaller index)
  *   cell[j]      flat rect index row + col*nrow of cell j                                    (n entries)
  *   task_of[j]   task (chain or pair, execution order) that routes cell j, -1 for lone source cells
  *   pos_of[j]    position of the cell inside its task, upstream -> downstream

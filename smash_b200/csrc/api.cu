@@ -102,15 +102,16 @@ struct SplitState {
     SplitTopo topo{};
 };
 
-// Large caller-owned host arrays (forcing in, domain series out) are page-locked in place the first time they are seen
-// (cudaHostRegister), so that the copies run at PCIe speed and asynchronously; the registration is remembered by address.
-// Arrays below the threshold, or ranges the driver refuses, stay pageable.
+// Opt-in (option "pin_host" = 1): large caller-owned host arrays (forcing in, domain series out) are page-locked in place
+// the first time they are seen (cudaHostRegister), so that the copies run at PCIe speed; the registration is remembered
+// by address until smash_b200_clear_cache().  The caller promises not to free such an array before clearing the cache
+// (a dangling registration makes later allocations fail), which is why it is off by default.
 static std::map<uintptr_t, size_t> &pinned_ranges() {
     static std::map<uintptr_t, size_t> m;
     return m;
 }
 static void pin_host(const void *ptr, size_t bytes) {
-    if (!ptr || bytes < ((size_t)option("pin_min_mb", 64) << 20) || !option("pin_host", 1)) return;
+    if (!ptr || bytes < ((size_t)option("pin_min_mb", 64) << 20) || !option("pin_host", 0)) return;
     const uintptr_t page = 4096, lo = reinterpret_cast<uintptr_t>(ptr) & ~(page - 1);
     const uintptr_t hi = (reinterpret_cast<uintptr_t>(ptr) + bytes + page - 1) & ~(page - 1);
     auto &m = pinned_ranges();
@@ -320,7 +321,7 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     TRY(sp.d_tcell.upload(rg.tcell, s)); TRY(sp.d_tup.upload(rg.tup, s));
     TRY(pl.d_ticket.ensure(1)); TRY(pl.d_sum.ensure(1));
     SplitTopo &t = sp.topo;
-    t.n = rg.n; t.npad = npad; t.ng = mesh->ng; t.ntask = rg.ntask; t.nchain = rg.nchain;
+    t.n = rg.n; t.npad = npad; t.ng = mesh->ng; t.ntask = rg.ntask; t.nchain = rg.nchain; t.nded = rg.nded;
     t.flwacc = sp.d_flwacc.p; t.up_begin = sp.d_up_begin.p; t.up = sp.d_up.p; t.down = sp.d_down.p; t.down_task = sp.d_down_task.p; t.down_need = sp.d_down_need.p;
     t.down_lag = sp.d_down_lag.p; t.task_begin = sp.d_task_begin.p; t.task_cells = sp.d_task_cells.p;
     t.gauge_first = sp.d_gfirst.p; t.gauge_next = sp.d_gnext.p;
@@ -383,6 +384,28 @@ static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp) {
     SplitArgs a{};
     a.tp = sp.topo; a.T = pl.tp.T; a.Tp = sp.Tp; a.W = sp.W; a.nwin = sp.nwin; a.nmember = pl.nmember; a.dt = pl.dt; a.dx = pl.dx;
     a.first_routed = sp.rg.first_routed;
+    a.dbg_prof = nullptr;
+    if (option("dbg_prof", 0) && sp.rg.nded > 0) {
+        static unsigned long long *dp = nullptr;
+        const size_t nb = 4 * (size_t)sp.rg.nded * sizeof(unsigned long long);
+        if (!dp) { cudaMalloc(&dp, 4 * 256 * sizeof(unsigned long long)); cudaMemset(dp, 0, 4 * 256 * sizeof(unsigned long long)); }
+        std::vector<unsigned long long> hv(4 * (size_t)sp.rg.nded);
+        cudaMemcpy(hv.data(), dp, nb, cudaMemcpyDeviceToHost);
+        unsigned long long tmax = 0;
+        for (int i = 0; i < sp.rg.nded; i++) tmax = std::max(tmax, hv[4 * i + 3]);
+        if (tmax) {
+            std::vector<int> idx(sp.rg.nded);
+            for (int i = 0; i < sp.rg.nded; i++) idx[i] = i;
+            std::sort(idx.begin(), idx.end(), [&](int x, int y) { return hv[4 * x + 3] > hv[4 * y + 3]; });
+            for (int k = 0; k < 6 && k < sp.rg.nded; k++) {
+                const int i = idx[k];
+                fprintf(stderr, "[dbg_prof] chain %d: %llu cells, %.0f cycles/cell, waiting %.0f %%, ended %.3f ms before the last\n", i,
+                        hv[4 * i], (double)hv[4 * i + 1] / std::max(1ull, hv[4 * i]), 100.0 * hv[4 * i + 2] / std::max(1ull, hv[4 * i + 1]),
+                        (tmax - hv[4 * i + 3]) * 1e-6);
+            }
+        }
+        a.dbg_prof = dp;
+    }
     a.save_q = save_q ? 1 : 0; a.save_netp = save_netp ? 1 : 0;
     a.fields = pl.d_fields.p; a.fstates = pl.d_fstates.p; a.rows = sp.d_rows.p; a.qdom = pl.d_qdom.p; a.netp = pl.d_netp.p;
     a.qpitch = sp.qpitch; a.qsim = pl.d_qsim.p; a.tape_hp = sp.d_tape_hp.p; a.tape_hft = sp.d_tape_hft.p; a.rows_hr = sp.d_rows_hr.p;
@@ -1327,7 +1350,7 @@ extern "C" int smash_b200_mesh_chains(const SmashMesh *mesh, int64_t info[8], in
                                         mesh->local_active_cell, mesh->path, mesh->gauge_pos);
     if (!err.empty()) return fail(err.rfind("unsupported", 0) == 0 ? SMASH_B200_EUNSUPPORTED : SMASH_B200_EINVAL, "%s", err.c_str());
     info[0] = rg.n; info[1] = rg.nchain; info[2] = rg.npair; info[3] = rg.max_height; info[4] = rg.max_chain;
-    info[5] = rg.critical_cells; info[6] = rg.nsrc; info[7] = rg.direct ? 1 : 0;
+    info[5] = rg.critical_cells; info[6] = rg.nsrc; info[7] = (rg.direct ? 1 : 0) | ((int64_t)rg.nded << 1);
     for (int j = 0; j < rg.n; j++) {
         if (cell) cell[j] = rg.cell[j];
         if (task_of) task_of[j] = rg.cell_task[j];

@@ -155,6 +155,15 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
         if (height[a] != height[b]) return height[a] < height[b];
         return chains[a].size() > chains[b].size();
     });
+    // the longest chains get warps of their own in the forward routing pass: they are moved to the end of the chain tasks
+    {
+        constexpr int DED_MIN = 48, DED_MAX = 256;
+        std::vector<int32_t> byl(torder);
+        std::stable_sort(byl.begin(), byl.end(), [&](int a, int b) { return chains[a].size() > chains[b].size(); });
+        std::vector<uint8_t> ded(nch, 0);
+        for (int i = 0; i < nch && i < DED_MAX && (int)chains[byl[i]].size() >= DED_MIN; i++) { ded[byl[i]] = 1; g.nded++; }
+        std::stable_partition(torder.begin(), torder.end(), [&](int c) { return !ded[c]; });
+    }
     std::vector<int32_t> task_of_chain(nch);
     for (int t = 0; t < nch; t++) task_of_chain[torder[t]] = t;
 
@@ -177,7 +186,8 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
             if (g.up[e].task == UP_NOWAIT) {
                 const int s = g.up[e].src;
                 if (g.cell_task[s] >= 0) {
-                    if (g.cell_task[s] >= g.cell_task[j]) return "internal: task order violates a dependency";
+                    const bool s_ded = g.cell_task[s] >= g.nchain - g.nded && g.cell_task[s] < g.nchain;
+                    if (g.cell_task[s] >= g.cell_task[j] && !s_ded) return "internal: task order violates a dependency";
                     g.up[e].task = g.cell_task[s];
                 }
             }

@@ -51,6 +51,7 @@ struct RouteGraph {
     std::vector<int32_t> cell_task;     // task that routes cell j, -1 for source cells outside every task
     // tasks: chains first (sorted by dependency height, longest first inside a height), then pit pairs
     int ntask = 0, nchain = 0, npair = 0;
+    int nded = 0;                       // the last nded chain tasks are the longest chains (dedicated warps in the forward pass)
     std::vector<int32_t> task_begin;    // ntask + 1
     std::vector<int32_t> task_cells;    // cells of each task, upstream -> downstream (pairs: early cell, late cell)
     std::vector<TaskCell> tcell;        // parallel to task_cells

@@ -477,88 +477,184 @@ __device__ __noinline__ void route_pair(const SplitArgs &a, int m, const int4 re
 }
 
 // One warp per task.  The records of up to 32 cells of the chain are fetched with one coalesced load, lane i then
-// owns the scalars of cell i (constants, carried state) and asks L2 for that cell's rows while the warp routes the
-// cells one after the other; nothing on the cell-to-cell critical path but L2 hits and the scan.
+// owns the scalars of cell i (constants, carried state) and one inflow entry of the group; the tributaries of the whole
+// group are awaited once, lane-parallel, and their rows requested from DRAM, before the warp routes the cells one after
+// the other.
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// Staging area of one warp: the next cell's own row and its first two tributary rows travel L2 -> shared memory
+// (cp.async, no registers) while the current cell is routed.  [slot][float4 index][lane]: every lane reads and writes
+// only its own column, so no warp barrier is involved.
+template <int S> struct RowStage { float4 v[3][S / 4][32]; };
+template <int S> __device__ __forceinline__ void stage_row(RowStage<S> &st, int slot, int lane, const float *src_lane) {
+#pragma unroll
+    for (int i = 0; i < S / 4; i++) cp_async16(&st.v[slot][i][lane], src_lane + 4 * i);
+}
+template <int S> __device__ __forceinline__ void staged_row(const RowStage<S> &st, int slot, int lane, float (&v)[S]) {
+#pragma unroll
+    for (int i = 0; i < S / 4; i++) {
+        const float4 x = st.v[slot][i][lane];
+        v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+    }
+}
+
 template <int S, int TAPE>
-__global__ void __launch_bounds__(128) route_forward_kernel(const SplitArgs a, const int w) {
+__device__ __forceinline__ void route_chain(const SplitArgs &a, RowStage<S> &stg, int m, int task, int w, int lane, int t_first,
+                                            int epoch) {
+    const SplitTopo &tp = a.tp;
+    const int cb = tp.task_begin[task], ce = tp.task_begin[task + 1];
+    int *done = a.done + (size_t)m * tp.ntask;
+    const float *rows_lane = a.rows + (size_t)m * tp.npad * a.Tp + t_first;
+    const float *rows_win = a.rows + (size_t)m * tp.npad * a.Tp + (size_t)w * a.W;
+    float r[S];
+#pragma unroll
+    for (int s = 0; s < S; s++) r[s] = 0.0f;
+    int ngr = 0;
+    const bool prof = a.dbg_prof != nullptr && task >= tp.nchain - tp.nded;
+    long long t_start = 0, t_wait = 0;
+    if (prof) t_start = clock64();
+#pragma unroll 1
+    for (int g0 = cb; g0 < ce; g0 += ngr) {
+        ngr = min(32, ce - g0);
+        int4 rec = make_int4(-1, 0, 0, 0);
+        if (lane < ngr) rec = tp.tcell[g0 + lane];
+        {   // the group ends where its inflow entries would no longer fit the 32 lanes that hold them
+            int cum = (lane < ngr) ? (rec.y >> 8) : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(FULL, cum, d);
+                if (lane >= d) cum += o;
+            }
+            ngr = max(1, __popc(__ballot_sync(FULL, lane < ngr && cum <= 32)));
+            if (lane >= ngr) rec = make_int4(-1, 0, 0, 0);
+        }
+        RouteConst ci = {0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+        if (lane < ngr) {
+            prefetch_row<S>(rows_win + (size_t)rec.x * a.Tp);
+            if (rec.y & 1) ci = route_const(a, m, rec.x, a.hcar);
+        }
+        const int up0 = __shfl_sync(FULL, rec.z, 0);
+        const int nup_all = __shfl_sync(FULL, rec.z + (rec.y >> 8), ngr - 1) - up0;
+        int2 ent = make_int2(-1, UP_HEAVY);
+        long long tw0 = 0;
+        if (prof) tw0 = clock64();
+        if (lane < nup_all) {
+            ent = tp.tup[up0 + lane];
+            if (ent.y >= 0)
+                while (ld_acquire(done + ent.y) < epoch) __nanosleep(64);   // tributary of another task
+            if (ent.y > UP_HEAVY) prefetch_row<S>(rows_win + (size_t)ent.x * a.Tp);
+        }
+        __syncwarp();
+        if (prof) t_wait += clock64() - tw0;
+        int ns1 = -1, ns2 = -1;                                         // group entry indices staged in slots 1 and 2
+        auto stage_cell = [&](int c) {
+            const int jn = __shfl_sync(FULL, rec.x, c);
+            const int mn = __shfl_sync(FULL, rec.y, c);
+            const int un = __shfl_sync(FULL, rec.z, c) - up0;
+            stage_row<S>(stg, 0, lane, rows_lane + (size_t)jn * a.Tp);
+            ns1 = -1; ns2 = -1;
+            const int nupn = (mn & 1) ? (mn >> 8) : 0;
+            for (int e = 0; e < nupn && ns2 < 0; e++) {
+                const int idx = un + e;
+                if (idx >= 32) break;
+                const int ux = __shfl_sync(FULL, ent.x, idx), uy = __shfl_sync(FULL, ent.y, idx);
+                if (uy > UP_HEAVY) {
+                    stage_row<S>(stg, ns1 < 0 ? 1 : 2, lane, rows_lane + (size_t)ux * a.Tp);
+                    if (ns1 < 0) ns1 = idx; else ns2 = idx;
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        stage_cell(0);
+#pragma unroll 1
+        for (int c = 0; c < ngr; c++) {
+            const int j = __shfl_sync(FULL, rec.x, c);
+            const int meta = __shfl_sync(FULL, rec.y, c);
+            const int uo = __shfl_sync(FULL, rec.z, c) - up0;
+            const int s1 = ns1, s2 = ns2;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            float qt[S];
+            staged_row<S>(stg, 0, lane, qt);
+            if (meta & 1) {
+                float x[S];
+#pragma unroll
+                for (int s = 0; s < S; s++) x[s] = 0.0f;
+                const int nup = meta >> 8;
+#pragma unroll 1
+                for (int e = 0; e < nup; e++) {                         // md_routing_operator.f90:37-53, same order
+                    const int idx = uo + e;
+                    int2 u;
+                    u.x = __shfl_sync(FULL, ent.x, idx & 31); u.y = __shfl_sync(FULL, ent.y, idx & 31);
+                    if (idx >= 32) {                                     // a single cell with more entries than lanes: never on a D8 mesh
+                        u = tp.tup[up0 + idx];
+                        if (u.y >= 0) wait_flag(done + u.y, epoch, lane);
+                    }
+                    if (u.y <= UP_HEAVY) {
+#pragma unroll
+                        for (int s = 0; s < S; s++) x[s] = x[s] + r[s];
+                    } else {
+                        float v[S];
+                        if (idx == s1) staged_row<S>(stg, 1, lane, v);
+                        else if (idx == s2) staged_row<S>(stg, 2, lane, v);
+                        else ld_row<S>(rows_lane + (size_t)u.x * a.Tp, v);
+#pragma unroll
+                        for (int s = 0; s < S; s++) x[s] = x[s] + v[s];
+                    }
+                }
+                if (c + 1 < ngr) stage_cell(c + 1);                     // travels while this cell is routed
+                const RouteConst cc = shfl_const(ci, c);
+                route_cell<S, TAPE>(a, cc, m, j, w, lane, t_first, (meta & 2) != 0, x, qt, r);
+            } else {
+                if (c + 1 < ngr) stage_cell(c + 1);
+#pragma unroll
+                for (int s = 0; s < S; s++) r[s] = qt[s];               // source cell at the chain head: already final
+            }
+        }
+    }
+    publish_flag(done + task, epoch, lane);
+    if (prof && lane == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        unsigned long long *o = a.dbg_prof + 4 * (size_t)(task - (tp.nchain - tp.nded));
+        o[0] = (unsigned long long)(ce - cb); o[1] = (unsigned long long)(clock64() - t_start); o[2] = (unsigned long long)t_wait; o[3] = gt;
+    }
+}
+
+// Tasks [0, nchain - nded) are claimed through the ticket, in dependency order.  The nded longest chains (main rivers)
+// have warps of their own (the first CTAs of the grid): they start at once and advance as their tributaries finish,
+// instead of queueing behind the rest of their basin -- a long chain is a serial walk and sets the kernel's duration.
+template <int S, int TAPE>
+__global__ void __launch_bounds__(128, 3) route_forward_kernel(const SplitArgs a, const int w, const int ded_blocks) {
+    __shared__ __align__(16) RowStage<S> stage_all[4];
+    RowStage<S> &stg = stage_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const SplitTopo &tp = a.tp;
     const int t_first = w * a.W + lane * S;
     const int epoch = w + 1;
-    const int total = tp.ntask * a.nmember;
+    if ((int)blockIdx.x < ded_blocks) {
+        const int d = blockIdx.x * 4 + (threadIdx.x >> 5);
+        if (d < tp.nded)
+            for (int m = 0; m < a.nmember; m++) route_chain<S, TAPE>(a, stg, m, tp.nchain - tp.nded + d, w, lane, t_first, epoch);
+        return;
+    }
+    const int nticket = tp.ntask - tp.nded;
+    const int total = nticket * a.nmember;
     int tk_next = claim_ticket(a.ticket, lane);
     for (;;) {
         const int tk = tk_next;
         if (tk >= total) break;
         tk_next = claim_ticket(a.ticket, lane);            // the next ticket travels while this task is routed
-        const int m = tk / tp.ntask, task = tk - m * tp.ntask;
-        const int cb = tp.task_begin[task], ce = tp.task_begin[task + 1];
-        int *done = a.done + (size_t)m * tp.ntask;
+        const int m = tk / nticket, t = tk - m * nticket;
+        const int task = t < tp.nchain - tp.nded ? t : t + tp.nded;
         if (task >= tp.nchain) {
+            const int cb = tp.task_begin[task];
+            int *done = a.done + (size_t)m * tp.ntask;
             route_pair<S, TAPE>(a, m, tp.tcell[cb], tp.tcell[cb + 1], w, lane, t_first, done, epoch);
             publish_flag(done + task, epoch, lane);
             continue;
         }
-        const float *rows_lane = a.rows + (size_t)m * tp.npad * a.Tp + t_first;
-        const float *rows_win = a.rows + (size_t)m * tp.npad * a.Tp + (size_t)w * a.W;
-        float r[S];
-#pragma unroll
-        for (int s = 0; s < S; s++) r[s] = 0.0f;
-#pragma unroll 1
-        for (int g0 = cb; g0 < ce; g0 += 32) {
-            const int ngr = min(32, ce - g0);
-            int4 rec = make_int4(-1, 0, 0, 0);
-            if (lane < ngr) rec = tp.tcell[g0 + lane];
-            RouteConst ci = {0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
-            if (lane < ngr) {
-                prefetch_row<S>(rows_win + (size_t)rec.x * a.Tp);
-                if (rec.y & 1) ci = route_const(a, m, rec.x, a.hcar);
-            }
-            const int up0 = __shfl_sync(FULL, rec.z, 0);
-            const int nup_all = __shfl_sync(FULL, rec.z + (rec.y >> 8), ngr - 1) - up0;
-            int2 ent = make_int2(-1, UP_HEAVY);
-            if (lane < nup_all) {
-                ent = tp.tup[up0 + lane];
-                if (ent.y > UP_HEAVY) prefetch_row<S>(rows_win + (size_t)ent.x * a.Tp);
-            }
-#pragma unroll 1
-            for (int c = 0; c < ngr; c++) {
-                const int j = __shfl_sync(FULL, rec.x, c);
-                const int meta = __shfl_sync(FULL, rec.y, c);
-                const int uo = __shfl_sync(FULL, rec.z, c) - up0;
-                float qt[S];
-                ld_row<S>(rows_lane + (size_t)j * a.Tp, qt);
-                if (meta & 1) {
-                    float x[S];
-#pragma unroll
-                    for (int s = 0; s < S; s++) x[s] = 0.0f;
-                    const int nup = meta >> 8;
-#pragma unroll 1
-                    for (int e = 0; e < nup; e++) {                         // md_routing_operator.f90:37-53, same order
-                        const int idx = uo + e;
-                        int2 u;
-                        u.x = __shfl_sync(FULL, ent.x, idx & 31); u.y = __shfl_sync(FULL, ent.y, idx & 31);
-                        if (idx >= 32) u = tp.tup[up0 + idx];
-                        if (u.y <= UP_HEAVY) {
-#pragma unroll
-                            for (int s = 0; s < S; s++) x[s] = x[s] + r[s];
-                        } else {
-                            if (u.y >= 0) wait_flag(done + u.y, epoch, lane);
-                            float v[S];
-                            ld_row<S>(rows_lane + (size_t)u.x * a.Tp, v);
-#pragma unroll
-                            for (int s = 0; s < S; s++) x[s] = x[s] + v[s];
-                        }
-                    }
-                    const RouteConst cc = shfl_const(ci, c);
-                    route_cell<S, TAPE>(a, cc, m, j, w, lane, t_first, (meta & 2) != 0, x, qt, r);
-                } else {
-#pragma unroll
-                    for (int s = 0; s < S; s++) r[s] = qt[s];               // source cell at the chain head: already final
-                }
-            }
-        }
-        publish_flag(done + task, epoch, lane);
+        route_chain<S, TAPE>(a, stg, m, task, w, lane, t_first, epoch);
     }
 }
 
@@ -992,14 +1088,16 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
     int blocks = 0;
     cudaError_t e = tape ? persistent_grid(route_forward_kernel<S, 1>, &blocks) : persistent_grid(route_forward_kernel<S, 0>, &blocks);
     if (e != cudaSuccess) return e;
-    const long long total = (long long)a.tp.ntask * a.nmember;
-    const int need = (int)((total + 3) / 4);
+    const int ded_blocks = (a.tp.nded + 3) / 4;            // api.cu keeps nded well below the resident grid
+    const long long total = (long long)(a.tp.ntask - a.tp.nded) * a.nmember;
+    const int need = (int)((total + 3) / 4) + ded_blocks;
     if (blocks > need) blocks = need > 0 ? need : 1;
+    if (blocks <= ded_blocks) return cudaErrorLaunchOutOfResources;
     for (int w = 0; w < a.nwin; w++) {
         e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), s);
         if (e != cudaSuccess) return e;
-        if (tape) route_forward_kernel<S, 1><<<blocks, 128, 0, s>>>(a, w);
-        else route_forward_kernel<S, 0><<<blocks, 128, 0, s>>>(a, w);
+        if (tape) route_forward_kernel<S, 1><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
+        else route_forward_kernel<S, 0><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

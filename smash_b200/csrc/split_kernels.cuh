@@ -22,6 +22,7 @@ namespace smash {
 
 struct SplitTopo {
     int n, npad, ng, ntask, nchain;
+    int nded;                    // the last nded chain tasks (longest chains) run on warps of their own in route_forward
     const int32_t *flwacc;       // [npad] (1 on padding)
     const int32_t *up_begin;     // [n + 1]
     const RouteUp *up;
@@ -43,6 +44,7 @@ struct SplitArgs {
     int nmember;
     float dt, dx;
     int save_q, save_netp;
+    unsigned long long *dbg_prof;  // diagnostics: per dedicated chain [cells, cycles, cycles waiting for tributaries, end time ns], or nullptr
     const float *fields;         // [m][NFIELD][npad]
     float *fstates;              // [m][3][npad]
     float *rows;                 // [m][npad][Tp]   qt of every cell after vertical_forward, q after route_forward
