@@ -24,3 +24,14 @@ for mode in (0, 1):
     L.lib().smash_b200_set_option(b"math", mode)
     q, c = run(smash_b200.forward)
     report(f"gpu math={mode}", q, c)
+
+# France window (300 x 300, 96 steps): domain discharge of the default engine against the f32 oracle
+a, b = cases.france(T=96, sub=(400, 700, 400, 700)), cases.france(T=96, sub=(400, 700, 400, 700))
+L.lib().smash_b200_set_option(b"math", 1)
+smash_b200.forward(a.setup, a.mesh, a.input_data, a.parameters, a.parameters.copy(), a.states, a.states.copy(), a.output)
+oracle.forward(b.setup, b.mesh, b.input_data, b.parameters, b.parameters.copy(), b.states, b.states.copy(), b.output)
+qa, qb = np.asarray(a.output.sparse_qsim_domain, np.float64), np.asarray(b.output.sparse_qsim_domain, np.float64)
+d = np.abs(qa - qb)
+big = np.abs(qb) > 1e-3
+print(f"france window: max abs {d.max():.3e}  max rel(q>1e-3) {(d[big]/np.abs(qb[big])).max():.3e}  "
+      f"median rel {np.median(d[big]/np.abs(qb[big])):.3e}  viol(1e-6+1e-4rel) {(d > 1e-6 + 1e-4*np.abs(qb)).sum()} of {d.size}")
