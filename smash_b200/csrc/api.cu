@@ -276,7 +276,8 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     SplitState &sp = pl.sp;
     RouteGraph &rg = sp.rg;
     std::string err = build_route_graph(rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
-                                        mesh->local_active_cell, mesh->path, mesh->gauge_pos);
+                                        mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
+                                        (int)option("route_ded_max", 64));
     if (!err.empty()) {
         *unsupported = err.rfind("unsupported", 0) == 0;
         return fail(SMASH_B200_EINVAL, "%s", err.c_str());

@@ -13,7 +13,7 @@ static const int RG_DROW[8] = {1, 1, 0, -1, -1, -1, 0, 1};
 
 std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const int32_t *flwdir, const int32_t *flwacc,
                               const int32_t *active_cell, const int32_t *local_active_cell, const int32_t *path,
-                              const int32_t *gauge_pos) {
+                              const int32_t *gauge_pos, int ded_min, int ded_max) {
     const int ncell = nrow * ncol;
     if (nrow <= 0 || ncol <= 0) return "mesh: nrow and ncol must be positive";
     g = RouteGraph();
@@ -157,7 +157,7 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
     });
     // the longest chains get warps of their own in the forward routing pass: they are moved to the end of the chain tasks
     {
-        constexpr int DED_MIN = 48, DED_MAX = 256;
+        const int DED_MIN = ded_min, DED_MAX = ded_max;
         std::vector<int32_t> byl(torder);
         std::stable_sort(byl.begin(), byl.end(), [&](int a, int b) { return chains[a].size() > chains[b].size(); });
         std::vector<uint8_t> ded(nch, 0);

@@ -69,6 +69,8 @@ struct RouteGraph {
 // Returns "" on success; "unsupported: ..." when the mesh needs the fused engine (lagged inflows outside pit pairs).
 std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const int32_t *flwdir, const int32_t *flwacc,
                               const int32_t *active_cell, const int32_t *local_active_cell, const int32_t *path,
-                              const int32_t *gauge_pos);
+                              const int32_t *gauge_pos, int ded_min = 96, int ded_max = 64);
+// ded_min / ded_max: chains of at least ded_min cells, at most ded_max of them (the longest), get a CTA of their own in
+// the forward routing pass
 
 }  // namespace smash

@@ -483,6 +483,25 @@ __device__ __noinline__ void route_pair(const SplitArgs &a, int m, const int4 re
 __device__ __forceinline__ void cp_async16(void *dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
+template <int N> __device__ __forceinline__ void ld_vec(const float *p, float (&v)[N]) {      // N even, p 8-byte aligned
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+        const float2 x = __ldcg(reinterpret_cast<const float2 *>(p) + i);
+        v[2 * i] = x.x; v[2 * i + 1] = x.y;
+    }
+}
+template <int N> __device__ __forceinline__ void st_vec(float *p, const float (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) reinterpret_cast<float2 *>(p)[i] = make_float2(v[2 * i], v[2 * i + 1]);
+}
+template <int N> __device__ __forceinline__ void lds_vec(const float *p, float (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+        const float2 x = reinterpret_cast<const float2 *>(p)[i];
+        v[2 * i] = x.x; v[2 * i + 1] = x.y;
+    }
+}
+
 // Staging area of one warp: the next cell's own row and its first two tributary rows travel L2 -> shared memory
 // (cp.async, no registers) while the current cell is routed.  [slot][float4 index][lane]: every lane reads and writes
 // only its own column, so no warp barrier is involved.
@@ -500,7 +519,7 @@ template <int S> __device__ __forceinline__ void staged_row(const RowStage<S> &s
 }
 
 template <int S, int TAPE>
-__device__ __forceinline__ void route_chain(const SplitArgs &a, RowStage<S> &stg, int m, int task, int w, int lane, int t_first,
+__device__ __forceinline__ void route_chain_warp(const SplitArgs &a, RowStage<S> &stg, int m, int task, int w, int lane, int t_first,
                                             int epoch) {
     const SplitTopo &tp = a.tp;
     const int cb = tp.task_begin[task], ce = tp.task_begin[task + 1];
@@ -621,41 +640,235 @@ __device__ __forceinline__ void route_chain(const SplitArgs &a, RowStage<S> &stg
     }
 }
 
-// Tasks [0, nchain - nded) are claimed through the ticket, in dependency order.  The nded longest chains (main rivers)
-// have warps of their own (the first CTAs of the grid): they start at once and advance as their tributaries finish,
-// instead of queueing behind the rest of their basin -- a long chain is a serial walk and sets the kernel's duration.
+// One CTA (4 warps) per task, the time window spread over its 128 threads (S4 consecutive steps each), so that a cell
+// on the critical path of a river costs S4-step passes, one warp scan and two CTA barriers.  Shared memory holds the
+// next cell's own row and its first two tributary rows (cp.async while the current cell is routed).
+template <int S4> struct ChainShared {
+    float stg[3][128 * S4];      // staged row windows: slot 0 own qt row, slots 1-2 first two tributaries
+    float warp_b[4];             // scan: end value of each warp's segment
+    int ticket;
+};
+
+template <int S4, int TAPE>
+__device__ __forceinline__ void route_chain_cta(const SplitArgs &a, ChainShared<S4> &sh, int m, int task, int w, int t_first, int epoch) {
+    constexpr int W = 128 * S4;
+    const SplitTopo &tp = a.tp;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cb = tp.task_begin[task], ce = tp.task_begin[task + 1];
+    int *done = a.done + (size_t)m * tp.ntask;
+    const float *rows_lane = a.rows + (size_t)m * tp.npad * a.Tp + t_first;
+    const float *rows_win = a.rows + (size_t)m * tp.npad * a.Tp + (size_t)w * W;
+    const int tcap = min(a.T, (w + 1) * W) - 1;                  // last valid step of this window: its state is carried on
+    float r[S4];
+#pragma unroll
+    for (int s = 0; s < S4; s++) r[s] = 0.0f;
+    const bool prof = a.dbg_prof != nullptr && task >= tp.nchain - tp.nded;
+    long long t_start = 0, t_wait = 0;
+    if (prof) t_start = clock64();
+    int ngr = 0;
+#pragma unroll 1
+    for (int g0 = cb; g0 < ce; g0 += ngr) {
+        ngr = min(32, ce - g0);
+        int4 rec = make_int4(-1, 0, 0, 0);
+        if (lane < ngr) rec = tp.tcell[g0 + lane];
+        {   // the group ends where its inflow entries would no longer fit the 32 lanes that hold them
+            int cum = (lane < ngr) ? (rec.y >> 8) : 0;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int o = __shfl_up_sync(FULL, cum, d);
+                if (lane >= d) cum += o;
+            }
+            ngr = max(1, __popc(__ballot_sync(FULL, lane < ngr && cum <= 32)));
+            if (lane >= ngr) rec = make_int4(-1, 0, 0, 0);
+        }
+        RouteConst ci = {0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+        if (lane < ngr && (rec.y & 1)) ci = route_const(a, m, rec.x, a.hcar);
+        const int up0 = __shfl_sync(FULL, rec.z, 0);
+        const int nup_all = __shfl_sync(FULL, rec.z + (rec.y >> 8), ngr - 1) - up0;
+        int2 ent = make_int2(-1, UP_HEAVY);
+        long long tw0 = 0;
+        if (prof) tw0 = clock64();
+        if (lane < nup_all) ent = tp.tup[up0 + lane];
+        if (warp == 0) {        // one warp awaits the tributaries of the whole group (lane-parallel) and asks DRAM for the rows
+            if (ent.y >= 0)
+                while (ld_acquire(done + ent.y) < epoch) __nanosleep(64);
+            if (ent.y > UP_HEAVY) prefetch_row<4 * S4>(rows_win + (size_t)ent.x * a.Tp);
+            if (lane < ngr) prefetch_row<4 * S4>(rows_win + (size_t)rec.x * a.Tp);
+        }
+        __syncthreads();
+        if (prof) t_wait += clock64() - tw0;
+        int ns1 = -1, ns2 = -1;                                         // group entry indices staged in slots 1 and 2
+        auto stage_window = [&](int slot, const float *row_window) {    // W floats = 32 * S4 chunks of 16 bytes
+            for (int k = tid; k < 32 * S4; k += 128) cp_async16(&sh.stg[slot][4 * k], row_window + 4 * k);
+        };
+        auto stage_cell = [&](int c) {
+            const int jn = __shfl_sync(FULL, rec.x, c);
+            const int mn = __shfl_sync(FULL, rec.y, c);
+            const int un = __shfl_sync(FULL, rec.z, c) - up0;
+            stage_window(0, rows_win + (size_t)jn * a.Tp);
+            ns1 = -1; ns2 = -1;
+            const int nupn = (mn & 1) ? (mn >> 8) : 0;
+            for (int e = 0; e < nupn && ns2 < 0; e++) {
+                const int idx = un + e;
+                if (idx >= 32) break;
+                const int ux = __shfl_sync(FULL, ent.x, idx), uy = __shfl_sync(FULL, ent.y, idx);
+                if (uy > UP_HEAVY) {
+                    stage_window(ns1 < 0 ? 1 : 2, rows_win + (size_t)ux * a.Tp);
+                    if (ns1 < 0) ns1 = idx; else ns2 = idx;
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        stage_cell(0);
+#pragma unroll 1
+        for (int c = 0; c < ngr; c++) {
+            const int j = __shfl_sync(FULL, rec.x, c);
+            const int meta = __shfl_sync(FULL, rec.y, c);
+            const int uo = __shfl_sync(FULL, rec.z, c) - up0;
+            const int s1 = ns1, s2 = ns2;
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();                                             // staged rows of this cell are in shared memory
+            float qt[S4];
+            lds_vec<S4>(&sh.stg[0][tid * S4], qt);
+            if (meta & 1) {
+                float x[S4];
+#pragma unroll
+                for (int s = 0; s < S4; s++) x[s] = 0.0f;
+                const int nup = meta >> 8;
+#pragma unroll 1
+                for (int e = 0; e < nup; e++) {                         // md_routing_operator.f90:37-53, same order
+                    const int idx = uo + e;
+                    int2 u;
+                    u.x = __shfl_sync(FULL, ent.x, idx & 31); u.y = __shfl_sync(FULL, ent.y, idx & 31);
+                    if (idx >= 32) {                                     // a single cell with more entries than lanes: never on a D8 mesh
+                        u = tp.tup[up0 + idx];
+                        if (u.y >= 0) wait_flag(done + u.y, epoch, lane);
+                    }
+                    if (u.y <= UP_HEAVY) {
+#pragma unroll
+                        for (int s = 0; s < S4; s++) x[s] = x[s] + r[s];
+                    } else {
+                        float v[S4];
+                        if (idx == s1) lds_vec<S4>(&sh.stg[1][tid * S4], v);
+                        else if (idx == s2) lds_vec<S4>(&sh.stg[2][tid * S4], v);
+                        else ld_vec<S4>(rows_lane + (size_t)u.x * a.Tp, v);
+#pragma unroll
+                        for (int s = 0; s < S4; s++) x[s] = x[s] + v[s];
+                    }
+                }
+                const RouteConst cc = shfl_const(ci, c);
+                const float E = cc.E;
+                // local pass from a zero state (thread 0 starts from the carried state), slopes by squaring
+                float h = (tid == 0) ? cc.h0 : 0.0f;
+                float A = 1.0f;
+#pragma unroll
+                for (int s = 0; s < S4; s++) {
+                    x[s] = x[s] * cc.s_q;
+                    h = fmaf(h, E, x[s] * E);                            // carries only: one dependent FMA per step
+                    A *= E;
+                }
+                float Bv = h, pw = 1.0f;                                 // pw -> A1^lane
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const float Bo = __shfl_up_sync(FULL, Bv, d);
+                    if (lane >= d) Bv = fmaf(A, Bo, Bv);
+                    if (lane & d) pw *= A;
+                    A *= A;
+                }
+                if (lane == 31) sh.warp_b[warp] = Bv;                    // A is now the slope of a whole warp
+                float hin = __shfl_up_sync(FULL, Bv, 1);
+                if (lane == 0) hin = 0.0f;
+                __syncthreads();                                         // warp totals visible; everybody is done with the staged rows
+                if (c + 1 < ngr) stage_cell(c + 1);                      // travels while this cell is finished
+                float cw = 0.0f;
+                for (int k = 0; k < warp; k++) cw = fmaf(A, cw, sh.warp_b[k]);
+                h = fmaf(pw, cw, hin);
+                if (tid == 0) h = cc.h0;
+                float hr[S4];
+#pragma unroll
+                for (int s = 0; s < S4; s++) {
+                    hr[s] = h + x[s];                                    // md_routing_operator.f90:73
+                    const float hn = hr[s] * E;                          // :75
+                    r[s] = fmaf(hr[s] - hn, cc.fa1, qt[s]) * cc.c0;     // :77, md_forward_structure.f90:155
+                    if (t_first + s == tcap) {
+                        a.hcar[(size_t)m * tp.npad + j] = hn;
+                        if (w == a.nwin - 1) a.fstates[((size_t)m * 3 + 2) * tp.npad + j] = hn;
+                    }
+                    h = hn;
+                }
+                st_vec<S4>(a.rows + ((size_t)m * tp.npad + j) * a.Tp + t_first, r);
+                if (TAPE) st_vec<S4>(a.rows_hr + ((size_t)m * tp.npad + j) * a.Tp + t_first, hr);
+                if (meta & 2) {
+                    float *qsim = a.qsim + (size_t)m * a.T * tp.ng;
+                    for (int g = tp.gauge_first[j]; g >= 0; g = tp.gauge_next[g])
+#pragma unroll
+                        for (int s = 0; s < S4; s++)
+                            if (t_first + s < a.T) qsim[(size_t)(t_first + s) * tp.ng + g] = r[s];   // :206-210
+                }
+            } else {
+                __syncthreads();
+                if (c + 1 < ngr) stage_cell(c + 1);
+#pragma unroll
+                for (int s = 0; s < S4; s++) r[s] = qt[s];               // source cell at the chain head: already final
+            }
+        }
+    }
+    __syncthreads();                                                     // every thread's row stores precede the release
+    if (tid == 0) st_release(done + task, epoch);
+    if (prof && tid == 0) {
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        unsigned long long *o = a.dbg_prof + 4 * (size_t)(task - (tp.nchain - tp.nded));
+        o[0] = (unsigned long long)(ce - cb); o[1] = (unsigned long long)(clock64() - t_start); o[2] = (unsigned long long)t_wait; o[3] = gt;
+    }
+}
+
+// Tasks [0, nchain - nded) are claimed through the ticket, in dependency order, one warp per chain (lane = S steps).
+// The nded longest chains (main rivers) have a CTA each (the first CTAs of the grid; thread = S/4 steps): they start at
+// once and advance as their tributaries finish instead of queueing behind the rest of their basin -- a long chain is a
+// serial walk and sets the kernel's duration, so it gets four warps per cell and no queue.
 template <int S, int TAPE>
 __global__ void __launch_bounds__(128, 3) route_forward_kernel(const SplitArgs a, const int w, const int ded_blocks) {
-    __shared__ __align__(16) RowStage<S> stage_all[4];
-    RowStage<S> &stg = stage_all[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
+    union Shared {
+        RowStage<S> warp_stage[4];
+        ChainShared<S / 4> cta;
+    };
+    __shared__ __align__(16) Shared sh;
     const SplitTopo &tp = a.tp;
-    const int t_first = w * a.W + lane * S;
     const int epoch = w + 1;
     if ((int)blockIdx.x < ded_blocks) {
-        const int d = blockIdx.x * 4 + (threadIdx.x >> 5);
-        if (d < tp.nded)
-            for (int m = 0; m < a.nmember; m++) route_chain<S, TAPE>(a, stg, m, tp.nchain - tp.nded + d, w, lane, t_first, epoch);
+        const int t_first = w * a.W + threadIdx.x * (S / 4);
+        for (int m = 0; m < a.nmember; m++) route_chain_cta<S / 4, TAPE>(a, sh.cta, m, tp.nchain - tp.nded + blockIdx.x, w, t_first, epoch);
         return;
     }
-    const int nticket = tp.ntask - tp.nded;
+    const int lane = threadIdx.x & 31;
+    RowStage<S> &stg = sh.warp_stage[threadIdx.x >> 5];
+    const int t_first = w * a.W + lane * S;
+    const int nticket = tp.nchain - tp.nded;                // pit pairs are routed by route_pairs_kernel afterwards
     const int total = nticket * a.nmember;
     int tk_next = claim_ticket(a.ticket, lane);
     for (;;) {
         const int tk = tk_next;
         if (tk >= total) break;
         tk_next = claim_ticket(a.ticket, lane);            // the next ticket travels while this task is routed
-        const int m = tk / nticket, t = tk - m * nticket;
-        const int task = t < tp.nchain - tp.nded ? t : t + tp.nded;
-        if (task >= tp.nchain) {
-            const int cb = tp.task_begin[task];
-            int *done = a.done + (size_t)m * tp.ntask;
-            route_pair<S, TAPE>(a, m, tp.tcell[cb], tp.tcell[cb + 1], w, lane, t_first, done, epoch);
-            publish_flag(done + task, epoch, lane);
-            continue;
-        }
-        route_chain<S, TAPE>(a, stg, m, task, w, lane, t_first, epoch);
+        const int m = tk / nticket, task = tk - m * nticket;
+        route_chain_warp<S, TAPE>(a, stg, m, task, w, lane, t_first, epoch);
     }
+}
+
+// pit pairs: terminal cells (they only drain into each other), routed after all chains; one warp per pair
+template <int S, int TAPE>
+__global__ void __launch_bounds__(128) route_pairs_kernel(const SplitArgs a, const int w) {
+    const SplitTopo &tp = a.tp;
+    const int lane = threadIdx.x & 31;
+    const int npair = tp.ntask - tp.nchain;
+    const int p = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (p >= npair * a.nmember) return;
+    const int m = p / npair, task = tp.nchain + (p - m * npair);
+    const int cb = tp.task_begin[task];
+    int *done = a.done + (size_t)m * tp.ntask;
+    route_pair<S, TAPE>(a, m, tp.tcell[cb], tp.tcell[cb + 1], w, lane, w * a.W + lane * S, done, w + 1);
+    publish_flag(done + task, w + 1, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1088,10 +1301,11 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
     int blocks = 0;
     cudaError_t e = tape ? persistent_grid(route_forward_kernel<S, 1>, &blocks) : persistent_grid(route_forward_kernel<S, 0>, &blocks);
     if (e != cudaSuccess) return e;
-    const int ded_blocks = (a.tp.nded + 3) / 4;            // api.cu keeps nded well below the resident grid
-    const long long total = (long long)(a.tp.ntask - a.tp.nded) * a.nmember;
-    const int need = (int)((total + 3) / 4) + ded_blocks;
-    if (blocks > need) blocks = need > 0 ? need : 1;
+    const int ded_blocks = a.tp.nded;                      // one CTA per dedicated chain (route_graph.cpp keeps nded small)
+    const long long total = (long long)(a.tp.nchain - a.tp.nded) * a.nmember;
+    const long long need = (total + 3) / 4 + ded_blocks;
+    const int npair = (a.tp.ntask - a.tp.nchain) * a.nmember;
+    if (blocks > need) blocks = need > 0 ? (int)need : 1;
     if (blocks <= ded_blocks) return cudaErrorLaunchOutOfResources;
     for (int w = 0; w < a.nwin; w++) {
         e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), s);
@@ -1100,6 +1314,12 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
         else route_forward_kernel<S, 0><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+        if (npair > 0) {
+            if (tape) route_pairs_kernel<S, 1><<<(npair + 3) / 4, 128, 0, s>>>(a, w);
+            else route_pairs_kernel<S, 0><<<(npair + 3) / 4, 128, 0, s>>>(a, w);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
     }
     return cudaSuccess;
 }
