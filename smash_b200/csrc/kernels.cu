@@ -457,10 +457,10 @@ struct Series {
 
 struct Moments { int n; float sum_x, sum_y, sum_xx, sum_yy, sum_xy, se, lg; };
 
-__device__ Moments moments(const Series &s) {
-    Moments m = {0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int i = 0; i < s.n; i++) {
-        const float x = s.qo(i), y = s.qs(i);
+// sums over one chunk of precomputed (x, y) = (qo, qs) values, in the reference's order (mwd_cost.f90:350-490)
+__device__ void moments_acc(Moments &m, const float *xs, const float *ys, int len) {
+    for (int i = 0; i < len; i++) {
+        const float x = xs[i], y = ys[i];
         if (x >= 0.0f) {
             m.n++;
             m.sum_x = FA(m.sum_x, x);
@@ -473,7 +473,6 @@ __device__ Moments moments(const Series &s) {
         }
         if (x > 0.0f && y > 0.0f) { const float lq = logf(FD(y, x)); m.lg = FA(m.lg, FM(FM(x, lq), lq)); }
     }
-    return m;
 }
 
 __device__ float nse_of(const Moments &m) {          // mwd_cost.f90:350-401
@@ -498,19 +497,33 @@ __device__ Kge kge_of(const Moments &m) {            // mwd_cost.f90:403-490
     return k;
 }
 
-__global__ void cost_kernel(const CostArgs c) {
-    extern __shared__ float sh[];            // [ng] gauge_jobs, [ng] gauge_jobs_b
-    float *gj = sh, *gjb = sh + c.ng;
+// One CTA per member, one thread per gauge for the order-dependent sums.  The element-wise part (unit conversion with
+// its IEEE divisions) is done by the whole CTA into shared memory, chunk by chunk, so the sequential part is adds only.
+__global__ void cost_kernel(const CostArgs c, const int CH) {
+    extern __shared__ float sh[];            // [ng] gauge_jobs, [ng] gauge_jobs_b, [ng][7] adjoint coefficients, [ng][CH] x, [ng][CH] y
+    float *gj = sh, *gjb = sh + c.ng, *coef = sh + 2 * c.ng, *xs = sh + 9 * c.ng, *ys = xs + (size_t)c.ng * CH;
     const int m = blockIdx.x;
     const int n = c.T - c.start;
-    // per gauge adjoint coefficients: y_b(i) = cx*x + cy*y + c0 (+ special terms)
-    for (int g = threadIdx.x; g < c.ng; g += blockDim.x) {
+    const int g = threadIdx.x;               // launch_cost: blockDim.x >= ng
+    const float *qsim = c.qsim + (size_t)m * c.T * c.ng;
+    const bool mine = g < c.ng && (c.wgauge[g] > 0.0f || c.wgauge[g] < 0.0f);
+    Moments mo = {0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c0 = 0; c0 < n; c0 += CH) {
+        const int len = min(CH, n - c0);
+        for (int idx = threadIdx.x; idx < len * c.ng; idx += blockDim.x) {
+            const int i = idx / c.ng, gg = idx - i * c.ng;
+            const size_t at = (size_t)(c.start + c0 + i) * c.ng + gg;
+            const float dden = FM(FM((float)c.gauge_flwacc[gg], c.dx), c.dx);
+            xs[(size_t)gg * CH + i] = FM(FD(FM(c.qobs[at], c.dt), dden), 1e3f);        // qo, mwd_cost.f90:88-92
+            ys[(size_t)gg * CH + i] = FM(FD(FM(qsim[at], c.dt), c.area[gg]), 1e3f);   // qs, :84-86
+        }
+        __syncthreads();
+        if (mine) moments_acc(mo, xs + (size_t)g * CH, ys + (size_t)g * CH, len);
+        __syncthreads();
+    }
+    if (g < c.ng) {
         float gauge_jobs = 0.0f;
-        const float wg = c.wgauge[g];
-        if (wg > 0.0f || wg < 0.0f) {
-            Series s = {c.qsim + (size_t)m * c.T * c.ng, c.qobs, c.ng, g, c.start, n, 0.f, 0.f, c.dt, c.area[g],
-                        FM(FM((float)c.gauge_flwacc[g], c.dx), c.dx)};
-            const Moments mo = moments(s);
+        if (mine) {
             float j_imd = 0.0f;
             for (int j = 0; j < c.njf; j++) {
                 if (mo.n > 0) {
@@ -565,15 +578,11 @@ __global__ void cost_kernel(const CostArgs c) {
     }
     if (c.qsim_b == nullptr) return;
     __syncthreads();
-    for (int g = threadIdx.x; g < c.ng; g += blockDim.x) {
-        float *qb = c.qsim_b + (size_t)m * c.T * c.ng;
-        for (int t = 0; t < c.T; t++) qb[(size_t)t * c.ng + g] = 0.0f;
-        const float wg = c.wgauge[g];
-        if (!(wg > 0.0f || wg < 0.0f)) continue;
-        Series s = {c.qsim + (size_t)m * c.T * c.ng, c.qobs, c.ng, g, c.start, n, 0.f, 0.f, c.dt, c.area[g],
-                    FM(FM((float)c.gauge_flwacc[g], c.dx), c.dx)};
-        const Moments mo = moments(s);
-        if (mo.n == 0) continue;
+    if (g < c.ng) {
+        float *cf = coef + 7 * g;
+        for (int k = 0; k < 7; k++) cf[k] = 0.0f;
+    }
+    if (mine && mo.n > 0) {
         const float gauge_jobs_b = gjb[g];
         // accumulate y_b(i) = cx*x(i) + cy*y(i) + c0 + (se / log terms)
         float cx = 0.f, cy = 0.f, c0 = 0.f, cse = 0.f, clg = 0.f;
@@ -614,14 +623,24 @@ __global__ void cost_kernel(const CostArgs c) {
                 default: break;
             }
         }
-        const float scale = FD(FM(c.dt, 1e3f), c.area[g]);       // :2709-2712
-        for (int i = 0; i < n; i++) {
-            const float x = s.qo(i), y = s.qs(i);
+        float *cf = coef + 7 * g;
+        cf[0] = cx; cf[1] = cy; cf[2] = c0; cf[3] = cse; cf[4] = clg; cf[5] = FD(FM(c.dt, 1e3f), c.area[g]); cf[6] = 1.0f;   // :2709-2712
+    }
+    __syncthreads();
+    float *qb = c.qsim_b + (size_t)m * c.T * c.ng;
+    for (int idx = threadIdx.x; idx < c.T * c.ng; idx += blockDim.x) {
+        const int t = idx / c.ng, gg = idx - t * c.ng;
+        const float *cf = coef + 7 * gg;
+        float out = 0.0f;
+        if (t >= c.start && cf[6] != 0.0f) {
+            const float dden = FM(FM((float)c.gauge_flwacc[gg], c.dx), c.dx);
+            const float x = FM(FD(FM(c.qobs[idx], c.dt), dden), 1e3f), y = FM(FD(FM(qsim[idx], c.dt), c.area[gg]), 1e3f);
             float yb = 0.0f;
-            if (x >= 0.0f) yb = FA(FA(FM(x, cx), FM(y, cy)), c0) - FM(FM(2.0f, FS(x, y)), cse);
-            if (clg != 0.0f && x > 0.0f && y > 0.0f) yb = FA(yb, FD(FM(FM(FM(2.0f, x), logf(FD(y, x))), clg), y));
-            qb[(size_t)(c.start + i) * c.ng + g] = FM(scale, yb);
+            if (x >= 0.0f) yb = FA(FA(FM(x, cf[0]), FM(y, cf[1])), cf[2]) - FM(FM(2.0f, FS(x, y)), cf[3]);
+            if (cf[4] != 0.0f && x > 0.0f && y > 0.0f) yb = FA(yb, FD(FM(FM(FM(2.0f, x), logf(FD(y, x))), cf[4]), y));
+            out = FM(cf[5], yb);
         }
+        qb[idx] = out;
     }
 }
 
@@ -729,8 +748,16 @@ cudaError_t launch_reverse(const SolverArgs &a, int math_mode, cudaStream_t s) {
 
 cudaError_t launch_cost(const CostArgs &c, cudaStream_t s) {
     if (c.ng <= 0 || c.nmember <= 0) return cudaSuccess;
-    int threads = c.ng < 32 ? 32 : (c.ng > 256 ? 256 : ((c.ng + 31) / 32) * 32);
-    cost_kernel<<<c.nmember, threads, 2 * c.ng * sizeof(float), s>>>(c);
+    if (c.ng > 1024) return cudaErrorInvalidValue;           // one thread per gauge
+    const int threads = c.ng <= 128 ? 128 : ((c.ng + 31) / 32) * 32;
+    int ch = (int)((40960 / sizeof(float) - 9 * (size_t)c.ng) / (2 * (size_t)c.ng));
+    ch = ch > 2048 ? 2048 : (ch < 32 ? 32 : ch / 32 * 32);
+    const size_t smem = (9 * (size_t)c.ng + 2 * (size_t)c.ng * ch) * sizeof(float);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    cost_kernel<<<c.nmember, threads, smem, s>>>(c, ch);
     return cudaGetLastError();
 }
 
