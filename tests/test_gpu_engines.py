@@ -1,0 +1,110 @@
+"""The two engines behind the ABI against each other, the plan API's per-kernel timers, and a
+full-size property check of the routing pass (BASELINE.json's France configuration, T = 720)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import smash_b200
+from smash_b200 import _lib as L
+from smash_b200.solver._derived_types import ParametersDT, StatesDT
+from test_gpu_parity import check_grad, random_fields
+
+pytestmark = pytest.mark.gpu
+
+
+def _with_engine(engine, fn):
+    lib = L.lib()
+    lib.smash_b200_set_option(b"engine", engine)
+    try:
+        return fn()
+    finally:
+        lib.smash_b200_set_option(b"engine", -1)
+        lib.smash_b200_clear_cache()
+
+
+def test_split_and_fused_engines_agree():
+    # 300 x 300 window of France, 96 steps, 4 gauges: discharge, cost and gradient of the split engine (reservoir pass +
+    # routing scan) against the fused tick wavefront, which evaluates the routing recurrence strictly sequentially
+    def run():
+        m = cases.france(T=96, sub=(400, 700, 400, 700), ngauge=4)
+        random_fields(m, seed=3)
+        pb, sb = ParametersDT(m.mesh), StatesDT(m.mesh)
+        smash_b200.forward_b(m.setup, m.mesh, m.input_data, m.parameters, pb, m.parameters.copy(), None, m.states, sb,
+                             m.states.copy(), None, m.output, None)
+        return m, pb, sb
+    a, pa, sa = _with_engine(1, run)
+    b, pb, sb = _with_engine(0, run)
+    qa, qb = np.asarray(a.output.qsim, np.float64), np.asarray(b.output.qsim, np.float64)
+    assert np.all(np.abs(qa - qb) <= 1e-6 + 1e-4 * np.abs(qb)), float(np.abs(qa - qb).max())
+    assert np.isclose(float(a.output.cost), float(b.output.cost), rtol=1e-4)
+    check_grad(pa, pb, ("cp", "cft", "exc", "lr"))
+    check_grad(sa, sb, ("hp", "hft", "hlr"))
+
+
+def _plan(m, members=1):
+    lib = L.lib()
+    pk = L.Packed()
+    s_, m_, i_ = L.pack_setup(m.setup, m.mesh, pk), L.pack_mesh(m.mesh, m.setup, pk), L.pack_input(m.input_data, m.setup, m.mesh, pk)
+    p_, st_ = L.pack_parameters(m.parameters, pk), L.pack_states(m.states, pk)
+    plan = C.c_void_p()
+    L.check(lib.smash_b200_plan_create(C.byref(s_), C.byref(m_), members, C.byref(plan)))
+    L.check(lib.smash_b200_plan_set_forcing(plan, C.byref(s_), C.byref(i_)))
+    L.check(lib.smash_b200_plan_set_fields(plan, C.byref(p_), C.byref(st_), None, None, 0))
+    return plan, pk
+
+
+def test_plan_kernel_times_and_stats():
+    lib = L.lib()
+    m = cases.cance(sparse=True, T=240)
+    plan, keep = _plan(m)
+    try:
+        assert lib.smash_b200_plan_stat(plan, b"engine") == 1.0                  # default: split engine
+        routed, src = lib.smash_b200_plan_stat(plan, b"routed_cells"), lib.smash_b200_plan_stat(plan, b"source_cells")
+        assert routed + src == 383 and src == 194                                # Cance: 194 cells with flwacc == 1
+        assert lib.smash_b200_plan_stat(plan, b"inflow_edges") == 382            # a tree with one outlet
+        ms = C.c_float(0)
+        L.check(lib.smash_b200_plan_run_forward(plan, C.byref(ms)))
+        kt = (C.c_float * 5)()
+        L.check(lib.smash_b200_plan_kernel_times(plan, kt))
+        assert kt[0] > 0 and kt[1] > 0 and kt[3] < 0 and kt[4] < 0             # forward kernels ran, adjoint ones did not
+        assert kt[0] + kt[1] <= ms.value * 1.05
+        f, r = C.c_float(0), C.c_float(0)
+        L.check(lib.smash_b200_plan_run_gradient(plan, C.byref(f), C.byref(r)))
+        L.check(lib.smash_b200_plan_kernel_times(plan, kt))
+        assert kt[3] > 0 and kt[4] > 0
+    finally:
+        lib.smash_b200_plan_destroy(plan)
+
+
+def test_france_full_size_engines_and_routing_properties():
+    # BASELINE.json's France configuration at full size (906 044 cells, T = 720): the CPU oracle needs minutes here, so the
+    # run is checked (a) by the checksum of the whole domain discharge (sum over 6.5e8 cell-steps, double accumulation)
+    # of the split engine against the fused engine -- two independent implementations, each pinned to the oracle at
+    # smaller sizes -- and (b) through a property of linear_routing (md_routing_operator.f90:62-79): a shorter routing
+    # time lr drains the routing stores earlier, so more water has passed through the cells by the end of the run.
+    lib = L.lib()
+    m = cases.france(T=720)
+
+    def checksum(engine, lr):
+        m.parameters.lr[...] = lr
+        lib.smash_b200_set_option(b"engine", engine)
+        try:
+            plan, keep = _plan(m)
+            try:
+                assert lib.smash_b200_plan_stat(plan, b"engine") == float(engine)
+                ms = C.c_float(0)
+                L.check(lib.smash_b200_plan_run_forward(plan, C.byref(ms)))
+                chk = C.c_double(0)
+                L.check(lib.smash_b200_plan_checksum(plan, C.byref(chk)))
+                return chk.value
+            finally:
+                lib.smash_b200_plan_destroy(plan)
+        finally:
+            lib.smash_b200_set_option(b"engine", -1)
+
+    split, fused, fast = checksum(1, 5.0), checksum(0, 5.0), checksum(1, 0.05)
+    assert np.isfinite([split, fused, fast]).all() and split > 0
+    assert abs(split - fused) <= 2e-6 * fused, (split, fused)
+    assert fast > split
