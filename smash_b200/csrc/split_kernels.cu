@@ -643,10 +643,16 @@ __device__ __forceinline__ void route_chain_warp(const SplitArgs &a, RowStage<S>
 // One CTA (4 warps) per task, the time window spread over its 128 threads (S4 consecutive steps each), so that a cell
 // on the critical path of a river costs S4-step passes, one warp scan and two CTA barriers.  Shared memory holds the
 // next cell's own row and its first two tributary rows (cp.async while the current cell is routed).
+struct CellPlan {                // decoded once per group, lane-parallel, then read by every thread (broadcast)
+    int j, meta;                 // meta: bit 0 routed, bit 1 gauge, bits 8-11 terms of the inflow sum, bits 12-15 position of the
+    int lat[3];                  //       chain predecessor among them (15: none), bit 16: more than three tributaries
+    int up_off, nup;             // lat: first three tributary cells in summation order (-1: none); full entry list for the rest
+    float fa1, s_q, E, c0, h0;
+};
 template <int S4> struct ChainShared {
-    float stg[3][128 * S4];      // staged row windows: slot 0 own qt row, slots 1-2 first two tributaries
+    float stg[4][128 * S4];      // staged row windows: slot 0 own qt row, slots 1-3 first three tributaries
     float warp_b[4];             // scan: end value of each warp's segment
-    int ticket;
+    CellPlan plan[32];
 };
 
 template <int S4, int TAPE>
@@ -669,63 +675,52 @@ __device__ __forceinline__ void route_chain_cta(const SplitArgs &a, ChainShared<
 #pragma unroll 1
     for (int g0 = cb; g0 < ce; g0 += ngr) {
         ngr = min(32, ce - g0);
-        int4 rec = make_int4(-1, 0, 0, 0);
-        if (lane < ngr) rec = tp.tcell[g0 + lane];
-        {   // the group ends where its inflow entries would no longer fit the 32 lanes that hold them
-            int cum = (lane < ngr) ? (rec.y >> 8) : 0;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int o = __shfl_up_sync(FULL, cum, d);
-                if (lane >= d) cum += o;
-            }
-            ngr = max(1, __popc(__ballot_sync(FULL, lane < ngr && cum <= 32)));
-            if (lane >= ngr) rec = make_int4(-1, 0, 0, 0);
-        }
-        RouteConst ci = {0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
-        if (lane < ngr && (rec.y & 1)) ci = route_const(a, m, rec.x, a.hcar);
-        const int up0 = __shfl_sync(FULL, rec.z, 0);
-        const int nup_all = __shfl_sync(FULL, rec.z + (rec.y >> 8), ngr - 1) - up0;
-        int2 ent = make_int2(-1, UP_HEAVY);
         long long tw0 = 0;
         if (prof) tw0 = clock64();
-        if (lane < nup_all) ent = tp.tup[up0 + lane];
-        if (warp == 0) {        // one warp awaits the tributaries of the whole group (lane-parallel) and asks DRAM for the rows
-            if (ent.y >= 0)
-                while (ld_acquire(done + ent.y) < epoch) __nanosleep(64);
-            if (ent.y > UP_HEAVY) prefetch_row<4 * S4>(rows_win + (size_t)ent.x * a.Tp);
-            if (lane < ngr) prefetch_row<4 * S4>(rows_win + (size_t)rec.x * a.Tp);
+        __syncthreads();                                                 // the previous group's plans are no longer read
+        if (warp == 0) {
+            // lane = cell: decode its record and inflow entries, await its tributaries, ask DRAM for its rows
+            if (lane < ngr) {
+                const int4 rec = tp.tcell[g0 + lane];
+                CellPlan P;
+                P.j = rec.x; P.up_off = rec.z; P.nup = (rec.y & 1) ? (rec.y >> 8) : 0;
+                P.lat[0] = P.lat[1] = P.lat[2] = -1;
+                int nlat = 0, hpos = 15;
+                for (int e = 0; e < P.nup; e++) {
+                    const int2 u = tp.tup[rec.z + e];
+                    if (u.y <= UP_HEAVY) { hpos = e; continue; }
+                    if (u.y >= 0)
+                        while (ld_acquire(done + u.y) < epoch) __nanosleep(64);   // tributary of another task
+                    prefetch_row<4 * S4>(rows_win + (size_t)u.x * a.Tp);
+                    if (nlat < 3) P.lat[nlat] = u.x;
+                    nlat++;
+                }
+                P.meta = (rec.y & 3) | (P.nup << 8) | (hpos << 12) | (nlat > 3 ? 1 << 16 : 0);
+                RouteConst ci = {0.f, 0.f, 0.f, 0.f, 1.f, 0.f};
+                if (rec.y & 1) ci = route_const(a, m, rec.x, a.hcar);
+                P.fa1 = ci.fa1; P.s_q = ci.s_q; P.E = ci.E; P.c0 = ci.c0; P.h0 = ci.h0;
+                prefetch_row<4 * S4>(rows_win + (size_t)rec.x * a.Tp);
+                sh.plan[lane] = P;
+            }
         }
         __syncthreads();
         if (prof) t_wait += clock64() - tw0;
-        int ns1 = -1, ns2 = -1;                                         // group entry indices staged in slots 1 and 2
         auto stage_window = [&](int slot, const float *row_window) {    // W floats = 32 * S4 chunks of 16 bytes
             for (int k = tid; k < 32 * S4; k += 128) cp_async16(&sh.stg[slot][4 * k], row_window + 4 * k);
         };
         auto stage_cell = [&](int c) {
-            const int jn = __shfl_sync(FULL, rec.x, c);
-            const int mn = __shfl_sync(FULL, rec.y, c);
-            const int un = __shfl_sync(FULL, rec.z, c) - up0;
-            stage_window(0, rows_win + (size_t)jn * a.Tp);
-            ns1 = -1; ns2 = -1;
-            const int nupn = (mn & 1) ? (mn >> 8) : 0;
-            for (int e = 0; e < nupn && ns2 < 0; e++) {
-                const int idx = un + e;
-                if (idx >= 32) break;
-                const int ux = __shfl_sync(FULL, ent.x, idx), uy = __shfl_sync(FULL, ent.y, idx);
-                if (uy > UP_HEAVY) {
-                    stage_window(ns1 < 0 ? 1 : 2, rows_win + (size_t)ux * a.Tp);
-                    if (ns1 < 0) ns1 = idx; else ns2 = idx;
-                }
-            }
+            const CellPlan &P = sh.plan[c];
+            stage_window(0, rows_win + (size_t)P.j * a.Tp);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+                if (P.lat[i] >= 0) stage_window(1 + i, rows_win + (size_t)P.lat[i] * a.Tp);
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         stage_cell(0);
 #pragma unroll 1
         for (int c = 0; c < ngr; c++) {
-            const int j = __shfl_sync(FULL, rec.x, c);
-            const int meta = __shfl_sync(FULL, rec.y, c);
-            const int uo = __shfl_sync(FULL, rec.z, c) - up0;
-            const int s1 = ns1, s2 = ns2;
+            const CellPlan &P = sh.plan[c];
+            const int j = P.j, meta = P.meta;
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();                                             // staged rows of this cell are in shared memory
             float qt[S4];
@@ -734,40 +729,46 @@ __device__ __forceinline__ void route_chain_cta(const SplitArgs &a, ChainShared<
                 float x[S4];
 #pragma unroll
                 for (int s = 0; s < S4; s++) x[s] = 0.0f;
-                const int nup = meta >> 8;
+                const int nup = meta >> 8 & 15, hpos = meta >> 12 & 15;
+                if (!(meta >> 16 & 1)) {
 #pragma unroll 1
-                for (int e = 0; e < nup; e++) {                         // md_routing_operator.f90:37-53, same order
-                    const int idx = uo + e;
-                    int2 u;
-                    u.x = __shfl_sync(FULL, ent.x, idx & 31); u.y = __shfl_sync(FULL, ent.y, idx & 31);
-                    if (idx >= 32) {                                     // a single cell with more entries than lanes: never on a D8 mesh
-                        u = tp.tup[up0 + idx];
-                        if (u.y >= 0) wait_flag(done + u.y, epoch, lane);
+                    for (int k = 0; k < nup; k++) {                     // md_routing_operator.f90:37-53, same order
+                        if (k == hpos) {
+#pragma unroll
+                            for (int s = 0; s < S4; s++) x[s] = x[s] + r[s];
+                        } else {
+                            float v[S4];
+                            lds_vec<S4>(&sh.stg[1 + k - (k > hpos ? 1 : 0)][tid * S4], v);
+#pragma unroll
+                            for (int s = 0; s < S4; s++) x[s] = x[s] + v[s];
+                        }
                     }
-                    if (u.y <= UP_HEAVY) {
+                } else {                                                 // more than three tributaries (rare): rows from memory
+#pragma unroll 1
+                    for (int k = 0; k < nup; k++) {
+                        const int2 u = tp.tup[P.up_off + k];
+                        if (u.y <= UP_HEAVY) {
 #pragma unroll
-                        for (int s = 0; s < S4; s++) x[s] = x[s] + r[s];
-                    } else {
-                        float v[S4];
-                        if (idx == s1) lds_vec<S4>(&sh.stg[1][tid * S4], v);
-                        else if (idx == s2) lds_vec<S4>(&sh.stg[2][tid * S4], v);
-                        else ld_vec<S4>(rows_lane + (size_t)u.x * a.Tp, v);
+                            for (int s = 0; s < S4; s++) x[s] = x[s] + r[s];
+                        } else {
+                            float v[S4];
+                            ld_vec<S4>(rows_lane + (size_t)u.x * a.Tp, v);
 #pragma unroll
-                        for (int s = 0; s < S4; s++) x[s] = x[s] + v[s];
+                            for (int s = 0; s < S4; s++) x[s] = x[s] + v[s];
+                        }
                     }
                 }
-                const RouteConst cc = shfl_const(ci, c);
-                const float E = cc.E;
+                const float E = P.E, h0 = P.h0;
                 // local pass from a zero state (thread 0 starts from the carried state), slopes by squaring
-                float h = (tid == 0) ? cc.h0 : 0.0f;
+                float h = (tid == 0) ? h0 : 0.0f;
                 float A = 1.0f;
 #pragma unroll
                 for (int s = 0; s < S4; s++) {
-                    x[s] = x[s] * cc.s_q;
+                    x[s] = x[s] * P.s_q;
                     h = fmaf(h, E, x[s] * E);                            // carries only: one dependent FMA per step
                     A *= E;
                 }
-                float Bv = h, pw = 1.0f;                                 // pw -> A1^lane
+                float Bv = h, pw = 1.0f;                                 // pw -> (slope of one thread)^lane
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
                     const float Bo = __shfl_up_sync(FULL, Bv, d);
@@ -778,18 +779,19 @@ __device__ __forceinline__ void route_chain_cta(const SplitArgs &a, ChainShared<
                 if (lane == 31) sh.warp_b[warp] = Bv;                    // A is now the slope of a whole warp
                 float hin = __shfl_up_sync(FULL, Bv, 1);
                 if (lane == 0) hin = 0.0f;
+                const float fa1 = P.fa1, c0 = P.c0;
                 __syncthreads();                                         // warp totals visible; everybody is done with the staged rows
                 if (c + 1 < ngr) stage_cell(c + 1);                      // travels while this cell is finished
                 float cw = 0.0f;
                 for (int k = 0; k < warp; k++) cw = fmaf(A, cw, sh.warp_b[k]);
                 h = fmaf(pw, cw, hin);
-                if (tid == 0) h = cc.h0;
+                if (tid == 0) h = h0;
                 float hr[S4];
 #pragma unroll
                 for (int s = 0; s < S4; s++) {
                     hr[s] = h + x[s];                                    // md_routing_operator.f90:73
                     const float hn = hr[s] * E;                          // :75
-                    r[s] = fmaf(hr[s] - hn, cc.fa1, qt[s]) * cc.c0;     // :77, md_forward_structure.f90:155
+                    r[s] = fmaf(hr[s] - hn, fa1, qt[s]) * c0;           // :77, md_forward_structure.f90:155
                     if (t_first + s == tcap) {
                         a.hcar[(size_t)m * tp.npad + j] = hn;
                         if (w == a.nwin - 1) a.fstates[((size_t)m * 3 + 2) * tp.npad + j] = hn;
