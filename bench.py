@@ -285,7 +285,7 @@ def main():
     if rank == 0 and world == 1:
         import cases
         import oracle
-        Ts = 16
+        Ts = 64                                  # ~10 s of single-thread CPU work
         mc = cases.france(T=Ts, seed=0)
         mc.setup.save_qsim_domain = False
         t0 = time.perf_counter()
