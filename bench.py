@@ -233,7 +233,8 @@ def main():
                     "frac": kernels[top]["frac"], "traffic": kernels[top]["traffic"], "peak_source": peak_src, "kernel": top,
                     "kernel_ms": kernels[top]["ms"], "algorithmic_bytes_per_launch": kernels[top]["algorithmic_bytes"],
                     "kernels": kernels, "step": roofline_step}
-        launches_per_step = len(kernels)
+        lib.smash_b200_plan_info(plan, info)
+        launches_per_step = int(info[7])             # kernels launched by the last plan_run_forward (counted by the library)
     else:
         roofline = {"bound": "hbm", "achieved": roofline_step["achieved"], "peak": peak, "unit": "GB/s",
                     "frac": roofline_step["frac"], "traffic": traffic.get("forward_kernel"), "peak_source": peak_src,

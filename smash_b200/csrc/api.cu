@@ -430,7 +430,7 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
     mark(1);
     CU(launch_route_forward(a, tape, pl.stream));
     mark(2);
-    pl.launches += 1 + sp.nwin;
+    pl.launches += 1 + sp.nwin * (1 + (sp.rg.npair > 0 ? 1 : 0));   // reservoir pass + per window: chains (+ pit pairs)
     if (save_q) { CU(launch_rows_to_domain(a, pl.stream)); pl.launches++; }
     mark(3);
     return 0;
