@@ -90,7 +90,7 @@ struct SplitState {
     RouteGraph rg;
     int S = 0, W = 0, nwin = 0, Tp = 0;
     int64_t qpitch = 0;
-    DBuf<int32_t> d_flwacc, d_up_begin, d_down, d_down_task, d_down_need, d_task_begin, d_task_cells, d_gfirst, d_gnext;
+    DBuf<int32_t> d_flwacc, d_up_begin, d_down, d_down_task, d_down_need, d_rlist, d_rindex, d_task_begin, d_task_cells, d_gfirst, d_gnext;
     DBuf<RouteUp> d_up, d_tup;
     DBuf<TaskCell> d_tcell;
     DBuf<uint8_t> d_down_lag;
@@ -135,6 +135,7 @@ struct SmashPlan {
     DeviceTopology dtp{};
     int engine = 0;                 // 0: fused tick wavefront (kernels.cu), 1: split reservoirs / routing (split_kernels.cu)
     int sparse = 0;                 // setup.sparse_storage the plan was built for
+    bool ensemble = false;          // plan made for compute_multiple_run / a multi-member plan: lane = member routing
     SplitState sp;
     std::vector<int32_t> col_cell;  // per device column (slot / cell j): flat rect index or -1 on padding
     int ncols = 0;                  // columns of the per-cell device arrays (fields, fstates, grad)
@@ -319,6 +320,9 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     TRY(sp.d_down.upload(down, s)); TRY(sp.d_down_task.upload(down_task, s)); TRY(sp.d_down_need.upload(down_need, s)); TRY(sp.d_down_lag.upload(down_lag, s));
     TRY(sp.d_task_begin.upload(rg.task_begin, s)); TRY(sp.d_task_cells.upload(rg.task_cells, s));
     TRY(sp.d_gfirst.upload(gfirst, s)); TRY(sp.d_gnext.upload(rg.gauge_next, s));
+    std::vector<int32_t> rlist, rindex(npad, -1);
+    for (int j = 0; j < rg.n; j++) if (rg.flwacc[j] > 1) { rindex[j] = (int32_t)rlist.size(); rlist.push_back(j); }
+    TRY(sp.d_rlist.upload(rlist, s)); TRY(sp.d_rindex.upload(rindex, s));
     TRY(sp.d_tcell.upload(rg.tcell, s)); TRY(sp.d_tup.upload(rg.tup, s));
     TRY(pl.d_ticket.ensure(1)); TRY(pl.d_sum.ensure(1));
     SplitTopo &t = sp.topo;
@@ -326,6 +330,7 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     t.flwacc = sp.d_flwacc.p; t.up_begin = sp.d_up_begin.p; t.up = sp.d_up.p; t.down = sp.d_down.p; t.down_task = sp.d_down_task.p; t.down_need = sp.d_down_need.p;
     t.down_lag = sp.d_down_lag.p; t.task_begin = sp.d_task_begin.p; t.task_cells = sp.d_task_cells.p;
     t.gauge_first = sp.d_gfirst.p; t.gauge_next = sp.d_gnext.p;
+    t.nrouted = (int)rlist.size(); t.rlist = sp.d_rlist.p; t.rindex = sp.d_rindex.p;
     t.tcell = reinterpret_cast<const int4 *>(sp.d_tcell.p); t.tup = reinterpret_cast<const int2 *>(sp.d_tup.p);
     // the field gather kernel only needs the column -> cell map
     pl.dtp = DeviceTopology{};
@@ -428,7 +433,10 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
                          npad * sizeof(float), (size_t)pl.nmember, cudaMemcpyDeviceToDevice, pl.stream));
     CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), tape, pl.stream));
     mark(1);
-    CU(launch_route_forward(a, tape, pl.stream));
+    // ensembles on a small mesh: lane = member, exact sequential routing; otherwise the per-chain scan
+    const bool by_member = pl.ensemble && sp.rg.npair == 0 && a.tp.nrouted <= 12000;   // whatever the size of this launch
+    if (by_member) CU(launch_route_members(a, tape, pl.stream));
+    else CU(launch_route_forward(a, tape, pl.stream));
     mark(2);
     pl.launches += 1 + sp.nwin * (1 + (sp.rg.npair > 0 ? 1 : 0));   // reservoir pass + per window: chains (+ pit pairs)
     if (save_q) { CU(launch_rows_to_domain(a, pl.stream)); pl.launches++; }
@@ -869,6 +877,7 @@ static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const 
     TRY(get_plan(setup, mesh, &pl));
     *plan_out = pl;
     pl->launches = 0;
+    pl->ensemble = false;
     const Topology &tp = pl->tp;
     const bool save_q = setup->save_qsim_domain && out && (setup->sparse_storage ? out->sparse_qsim_domain : out->qsim_domain);
     const bool save_n = setup->save_net_prcp_domain && out && (setup->sparse_storage ? out->sparse_net_prcp_domain : out->net_prcp_domain);
@@ -943,6 +952,7 @@ static int gradient_common(const SmashSetup *setup, const SmashMesh *mesh, const
     TRY(get_plan(setup, mesh, &pl));
     *plan_out = pl;
     pl->launches = 0;
+    pl->ensemble = false;
     const Topology &tp = pl->tp;
     TRY(plan_members(*pl, 1, false, false, true));
     TRY(plan_set_forcing(*pl, setup, mesh, in));
@@ -1097,6 +1107,7 @@ extern "C" int smash_b200_compute_multiple_run(const SmashSetup *setup, const Sm
         if (ind[j] < 1 || ind[j] > SMASH_B200_GNP + SMASH_B200_GNS) return fail(SMASH_B200_EINVAL, "ind_parameters_states[%d] = %d out of range", j, ind[j]);
     SmashPlan *pl;
     TRY(get_plan(setup, mesh, &pl, (int)option("ensemble_engine", 0)));
+    pl->ensemble = true;
     pl->launches = 0;
     const Topology &tp = pl->tp;
     // members per launch bounded by a memory budget
@@ -1177,6 +1188,7 @@ extern "C" int smash_b200_plan_create(const SmashSetup *setup, const SmashMesh *
     std::unique_ptr<SmashPlan> pl(new SmashPlan());
     TRY(plan_build(*pl, setup, mesh, nmember, nmember > 1 ? (int)option("ensemble_engine", 0) : -1));
     pl->nmember = nmember > 0 ? nmember : 1;
+    pl->ensemble = nmember > 1;
     *plan = pl.release();
     return 0;
 }

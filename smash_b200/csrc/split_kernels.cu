@@ -874,6 +874,116 @@ __global__ void __launch_bounds__(128) route_pairs_kernel(const SplitArgs a, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// route_members: the routing pass for ensembles (compute_multiple_run: many members, one small mesh).  The members share
+// the mesh, so lane = member: a warp routes one cell for 32 members at once, every lane following the same control flow,
+// strictly sequentially in time -- the reference's arithmetic and summation order (md_routing_operator.f90:17-79,
+// md_forward_structure.f90:155), no scan.  A CTA owns a batch of 32 members; its warps claim the routed cells in path
+// order (a topological order) from a counter in shared memory and wait for the cell's routed inflows through flags in
+// shared memory, so independent branches of the river network are routed concurrently.
+// ------------------------------------------------------------------------------------------------
+template <int TAPE>
+__global__ void __launch_bounds__(512) route_members_kernel(const SplitArgs a) {
+    extern __shared__ int sm_i[];            // [0] next cell, [1 ..] done flag per routed cell
+    volatile int *done = sm_i + 1;
+    const SplitTopo &tp = a.tp;
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * 32 + lane;
+    const bool on = m < a.nmember;
+    const int mm = on ? m : a.nmember - 1;   // idle lanes shadow the last member (loads only)
+    const int T = a.T, nblk = (T + 7) / 8;
+    for (int i = threadIdx.x; i <= tp.nrouted; i += blockDim.x) sm_i[i] = 0;
+    __syncthreads();
+    const size_t mrow = (size_t)mm * tp.npad * a.Tp;
+    float *qsim = a.qsim + (size_t)mm * T * tp.ng;
+    for (;;) {
+        int idx = 0;
+        if (lane == 0) idx = atomicAdd(&sm_i[0], 1);
+        idx = __shfl_sync(FULL, idx, 0);
+        if (idx >= tp.nrouted) break;
+        const int j = tp.rlist[idx];
+        const int ub = tp.up_begin[j], nup = tp.up_begin[j + 1] - ub;
+        const float *src[8];
+#pragma unroll
+        for (int e = 0; e < 8; e++) src[e] = nullptr;
+        for (int e = 0; e < nup && e < 8; e++) {
+            const int sc = tp.up[ub + e].src;
+            const int ri = tp.rindex[sc];
+            if (ri >= 0) {
+                if (lane == 0)
+                    while (done[ri] == 0) __nanosleep(100);
+                __syncwarp();
+            }
+            src[e] = a.rows + mrow + (size_t)sc * a.Tp;
+        }
+        __threadfence();                     // rows published by other warps before their flag are read after it
+        const int fa = tp.flwacc[j];
+        const float lr = a.fields[((size_t)mm * NFIELD + F_LR) * tp.npad + j];
+        const float fa1 = (float)(fa - 1);
+        const float s_q = a.dt / (0.001f * a.dx * a.dx * fa1);                 // md_routing_operator.f90:55-56
+        const float E = expf(-a.dt / (lr * 60.0f));                           // :75
+        const float c0 = a.dx * a.dx * 0.001f / a.dt;                         // md_forward_structure.f90:155
+        float h = a.fields[((size_t)mm * NFIELD + F_HLR) * tp.npad + j];
+        float *rowj = a.rows + mrow + (size_t)j * a.Tp;
+        float *hrj = TAPE ? a.rows_hr + mrow + (size_t)j * a.Tp : nullptr;
+        const int gfirst = tp.gauge_first[j];
+        // loads run one block ahead of the arithmetic: own row and the first two inflows in registers
+        float nqt[8], nv0[8], nv1[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) { nv0[i] = 0.0f; nv1[i] = 0.0f; }
+        ld8(rowj, nqt);
+        if (nup > 0) ld8(src[0], nv0);
+        if (nup > 1) ld8(src[1], nv1);
+#pragma unroll 1
+        for (int b = 0; b < nblk; b++) {
+            const int tb = b * 8;
+            float qt[8], x[8], v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) { qt[i] = nqt[i]; x[i] = nv0[i]; v[i] = nv1[i]; }
+            if (b + 1 < nblk) {
+                ld8(rowj + tb + 8, nqt);
+                if (nup > 0) ld8(src[0] + tb + 8, nv0);
+                if (nup > 1) ld8(src[1] + tb + 8, nv1);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) x[i] = (0.0f + x[i]) + v[i];            // :37-53, neighbour order (absent inflows are 0)
+#pragma unroll
+            for (int e = 2; e < 8; e++)
+                if (e < nup) {
+                    ld8(src[e] + tb, v);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) x[i] = x[i] + v[i];
+                }
+            if ((b & 3) == 0 && b + 8 < nblk) {                                 // next lines of the rows: DRAM -> L2 ahead of use
+                prefetch_l2(rowj + tb + 64);
+#pragma unroll
+                for (int e = 0; e < 8; e++)
+                    if (e < nup) prefetch_l2(src[e] + tb + 64);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float hr = h + x[i] * s_q;                                // :55-56, :73
+                const float hn = hr * E;                                        // :75
+                qt[i] = fmaf(hr - hn, fa1, qt[i]) * c0;                         // :77, md_forward_structure.f90:155
+                x[i] = hr;
+                if (tb + i < T) h = hn;
+            }
+            if (on) {
+                st8(rowj + tb, qt);
+                if (TAPE) st8(hrj + tb, x);
+                if (gfirst >= 0)
+                    for (int g = gfirst; g >= 0; g = tp.gauge_next[g])
+#pragma unroll
+                        for (int i = 0; i < 8; i++)
+                            if (tb + i < T) qsim[(size_t)(tb + i) * tp.ng + g] = qt[i];     // :206-210
+            }
+        }
+        if (on) a.fstates[((size_t)m * 3 + 2) * tp.npad + j] = h;
+        __syncwarp();
+        if (lane == 0) { __threadfence(); done[idx] = 1; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // rows_to_domain: q rows of the routed cells -> qsim_domain layout [t][cell]
 // ------------------------------------------------------------------------------------------------
 constexpr int RD_T = 128;   // time steps per tile
@@ -1324,6 +1434,18 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
         }
     }
     return cudaSuccess;
+}
+
+cudaError_t launch_route_members(const SplitArgs &a, bool tape, cudaStream_t s) {
+    if (a.tp.nrouted == 0) return cudaSuccess;
+    const size_t smem = sizeof(int) * (size_t)(a.tp.nrouted + 1);
+    const unsigned grid = (unsigned)((a.nmember + 31) / 32);
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) return cudaErrorInvalidValue;
+    if (tape) route_members_kernel<1><<<grid, 512, smem, s>>>(a);
+    else route_members_kernel<0><<<grid, 512, smem, s>>>(a);
+    e = cudaGetLastError();
+    return e;
 }
 
 cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s) {

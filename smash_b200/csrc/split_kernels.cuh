@@ -33,6 +33,9 @@ struct SplitTopo {
     const int32_t *task_begin, *task_cells;
     const int4 *tcell;           // TaskCell records, parallel to task_cells
     const int2 *tup;             // RouteUp entries of the task cells
+    int nrouted;                 // cells with flwacc > 1
+    const int32_t *rlist;        // [nrouted] routed cells in path order (a topological order)
+    const int32_t *rindex;       // [npad] position in rlist or -1
     const int32_t *gauge_first;  // [npad]
     const int32_t *gauge_next;   // [ng]
 };
@@ -70,7 +73,9 @@ int make_tensor_map_2d(CUtensorMap *tm, const float *base, uint64_t cols, uint64
 
 cudaError_t launch_vertical_forward(const SplitArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, int math_mode, bool tape,
                                     cudaStream_t s);
-cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s);     // all windows
+cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s);
+// ensembles on small meshes without pit pairs: lane = member, strictly sequential arithmetic (nrouted <= 12000)
+cudaError_t launch_route_members(const SplitArgs &a, bool tape, cudaStream_t s);     // all windows
 cudaError_t launch_rows_to_domain(const SplitArgs &a, cudaStream_t s);
 cudaError_t launch_route_adjoint(const SplitArgs &a, cudaStream_t s);                // all windows, reverse order
 cudaError_t launch_vertical_adjoint(const SplitArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, const CUtensorMap &hp,

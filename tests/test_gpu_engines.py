@@ -108,3 +108,29 @@ def test_france_full_size_engines_and_routing_properties():
     assert np.isfinite([split, fused, fast]).all() and split > 0
     assert abs(split - fused) <= 2e-6 * fused, (split, fused)
     assert fast > split
+
+
+def test_multiple_run_on_split_engine_lane_per_member(golden):
+    # option ensemble_engine = 1: reservoir pass + routing with lane = member (route_members_kernel), against the
+    # reference's golden ensemble (smash/tests/baseline.hdf5 multiple_run.*, atol 1e-4 as in test_simu.py:53) and against
+    # the default (fused) ensemble path
+    lib = L.lib()
+    m = cases.cance()
+    rng = np.random.RandomState(99)
+    ns = 10
+    smp = np.asfortranarray(np.stack([rng.uniform(lo, hi, ns) for lo, hi in [(1e-6, 1e3), (1e-6, 1e3), (-50, 50), (1e-6, 1e3)]]).astype(np.float32))
+    res = {}
+    for eng in (0, 1):
+        lib.smash_b200_set_option(b"ensemble_engine", eng)
+        try:
+            cost = np.zeros(ns, np.float32)
+            qsim = np.zeros((3, m.setup._ntime_step, ns), np.float32, order="F")
+            smash_b200.compute_multiple_run(m.setup, m.mesh, m.input_data, m.parameters, m.states, m.output, smp,
+                                            cases.IND_CP_CFT_EXC_LR, cost, qsim)
+            res[eng] = (cost, qsim)
+        finally:
+            lib.smash_b200_set_option(b"ensemble_engine", 0)
+            lib.smash_b200_clear_cache()
+    assert np.allclose(res[1][1], golden["multiple_run.qsim"], atol=1e-4)
+    assert np.allclose(res[1][0], golden["multiple_run.cost"], atol=1e-4, rtol=1e-5)
+    assert np.allclose(res[1][1], res[0][1], rtol=2e-3, atol=1e-4)
