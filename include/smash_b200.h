@@ -161,7 +161,8 @@ void smash_b200_clear_cache(void);           /* drop cached mesh plans and devic
  * reference's own float32 arithmetic), 0 = IEEE division / sqrt + libm tanhf in the reference's
  * statement order; "block" = cells per CTA (0 = automatic);
  * "member_budget_mb" = device memory per ensemble launch; "engine" 1 = split engine (reservoir pass per cell + routing
- * scan per chain, default with math = 1), 0 = fused tick wavefront; "pin_host" 1 = page-lock large caller-owned host
+ * scan per chain, default with math = 1), 0 = fused tick wavefront; "ensemble_engine" the same choice for
+ * compute_multiple_run (split engine: routing with lane = member); "pin_host" 1 = page-lock large caller-owned host
  * arrays in place on first use (PCIe-speed copies) -- the caller must then call smash_b200_clear_cache() before freeing
  * them; off by default. */
 int smash_b200_set_option(const char *name, long long value);

@@ -1106,7 +1106,7 @@ extern "C" int smash_b200_compute_multiple_run(const SmashSetup *setup, const Sm
     for (int j = 0; j < nvar; j++)
         if (ind[j] < 1 || ind[j] > SMASH_B200_GNP + SMASH_B200_GNS) return fail(SMASH_B200_EINVAL, "ind_parameters_states[%d] = %d out of range", j, ind[j]);
     SmashPlan *pl;
-    TRY(get_plan(setup, mesh, &pl, (int)option("ensemble_engine", 0)));
+    TRY(get_plan(setup, mesh, &pl, (int)option("ensemble_engine", -1)));
     pl->ensemble = true;
     pl->launches = 0;
     const Topology &tp = pl->tp;
@@ -1186,7 +1186,7 @@ extern "C" int smash_b200_plan_create(const SmashSetup *setup, const SmashMesh *
     if (!plan) return fail(SMASH_B200_EINVAL, "plan is NULL");
     TRY(check_device());
     std::unique_ptr<SmashPlan> pl(new SmashPlan());
-    TRY(plan_build(*pl, setup, mesh, nmember, nmember > 1 ? (int)option("ensemble_engine", 0) : -1));
+    TRY(plan_build(*pl, setup, mesh, nmember, nmember > 1 ? (int)option("ensemble_engine", -1) : -1));
     pl->nmember = nmember > 0 ? nmember : 1;
     pl->ensemble = nmember > 1;
     *plan = pl.release();

@@ -111,9 +111,9 @@ def test_france_full_size_engines_and_routing_properties():
 
 
 def test_multiple_run_on_split_engine_lane_per_member(golden):
-    # option ensemble_engine = 1: reservoir pass + routing with lane = member (route_members_kernel), against the
-    # reference's golden ensemble (smash/tests/baseline.hdf5 multiple_run.*, atol 1e-4 as in test_simu.py:53) and against
-    # the default (fused) ensemble path
+    # ensembles run on the split engine by default (ensemble_engine = -1 -> 1 with math = 1): reservoir pass + routing
+    # with lane = member (route_members_kernel); checked against the reference's golden ensemble (smash/tests/baseline.hdf5
+    # multiple_run.*, atol 1e-4 as in test_simu.py:53) and against the fused engine (ensemble_engine = 0)
     lib = L.lib()
     m = cases.cance()
     rng = np.random.RandomState(99)
@@ -129,7 +129,7 @@ def test_multiple_run_on_split_engine_lane_per_member(golden):
                                             cases.IND_CP_CFT_EXC_LR, cost, qsim)
             res[eng] = (cost, qsim)
         finally:
-            lib.smash_b200_set_option(b"ensemble_engine", 0)
+            lib.smash_b200_set_option(b"ensemble_engine", -1)
             lib.smash_b200_clear_cache()
     assert np.allclose(res[1][1], golden["multiple_run.qsim"], atol=1e-4)
     assert np.allclose(res[1][0], golden["multiple_run.cost"], atol=1e-4, rtol=1e-5)
