@@ -149,10 +149,18 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
             g.max_chain = std::max(g.max_chain, (int)chains[ci].size());
         }
     }
+    // Task order: by the topological level of the chain's last cell (level = cells on the longest path from a source to the
+    // cell).  A chain's tributaries end at a lower level than the cell they join, so this is a dependency order, and it is
+    // the order in which the serial walks down the rivers need their tributaries: what joins the upper reaches comes first.
+    std::vector<int32_t> level(n, 1);
+    for (int j = 0; j < n; j++)
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++)
+            if (g.up[e].src < j) level[j] = std::max(level[j], level[g.up[e].src] + 1);
     std::vector<int32_t> torder(nch);
     std::iota(torder.begin(), torder.end(), 0);
     std::stable_sort(torder.begin(), torder.end(), [&](int a, int b) {
-        if (height[a] != height[b]) return height[a] < height[b];
+        const int la = level[chains[a].back()], lb = level[chains[b].back()];
+        if (la != lb) return la < lb;
         return chains[a].size() > chains[b].size();
     });
     // the longest chains get warps of their own in the forward routing pass: they are moved to the end of the chain tasks
