@@ -1,0 +1,134 @@
+"""Host-side optimiser drivers (smash_b200/solver/_mw_optimize.py, smash_b200/simulation.py) against the reference's
+golden ``optimize.*`` values of smash/tests/baseline.hdf5 (generic_optimize, smash/tests/core/test_simu.py:77-189).
+
+CPU tests drive the drivers with the oracle as the solver (tests/oracle_solver.py): they pin the *driver logic*
+(control vector layout, transformations, L-BFGS-B settings, stopping rules, auto-wjreg) to the golden file.  The GPU
+tests run the same cases through libsmash_b200.so.  Tolerance: the reference compares at atol = 1e-6 with its own
+Fortran arithmetic; the float32 oracle under these drivers reproduces the costs to <= 1.8e-6 and the optimised
+maps to ~1e-3 relative (the line search amplifies last-place differences), which is what is asserted here."""
+import numpy as np
+import pytest
+
+import cases
+import oracle
+import oracle_solver
+from smash_b200 import simulation
+
+COST_ATOL = 5e-6      # CPU: driver logic on the float32 oracle (measured <= 1.8e-6)
+COST_ATOL_GPU = 2e-4  # GPU: device arithmetic differs from the oracle in the last places
+
+CASES = {
+    "optimize.uniform_sbs.cost": dict(mapping="uniform", algorithm="sbs", options={"maxiter": 1}),
+    "optimize.distributed_l-bfgs-b.cost": dict(mapping="distributed", algorithm="l-bfgs-b", options={"maxiter": 1}),
+    "optimize.hyper-linear_l-bfgs-b.cost": dict(mapping="hyper-linear", algorithm="l-bfgs-b", options={"maxiter": 1}),
+    "optimize.hyper-polynomial_l-bfgs-b.cost": dict(mapping="hyper-polynomial", algorithm="l-bfgs-b",
+                                                    options={"maxiter": 1}),
+    "optimize.uniform_sbs_mtg.cost": dict(gauge="all", wgauge="median", options={"maxiter": 1}),
+    "optimize.distributed_l-bfgs-b_reg_fast.cost": dict(
+        mapping="distributed", control_vector=["cp", "cft", "lr"],
+        options={"maxiter": 2, "jreg_fun": ["prior", "smoothing"], "wjreg_fun": [1.0, 2.0], "auto_wjreg": "fast"}),
+    "optimize.distributed_l-bfgs-b_reg_lcurve.cost": dict(
+        mapping="distributed", control_vector=["cp", "cft", "lr"],
+        options={"maxiter": 2, "jreg_fun": ["prior", "smoothing"], "wjreg_fun": [1.0, 2.0], "auto_wjreg": "lcurve",
+                 "nb_wjreg_lcurve": 8}),
+}
+
+
+def _cost(inst):
+    return cases.output_cost(inst, oracle.nse, oracle.kge)
+
+
+def _check_case(key, golden, solver):
+    inst = simulation.optimize(cases.cance(), solver=solver, **CASES[key])
+    got, want = _cost(inst), golden[key]
+    atol = COST_ATOL if solver is not None else COST_ATOL_GPU
+    print(key, "max |cost - golden| =", np.abs(got - want).max())
+    assert np.allclose(got, want, atol=atol), (key, got, want)
+    return inst
+
+
+@pytest.mark.parametrize("key", list(CASES))
+def test_optimize_golden_cpu(key, golden):
+    _check_case(key, golden, oracle_solver)
+
+
+def test_optimize_states_and_bounds_cpu(golden):
+    # states in the control vector (test_simu.py:119-128)
+    m = cases.cance()
+    m.states.hlr[...] = 1.0
+    inst = simulation.optimize(m, control_vector=["cp", "hlr"], options={"maxiter": 1}, solver=oracle_solver)
+    assert np.allclose(_cost(inst), golden["optimize.uniform_sbs_states.cost"], atol=COST_ATOL)
+    assert np.allclose(inst.states.hlr, golden["optimize.uniform_sbs_states.hlr"], rtol=1e-5)
+    # user bounds (test_simu.py:131-142)
+    inst = simulation.optimize(cases.cance(), mapping="distributed", algorithm="l-bfgs-b", control_vector=["cp", "cft"],
+                               bounds={"cp": [1, 300]}, options={"maxiter": 1}, solver=oracle_solver)
+    assert np.allclose(_cost(inst), golden["optimize.distributed_l-bfgs-b_bounds.cost"], atol=COST_ATOL)
+    assert np.allclose(inst.parameters.cp, golden["optimize.distributed_l-bfgs-b_bounds.cp"], rtol=2e-3)
+    assert np.allclose(inst.parameters.cft, golden["optimize.distributed_l-bfgs-b_bounds.cft"], rtol=2e-3)
+
+
+def test_sbs_leaves_other_fields_alone_cpu():
+    # test_simu.py:196-211: a distributed prior of a field that is not optimised survives optimize_sbs
+    m = cases.cance(T=240)
+    m.parameters.cft = np.asfortranarray(np.random.default_rng(0).random(m.parameters.cft.shape, dtype=np.float32) + 500)
+    inst = simulation.optimize(m, control_vector="cp", options={"maxiter": 1}, solver=oracle_solver)
+    assert np.array_equal(m.parameters.cft, inst.parameters.cft)
+    assert not np.array_equal(m.parameters.cp, inst.parameters.cp)
+
+
+def test_multiple_run_equals_forward_cpu():
+    # test_simu.py:55-74: multiple_run of one member = optimize with maxiter 0 on the same uniform parameters
+    m = cases.cance(T=240)
+    smp = cases.golden("cance_golden.npz")["samples.cp_cft_exc_lr"].T[:2]
+    cost, qsim = simulation.multiple_run(m, smp, ["cp", "cft", "exc", "lr"], return_qsim=True, solver=oracle_solver)
+    for k in range(2):
+        inst = m.copy()
+        for name, v in zip(["cp", "cft", "exc", "lr"], smp[k]):
+            getattr(inst.parameters, name)[...] = v
+        inst = simulation.optimize(inst, options={"maxiter": 0}, solver=oracle_solver)
+        assert np.allclose(inst.output.cost, cost[k], atol=1e-4)
+        assert np.allclose(inst.output.qsim, qsim[..., k], atol=1e-4)
+
+
+def test_argument_errors():
+    m = cases.cance(T=24)
+    with pytest.raises(ValueError):
+        simulation.optimize(m, mapping="nope", solver=oracle_solver)
+    with pytest.raises(ValueError):
+        simulation.optimize(m, mapping="distributed", jobs_fun="kge", solver=oracle_solver)
+    with pytest.raises(ValueError):
+        simulation.optimize(m, control_vector=["cst"], solver=oracle_solver)
+    with pytest.raises(ValueError):
+        simulation.optimize(m, bounds={"cp": [300, 1]}, solver=oracle_solver)
+    with pytest.raises(KeyError):
+        simulation.optimize(m, options={"maxiter": 1, "bogus": 2}, solver=oracle_solver)
+
+
+# ------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("key", list(CASES))
+def test_optimize_golden_gpu(key, golden):
+    _check_case(key, golden, None)
+
+
+@pytest.mark.gpu
+def test_optimize_bounds_maps_gpu(golden):
+    inst = simulation.optimize(cases.cance(), mapping="distributed", algorithm="l-bfgs-b", control_vector=["cp", "cft"],
+                               bounds={"cp": [1, 300]}, options={"maxiter": 1})
+    assert np.allclose(_cost(inst), golden["optimize.distributed_l-bfgs-b_bounds.cost"], atol=COST_ATOL_GPU)
+    assert np.allclose(inst.parameters.cp, golden["optimize.distributed_l-bfgs-b_bounds.cp"], rtol=2e-3)
+    assert np.allclose(inst.parameters.cft, golden["optimize.distributed_l-bfgs-b_bounds.cft"], rtol=2e-3)
+
+
+@pytest.mark.gpu
+def test_vda_converges_gpu():
+    """BASELINE.json configs[1]: distributed-mapping variational calibration on Cance driven by the adjoint
+    gradient.  30 L-BFGS-B iterations must take 1 - NSE well below the uniform first guess, and the GPU-driven
+    optimisation must follow the oracle-driven one (same driver, same settings)."""
+    g = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": 30})
+    first = simulation.run(cases.cance())
+    j0 = 1.0 - oracle.nse(first.input_data.qobs[0], first.output.qsim[0])
+    assert g.output.cost < 0.5 * j0
+    c = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": 5})
+    r = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": 5}, solver=oracle_solver)
+    assert abs(float(c.output.cost) - float(r.output.cost)) < 5e-3
