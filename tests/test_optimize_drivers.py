@@ -15,7 +15,7 @@ import oracle_solver
 from smash_b200 import simulation
 
 COST_ATOL = 5e-6      # CPU: driver logic on the float32 oracle (measured <= 1.8e-6)
-COST_ATOL_GPU = 2e-4  # GPU: device arithmetic differs from the oracle in the last places
+COST_ATOL_GPU = 2e-5  # GPU: device arithmetic differs from the oracle in the last places (measured <= 6.9e-6 on B200)
 
 CASES = {
     "optimize.uniform_sbs.cost": dict(mapping="uniform", algorithm="sbs", options={"maxiter": 1}),
@@ -127,7 +127,7 @@ def test_vda_converges_gpu():
     optimisation must follow the oracle-driven one (same driver, same settings)."""
     g = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": 30})
     first = simulation.run(cases.cance())
-    j0 = 1.0 - oracle.nse(first.input_data.qobs[0], first.output.qsim[0])
+    j0 = float(first.output.cost)                       # 1 - NSE at the downstream gauge, uniform first guess
     assert g.output.cost < 0.5 * j0
     c = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": 5})
     r = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": 5}, solver=oracle_solver)
