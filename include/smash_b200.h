@@ -164,7 +164,9 @@ void smash_b200_clear_cache(void);           /* drop cached mesh plans and devic
  * scan per chain, default with math = 1), 0 = fused tick wavefront; "ensemble_engine" the same choice for
  * compute_multiple_run (split engine: routing with lane = member); "pin_host" 1 = page-lock large caller-owned host
  * arrays in place on first use (PCIe-speed copies) -- the caller must then call smash_b200_clear_cache() before freeing
- * them; off by default. */
+ * them; off by default; "river_wave" 1 = the longest chains are cut into reaches of at most 128 cells, one CTA per reach,
+ * routed as pipelined tick wavefronts (thread = cell, strictly sequential arithmetic) instead of a window scan per cell
+ * (experimental: slower than the default on the France mesh). */
 int smash_b200_set_option(const char *name, long long value);
 
 /* ---- device-resident plan API (bench / advanced callers) --------------------------------------

@@ -278,7 +278,8 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     RouteGraph &rg = sp.rg;
     std::string err = build_route_graph(rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
                                         mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
-                                        (int)option("route_ded_max", 64));
+                                        (int)option("route_ded_max", option("river_wave", 0) ? 224 : 64),
+                                        option("river_wave", 0) ? 128 : 0);
     if (!err.empty()) {
         *unsupported = err.rfind("unsupported", 0) == 0;
         return fail(SMASH_B200_EINVAL, "%s", err.c_str());
@@ -362,7 +363,7 @@ static int split_members(SmashPlan &pl, int nmember, bool save_q, bool save_netp
     const size_t nrows = nm * npad * sp.Tp;
     if (sp.d_rows.n < nrows) { TRY(sp.d_rows.ensure(nrows)); CU(cudaMemsetAsync(sp.d_rows.p, 0, nrows * sizeof(float), pl.stream)); }
     TRY(sp.d_hcar.ensure(nm * npad));
-    TRY(sp.d_done.ensure(std::max<size_t>(1, nm * sp.rg.ntask)));
+    TRY(sp.d_done.ensure(std::max<size_t>(1, 2 * nm * sp.rg.ntask)));   // done flags + block counters of the river reaches
     if (save_q || gradient) TRY(pl.d_qdom.ensure(nm * tp.T * sp.qpitch));
     if (save_netp) TRY(pl.d_netp.ensure(nm * tp.T * sp.qpitch));
     if (gradient) {
@@ -391,28 +392,32 @@ static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp) {
     a.tp = sp.topo; a.T = pl.tp.T; a.Tp = sp.Tp; a.W = sp.W; a.nwin = sp.nwin; a.nmember = pl.nmember; a.dt = pl.dt; a.dx = pl.dx;
     a.first_routed = sp.rg.first_routed;
     a.dbg_prof = nullptr;
-    if (option("dbg_prof", 0) && sp.rg.nded > 0) {
+    if (option("dbg_prof", 0) && sp.rg.nded > 0 && sp.rg.nded <= 256) {
+        // per dedicated chain / reach: [0] cells [1] cycles [2] cycles blocked on whole-series tributaries (sum over threads)
+        // [3] end time ns [4] cycles blocked on streamed blocks (sum over threads) [5] ticks
         static unsigned long long *dp = nullptr;
-        const size_t nb = 4 * (size_t)sp.rg.nded * sizeof(unsigned long long);
-        if (!dp) { cudaMalloc(&dp, 4 * 256 * sizeof(unsigned long long)); cudaMemset(dp, 0, 4 * 256 * sizeof(unsigned long long)); }
-        std::vector<unsigned long long> hv(4 * (size_t)sp.rg.nded);
+        const size_t nb = 8 * (size_t)sp.rg.nded * sizeof(unsigned long long);
+        if (!dp) { cudaMalloc(&dp, 8 * 256 * sizeof(unsigned long long)); cudaMemset(dp, 0, 8 * 256 * sizeof(unsigned long long)); }
+        std::vector<unsigned long long> hv(8 * (size_t)sp.rg.nded);
         cudaMemcpy(hv.data(), dp, nb, cudaMemcpyDeviceToHost);
-        unsigned long long tmax = 0;
-        for (int i = 0; i < sp.rg.nded; i++) tmax = std::max(tmax, hv[4 * i + 3]);
+        unsigned long long tmax = 0, tmin = ~0ull;
+        for (int i = 0; i < sp.rg.nded; i++) { tmax = std::max(tmax, hv[8 * i + 3]); if (hv[8 * i + 3]) tmin = std::min(tmin, hv[8 * i + 3]); }
         if (tmax) {
             std::vector<int> idx(sp.rg.nded);
             for (int i = 0; i < sp.rg.nded; i++) idx[i] = i;
-            std::sort(idx.begin(), idx.end(), [&](int x, int y) { return hv[4 * x + 3] > hv[4 * y + 3]; });
-            for (int k = 0; k < 6 && k < sp.rg.nded; k++) {
-                const int i = idx[k];
-                fprintf(stderr, "[dbg_prof] chain %d: %llu cells, %.0f cycles/cell, waiting %.0f %%, ended %.3f ms before the last\n", i,
-                        hv[4 * i], (double)hv[4 * i + 1] / std::max(1ull, hv[4 * i]), 100.0 * hv[4 * i + 2] / std::max(1ull, hv[4 * i + 1]),
-                        (tmax - hv[4 * i + 3]) * 1e-6);
+            std::sort(idx.begin(), idx.end(), [&](int x, int y) { return hv[8 * x + 3] > hv[8 * y + 3]; });
+            fprintf(stderr, "[dbg_prof] %d dedicated tasks, first ended %.3f ms before the last\n", sp.rg.nded, (tmax - tmin) * 1e-6);
+            for (int kk = 0; kk < 16 && kk < sp.rg.nded; kk++) {
+                const int k = kk < 8 ? kk : sp.rg.nded - 1 - (kk - 8);       // the eight last and the eight first to end
+                const unsigned long long *h = &hv[8 * (size_t)idx[k]];
+                fprintf(stderr, "[dbg_prof] task %d: %llu cells, %llu cycles, %llu ticks, blocked on tributaries %llu (thread-cycles), on streamed "
+                        "blocks %llu, ended %.3f ms before the last\n", idx[k], h[0], h[1], h[5], h[2], h[4], (tmax - h[3]) * 1e-6);
             }
         }
         a.dbg_prof = dp;
     }
     a.save_q = save_q ? 1 : 0; a.save_netp = save_netp ? 1 : 0;
+    a.river_wave = (int)option("river_wave", 0);
     a.fields = pl.d_fields.p; a.fstates = pl.d_fstates.p; a.rows = sp.d_rows.p; a.qdom = pl.d_qdom.p; a.netp = pl.d_netp.p;
     a.qpitch = sp.qpitch; a.qsim = pl.d_qsim.p; a.tape_hp = sp.d_tape_hp.p; a.tape_hft = sp.d_tape_hft.p; a.rows_hr = sp.d_rows_hr.p;
     a.hcar = sp.d_hcar.p; a.done = sp.d_done.p; a.ticket = pl.d_ticket.p; a.qsim_b = pl.d_qsim_b.p; a.rows_w = sp.d_rows_w.p;

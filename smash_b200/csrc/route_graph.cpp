@@ -13,7 +13,7 @@ static const int RG_DROW[8] = {1, 1, 0, -1, -1, -1, 0, 1};
 
 std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const int32_t *flwdir, const int32_t *flwacc,
                               const int32_t *active_cell, const int32_t *local_active_cell, const int32_t *path,
-                              const int32_t *gauge_pos, int ded_min, int ded_max) {
+                              const int32_t *gauge_pos, int ded_min, int ded_max, int reach) {
     const int ncell = nrow * ncol;
     if (nrow <= 0 || ncol <= 0) return "mesh: nrow and ncol must be positive";
     g = RouteGraph();
@@ -118,6 +118,43 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
         if (chain_of[j] < 0 && partner[j] < 0 && (heavy[j] >= 0 || g.flwacc[j] > 1))
             return "mesh: flow directions contain a cycle longer than two cells";
 
+    // ---- river reaches (reach > 0): the longest chains, as many as ded_max dedicated CTAs can take, are cut into reaches
+    // of at most `reach` cells.  A reach is a chain of its own whose head gathers the tail of the previous reach like any
+    // tributary; the forward routing pass runs the reaches as a pipeline (tick wavefront, split_kernels.cu).
+    std::vector<uint8_t> ded_reach;
+    if (reach > 0) {
+        std::vector<int32_t> byl(chains.size());
+        std::iota(byl.begin(), byl.end(), 0);
+        std::stable_sort(byl.begin(), byl.end(), [&](int a, int b) { return chains[a].size() > chains[b].size(); });
+        ded_reach.assign(chains.size(), 0);
+        int used = 0;
+        for (int ci : byl) {
+            const int sz = (int)chains[ci].size();
+            if (sz < ded_min) break;
+            const int nseg = (sz + reach - 1) / reach;
+            if (used + nseg > ded_max) break;
+            used += nseg;
+            ded_reach[ci] = 1;
+            if (nseg == 1) continue;
+            const std::vector<int32_t> whole = chains[ci];
+            const int base = sz / nseg, rem = sz % nseg;
+            int at = base + (rem > 0 ? 1 : 0);
+            chains[ci].assign(whole.begin(), whole.begin() + at);
+            for (int k = 1; k < nseg; k++) {
+                const int len = base + (k < rem ? 1 : 0);
+                const int c0 = whole[at], prev = whole[at - 1];
+                for (int e = g.up_begin[c0]; e < g.up_begin[c0 + 1]; e++)
+                    if (g.up[e].src == prev) g.up[e].task = UP_NOWAIT;       // no longer the chain predecessor
+                heavy[c0] = -1; next[prev] = -1;
+                std::vector<int32_t> part(whole.begin() + at, whole.begin() + at + len);
+                for (int c : part) chain_of[c] = (int32_t)chains.size();
+                chains.push_back(std::move(part));
+                ded_reach.push_back(1);
+                at += len;
+            }
+        }
+    }
+
     // ---- dependency height of every chain (laterals are tails of other chains); processed in order of the tail's
     // position in path, which is a topological order for non-lagged edges (producer earlier in path than consumer)
     const int nch = (int)chains.size();
@@ -169,7 +206,10 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
         std::vector<int32_t> byl(torder);
         std::stable_sort(byl.begin(), byl.end(), [&](int a, int b) { return chains[a].size() > chains[b].size(); });
         std::vector<uint8_t> ded(nch, 0);
-        for (int i = 0; i < nch && i < DED_MAX && (int)chains[byl[i]].size() >= DED_MIN; i++) { ded[byl[i]] = 1; g.nded++; }
+        if (reach > 0) {
+            for (int c = 0; c < nch; c++) if (ded_reach[c]) { ded[c] = 1; g.nded++; }
+        } else
+            for (int i = 0; i < nch && i < DED_MAX && (int)chains[byl[i]].size() >= DED_MIN; i++) { ded[byl[i]] = 1; g.nded++; }
         std::stable_partition(torder.begin(), torder.end(), [&](int c) { return !ded[c]; });
     }
     std::vector<int32_t> task_of_chain(nch);

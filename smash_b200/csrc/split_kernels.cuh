@@ -47,6 +47,7 @@ struct SplitArgs {
     int nmember;
     float dt, dx;
     int save_q, save_netp;
+    int river_wave;              // 1: dedicated chains run the tick wavefront (thread = cells), 0: whole-window scan per cell
     unsigned long long *dbg_prof;  // diagnostics: per dedicated chain [cells, cycles, cycles waiting for tributaries, end time ns], or nullptr
     const float *fields;         // [m][NFIELD][npad]
     float *fstates;              // [m][3][npad]
