@@ -263,9 +263,11 @@ def main():
     # the forcing / output arrays live until clear_cache() below: let the library page-lock them in place (opt-in option)
     lib.smash_b200_set_option(b"pin_host", 1)
 
+    par_bgd, sta_bgd = model.parameters.copy(), model.states.copy()     # the background never changes between calls
+
     def e2e_step():
-        smash_b200.forward(model.setup, model.mesh, model.input_data, model.parameters, model.parameters.copy(),
-                           model.states, model.states.copy(), model.output)
+        smash_b200.forward(model.setup, model.mesh, model.input_data, model.parameters, par_bgd, model.states, sta_bgd,
+                           model.output)
 
     e2e_step()
     barrier()
@@ -278,7 +280,8 @@ def main():
     d2h = nac * T * 4 + 3 * int(info[1]) * int(info[2]) * 4 + 4
     e2e = {"value": world * units * e2e_steps / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
-           "host_buffers": "caller's NumPy arrays, page-locked in place by the library (option pin_host=1) during the untimed first call"}
+           "host_buffers": "caller's NumPy arrays, page-locked in place by the library (option pin_host=1) during the untimed first call",
+           "streamed": "256-step windows: upload, kernels and download overlap on three streams"}
     lib.smash_b200_clear_cache()
     lib.smash_b200_set_option(b"pin_host", 0)
 
@@ -372,6 +375,23 @@ def cance_extras(lib, L, smash_b200, oracle, cases):
     out["cance_ensemble_4096"] = {"cell_timesteps_per_s_e2e": ns * cs / dte, "ms_per_call": dte * 1e3,
                                   "cpu_port_cell_timesteps_per_s": nso * cs / dtoe, "cpu_cores": nthreads,
                                   "cpu_sample": f"{nso} members, OpenMP over members"}
+    # configs[1]: distributed-mapping variational calibration, L-BFGS-B driven by the adjoint gradient (mw_optimize.f90:484-676)
+    from smash_b200 import simulation
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_solver                                  # the CPU port behind the solver signatures (checker / baseline only)
+    iters = 20
+    simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": 2})            # warm-up (plan, forcing)
+    t0 = time.perf_counter()
+    g = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": iters})
+    tg = time.perf_counter() - t0
+    it_cpu = 3
+    t0 = time.perf_counter()
+    c = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": it_cpu}, solver=oracle_solver)
+    tc = time.perf_counter() - t0
+    c_same = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": it_cpu})
+    out["cance_vda_lbfgsb"] = {"iterations": iters, "wall_s": tg, "s_per_iteration": tg / iters, "final_cost": float(g.output.cost),
+                               "cpu_port_s_per_iteration": tc / it_cpu, "cpu_port_iterations": it_cpu, "cpu_cores": 1,
+                               "cost_after_cpu_port_iterations": {"b200": float(c_same.output.cost), "cpu_port": float(c.output.cost)}}
     return out
 
 

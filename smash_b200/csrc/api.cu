@@ -143,6 +143,11 @@ struct SmashPlan {
     float dt = 0, dx = 0;
     int ncell = 0;
     cudaStream_t stream = nullptr;
+    // streamed forward runs (large host-resident forcing): 256-step windows, forcing in / domain series out on streams of
+    // their own so that the two PCIe directions and the kernels overlap
+    bool small_windows = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in, ev_cmp;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaEvent_t evk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // per-kernel marks
     int kmark[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 1: evk[i] was recorded in the last run
@@ -172,6 +177,10 @@ struct SmashPlan {
         if (ev1) cudaEventDestroy(ev1);
         if (ev2) cudaEventDestroy(ev2);
         for (auto &e : evk) if (e) cudaEventDestroy(e);
+        for (auto &e : ev_in) if (e) cudaEventDestroy(e);
+        for (auto &e : ev_cmp) if (e) cudaEventDestroy(e);
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -293,7 +302,7 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     tp.sparse_k.assign(rg.npad, -1);
     for (int j = 0; j < rg.n; j++) tp.sparse_k[j] = rg.sparse_k[j];
     tp.gauge_slot = rg.gauge_cell;
-    sp.W = split_pick_window(tp.T, &sp.S, &sp.nwin);
+    sp.W = split_pick_window(tp.T, &sp.S, &sp.nwin, pl.small_windows);
     sp.Tp = sp.W * sp.nwin;
     CU(cudaStreamCreateWithFlags(&pl.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&pl.ev0)); CU(cudaEventCreate(&pl.ev1)); CU(cudaEventCreate(&pl.ev2));
@@ -391,6 +400,7 @@ static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp) {
     SplitArgs a{};
     a.tp = sp.topo; a.T = pl.tp.T; a.Tp = sp.Tp; a.W = sp.W; a.nwin = sp.nwin; a.nmember = pl.nmember; a.dt = pl.dt; a.dx = pl.dx;
     a.first_routed = sp.rg.first_routed;
+    a.t_begin = 0; a.t_end = pl.tp.T;
     a.dbg_prof = nullptr;
     if (option("dbg_prof", 0) && sp.rg.nded > 0 && sp.rg.nded <= 256) {
         // per dedicated chain / reach: [0] cells [1] cycles [2] cycles blocked on whole-series tributaries (sum over threads)
@@ -497,7 +507,8 @@ static SolverArgs solver_args(SmashPlan &pl, bool save_q, bool save_netp, bool t
 }
 
 // ---- forcing ------------------------------------------------------------------------------------
-static int plan_set_forcing(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in) {
+static int plan_set_forcing(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, bool upload = true,
+                            bool *fresh = nullptr) {
     if (!in) return fail(SMASH_B200_EINVAL, "input_data is NULL");
     const Topology &tp = pl.tp;
     const bool sparse = setup->sparse_storage != 0;
@@ -505,15 +516,20 @@ static int plan_set_forcing(SmashPlan &pl, const SmashSetup *setup, const SmashM
     const float *pet = sparse ? in->sparse_pet : in->pet;
     if (!prcp || !pet) return fail(SMASH_B200_EINVAL, "input_data.%sprcp / pet is NULL", sparse ? "sparse_" : "");
     if (pl.have_forcing && in->forcing_version != 0 && pl.forcing_version == in->forcing_version && pl.forcing_ptr == prcp &&
-        pl.forcing_sparse == (int)sparse)
+        pl.forcing_sparse == (int)sparse) {
+        if (fresh) *fresh = false;
         return 0;
+    }
+    if (fresh) *fresh = true;
     const int64_t stride = sparse ? mesh->nac : (int64_t)mesh->nrow * mesh->ncol;
     const size_t nraw = (size_t)stride * tp.T;
     TRY(pl.d_raw_prcp.ensure(nraw)); TRY(pl.d_raw_pet.ensure(nraw));
     if (pl.engine == 0) TRY(pl.d_forcing.ensure((size_t)tp.total_ticks * 2 * tp.B));
     pin_host(prcp, nraw * sizeof(float)); pin_host(pet, nraw * sizeof(float));
-    CU(cudaMemcpyAsync(pl.d_raw_prcp.p, prcp, nraw * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
-    CU(cudaMemcpyAsync(pl.d_raw_pet.p, pet, nraw * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+    if (upload) {
+        CU(cudaMemcpyAsync(pl.d_raw_prcp.p, prcp, nraw * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+        CU(cudaMemcpyAsync(pl.d_raw_pet.p, pet, nraw * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+    }
     if (pl.engine == 1) {
         // the reservoir pass reads [t][cell j] tiles by TMA: sparse arrays whose order is already j are used in place
         SplitState &sp = pl.sp;
@@ -787,12 +803,18 @@ static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **
                                  mesh->local_active_cell, mesh->path, mesh->gauge_pos);
     int dev = 0;
     cudaGetDevice(&dev);
+    // large sparse forcing that lives on the host: plans of the ABI entry points use 256-step windows so that a forward run
+    // can stream (forward_streamed); option "stream" 0 turns it off, "stream_min_mb" is the forcing size it starts at
+    const bool small = option("stream", 1) != 0 && setup->sparse_storage &&
+                       (size_t)mesh->nac * setup->ntime_step * 8 >= ((size_t)option("stream_min_mb", 256) << 20);
     char key[192];
-    snprintf(key, sizeof key, "%016llx:%d:%d:%g:%g:%lld:%d:%d", (unsigned long long)h, dev, setup->ntime_step, (double)setup->dt,
-             (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0);
+    snprintf(key, sizeof key, "%016llx:%d:%d:%g:%g:%lld:%d:%d:%d:%lld", (unsigned long long)h, dev, setup->ntime_step, (double)setup->dt,
+             (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0, small ? 1 : 0,
+             option("river_wave", 0));
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
         std::unique_ptr<SmashPlan> pl(new SmashPlan());
+        pl->small_windows = small;
         TRY(plan_build(*pl, setup, mesh, 1, engine));
         it = g_plans.emplace(key, std::move(pl)).first;
     }
@@ -856,6 +878,57 @@ static void scatter_sorted(const SmashPlan &pl, const float *sorted, float *plan
     for (int s = 0; s < pl.ncols; s++) if (pl.col_cell[s] >= 0) plane[pl.col_cell[s]] = sorted[s];
 }
 
+// Streamed forward run of the split engine.  The sparse forcing arrays are used in place on the device ([t][k], k = j), so
+// a time window of them is one contiguous piece of the caller's arrays, and so is a window of sparse_qsim_domain.  Window w
+// is uploaded on s_in while window w - 1 is computed on the plan's stream and window w - 2 travels back on s_out: both PCIe
+// directions and the kernels overlap, and the run costs about as long as the larger of the two transfers.
+static bool can_stream(const SmashPlan &pl, const SmashSetup *setup) {
+    return pl.engine == 1 && pl.small_windows && pl.sp.nwin > 1 && setup->sparse_storage && pl.sp.rg.direct && pl.tp.nactive % 4 == 0 &&
+           option("stream", 1) != 0;
+}
+static int forward_streamed(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, SmashOutput *out,
+                            bool save_q, bool save_netp) {
+    SplitState &sp = pl.sp;
+    const Topology &tp = pl.tp;
+    const size_t nac = (size_t)mesh->nac, npad = (size_t)sp.rg.npad;
+    bool fresh = true;
+    TRY(plan_set_forcing(pl, setup, mesh, in, false, &fresh));           // buffers, tensor maps, qobs; no forcing copy
+    if (!pl.s_in) { CU(cudaStreamCreateWithFlags(&pl.s_in, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&pl.s_out, cudaStreamNonBlocking)); }
+    while ((int)pl.ev_in.size() < sp.nwin) {
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreateWithFlags(&e0, cudaEventDisableTiming)); pl.ev_in.push_back(e0);
+        CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming)); pl.ev_cmp.push_back(e1);
+    }
+    float *hq = save_q ? out->sparse_qsim_domain : nullptr, *hn = save_netp ? out->sparse_net_prcp_domain : nullptr;
+    if (hq) pin_host(hq, nac * tp.T * sizeof(float));
+    if (hn) pin_host(hn, nac * tp.T * sizeof(float));
+    SplitArgs a = split_args(pl, save_q, save_netp);
+    for (int i = 0; i < 8; i++) pl.kmark[i] = 0;
+    // the fields are uploaded on the plan's stream: nothing of this run may start before them
+    CU(cudaMemcpy2DAsync(sp.d_hcar.p, npad * sizeof(float), pl.d_fields.p + (size_t)F_HLR * npad, (size_t)NFIELD * npad * sizeof(float),
+                         npad * sizeof(float), 1, cudaMemcpyDeviceToDevice, pl.stream));
+    for (int w = 0; w < sp.nwin; w++) {
+        const int t0 = w * sp.W, t1 = std::min(tp.T, (w + 1) * sp.W);
+        const size_t off = (size_t)t0 * nac, cnt = (size_t)(t1 - t0) * nac;
+        if (fresh) {
+            CU(cudaMemcpyAsync(pl.d_raw_prcp.p + off, in->sparse_prcp + off, cnt * sizeof(float), cudaMemcpyHostToDevice, pl.s_in));
+            CU(cudaMemcpyAsync(pl.d_raw_pet.p + off, in->sparse_pet + off, cnt * sizeof(float), cudaMemcpyHostToDevice, pl.s_in));
+            CU(cudaEventRecord(pl.ev_in[w], pl.s_in));
+            CU(cudaStreamWaitEvent(pl.stream, pl.ev_in[w], 0));
+        }
+        a.t_begin = t0; a.t_end = t1;
+        CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), false, pl.stream));
+        CU(launch_route_forward_window(a, w, false, pl.stream));
+        pl.launches += 2 + (sp.rg.npair > 0 ? 1 : 0);
+        if (save_q) { CU(launch_rows_to_domain(a, pl.stream)); pl.launches++; }
+        CU(cudaEventRecord(pl.ev_cmp[w], pl.stream));
+        if (hq || hn) CU(cudaStreamWaitEvent(pl.s_out, pl.ev_cmp[w], 0));
+        if (hq) CU(cudaMemcpyAsync(hq + off, pl.d_qdom.p + (size_t)t0 * sp.qpitch, cnt * sizeof(float), cudaMemcpyDeviceToHost, pl.s_out));
+        if (hn) CU(cudaMemcpyAsync(hn + off, pl.d_netp.p + (size_t)t0 * sp.qpitch, cnt * sizeof(float), cudaMemcpyDeviceToHost, pl.s_out));
+    }
+    return 0;
+}
+
 static int run_forward_engine(SmashPlan &pl, bool save_q, bool save_netp, bool tape) {
     if (pl.engine == 1) return split_forward(pl, save_q, save_netp, tape);
     SolverArgs a = solver_args(pl, save_q, save_netp, tape);
@@ -887,23 +960,31 @@ static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const 
     const bool save_q = setup->save_qsim_domain && out && (setup->sparse_storage ? out->sparse_qsim_domain : out->qsim_domain);
     const bool save_n = setup->save_net_prcp_domain && out && (setup->sparse_storage ? out->sparse_net_prcp_domain : out->net_prcp_domain);
     TRY(plan_members(*pl, 1, save_q, save_n, false));
-    TRY(plan_set_forcing(*pl, setup, mesh, in));
-    TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
-    TRY(run_forward_engine(*pl, save_q, save_n, false));
+    const bool streamed = can_stream(*pl, setup) && in && in->sparse_prcp && in->sparse_pet;
+    if (streamed) {
+        TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
+        TRY(forward_streamed(*pl, setup, mesh, in, out, save_q, save_n));
+    } else {
+        TRY(plan_set_forcing(*pl, setup, mesh, in));
+        TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
+        TRY(run_forward_engine(*pl, save_q, save_n, false));
+    }
     TRY(run_cost(*pl, setup, mesh, 0.0f, false));
     std::vector<float> fs((size_t)3 * pl->ncols);
     float jobs = 0.0f;
     TRY(download(*pl, fs.data(), pl->d_fstates.p, fs.size() * sizeof(float)));
     TRY(download(*pl, &jobs, pl->d_cost_jobs.p, sizeof(float)));
     if (out && out->qsim && mesh->ng > 0) TRY(download(*pl, out->qsim, pl->d_qsim.p, (size_t)mesh->ng * tp.T * sizeof(float)));
-    if (save_q) TRY(export_domain(*pl, setup, mesh, pl->d_qdom.p, out->qsim_domain, out->sparse_qsim_domain));
-    if (save_n) TRY(export_domain(*pl, setup, mesh, pl->d_netp.p, out->net_prcp_domain, out->sparse_net_prcp_domain));
-    CU(cudaStreamSynchronize(pl->stream));
+    if (save_q && !streamed) TRY(export_domain(*pl, setup, mesh, pl->d_qdom.p, out->qsim_domain, out->sparse_qsim_domain));
+    if (save_n && !streamed) TRY(export_domain(*pl, setup, mesh, pl->d_netp.p, out->net_prcp_domain, out->sparse_net_prcp_domain));
     const size_t nc = (size_t)pl->ncell;
-    // output%fstates = states (forward.f90:71): every plane is copied, the three prognostic ones hold final values
+    // output%fstates = states (forward.f90:71): every plane is copied, the three prognostic ones hold final values.  The
+    // host copies run while the device works.
     if (out)
         for (int i = 0; i < SMASH_B200_GNS; i++)
             if (out->fstates.v[i] && st->v[i]) memcpy(out->fstates.v[i], st->v[i], nc * sizeof(float));
+    CU(cudaStreamSynchronize(pl->stream));
+    if (streamed) CU(cudaStreamSynchronize(pl->s_out));
     for (int f = 0; f < 3; f++) {
         float *dst = restore_states ? (out ? out->fstates.v[FIELD_STATE[f]] : nullptr) : st->v[FIELD_STATE[f]];
         if (dst) scatter_sorted(*pl, fs.data() + (size_t)f * pl->ncols, dst);

@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_forward_kernel(const _
     if (j0 >= n) return;
     const int j = j0 + lane;
     const bool valid = j < n;
-    const int nst = (T + VT_TK - 1) / VT_TK;
+    const int t_begin = a.t_begin, t_end = a.t_end;                       // whole run: 0, T; streamed runs: one window
+    const int nst = (t_end - t_begin + VT_TK - 1) / VT_TK;
     constexpr uint32_t STAGE_BYTES = sizeof(FwdStage);
 
     if (lane == 0) {
@@ -182,8 +183,8 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_forward_kernel(const _
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int s = 0; s < VF_NST && s < nst; s++) {
             mbar_expect_tx(&bars[s], STAGE_BYTES);
-            tma_load_2d(&stage[s][0][0][0], &tm_prcp, j0, s * VT_TK, &bars[s]);
-            tma_load_2d(&stage[s][1][0][0], &tm_pet, j0, s * VT_TK, &bars[s]);
+            tma_load_2d(&stage[s][0][0][0], &tm_prcp, j0, t_begin + s * VT_TK, &bars[s]);
+            tma_load_2d(&stage[s][1][0][0], &tm_pet, j0, t_begin + s * VT_TK, &bars[s]);
         }
     }
     __syncwarp();
@@ -197,6 +198,11 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_forward_kernel(const _
         k = make_const(fld[(size_t)F_CP * npad], fld[(size_t)F_CFT * npad], fld[(size_t)F_EXC * npad], fld[(size_t)F_LR * npad], fa,
                        a.dt, a.dx);
         hp = fld[(size_t)F_HP * npad]; hft = fld[(size_t)F_HFT * npad]; hlr = fld[(size_t)F_HLR * npad];
+        if (t_begin > 0) {                                               // a later window: the states the previous one left
+            const float *fs = a.fstates + (size_t)m * 3 * npad + j;
+            hp = fs[0]; hft = fs[(size_t)npad];
+            if (fa <= 1) hlr = fs[(size_t)2 * npad];
+        }
     }
     const bool src = fa <= 1;
     const int gfirst = valid ? a.tp.gauge_first[j] : -1;
@@ -229,11 +235,11 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_forward_kernel(const _
         __syncwarp();   // every lane holds its stage in registers: refill the slot
         if (lane == 0 && st + VF_NST < nst) {
             mbar_expect_tx(&bars[slot], STAGE_BYTES);
-            tma_load_2d(&stage[slot][0][0][0], &tm_prcp, j0, (st + VF_NST) * VT_TK, &bars[slot]);
-            tma_load_2d(&stage[slot][1][0][0], &tm_pet, j0, (st + VF_NST) * VT_TK, &bars[slot]);
+            tma_load_2d(&stage[slot][0][0][0], &tm_prcp, j0, t_begin + (st + VF_NST) * VT_TK, &bars[slot]);
+            tma_load_2d(&stage[slot][1][0][0], &tm_pet, j0, t_begin + (st + VF_NST) * VT_TK, &bars[slot]);
         }
-        const int tb = st * VT_TK;
-        const bool full = all_valid && tb + VT_TK <= T;
+        const int tb = t_begin + st * VT_TK;
+        const bool full = all_valid && tb + VT_TK <= t_end;
         const float xm = mx * inv_cp;
         const bool lean = FAST && full && __all_sync(FULL, mn >= 0.0f && xm < 0.25f && fmaf(8.0f, xm, hp) < 15.0f);
         if (lean) {
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_forward_kernel(const _
 #pragma unroll
             for (int i = 0; i < VT_TK; i++) {
                 const int t = tb + i;
-                const bool act = valid && t < T;
+                const bool act = valid && t < t_end;
                 if (TAPE && act) { thp[(size_t)t * npad] = hp; thft[(size_t)t * npad] = hft; }
                 float hp_n = hp, hft_n = hft, qt;
                 const bool gapless = (pv[i] >= 0.0f) && (ev[i] >= 0.0f);
@@ -1223,7 +1229,7 @@ constexpr int RD_T = 128;   // time steps per tile
 __global__ void __launch_bounds__(256) rows_to_domain_kernel(const SplitArgs a, const int j_first) {
     __shared__ float tile[32][RD_T + 1];
     const int m = blockIdx.z;
-    const int j0 = j_first + blockIdx.x * 32, t0 = blockIdx.y * RD_T;
+    const int j0 = j_first + blockIdx.x * 32, t0 = a.t_begin + blockIdx.y * RD_T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = warp; i < 32; i += 8) {
         const int j = j0 + i;
@@ -1237,7 +1243,7 @@ __global__ void __launch_bounds__(256) rows_to_domain_kernel(const SplitArgs a, 
     if (j < a.tp.n && a.tp.flwacc[j] > 1)
         for (int i = warp; i < RD_T; i += 8) {
             const int t = t0 + i;
-            if (t < a.T) a.qdom[((size_t)m * a.T + t) * a.qpitch + j] = tile[lane][i];
+            if (t < a.t_end) a.qdom[((size_t)m * a.T + t) * a.qpitch + j] = tile[lane][i];
         }
 }
 
@@ -1572,7 +1578,8 @@ __global__ void sum_domain_kernel(const float *src, int64_t pitch, int n, int T,
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-int split_pick_window(int T, int *S, int *nwin) {
+int split_pick_window(int T, int *S, int *nwin, bool small) {
+    if (small) { *S = 8; *nwin = (T + 255) / 256; return 256; }
     const int nw = (T + 1023) / 1024;
     const int need = (T + nw - 1) / nw;
     int s = 8;
@@ -1642,7 +1649,7 @@ template <typename K> static cudaError_t persistent_grid(K kern, int *blocks) {
     return cudaSuccess;
 }
 
-template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bool tape, cudaStream_t s) {
+template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bool tape, cudaStream_t s, int w_begin, int w_end) {
     int blocks = 0;
     cudaError_t e = tape ? persistent_grid(route_forward_kernel<S, 1>, &blocks) : persistent_grid(route_forward_kernel<S, 0>, &blocks);
     if (e != cudaSuccess) return e;
@@ -1652,7 +1659,7 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
     const int npair = (a.tp.ntask - a.tp.nchain) * a.nmember;
     if (blocks > need) blocks = need > 0 ? (int)need : 1;
     if (blocks <= ded_blocks) return cudaErrorLaunchOutOfResources;
-    for (int w = 0; w < a.nwin; w++) {
+    for (int w = w_begin; w < w_end; w++) {
         e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), s);
         if (e != cudaSuccess) return e;
         if (tape) route_forward_kernel<S, 1><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
@@ -1681,16 +1688,22 @@ cudaError_t launch_route_members(const SplitArgs &a, bool tape, cudaStream_t s) 
     return e;
 }
 
-cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s) {
+static cudaError_t route_forward_range(const SplitArgs &a, bool tape, cudaStream_t s, int w_begin, int w_end) {
     if (a.tp.ntask == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(a.done, 0, 2 * sizeof(int) * (size_t)a.tp.ntask * a.nmember, s);   // flags + block counters
-    if (e != cudaSuccess) return e;
-    switch (a.W / 32) {
-        case 8: return route_forward_windows<8>(a, tape, s);
-        case 16: return route_forward_windows<16>(a, tape, s);
-        case 24: return route_forward_windows<24>(a, tape, s);
-        default: return route_forward_windows<32>(a, tape, s);
+    if (w_begin == 0) {
+        cudaError_t e = cudaMemsetAsync(a.done, 0, 2 * sizeof(int) * (size_t)a.tp.ntask * a.nmember, s);   // flags + block counters
+        if (e != cudaSuccess) return e;
     }
+    switch (a.W / 32) {
+        case 8: return route_forward_windows<8>(a, tape, s, w_begin, w_end);
+        case 16: return route_forward_windows<16>(a, tape, s, w_begin, w_end);
+        case 24: return route_forward_windows<24>(a, tape, s, w_begin, w_end);
+        default: return route_forward_windows<32>(a, tape, s, w_begin, w_end);
+    }
+}
+cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s) { return route_forward_range(a, tape, s, 0, a.nwin); }
+cudaError_t launch_route_forward_window(const SplitArgs &a, int w, bool tape, cudaStream_t s) {
+    return route_forward_range(a, tape, s, w, w + 1);
 }
 
 template <int S> static cudaError_t route_adjoint_windows(const SplitArgs &a, cudaStream_t s) {
@@ -1727,7 +1740,7 @@ cudaError_t launch_route_adjoint(const SplitArgs &a, cudaStream_t s) {
 cudaError_t launch_rows_to_domain(const SplitArgs &a, cudaStream_t s) {
     const int j_first = (a.first_routed / 32) * 32;
     if (j_first >= a.tp.n) return cudaSuccess;
-    dim3 grid((unsigned)((a.tp.n - j_first + 31) / 32), (unsigned)((a.T + RD_T - 1) / RD_T), (unsigned)a.nmember);
+    dim3 grid((unsigned)((a.tp.n - j_first + 31) / 32), (unsigned)((a.t_end - a.t_begin + RD_T - 1) / RD_T), (unsigned)a.nmember);
     rows_to_domain_kernel<<<grid, 256, 0, s>>>(a, j_first);
     return cudaGetLastError();
 }

@@ -43,6 +43,7 @@ struct SplitTopo {
 struct SplitArgs {
     SplitTopo tp;
     int T, Tp, W, nwin;          // time steps, row pitch (= nwin * W), steps per window (= 32 * S), windows
+    int t_begin, t_end;          // time range of this launch of the per-cell forward pass / the export (multiples of 8; whole run: 0, T)
     int first_routed;            // smallest cell index with flwacc > 1
     int nmember;
     float dt, dx;
@@ -74,7 +75,9 @@ int make_tensor_map_2d(CUtensorMap *tm, const float *base, uint64_t cols, uint64
 
 cudaError_t launch_vertical_forward(const SplitArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, int math_mode, bool tape,
                                     cudaStream_t s);
-cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s);
+cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s);      // all windows
+// one window (streamed runs: window w is routed as soon as its forcing has arrived); w = 0 resets the flags
+cudaError_t launch_route_forward_window(const SplitArgs &a, int w, bool tape, cudaStream_t s);
 // ensembles on small meshes without pit pairs: lane = member, strictly sequential arithmetic (nrouted <= 12000)
 cudaError_t launch_route_members(const SplitArgs &a, bool tape, cudaStream_t s);     // all windows
 cudaError_t launch_rows_to_domain(const SplitArgs &a, cudaStream_t s);
@@ -91,6 +94,6 @@ cudaError_t launch_scatter_columns(const float *src, int64_t pitch, const int32_
 // sum over t < T, j < n of a [T][pitch] array (double accumulation)
 cudaError_t launch_sum_domain(const float *src, int64_t pitch, int n, int T, double *out, cudaStream_t s);
 
-int split_pick_window(int T, int *S, int *nwin);   // returns W = 32 * S
+int split_pick_window(int T, int *S, int *nwin, bool small = false);   // returns W = 32 * S; small: 256-step windows
 
 }  // namespace smash

@@ -73,6 +73,50 @@ def test_river_reaches_wavefront_agrees():
     check_grad(sa, sb, ("hp", "hft", "hlr"))
 
 
+def test_streamed_forward_agrees():
+    # large host-resident sparse forcing: the ABI forward streams 256-step windows (upload, kernels, download overlapped).
+    # Same run with streaming off (one 640-step window): discharge, domain series, final states and cost must agree to the
+    # last places (the routing scan groups the time steps differently), and the second call reuses the device forcing.
+    lib = L.lib()
+    def run(stream, version=0):
+        lib.smash_b200_set_option(b"stream", stream)
+        lib.smash_b200_set_option(b"stream_min_mb", 0)
+        try:
+            m = cases.france(T=600, sub=(400, 560, 400, 560), ngauge=3)
+            random_fields(m, seed=7)
+            m.setup.save_net_prcp_domain = True
+            m.output = type(m.output)(m.setup, m.mesh)
+            m.input_data._forcing_version = version
+            smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(),
+                               m.output)
+            first = np.array(m.output.sparse_qsim_domain, copy=True)
+            if version:
+                m.output.sparse_qsim_domain[...] = -1.0
+                smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states,
+                                   m.states.copy(), m.output)
+                assert np.array_equal(first, m.output.sparse_qsim_domain)
+            return m
+        finally:
+            lib.smash_b200_set_option(b"stream", 1)
+            lib.smash_b200_set_option(b"stream_min_mb", 256)
+            lib.smash_b200_clear_cache()
+    a, b = run(1), run(0)
+    assert a.mesh.nac % 4 == 0, a.mesh.nac                                   # else the streamed path is not taken
+    run(1, version=77)
+    for x, y in ((a.output.qsim, b.output.qsim), (a.output.sparse_qsim_domain, b.output.sparse_qsim_domain),
+                 (a.output.sparse_net_prcp_domain, b.output.sparse_net_prcp_domain), (a.output.fstates.hlr, b.output.fstates.hlr),
+                 (a.output.fstates.hp, b.output.fstates.hp)):
+        x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+        assert np.all(np.abs(x - y) <= 1e-7 + 1e-5 * np.abs(y)), float(np.abs(x - y).max())
+    assert np.isclose(float(a.output.cost), float(b.output.cost), rtol=1e-5)
+    import oracle
+    c = cases.france(T=600, sub=(400, 560, 400, 560), ngauge=3)
+    random_fields(c, seed=7)
+    oracle.forward(c.setup, c.mesh, c.input_data, c.parameters, c.parameters.copy(), c.states, c.states.copy(), c.output)
+    qa, qc = np.asarray(a.output.sparse_qsim_domain, np.float64), np.asarray(c.output.sparse_qsim_domain, np.float64)
+    assert np.all(np.abs(qa - qc) <= 1e-4 + 2e-3 * np.abs(qc)), float(np.abs(qa - qc).max())
+
+
 def _plan(m, members=1):
     lib = L.lib()
     pk = L.Packed()
