@@ -300,6 +300,33 @@ def main():
                          "(a single forward of the reference is single-threaded)"}
         if not args.no_extra:
             extra.update(cance_extras(lib, L, smash_b200, oracle, cases))
+    if world > 1 and not args.no_extra:
+        # configs[2]: the 4096-member Cance ensemble split over the ranks (contiguous member blocks, no data-path collective;
+        # one all-gather of the costs afterwards) -- total work fixed, i.e. strong scaling of this extra
+        import cases
+        from smash_b200 import distributed as sdist
+        mc = cases.cance()
+        mc.input_data._forcing_version = 1
+        ns = 4096
+        rng = np.random.RandomState(99)
+        bounds = [(1e-6, 1e3), (1e-6, 1e3), (-50.0, 50.0), (1e-6, 1e3)]
+        smp = np.asfortranarray(np.stack([rng.uniform(lo, hi, ns) for lo, hi in bounds]).astype(np.float32))
+        cost, q0 = np.zeros(ns, np.float32), np.zeros((0,), np.float32)
+
+        def ens():
+            sdist.multiple_run_sharded(mc.setup, mc.mesh, mc.input_data, mc.parameters, mc.states, mc.output, smp,
+                                       cases.IND_CP_CFT_EXC_LR, cost, q0)
+
+        ens()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ens()
+        barrier()
+        dte = max_over_ranks(time.perf_counter() - t0) / 3
+        extra["cance_ensemble_4096_sharded"] = {"cell_timesteps_per_s_e2e": ns * 383 * 1440 / dte, "ms_per_call": dte * 1e3,
+                                                "members_per_rank": ns // world, "scaling": "strong",
+                                                "cost_checksum": float(np.sum(cost[np.isfinite(cost)], dtype=np.float64))}
 
     if rank == 0:
         print(json.dumps({
