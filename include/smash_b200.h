@@ -166,7 +166,9 @@ void smash_b200_clear_cache(void);           /* drop cached mesh plans and devic
  * arrays in place on first use (PCIe-speed copies) -- the caller must then call smash_b200_clear_cache() before freeing
  * them; off by default; "river_wave" 1 = the longest chains are cut into reaches of at most 128 cells, one CTA per reach,
  * routed as pipelined tick wavefronts (thread = cell, strictly sequential arithmetic) instead of a window scan per cell
- * (experimental: slower than the default on the France mesh). */
+ * (experimental: slower than the default on the France mesh); "stream" 1 (default) = forward runs
+ * whose sparse forcing is at least "stream_min_mb" (256) megabytes are cut into 256-step windows so that the forcing upload,
+ * the kernels and the download of sparse_qsim_domain overlap on three streams (effective with page-locked arrays). */
 int smash_b200_set_option(const char *name, long long value);
 
 /* ---- device-resident plan API (bench / advanced callers) --------------------------------------
