@@ -327,3 +327,238 @@ def multiple_run(model, sample, names, jobs_fun="nse", wjobs_fun=None, gauge="do
     sv.compute_multiple_run(inst.setup, inst.mesh, inst.input_data, inst.parameters, inst.states, inst.output, smp,
                             np.array(ind, dtype=np.int32), cost, qsim)
     return (cost, qsim) if return_qsim else cost
+
+
+# ------------------------------------------------------------------------------------------ samples / Bayesian estimation
+class SampleResult(dict):
+    """smash/core/generate_samples.py:22-270: the generated samples, one array per name plus ``_<name>`` (the density of
+    each drawn value), ``generator``, ``n_sample`` and ``_problem``."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError as e:
+            raise AttributeError(name) from e
+
+    __setattr__ = dict.__setitem__
+
+    def to_numpy(self, axis=0):
+        return np.stack([self[k] for k in self._problem["names"]], axis=axis)
+
+    def slice(self, n, start=0):
+        if start < 0 or n > self.n_sample or start >= n:
+            raise ValueError("invalid slice")
+        d = {k: (v[start:n] if isinstance(v, np.ndarray) and v.shape == (self.n_sample,) else v) for k, v in self.items()}
+        d["n_sample"] = n - start
+        return SampleResult(d)
+
+    def iterslice(self, by=1):
+        for start in range(0, self.n_sample, by):
+            yield self.slice(min(start + by, self.n_sample), start)
+
+
+def get_bound_constraints(model, states=False):
+    """Model.get_bound_constraints / _get_bound_constraints (generate_samples.py:389-414)."""
+    o = model.setup._optimize
+    names = (STRUCTURE_STATES if states else STRUCTURE_PARAMETERS)[str(model.setup.structure)]
+    bounds = []
+    for name in names:
+        if name in GSTATES_NAME:
+            k = GSTATES_NAME.index(name)
+            bounds.append([o.lb_states[k].item(), o.ub_states[k].item()])
+        else:
+            k = GPARAMETERS_NAME.index(name)
+            bounds.append([o.lb_parameters[k].item(), o.ub_parameters[k].item()])
+    return {"num_vars": len(names), "names": list(names), "bounds": bounds}
+
+
+def generate_samples(problem, generator="uniform", n=1000, random_state=None, mean=None, coef_std=None):
+    """smash.generate_samples (generate_samples.py:273-383): one ``np.random`` draw per name, in the order of
+    ``problem['names']``, after seeding the legacy global generator."""
+    generator = str(generator).lower()
+    if generator not in ("uniform", "normal", "gaussian"):
+        raise ValueError(f"Unknown generator '{generator}': Choices: ['uniform', 'normal', 'gaussian']")
+    ret = {"generator": generator, "n_sample": n, "_problem": dict(problem)}
+    if random_state is not None:
+        np.random.seed(random_state)
+    for i, p in enumerate(problem["names"]):
+        low, upp = problem["bounds"][i]
+        if generator == "uniform":
+            ret[p] = np.random.uniform(low, upp, n)
+            ret["_" + p] = np.ones(n) / (upp - low)
+        else:
+            from scipy.stats import truncnorm
+            mu = (low + upp) / 2 if not mean or mean.get(p) is None else mean[p]
+            sd = (upp - low) / (3 if coef_std is None else coef_std)
+            tn = truncnorm((low - mu) / sd, (upp - mu) / sd, loc=mu, scale=sd)
+            ret[p] = tn.rvs(size=n)
+            ret["_" + p] = tn.pdf(ret[p])
+    return SampleResult(ret)
+
+
+class BayesResult(dict):
+    """smash/core/simulation/bayes_optimize.py:23-76"""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError as e:
+            raise AttributeError(name) from e
+
+    __setattr__ = dict.__setitem__
+
+
+def _compute_mean_U(U, J, rho, alpha, mask):
+    """bayes_optimize.py:433-454.  ``alpha`` enters as a Python float so that the float32 cost array keeps its type, as
+    under the NumPy the reference's golden file was made with."""
+    L = np.exp(-(2 ** float(alpha)) * (J / min(J) - 1) ** 2)
+    Lrho = L * rho
+    C = np.sum(Lrho, axis=2)
+    U_alp = 1 / C * np.sum(U * Lrho, axis=2)
+    varU = 1 / C * np.sum((U - U_alp[..., np.newaxis]) ** 2 * Lrho, axis=2)
+    varU = np.mean(varU[mask])
+    Uinf = np.mean(U, axis=2)
+    D_alp = np.mean(np.square(U_alp - Uinf)[mask]) / varU
+    return U_alp, varU, D_alp
+
+
+def _bayes(model, sample, alpha, n, random_state, de_bw_method, de_weights, mapping, algorithm, control_vector, bounds, jobs_fun,
+           wjobs_fun, gauge, wgauge, ost_step, options, inplace, return_br, solver, mr_solver):
+    """_bayes_computation (bayes_optimize.py:79-185).  ``algorithm is None``: Bayesian estimation -- the direct simulations
+    of the sample are ONE ``compute_multiple_run`` call (all members in one GPU launch); otherwise every member is the
+    first guess of an optimisation."""
+    inst = model if inplace else model.copy()
+    sv = solver or _mw_forward
+    names = None
+    if algorithm is None:
+        _setup_optimize(inst, "uniform", "sbs", None, None, jobs_fun, wjobs_fun, gauge, wgauge, ost_step, False)
+        inst.setup._optimize.mapping = "..."
+        if sample is None:
+            sample = generate_samples(get_bound_constraints(inst, states=False), "uniform", n, random_state)
+        elif not isinstance(sample, SampleResult):
+            raise TypeError("sample must be a SampleResult object or None")
+    else:
+        algorithm, cv = _setup_optimize(inst, mapping, algorithm, control_vector, bounds, jobs_fun, wjobs_fun, gauge, wgauge,
+                                        ost_step, False)
+        if sample is None:
+            o = inst.setup._optimize
+            bnd = []
+            for c in cv:
+                if c in GPARAMETERS_NAME:
+                    k = GPARAMETERS_NAME.index(c)
+                    bnd.append([o.lb_parameters[k].item(), o.ub_parameters[k].item()])
+                else:
+                    k = GSTATES_NAME.index(c)
+                    bnd.append([o.lb_states[k].item(), o.ub_states[k].item()])
+            sample = generate_samples({"num_vars": len(cv), "names": list(cv), "bounds": bnd}, "uniform", n, random_state)
+        elif set(sample._problem["names"]) != set(cv):
+            raise ValueError(f"Problem names ({sample._problem['names']}) and control vectors ({cv}) must have the same elements")
+    if isinstance(alpha, (range, np.ndarray, tuple)):
+        alpha = list(alpha)
+    elif not isinstance(alpha, (int, float, list)):
+        raise TypeError("alpha must be numerical or list-like object")
+    names = list(sample._problem["names"])
+    ns = sample.n_sample
+    shape = (inst.mesh.nrow, inst.mesh.ncol)
+    a = (inst.setup, inst.mesh, inst.input_data)
+
+    def field(name):
+        return getattr(inst.parameters if name in GPARAMETERS_NAME else inst.states, name)
+
+    # ---- _multi_simu (:308-390)
+    prior, density = {}, {}
+    if algorithm is None:
+        smp = np.asfortranarray(np.stack([np.asarray(sample[p], dtype=np.float32) for p in names]))
+        ind = [GPARAMETERS_NAME.index(p) + 1 if p in GPARAMETERS_NAME else len(GPARAMETERS_NAME) + GSTATES_NAME.index(p) + 1
+               for p in names]
+        cost = np.zeros(ns, dtype=np.float32)
+        (mr_solver or _mw_multiple_run).compute_multiple_run(*a, inst.parameters, inst.states, inst.output, smp,
+                                                             np.array(ind, dtype=np.int32), cost, np.zeros((0, 0, 0), np.float32))
+        for k, p in enumerate(names):
+            prior[p] = np.broadcast_to(smp[k][None, None, :], shape + (ns,)).astype(np.float32)
+    else:
+        opts = dict(options or {})
+        inst.setup._optimize.maxiter = int(opts.pop("maxiter", 100))
+        if opts:
+            raise KeyError("Unknown algorithm options: '%s'" % ", ".join(map(str, opts)))
+        cost = np.zeros(ns, dtype=np.float32)
+        stack = {p: [] for p in names}
+        for i in range(ns):
+            run_i = inst.copy()
+            run_i.setup._optimize = inst.setup._optimize.copy()
+            for p in names:
+                getattr(run_i.parameters if p in GPARAMETERS_NAME else run_i.states, p)[...] = sample[p][i]
+            drv = _mw_optimize.optimize_sbs if algorithm == "sbs" else (
+                _mw_optimize.optimize_hyper_lbfgsb if mapping.startswith("hyper") else _mw_optimize.optimize_lbfgsb)
+            drv(run_i.setup, run_i.mesh, run_i.input_data, run_i.parameters, run_i.states, run_i.output, solver=solver)
+            cost[i] = run_i.output.cost
+            for p in names:
+                stack[p].append(np.copy(getattr(run_i.parameters if p in GPARAMETERS_NAME else run_i.states, p)))
+        for p in names:
+            prior[p] = np.dstack(stack[p])
+    prior["cost"] = cost
+    ret_data = {"cost": np.array(cost)}
+    for p in names:
+        ret_data[p] = sample[p]
+        density[p] = np.ones(prior[p].shape)
+
+    # ---- _compute_density (:392-430)
+    mask = np.where(np.asarray(inst.mesh.active_cell) == 1)
+    x, y = mask
+    for p in names:
+        if algorithm == "l-bfgs-b":
+            from scipy.stats import gaussian_kde
+            for xi, yi in zip(x, y):
+                density[p][xi, yi] = gaussian_kde(prior[p][xi, yi], bw_method=de_bw_method, weights=de_weights)(prior[p][xi, yi])
+        elif isinstance(algorithm, str):
+            from scipy.stats import gaussian_kde
+            u_dis = np.mean(prior[p][mask], axis=0)
+            density[p][x, y] = gaussian_kde(u_dis, bw_method=de_bw_method, weights=de_weights)(u_dis)
+        else:
+            density[p][x, y] = sample["_" + p]
+
+    # ---- _compute_param / _lcurve_compute_param (:457-566)
+    def compute_param(al):
+        D, var = [], {}
+        for p in names:
+            u, v, d = _compute_mean_U(prior[p], prior["cost"], density[p], al, mask)
+            setattr(inst.parameters if p in GPARAMETERS_NAME else inst.states, p, np.asfortranarray(u, dtype=np.float32))
+            D.append(d)
+            var[p] = v
+        sv.forward(*a, inst.parameters, inst.parameters.copy(), inst.states, inst.states.copy(), inst.output)
+        return inst.output.cost, np.mean(D), var
+
+    lcurve = {}
+    if isinstance(alpha, list):
+        costs, Ds, vars_ = [], [], []
+        for al in alpha:
+            c, d, v = compute_param(al)
+            costs.append(c); Ds.append(d); vars_.append(v)
+        cs = (costs - np.min(costs)) / (np.max(costs) - np.min(costs))
+        ds = (Ds - np.min(Ds)) / (np.max(Ds) - np.min(Ds))
+        alpha_opt = alpha[int(np.argmin(np.square(cs) + np.square(ds)))]
+        compute_param(alpha_opt)
+        lcurve = {"alpha": alpha, "alpha_opt": alpha_opt, "mahal_dist": Ds, "cost": costs, "var": vars_}
+    else:
+        compute_param(alpha)
+    br = BayesResult(data=ret_data, lcurve=lcurve)
+    if return_br:
+        return br if inplace else (inst, br)
+    return None if inplace else inst
+
+
+def bayes_estimate(model, sample=None, alpha=4, n=1000, random_state=None, jobs_fun="nse", wjobs_fun=None, gauge="downstream",
+                   wgauge="mean", ost_step=0, inplace=False, return_br=False, solver=None, mr_solver=None):
+    """Model.bayes_estimate (model.py:849-1010)."""
+    return _bayes(model, sample, alpha, n, random_state, None, None, None, None, None, None, jobs_fun, wjobs_fun, gauge, wgauge,
+                  ost_step, None, inplace, return_br, solver, mr_solver)
+
+
+def bayes_optimize(model, sample=None, alpha=4, n=1000, random_state=None, de_bw_method=None, de_weights=None, mapping="uniform",
+                   algorithm=None, control_vector=None, bounds=None, jobs_fun="nse", wjobs_fun=None, gauge="downstream",
+                   wgauge="mean", ost_step=0, options=None, inplace=False, return_br=False, solver=None):
+    """Model.bayes_optimize (model.py:1012-1200)."""
+    if algorithm is None:
+        algorithm = "sbs" if mapping == "uniform" else "l-bfgs-b"
+    return _bayes(model, sample, alpha, n, random_state, de_bw_method, de_weights, mapping, algorithm, control_vector, bounds,
+                  jobs_fun, wjobs_fun, gauge, wgauge, ost_step, options, inplace, return_br, solver, None)

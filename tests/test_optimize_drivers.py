@@ -132,3 +132,42 @@ def test_vda_converges_gpu():
     c = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": 5})
     r = simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": 5}, solver=oracle_solver)
     assert abs(float(c.output.cost) - float(r.output.cost)) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------ Bayesian estimation
+def test_generate_samples_golden(golden):
+    # generate_samples(problem, n=10, random_state=99) of generic_multiple_run (test_simu.py:28-31)
+    m = cases.cance(T=24)
+    sr = simulation.generate_samples(simulation.get_bound_constraints(m), n=10, random_state=99)
+    assert np.allclose(sr.to_numpy(axis=0), golden["samples.cp_cft_exc_lr"], rtol=1e-12)
+    assert [s.n_sample for s in sr.iterslice(4)] == [4, 4, 2]
+
+
+def _bayes_estimate(golden, solver, mr_solver, atol):
+    # generic_bayes_estimate (test_simu.py:214-237)
+    inst, br = simulation.bayes_estimate(cases.cance(), alpha=np.linspace(-1, 5, 10), n=5, return_br=True, random_state=11,
+                                         solver=solver, mr_solver=mr_solver)
+    got = np.array(br.lcurve["cost"])
+    print("bayes_estimate.br_cost max diff", np.abs(got - golden["bayes_estimate.br_cost"]).max())
+    assert np.allclose(got, golden["bayes_estimate.br_cost"], atol=atol)
+    assert np.allclose(_cost(inst), golden["bayes_estimate.cost"], atol=atol)
+
+
+def test_bayes_estimate_golden_cpu(golden):
+    _bayes_estimate(golden, oracle_solver, oracle_solver, COST_ATOL)
+
+
+def test_bayes_optimize_golden_cpu(golden):
+    # generic_bayes_optimize (test_simu.py:240-268)
+    inst, br = simulation.bayes_optimize(cases.cance(), alpha=np.linspace(-1, 5, 10), n=5, mapping="distributed",
+                                         algorithm="l-bfgs-b", options={"maxiter": 1}, return_br=True, random_state=11,
+                                         solver=oracle_solver)
+    got = np.array(br.lcurve["cost"])
+    print("bayes_optimize.br_cost max diff", np.abs(got - golden["bayes_optimize.br_cost"]).max())
+    assert np.allclose(got, golden["bayes_optimize.br_cost"], atol=2e-5)
+    assert np.allclose(_cost(inst), golden["bayes_optimize.cost"], atol=2e-5)
+
+
+@pytest.mark.gpu
+def test_bayes_estimate_golden_gpu(golden):
+    _bayes_estimate(golden, None, None, COST_ATOL_GPU)
