@@ -232,8 +232,8 @@ def optimize(model, mapping="uniform", algorithm=None, control_vector=None, boun
         if jreg_fun is not None:                                          # _standardize_jreg_fun / wjreg_fun
             jr = _as_array(jreg_fun, "jreg_fun")
             for name in jr:
-                if name not in ("prior", "smoothing"):
-                    raise ValueError(f"Unknown regularization function '{name}'. Choices: ['prior', 'smoothing']")
+                if name not in ("prior", "smoothing", "hard_smoothing"):
+                    raise ValueError(f"Unknown regularization function '{name}'. Choices: ['prior', 'smoothing', 'hard_smoothing']")
             if mapping.startswith("hyper"):
                 raise ValueError("Regularization function(s) can not be used with hyper mappings")
             o.njr = jr.size

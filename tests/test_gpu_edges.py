@@ -1,0 +1,143 @@
+"""Edge cases of the hot path on the GPU against the oracle: run lengths that do not fill a forcing tile or a scan window,
+cost windows that start late, missing observations, sparse layouts that need the gather pass (nac not a multiple of 4),
+a mesh without gauges, and error behaviour at the boundary."""
+import numpy as np
+import pytest
+
+import cases
+import oracle
+import smash_b200
+from smash_b200 import _lib as L
+from test_gpu_parity import close_q, gradients, random_fields
+
+pytestmark = pytest.mark.gpu
+
+
+def check_grad(ga, gb, names, model=None):
+    """Gradient fields of the device (ga) against the float32 restatement (gb).  Where ``model`` is given the comparison is
+    made against the float64 build of the restatement and the tolerance is the larger of the suite's 2e-3 (relative to the
+    inf-norm of the field) and three times the distance of the float32 restatement from the float64 one: short runs from
+    nearly empty reservoirs have gradients that float32 itself only resolves to a few 1e-3; fields it does not resolve
+    at all there (cft, hlr: the two builds of the restatement disagree by more than 5 %) are not compared."""
+    g64 = None
+    if model is not None:
+        g64 = gradients(model, "cpu", precision="f64")
+    for n in names:
+        x, y = np.asarray(getattr(ga, n), np.float64), np.asarray(getattr(gb, n), np.float64)
+        ref, tol = y, 2e-3
+        if g64 is not None:
+            ref = np.asarray(getattr(g64[0] if hasattr(g64[0], n) else g64[1], n), np.float64)
+            scale = np.abs(ref).max()
+            noise = np.abs(y - ref).max() / scale if scale > 0 else 0.0
+            if noise > 5e-2:
+                print(f"grad {n}: float32 resolves this field only to {noise:.1e} of its inf-norm here -- not compared")
+                continue
+            tol = max(2e-3, 3.0 * noise)
+        scale = np.abs(ref).max()
+        err = np.abs(x - ref).max()
+        print(f"grad {n}: |gpu - ref| / scale = {err / scale if scale else 0:.2e}, tolerance {tol:.2e}")
+        assert err <= tol * scale + 1e-12, (n, err, scale, tol)
+
+
+@pytest.mark.parametrize("T", [1, 5, 8, 9, 33, 257])
+def test_short_and_ragged_runs(T):
+    # T = 1 (a single step), T < 8 (one partial TMA box), T = 8k + 1, T just past a 256-step boundary
+    a, b = cases.cance(T=T), cases.cance(T=T)
+    for m in (a, b):
+        random_fields(m, seed=2)
+    smash_b200.forward(a.setup, a.mesh, a.input_data, a.parameters, a.parameters.copy(), a.states, a.states.copy(), a.output)
+    oracle.forward(b.setup, b.mesh, b.input_data, b.parameters, b.parameters.copy(), b.states, b.states.copy(), b.output)
+    assert a.output.qsim.shape == (3, T)
+    assert close_q(a.output.qsim, b.output.qsim)
+    for n in ("hp", "hft", "hlr"):
+        assert np.allclose(getattr(a.output.fstates, n), getattr(b.output.fstates, n), rtol=1e-4, atol=1e-7), n
+
+
+@pytest.mark.parametrize("T", [33, 100])
+def test_short_run_gradient(T):
+    # (below ~ 30 steps the gradient of a run that starts from nearly empty reservoirs is at the float32 noise level,
+    # 1e-12, in both implementations and cannot be compared)
+    a, b = cases.cance(T=T), cases.cance(T=T)
+    for m in (a, b):
+        cases.set_optimize(m.setup, m.mesh, jobs_fun=("rmse",))        # nse degenerates on a handful of steps
+        random_fields(m, seed=2)
+    pa, sa = gradients(a, "gpu")
+    pb, sb = gradients(b, "cpu")
+    assert np.isclose(float(a.output.cost), float(b.output.cost), rtol=1e-4, atol=1e-6)
+    c = cases.cance(T=T)
+    cases.set_optimize(c.setup, c.mesh, jobs_fun=("rmse",))
+    random_fields(c, seed=2)
+    check_grad(pa, pb, ("cp", "cft", "exc", "lr"), c)
+    check_grad(sa, sb, ("hp", "hft", "hlr"), c)
+
+
+@pytest.mark.parametrize("jobs", [("nse",), ("kge",)])
+def test_late_cost_window_and_missing_observations(jobs):
+    # optimize_start_step > 1 (mwd_cost.f90:84-92) and observations with gaps (qobs < 0 is skipped, :509-520)
+    a, b = cases.cance(T=600), cases.cance(T=600)
+    rng = np.random.default_rng(4)
+    holes = rng.random(a.input_data.qobs.shape) < 0.15
+    for m in (a, b):
+        cases.set_optimize(m.setup, m.mesh, jobs_fun=jobs, gauge="all", ost=241)
+        m.input_data.qobs = np.asfortranarray(np.where(holes, np.float32(-99.0), m.input_data.qobs))
+        random_fields(m, seed=6)
+    pa, sa = gradients(a, "gpu")
+    pb, sb = gradients(b, "cpu")
+    print("cost gpu", float(a.output.cost), "oracle", float(b.output.cost))
+    assert abs(float(a.output.cost) - float(b.output.cost)) < 1e-5 + 1e-5 * abs(float(b.output.cost))
+    c = cases.cance(T=600)
+    cases.set_optimize(c.setup, c.mesh, jobs_fun=jobs, gauge="all", ost=241)
+    c.input_data.qobs = np.asfortranarray(np.where(holes, np.float32(-99.0), c.input_data.qobs))
+    random_fields(c, seed=6)
+    check_grad(pa, pb, ("cp", "cft", "exc", "lr"), c)
+    check_grad(sa, sb, ("hp", "hft", "hlr"), c)
+
+
+def test_gauge_without_observations_has_no_weight():
+    # a gauge whose series is entirely missing is dropped by the caller (_standardize_gauge, _standardize.py:329-341) and
+    # gets weight 0.  (With a non-zero weight the reference adds the stale j_imd of the previous gauge, undefined for the
+    # first one, mwd_cost.f90:100-136; the device adds nothing.  Unreachable through the Python API.)
+    from smash_b200 import simulation
+    a, b = cases.cance(T=240), cases.cance(T=240)
+    for m in (a, b):
+        m.input_data.qobs[1, :] = -99.0
+        w = simulation._gauge_weights(m.mesh, m.input_data, "all", "mean", 0)
+        assert w[1] == 0 and np.isclose(w.sum(), 1.0)
+        cases.set_optimize(m.setup, m.mesh, jobs_fun=("nse",), wgauge=w)
+    smash_b200.forward(a.setup, a.mesh, a.input_data, a.parameters, a.parameters.copy(), a.states, a.states.copy(), a.output)
+    oracle.forward(b.setup, b.mesh, b.input_data, b.parameters, b.parameters.copy(), b.states, b.states.copy(), b.output)
+    assert np.isfinite(float(a.output.cost))
+    assert abs(float(a.output.cost) - float(b.output.cost)) < 1e-5 + 1e-5 * abs(float(b.output.cost))
+
+
+def test_sparse_layout_needing_the_gather_pass():
+    # 31 x 33 window: nac = 1023 is not a multiple of 4, so the sparse arrays cannot be used in place by the TMA tiles
+    a, b = (cases.france(T=40, sub=(400, 431, 400, 433), ngauge=2) for _ in range(2))
+    assert a.mesh.nac % 4 != 0
+    for m in (a, b):
+        random_fields(m, seed=8)
+    pa, sa = gradients(a, "gpu")
+    pb, sb = gradients(b, "cpu")
+    assert close_q(a.output.qsim, b.output.qsim)
+    c = cases.france(T=40, sub=(400, 431, 400, 433), ngauge=2)
+    random_fields(c, seed=8)
+    check_grad(pa, pb, ("cp", "cft", "exc", "lr"), c)
+    smash_b200.forward(a.setup, a.mesh, a.input_data, a.parameters, a.parameters.copy(), a.states, a.states.copy(), a.output)
+    oracle.forward(b.setup, b.mesh, b.input_data, b.parameters, b.parameters.copy(), b.states, b.states.copy(), b.output)
+    assert close_q(a.output.sparse_qsim_domain, b.output.sparse_qsim_domain)
+
+
+def test_errors_at_the_boundary():
+    m = cases.cance(T=24)
+    m.setup.structure = "gr-b"
+    with pytest.raises(RuntimeError, match="gr-a"):
+        smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
+    m = cases.cance(T=24)
+    cases.set_optimize(m.setup, m.mesh, jobs_fun=("Crc",))
+    with pytest.raises(RuntimeError):
+        smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
+    m = cases.cance(T=24)
+    m.mesh.path = np.asfortranarray(m.mesh.path + 1000)                      # indices outside the grid
+    with pytest.raises(RuntimeError):
+        smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
+    L.lib().smash_b200_clear_cache()
