@@ -1272,6 +1272,7 @@ extern "C" int smash_b200_plan_create(const SmashSetup *setup, const SmashMesh *
     if (!plan) return fail(SMASH_B200_EINVAL, "plan is NULL");
     TRY(check_device());
     std::unique_ptr<SmashPlan> pl(new SmashPlan());
+    pl->small_windows = option("plan_small_windows", 0) != 0;          // diagnostics: 256-step routing windows in a resident plan
     TRY(plan_build(*pl, setup, mesh, nmember, nmember > 1 ? (int)option("ensemble_engine", -1) : -1));
     pl->nmember = nmember > 0 ? nmember : 1;
     pl->ensemble = nmember > 1;

@@ -1,0 +1,382 @@
+"""Descriptor-to-parameter network of ``Model.ann_optimize`` (smash/core/net.py:22-1117, simulation/_ann_optimize.py:20-254).
+
+Host-side restatement: the network is a few hundred weights for a catchment such as Cance (2 -> 18 -> 9 -> 4), its
+forward / backward passes are NumPy; what it differentiates through is the hydrological cost, whose gradient with respect
+to the distributed parameters comes from ``forward_b`` on the GPU (``_hcost_prime``, net.py:1001-1056).  Layer and
+optimiser arithmetic, weight initialisation and the use of the legacy global NumPy generator follow the reference, so a
+given ``random_state`` gives the reference's weights."""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+from .solver import _mw_forward
+from .solver._derived_types import GPARAMETERS_NAME
+
+
+class _Sigmoid:
+    def __call__(self, x):
+        return 1 / (1 + np.exp(-x))
+
+    def gradient(self, x):
+        return self(x) * (1 - self(x))
+
+
+class _Softmax:
+    def __call__(self, x):
+        e = np.exp(x - np.max(x, axis=-1, keepdims=True))
+        return e / np.sum(e, axis=-1, keepdims=True)
+
+    def gradient(self, x):
+        p = self(x)
+        return p * (1 - p)
+
+
+class _TanH:
+    def __call__(self, x):
+        return 2 / (1 + np.exp(-2 * x)) - 1
+
+    def gradient(self, x):
+        return 1 - np.power(self(x), 2)
+
+
+class _ReLU:
+    def __call__(self, x):
+        return np.where(x >= 0, x, 0)
+
+    def gradient(self, x):
+        return np.where(x >= 0, 1, 0)
+
+
+class _LeakyReLU:
+    alpha = 0.2
+
+    def __call__(self, x):
+        return np.where(x >= 0, x, self.alpha * x)
+
+    def gradient(self, x):
+        return np.where(x >= 0, 1, self.alpha)
+
+
+class _ELU:
+    alpha = 0.1
+
+    def __call__(self, x):
+        return np.where(x >= 0.0, x, self.alpha * (np.exp(x) - 1))
+
+    def gradient(self, x):
+        return np.where(x >= 0.0, 1, self(x) + self.alpha)
+
+
+class _SELU:
+    alpha, scale = 1.6732632423543772848170429916717, 1.0507009873554804934193349852946
+
+    def __call__(self, x):
+        return self.scale * np.where(x >= 0.0, x, self.alpha * (np.exp(x) - 1))
+
+    def gradient(self, x):
+        return self.scale * np.where(x >= 0.0, 1, self.alpha * np.exp(x))
+
+
+class _SoftPlus:
+    def __call__(self, x):
+        return np.log(1 + np.exp(x))
+
+    def gradient(self, x):
+        return 1 / (1 + np.exp(-x))
+
+
+ACTIVATION_FUNC = {"relu": _ReLU, "sigmoid": _Sigmoid, "selu": _SELU, "elu": _ELU, "softmax": _Softmax,
+                   "leaky_relu": _LeakyReLU, "tanh": _TanH, "softplus": _SoftPlus}
+WB_INITIALIZER = ("uniform", "glorot_uniform", "he_uniform", "normal", "glorot_normal", "he_normal", "zeros")
+
+
+def _no_unknown(what, opts):
+    if opts:
+        raise KeyError("Unknown %s options: '%s'" % (what, ", ".join(map(str, opts))))
+
+
+class Activation:
+    """net.py:458-498"""
+
+    def __init__(self, name, **unknown):
+        _no_unknown("Activation Layer", unknown)
+        self.input_shape = None
+        self.activation_name = name
+        self._f = ACTIVATION_FUNC[name.lower()]()
+        self.trainable = True
+
+    def _set_input_shape(self, shape):
+        self.input_shape = shape
+
+    def _forward_pass(self, x, training=True):
+        self.layer_input = x
+        return self._f(x)
+
+    def _backward_pass(self, g):
+        return g * self._f.gradient(self.layer_input)
+
+    def output_shape(self):
+        return self.input_shape
+
+    def n_params(self):
+        return 0
+
+
+class Scale:
+    """net.py:501-534, MinMaxScale :831-845"""
+
+    def __init__(self, bounds, **unknown):
+        _no_unknown("Scale Layer", unknown)
+        self.input_shape = None
+        b = np.array(bounds)
+        self.lower, self.upper = np.array([x[0] for x in b]), np.array([x[1] for x in b])
+        self.trainable = True
+
+    def _set_input_shape(self, shape):
+        self.input_shape = shape
+
+    def _forward_pass(self, x, training=True):
+        self.layer_input = x
+        return self.lower + x * (self.upper - self.lower)
+
+    def _backward_pass(self, g):
+        return g * (self.upper - self.lower)
+
+    def output_shape(self):
+        return self.input_shape
+
+    def n_params(self):
+        return 0
+
+
+class Dense:
+    """net.py:579-688; weights drawn from the legacy global generator in the order weight, bias (_wb_initialization
+    :537-576)."""
+
+    def __init__(self, neurons, input_shape=None, kernel_initializer="glorot_uniform", bias_initializer="zeros", **unknown):
+        _no_unknown("Dense Layer", unknown)
+        self.layer_input, self.input_shape, self.neurons, self.trainable = None, input_shape, neurons, True
+        self.weight = self.bias = None
+        self.kernel_initializer, self.bias_initializer = kernel_initializer.lower(), bias_initializer.lower()
+        for ini in (self.kernel_initializer, self.bias_initializer):
+            if ini not in WB_INITIALIZER:
+                raise ValueError(f"Unknown initializer: {ini}. Choices {list(WB_INITIALIZER)}")
+
+    def _set_input_shape(self, shape):
+        self.input_shape = shape
+
+    def _draw(self, initializer, shape):
+        fin, fout = self.input_shape[0], self.neurons
+        kind = initializer.split("_")
+        if kind[-1] == "uniform":
+            limit = np.sqrt(6 / (fin + fout)) if kind[0] == "glorot" else np.sqrt(6 / fin) if kind[0] == "he" else 1 / np.sqrt(fin)
+            return np.random.uniform(-limit, limit, shape)
+        if kind[-1] == "normal":
+            std = np.sqrt(2 / (fin + fout)) if kind[0] == "glorot" else np.sqrt(2 / fin) if kind[0] == "he" else 0.01
+            return np.random.normal(0, std, shape)
+        return np.zeros(shape)
+
+    def _initialize(self, optimizer):
+        self.weight = self._draw(self.kernel_initializer, (self.input_shape[0], self.neurons))
+        self.bias = self._draw(self.bias_initializer, (1, self.neurons))
+        self._weight_opt, self._bias_opt = copy.copy(optimizer), copy.copy(optimizer)
+
+    def n_params(self):
+        return int(np.prod(self.weight.shape) + np.prod(self.bias.shape))
+
+    def _forward_pass(self, x, training=True):
+        if training:
+            self.layer_input = x
+        return x.dot(self.weight) + self.bias
+
+    def _backward_pass(self, g):
+        weight = self.weight
+        if self.trainable:
+            grad_w = self.layer_input.T.dot(g)
+            grad_w0 = np.sum(g, axis=0, keepdims=True)
+            self.weight = self._weight_opt.update(self.weight, grad_w)
+            self.bias = self._bias_opt.update(self.bias, grad_w0)
+        return g.dot(weight.T)
+
+    def output_shape(self):
+        return (self.neurons,)
+
+
+class Dropout:
+    """net.py:691-727"""
+
+    def __init__(self, drop_rate, **unknown):
+        _no_unknown("Dropout Layer", unknown)
+        self.drop_rate, self._mask, self.input_shape, self.trainable = drop_rate, None, None, True
+
+    def _set_input_shape(self, shape):
+        self.input_shape = shape
+
+    def _forward_pass(self, x, training=True):
+        c = 1 - self.drop_rate
+        if training:
+            self._mask = np.random.uniform(size=x.shape) > self.drop_rate
+            c = self._mask
+        return x * c
+
+    def _backward_pass(self, g):
+        return g * self._mask
+
+    def output_shape(self):
+        return self.input_shape
+
+    def n_params(self):
+        return 0
+
+
+LAYERS = {"dense": Dense, "activation": Activation, "scale": Scale, "dropout": Dropout}
+
+
+class SGD:
+    def __init__(self, learning_rate=0.01, momentum=0, **unknown):
+        _no_unknown("SGD optimizer", unknown)
+        self.learning_rate, self.momentum, self.w_updt = learning_rate, momentum, None
+
+    def update(self, w, g):
+        if self.w_updt is None:
+            self.w_updt = np.zeros(np.shape(w))
+        self.w_updt = self.momentum * self.w_updt + (1 - self.momentum) * g
+        return w - self.learning_rate * self.w_updt
+
+
+class Adam:
+    """net.py:893-938 (the moment estimates are divided by (1 - b), not by (1 - b^t), as in the reference)"""
+
+    def __init__(self, learning_rate=0.001, b1=0.9, b2=0.999, **unknown):
+        _no_unknown("Adam optimizer", unknown)
+        self.learning_rate, self.eps, self.m, self.v, self.b1, self.b2 = learning_rate, 1e-8, None, None, b1, b2
+
+    def update(self, w, g):
+        if self.m is None:
+            self.m, self.v = np.zeros(np.shape(g)), np.zeros(np.shape(g))
+        self.m = self.b1 * self.m + (1 - self.b1) * g
+        self.v = self.b2 * self.v + (1 - self.b2) * np.power(g, 2)
+        m_hat, v_hat = self.m / (1 - self.b1), self.v / (1 - self.b2)
+        return w - self.learning_rate * m_hat / (np.sqrt(v_hat) + self.eps)
+
+
+class Adagrad:
+    def __init__(self, learning_rate=0.01, **unknown):
+        _no_unknown("Adagrad optimizer", unknown)
+        self.learning_rate, self.G, self.eps = learning_rate, None, 1e-8
+
+    def update(self, w, g):
+        if self.G is None:
+            self.G = np.zeros(np.shape(w))
+        self.G += np.power(g, 2)
+        return w - self.learning_rate * g / np.sqrt(self.G + self.eps)
+
+
+class RMSprop:
+    def __init__(self, learning_rate=0.001, rho=0.9, **unknown):
+        _no_unknown("RMSprop optimizer", unknown)
+        self.learning_rate, self.Eg, self.eps, self.rho = learning_rate, None, 1e-8, rho
+
+    def update(self, w, g):
+        if self.Eg is None:
+            self.Eg = np.zeros(np.shape(g))
+        self.Eg = self.rho * self.Eg + (1 - self.rho) * np.power(g, 2)
+        return w - self.learning_rate * g / np.sqrt(self.Eg + self.eps)
+
+
+OPT_FUNC = {"sgd": SGD, "adam": Adam, "adagrad": Adagrad, "rmsprop": RMSprop}
+
+
+class Net:
+    """net.py:22-436"""
+
+    def __init__(self):
+        self.layers, self.history = [], {"loss_train": []}
+        self._opt = self._optimizer = self._learning_rate = None
+        self._compiled = False
+
+    def add(self, layer, options):
+        if not isinstance(layer, str):
+            raise TypeError("layer argument must be str")
+        if layer.lower() not in LAYERS:
+            raise ValueError(f"Unknown layer type '{layer}'. Choices: {list(LAYERS)}")
+        lay = LAYERS[layer.lower()](**options)
+        if not self.layers:
+            if "input_shape" not in options:
+                raise TypeError("First layer missing required option argument: 'input_shape'")
+            if not isinstance(options["input_shape"], tuple):
+                raise ValueError(f"input_shape option should be a tuple, not {type(options['input_shape'])}")
+        else:
+            lay._set_input_shape(self.layers[-1].output_shape())
+        self.layers.append(lay)
+
+    def compile(self, optimizer="adam", options=None, random_state=None):
+        if not self.layers:
+            raise ValueError("The network does not contain layers")
+        if not isinstance(optimizer, str):
+            raise TypeError("optimizer argument must be str")
+        if optimizer.lower() not in OPT_FUNC:
+            raise ValueError(f"Unknown optimizer '{optimizer}'. Choices: {list(OPT_FUNC)}")
+        if random_state is not None:
+            np.random.seed(random_state)
+        opt = OPT_FUNC[optimizer.lower()](**(options or {}))
+        for layer in self.layers:
+            if hasattr(layer, "_initialize"):
+                layer._initialize(opt)
+        self._compiled, self._optimizer, self._learning_rate = True, optimizer.lower(), opt.learning_rate
+
+    def copy(self):
+        return copy.deepcopy(self)
+
+    def n_params(self):
+        return sum(layer.n_params() for layer in self.layers)
+
+    def _forward_pass(self, x, training=True):
+        for layer in self.layers:
+            x = layer._forward_pass(x, training)
+        return x
+
+    def _backward_pass(self, loss_grad):
+        for layer in reversed(self.layers):
+            loss_grad = layer._backward_pass(loss_grad)
+
+    def _predict(self, x):
+        return self._forward_pass(x, training=False)
+
+    def _fit_d2p(self, x_train, instance, control_vector, mask, parameters_bgd, states_bgd, epochs, early_stopping, verbose,
+                 solver=None):
+        """net.py:353-415"""
+        if not self._compiled:
+            raise ValueError("The network has not been compiled yet")
+        loss_opt = 0
+        for epo in range(epochs):
+            y_pred = self._forward_pass(x_train)
+            loss_grad = _hcost_prime(y_pred, control_vector, mask, instance, parameters_bgd, states_bgd, solver)
+            loss = instance.output.cost
+            if early_stopping and (loss_opt > loss or epo == 0):
+                loss_opt = loss
+                for layer in self.layers:
+                    if hasattr(layer, "_initialize"):
+                        layer._weight, layer._bias = np.copy(layer.weight), np.copy(layer.bias)
+            self._backward_pass(loss_grad)
+            if verbose:
+                print(f"    At epoch    {epo + 1:3}    J ={loss:10.6f}    |proj g| ={np.amax(np.abs(loss_grad)):10.6f}")
+            self.history["loss_train"].append(loss)
+        if early_stopping:
+            for layer in self.layers:
+                if hasattr(layer, "_initialize"):
+                    layer.weight, layer.bias = np.copy(layer._weight), np.copy(layer._bias)
+
+
+def _hcost_prime(y, control_vector, mask, instance, parameters_bgd, states_bgd, solver=None):
+    """net.py:1001-1056: predicted fields on the active cells, one ``forward_b``, gradient rows in the same cell order."""
+    sv = solver or _mw_forward
+    for i, name in enumerate(control_vector):
+        getattr(instance.parameters if name in GPARAMETERS_NAME else instance.states, name)[mask] = y[:, i]
+    parameters_b, states_b = instance.parameters.copy(), instance.states.copy()
+    sv.forward_b(instance.setup, instance.mesh, instance.input_data, instance.parameters, parameters_b, parameters_bgd,
+                 instance.parameters.copy(), instance.states, states_b, states_bgd, instance.states.copy(), instance.output,
+                 None, 0.0, 1.0)
+    return np.transpose([getattr(parameters_b if name in GPARAMETERS_NAME else states_b, name)[mask] for name in control_vector])

@@ -562,3 +562,57 @@ def bayes_optimize(model, sample=None, alpha=4, n=1000, random_state=None, de_bw
         algorithm = "sbs" if mapping == "uniform" else "l-bfgs-b"
     return _bayes(model, sample, alpha, n, random_state, de_bw_method, de_weights, mapping, algorithm, control_vector, bounds,
                   jobs_fun, wjobs_fun, gauge, wgauge, ost_step, options, inplace, return_br, solver, None)
+
+
+def ann_optimize(model, net=None, optimizer="adam", learning_rate=0.003, control_vector=None, bounds=None, jobs_fun="nse",
+                 wjobs_fun=None, gauge="downstream", wgauge="mean", ost_step=0, epochs=400, early_stopping=False,
+                 random_state=None, verbose=False, inplace=False, return_net=False, solver=None):
+    """Model.ann_optimize (model.py:1223-1420, simulation/_ann_optimize.py:20-254): a network maps the normalised
+    descriptors of the active cells to the control fields; every epoch is one ``forward_b`` on the GPU."""
+    from .net import Net
+    inst = model if inplace else model.copy()
+    _, cv = _setup_optimize(inst, "uniform", "sbs", control_vector, bounds, jobs_fun, wjobs_fun, gauge, wgauge, ost_step, verbose)
+    o = inst.setup._optimize
+    o.mapping = "..."
+    bnd = np.array([[(o.lb_parameters if c in GPARAMETERS_NAME else o.lb_states)[(GPARAMETERS_NAME if c in GPARAMETERS_NAME else GSTATES_NAME).index(c)],
+                     (o.ub_parameters if c in GPARAMETERS_NAME else o.ub_states)[(GPARAMETERS_NAME if c in GPARAMETERS_NAME else GSTATES_NAME).index(c)]]
+                    for c in cv], dtype=np.float32)
+    parameters_bgd, states_bgd = inst.parameters.copy(), inst.states.copy()
+    desc = inst.input_data.descriptor
+    nd = int(inst.setup._nd)
+    active, inactive = np.where(np.asarray(inst.mesh.active_cell) == 1), np.where(np.asarray(inst.mesh.active_cell) == 0)
+    dmin = np.array([np.amin(desc[..., i]) for i in range(nd)], dtype=np.float32)
+    dmax = np.array([np.amax(desc[..., i]) for i in range(nd)], dtype=np.float32)
+    norm = np.empty_like(desc)
+    for i in range(nd):                                                   # _normalize_descriptor (_optimize.py:801-811)
+        norm[..., i] = (desc[..., i] - dmin[i]) / (dmax[i] - dmin[i])
+    x_train, x_inactive = norm[active], norm[inactive]
+    if net is None:                                                       # auto-graph (_ann_optimize.py:140-180)
+        net = Net()
+        n_neurons = round(np.sqrt(len(x_train) * nd) * 2 / 3)
+        net.add("dense", {"input_shape": (nd,), "neurons": n_neurons, "kernel_initializer": "glorot_uniform"})
+        net.add("activation", {"name": "relu"})
+        net.add("dense", {"neurons": round(n_neurons / 2), "kernel_initializer": "glorot_uniform"})
+        net.add("activation", {"name": "relu"})
+        net.add("dense", {"neurons": cv.size, "kernel_initializer": "glorot_uniform"})
+        net.add("activation", {"name": "sigmoid"})
+        net.add("scale", {"bounds": bnd})
+        net.compile(optimizer=optimizer, random_state=random_state, options={"learning_rate": learning_rate})
+    elif not isinstance(net, Net):
+        raise ValueError(f"Unknown network {net}")
+    elif not net.layers:
+        raise ValueError("The graph has not been set yet")
+    else:
+        if net.layers[0].input_shape[0] != nd:
+            raise ValueError(f"Inconsistent value between the number of input layer ({net.layers[0].input_shape}) and the "
+                             f"number of descriptors ({nd})")
+        if net.layers[-1].output_shape()[0] != cv.size:
+            raise ValueError(f"Inconsistent value between the number of output layer ({net.layers[-1].output_shape()}) and "
+                             f"the number of control vectors ({cv.size})")
+    net._fit_d2p(x_train, inst, cv, active, parameters_bgd, states_bgd, epochs, early_stopping, verbose, solver=solver)
+    y = net._predict(x_inactive)                                         # predicted maps on the inactive cells
+    for i, name in enumerate(cv):
+        getattr(inst.parameters if name in GPARAMETERS_NAME else inst.states, name)[inactive] = y[:, i]
+    if return_net:
+        return net if inplace else (inst, net)
+    return None if inplace else inst

@@ -171,3 +171,47 @@ def test_bayes_optimize_golden_cpu(golden):
 @pytest.mark.gpu
 def test_bayes_estimate_golden_gpu(golden):
     _bayes_estimate(golden, None, None, COST_ATOL_GPU)
+
+
+# ------------------------------------------------------------------------------------------ ANN mapping
+def _ann_1(golden, solver, atol):
+    # generic_ann_optimize_1 (test_simu.py:271-289): auto-graph 2 -> 18 -> 9 -> 4, Adam
+    inst, net = simulation.ann_optimize(cases.cance(), epochs=5, learning_rate=0.001, return_net=True, random_state=11,
+                                        solver=solver)
+    assert [getattr(l, "neurons", None) for l in net.layers if hasattr(l, "neurons")] == [18, 9, 4] and net.n_params() == 265
+    loss = np.array(net.history["loss_train"])
+    print("ann_optimize_1.loss max diff", np.abs(loss - golden["ann_optimize_1.loss"]).max())
+    assert np.allclose(loss, golden["ann_optimize_1.loss"], atol=atol)
+    assert np.allclose(_cost(inst), golden["ann_optimize_1.cost"], atol=atol)
+
+
+def _ann_2(golden, solver, atol):
+    # generic_ann_optimize_2 (test_simu.py:292-330): user graph, SGD with momentum
+    from smash_b200.net import Net
+    m = cases.cance()
+    problem = simulation.get_bound_constraints(m, states=False)
+    net = Net()
+    net.add(layer="dense", options={"input_shape": (2,), "neurons": 16})
+    net.add(layer="activation", options={"name": "relu"})
+    net.add(layer="dense", options={"neurons": 8})
+    net.add(layer="activation", options={"name": "relu"})
+    net.add(layer="dense", options={"neurons": problem["num_vars"]})
+    net.add(layer="activation", options={"name": "sigmoid"})
+    net.add(layer="scale", options={"bounds": problem["bounds"]})
+    net.compile(optimizer="sgd", options={"learning_rate": 0.01, "momentum": 0.001}, random_state=11)
+    inst = simulation.ann_optimize(m, net=net, epochs=5, solver=solver)
+    loss = np.array(net.history["loss_train"])
+    print("ann_optimize_2.loss max diff", np.abs(loss - golden["ann_optimize_2.loss"]).max())
+    assert np.allclose(loss, golden["ann_optimize_2.loss"], atol=atol)
+    assert np.allclose(_cost(inst), golden["ann_optimize_2.cost"], atol=atol)
+
+
+def test_ann_optimize_golden_cpu(golden):
+    _ann_1(golden, oracle_solver, COST_ATOL)
+    _ann_2(golden, oracle_solver, COST_ATOL)
+
+
+@pytest.mark.gpu
+def test_ann_optimize_golden_gpu(golden):
+    _ann_1(golden, None, COST_ATOL_GPU)
+    _ann_2(golden, None, COST_ATOL_GPU)
