@@ -324,6 +324,28 @@ def main():
             ens()
         barrier()
         dte = max_over_ranks(time.perf_counter() - t0) / 3
+        # configs[4]: regionalised calibration, one Cance-sized catchment per rank, shared hyper-polynomial mapping,
+        # one all-reduce of (cost, gradient) per evaluation
+        def catchment():
+            mk = cases.cance()
+            mk.input_data.qobs = np.asfortranarray(mk.input_data.qobs * np.float32(1.0 + 0.05 * rank))
+            mk.input_data._forcing_version = 100 + rank
+            cases.set_optimize(mk.setup, mk.mesh, jobs_fun=("nse",), mapping="hyper-polynomial")
+            mk.setup._optimize.optim_parameters[[1, 3, 6, 15]] = 1
+            mk.setup._optimize.maxiter = 10
+            mk.setup._optimize.verbose = False
+            return mk
+        mk = catchment()
+        sdist.optimize_hyper_lbfgsb_sharded([(mk.setup, mk.mesh, mk.input_data, mk.parameters, mk.states, mk.output)])
+        mk = catchment()
+        barrier()
+        t0 = time.perf_counter()
+        sdist.optimize_hyper_lbfgsb_sharded([(mk.setup, mk.mesh, mk.input_data, mk.parameters, mk.states, mk.output)])
+        barrier()
+        dtr = max_over_ranks(time.perf_counter() - t0)
+        extra["regional_hyper_polynomial_lbfgsb"] = {"catchments": world, "iterations": 10, "wall_s": dtr,
+                                                     "s_per_iteration": dtr / 10, "collective": "all-reduce of 21 float64 per evaluation",
+                                                     "rank0_cost": float(mk.output.cost)}
         extra["cance_ensemble_4096_sharded"] = {"cell_timesteps_per_s_e2e": ns * 383 * 1440 / dte, "ms_per_call": dte * 1e3,
                                                 "members_per_rank": ns // world, "scaling": "strong",
                                                 "cost_checksum": float(np.sum(cost[np.isfinite(cost)], dtype=np.float64))}

@@ -93,3 +93,28 @@ def allreduce_shared_gradient(cost, hyper_parameters_b, hyper_states_b, group=No
         getattr(obj, n)[...] = flat[k:k + size].reshape(shp, order="F")
         k += size
     return np.float32(flat[0])
+
+
+def optimize_hyper_lbfgsb_sharded(catchments, group=None, solver=None):
+    """Regionalised multi-catchment calibration with the catchments spread over the ranks of ``group``: every rank passes
+    its own ``(setup, mesh, input_data, parameters, states, output)`` tuples, the summed cost and shared hyper-parameter
+    gradient travel in ONE all-reduce of ``1 + n_control * nhyper`` values per evaluation (plus one min / max all-reduce
+    of the descriptor extrema at the start), and every rank walks the same L-BFGS-B path
+    (``smash_b200.solver._mw_optimize.optimize_hyper_lbfgsb_multi``)."""
+    import torch
+    from .solver._mw_optimize import optimize_hyper_lbfgsb_multi
+    dist = _dist()
+    dev = _device(group)
+
+    def reduce_sum(vec):
+        t = torch.from_numpy(np.asarray(vec, dtype=np.float64)).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return t.cpu().numpy()
+
+    def reduce_minmax(mins, maxs):
+        lo, hi = torch.from_numpy(np.asarray(mins, np.float32)).to(dev), torch.from_numpy(np.asarray(maxs, np.float32)).to(dev)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+        return lo.cpu().numpy(), hi.cpu().numpy()
+
+    return optimize_hyper_lbfgsb_multi(catchments, solver=solver, reduce_sum=reduce_sum, reduce_minmax=reduce_minmax)

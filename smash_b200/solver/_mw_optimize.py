@@ -357,28 +357,47 @@ def optimize_lbfgsb(setup, mesh, input_data, parameters, states, output, *, solv
 def optimize_hyper_lbfgsb(setup, mesh, input_data, parameters, states, output, *, solver=None):
     """mw_optimize.f90:779-958.  Descriptors are normalised to [0, 1] for the duration of the optimisation and
     restored afterwards (:960-999); the control holds ``nhyper`` coefficients per optimised field."""
+    return optimize_hyper_lbfgsb_multi([(setup, mesh, input_data, parameters, states, output)], solver=solver)
+
+
+def optimize_hyper_lbfgsb_multi(catchments, *, solver=None, reduce_sum=None, reduce_minmax=None):
+    """Regionalised calibration over several catchments that share one hyper-parameter set: minimises the SUM of the
+    catchments' costs with the driver of ``optimize_hyper_lbfgsb`` (one catchment = the reference's subroutine).
+
+    ``catchments`` is a list of ``(setup, mesh, input_data, parameters, states, output)``; every ``setup._optimize`` holds
+    the same mapping, control vector, bounds and ``maxiter``, and the catchments start from the same uniform background.
+    Descriptors are normalised with the extrema over ALL catchments, so that a coefficient means the same everywhere.
+    ``reduce_sum(vector) -> vector`` and ``reduce_minmax(mins, maxs) -> (mins, maxs)`` combine the local values with
+    those of other processes (``smash_b200.distributed``: one small all-reduce per evaluation); with them every process
+    sees the same cost and gradient and therefore walks the same L-BFGS-B path."""
     sv = solver or _mw_forward
+    setup = catchments[0][0]
     o = setup._optimize
     nh = int(o.nhyper)
+    nd = int(setup._nd)
     optim, lb, ub = _optim_flags(setup)
     idx = np.flatnonzero(optim > 0)
     n = idx.size * nh
 
-    desc = input_data.descriptor
-    dmin = np.array([desc[:, :, i].min() for i in range(setup._nd)], dtype=f32)
-    dmax = np.array([desc[:, :, i].max() for i in range(setup._nd)], dtype=f32)
-    for i in range(setup._nd):                                            # :960-980
-        desc[:, :, i] = (desc[:, :, i] - dmin[i]) / (dmax[i] - dmin[i])
+    dmin = np.array([min(c[2].descriptor[:, :, i].min() for c in catchments) for i in range(nd)], dtype=f32)
+    dmax = np.array([max(c[2].descriptor[:, :, i].max() for c in catchments) for i in range(nd)], dtype=f32)
+    if reduce_minmax is not None:
+        dmin, dmax = reduce_minmax(dmin, dmax)
+    for c in catchments:                                                  # :960-980
+        for i in range(nd):
+            c[2].descriptor[:, :, i] = (c[2].descriptor[:, :, i] - dmin[i]) / (dmax[i] - dmin[i])
 
     try:
         hyper_parameters, hyper_states = Hyper_ParametersDT(setup), Hyper_StatesDT(setup)
-        hyper_parameters_b, hyper_states_b = Hyper_ParametersDT(setup), Hyper_StatesDT(setup)
-        parameters_b, states_b = ParametersDT(mesh), StatesDT(mesh)
         hplanes = _planes(hyper_parameters, hyper_states)
+        work = []                                                         # per catchment: gradient holders
+        for c in catchments:
+            work.append((Hyper_ParametersDT(c[0]), Hyper_StatesDT(c[0]), ParametersDT(c[1]), StatesDT(c[1])))
 
         # problem_initialise_hyper_lbfgsb :1001-1096
-        r0, c0 = _first_active(mesh)
-        v = np.array([p[r0, c0] for p in _planes(parameters, states)], dtype=f32)
+        _, mesh0, _, parameters0, states0, _ = catchments[0]
+        r0, c0 = _first_active(mesh0)
+        v = np.array([p[r0, c0] for p in _planes(parameters0, states0)], dtype=f32)
         first = np.log(np.maximum(f32(1e-8), v - lb) / np.maximum(f32(1e-8), ub - v)).astype(f32)
         nbd, l, u = np.zeros(n, np.int32), np.zeros(n), np.zeros(n)
         for i in range(GNP + GNS):
@@ -404,19 +423,32 @@ def optimize_hyper_lbfgsb(setup, mesh, input_data, parameters, states, output, *
             for j, i in enumerate(idx):
                 hplanes[i][:, 0] = x[j * nh:(j + 1) * nh].astype(f32)
 
+        single = len(catchments) == 1 and reduce_sum is None
+
         def fg():
-            cost = sv.hyper_forward_b(setup, mesh, input_data, parameters, parameters_b, hyper_parameters, hyper_parameters_b,
-                                      hyper_parameters_bgd, None, states, states_b, hyper_states, hyper_states_b,
-                                      hyper_states_bgd, None, output, None, 0.0, 1.0)
-            return cost, var_to_control(hyper_parameters_b, hyper_states_b)
+            if single:
+                (su, me, inp, par, sta, out), (hp_b, hs_b, par_b, sta_b) = catchments[0], work[0]
+                cost = sv.hyper_forward_b(su, me, inp, par, par_b, hyper_parameters, hp_b, hyper_parameters_bgd, None, sta,
+                                          sta_b, hyper_states, hs_b, hyper_states_bgd, None, out, None, 0.0, 1.0)
+                return cost, var_to_control(hp_b, hs_b)
+            acc = np.zeros(n + 1, dtype=np.float64)
+            for (su, me, inp, par, sta, out), (hp_b, hs_b, par_b, sta_b) in zip(catchments, work):
+                cost = sv.hyper_forward_b(su, me, inp, par, par_b, hyper_parameters, hp_b, hyper_parameters_bgd, None, sta,
+                                          sta_b, hyper_states, hs_b, hyper_states_bgd, None, out, None, 0.0, 1.0)
+                acc[0] += float(cost)
+                acc[1:] += var_to_control(hp_b, hs_b)
+            if reduce_sum is not None:
+                acc = np.asarray(reduce_sum(acc), dtype=np.float64)
+            return f32(acc[0]), acc[1:]
 
         sb = _Setulb(n, 10, 1e6, 1e-12, var_to_control(hyper_parameters, hyper_states), l, u, nbd)
-        msg = _drive_lbfgsb(sb, setup, output, control_to_var, fg)
+        msg = _drive_lbfgsb(sb, setup, catchments[0][5], control_to_var, fg)
         # hyper_forward maps the hyper control to parameters / states in place (forward.f90:117-121), which is
         # what hyper_parameters_to_parameters / hyper_states_to_states repeat at :953-954
-        sv.hyper_forward(setup, mesh, input_data, parameters, hyper_parameters, hyper_parameters_bgd, states, hyper_states,
-                         hyper_states_bgd, output)
+        for su, me, inp, par, sta, out in catchments:
+            sv.hyper_forward(su, me, inp, par, hyper_parameters, hyper_parameters_bgd, sta, hyper_states, hyper_states_bgd, out)
     finally:
-        for i in range(setup._nd):                                        # :982-999
-            desc[:, :, i] = desc[:, :, i] * (dmax[i] - dmin[i]) + dmin[i]
+        for c in catchments:                                              # :982-999
+            for i in range(nd):
+                c[2].descriptor[:, :, i] = c[2].descriptor[:, :, i] * (dmax[i] - dmin[i]) + dmin[i]
     return msg

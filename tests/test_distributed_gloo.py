@@ -61,3 +61,58 @@ def test_sharded_ensemble_and_allreduce_world2():
         assert np.allclose(ret["qsim"], want)
         assert ret["total"] == 0.5 + 1.5
         assert np.all(ret["cp"] == 3.0) and np.all(ret["hlr"] == 30.0)
+
+
+def _catchment(k):
+    """Two distinct 'catchments' for the regionalisation test: the Cance mesh over different periods / observations."""
+    import cases
+    m = cases.cance(T=240 if k == 0 else 300)
+    if k == 1:
+        m.input_data.qobs = np.asfortranarray(m.input_data.qobs * np.float32(1.2))
+    cases.set_optimize(m.setup, m.mesh, jobs_fun=("nse",), mapping="hyper-polynomial")
+    o = m.setup._optimize
+    o.optim_parameters[[1, 3, 6, 15]] = 1                                  # cp, cft, exc, lr
+    o.maxiter = 3
+    o.verbose = False
+    return m
+
+
+def _as_tuple(m):
+    return (m.setup, m.mesh, m.input_data, m.parameters, m.states, m.output)
+
+
+def _regional_worker(rank, world, port, ret):
+    import torch.distributed as dist
+
+    import oracle_solver
+    from smash_b200 import distributed as D
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = _catchment(rank)
+    D.optimize_hyper_lbfgsb_sharded([_as_tuple(m)], solver=oracle_solver)
+    ret[rank] = (float(m.output.cost), m.parameters.cp.copy(), m.parameters.lr.copy())
+    dist.destroy_process_group()
+
+
+def test_regionalised_calibration_world2_equals_single_process():
+    # configs[4]: catchments spread over ranks, shared hyper-parameters, one all-reduce of (cost, gradient) per evaluation.
+    # Two ranks with one catchment each must walk the same L-BFGS-B path as one process holding both.
+    import oracle_solver
+    from smash_b200.solver import _mw_optimize
+    a, b = _catchment(0), _catchment(1)
+    d0 = a.input_data.descriptor.copy()
+    _mw_optimize.optimize_hyper_lbfgsb_multi([_as_tuple(a), _as_tuple(b)], solver=oracle_solver)
+    assert np.allclose(a.input_data.descriptor, d0, rtol=1e-6)              # descriptors restored
+    first = _catchment(0)
+    oracle_solver.forward(first.setup, first.mesh, first.input_data, first.parameters, first.parameters.copy(), first.states,
+                          first.states.copy(), first.output)
+    assert float(a.output.cost) < float(first.output.cost)                  # the shared mapping improved catchment 0
+    assert np.ptp(a.parameters.cp[a.mesh.active_cell == 1]) > 0             # and it is spatially distributed
+    assert np.array_equal(a.parameters.cp, b.parameters.cp)                 # same mapping, same descriptors -> same field
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_regional_worker, args=(2, 29600 + os.getpid() % 1000, ret), nprocs=2, join=True)
+        for rank, m in ((0, a), (1, b)):
+            cost, cp, lr = ret[rank]
+            assert np.isclose(cost, float(m.output.cost), rtol=1e-6)
+            assert np.allclose(cp, m.parameters.cp, rtol=1e-6) and np.allclose(lr, m.parameters.lr, rtol=1e-6)
