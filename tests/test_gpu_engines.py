@@ -95,12 +95,22 @@ def test_streamed_forward_agrees():
                 smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states,
                                    m.states.copy(), m.output)
                 assert np.array_equal(first, m.output.sparse_qsim_domain)
+            # the gradient through the same cached plan (256-step routing windows when streaming is on)
+            m.grad = (ParametersDT(m.mesh), StatesDT(m.mesh))
+            g = cases.france(T=600, sub=(400, 560, 400, 560), ngauge=3)
+            random_fields(g, seed=7)
+            smash_b200.forward_b(g.setup, g.mesh, g.input_data, g.parameters, m.grad[0], g.parameters.copy(), None, g.states,
+                                 m.grad[1], g.states.copy(), None, g.output, None)
+            m.grad_cost = float(g.output.cost)
             return m
         finally:
             lib.smash_b200_set_option(b"stream", 1)
             lib.smash_b200_set_option(b"stream_min_mb", 256)
             lib.smash_b200_clear_cache()
     a, b = run(1), run(0)
+    assert np.isclose(a.grad_cost, b.grad_cost, rtol=1e-5)
+    check_grad(a.grad[0], b.grad[0], ("cp", "cft", "exc", "lr"))
+    check_grad(a.grad[1], b.grad[1], ("hp", "hft", "hlr"))
     assert a.mesh.nac % 4 == 0, a.mesh.nac                                   # else the streamed path is not taken
     run(1, version=77)
     for x, y in ((a.output.qsim, b.output.qsim), (a.output.sparse_qsim_domain, b.output.sparse_qsim_domain),
