@@ -90,7 +90,7 @@ struct SplitState {
     RouteGraph rg;
     int S = 0, W = 0, nwin = 0, Tp = 0;
     int64_t qpitch = 0;
-    DBuf<int32_t> d_flwacc, d_up_begin, d_down, d_down_task, d_down_need, d_rlist, d_rindex, d_task_begin, d_task_cells, d_gfirst, d_gnext;
+    DBuf<int32_t> d_flwacc, d_up_begin, d_down, d_down_task, d_down_need, d_rlist, d_rindex, d_task_begin, d_task_cells, d_gfirst, d_gnext, d_cell_task;
     DBuf<RouteUp> d_up, d_tup;
     DBuf<TaskCell> d_tcell;
     DBuf<uint8_t> d_down_lag;
@@ -256,7 +256,7 @@ static int plan_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *m
     TRY(pl.d_gfirst.upload(tp.gauge_first, s)); TRY(pl.d_gnext.upload(tp.gauge_next, s));
     TRY(pl.d_hmax.upload(tp.hmax, s)); TRY(pl.d_tick_base.upload(tp.tick_base, s)); TRY(pl.d_bflags.upload(tp.flags, s));
     TRY(pl.d_sparse_k.upload(tp.sparse_k, s));
-    TRY(pl.d_ticket.ensure(1)); TRY(pl.d_sum.ensure(1));
+    TRY(pl.d_ticket.ensure(2)); TRY(pl.d_sum.ensure(1));
     DeviceTopology &d = pl.dtp;
     d.T = tp.T; d.B = tp.B; d.nblocks = tp.nblocks; d.nslots = tp.nslots; d.ng = tp.ng; d.total_ticks = tp.total_ticks;
     d.cell = pl.d_cell.p; d.off = pl.d_off.p; d.flwacc = pl.d_flwacc.p; d.late = pl.d_late.p; d.early = pl.d_early.p;
@@ -334,12 +334,15 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     for (int j = 0; j < rg.n; j++) if (rg.flwacc[j] > 1) { rindex[j] = (int32_t)rlist.size(); rlist.push_back(j); }
     TRY(sp.d_rlist.upload(rlist, s)); TRY(sp.d_rindex.upload(rindex, s));
     TRY(sp.d_tcell.upload(rg.tcell, s)); TRY(sp.d_tup.upload(rg.tup, s));
-    TRY(pl.d_ticket.ensure(1)); TRY(pl.d_sum.ensure(1));
+    std::vector<int32_t> cell_task(npad, -1);
+    for (int j = 0; j < rg.n; j++) cell_task[j] = rg.cell_task[j];
+    TRY(sp.d_cell_task.upload(cell_task, s));
+    TRY(pl.d_ticket.ensure(2)); TRY(pl.d_sum.ensure(1));
     SplitTopo &t = sp.topo;
     t.n = rg.n; t.npad = npad; t.ng = mesh->ng; t.ntask = rg.ntask; t.nchain = rg.nchain; t.nded = rg.nded;
     t.flwacc = sp.d_flwacc.p; t.up_begin = sp.d_up_begin.p; t.up = sp.d_up.p; t.down = sp.d_down.p; t.down_task = sp.d_down_task.p; t.down_need = sp.d_down_need.p;
     t.down_lag = sp.d_down_lag.p; t.task_begin = sp.d_task_begin.p; t.task_cells = sp.d_task_cells.p;
-    t.gauge_first = sp.d_gfirst.p; t.gauge_next = sp.d_gnext.p;
+    t.gauge_first = sp.d_gfirst.p; t.gauge_next = sp.d_gnext.p; t.cell_task = sp.d_cell_task.p;
     t.nrouted = (int)rlist.size(); t.rlist = sp.d_rlist.p; t.rindex = sp.d_rindex.p;
     t.tcell = reinterpret_cast<const int4 *>(sp.d_tcell.p); t.tup = reinterpret_cast<const int2 *>(sp.d_tup.p);
     // the field gather kernel only needs the column -> cell map
@@ -428,6 +431,7 @@ static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp) {
     }
     a.save_q = save_q ? 1 : 0; a.save_netp = save_netp ? 1 : 0;
     a.river_wave = (int)option("river_wave", 0);
+    a.fuse_export = 0;
     a.fields = pl.d_fields.p; a.fstates = pl.d_fstates.p; a.rows = sp.d_rows.p; a.qdom = pl.d_qdom.p; a.netp = pl.d_netp.p;
     a.qpitch = sp.qpitch; a.qsim = pl.d_qsim.p; a.tape_hp = sp.d_tape_hp.p; a.tape_hft = sp.d_tape_hft.p; a.rows_hr = sp.d_rows_hr.p;
     a.hcar = sp.d_hcar.p; a.done = sp.d_done.p; a.ticket = pl.d_ticket.p; a.qsim_b = pl.d_qsim_b.p; a.rows_w = sp.d_rows_w.p;
@@ -450,11 +454,13 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
     mark(1);
     // ensembles on a small mesh: lane = member, exact sequential routing; otherwise the per-chain scan
     const bool by_member = pl.ensemble && sp.rg.npair == 0 && a.tp.nrouted <= 12000;   // whatever the size of this launch
+    // the routing warps export the routed cells' series themselves, in the shadow of the river walks (option fuse_export)
+    a.fuse_export = (save_q && !by_member && option("fuse_export", 1) != 0) ? 1 : 0;
     if (by_member) CU(launch_route_members(a, tape, pl.stream));
     else CU(launch_route_forward(a, tape, pl.stream));
     mark(2);
     pl.launches += 1 + sp.nwin * (1 + (sp.rg.npair > 0 ? 1 : 0));   // reservoir pass + per window: chains (+ pit pairs)
-    if (save_q) { CU(launch_rows_to_domain(a, pl.stream)); pl.launches++; }
+    if (save_q && !a.fuse_export) { CU(launch_rows_to_domain(a, pl.stream)); pl.launches++; }
     mark(3);
     return 0;
 }
@@ -918,9 +924,10 @@ static int forward_streamed(SmashPlan &pl, const SmashSetup *setup, const SmashM
         }
         a.t_begin = t0; a.t_end = t1;
         CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), false, pl.stream));
+        a.fuse_export = (save_q && option("fuse_export", 1) != 0) ? 1 : 0;
         CU(launch_route_forward_window(a, w, false, pl.stream));
         pl.launches += 2 + (sp.rg.npair > 0 ? 1 : 0);
-        if (save_q) { CU(launch_rows_to_domain(a, pl.stream)); pl.launches++; }
+        if (save_q && !a.fuse_export) { CU(launch_rows_to_domain(a, pl.stream)); pl.launches++; }
         CU(cudaEventRecord(pl.ev_cmp[w], pl.stream));
         if (hq || hn) CU(cudaStreamWaitEvent(pl.s_out, pl.ev_cmp[w], 0));
         if (hq) CU(cudaMemcpyAsync(hq + off, pl.d_qdom.p + (size_t)t0 * sp.qpitch, cnt * sizeof(float), cudaMemcpyDeviceToHost, pl.s_out));

@@ -459,6 +459,15 @@ __device__ __noinline__ void route_pair(const SplitArgs &a, int m, const int4 re
     float *rows = a.rows + (size_t)m * npad * a.Tp + t_first;
     st_row<S>(rows + (size_t)jA * a.Tp, qA);
     st_row<S>(rows + (size_t)jB * a.Tp, qB);
+    if (a.fuse_export) {                                                 // the routing warps leave the pit cells to their own kernel
+        float *qd = a.qdom + (size_t)m * a.T * a.qpitch;
+#pragma unroll
+        for (int s = 0; s < S; s++)
+            if (t_first + s < a.T) {
+                qd[(size_t)(t_first + s) * a.qpitch + jA] = qA[s];
+                qd[(size_t)(t_first + s) * a.qpitch + jB] = qB[s];
+            }
+    }
     if (TAPE) {
         float *hr = a.rows_hr + (size_t)m * npad * a.Tp + t_first;
         st_row<S>(hr + (size_t)jA * a.Tp, latA);
@@ -1058,6 +1067,43 @@ __device__ __forceinline__ void route_chain_wave(const SplitArgs &a, WaveShared 
     }
 }
 
+// Export of a tile of 32 consecutive cells to the domain layout qdom[t][cell], done by a routing warp once the chains that
+// own the tile's cells have finished this window (fuse_export): the transposition runs in the shadow of the serial walks
+// down the main rivers instead of in a kernel of its own.  Source cells were written by the reservoir pass already.
+template <int S>
+__device__ __forceinline__ void export_tile(const SplitArgs &a, float *tile, int m, int j0, int w, int lane, int epoch) {
+    constexpr int TC = 2 * S, P = TC + 1;                    // steps per chunk; padded pitch of the shared tile [32][P]
+    const SplitTopo &tp = a.tp;
+    const int j = j0 + lane;
+    const int task = j < tp.n ? tp.cell_task[j] : -1;
+    const bool mine = j < tp.n && tp.flwacc[j] > 1 && task < tp.nchain;      // pit pairs are routed (and exported) afterwards
+    if (mine) {
+        if (task >= 0) {
+            const int *flag = a.done + (size_t)m * tp.ntask + task;
+            while (ld_acquire(flag) < epoch) __nanosleep(128);
+        }
+    }
+    __syncwarp();
+    const int t_lo = w * a.W, t_hi = min(a.T, (w + 1) * a.W);
+    const float *rows = a.rows + ((size_t)m * tp.npad + j0) * a.Tp;
+    float *qd = a.qdom + (size_t)m * a.T * a.qpitch + j;
+#pragma unroll 1
+    for (int t0 = t_lo; t0 < t_hi; t0 += TC) {
+#pragma unroll 8
+        for (int k = 0; k < TC; k++) {                       // element e = cell * TC + step: consecutive lanes, consecutive steps
+            const int e = k * 32 + lane, i = e / TC, sidx = e - i * TC;
+            tile[i * P + sidx] = (j0 + i < tp.n) ? __ldcs(rows + (size_t)i * a.Tp + t0 + sidx) : 0.0f;   // rows are padded to Tp
+        }
+        __syncwarp();
+        if (mine) {
+            const int nt = min(TC, t_hi - t0);
+#pragma unroll 4
+            for (int tt = 0; tt < nt; tt++) qd[(size_t)(t0 + tt) * a.qpitch] = tile[lane * P + tt];
+        }
+        __syncwarp();
+    }
+}
+
 // Tasks [0, nchain - nded) are claimed through the ticket, in dependency order, one warp per chain (lane = S steps).
 // The nded longest chains (main rivers) have a CTA each (the first CTAs of the grid; thread = S/4 steps): they start at
 // once and advance as their tributaries finish instead of queueing behind the rest of their basin -- a long chain is a
@@ -1094,6 +1140,20 @@ __global__ void __launch_bounds__(128, 3) route_forward_kernel(const SplitArgs a
         tk_next = claim_ticket(a.ticket, lane);            // the next ticket travels while this task is routed
         const int m = tk / nticket, task = tk - m * nticket;
         route_chain_warp<S, TAPE>(a, stg, m, task, w, lane, t_first, epoch);
+    }
+    if (a.fuse_export) {
+        // every chain has been claimed: an export tile only ever waits for chains that are running or done
+        const int j_first = (a.first_routed / 32) * 32;
+        const int ntile = (tp.n - j_first + 31) / 32;
+        const int total_e = ntile * a.nmember;
+        static_assert(sizeof(RowStage<S>) >= 32 * (2 * S + 1) * sizeof(float), "export tile does not fit the warp's staging area");
+        float *tile = reinterpret_cast<float *>(&stg);
+        for (;;) {
+            const int tk = claim_ticket(a.ticket + 1, lane);
+            if (tk >= total_e) break;
+            const int m = tk / ntile, tl = tk - m * ntile;
+            export_tile<S>(a, tile, m, j_first + 32 * tl, w, lane, epoch);
+        }
     }
 }
 
@@ -1660,7 +1720,7 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
     if (blocks > need) blocks = need > 0 ? (int)need : 1;
     if (blocks <= ded_blocks) return cudaErrorLaunchOutOfResources;
     for (int w = w_begin; w < w_end; w++) {
-        e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), s);
+        e = cudaMemsetAsync(a.ticket, 0, 2 * sizeof(unsigned int), s);
         if (e != cudaSuccess) return e;
         if (tape) route_forward_kernel<S, 1><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
         else route_forward_kernel<S, 0><<<blocks, 128, 0, s>>>(a, w, ded_blocks);

@@ -36,6 +36,7 @@ struct SplitTopo {
     int nrouted;                 // cells with flwacc > 1
     const int32_t *rlist;        // [nrouted] routed cells in path order (a topological order)
     const int32_t *rindex;       // [npad] position in rlist or -1
+    const int32_t *cell_task;    // [npad] task that routes the cell, -1 for lone source cells and padding
     const int32_t *gauge_first;  // [npad]
     const int32_t *gauge_next;   // [ng]
 };
@@ -48,6 +49,7 @@ struct SplitArgs {
     int nmember;
     float dt, dx;
     int save_q, save_netp;
+    int fuse_export;             // 1: the routing warps also write the routed cells' series to qdom ([t][cell]) once their chains are done
     int river_wave;              // 1: dedicated chains run the tick wavefront (thread = cells), 0: whole-window scan per cell
     unsigned long long *dbg_prof;  // diagnostics: per dedicated chain [cells, cycles, cycles waiting for tributaries, end time ns], or nullptr
     const float *fields;         // [m][NFIELD][npad]
@@ -61,7 +63,7 @@ struct SplitArgs {
     float *rows_hr;              // [m][npad][Tp]   hr_imd = hlr0 + qup of the routed cells (gradient runs)
     float *hcar;                 // [m][npad]       routing state carried across windows (starts as the hlr field)
     int *done;                   // [m][ntask]      forward: windows finished by each task
-    unsigned int *ticket;
+    unsigned int *ticket;        // [2] chain tickets, export-tile tickets
     // adjoint
     const float *qsim_b;         // [m][T][ng]
     float *rows_w;               // [m][npad][Tp]   s * hr_imd_b of the routed cells (UPSTREAM_DISCHARGE_B)
