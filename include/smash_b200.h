@@ -168,7 +168,10 @@ void smash_b200_clear_cache(void);           /* drop cached mesh plans and devic
  * routed as pipelined tick wavefronts (thread = cell, strictly sequential arithmetic) instead of a window scan per cell
  * (experimental: slower than the default on the France mesh); "stream" 1 (default) = forward runs
  * whose sparse forcing is at least "stream_min_mb" (256) megabytes are cut into 256-step windows so that the forcing upload,
- * the kernels and the download of sparse_qsim_domain overlap on three streams (effective with page-locked arrays). */
+ * the kernels and the download of sparse_qsim_domain overlap on three streams (effective with page-locked arrays);
+ * "fuse_export" (default 4) = warps per routing CTA that, once every chain has been claimed, also write the routed cells'
+ * series to the [t][cell] domain layout as the chains owning a tile of 32 cells finish, in the shadow of the serial walks
+ * down the main rivers; 0 = separate rows_to_domain kernel after the routing pass. */
 int smash_b200_set_option(const char *name, long long value);
 
 /* ---- device-resident plan API (bench / advanced callers) --------------------------------------

@@ -455,7 +455,7 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
     // ensembles on a small mesh: lane = member, exact sequential routing; otherwise the per-chain scan
     const bool by_member = pl.ensemble && sp.rg.npair == 0 && a.tp.nrouted <= 12000;   // whatever the size of this launch
     // the routing warps export the routed cells' series themselves, in the shadow of the river walks (option fuse_export)
-    a.fuse_export = (save_q && !by_member && option("fuse_export", 1) != 0) ? 1 : 0;
+    a.fuse_export = (save_q && !by_member) ? (int)option("fuse_export", 4) : 0;
     if (by_member) CU(launch_route_members(a, tape, pl.stream));
     else CU(launch_route_forward(a, tape, pl.stream));
     mark(2);
@@ -924,7 +924,7 @@ static int forward_streamed(SmashPlan &pl, const SmashSetup *setup, const SmashM
         }
         a.t_begin = t0; a.t_end = t1;
         CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), false, pl.stream));
-        a.fuse_export = (save_q && option("fuse_export", 1) != 0) ? 1 : 0;
+        a.fuse_export = save_q ? (int)option("fuse_export", 4) : 0;
         CU(launch_route_forward_window(a, w, false, pl.stream));
         pl.launches += 2 + (sp.rg.npair > 0 ? 1 : 0);
         if (save_q && !a.fuse_export) { CU(launch_rows_to_domain(a, pl.stream)); pl.launches++; }

@@ -1097,7 +1097,7 @@ __device__ __forceinline__ void export_tile(const SplitArgs &a, float *tile, int
         __syncwarp();
         if (mine) {
             const int nt = min(TC, t_hi - t0);
-#pragma unroll 4
+#pragma unroll 8
             for (int tt = 0; tt < nt; tt++) qd[(size_t)(t0 + tt) * a.qpitch] = tile[lane * P + tt];
         }
         __syncwarp();
@@ -1141,7 +1141,7 @@ __global__ void __launch_bounds__(128, 3) route_forward_kernel(const SplitArgs a
         const int m = tk / nticket, task = tk - m * nticket;
         route_chain_warp<S, TAPE>(a, stg, m, task, w, lane, t_first, epoch);
     }
-    if (a.fuse_export) {
+    if (a.fuse_export > (int)(threadIdx.x >> 5)) {            // fuse_export = warps per CTA that take export tiles
         // every chain has been claimed: an export tile only ever waits for chains that are running or done
         const int j_first = (a.first_routed / 32) * 32;
         const int ntile = (tp.n - j_first + 31) / 32;
