@@ -228,9 +228,7 @@ def main():
         fused_export = pk_ms[2] < 0.02                # option fuse_export: the routing warps write qsim_domain themselves
         ktraffic = [traffic.get(n) for n in names]
         if fused_export:
-            kbytes[1] += kbytes[2]
-            if ktraffic[1] is not None and ktraffic[2] is not None:
-                ktraffic[1] += ktraffic[2]
+            kbytes[1] += kbytes[2]                    # (profiles/ncu_traffic.json holds the traffic of the fused kernel)
         kernels = {names[i]: {"ms": float(pk_ms[i]), "share": float(pk_ms[i] / kms), "algorithmic_bytes": kbytes[i],
                               "achieved_gbs": kbytes[i] / (pk_ms[i] * 1e-3) / 1e9, "frac": kbytes[i] / (pk_ms[i] * 1e-3) / 1e9 / peak,
                               "traffic": ktraffic[i]} for i in range(3) if pk_ms[i] > 0 and not (i == 2 and fused_export)}
