@@ -352,6 +352,35 @@ def main():
         extra["regional_hyper_polynomial_lbfgsb"] = {"catchments": world, "iterations": 10, "wall_s": dtr,
                                                      "s_per_iteration": dtr / 10, "collective": "all-reduce of 21 float64 per evaluation",
                                                      "rank0_cost": float(mk.output.cost)}
+        # ONE France run with its 3 434 drainage basins spread over the ranks (whole basins per rank, no exchange):
+        # strong scaling of a single domain, bounded by the largest basin (the Loire, 15 % of the cells)
+        masks, load = sdist.basin_masks(model.mesh, world, model.setup)
+        keep_mask = model.mesh._local_active_cell
+        model.mesh._local_active_cell = masks[rank]
+        if hasattr(model.mesh, "_b200_cache"):
+            del model.mesh._b200_cache
+        pkb = L.Packed()
+        sb_, mb_, ib_ = L.pack_setup(model.setup, model.mesh, pkb), L.pack_mesh(model.mesh, model.setup, pkb), L.pack_input(model.input_data, model.setup, model.mesh, pkb)
+        planb = C.c_void_p()
+        L.check(lib.smash_b200_plan_create(C.byref(sb_), C.byref(mb_), 1, C.byref(planb)))
+        L.check(lib.smash_b200_plan_set_forcing(planb, C.byref(sb_), C.byref(ib_)))
+        L.check(lib.smash_b200_plan_set_fields(planb, C.byref(p_), C.byref(st_), None, None, 0))
+        msb = C.c_float(0.0)
+        for _ in range(3):
+            L.check(lib.smash_b200_plan_run_forward(planb, C.byref(msb)))
+        barrier()
+        tb0 = time.perf_counter()
+        nrep = 20
+        for _ in range(nrep):
+            L.check(lib.smash_b200_plan_run_forward(planb, C.byref(msb)))
+        barrier()
+        dtb = max_over_ranks(time.perf_counter() - tb0) / nrep
+        lib.smash_b200_plan_destroy(planb)
+        model.mesh._local_active_cell = keep_mask
+        if hasattr(model.mesh, "_b200_cache"):
+            del model.mesh._b200_cache
+        extra["france_one_domain_split_by_basin"] = {"cell_timesteps_per_s": units / dtb, "ms_per_run": dtb * 1e3, "scaling": "strong",
+                                                     "cells_per_rank": [int(x) for x in load], "collective": "none"}
         extra["cance_ensemble_4096_sharded"] = {"cell_timesteps_per_s_e2e": ns * 383 * 1440 / dte, "ms_per_call": dte * 1e3,
                                                 "members_per_rank": ns // world, "scaling": "strong",
                                                 "cost_checksum": float(np.sum(cost[np.isfinite(cost)], dtype=np.float64))}

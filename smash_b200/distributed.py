@@ -118,3 +118,93 @@ def optimize_hyper_lbfgsb_sharded(catchments, group=None, solver=None):
         return lo.cpu().numpy(), hi.cpu().numpy()
 
     return optimize_hyper_lbfgsb_multi(catchments, solver=solver, reduce_sum=reduce_sum, reduce_minmax=reduce_minmax)
+
+
+# ---- a single large domain split by drainage basin ("France single run: shards by basin") -----------------
+def basin_labels(mesh, setup=None):
+    """Label of the drainage basin (connected component of the D8 gather graph, md_routing_operator.f90:37-53) of every
+    computed cell, as an (nrow, ncol) int32 array (-1 elsewhere), and the number of basins.  Basins exchange nothing: no
+    cell of one gathers a cell of another."""
+    import ctypes as C
+
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import connected_components
+
+    from . import _lib as L
+    pk = L.Packed()
+    me = L.pack_mesh(mesh, setup, pk)
+    act = (np.asarray(mesh.active_cell) == 1) & (np.asarray(getattr(mesh, "_local_active_cell", mesh.active_cell)) == 1)
+    n = int(act.sum())
+    info = (C.c_int64 * 8)()
+    cell, task, pos, down = (np.zeros(n, np.int32) for _ in range(4))
+    L.check(L.lib().smash_b200_mesh_chains(C.byref(me), info, L._ip(cell), L._ip(task), L._ip(pos), L._ip(down)))
+    has = down >= 0
+    src = np.nonzero(has)[0]
+    g = coo_matrix((np.ones(src.size, np.int8), (src, down[has])), shape=(n, n))
+    nb, lab = connected_components(g, directed=False)
+    out = np.full(mesh.nrow * mesh.ncol, -1, dtype=np.int32)
+    out[cell] = lab.astype(np.int32)
+    return np.asfortranarray(out.reshape((mesh.nrow, mesh.ncol), order="F")), int(nb)
+
+
+def basin_masks(mesh, world, setup=None):
+    """``world`` masks for ``mesh._local_active_cell`` (mwd_mesh.f90:68, md_forward_structure.f90:88): whole basins are
+    assigned to ranks, largest first, each to the least loaded rank.  The largest basin bounds the imbalance."""
+    labels, nb = basin_labels(mesh, setup)
+    size = np.bincount(labels[labels >= 0], minlength=nb)
+    load = np.zeros(world, dtype=np.int64)
+    owner = np.zeros(nb, dtype=np.int32)
+    for b in np.argsort(-size, kind="stable"):
+        r = int(np.argmin(load))
+        owner[b] = r
+        load[r] += size[b]
+    own = np.where(labels >= 0, owner[np.maximum(labels, 0)], -1)
+    return [np.asfortranarray((own == r).astype(np.int32)) for r in range(world)], load
+
+
+def forward_sharded_by_basin(model, group=None, gather=True, solver=None):
+    """One forward run of a large domain with its basins spread over the ranks of ``group``: every rank computes the cells
+    of its basins only (``local_active_cell``), there is no exchange on the data path.  With ``gather`` the domain series
+    (``sparse_qsim_domain`` / ``qsim_domain``) and ``qsim`` of all ranks are combined by one all-reduce afterwards."""
+    import torch
+    dist = _dist()
+    if solver is None:
+        from .solver import _mw_forward as solver
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    masks, _ = basin_masks(model.mesh, world, model.setup)
+    keep = model.mesh._local_active_cell
+    model.mesh._local_active_cell = masks[rank]
+    if hasattr(model.mesh, "_b200_cache"):
+        del model.mesh._b200_cache
+    try:
+        solver.forward(model.setup, model.mesh, model.input_data, model.parameters, model.parameters.copy(), model.states,
+                       model.states.copy(), model.output)
+    finally:
+        model.mesh._local_active_cell = keep
+        if hasattr(model.mesh, "_b200_cache"):
+            del model.mesh._b200_cache
+    if gather:
+        dev = _device(group)
+        mine = masks[rank] == 1
+        for name in ("sparse_qsim_domain", "qsim_domain"):
+            a = getattr(model.output, name, None)
+            if a is None:
+                continue
+            if name == "sparse_qsim_domain":
+                k = model.mesh._rowcol_to_ind_sparse
+                own = np.zeros(model.mesh.nac, dtype=bool)
+                own[k[mine] - 1] = True
+                part = np.where(own[:, None], a, np.float32(0.0))
+            else:
+                part = np.where(mine[:, :, None], a, np.float32(0.0))
+            t = torch.from_numpy(np.ascontiguousarray(part, dtype=np.float32)).to(dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            a[...] = t.cpu().numpy()
+        if model.mesh.ng > 0:
+            gp = np.asarray(model.mesh.gauge_pos)
+            own_g = mine[gp[:, 0], gp[:, 1]]
+            t = torch.from_numpy(np.ascontiguousarray(np.where(own_g[:, None], model.output.qsim, np.float32(0.0)),
+                                                      dtype=np.float32)).to(dev)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            model.output.qsim[...] = t.cpu().numpy()
+    return masks[rank]

@@ -170,3 +170,24 @@ def test_chains_france():
     info = out[-1]
     assert info[0] == 906044 and info[2] == 50 and info[7] & 1 == 1 and 0 < info[7] >> 1 <= 256
     assert info[3] <= 16 and info[5] <= 820
+
+
+def test_basin_masks_partition_the_domain():
+    # a France run shards by basin -- whole basins per rank, nothing gathered across ranks
+    from smash_b200 import distributed as D
+    m = cases.france(T=8)
+    labels, nb = D.basin_labels(m.mesh, m.setup)
+    act = m.mesh.active_cell == 1
+    assert nb == 3434 and np.bincount(labels[labels >= 0]).max() == 136170  # the largest basin (the Loire) = the largest flwacc
+    assert np.all(labels[act] >= 0) and np.all(labels[~act] == -1)
+    masks, load = D.basin_masks(m.mesh, 4, m.setup)
+    total = sum(mk.astype(np.int64) for mk in masks)
+    assert np.array_equal(total, act.astype(np.int64))                       # a partition of the active cells
+    cell, task, pos, down, info = mesh_chains(m)
+    own = np.full(m.mesh.nrow * m.mesh.ncol, -1)
+    for r, mk in enumerate(masks):
+        own[np.flatnonzero(mk.ravel(order="F") == 1)] = r
+    has = down >= 0
+    assert np.array_equal(own[cell[has]], own[cell[down[has]]])              # no gather crosses a rank boundary
+    biggest = np.bincount(labels[labels >= 0]).max()
+    assert load.max() - load.min() <= biggest and load.sum() == act.sum()

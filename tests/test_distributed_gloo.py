@@ -116,3 +116,34 @@ def test_regionalised_calibration_world2_equals_single_process():
             cost, cp, lr = ret[rank]
             assert np.isclose(cost, float(m.output.cost), rtol=1e-6)
             assert np.allclose(cp, m.parameters.cp, rtol=1e-6) and np.allclose(lr, m.parameters.lr, rtol=1e-6)
+
+
+def _basin_worker(rank, world, port, ret):
+    import torch.distributed as dist
+
+    import cases
+    import oracle_solver
+    from smash_b200 import distributed as D
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    m = cases.france(T=24, sub=(400, 520, 400, 520), ngauge=2)
+    mask = D.forward_sharded_by_basin(m, solver=oracle_solver)
+    ret[rank] = (m.output.sparse_qsim_domain.copy(), m.output.qsim.copy(), int(mask.sum()))
+    dist.destroy_process_group()
+
+
+def test_domain_sharded_by_basin_world2_equals_full_run():
+    # one domain, its drainage basins spread over the ranks, no exchange on the data path; the gathered series
+    # are those of the undivided run
+    import cases
+    import oracle_solver
+    full = cases.france(T=24, sub=(400, 520, 400, 520), ngauge=2)
+    oracle_solver.forward(full.setup, full.mesh, full.input_data, full.parameters, full.parameters.copy(), full.states,
+                          full.states.copy(), full.output)
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_basin_worker, args=(2, 29700 + os.getpid() % 1000, ret), nprocs=2, join=True)
+        assert ret[0][2] + ret[1][2] == full.mesh.nac and min(ret[0][2], ret[1][2]) > 0
+        for rank in (0, 1):
+            assert np.array_equal(ret[rank][0], full.output.sparse_qsim_domain)
+            assert np.array_equal(ret[rank][1], full.output.qsim)

@@ -219,3 +219,29 @@ def test_multiple_run_on_split_engine_lane_per_member(golden):
     assert np.allclose(res[1][1], golden["multiple_run.qsim"], atol=1e-4)
     assert np.allclose(res[1][0], golden["multiple_run.cost"], atol=1e-4, rtol=1e-5)
     assert np.allclose(res[1][1], res[0][1], rtol=2e-3, atol=1e-4)
+
+
+def test_domain_split_by_basin_equals_full_run():
+    # the basins of one domain computed separately (what each rank of forward_sharded_by_basin does, here one
+    # after the other on one GPU) give the series of the undivided run: basins exchange nothing
+    from smash_b200 import distributed as D
+    full = cases.france(T=96, sub=(300, 700, 300, 700), ngauge=3)
+    random_fields(full, seed=9)
+    smash_b200.forward(full.setup, full.mesh, full.input_data, full.parameters, full.parameters.copy(), full.states,
+                       full.states.copy(), full.output)
+    masks, load = D.basin_masks(full.mesh, 3, full.setup)
+    assert load.sum() == full.mesh.nac and load.min() > 0
+    got = np.zeros_like(full.output.sparse_qsim_domain)
+    k = full.mesh._rowcol_to_ind_sparse
+    for mk in masks:
+        part = cases.france(T=96, sub=(300, 700, 300, 700), ngauge=3)
+        random_fields(part, seed=9)
+        part.mesh._local_active_cell = mk
+        smash_b200.forward(part.setup, part.mesh, part.input_data, part.parameters, part.parameters.copy(), part.states,
+                           part.states.copy(), part.output)
+        own = np.zeros(full.mesh.nac, dtype=bool)
+        own[k[mk == 1] - 1] = True
+        got[own] = part.output.sparse_qsim_domain[own]
+    a, b = np.asarray(got, np.float64), np.asarray(full.output.sparse_qsim_domain, np.float64)
+    assert np.all(np.abs(a - b) <= 1e-9 + 1e-6 * np.abs(b)), float(np.abs(a - b).max())
+    L.lib().smash_b200_clear_cache()
