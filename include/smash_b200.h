@@ -171,7 +171,11 @@ void smash_b200_clear_cache(void);           /* drop cached mesh plans and devic
  * the kernels and the download of sparse_qsim_domain overlap on three streams (effective with page-locked arrays);
  * "fuse_export" (default 4) = warps per routing CTA that, once every chain has been claimed, also write the routed cells'
  * series to the [t][cell] domain layout as the chains owning a tile of 32 cells finish, in the shadow of the serial walks
- * down the main rivers; 0 = separate rows_to_domain kernel after the routing pass. */
+ * down the main rivers; 0 = separate rows_to_domain kernel after the routing pass; "route_dynamic" 1 (default) = the
+ * ticketed chains of the routing pass are handed out from ready queues (a chain is queued when its last tributary chain has
+ * finished; one queue per basin of a long river, longest first, "route_queues" of them, plus one for the rest), 0 = static
+ * ticket order with done-flag waits; "route_order" = static ticket order: 0 by topological level (default), 1 by distance
+ * to the outlet, 2 basin by basin (both measured slower). */
 int smash_b200_set_option(const char *name, long long value);
 
 /* ---- device-resident plan API (bench / advanced callers) --------------------------------------

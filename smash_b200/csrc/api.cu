@@ -91,6 +91,10 @@ struct SplitState {
     int S = 0, W = 0, nwin = 0, Tp = 0;
     int64_t qpitch = 0;
     DBuf<int32_t> d_flwacc, d_up_begin, d_down, d_down_task, d_down_need, d_rlist, d_rindex, d_task_begin, d_task_cells, d_gfirst, d_gnext, d_cell_task;
+    // dynamic scheduling of the ticketed chains (SplitArgs::dyn)
+    DBuf<int32_t> d_queue, d_queue0, d_ndep, d_ndep0, d_cons, d_qid, d_qoff;
+    DBuf<unsigned int> d_qctl, d_qctl0;
+    int dyn_nq = 0;
     DBuf<RouteUp> d_up, d_tup;
     DBuf<TaskCell> d_tcell;
     DBuf<uint8_t> d_down_lag;
@@ -288,7 +292,7 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     std::string err = build_route_graph(rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
                                         mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
                                         (int)option("route_ded_max", option("river_wave", 0) ? 224 : 64),
-                                        option("river_wave", 0) ? 128 : 0);
+                                        option("river_wave", 0) ? 128 : 0, (int)option("route_order", 0));
     if (!err.empty()) {
         *unsupported = err.rfind("unsupported", 0) == 0;
         return fail(SMASH_B200_EINVAL, "%s", err.c_str());
@@ -337,6 +341,45 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     std::vector<int32_t> cell_task(npad, -1);
     for (int j = 0; j < rg.n; j++) cell_task[j] = rg.cell_task[j];
     TRY(sp.d_cell_task.upload(cell_task, s));
+    {   // ---- ready queues of the dynamic scheduler: one per basin of a long river (longest first), one for the rest
+        const int nticket = rg.nchain - rg.nded;
+        std::vector<int32_t> cons(std::max(1, rg.nchain), -1), ndep0(std::max(1, nticket), 0), qid(std::max(1, nticket), 0);
+        for (int t = 0; t < rg.nchain; t++) {
+            const int tail = rg.task_cells[rg.task_begin[t + 1] - 1];
+            const int ct = rg.down_task[tail];
+            if (ct >= 0 && ct < nticket) cons[t] = ct;
+        }
+        for (int t = 0; t < nticket; t++)
+            for (int i = rg.task_begin[t]; i < rg.task_begin[t + 1]; i++) {
+                const TaskCell &tc = rg.tcell[i];
+                for (int e = 0; e < (tc.meta >> 8); e++) if (rg.tup[tc.up_off + e].task >= 0) ndep0[t]++;
+            }
+        // basins (cells that drain to the same outlet) ranked by their longest chain
+        std::vector<int32_t> root(rg.n), longest(rg.n, 0);
+        for (int j = rg.n - 1; j >= 0; j--) root[j] = (rg.down[j] > j) ? root[rg.down[j]] : j;
+        for (int t = 0; t < rg.nchain; t++) {
+            const int r = root[rg.task_cells[rg.task_begin[t]]];
+            longest[r] = std::max(longest[r], rg.task_begin[t + 1] - rg.task_begin[t]);
+        }
+        std::vector<int32_t> roots;
+        for (int j = 0; j < rg.n; j++) if (root[j] == j && longest[j] >= (int)option("route_ded_min", 96)) roots.push_back(j);
+        std::stable_sort(roots.begin(), roots.end(), [&](int x, int y) { return longest[x] > longest[y]; });
+        const int nq = (int)std::min<size_t>(roots.size(), (size_t)std::min<long long>(15, std::max<long long>(0, option("route_queues", 12)))) + 1;
+        std::vector<int32_t> qof_root(rg.n, nq - 1);
+        for (int k = 0; k + 1 < nq; k++) qof_root[roots[k]] = k;
+        std::vector<int32_t> qoff(nq + 1, 0), fill(nq, 0);
+        for (int t = 0; t < nticket; t++) { qid[t] = qof_root[root[rg.task_cells[rg.task_begin[t]]]]; qoff[qid[t] + 1]++; }
+        for (int q = 0; q < nq; q++) qoff[q + 1] += qoff[q];
+        std::vector<int32_t> queue0(std::max(1, nticket), -1);
+        std::vector<unsigned int> qctl0(32, 0u);
+        for (int t = 0; t < nticket; t++)                        // chains without tributary chains are ready from the start, in task order
+            if (ndep0[t] == 0) { queue0[qoff[qid[t]] + fill[qid[t]]++] = t; }
+        for (int q = 0; q < nq; q++) qctl0[16 + q] = (unsigned int)fill[q];
+        sp.dyn_nq = nq;
+        TRY(sp.d_cons.upload(cons, s)); TRY(sp.d_ndep0.upload(ndep0, s)); TRY(sp.d_qid.upload(qid, s)); TRY(sp.d_qoff.upload(qoff, s));
+        TRY(sp.d_queue0.upload(queue0, s)); TRY(sp.d_qctl0.upload(qctl0, s));
+        TRY(sp.d_queue.ensure(queue0.size())); TRY(sp.d_ndep.ensure(ndep0.size())); TRY(sp.d_qctl.ensure(32));
+    }
     TRY(pl.d_ticket.ensure(2)); TRY(pl.d_sum.ensure(1));
     SplitTopo &t = sp.topo;
     t.n = rg.n; t.npad = npad; t.ng = mesh->ng; t.ntask = rg.ntask; t.nchain = rg.nchain; t.nded = rg.nded;
@@ -432,6 +475,9 @@ static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp) {
     a.save_q = save_q ? 1 : 0; a.save_netp = save_netp ? 1 : 0;
     a.river_wave = (int)option("river_wave", 0);
     a.fuse_export = 0;
+    a.dyn = (option("route_dynamic", 1) != 0 && pl.nmember == 1 && sp.rg.nchain > sp.rg.nded) ? 1 : 0;
+    a.dyn_nq = sp.dyn_nq; a.qctl = sp.d_qctl.p; a.queue = sp.d_queue.p; a.ndep = sp.d_ndep.p; a.cons = sp.d_cons.p; a.qid = sp.d_qid.p;
+    a.qoff = sp.d_qoff.p; a.qctl0 = sp.d_qctl0.p; a.queue0 = sp.d_queue0.p; a.ndep0 = sp.d_ndep0.p;
     a.fields = pl.d_fields.p; a.fstates = pl.d_fstates.p; a.rows = sp.d_rows.p; a.qdom = pl.d_qdom.p; a.netp = pl.d_netp.p;
     a.qpitch = sp.qpitch; a.qsim = pl.d_qsim.p; a.tape_hp = sp.d_tape_hp.p; a.tape_hft = sp.d_tape_hft.p; a.rows_hr = sp.d_rows_hr.p;
     a.hcar = sp.d_hcar.p; a.done = sp.d_done.p; a.ticket = pl.d_ticket.p; a.qsim_b = pl.d_qsim_b.p; a.rows_w = sp.d_rows_w.p;
@@ -816,7 +862,7 @@ static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **
     char key[192];
     snprintf(key, sizeof key, "%016llx:%d:%d:%g:%g:%lld:%d:%d:%d:%lld", (unsigned long long)h, dev, setup->ntime_step, (double)setup->dt,
              (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0, small ? 1 : 0,
-             option("river_wave", 0));
+             option("river_wave", 0) + 16 * option("route_order", 0));
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
         std::unique_ptr<SmashPlan> pl(new SmashPlan());

@@ -13,7 +13,7 @@ static const int RG_DROW[8] = {1, 1, 0, -1, -1, -1, 0, 1};
 
 std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const int32_t *flwdir, const int32_t *flwacc,
                               const int32_t *active_cell, const int32_t *local_active_cell, const int32_t *path,
-                              const int32_t *gauge_pos, int ded_min, int ded_max, int reach) {
+                              const int32_t *gauge_pos, int ded_min, int ded_max, int reach, int order) {
     const int ncell = nrow * ncol;
     if (nrow <= 0 || ncol <= 0) return "mesh: nrow and ncol must be positive";
     g = RouteGraph();
@@ -195,6 +195,38 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
             if (g.up[e].src < j) level[j] = std::max(level[j], level[g.up[e].src] + 1);
     std::vector<int32_t> torder(nch);
     std::iota(torder.begin(), torder.end(), 0);
+    if (order == 1) {
+        // Critical-path order: by the number of cells between the chain's last cell and the outlet of its basin, farthest
+        // first.  A tributary joins its consumer above the consumer's last cell, so it is farther from the outlet: this
+        // is a dependency order too, and the headwaters of the long rivers no longer queue behind every short coastal
+        // chain of the domain.
+        std::vector<int32_t> dist(n, 1);
+        for (int j = n - 1; j >= 0; j--)
+            if (g.down[j] > j) dist[j] = dist[g.down[j]] + 1;
+        std::stable_sort(torder.begin(), torder.end(), [&](int a, int b) {
+            const int da = dist[chains[a].back()], db = dist[chains[b].back()];
+            if (da != db) return da > db;
+            return chains[a].size() > chains[b].size();
+        });
+    } else if (order == 2) {
+        // Basin by basin, the basins with the longest rivers first, each in level order.  The serial walk down a main river
+        // can only start once the low levels of ITS basin are done; in a domain-wide level order that is when 90 % of the
+        // whole domain is done.  Basins exchange nothing, so any basin order keeps the dependencies.
+        std::vector<int32_t> root(n), crit(n, 0), rank_of(n, 0);
+        for (int j = n - 1; j >= 0; j--) root[j] = (g.down[j] > j) ? root[g.down[j]] : j;
+        for (int j = 0; j < n; j++) crit[root[j]] = std::max(crit[root[j]], level[j]);
+        std::vector<int32_t> roots;
+        for (int j = 0; j < n; j++) if (root[j] == j) roots.push_back(j);
+        std::stable_sort(roots.begin(), roots.end(), [&](int a, int b) { return crit[a] > crit[b]; });
+        for (size_t r = 0; r < roots.size(); r++) rank_of[roots[r]] = (int32_t)r;
+        std::stable_sort(torder.begin(), torder.end(), [&](int a, int b) {
+            const int ta = chains[a].back(), tb = chains[b].back();
+            const int ra = rank_of[root[ta]], rb = rank_of[root[tb]];
+            if (ra != rb) return ra < rb;
+            if (level[ta] != level[tb]) return level[ta] < level[tb];
+            return chains[a].size() > chains[b].size();
+        });
+    } else
     std::stable_sort(torder.begin(), torder.end(), [&](int a, int b) {
         const int la = level[chains[a].back()], lb = level[chains[b].back()];
         if (la != lb) return la < lb;

@@ -69,7 +69,9 @@ struct RouteGraph {
 // Returns "" on success; "unsupported: ..." when the mesh needs the fused engine (lagged inflows outside pit pairs).
 std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const int32_t *flwdir, const int32_t *flwacc,
                               const int32_t *active_cell, const int32_t *local_active_cell, const int32_t *path,
-                              const int32_t *gauge_pos, int ded_min = 96, int ded_max = 64, int reach = 0);
+                              const int32_t *gauge_pos, int ded_min = 96, int ded_max = 64, int reach = 0, int order = 0);
+// order: ticket order of the chains -- 0 by the topological level of the chain's last cell, 1 by its distance to the outlet
+// (farthest first)
 // ded_min / ded_max: chains of at least ded_min cells, the longest first, get CTAs of their own in the forward routing
 // pass, at most ded_max CTAs.  reach > 0: those chains are cut into reaches of at most `reach` cells, one CTA per reach
 // (tick wavefront, the reaches of a river pipelined); reach = 0: one CTA per whole chain (window scan per cell).

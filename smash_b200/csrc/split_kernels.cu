@@ -533,6 +533,52 @@ template <int S> __device__ __forceinline__ void staged_row(const RowStage<S> &s
     }
 }
 
+// ---- dynamic scheduling of the ticketed chains -------------------------------------------------------------------
+// A finished task tells the ticketed chain that gathers its last cell; the chain whose last tributary chain has finished
+// is pushed to the ready queue of its class.  Called by one thread after the task's done flag has been released.
+__device__ __forceinline__ void notify_consumer(const SplitArgs &a, int task) {
+    if (!a.dyn) return;
+    const int c = a.cons[task];
+    if (c < 0) return;
+    __threadfence();
+    if (atomicSub(a.ndep + c, 1) == 1) {
+        const int q = a.qid[c];
+        const unsigned s = atomicAdd(a.qctl + 16 + q, 1u);
+        st_release(a.queue + a.qoff[q] + (int)s, c);
+    }
+}
+// Next ready chain, queues in priority order; -1 when every chain has been handed out.  A warp never holds a task while
+// it waits here, and a chain in a queue has no unfinished tributary: nothing ever spins on a chain that has not started.
+// block = false: returns -2 instead of waiting when no chain is ready at the moment (the caller has other work).
+__device__ __forceinline__ int pop_ready(const SplitArgs &a, int lane, bool block = true) {
+    for (;;) {
+        unsigned h = 0, t = 0, cap = 0;
+        if (lane < a.dyn_nq) {
+            h = *reinterpret_cast<volatile unsigned int *>(a.qctl + lane);
+            t = *reinterpret_cast<volatile unsigned int *>(a.qctl + 16 + lane);
+            cap = (unsigned)(a.qoff[lane + 1] - a.qoff[lane]);
+        }
+        const unsigned alive = __ballot_sync(FULL, h < cap);
+        if (!alive) return -1;
+        const unsigned avail = __ballot_sync(FULL, h < t && h < cap);
+        if (!avail) {
+            if (!block) return -2;
+            __nanosleep(256);
+            continue;
+        }
+        const int q = __ffs(avail) - 1;
+        unsigned s = 0;
+        if (lane == 0) s = atomicAdd(a.qctl + q, 1u);
+        s = __shfl_sync(FULL, s, 0);
+        const unsigned capq = __shfl_sync(FULL, cap, q);
+        if (s >= capq) continue;                             // the queue ran out between the look and the claim
+        int task = -1;
+        if (lane == 0)
+            while ((task = ld_acquire(a.queue + a.qoff[q] + (int)s)) < 0) __nanosleep(64);   // claimed ahead of the push
+        return __shfl_sync(FULL, task, 0);
+    }
+}
+
 template <int S, int TAPE>
 __device__ __forceinline__ void route_chain_warp(const SplitArgs &a, RowStage<S> &stg, int m, int task, int w, int lane, int t_first,
                                             int epoch) {
@@ -647,6 +693,7 @@ __device__ __forceinline__ void route_chain_warp(const SplitArgs &a, RowStage<S>
         }
     }
     publish_flag(done + task, epoch, lane);
+    if (lane == 0) notify_consumer(a, task);
     if (prof && lane == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -831,7 +878,7 @@ __device__ __forceinline__ void route_chain_cta(const SplitArgs &a, ChainShared<
         }
     }
     __syncthreads();                                                     // every thread's row stores precede the release
-    if (tid == 0) st_release(done + task, epoch);
+    if (tid == 0) { st_release(done + task, epoch); notify_consumer(a, task); }
     if (prof && tid == 0) {
         unsigned long long gt;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
@@ -1054,7 +1101,7 @@ __device__ __forceinline__ void route_chain_wave(const SplitArgs &a, WaveShared 
         }
         __syncthreads();
     }
-    if (tid == 0) st_release(done + task, epoch);     // every thread's row stores precede the last barrier
+    if (tid == 0) { st_release(done + task, epoch); notify_consumer(a, task); }   // every thread's row stores precede the last barrier
     if (prof) {
         unsigned long long *o = a.dbg_prof + 8 * (size_t)(task - (tp.nchain - tp.nded));
         if (t_wait) atomicAdd(o + 2, (unsigned long long)t_wait);
@@ -1070,18 +1117,27 @@ __device__ __forceinline__ void route_chain_wave(const SplitArgs &a, WaveShared 
 // Export of a tile of 32 consecutive cells to the domain layout qdom[t][cell], done by a routing warp once the chains that
 // own the tile's cells have finished this window (fuse_export): the transposition runs in the shadow of the serial walks
 // down the main rivers instead of in a kernel of its own.  Source cells were written by the reservoir pass already.
+// true when every chain that owns a cell of the tile has finished this window (one look, no waiting)
+__device__ __forceinline__ bool tile_ready(const SplitArgs &a, int m, int j0, int lane, int epoch) {
+    const SplitTopo &tp = a.tp;
+    const int j = j0 + lane;
+    bool ok = true;
+    if (j < tp.n && tp.flwacc[j] > 1) {
+        const int task = tp.cell_task[j];
+        if (task >= 0 && task < tp.nchain) ok = ld_acquire(a.done + (size_t)m * tp.ntask + task) >= epoch;
+    }
+    return __all_sync(FULL, ok);
+}
 template <int S>
-__device__ __forceinline__ void export_tile(const SplitArgs &a, float *tile, int m, int j0, int w, int lane, int epoch) {
+__device__ __forceinline__ void export_tile(const SplitArgs &a, float *tile, int m, int j0, int w, int lane, int epoch, bool wait = true) {
     constexpr int TC = 2 * S, P = TC + 1;                    // steps per chunk; padded pitch of the shared tile [32][P]
     const SplitTopo &tp = a.tp;
     const int j = j0 + lane;
     const int task = j < tp.n ? tp.cell_task[j] : -1;
     const bool mine = j < tp.n && tp.flwacc[j] > 1 && task < tp.nchain;      // pit pairs are routed (and exported) afterwards
-    if (mine) {
-        if (task >= 0) {
-            const int *flag = a.done + (size_t)m * tp.ntask + task;
-            while (ld_acquire(flag) < epoch) __nanosleep(128);
-        }
+    if (wait && mine && task >= 0) {
+        const int *flag = a.done + (size_t)m * tp.ntask + task;
+        while (ld_acquire(flag) < epoch) __nanosleep(128);
     }
     __syncwarp();
     const int t_lo = w * a.W, t_hi = min(a.T, (w + 1) * a.W);
@@ -1133,13 +1189,40 @@ __global__ void __launch_bounds__(128, 3) route_forward_kernel(const SplitArgs a
     const int t_first = w * a.W + lane * S;
     const int nticket = tp.nchain - tp.nded;                // pit pairs are routed by route_pairs_kernel afterwards
     const int total = nticket * a.nmember;
-    int tk_next = claim_ticket(a.ticket, lane);
-    for (;;) {
-        const int tk = tk_next;
-        if (tk >= total) break;
-        tk_next = claim_ticket(a.ticket, lane);            // the next ticket travels while this task is routed
-        const int m = tk / nticket, task = tk - m * nticket;
-        route_chain_warp<S, TAPE>(a, stg, m, task, w, lane, t_first, epoch);
+    if (a.dyn) {
+        // no chain ready at the moment: take an export tile whose chains are done instead of waiting (one tile may be held
+        // back per warp until its chains finish)
+        const bool exporter = a.fuse_export > (int)(threadIdx.x >> 5);
+        const int j_first = (a.first_routed / 32) * 32;
+        const int ntile = (tp.n - j_first + 31) / 32;
+        float *tile = reinterpret_cast<float *>(&stg);
+        int pend = -1;
+        bool tiles_left = exporter;
+        for (;;) {
+            const int task = pop_ready(a, lane, !exporter);
+            if (task >= 0) { route_chain_warp<S, TAPE>(a, stg, 0, task, w, lane, t_first, epoch); continue; }
+            if (task == -1) break;                               // every chain has been handed out
+            if (pend < 0 && tiles_left) {
+                pend = claim_ticket(a.ticket + 1, lane);
+                if (pend >= ntile) { pend = -1; tiles_left = false; }
+            }
+            if (pend >= 0 && tile_ready(a, 0, j_first + 32 * pend, lane, epoch)) {
+                export_tile<S>(a, tile, 0, j_first + 32 * pend, w, lane, epoch, false);
+                pend = -1;
+                continue;
+            }
+            __nanosleep(200);
+        }
+        if (pend >= 0) export_tile<S>(a, tile, 0, j_first + 32 * pend, w, lane, epoch);
+    } else {
+        int tk_next = claim_ticket(a.ticket, lane);
+        for (;;) {
+            const int tk = tk_next;
+            if (tk >= total) break;
+            tk_next = claim_ticket(a.ticket, lane);            // the next ticket travels while this task is routed
+            const int m = tk / nticket, task = tk - m * nticket;
+            route_chain_warp<S, TAPE>(a, stg, m, task, w, lane, t_first, epoch);
+        }
     }
     if (a.fuse_export > (int)(threadIdx.x >> 5)) {            // fuse_export = warps per CTA that take export tiles
         // every chain has been claimed: an export tile only ever waits for chains that are running or done
@@ -1722,6 +1805,13 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
     for (int w = w_begin; w < w_end; w++) {
         e = cudaMemsetAsync(a.ticket, 0, 2 * sizeof(unsigned int), s);
         if (e != cudaSuccess) return e;
+        if (a.dyn) {                                         // ready queues, tributary counters and queue heads / tails of this window
+            const size_t nt = (size_t)(a.tp.nchain - a.tp.nded);
+            e = cudaMemcpyAsync(a.queue, a.queue0, nt * sizeof(int), cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(a.ndep, a.ndep0, nt * sizeof(int), cudaMemcpyDeviceToDevice, s);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(a.qctl, a.qctl0, 32 * sizeof(unsigned int), cudaMemcpyDeviceToDevice, s);
+            if (e != cudaSuccess) return e;
+        }
         if (tape) route_forward_kernel<S, 1><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
         else route_forward_kernel<S, 0><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
         e = cudaGetLastError();

@@ -64,6 +64,17 @@ struct SplitArgs {
     float *hcar;                 // [m][npad]       routing state carried across windows (starts as the hlr field)
     int *done;                   // [m][ntask]      forward: windows finished by each task
     unsigned int *ticket;        // [2] chain tickets, export-tile tickets
+    // dynamic scheduling of the ticketed chains (option route_dynamic): a chain is pushed to the ready queue of its basin
+    // class when its last tributary chain has finished; warps pop from the queues in priority order
+    int dyn, dyn_nq;             // on / number of queues (<= 16)
+    unsigned int *qctl;          // [32] heads [0..16), tails [16..32): one 128-byte line
+    int *queue;                  // [nticket] ready entries of all queues, queue q owns [qoff[q], qoff[q + 1]); -1 = not pushed yet
+    int *ndep;                   // [nticket] tributary chains still running
+    const int *cons;             // [nchain] ticketed chain that gathers the task's last cell, or -1
+    const int *qid;              // [nticket] queue of the chain
+    const int *qoff;             // [dyn_nq + 1]
+    const unsigned int *qctl0;   // initial images, copied before every window
+    const int *queue0, *ndep0;
     // adjoint
     const float *qsim_b;         // [m][T][ng]
     float *rows_w;               // [m][npad][Tp]   s * hr_imd_b of the routed cells (UPSTREAM_DISCHARGE_B)
