@@ -475,6 +475,7 @@ static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp) {
     a.save_q = save_q ? 1 : 0; a.save_netp = save_netp ? 1 : 0;
     a.river_wave = (int)option("river_wave", 0);
     a.fuse_export = 0;
+    a.route_ctas_per_sm = (int)option("route_ctas_per_sm", 0);
     a.dyn = (option("route_dynamic", 1) != 0 && pl.nmember == 1 && sp.rg.nchain > sp.rg.nded) ? 1 : 0;
     a.dyn_nq = sp.dyn_nq; a.qctl = sp.d_qctl.p; a.queue = sp.d_queue.p; a.ndep = sp.d_ndep.p; a.cons = sp.d_cons.p; a.qid = sp.d_qid.p;
     a.qoff = sp.d_qoff.p; a.qctl0 = sp.d_qctl0.p; a.queue0 = sp.d_queue0.p; a.ndep0 = sp.d_ndep0.p;

@@ -3,6 +3,8 @@
 // Reference statements are cited as file:line under /root/reference/smash/solver/.
 #include "split_kernels.cuh"
 
+#include <algorithm>
+
 #include "cell_math.cuh"
 
 namespace smash {
@@ -1796,6 +1798,12 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
     int blocks = 0;
     cudaError_t e = tape ? persistent_grid(route_forward_kernel<S, 1>, &blocks) : persistent_grid(route_forward_kernel<S, 0>, &blocks);
     if (e != cudaSuccess) return e;
+    if (a.route_ctas_per_sm > 0) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        blocks = std::min(blocks, sms * a.route_ctas_per_sm);
+    }
     const int ded_blocks = a.tp.nded;                      // one CTA per dedicated chain (route_graph.cpp keeps nded small)
     const long long total = (long long)(a.tp.nchain - a.tp.nded) * a.nmember;
     const long long need = (total + 3) / 4 + ded_blocks;
