@@ -542,8 +542,9 @@ __device__ __forceinline__ void notify_consumer(const SplitArgs &a, int task) {
     if (!a.dyn) return;
     const int c = a.cons[task];
     if (c < 0) return;
-    __threadfence();
+    __threadfence();                                         // release: this task's rows before the decrement
     if (atomicSub(a.ndep + c, 1) == 1) {
+        __threadfence();                                     // acquire: the other tributaries' decrements (and rows) before the push
         const int q = a.qid[c];
         const unsigned s = atomicAdd(a.qctl + 16 + q, 1u);
         st_release(a.queue + a.qoff[q] + (int)s, c);
