@@ -110,6 +110,9 @@ class Activation:
     def _set_input_shape(self, shape):
         self.input_shape = shape
 
+    def layer_name(self):
+        return "Activation (%s)" % type(self._f).__name__.lstrip("_")
+
     def _forward_pass(self, x, training=True):
         self.layer_input = x
         return self._f(x)
@@ -136,6 +139,9 @@ class Scale:
 
     def _set_input_shape(self, shape):
         self.input_shape = shape
+
+    def layer_name(self):
+        return "Scale (MinMaxScale)"
 
     def _forward_pass(self, x, training=True):
         self.layer_input = x
@@ -183,6 +189,9 @@ class Dense:
         self.bias = self._draw(self.bias_initializer, (1, self.neurons))
         self._weight_opt, self._bias_opt = copy.copy(optimizer), copy.copy(optimizer)
 
+    def layer_name(self):
+        return "Dense"
+
     def n_params(self):
         return int(np.prod(self.weight.shape) + np.prod(self.bias.shape))
 
@@ -213,6 +222,9 @@ class Dropout:
 
     def _set_input_shape(self, shape):
         self.input_shape = shape
+
+    def layer_name(self):
+        return "Dropout"
 
     def _forward_pass(self, x, training=True):
         c = 1 - self.drop_rate

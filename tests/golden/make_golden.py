@@ -180,7 +180,7 @@ def build_cance():
 # ----------------------------------------------------------------------------- golden outputs
 def build_golden():
     g = H5File(f"{REF}/tests/baseline.hdf5")
-    keep = [k for k in g.keys() if k.split(".")[0] in ("run", "multiple_run", "mutiple_run", "optimize", "bayes_estimate", "bayes_optimize", "ann_optimize_1", "ann_optimize_2")
+    keep = [k for k in g.keys() if k.split(".")[0] in ("run", "multiple_run", "mutiple_run", "optimize", "bayes_estimate", "bayes_optimize", "ann_optimize_1", "ann_optimize_2", "gen_samples", "net_init")
             or k.startswith("xy_mesh.") or k.startswith("mesh_io.")]
     out = {k: g[k] for k in keep}
     # generate_samples(problem, n=10, random_state=99): one legacy-uniform draw per variable

@@ -215,3 +215,37 @@ def test_ann_optimize_golden_cpu(golden):
 def test_ann_optimize_golden_gpu(golden):
     _ann_1(golden, None, COST_ATOL_GPU)
     _ann_2(golden, None, COST_ATOL_GPU)
+
+
+def test_gen_samples_uniform_and_normal_golden(golden):
+    # generic_gen_samples (smash/tests/core/test_gen_samples.py:9-35)
+    m = cases.cance(T=24)
+    problem = simulation.get_bound_constraints(m)
+    uni = simulation.generate_samples(problem, generator="uniform", n=20, random_state=11).to_numpy(axis=-1)
+    nor = simulation.generate_samples(problem, generator="normal", n=20,
+                                      mean={problem["names"][1]: 1 / 3 * np.mean(problem["bounds"][1])}, coef_std=2,
+                                      random_state=11).to_numpy(axis=-1)
+    assert np.allclose(uni, golden["gen_samples.uni"], atol=1e-6)
+    assert np.allclose(nor, golden["gen_samples.nor"], atol=1e-6)
+
+
+def test_net_init_golden(golden):
+    # generic_net_init (smash/tests/core/test_net.py:9-66): graph, He / Glorot weights of the legacy global generator
+    from smash_b200.net import Net
+    net = Net()
+    for i in range(4):
+        if i == 0:
+            net.add(layer="dense", options={"input_shape": (6,), "neurons": 16, "kernel_initializer": "he_uniform"})
+        else:
+            net.add(layer="dense", options={"neurons": round(16 * (4 - i) / 4), "kernel_initializer": "he_uniform"})
+        net.add(layer="activation", options={"name": "relu"})
+        net.add(layer="dropout", options={"drop_rate": 0.1})
+    net.add(layer="dense", options={"neurons": 2, "kernel_initializer": "glorot_uniform"})
+    net.add(layer="activation", options={"name": "sigmoid"})
+    net.compile(optimizer="adam", options={"learning_rate": 0.002, "b1": 0.8, "b2": 0.99}, random_state=11)
+    graph = np.array([l.layer_name() for l in net.layers]).astype("S")
+    assert np.array_equal(graph, golden["net_init.graph"])
+    for i in range(4):
+        layer = net.layers[3 * i]
+        assert np.allclose(layer.weight, golden[f"net_init.weight_layer_{i + 1}"], atol=1e-6)
+        assert np.allclose(layer.bias, golden[f"net_init.bias_layer_{i + 1}"], atol=1e-6)
