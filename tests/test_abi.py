@@ -191,3 +191,17 @@ def test_basin_masks_partition_the_domain():
     assert np.array_equal(own[cell[has]], own[cell[down[has]]])              # no gather crosses a rank boundary
     biggest = np.bincount(labels[labels >= 0]).max()
     assert load.max() - load.min() <= biggest and load.sum() == act.sum()
+
+
+def test_flow_accumulation_bit_exact(golden):
+    # the reference's flow accumulation (mw_meshing.f90:204-233) recomputed from the flow directions: integer-exact on the
+    # Cance catchment window (golden mesh_io.flwacc / xy_mesh.flwacc) and on the France mesh (288 pit cells)
+    from smash_b200.mesh import flow_accumulation
+    act = golden["mesh_io.active_cell"] == 1
+    fa = flow_accumulation(golden["mesh_io.flwdir"], mask=act)
+    assert np.array_equal(fa[act], golden["mesh_io.flwacc"][act])
+    assert np.array_equal(fa[act], golden["xy_mesh.flwacc"][act])
+    f = cases.golden("france_mesh.npz")
+    fa = flow_accumulation(f["flwdir"])
+    actf = f["active_cell"] == 1
+    assert np.array_equal(fa[actf], f["flwacc"][actf])
