@@ -205,3 +205,13 @@ def test_flow_accumulation_bit_exact(golden):
     fa = flow_accumulation(f["flwdir"])
     actf = f["active_cell"] == 1
     assert np.array_equal(fa[actf], f["flwacc"][actf])
+
+
+def test_path_is_sorted_by_flow_accumulation(golden):
+    # the stored cell order (meshing.py:216-218: argsort of flwacc) is ascending in flwacc, so every cell comes after the
+    # cells it gathers -- the property the solver's single sweep over `path` relies on (md_forward_structure.f90:82-92)
+    for fa, path in ((golden["mesh_io.flwacc"], golden["mesh_io.path"]),
+                     (cases.golden("france_mesh.npz")["flwacc"], cases.golden("france_mesh.npz")["path"])):
+        ok = (path[0] >= 0) & (path[1] >= 0)
+        seq = fa[path[0][ok], path[1][ok]]
+        assert np.all(np.diff(seq.astype(np.int64)) >= 0)
