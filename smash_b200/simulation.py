@@ -154,6 +154,19 @@ def _setup_optimize(model, mapping, algorithm, control_vector, bounds, jobs_fun,
     return algorithm, cv
 
 
+def _control_bounds(o, names):
+    """Bounds of the control fields as standardised into ``setup._optimize`` (lb_/ub_parameters, lb_/ub_states)."""
+    out = []
+    for c in names:
+        if c in GPARAMETERS_NAME:
+            k = GPARAMETERS_NAME.index(c)
+            out.append([o.lb_parameters[k].item(), o.ub_parameters[k].item()])
+        else:
+            k = GSTATES_NAME.index(c)
+            out.append([o.lb_states[k].item(), o.ub_states[k].item()])
+    return out
+
+
 def _compute_wjreg_range(wjreg_opt, nb_wjreg_lcurve):
     """_optimize.py:911-947"""
     lw = np.log10(wjreg_opt)
@@ -441,15 +454,7 @@ def _bayes(model, sample, alpha, n, random_state, de_bw_method, de_weights, mapp
         algorithm, cv = _setup_optimize(inst, mapping, algorithm, control_vector, bounds, jobs_fun, wjobs_fun, gauge, wgauge,
                                         ost_step, False)
         if sample is None:
-            o = inst.setup._optimize
-            bnd = []
-            for c in cv:
-                if c in GPARAMETERS_NAME:
-                    k = GPARAMETERS_NAME.index(c)
-                    bnd.append([o.lb_parameters[k].item(), o.ub_parameters[k].item()])
-                else:
-                    k = GSTATES_NAME.index(c)
-                    bnd.append([o.lb_states[k].item(), o.ub_states[k].item()])
+            bnd = _control_bounds(inst.setup._optimize, cv)
             sample = generate_samples({"num_vars": len(cv), "names": list(cv), "bounds": bnd}, "uniform", n, random_state)
         elif set(sample._problem["names"]) != set(cv):
             raise ValueError(f"Problem names ({sample._problem['names']}) and control vectors ({cv}) must have the same elements")
@@ -574,9 +579,7 @@ def ann_optimize(model, net=None, optimizer="adam", learning_rate=0.003, control
     _, cv = _setup_optimize(inst, "uniform", "sbs", control_vector, bounds, jobs_fun, wjobs_fun, gauge, wgauge, ost_step, verbose)
     o = inst.setup._optimize
     o.mapping = "..."
-    bnd = np.array([[(o.lb_parameters if c in GPARAMETERS_NAME else o.lb_states)[(GPARAMETERS_NAME if c in GPARAMETERS_NAME else GSTATES_NAME).index(c)],
-                     (o.ub_parameters if c in GPARAMETERS_NAME else o.ub_states)[(GPARAMETERS_NAME if c in GPARAMETERS_NAME else GSTATES_NAME).index(c)]]
-                    for c in cv], dtype=np.float32)
+    bnd = np.array(_control_bounds(o, cv), dtype=np.float32)
     parameters_bgd, states_bgd = inst.parameters.copy(), inst.states.copy()
     desc = inst.input_data.descriptor
     nd = int(inst.setup._nd)
