@@ -175,7 +175,9 @@ void smash_b200_clear_cache(void);           /* drop cached mesh plans and devic
  * ticketed chains of the routing pass are handed out from ready queues (a chain is queued when its last tributary chain has
  * finished; one queue per basin of a long river, longest first, "route_queues" of them, plus one for the rest), 0 = static
  * ticket order with done-flag waits; "route_order" = static ticket order: 0 by topological level (default), 1 by distance
- * to the outlet, 2 basin by basin (both measured slower). */
+ * to the outlet, 2 basin by basin (both measured slower); diagnostics: "route_ctas_per_sm" (1 / 2:
+ * fewer routing CTAs per SM than fit), "plan_small_windows" (256-step routing windows in plans of the plan API),
+ * "dbg_prof" (per-river-chain cycle counts on stderr). */
 int smash_b200_set_option(const char *name, long long value);
 
 /* ---- device-resident plan API (bench / advanced callers) --------------------------------------
