@@ -104,6 +104,21 @@ struct SplitState {
     const float *tape_mapped = nullptr;
     size_t tape_rows = 0;
     SplitTopo topo{};
+    DBuf<uint8_t> d_deep;          // graph of the deep cells only: SplitTopo::deep
+};
+
+// window pass (window_kernels.cu) + chain scans over the deep cells only: forward runs of large domains
+struct WindowState {
+    bool on = false;
+    WindowTopoHost host;
+    SplitState deep;               // route graph of the deep cells and its device image (graph members only)
+    DBuf<int32_t> d_meta, d_upoff, d_ups;
+    DBuf<uint8_t> d_rounds;
+    DBuf<float4> d_cc;
+    DBuf<float> d_X;
+    DBuf<int> d_prog;
+    int nx = 2;
+    WfTopo topo{};
 };
 
 // Opt-in (option "pin_host" = 1): large caller-owned host arrays (forcing in, domain series out) are page-locked in place
@@ -141,6 +156,7 @@ struct SmashPlan {
     int sparse = 0;                 // setup.sparse_storage the plan was built for
     bool ensemble = false;          // plan made for compute_multiple_run / a multi-member plan: lane = member routing
     SplitState sp;
+    WindowState win;
     std::vector<int32_t> col_cell;  // per device column (slot / cell j): flat rect index or -1 on padding
     int ncols = 0;                  // columns of the per-cell device arrays (fields, fstates, grad)
     int nmember = 0;
@@ -285,35 +301,11 @@ static int plan_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *m
     return 0;
 }
 
-// ---- split engine: build -------------------------------------------------------------------------
-static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, bool *unsupported) {
-    SplitState &sp = pl.sp;
+// device image of a route graph (sp.rg -> sp.topo): the full graph of a mesh, or the deep-cell graph of the window pass
+static int upload_route_graph(SplitState &sp, int ng, cudaStream_t s) {
     RouteGraph &rg = sp.rg;
-    std::string err = build_route_graph(rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
-                                        mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
-                                        (int)option("route_ded_max", option("river_wave", 0) ? 224 : 64),
-                                        option("river_wave", 0) ? 128 : 0, (int)option("route_order", 0));
-    if (!err.empty()) {
-        *unsupported = err.rfind("unsupported", 0) == 0;
-        return fail(SMASH_B200_EINVAL, "%s", err.c_str());
-    }
-    const int ncell = mesh->nrow * mesh->ncol;
-    pl.dt = setup->dt; pl.dx = mesh->dx; pl.ncell = ncell; pl.nmember = 0;
-    Topology &tp = pl.tp;
-    tp = Topology();
-    tp.nrow = mesh->nrow; tp.ncol = mesh->ncol; tp.ng = mesh->ng; tp.T = setup->ntime_step; tp.B = 256;
-    tp.nactive = rg.n; tp.nslots = rg.npad; tp.nblocks = (rg.n + 255) / 256; tp.n_pairs = rg.npair;
-    tp.sparse_k.assign(rg.npad, -1);
-    for (int j = 0; j < rg.n; j++) tp.sparse_k[j] = rg.sparse_k[j];
-    tp.gauge_slot = rg.gauge_cell;
-    sp.W = split_pick_window(tp.T, &sp.S, &sp.nwin, pl.small_windows);
-    sp.Tp = sp.W * sp.nwin;
-    CU(cudaStreamCreateWithFlags(&pl.stream, cudaStreamNonBlocking));
-    CU(cudaEventCreate(&pl.ev0)); CU(cudaEventCreate(&pl.ev1)); CU(cudaEventCreate(&pl.ev2));
-    for (auto &e : pl.evk) CU(cudaEventCreate(&e));
-    cudaStream_t s = pl.stream;
     const int npad = rg.npad;
-    std::vector<int32_t> cell(npad, -1), flw(npad, 1), down(npad, -1), down_task(npad, -1), gfirst(npad, -1);
+    std::vector<int32_t> flw(npad, 1), down(npad, -1), down_task(npad, -1), gfirst(npad, -1);
     std::vector<uint8_t> down_lag(npad, 0);
     std::vector<int32_t> down_need(npad, 0xffff), pos_in_task(rg.n, 0);
     for (int t = 0; t < rg.ntask; t++)
@@ -326,10 +318,9 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
         }
     }
     for (int j = 0; j < rg.n; j++) {
-        cell[j] = rg.cell[j]; flw[j] = rg.flwacc[j]; down[j] = rg.down[j]; down_task[j] = rg.down_task[j]; gfirst[j] = rg.gauge_first[j];
+        flw[j] = rg.flwacc[j]; down[j] = rg.down[j]; down_task[j] = rg.down_task[j]; gfirst[j] = rg.gauge_first[j];
         if (rg.down[j] >= 0 && j > rg.down[j]) down_lag[j] = 1;   // producer later in path: the reader sees its previous step
     }
-    TRY(pl.d_cell.upload(cell, s)); TRY(pl.d_sparse_k.upload(tp.sparse_k, s));
     TRY(sp.d_flwacc.upload(flw, s)); TRY(sp.d_up_begin.upload(rg.up_begin, s)); TRY(sp.d_up.upload(rg.up, s));
     TRY(sp.d_down.upload(down, s)); TRY(sp.d_down_task.upload(down_task, s)); TRY(sp.d_down_need.upload(down_need, s)); TRY(sp.d_down_lag.upload(down_lag, s));
     TRY(sp.d_task_begin.upload(rg.task_begin, s)); TRY(sp.d_task_cells.upload(rg.task_cells, s));
@@ -380,14 +371,82 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
         TRY(sp.d_queue0.upload(queue0, s)); TRY(sp.d_qctl0.upload(qctl0, s));
         TRY(sp.d_queue.ensure(queue0.size())); TRY(sp.d_ndep.ensure(ndep0.size())); TRY(sp.d_qctl.ensure(32));
     }
-    TRY(pl.d_ticket.ensure(2)); TRY(pl.d_sum.ensure(1));
     SplitTopo &t = sp.topo;
-    t.n = rg.n; t.npad = npad; t.ng = mesh->ng; t.ntask = rg.ntask; t.nchain = rg.nchain; t.nded = rg.nded;
+    t.n = rg.n; t.npad = npad; t.ng = ng; t.ntask = rg.ntask; t.nchain = rg.nchain; t.nded = rg.nded;
     t.flwacc = sp.d_flwacc.p; t.up_begin = sp.d_up_begin.p; t.up = sp.d_up.p; t.down = sp.d_down.p; t.down_task = sp.d_down_task.p; t.down_need = sp.d_down_need.p;
     t.down_lag = sp.d_down_lag.p; t.task_begin = sp.d_task_begin.p; t.task_cells = sp.d_task_cells.p;
     t.gauge_first = sp.d_gfirst.p; t.gauge_next = sp.d_gnext.p; t.cell_task = sp.d_cell_task.p;
     t.nrouted = (int)rlist.size(); t.rlist = sp.d_rlist.p; t.rindex = sp.d_rindex.p;
     t.tcell = reinterpret_cast<const int4 *>(sp.d_tcell.p); t.tup = reinterpret_cast<const int2 *>(sp.d_tup.p);
+    return 0;
+}
+
+// ---- window pass: classes, deep-cell graph, exchange buffer ---------------------------------------
+// Forward runs of large domains (no tape, one member): window_kernels.cu routes the shallow cells inside the reservoir pass,
+// the chain scans then only see the deep cells.  Not eligible (tiny domain, option off, unsupported mesh): win.on stays false
+// and the run uses the row-based passes.
+static int window_build(SmashPlan &pl, const SmashMesh *mesh) {
+    WindowState &wn = pl.win;
+    const RouteGraph &rg = pl.sp.rg;
+    wn.on = false;
+    if (!option("window_pass", 1) || rg.n < option("window_min_cells", 65536)) return 0;
+    if (!build_window_topo(rg, (int)option("shallow_acc", 32), wn.host).empty()) return 0;
+    std::string err = build_route_graph(wn.deep.rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
+                                        mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
+                                        (int)option("route_ded_max", 64), 0, 0, wn.host.deep.data());
+    if (!err.empty() || wn.deep.rg.n != rg.n) return 0;
+    cudaStream_t s = pl.stream;
+    const size_t npad = (size_t)rg.npad, ntile = npad / 32;
+    TRY(upload_route_graph(wn.deep, mesh->ng, s));
+    TRY(wn.deep.d_deep.upload(wn.host.deep, s));
+    wn.deep.topo.deep = wn.deep.d_deep.p;
+    TRY(wn.deep.d_done.ensure(std::max<size_t>(1, 2 * (size_t)wn.deep.rg.ntask)));
+    TRY(wn.d_meta.upload(wn.host.meta, s)); TRY(wn.d_upoff.upload(wn.host.upoff, s)); TRY(wn.d_ups.upload(wn.host.ups, s));
+    TRY(wn.d_rounds.upload(wn.host.tile_rounds, s));
+    wn.nx = (int)std::min<long long>(2, std::max<long long>(1, option("window_nx", 2)));
+    TRY(wn.d_cc.ensure(npad)); TRY(wn.d_X.ensure((size_t)wn.nx * npad * WF_W)); TRY(wn.d_prog.ensure(ntile));
+    CU(cudaMemsetAsync(wn.d_X.p, 0, (size_t)wn.nx * npad * WF_W * sizeof(float), s));
+    WfTopo &t = wn.topo;
+    t.n = rg.n; t.npad = (int)npad; t.ntile = (int)ntile; t.ng = mesh->ng;
+    t.meta = wn.d_meta.p; t.upoff = wn.d_upoff.p; t.ups = wn.d_ups.p; t.down = pl.sp.d_down.p; t.tile_rounds = wn.d_rounds.p;
+    t.gauge_first = pl.sp.d_gfirst.p; t.gauge_next = pl.sp.d_gnext.p;
+    wn.on = true;
+    return 0;
+}
+
+// ---- split engine: build -------------------------------------------------------------------------
+static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, bool *unsupported) {
+    SplitState &sp = pl.sp;
+    RouteGraph &rg = sp.rg;
+    std::string err = build_route_graph(rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
+                                        mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
+                                        (int)option("route_ded_max", option("river_wave", 0) ? 224 : 64),
+                                        option("river_wave", 0) ? 128 : 0, (int)option("route_order", 0));
+    if (!err.empty()) {
+        *unsupported = err.rfind("unsupported", 0) == 0;
+        return fail(SMASH_B200_EINVAL, "%s", err.c_str());
+    }
+    const int ncell = mesh->nrow * mesh->ncol;
+    pl.dt = setup->dt; pl.dx = mesh->dx; pl.ncell = ncell; pl.nmember = 0;
+    Topology &tp = pl.tp;
+    tp = Topology();
+    tp.nrow = mesh->nrow; tp.ncol = mesh->ncol; tp.ng = mesh->ng; tp.T = setup->ntime_step; tp.B = 256;
+    tp.nactive = rg.n; tp.nslots = rg.npad; tp.nblocks = (rg.n + 255) / 256; tp.n_pairs = rg.npair;
+    tp.sparse_k.assign(rg.npad, -1);
+    for (int j = 0; j < rg.n; j++) tp.sparse_k[j] = rg.sparse_k[j];
+    tp.gauge_slot = rg.gauge_cell;
+    sp.W = split_pick_window(tp.T, &sp.S, &sp.nwin, pl.small_windows);
+    sp.Tp = sp.W * sp.nwin;
+    CU(cudaStreamCreateWithFlags(&pl.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&pl.ev0)); CU(cudaEventCreate(&pl.ev1)); CU(cudaEventCreate(&pl.ev2));
+    for (auto &e : pl.evk) CU(cudaEventCreate(&e));
+    cudaStream_t s = pl.stream;
+    const int npad = rg.npad;
+    std::vector<int32_t> cell(npad, -1);
+    for (int j = 0; j < rg.n; j++) cell[j] = rg.cell[j];
+    TRY(pl.d_cell.upload(cell, s)); TRY(pl.d_sparse_k.upload(tp.sparse_k, s));
+    TRY(upload_route_graph(sp, mesh->ng, s));
+    TRY(pl.d_ticket.ensure(2)); TRY(pl.d_sum.ensure(1));
     // the field gather kernel only needs the column -> cell map
     pl.dtp = DeviceTopology{};
     pl.dtp.T = tp.T; pl.dtp.B = 256; pl.dtp.nblocks = tp.nblocks; pl.dtp.nslots = npad; pl.dtp.ng = mesh->ng; pl.dtp.cell = pl.d_cell.p;
@@ -400,6 +459,7 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
         TRY(pl.d_gauge_flwacc.upload(pl.gauge_flwacc, s));
     }
     TRY(pl.d_planes.ensure((size_t)NFIELD * ncell));
+    TRY(window_build(pl, mesh));
     CU(cudaStreamSynchronize(s));
     pl.col_cell = cell;
     pl.ncols = npad;
@@ -441,11 +501,14 @@ static int split_members(SmashPlan &pl, int nmember, bool save_q, bool save_netp
     return 0;
 }
 
-static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp) {
+// graph: the route graph the routing kernels walk (default: the full graph of the mesh; the window pass hands the chain
+// scans the graph of the deep cells)
+static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp, SplitState *graph = nullptr) {
     SplitState &sp = pl.sp;
+    SplitState &gr = graph ? *graph : pl.sp;
     SplitArgs a{};
-    a.tp = sp.topo; a.T = pl.tp.T; a.Tp = sp.Tp; a.W = sp.W; a.nwin = sp.nwin; a.nmember = pl.nmember; a.dt = pl.dt; a.dx = pl.dx;
-    a.first_routed = sp.rg.first_routed;
+    a.tp = gr.topo; a.T = pl.tp.T; a.Tp = sp.Tp; a.W = sp.W; a.nwin = sp.nwin; a.nmember = pl.nmember; a.dt = pl.dt; a.dx = pl.dx;
+    a.first_routed = gr.rg.first_routed;
     a.t_begin = 0; a.t_end = pl.tp.T;
     a.dbg_prof = nullptr;
     if (option("dbg_prof", 0) && sp.rg.nded > 0 && sp.rg.nded <= 256) {
@@ -476,12 +539,12 @@ static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp) {
     a.river_wave = (int)option("river_wave", 0);
     a.fuse_export = 0;
     a.route_ctas_per_sm = (int)option("route_ctas_per_sm", 0);
-    a.dyn = (option("route_dynamic", 1) != 0 && pl.nmember == 1 && sp.rg.nchain > sp.rg.nded) ? 1 : 0;
-    a.dyn_nq = sp.dyn_nq; a.qctl = sp.d_qctl.p; a.queue = sp.d_queue.p; a.ndep = sp.d_ndep.p; a.cons = sp.d_cons.p; a.qid = sp.d_qid.p;
-    a.qoff = sp.d_qoff.p; a.qctl0 = sp.d_qctl0.p; a.queue0 = sp.d_queue0.p; a.ndep0 = sp.d_ndep0.p;
+    a.dyn = (option("route_dynamic", 1) != 0 && pl.nmember == 1 && gr.rg.nchain > gr.rg.nded) ? 1 : 0;
+    a.dyn_nq = gr.dyn_nq; a.qctl = gr.d_qctl.p; a.queue = gr.d_queue.p; a.ndep = gr.d_ndep.p; a.cons = gr.d_cons.p; a.qid = gr.d_qid.p;
+    a.qoff = gr.d_qoff.p; a.qctl0 = gr.d_qctl0.p; a.queue0 = gr.d_queue0.p; a.ndep0 = gr.d_ndep0.p;
     a.fields = pl.d_fields.p; a.fstates = pl.d_fstates.p; a.rows = sp.d_rows.p; a.qdom = pl.d_qdom.p; a.netp = pl.d_netp.p;
     a.qpitch = sp.qpitch; a.qsim = pl.d_qsim.p; a.tape_hp = sp.d_tape_hp.p; a.tape_hft = sp.d_tape_hft.p; a.rows_hr = sp.d_rows_hr.p;
-    a.hcar = sp.d_hcar.p; a.done = sp.d_done.p; a.ticket = pl.d_ticket.p; a.qsim_b = pl.d_qsim_b.p; a.rows_w = sp.d_rows_w.p;
+    a.hcar = sp.d_hcar.p; a.done = graph ? gr.d_done.p : sp.d_done.p; a.ticket = pl.d_ticket.p; a.qsim_b = pl.d_qsim_b.p; a.rows_w = sp.d_rows_w.p;
     a.gcar = sp.d_gcar.p; a.grad = pl.d_grad.p; a.rdone = sp.d_rdone.p;
     return a;
 }
@@ -497,6 +560,26 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
     // routing state of window 0 = the hlr field
     CU(cudaMemcpy2DAsync(sp.d_hcar.p, npad * sizeof(float), pl.d_fields.p + (size_t)F_HLR * npad, (size_t)NFIELD * npad * sizeof(float),
                          npad * sizeof(float), (size_t)pl.nmember, cudaMemcpyDeviceToDevice, pl.stream));
+    if (pl.win.on && !tape && pl.nmember == 1 && !pl.ensemble && math_mode() == 1) {
+        // window pass: reservoirs of every cell + routing of the shallow cells; then the chain scans over the deep cells
+        WindowState &wn = pl.win;
+        WfArgs wa{};
+        wa.tp = wn.topo; wa.T = pl.tp.T; wa.Tp = sp.Tp; wa.w_begin = 0; wa.w_end = (pl.tp.T + WF_W - 1) / WF_W; wa.nx = wn.nx;
+        wa.dt = pl.dt; wa.dx = pl.dx; wa.save_q = save_q ? 1 : 0; wa.save_netp = save_netp ? 1 : 0;
+        wa.cc = wn.d_cc.p; wa.fstates = pl.d_fstates.p; wa.X = wn.d_X.p; wa.rows = sp.d_rows.p; wa.qdom = pl.d_qdom.p;
+        wa.netp = pl.d_netp.p; wa.qpitch = sp.qpitch; wa.qsim = pl.d_qsim.p; wa.prog = wn.d_prog.p;
+        CU(launch_window_forward(wa, pl.d_fields.p, sp.tm_prcp, sp.tm_pet, pl.stream, (int)option("window_ctas_per_sm", 0),
+                                 (int)option("window_variant", 8)));
+        mark(1);
+        SplitArgs b = split_args(pl, save_q, save_netp, &wn.deep);
+        b.fuse_export = save_q ? (int)option("fuse_export", 4) : 0;
+        CU(launch_route_forward(b, false, pl.stream));
+        mark(2);
+        pl.launches += 2 + sp.nwin * (1 + (wn.deep.rg.npair > 0 ? 1 : 0));
+        if (save_q && !b.fuse_export) { CU(launch_rows_to_domain(b, pl.stream)); pl.launches++; }
+        mark(3);
+        return 0;
+    }
     CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), tape, pl.stream));
     mark(1);
     // ensembles on a small mesh: lane = member, exact sequential routing; otherwise the per-chain scan

@@ -13,7 +13,7 @@ static const int RG_DROW[8] = {1, 1, 0, -1, -1, -1, 0, 1};
 
 std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const int32_t *flwdir, const int32_t *flwacc,
                               const int32_t *active_cell, const int32_t *local_active_cell, const int32_t *path,
-                              const int32_t *gauge_pos, int ded_min, int ded_max, int reach, int order) {
+                              const int32_t *gauge_pos, int ded_min, int ded_max, int reach, int order, const uint8_t *deep_mask) {
     const int ncell = nrow * ncol;
     if (nrow <= 0 || ncol <= 0) return "mesh: nrow and ncol must be positive";
     g = RouteGraph();
@@ -52,9 +52,10 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
     g.up_begin.assign(n + 1, 0);
     g.down.assign(n, -1);
     std::vector<uint8_t> lagged;   // per up entry: producer later in path (reader sees the previous time step)
+    auto routed = [&](int j) { return deep_mask ? deep_mask[j] != 0 : g.flwacc[j] > 1; };
     for (int j = 0; j < n; j++) {
         g.up_begin[j] = (int32_t)g.up.size();
-        if (g.flwacc[j] <= 1) continue;
+        if (g.flwacc[j] <= 1 || !routed(j)) continue;
         const int c = g.cell[j];
         const int row = c % nrow, col = c / nrow;
         for (int i = 0; i < 8; i++) {
@@ -105,7 +106,7 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
     std::vector<int32_t> chain_of(n, -1);
     for (int j = 0; j < n; j++) {
         if (heavy[j] >= 0 || partner[j] >= 0) continue;          // not a chain head
-        if (next[j] < 0 && g.flwacc[j] <= 1) continue;           // lone source cell: final after the reservoir pass
+        if (next[j] < 0 && !routed(j)) continue;                 // lone source cell: final after the reservoir pass
         std::vector<int32_t> ch;
         for (int c = j; c >= 0; c = next[c]) {
             if (chain_of[c] >= 0) return "mesh: flow directions contain a cycle";
@@ -115,7 +116,7 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
         chains.push_back(std::move(ch));
     }
     for (int j = 0; j < n; j++)
-        if (chain_of[j] < 0 && partner[j] < 0 && (heavy[j] >= 0 || g.flwacc[j] > 1))
+        if (chain_of[j] < 0 && partner[j] < 0 && (heavy[j] >= 0 || routed(j)))
             return "mesh: flow directions contain a cycle longer than two cells";
 
     // ---- river reaches (reach > 0): the longest chains, as many as ded_max dedicated CTAs can take, are cut into reaches
@@ -292,14 +293,62 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
         TaskCell tc;
         tc.j = j;
         const int nup = g.up_begin[j + 1] - g.up_begin[j];
-        tc.meta = (g.flwacc[j] > 1 ? 1 : 0) | (g.gauge_first[j] >= 0 ? 2 : 0) | (nup << 8);
+        tc.meta = (routed(j) ? 1 : 0) | (g.gauge_first[j] >= 0 ? 2 : 0) | (nup << 8);
         tc.up_off = (int32_t)g.tup.size();
         tc.pad_ = 0;
         for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) g.tup.push_back(g.up[e]);
         g.tcell[i] = tc;
     }
     g.first_routed = n;
-    for (int j = 0; j < n; j++) if (g.flwacc[j] > 1) { g.first_routed = j; break; }
+    for (int j = 0; j < n; j++) if (routed(j) && (!deep_mask || partner[j] < 0)) { g.first_routed = j; break; }
+    return "";
+}
+
+// ------------------------------------------------------------------------------------------------
+// Classes of the window pass (window_kernels.cu) from the full route graph.  Cells are visited in path order, which is a
+// topological order of every non-lagged edge: a cell is deep when its flow accumulation exceeds shallow_acc, when it sits in
+// a pit pair, or when one of its inflows is deep or lagged; every other gathering cell is shallow and routed inside the
+// window pass.
+// ------------------------------------------------------------------------------------------------
+std::string build_window_topo(const RouteGraph &g, int shallow_acc, WindowTopoHost &out) {
+    const int n = g.n, npad = g.npad, ntile = npad / 32;
+    out = WindowTopoHost();
+    out.meta.assign(npad, 0); out.upoff.assign(npad, 0); out.deep.assign(npad, 0); out.tile_rounds.assign(ntile, 0);
+    std::vector<uint8_t> cls(n, 0), round(n, 0);
+    for (int j = 0; j < n; j++) {
+        const int nup = g.up_begin[j + 1] - g.up_begin[j];
+        if (g.flwacc[j] <= 1) { cls[j] = 0; continue; }
+        // flwacc > 1 without a computed inflow: still routed (qup = 0, md_forward_structure.f90:146-156)
+        bool deep = g.flwacc[j] > shallow_acc || nup > 8 || (g.flwacc[j] - 1) >= (1 << 19);
+        int r = 0;
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1] && !deep; e++) {
+            const int s = g.up[e].src;
+            if (g.up[e].task == UP_PARTNER || s >= j || cls[s] == 2) { deep = true; break; }
+            if (cls[s] == 1 && (s >> 5) == (j >> 5)) r = std::max(r, round[s] + 1);
+        }
+        if (!deep && r > 7) deep = true;
+        cls[j] = deep ? 2 : 1;
+        round[j] = deep ? 0 : (uint8_t)r;
+    }
+    for (int j = 0; j < n; j++) {
+        const int nup = (cls[j] == 1) ? g.up_begin[j + 1] - g.up_begin[j] : 0;
+        const int d = g.down[j];
+        const bool want_x = d >= 0 && cls[d] == 1, want_row = d >= 0 && cls[d] == 2 && cls[j] != 2;
+        out.upoff[j] = (int32_t)out.ups.size();
+        for (int e = 0; e < nup; e++) out.ups.push_back(g.up[g.up_begin[j] + e].src);
+        out.meta[j] = cls[j] | (want_x ? 4 : 0) | (want_row ? 8 : 0) | (g.gauge_first[j] >= 0 ? 16 : 0) | (round[j] << 5) | (nup << 8) |
+                      (std::min(g.flwacc[j] - 1, (1 << 19) - 1) << 12);
+        out.deep[j] = cls[j] == 2;
+        if (cls[j] == 1) {
+            out.nshallow++;
+            out.tile_rounds[j >> 5] = std::max<uint8_t>(out.tile_rounds[j >> 5], (uint8_t)(round[j] + 1));
+            out.max_round = std::max(out.max_round, (int)round[j]);
+        }
+        if (cls[j] == 2) out.ndeep++;
+        if (want_row) out.nrow++;
+        if (want_x) out.nx_cells++;
+    }
+    if (out.ups.empty()) out.ups.push_back(-1);
     return "";
 }
 

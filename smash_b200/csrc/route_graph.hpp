@@ -69,11 +69,24 @@ struct RouteGraph {
 // Returns "" on success; "unsupported: ..." when the mesh needs the fused engine (lagged inflows outside pit pairs).
 std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const int32_t *flwdir, const int32_t *flwacc,
                               const int32_t *active_cell, const int32_t *local_active_cell, const int32_t *path,
-                              const int32_t *gauge_pos, int ded_min = 96, int ded_max = 64, int reach = 0, int order = 0);
+                              const int32_t *gauge_pos, int ded_min = 96, int ded_max = 64, int reach = 0, int order = 0,
+                              const uint8_t *deep_mask = nullptr);
+// deep_mask (per computed cell j, or nullptr): graph of the chain scans that follow the window pass (window_kernels.cu).
+// Only cells with deep_mask[j] != 0 gather and are routed; every other cell is final (a "source") when the scans start.
 // order: ticket order of the chains -- 0 by the topological level of the chain's last cell, 1 by its distance to the outlet
 // (farthest first)
 // ded_min / ded_max: chains of at least ded_min cells, the longest first, get CTAs of their own in the forward routing
 // pass, at most ded_max CTAs.  reach > 0: those chains are cut into reaches of at most `reach` cells, one CTA per reach
 // (tick wavefront, the reaches of a river pipelined); reach = 0: one CTA per whole chain (window scan per cell).
+
+// host side of the window pass topology (WfTopo, split_kernels.cuh)
+struct WindowTopoHost {
+    std::vector<int32_t> meta, upoff, ups;
+    std::vector<uint8_t> tile_rounds, deep;
+    int nshallow = 0, ndeep = 0, nrow = 0, nx_cells = 0, max_round = 0;
+};
+// Classes of the window pass from the full route graph; shallow_acc = largest flwacc routed inside the window pass.
+// Returns "" or "unsupported: ...".
+std::string build_window_topo(const RouteGraph &g, int shallow_acc, WindowTopoHost &out);
 
 }  // namespace smash

@@ -1125,7 +1125,7 @@ __device__ __forceinline__ bool tile_ready(const SplitArgs &a, int m, int j0, in
     const SplitTopo &tp = a.tp;
     const int j = j0 + lane;
     bool ok = true;
-    if (j < tp.n && tp.flwacc[j] > 1) {
+    if (j < tp.n && (tp.deep ? tp.deep[j] != 0 : tp.flwacc[j] > 1)) {
         const int task = tp.cell_task[j];
         if (task >= 0 && task < tp.nchain) ok = ld_acquire(a.done + (size_t)m * tp.ntask + task) >= epoch;
     }
@@ -1137,7 +1137,7 @@ __device__ __forceinline__ void export_tile(const SplitArgs &a, float *tile, int
     const SplitTopo &tp = a.tp;
     const int j = j0 + lane;
     const int task = j < tp.n ? tp.cell_task[j] : -1;
-    const bool mine = j < tp.n && tp.flwacc[j] > 1 && task < tp.nchain;      // pit pairs are routed (and exported) afterwards
+    const bool mine = j < tp.n && (tp.deep ? tp.deep[j] != 0 : tp.flwacc[j] > 1) && task < tp.nchain;   // pit pairs are routed (and exported) afterwards
     if (wait && mine && task >= 0) {
         const int *flag = a.done + (size_t)m * tp.ntask + task;
         while (ld_acquire(flag) < epoch) __nanosleep(128);
@@ -1386,7 +1386,7 @@ __global__ void __launch_bounds__(256) rows_to_domain_kernel(const SplitArgs a, 
     }
     __syncthreads();
     const int j = j0 + lane;
-    if (j < a.tp.n && a.tp.flwacc[j] > 1)
+    if (j < a.tp.n && (a.tp.deep ? a.tp.deep[j] != 0 : a.tp.flwacc[j] > 1))
         for (int i = warp; i < RD_T; i += 8) {
             const int t = t0 + i;
             if (t < a.t_end) a.qdom[((size_t)m * a.T + t) * a.qpitch + j] = tile[lane][i];
@@ -1810,7 +1810,15 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
     const long long need = (total + 3) / 4 + ded_blocks;
     const int npair = (a.tp.ntask - a.tp.nchain) * a.nmember;
     if (blocks > need) blocks = need > 0 ? (int)need : 1;
-    if (blocks <= ded_blocks) return cudaErrorLaunchOutOfResources;
+    if (blocks <= ded_blocks) {
+        // every chain is a dedicated one (e.g. a straight channel): one more CTA for the export tiles; the dedicated CTAs
+        // must all be resident
+        int limit = 0;
+        e = tape ? persistent_grid(route_forward_kernel<S, 1>, &limit) : persistent_grid(route_forward_kernel<S, 0>, &limit);
+        if (e != cudaSuccess) return e;
+        if (ded_blocks + 1 > limit) return cudaErrorLaunchOutOfResources;
+        blocks = ded_blocks + 1;
+    }
     for (int w = w_begin; w < w_end; w++) {
         e = cudaMemsetAsync(a.ticket, 0, 2 * sizeof(unsigned int), s);
         if (e != cudaSuccess) return e;

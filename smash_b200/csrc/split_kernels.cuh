@@ -39,6 +39,9 @@ struct SplitTopo {
     const int32_t *cell_task;    // [npad] task that routes the cell, -1 for lone source cells and padding
     const int32_t *gauge_first;  // [npad]
     const int32_t *gauge_next;   // [ng]
+    const uint8_t *deep;         // [npad] or nullptr.  Set for the graph of the deep cells that follows the window pass: 1 = the
+                                 // cell is routed by the chain scans; every other cell is final when they start (nullptr: the
+                                 // cells with flwacc > 1 are routed)
 };
 
 struct SplitArgs {
@@ -83,6 +86,43 @@ struct SplitArgs {
     float *grad;                 // [m][NFIELD][npad]
     int *rdone;                  // [m][ntask]
 };
+
+// ---- window pass (window_kernels.cu): reservoirs of every cell + routing of the shallow cells, 8 steps at a time ----------
+constexpr int WF_W = 8;          // time steps per window = one TMA box = one 32-byte sector of a row
+
+struct WfTopo {
+    int n, npad, ntile, ng;
+    const int32_t *meta;         // [npad] bits 0-1 class (0 source, 1 shallow routed, 2 deep), bit 2: the consumer reads the exchange
+                                 // buffer, bit 3: the consumer is a deep cell (the series is also written as a row), bit 4: gauge,
+                                 // bits 5-7: round inside the tile, bits 8-11: inflows, bits 12-: flwacc - 1
+    const int32_t *upoff;        // [npad] first inflow entry of a shallow routed cell
+    const int32_t *ups;          // producer cells, reference summation order (md_routing_operator.f90:37-53)
+    const int32_t *down;         // [npad] consumer cell or -1
+    const uint8_t *tile_rounds;  // [ntile] dependency rounds inside the tile (0: no shallow routed cell)
+    const int32_t *gauge_first;  // [npad]
+    const int32_t *gauge_next;   // [ng]
+};
+
+struct WfArgs {
+    WfTopo tp;
+    int T, Tp;                   // time steps; pitch of the deep rows
+    int w_begin, w_end;          // windows of this launch
+    int nx;                      // slots of the exchange buffer (windows a block stays readable): 1 or 2
+    float dt, dx;
+    int save_q, save_netp;
+    float4 *cc;                  // [npad] cp, cft, exc, exp(-dt / (60 lr))
+    float *fstates;              // [3][npad] reservoir and routing states carried from window to window; final states
+    float *X;                    // [nx][npad][WF_W] discharge blocks handed from producer to consumer (L2-resident)
+    float *rows;                 // [npad][Tp] qt of the deep cells, q of the cells that flow into a deep cell
+    float *qdom, *netp;          // [T][qpitch]
+    int64_t qpitch;
+    float *qsim;                 // [T][ng]
+    int *prog;                   // [ntile] windows finished
+};
+
+// all windows [w_begin, w_end); w_begin == 0 also prepares the per-cell constants and the carried states from `fields`
+cudaError_t launch_window_forward(const WfArgs &a, const float *fields, const CUtensorMap &prcp, const CUtensorMap &pet, cudaStream_t s,
+                                  int ctas_per_sm = 0, int variant = 8);
 
 // 2-D tensor map over a [rows][pitch] float array, box = 8 rows x 32 columns.  cols = valid columns (the rest reads 0).
 int make_tensor_map_2d(CUtensorMap *tm, const float *base, uint64_t cols, uint64_t rows, uint64_t pitch_elems, const char **err);

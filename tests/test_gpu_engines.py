@@ -245,3 +245,58 @@ def test_domain_split_by_basin_equals_full_run():
     a, b = np.asarray(got, np.float64), np.asarray(full.output.sparse_qsim_domain, np.float64)
     assert np.all(np.abs(a - b) <= 1e-9 + 1e-6 * np.abs(b)), float(np.abs(a - b).max())
     L.lib().smash_b200_clear_cache()
+
+
+def _run_window(m, opts):
+    lib = L.lib()
+    for k, v in opts.items():
+        lib.smash_b200_set_option(k.encode(), v)
+    lib.smash_b200_clear_cache()
+    try:
+        smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
+        return m
+    finally:
+        for k in opts:
+            lib.smash_b200_set_option(k.encode(), {"window_pass": 1, "shallow_acc": 32, "window_nx": 2, "window_variant": 8,
+                                                   "window_min_cells": 65536}[k])
+        lib.smash_b200_clear_cache()
+
+
+@pytest.mark.parametrize("opts", [{"shallow_acc": 32}, {"shallow_acc": 3, "window_nx": 1}, {"shallow_acc": 100000, "window_variant": 6},
+                                  {"shallow_acc": 200, "window_variant": 4}])
+def test_window_pass_agrees_with_row_passes(opts):
+    # forward runs of large domains: the window pass (reservoirs + routing of the shallow cells, 8 steps at a time, discharge
+    # blocks handed over through the L2-resident exchange buffer) followed by the chain scans over the deep cells, against the
+    # row-based passes (window_pass = 0).  T = 100 ends in a partial window; shallow_acc moves the class boundary from
+    # "almost everything deep" to "everything shallow" (then the pit pairs are the only deep cells).
+    def model():
+        m = cases.france(T=100, sub=(250, 900, 250, 900), ngauge=4)
+        random_fields(m, seed=11)
+        m.setup.save_net_prcp_domain = True
+        m.output = type(m.output)(m.setup, m.mesh)
+        return m
+    o = dict(opts)
+    o["window_min_cells"] = 1000
+    a = _run_window(model(), o)
+    b = _run_window(model(), {"window_pass": 0})
+    assert a.mesh.nac > 100000
+    for name, x, y in (("qsim", a.output.qsim, b.output.qsim), ("qdom", a.output.sparse_qsim_domain, b.output.sparse_qsim_domain),
+                       ("netp", a.output.sparse_net_prcp_domain, b.output.sparse_net_prcp_domain),
+                       ("hlr", a.output.fstates.hlr, b.output.fstates.hlr), ("hp", a.output.fstates.hp, b.output.fstates.hp),
+                       ("hft", a.output.fstates.hft, b.output.fstates.hft)):
+        x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+        assert np.all(np.abs(x - y) <= 1e-7 + 1e-5 * np.abs(y)), (name, float(np.abs(x - y).max()))
+    assert np.isclose(float(a.output.cost), float(b.output.cost), rtol=1e-5)
+
+
+def test_window_pass_against_oracle():
+    import oracle
+    m = cases.france(T=50, sub=(400, 700, 400, 700), ngauge=3)
+    random_fields(m, seed=13)
+    c = m.copy()
+    c.output = type(m.output)(m.setup, m.mesh)
+    a = _run_window(m, {"window_min_cells": 1000, "shallow_acc": 16})
+    oracle.forward(c.setup, c.mesh, c.input_data, c.parameters, c.parameters.copy(), c.states, c.states.copy(), c.output)
+    qa, qc = np.asarray(a.output.sparse_qsim_domain, np.float64), np.asarray(c.output.sparse_qsim_domain, np.float64)
+    assert np.all(np.abs(qa - qc) <= 1e-4 + 2e-3 * np.abs(qc)), float(np.abs(qa - qc).max())
+    assert np.all(np.abs(np.asarray(a.output.qsim, np.float64) - c.output.qsim) <= 1e-4 + 2e-3 * np.abs(c.output.qsim))
