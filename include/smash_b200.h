@@ -195,6 +195,13 @@ int smash_b200_plan_set_fields(SmashPlan *plan, const SmashParameters *parameter
                                const float *sample, const int32_t *ind_parameters_states, int32_t nvar);
 int smash_b200_plan_run_forward(SmashPlan *plan, float *elapsed_ms);
 int smash_b200_plan_run_gradient(SmashPlan *plan, float *elapsed_ms_forward, float *elapsed_ms_reverse);
+/* regionalisation step with everything resident on the device: hyper-parameters (Hyper_ParametersDT / Hyper_StatesDT,
+ * (nhyper,1) planes) -> field planes by the mapping kernel (routine/mwd_parameters_manipulation.f90:304-362), forward and
+ * reverse sweeps, hyper adjoint reductions (forward/forward_db.f90:1434-1537).  hyper_b: [7][nhyper] gradient of cp, cft,
+ * exc, lr, hp, hft, hlr; ms: device time of the mapping, forward sweep, reverse sweep, reductions */
+int smash_b200_plan_run_hyper_gradient(SmashPlan *plan, const SmashSetup *setup, const SmashInputData *input_data,
+                                       const SmashParameters *hyper_parameters, const SmashStates *hyper_states, float *hyper_b,
+                                       float ms[4]);
 int smash_b200_plan_get_qsim(SmashPlan *plan, float *qsim /* F(ng,T,nmember) */, float *cost /* (nmember) */);
 int smash_b200_plan_get_gradient(SmashPlan *plan, SmashParameters *parameters_b, SmashStates *states_b);
 /* sum of the device-resident q of the last run over all active cell-steps (size-independent checksum) */

@@ -75,7 +75,7 @@ EXPORTS = [
     "smash_b200_compute_multiple_run", "smash_b200_last_error", "smash_b200_version", "smash_b200_device_count",
     "smash_b200_set_device", "smash_b200_clear_cache", "smash_b200_set_option", "smash_b200_plan_create",
     "smash_b200_plan_destroy", "smash_b200_plan_set_forcing", "smash_b200_plan_set_fields",
-    "smash_b200_plan_run_forward", "smash_b200_plan_run_gradient", "smash_b200_plan_get_qsim",
+    "smash_b200_plan_run_forward", "smash_b200_plan_run_gradient", "smash_b200_plan_run_hyper_gradient", "smash_b200_plan_get_qsim",
     "smash_b200_plan_get_gradient", "smash_b200_plan_checksum", "smash_b200_plan_info", "smash_b200_plan_order",
     "smash_b200_mesh_order", "smash_b200_mesh_chains", "smash_b200_plan_kernel_times", "smash_b200_plan_stat",
 ]

@@ -13,11 +13,13 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/smash_b200.h"
 #include "kernels.cuh"
 #include "route_graph.hpp"
+#include "field_kernels.cuh"
 #include "split_kernels.cuh"
 #include "topology.hpp"
 
@@ -185,6 +187,13 @@ struct SmashPlan {
     DBuf<int> d_prog, d_rprog;
     DBuf<unsigned int> d_ticket;
     DBuf<double> d_sum;
+    // rectangle-level work on the device (field_kernels.cu): descriptors, hyper-parameters, Jreg planes, gradient planes
+    DBuf<float> d_desc, d_hyper, d_hyper_b, d_rect, d_rectb, d_jr_mat, d_jr_bgd, d_jr_b, d_jreg;
+    DBuf<double> d_partial;
+    DBuf<int32_t> d_active;
+    const void *desc_ptr = nullptr;
+    uint64_t desc_version = 0;
+    bool have_active = false;
     bool need_qdom = false;
     bool have_forcing = false, have_qobs = false, have_tape = false;
     const void *forcing_ptr = nullptr;
@@ -389,7 +398,7 @@ static int window_build(SmashPlan &pl, const SmashMesh *mesh) {
     WindowState &wn = pl.win;
     const RouteGraph &rg = pl.sp.rg;
     wn.on = false;
-    if (!option("window_pass", 1) || rg.n < option("window_min_cells", 65536)) return 0;
+    if (!option("window_pass", 0) || rg.n < option("window_min_cells", 65536)) return 0;
     if (!build_window_topo(rg, (int)option("shallow_acc", 32), wn.host).empty()) return 0;
     std::string err = build_route_graph(wn.deep.rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
                                         mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
@@ -771,162 +780,120 @@ static int run_cost(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mes
 }
 
 // ------------------------------------------------------------------------------------------------
-// host-side pieces of base_forward: (de)normalisation, Jreg and its adjoint, hyper mapping
-// (compiled with -ffp-contract=off on the host side: plain float arithmetic in the reference's order)
+// the O(nrow * ncol) pieces of base_forward / BASE_FORWARD_B: (de)normalisation of the caller's planes, Jreg and its
+// adjoint, hyper mapping and its adjoint.  The arithmetic runs on the device (field_kernels.cu); what stays on the host is
+// the in-place affine map of the caller's own arrays, which the boundary demands (forward.f90:33-38: parameters and states
+// are left denormalised in the caller's memory), spread over a few threads.
 // ------------------------------------------------------------------------------------------------
+static int download(SmashPlan &pl, void *dst, const void *src, size_t bytes);
+
 static void normalize_planes(float *const *v, int nplanes, size_t nc, const float *lb, const float *ub, bool inverse) {
-    for (int i = 0; i < nplanes; i++) {
-        if (!v[i]) continue;
+    auto one = [&](int i) {
+        if (!v[i]) return;
         const float l = lb[i], u = ub[i];
         if (!inverse) for (size_t c = 0; c < nc; c++) v[i][c] = (v[i][c] - l) / (u - l);   // mwd_parameters_manipulation.f90:154-179
         else for (size_t c = 0; c < nc; c++) v[i][c] = v[i][c] * (u - l) + l;               // :181-206
-    }
+    };
+    if (nc * (size_t)nplanes < (1u << 20)) { for (int i = 0; i < nplanes; i++) one(i); return; }
+    std::vector<std::thread> th;
+    const int nth = std::min(nplanes, 8);
+    for (int k = 0; k < nth; k++) th.emplace_back([&, k]() { for (int i = k; i < nplanes; i += nth) one(i); });
+    for (auto &t : th) t.join();
 }
 
-struct JregCtx {
-    const SmashSetup *setup;
-    const SmashMesh *mesh;
-};
+// stacked plane index (16 parameters, then 8 states) of the device field f
+static int live_plane(int f) { return f < 4 ? FIELD_PARAM[f] : SMASH_B200_GNP + FIELD_STATE[f - 4]; }
 
-// reg_prior mwd_cost.f90:1180-1221 / REG_PRIOR_B forward_db.f90:5756-5799
-static float reg_prior(const JregCtx &jc, const int32_t *optim, int nplanes, float *const *mat, float *const *bgd, float *const *mat_b, float res_b) {
-    const size_t nc = (size_t)jc.mesh->nrow * jc.mesh->ncol;
-    float res = 0.0f;
-    for (int i = 0; i < nplanes; i++)
-        if (optim[i] > 0 && mat[i] && bgd[i])
-            for (size_t c = 0; c < nc; c++) { const float d = mat[i][c] - bgd[i][c]; res = res + d * d; }
-    if (mat_b)
-        for (int i = nplanes - 1; i >= 0; i--)
-            if (optim[i] > 0 && mat[i] && bgd[i] && mat_b[i])
-                for (size_t c = nc; c-- > 0;) mat_b[i][c] = mat_b[i][c] + 2.0f * (mat[i][c] - bgd[i][c]) * res_b;
-    return res;
-}
-
-// reg_smoothing mwd_cost.f90:1100-1178 / REG_SMOOTHING_B forward_db.f90:5504-5657
-static float reg_smoothing(const JregCtx &jc, const int32_t *optim, int nplanes, float *const *matrix, float *const *bgd,
-                           bool rel_to_bgd, float *const *matrix_b, float res_b) {
-    const int nrow = jc.mesh->nrow, ncol = jc.mesh->ncol;
-    const int32_t *act = jc.mesh->active_cell;
-    float res = 0.0f;
-    std::vector<float> mat((size_t)nrow * ncol);
-    auto at = [&](int r, int c) -> size_t { return (size_t)(r - 1) + (size_t)(c - 1) * nrow; };
-    for (int i = 0; i < nplanes; i++) {
-        if (!(optim[i] > 0) || !matrix[i]) continue;
-        for (size_t c = 0; c < mat.size(); c++) mat[c] = rel_to_bgd ? matrix[i][c] - bgd[i][c] : matrix[i][c];
-        for (int col = 1; col <= ncol; col++)
-            for (int row = 1; row <= nrow; row++) {
-                if (act[at(row, col)] != 1) continue;
-                int min_col = std::max(1, col - 1), max_col = std::min(ncol, col + 1);
-                int min_row = std::max(1, row - 1), max_row = std::min(nrow, row + 1);
-                if (act[at(row, min_col)] == 0) min_col = col;
-                if (act[at(row, max_col)] == 0) max_col = col;
-                if (act[at(min_row, col)] == 0) min_row = row;
-                if (act[at(max_row, col)] == 0) max_row = row;
-                const float dr = mat[at(max_row, col)] - 2.0f * mat[at(row, col)] + mat[at(min_row, col)];
-                const float dc = mat[at(row, max_col)] - 2.0f * mat[at(row, col)] + mat[at(row, min_col)];
-                res = res + (dr * dr + dc * dc);
-                if (matrix_b && matrix_b[i]) {
-                    const float tb = 2.0f * dr * res_b, tb0 = 2.0f * dc * res_b;
-                    float *mb = matrix_b[i];
-                    mb[at(row, max_col)] += tb0; mb[at(row, col)] -= 2.0f * tb0; mb[at(row, min_col)] += tb0;
-                    mb[at(max_row, col)] += tb; mb[at(row, col)] -= 2.0f * tb; mb[at(min_row, col)] += tb;
-                }
-            }
-    }
-    return res;
-}
-
-// compute_jreg mwd_cost.f90:159-245 (+ COMPUTE_JREG_B forward_db.f90:2927-3092 when *_b given; they accumulate)
-static int compute_jreg(const JregCtx &jc, float *const *par, float *const *par_bgd, float *const *st, float *const *st_bgd,
-                        float *const *par_b, float *const *st_b, float jreg_b, float *jreg) {
-    const SmashSetup *s = jc.setup;
-    float pj = 0.0f, sj = 0.0f;
-    for (int i = 0; i < s->njr; i++) {
-        const float w = s->wjreg_fun[i];
-        switch (s->jreg_fun[i]) {
-            case SMASH_JREG_PRIOR:
-                pj = pj + w * reg_prior(jc, s->optim_parameters, SMASH_B200_GNP, par, par_bgd, par_b, w * jreg_b);
-                sj = sj + w * reg_prior(jc, s->optim_states, SMASH_B200_GNS, st, st_bgd, st_b, w * jreg_b);
-                break;
-            case SMASH_JREG_SMOOTHING:
-            case SMASH_JREG_HARD_SMOOTHING: {
-                const bool rel = s->jreg_fun[i] == SMASH_JREG_SMOOTHING;
-                const float w2 = powf(w, 2.0f);
-                pj = pj + w2 * reg_smoothing(jc, s->optim_parameters, SMASH_B200_GNP, par, par_bgd, rel, par_b, w2 * jreg_b);
-                sj = sj + w2 * reg_smoothing(jc, s->optim_states, SMASH_B200_GNS, st, st_bgd, rel, st_b, w2 * jreg_b);
-            } break;
-            default:
-                return fail(SMASH_B200_EUNSUPPORTED, "jreg_fun code %d is not implemented", s->jreg_fun[i]);
-        }
-    }
-    *jreg = pj + sj;
+static int ensure_active(SmashPlan &pl, const SmashMesh *mesh) {
+    if (pl.have_active) return 0;
+    const size_t nc = (size_t)pl.ncell;
+    TRY(pl.d_active.ensure(nc));
+    CU(cudaMemcpyAsync(pl.d_active.p, mesh->active_cell, nc * sizeof(int32_t), cudaMemcpyHostToDevice, pl.stream));
+    pl.have_active = true;
     return 0;
 }
 
-// hyper_parameters_to_parameters mwd_parameters_manipulation.f90:304-362 (+ states twin mwd_states_manipulation.f90:271-329)
-static void hyper_to_planes(const SmashSetup *s, const SmashMesh *m, const float *desc, float *const *hyper, float *const *planes,
-                            int nplanes, const float *lb, const float *ub) {
-    const size_t nc = (size_t)m->nrow * m->ncol;
-    for (int i = 0; i < nplanes; i++) {
-        if (!planes[i] || !hyper[i]) continue;
-        float *f = planes[i];
-        const float *h = hyper[i];
-        for (size_t c = 0; c < nc; c++) f[c] = h[0];
-        for (int j = 1; j <= s->nd; j++) {
-            const float *d = desc + (size_t)(j - 1) * nc;
-            float a, b;
-            if (s->mapping == SMASH_MAPPING_HYPER_LINEAR) { a = h[j]; b = 1.0f; }
-            else { a = h[2 * j - 1]; b = h[2 * j]; }
-            for (size_t c = 0; c < nc; c++) f[c] = f[c] + a * powf(d[c], b);
-        }
-        for (size_t c = 0; c < nc; c++) f[c] = (ub[i] - lb[i]) * (1.0f / (1.0f + expf(-f[c]))) + lb[i];
+// compute_jreg mwd_cost.f90:159-245 on the device; with jreg_b != 0 also COMPUTE_JREG_B (forward_db.f90:2927-3092): the
+// adjoint planes (normalised space) of the optimised fields stay in pl.d_jr_b, `planes` lists their stacked indices.
+// The caller's planes are denormalised when setup->denormalize_forward is set; the kernels normalise them on the fly
+// (compute_cost mwd_cost.f90:284-298).
+static int jreg_device(SmashPlan &pl, const SmashSetup *s, const SmashMesh *mesh, const SmashParameters *par, const SmashParameters *par_bgd,
+                       const SmashStates *st, const SmashStates *st_bgd, float jreg_b, float *jreg, std::vector<int> &planes) {
+    planes.clear();
+    for (int i = 0; i < SMASH_B200_GNP; i++) if (s->optim_parameters[i] > 0 && par->v[i] && par_bgd->v[i]) planes.push_back(i);
+    for (int i = 0; i < SMASH_B200_GNS; i++) if (s->optim_states[i] > 0 && st->v[i] && st_bgd->v[i]) planes.push_back(SMASH_B200_GNP + i);
+    for (int i = 0; i < s->njr; i++)
+        if (s->jreg_fun[i] != SMASH_JREG_PRIOR && s->jreg_fun[i] != SMASH_JREG_SMOOTHING && s->jreg_fun[i] != SMASH_JREG_HARD_SMOOTHING)
+            return fail(SMASH_B200_EUNSUPPORTED, "jreg_fun code %d is not implemented", s->jreg_fun[i]);
+    *jreg = 0.0f;
+    if (planes.empty()) return 0;
+    const size_t nc = (size_t)pl.ncell, np = planes.size();
+    TRY(ensure_active(pl, mesh));
+    TRY(pl.d_jr_mat.ensure(np * nc)); TRY(pl.d_jr_bgd.ensure(np * nc)); TRY(pl.d_jr_b.ensure(np * nc)); TRY(pl.d_jreg.ensure(1));
+    TRY(pl.d_partial.ensure(std::max<size_t>((size_t)jreg_blocks((int)nc) * np, (size_t)hyper_reduce_blocks(pl.ncols) * NFIELD * (1 + 2 * HYPER_MAX_ND))));
+    JregArgs a{};
+    a.nrow = mesh->nrow; a.ncol = mesh->ncol; a.ncell = (int)nc; a.nplanes = (int)np; a.normalize = s->denormalize_forward ? 1 : 0;
+    a.active = pl.d_active.p; a.mat = pl.d_jr_mat.p; a.bgd = pl.d_jr_bgd.p; a.mat_b = pl.d_jr_b.p;
+    for (size_t k = 0; k < np; k++) {
+        const int i = planes[k];
+        const float *m = i < SMASH_B200_GNP ? par->v[i] : st->v[i - SMASH_B200_GNP];
+        const float *b = i < SMASH_B200_GNP ? par_bgd->v[i] : st_bgd->v[i - SMASH_B200_GNP];
+        a.lb[k] = i < SMASH_B200_GNP ? s->lb_parameters[i] : s->lb_states[i - SMASH_B200_GNP];
+        a.ub[k] = i < SMASH_B200_GNP ? s->ub_parameters[i] : s->ub_states[i - SMASH_B200_GNP];
+        CU(cudaMemcpyAsync(pl.d_jr_mat.p + k * nc, m, nc * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+        CU(cudaMemcpyAsync(pl.d_jr_bgd.p + k * nc, b, nc * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
     }
+    CU(cudaMemsetAsync(pl.d_jr_b.p, 0, np * nc * sizeof(float), pl.stream));
+    CU(cudaMemsetAsync(pl.d_jreg.p, 0, sizeof(float), pl.stream));
+    for (int i = 0; i < s->njr; i++) {
+        const float w = s->wjreg_fun[i];
+        const bool prior = s->jreg_fun[i] == SMASH_JREG_PRIOR;
+        const float wt = prior ? w : powf(w, 2.0f);                      // mwd_cost.f90:206-226
+        CU(launch_jreg_term(a, s->jreg_fun[i], wt, wt * jreg_b, pl.d_partial.p, pl.d_jreg.p, pl.stream));
+        pl.launches += 2;
+    }
+    TRY(download(pl, jreg, pl.d_jreg.p, sizeof(float)));
+    return 0;
 }
 
-// HYPER_PARAMETERS_TO_PARAMETERS_B forward_db.f90:1434-1537 (+ states twin :2272-2369); planes_b is consumed
-static void hyper_to_planes_b(const SmashSetup *s, const SmashMesh *m, const float *desc, float *const *hyper, float *const *hyper_b,
-                              std::vector<std::vector<float>> &planes_b, int nplanes, const float *lb, const float *ub) {
-    const size_t nc = (size_t)m->nrow * m->ncol;
-    const int nh = s->nhyper;
-    std::vector<float> z(nc);
-    for (int i = nplanes - 1; i >= 0; i--) {
-        if (!hyper[i] || !hyper_b[i]) continue;
-        const float *h = hyper[i];
-        float *hb = hyper_b[i];
-        for (int k = 0; k < nh; k++) hb[k] = 0.0f;
-        std::vector<float> &fb = planes_b[i];
-        if (fb.empty()) continue;
-        for (size_t c = 0; c < nc; c++) z[c] = h[0];
-        for (int j = 1; j <= s->nd; j++) {
-            const float *d = desc + (size_t)(j - 1) * nc;
-            float a, b;
-            if (s->mapping == SMASH_MAPPING_HYPER_LINEAR) { a = h[j]; b = 1.0f; }
-            else { a = h[2 * j - 1]; b = h[2 * j]; }
-            for (size_t c = 0; c < nc; c++) z[c] = z[c] + a * powf(d[c], b);
-        }
-        for (size_t c = 0; c < nc; c++) {
-            const float e = expf(-z[c]);
-            const float temp = e + 1.0f;
-            fb[c] = e * (ub[i] - lb[i]) * fb[c] / (temp * temp);
-        }
-        for (int j = s->nd; j >= 1; j--) {
-            const float *d = desc + (size_t)(j - 1) * nc;
-            float a, b;
-            if (s->mapping == SMASH_MAPPING_HYPER_LINEAR) { a = h[j]; b = 1.0f; }
-            else { a = h[2 * j - 1]; b = h[2 * j]; }
-            float a_b = 0.0f, b_b = 0.0f;
-            for (size_t c = 0; c < nc; c++) a_b = a_b + powf(d[c], b) * fb[c];
-            if (s->mapping == SMASH_MAPPING_HYPER_LINEAR) hb[j] += a_b;
-            else {
-                for (size_t c = 0; c < nc; c++)
-                    if (!(d[c] <= 0.0f)) b_b = b_b + powf(d[c], b) * logf(d[c]) * (a * fb[c]);
-                hb[2 * j] += b_b; hb[2 * j - 1] += a_b;
-            }
-        }
-        float sum = 0.0f;
-        for (size_t c = 0; c < nc; c++) sum = sum + fb[c];
-        hb[0] += sum;
+// descriptors + hyper-parameters on the device; fills the argument block of the hyper kernels
+static int hyper_args(SmashPlan &pl, const SmashSetup *s, const SmashMesh *mesh, const SmashInputData *in, const SmashParameters *hp,
+                      const SmashStates *hs, HyperArgs &a) {
+    const size_t nc = (size_t)pl.ncell;
+    if (s->nd > HYPER_MAX_ND) return fail(SMASH_B200_EUNSUPPORTED, "more than %d descriptors", HYPER_MAX_ND);
+    (void)mesh;
+    if (s->nd > 0 && !(pl.desc_ptr == in->descriptor && in->forcing_version != 0 && pl.desc_version == in->forcing_version)) {
+        TRY(pl.d_desc.ensure((size_t)s->nd * nc));
+        CU(cudaMemcpyAsync(pl.d_desc.p, in->descriptor, (size_t)s->nd * nc * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+        pl.desc_ptr = in->descriptor; pl.desc_version = in->forcing_version;
     }
+    const int nh = s->nhyper;
+    std::vector<float> h((size_t)HYPER_NPLANE * nh, 0.0f);
+    for (int i = 0; i < SMASH_B200_GNP; i++) if (hp->v[i]) std::copy(hp->v[i], hp->v[i] + nh, h.begin() + (size_t)i * nh);
+    for (int i = 0; i < SMASH_B200_GNS; i++) if (hs->v[i]) std::copy(hs->v[i], hs->v[i] + nh, h.begin() + (size_t)(SMASH_B200_GNP + i) * nh);
+    TRY(pl.d_hyper.upload(h, pl.stream));
+    CU(cudaStreamSynchronize(pl.stream));                                // h is a local
+    a = HyperArgs{};
+    a.n = pl.ncols; a.npad = pl.ncols; a.ncell = (int)nc; a.nd = s->nd; a.nh = nh; a.poly = s->mapping == SMASH_MAPPING_HYPER_POLYNOMIAL;
+    a.cell = pl.d_cell.p; a.desc = pl.d_desc.p; a.hyper = pl.d_hyper.p; a.fields = pl.d_fields.p;
+    for (int f = 0; f < NFIELD; f++) a.live[f] = live_plane(f);
+    for (int i = 0; i < SMASH_B200_GNP; i++) { a.lb[i] = s->lb_parameters[i]; a.ub[i] = s->ub_parameters[i]; }
+    for (int i = 0; i < SMASH_B200_GNS; i++) { a.lb[SMASH_B200_GNP + i] = s->lb_states[i]; a.ub[SMASH_B200_GNP + i] = s->ub_states[i]; }
+    return 0;
+}
+
+// hyper_parameters_to_parameters / hyper_states_to_states (mwd_parameters_manipulation.f90:304-362,
+// mwd_states_manipulation.f90:271-329): the plan's field planes are written directly; the caller's 16 + 8 rectangles,
+// which the reference rewrites as a side effect, are filled from one device pass over the rectangle.
+static int hyper_apply(SmashPlan &pl, const HyperArgs &a, SmashParameters *par, SmashStates *st) {
+    const size_t nc = (size_t)pl.ncell;
+    CU(launch_hyper_fields(a, pl.stream));
+    TRY(pl.d_rect.ensure((size_t)HYPER_NPLANE * nc));
+    CU(launch_hyper_rect(a, pl.d_rect.p, pl.stream));
+    pl.launches += 2;
+    for (int i = 0; i < SMASH_B200_GNP; i++) if (par->v[i]) TRY(download(pl, par->v[i], pl.d_rect.p + (size_t)i * nc, nc * sizeof(float)));
+    for (int i = 0; i < SMASH_B200_GNS; i++) if (st->v[i]) TRY(download(pl, st->v[i], pl.d_rect.p + (size_t)(SMASH_B200_GNP + i) * nc, nc * sizeof(float)));
+    return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1086,8 +1053,10 @@ static int math_mode() { return (int)option("math", 1); }
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// fields_ready: the plan's field planes were written on the device already (hyper mapping), nothing is taken from par / st
 static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, SmashParameters *par,
-                          SmashStates *st, SmashOutput *out, SmashPlan **plan_out, float *jobs_out, bool restore_states) {
+                          SmashStates *st, SmashOutput *out, SmashPlan **plan_out, float *jobs_out, bool restore_states,
+                          bool fields_ready = false) {
     SmashPlan *pl;
     TRY(get_plan(setup, mesh, &pl));
     *plan_out = pl;
@@ -1099,11 +1068,11 @@ static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const 
     TRY(plan_members(*pl, 1, save_q, save_n, false));
     const bool streamed = can_stream(*pl, setup) && in && in->sparse_prcp && in->sparse_pet;
     if (streamed) {
-        TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
+        if (!fields_ready) TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
         TRY(forward_streamed(*pl, setup, mesh, in, out, save_q, save_n));
     } else {
         TRY(plan_set_forcing(*pl, setup, mesh, in));
-        TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
+        if (!fields_ready) TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
         TRY(run_forward_engine(*pl, save_q, save_n, false));
     }
     TRY(run_cost(*pl, setup, mesh, 0.0f, false));
@@ -1144,20 +1113,13 @@ extern "C" int smash_b200_forward(const SmashSetup *setup, const SmashMesh *mesh
     SmashPlan *pl;
     float jobs = 0.0f;
     TRY(forward_common(setup, mesh, in, par, st, out, &pl, &jobs, true));
-    // compute_cost mwd_cost.f90:247-306
+    // compute_cost mwd_cost.f90:247-306: Jreg on normalised values (the kernels normalise the planes on the fly)
     float jreg = 0.0f;
-    if (setup->denormalize_forward) {
-        normalize_planes(par->v, SMASH_B200_GNP, nc, setup->lb_parameters, setup->ub_parameters, false);
-        normalize_planes(st->v, SMASH_B200_GNS, nc, setup->lb_states, setup->ub_states, false);
-    }
     if (setup->njr > 0) {
         if (!par_bgd || !st_bgd) return fail(SMASH_B200_EINVAL, "parameters_bgd / states_bgd required by the regularisation term");
-        JregCtx jc{setup, mesh};
-        TRY(compute_jreg(jc, par->v, par_bgd->v, st->v, st_bgd->v, nullptr, nullptr, 0.0f, &jreg));
-    }
-    if (setup->denormalize_forward) {
-        normalize_planes(par->v, SMASH_B200_GNP, nc, setup->lb_parameters, setup->ub_parameters, true);
-        normalize_planes(st->v, SMASH_B200_GNS, nc, setup->lb_states, setup->ub_states, true);
+        std::vector<int> planes;
+        TRY(jreg_device(*pl, setup, mesh, par, par_bgd, st, st_bgd, 0.0f, &jreg, planes));
+        CU(cudaStreamSynchronize(pl->stream));
     }
     const float c = jobs + setup->wjreg * jreg;
     if (out) { out->cost = c; out->cost_jobs = jobs; out->cost_jreg = jreg; }
@@ -1170,7 +1132,7 @@ extern "C" int smash_b200_forward(const SmashSetup *setup, const SmashMesh *mesh
 // ------------------------------------------------------------------------------------------------
 static int gradient_common(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, SmashParameters *par,
                            SmashStates *st, SmashOutput *out, float cost_b, SmashPlan **plan_out, float *jobs_out,
-                           std::vector<float> &grad) {
+                           bool fields_ready = false) {
     SmashPlan *pl;
     TRY(get_plan(setup, mesh, &pl));
     *plan_out = pl;
@@ -1179,14 +1141,12 @@ static int gradient_common(const SmashSetup *setup, const SmashMesh *mesh, const
     const Topology &tp = pl->tp;
     TRY(plan_members(*pl, 1, false, false, true));
     TRY(plan_set_forcing(*pl, setup, mesh, in));
-    TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
+    if (!fields_ready) TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
     TRY(run_forward_engine(*pl, false, false, true));
     if (mesh->ng > 0) TRY(run_cost(*pl, setup, mesh, cost_b, true));
     else CU(cudaMemsetAsync(pl->d_cost_jobs.p, 0, sizeof(float), pl->stream));
-    TRY(run_reverse_engine(*pl));
-    grad.resize((size_t)NFIELD * pl->ncols);
+    TRY(run_reverse_engine(*pl));                                       // the gradient planes stay on the device (pl->d_grad)
     float jobs = 0.0f;
-    TRY(download(*pl, grad.data(), pl->d_grad.p, grad.size() * sizeof(float)));
     TRY(download(*pl, &jobs, pl->d_cost_jobs.p, sizeof(float)));
     if (out && out->qsim && mesh->ng > 0) TRY(download(*pl, out->qsim, pl->d_qsim.p, (size_t)mesh->ng * tp.T * sizeof(float)));
     CU(cudaStreamSynchronize(pl->stream));
@@ -1207,46 +1167,50 @@ extern "C" int smash_b200_forward_b(const SmashSetup *setup, const SmashMesh *me
     }
     SmashPlan *pl;
     float jobs = 0.0f;
-    std::vector<float> grad;
-    TRY(gradient_common(setup, mesh, in, par, st, out, seed, &pl, &jobs, grad));
+    TRY(gradient_common(setup, mesh, in, par, st, out, seed, &pl, &jobs));
     for (int i = 0; i < SMASH_B200_GNP; i++) if (par_b->v[i]) memset(par_b->v[i], 0, nc * sizeof(float));   // :10869
     for (int i = 0; i < SMASH_B200_GNS; i++) if (st_b->v[i]) memset(st_b->v[i], 0, nc * sizeof(float));     // :10870
-    // COMPUTE_COST_B :3252-3353: Jreg and its adjoint act on normalised copies, the caller's arrays stay denormalised
+    // the seven live gradient planes are assembled on the device in rectangle layout: Jreg adjoint (normalised space,
+    // COMPUTE_COST_B :3252-3353) -> NORMALIZE_*_B -> + GR_A_FORWARD_B (:10885) -> DENORMALIZE_*_B (:10931-10935)
+    TRY(pl->d_rectb.ensure((size_t)NFIELD * nc));
+    CU(cudaMemsetAsync(pl->d_rectb.p, 0, (size_t)NFIELD * nc * sizeof(float), pl->stream));
     float jreg = 0.0f;
     if (setup->njr > 0) {
         if (!par_bgd || !st_bgd) return fail(SMASH_B200_EINVAL, "parameters_bgd / states_bgd required by the regularisation term");
-        std::vector<std::vector<float>> pc(SMASH_B200_GNP), sc(SMASH_B200_GNS);
-        float *pv[SMASH_B200_GNP], *sv[SMASH_B200_GNS];
-        for (int i = 0; i < SMASH_B200_GNP; i++) { pv[i] = nullptr; if (par->v[i]) { pc[i].assign(par->v[i], par->v[i] + nc); pv[i] = pc[i].data(); } }
-        for (int i = 0; i < SMASH_B200_GNS; i++) { sv[i] = nullptr; if (st->v[i]) { sc[i].assign(st->v[i], st->v[i] + nc); sv[i] = sc[i].data(); } }
-        if (setup->denormalize_forward) {
-            normalize_planes(pv, SMASH_B200_GNP, nc, setup->lb_parameters, setup->ub_parameters, false);
-            normalize_planes(sv, SMASH_B200_GNS, nc, setup->lb_states, setup->ub_states, false);
+        std::vector<int> planes;
+        TRY(jreg_device(*pl, setup, mesh, par, par_bgd, st, st_bgd, setup->wjreg * seed, &jreg, planes));
+        for (size_t k = 0; k < planes.size(); k++) {
+            int f = -1;
+            for (int q = 0; q < NFIELD; q++) if (live_plane(q) == planes[k]) f = q;
+            if (f >= 0) {
+                CU(cudaMemcpyAsync(pl->d_rectb.p + (size_t)f * nc, pl->d_jr_b.p + k * nc, nc * sizeof(float), cudaMemcpyDeviceToDevice, pl->stream));
+            } else {
+                // an optimised plane the structure does not use: its gradient is the Jreg adjoint alone
+                const int i = planes[k];
+                float *dst = i < SMASH_B200_GNP ? par_b->v[i] : st_b->v[i - SMASH_B200_GNP];
+                if (!dst) continue;
+                TRY(download(*pl, dst, pl->d_jr_b.p + k * nc, nc * sizeof(float)));
+                CU(cudaStreamSynchronize(pl->stream));
+                if (setup->denormalize_forward) {
+                    const float span = i < SMASH_B200_GNP ? setup->ub_parameters[i] - setup->lb_parameters[i]
+                                                          : setup->ub_states[i - SMASH_B200_GNP] - setup->lb_states[i - SMASH_B200_GNP];
+                    for (size_t c = 0; c < nc; c++) dst[c] = span * (dst[c] / span);
+                }
+            }
         }
-        JregCtx jc{setup, mesh};
-        TRY(compute_jreg(jc, pv, par_bgd->v, sv, st_bgd->v, par_b->v, st_b->v, setup->wjreg * seed, &jreg));
-        if (setup->denormalize_forward) {                               // NORMALIZE_*_B :809-889, :1877-1900
-            for (int i = 0; i < SMASH_B200_GNS; i++) if (st_b->v[i]) for (size_t c = 0; c < nc; c++) st_b->v[i][c] = st_b->v[i][c] / (setup->ub_states[i] - setup->lb_states[i]);
-            for (int i = 0; i < SMASH_B200_GNP; i++) if (par_b->v[i]) for (size_t c = 0; c < nc; c++) par_b->v[i][c] = par_b->v[i][c] / (setup->ub_parameters[i] - setup->lb_parameters[i]);
-        }
     }
-    // GR_A_FORWARD_B accumulates on top (:10885)
-    for (int f = 0; f < 4; f++) {
-        float *dst = par_b->v[FIELD_PARAM[f]];
-        if (!dst) continue;
-        const float *g = grad.data() + (size_t)f * pl->ncols;
-        for (int s = 0; s < pl->ncols; s++) if (pl->col_cell[s] >= 0) dst[pl->col_cell[s]] += g[s];
+    GradScale sc{};
+    sc.on = setup->denormalize_forward ? 1 : 0;
+    for (int f = 0; f < NFIELD; f++)
+        sc.span[f] = f < 4 ? setup->ub_parameters[FIELD_PARAM[f]] - setup->lb_parameters[FIELD_PARAM[f]]
+                           : setup->ub_states[FIELD_STATE[f - 4]] - setup->lb_states[FIELD_STATE[f - 4]];
+    CU(launch_scatter_grad(pl->d_grad.p, pl->d_cell.p, pl->ncols, pl->ncols, (int)nc, sc, pl->d_rectb.p, pl->stream));
+    pl->launches++;
+    for (int f = 0; f < NFIELD; f++) {
+        float *dst = f < 4 ? par_b->v[FIELD_PARAM[f]] : st_b->v[FIELD_STATE[f - 4]];
+        if (dst) TRY(download(*pl, dst, pl->d_rectb.p + (size_t)f * nc, nc * sizeof(float)));
     }
-    for (int f = 0; f < 3; f++) {
-        float *dst = st_b->v[FIELD_STATE[f]];
-        if (!dst) continue;
-        const float *g = grad.data() + (size_t)(4 + f) * pl->ncols;
-        for (int s = 0; s < pl->ncols; s++) if (pl->col_cell[s] >= 0) dst[pl->col_cell[s]] += g[s];
-    }
-    if (setup->denormalize_forward) {                                   // :10931-10935
-        for (int i = 0; i < SMASH_B200_GNS; i++) if (st_b->v[i]) for (size_t c = 0; c < nc; c++) st_b->v[i][c] = (setup->ub_states[i] - setup->lb_states[i]) * st_b->v[i][c];
-        for (int i = 0; i < SMASH_B200_GNP; i++) if (par_b->v[i]) for (size_t c = 0; c < nc; c++) par_b->v[i][c] = (setup->ub_parameters[i] - setup->lb_parameters[i]) * par_b->v[i][c];
-    }
+    CU(cudaStreamSynchronize(pl->stream));
     const float c = jobs + setup->wjreg * jreg;
     if (out) { out->cost = c; out->cost_jobs = jobs; out->cost_jreg = jreg; }
     if (cost) *cost = c;
@@ -1273,11 +1237,16 @@ extern "C" int smash_b200_hyper_forward(const SmashSetup *setup, const SmashMesh
     std::lock_guard<std::mutex> lk(g_mu);
     if (!setup || !mesh || !par || !st || !hyper_par || !hyper_st) return fail(SMASH_B200_EINVAL, "NULL argument");
     TRY(hyper_check(setup, in));
-    hyper_to_planes(setup, mesh, in->descriptor, hyper_par->v, par->v, SMASH_B200_GNP, setup->lb_parameters, setup->ub_parameters);
-    hyper_to_planes(setup, mesh, in->descriptor, hyper_st->v, st->v, SMASH_B200_GNS, setup->lb_states, setup->ub_states);
     SmashPlan *pl;
+    TRY(get_plan(setup, mesh, &pl));
+    const bool save_q = setup->save_qsim_domain && out && (setup->sparse_storage ? out->sparse_qsim_domain : out->qsim_domain);
+    const bool save_n = setup->save_net_prcp_domain && out && (setup->sparse_storage ? out->sparse_net_prcp_domain : out->net_prcp_domain);
+    TRY(plan_members(*pl, 1, save_q, save_n, false));
+    HyperArgs ha;
+    TRY(hyper_args(*pl, setup, mesh, in, hyper_par, hyper_st, ha));
+    TRY(hyper_apply(*pl, ha, par, st));
     float jobs = 0.0f;
-    TRY(forward_common(setup, mesh, in, par, st, out, &pl, &jobs, false));   // states keep their final values (forward.f90:145)
+    TRY(forward_common(setup, mesh, in, par, st, out, &pl, &jobs, false, true));   // states keep their final values (forward.f90:145)
     const float c = jobs + setup->wjreg * 0.0f;                          // hyper_compute_cost mwd_cost.f90:309-348
     if (out) { out->cost = c; out->cost_jobs = jobs; }
     if (cost) *cost = c;
@@ -1292,23 +1261,32 @@ extern "C" int smash_b200_hyper_forward_b(const SmashSetup *setup, const SmashMe
     if (!setup || !mesh || !par || !st || !hyper_par || !hyper_st || !hyper_par_b || !hyper_st_b)
         return fail(SMASH_B200_EINVAL, "NULL argument");
     TRY(hyper_check(setup, in));
-    const size_t nc = (size_t)mesh->nrow * mesh->ncol;
     const float seed = cost_b ? *cost_b : 1.0f;
-    hyper_to_planes(setup, mesh, in->descriptor, hyper_par->v, par->v, SMASH_B200_GNP, setup->lb_parameters, setup->ub_parameters);
-    hyper_to_planes(setup, mesh, in->descriptor, hyper_st->v, st->v, SMASH_B200_GNS, setup->lb_states, setup->ub_states);
     SmashPlan *pl;
+    TRY(get_plan(setup, mesh, &pl));
+    TRY(plan_members(*pl, 1, false, false, true));
+    HyperArgs ha;
+    TRY(hyper_args(*pl, setup, mesh, in, hyper_par, hyper_st, ha));
+    TRY(hyper_apply(*pl, ha, par, st));
     float jobs = 0.0f;
-    std::vector<float> grad;
-    TRY(gradient_common(setup, mesh, in, par, st, out, seed, &pl, &jobs, grad));
-    std::vector<std::vector<float>> pb(SMASH_B200_GNP), sb(SMASH_B200_GNS);
-    for (int i = 0; i < SMASH_B200_GNP; i++) if (i != SMASH_P_BETA && i != SMASH_P_ALPHA) pb[i].assign(nc, 0.0f);   // forward_db.f90:1489-1490
-    for (int i = 0; i < SMASH_B200_GNS; i++) sb[i].assign(nc, 0.0f);
-    for (int f = 0; f < 4; f++) { const float *g = grad.data() + (size_t)f * pl->ncols; for (int s = 0; s < pl->ncols; s++) if (pl->col_cell[s] >= 0) pb[FIELD_PARAM[f]][pl->col_cell[s]] = g[s]; }
-    for (int f = 0; f < 3; f++) { const float *g = grad.data() + (size_t)(4 + f) * pl->ncols; for (int s = 0; s < pl->ncols; s++) if (pl->col_cell[s] >= 0) sb[FIELD_STATE[f]][pl->col_cell[s]] = g[s]; }
-    hyper_to_planes_b(setup, mesh, in->descriptor, hyper_st->v, hyper_st_b->v, sb, SMASH_B200_GNS, setup->lb_states, setup->ub_states);
-    hyper_to_planes_b(setup, mesh, in->descriptor, hyper_par->v, hyper_par_b->v, pb, SMASH_B200_GNP, setup->lb_parameters, setup->ub_parameters);
-    if (hyper_par_b->v[SMASH_P_BETA]) for (int k = 0; k < setup->nhyper; k++) hyper_par_b->v[SMASH_P_BETA][k] = 0.0f;
-    if (hyper_par_b->v[SMASH_P_ALPHA]) for (int k = 0; k < setup->nhyper; k++) hyper_par_b->v[SMASH_P_ALPHA][k] = 0.0f;
+    TRY(gradient_common(setup, mesh, in, par, st, out, seed, &pl, &jobs, true));
+    // HYPER_*_B forward_db.f90:1434-1537, 2272-2369: reductions of the seven live gradient planes; every other plane has a
+    // zero adjoint (beta / alpha are not even read, :1489-1490)
+    const int nh = setup->nhyper;
+    TRY(pl->d_hyper_b.ensure((size_t)NFIELD * nh));
+    TRY(pl->d_partial.ensure((size_t)hyper_reduce_blocks(pl->ncols) * NFIELD * (1 + 2 * HYPER_MAX_ND)));
+    CU(launch_hyper_reduce(ha, pl->d_grad.p, pl->d_partial.p, pl->d_hyper_b.p, pl->stream));
+    pl->launches += 2;
+    std::vector<float> hb((size_t)NFIELD * nh);
+    TRY(download(*pl, hb.data(), pl->d_hyper_b.p, hb.size() * sizeof(float)));
+    CU(cudaStreamSynchronize(pl->stream));
+    for (int i = 0; i < SMASH_B200_GNP; i++) if (hyper_par_b->v[i]) for (int k = 0; k < nh; k++) hyper_par_b->v[i][k] = 0.0f;
+    for (int i = 0; i < SMASH_B200_GNS; i++) if (hyper_st_b->v[i]) for (int k = 0; k < nh; k++) hyper_st_b->v[i][k] = 0.0f;
+    for (int f = 0; f < NFIELD; f++) {
+        float *dst = f < 4 ? hyper_par_b->v[FIELD_PARAM[f]] : hyper_st_b->v[FIELD_STATE[f - 4]];
+        const float *src_h = f < 4 ? hyper_par->v[FIELD_PARAM[f]] : hyper_st->v[FIELD_STATE[f - 4]];
+        if (dst && src_h) std::copy(hb.begin() + (size_t)f * nh, hb.begin() + (size_t)(f + 1) * nh, dst);
+    }
     if (out) { out->cost = jobs; out->cost_jobs = jobs; }
     if (cost) *cost = jobs;
     return 0;
@@ -1357,8 +1335,10 @@ extern "C" int smash_b200_compute_multiple_run(const SmashSetup *setup, const Sm
     if (setup->njr > 0 && setup->wjreg != 0.0f) {
         const size_t nc = (size_t)mesh->nrow * mesh->ncol;
         std::vector<std::vector<float>> pc(SMASH_B200_GNP), sc(SMASH_B200_GNS);
-        float *pv[SMASH_B200_GNP], *sv[SMASH_B200_GNS];
-        JregCtx jc{setup, mesh};
+        SmashParameters pm{};
+        SmashStates sm{};
+        float **pv = pm.v, **sv = sm.v;
+        std::vector<int> planes;
         for (int m = 0; m < ns; m++) {
             for (int i = 0; i < SMASH_B200_GNP; i++) { pv[i] = nullptr; if (par->v[i]) { pc[i].assign(par->v[i], par->v[i] + nc); pv[i] = pc[i].data(); } }
             for (int i = 0; i < SMASH_B200_GNS; i++) { sv[i] = nullptr; if (st->v[i]) { sc[i].assign(st->v[i], st->v[i] + nc); sv[i] = sc[i].data(); } }
@@ -1368,7 +1348,8 @@ extern "C" int smash_b200_compute_multiple_run(const SmashSetup *setup, const Sm
                 if (plane) std::fill(plane, plane + nc, sample[(size_t)m * nvar + j]);
             }
             float jreg = 0.0f;
-            TRY(compute_jreg(jc, pv, par->v, sv, st->v, nullptr, nullptr, 0.0f, &jreg));
+            TRY(jreg_device(*pl, setup, mesh, &pm, par, &sm, st, 0.0f, &jreg, planes));
+            CU(cudaStreamSynchronize(pl->stream));
             res_cost[m] = res_cost[m] + setup->wjreg * jreg;
         }
     }
@@ -1492,6 +1473,42 @@ extern "C" int smash_b200_plan_run_gradient(SmashPlan *plan, float *ms_fwd, floa
     CU(cudaEventSynchronize(plan->ev2));
     if (ms_fwd) CU(cudaEventElapsedTime(ms_fwd, plan->ev0, plan->ev1));
     if (ms_rev) CU(cudaEventElapsedTime(ms_rev, plan->ev1, plan->ev2));
+    return 0;
+}
+
+// Device-resident regionalisation step (bench / calibration loops): hyper-parameters -> field planes (hyper mapping kernel),
+// forward + reverse sweeps, hyper adjoint reductions.  hyper_b: [7][nhyper] gradient of the live fields cp, cft, exc, lr,
+// hp, hft, hlr.  ms[0..3]: mapping, forward sweep, reverse sweep, reductions (CUDA events on the plan's stream).
+extern "C" int smash_b200_plan_run_hyper_gradient(SmashPlan *plan, const SmashSetup *setup, const SmashInputData *in,
+                                                  const SmashParameters *hyper_par, const SmashStates *hyper_st, float *hyper_b,
+                                                  float ms[4]) {
+    if (!plan || !setup || !in || !hyper_par || !hyper_st) return fail(SMASH_B200_EINVAL, "NULL argument");
+    if (!plan->have_forcing) return fail(SMASH_B200_EINVAL, "plan has no forcing");
+    TRY(hyper_check(setup, in));
+    TRY(plan_members(*plan, 1, true, false, true));
+    HyperArgs ha;
+    TRY(hyper_args(*plan, setup, nullptr, in, hyper_par, hyper_st, ha));
+    const int nh = setup->nhyper;
+    TRY(plan->d_hyper_b.ensure((size_t)NFIELD * nh));
+    TRY(plan->d_partial.ensure((size_t)hyper_reduce_blocks(plan->ncols) * NFIELD * (1 + 2 * HYPER_MAX_ND)));
+    cudaEvent_t e[5];
+    for (auto &x : e) CU(cudaEventCreate(&x));
+    CU(cudaEventRecord(e[0], plan->stream));
+    CU(launch_hyper_fields(ha, plan->stream));
+    CU(cudaEventRecord(e[1], plan->stream));
+    float f = 0, r = 0;
+    TRY(smash_b200_plan_run_gradient(plan, &f, &r));
+    CU(cudaEventRecord(e[3], plan->stream));
+    CU(launch_hyper_reduce(ha, plan->d_grad.p, plan->d_partial.p, plan->d_hyper_b.p, plan->stream));
+    CU(cudaEventRecord(e[4], plan->stream));
+    if (hyper_b) TRY(download(*plan, hyper_b, plan->d_hyper_b.p, (size_t)NFIELD * nh * sizeof(float)));
+    CU(cudaStreamSynchronize(plan->stream));
+    if (ms) {
+        CU(cudaEventElapsedTime(&ms[0], e[0], e[1]));
+        ms[1] = f; ms[2] = r;
+        CU(cudaEventElapsedTime(&ms[3], e[3], e[4]));
+    }
+    for (auto &x : e) cudaEventDestroy(x);
     return 0;
 }
 

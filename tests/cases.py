@@ -158,7 +158,7 @@ def synthetic_forcing(nac, T, seed=0, gap_fraction=0.0):
     return prcp.T, np.ascontiguousarray(pet, dtype=np.float32).T
 
 
-def france(T=24, seed=0, sub=None, ngauge=0):
+def france(T=24, seed=0, sub=None, ngauge=0, nd=0):
     """France 1 km mesh (mesh_France.hdf5) with synthetic sparse forcing; `sub=(r0,r1,c0,c1)` crops a window
     (flow directions leaving the window simply drain nowhere, as at the domain edge); `ngauge` puts synthetic gauges
     on the cells with the largest flow accumulation (the shipped France mesh has none)."""
@@ -171,7 +171,7 @@ def france(T=24, seed=0, sub=None, ngauge=0):
         keep = (path[0] >= r0) & (path[0] < r1) & (path[1] >= c0) & (path[1] < c1)
         path = path[:, keep] - np.array([[r0], [c0]], dtype=np.int32)
     nrow, ncol = flwdir.shape
-    setup = SetupDT(nd=0, ng=ngauge)
+    setup = SetupDT(nd=nd, ng=ngauge)
     setup.sparse_storage = True
     setup._ntime_step = int(T)
     setup.save_qsim_domain = True                                       # setup_France.yaml:18
@@ -194,6 +194,8 @@ def france(T=24, seed=0, sub=None, ngauge=0):
         mesh.area = (flwacc[gr, gc].astype(np.float32) * mesh.dx * mesh.dx).astype(np.float32)
     inp = Input_DataDT(setup, mesh)
     inp.sparse_prcp, inp.sparse_pet = synthetic_forcing(mesh.nac, T, seed)
+    if nd > 0:                                                          # synthetic descriptors, already normalised to [0, 1]
+        inp.descriptor = np.asfortranarray(np.random.default_rng(seed + 5).uniform(0.0, 1.0, (nrow, ncol, nd)).astype(np.float32))
     par = ParametersDT(mesh)
     st = StatesDT(mesh)
     out = OutputDT(setup, mesh)

@@ -257,7 +257,7 @@ def _run_window(m, opts):
         return m
     finally:
         for k in opts:
-            lib.smash_b200_set_option(k.encode(), {"window_pass": 1, "shallow_acc": 32, "window_nx": 2, "window_variant": 8,
+            lib.smash_b200_set_option(k.encode(), {"window_pass": 0, "shallow_acc": 32, "window_nx": 2, "window_variant": 8,
                                                    "window_min_cells": 65536}[k])
         lib.smash_b200_clear_cache()
 
@@ -277,6 +277,7 @@ def test_window_pass_agrees_with_row_passes(opts):
         return m
     o = dict(opts)
     o["window_min_cells"] = 1000
+    o["window_pass"] = 1
     a = _run_window(model(), o)
     b = _run_window(model(), {"window_pass": 0})
     assert a.mesh.nac > 100000
@@ -295,7 +296,7 @@ def test_window_pass_against_oracle():
     random_fields(m, seed=13)
     c = m.copy()
     c.output = type(m.output)(m.setup, m.mesh)
-    a = _run_window(m, {"window_min_cells": 1000, "shallow_acc": 16})
+    a = _run_window(m, {"window_pass": 1, "window_min_cells": 1000, "shallow_acc": 16})
     oracle.forward(c.setup, c.mesh, c.input_data, c.parameters, c.parameters.copy(), c.states, c.states.copy(), c.output)
     qa, qc = np.asarray(a.output.sparse_qsim_domain, np.float64), np.asarray(c.output.sparse_qsim_domain, np.float64)
     assert np.all(np.abs(qa - qc) <= 1e-4 + 2e-3 * np.abs(qc)), float(np.abs(qa - qc).max())

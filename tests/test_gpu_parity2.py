@@ -68,6 +68,68 @@ def test_hyper_forward_and_adjoint(mapping):
         assert np.allclose(x, y, rtol=2e-3, atol=2e-3 * np.abs(y).max() + 1e-12), (n, x, y)
 
 
+def _hyper_objects(m, mapping, seed=5):
+    o = m.setup._optimize
+    nh = o.nhyper
+    hp, hs = Hyper_ParametersDT(m.setup), Hyper_StatesDT(m.setup)
+    rng = np.random.default_rng(seed)
+    defaults = dict(cp=200.0, cft=500.0, exc=0.0, lr=5.0, hp=0.01, hft=0.01, hlr=1e-6)
+    for names, obj, lb, ub in ((L.PARAM_NAMES, hp, o.lb_parameters, o.ub_parameters), (L.STATE_NAMES, hs, o.lb_states, o.ub_states)):
+        for i, n in enumerate(names):
+            h = np.zeros((nh, 1), np.float32, order="F")
+            x = (defaults.get(n, 0.5 * (float(lb[i]) + float(ub[i]))) - float(lb[i])) / (float(ub[i]) - float(lb[i]))
+            x = min(max(x, 1e-6), 1 - 1e-6)
+            h[0, 0] = np.log(x / (1 - x))
+            if n in ("cp", "cft", "lr", "exc"):
+                if mapping == "hyper-linear":
+                    h[1:, 0] = rng.uniform(-0.3, 0.3, nh - 1)
+                else:
+                    h[1::2, 0] = rng.uniform(-0.3, 0.3, (nh - 1) // 2)
+                    h[2::2, 0] = rng.uniform(0.6, 1.8, (nh - 1) // 2)
+            elif mapping == "hyper-polynomial":
+                h[2::2, 0] = 1.0
+            setattr(obj, n, h)
+    return hp, hs
+
+
+def test_hyper_gradient_france_scale_on_device():
+    # Regionalisation step at France scale (906 044 cells, nd = 6, hyper-polynomial: 13 coefficients per field): the mapping
+    # kernel writes the plan's field planes, the reductions of HYPER_*_B (forward_db.f90:1434-1537) run on the gradient
+    # planes in place -- no rectangle leaves the device.  Checked against the oracle's hyper_forward_b (T = 24) and timed
+    # with CUDA events: mapping + reductions must stay below 1 ms on top of the sweeps.
+    m = cases.france(T=24, ngauge=4, nd=6)
+    cases.set_optimize(m.setup, m.mesh, jobs_fun=("nse",), mapping="hyper-polynomial", gauge="all")
+    hp, hs = _hyper_objects(m, "hyper-polynomial")
+    lib = L.lib()
+    pk = L.Packed()
+    s_, m_, i_ = L.pack_setup(m.setup, m.mesh, pk), L.pack_mesh(m.mesh, m.setup, pk), L.pack_input(m.input_data, m.setup, m.mesh, pk)
+    p_, st_ = L.pack_parameters(m.parameters, pk), L.pack_states(m.states, pk)
+    hp_, hs_ = L.pack_parameters(hp, pk), L.pack_states(hs, pk)
+    plan = C.c_void_p()
+    L.check(lib.smash_b200_plan_create(C.byref(s_), C.byref(m_), 1, C.byref(plan)))
+    try:
+        L.check(lib.smash_b200_plan_set_forcing(plan, C.byref(s_), C.byref(i_)))
+        L.check(lib.smash_b200_plan_set_fields(plan, C.byref(p_), C.byref(st_), None, None, 0))
+        nh = m.setup._optimize.nhyper
+        hb = np.zeros((7, nh), np.float32)
+        ms = (C.c_float * 4)()
+        for _ in range(3):
+            L.check(lib.smash_b200_plan_run_hyper_gradient(plan, C.byref(s_), C.byref(i_), C.byref(hp_), C.byref(hs_), L._fp(hb), ms))
+        print("hyper step device times (ms): mapping %.3f forward %.3f reverse %.3f reductions %.3f" % tuple(ms))
+        assert ms[0] + ms[3] < 1.0, tuple(ms)
+    finally:
+        lib.smash_b200_plan_destroy(plan)
+    b = m.copy()
+    gb, gsb = Hyper_ParametersDT(m.setup), Hyper_StatesDT(m.setup)
+    oracle.hyper_forward_b(b.setup, b.mesh, b.input_data, b.parameters, hp, gb, b.states, hs, gsb, b.output)
+    for f, n in enumerate(("cp", "cft", "exc", "lr")):
+        x, y = hb[f].astype(np.float64), np.asarray(getattr(gb, n), np.float64).ravel()
+        assert np.allclose(x, y, rtol=2e-3, atol=2e-3 * np.abs(y).max() + 1e-12), (n, x, y)
+    for f, n in enumerate(("hp", "hft", "hlr")):
+        x, y = hb[4 + f].astype(np.float64), np.asarray(getattr(gsb, n), np.float64).ravel()
+        assert np.allclose(x, y, rtol=2e-3, atol=2e-3 * np.abs(y).max() + 1e-12), (n, x, y)
+
+
 def test_vda_gradient_with_regularisation_and_normalisation():
     # optimize_lbfgsb setting (mw_optimize.f90:547-561): normalised controls, denormalize_forward, prior + smoothing
     def make():

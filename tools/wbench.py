@@ -13,7 +13,7 @@ ap.add_argument("sets", nargs="*", default=["base"])
 a = ap.parse_args()
 lib = L.lib()
 m = cases.france(T=a.T)
-DEFAULTS = {"window_pass": 1, "shallow_acc": 32, "window_nx": 2, "window_variant": 8, "window_ctas_per_sm": 0, "fuse_export": 4}
+DEFAULTS = {"window_pass": 0, "shallow_acc": 32, "window_nx": 2, "window_variant": 8, "window_ctas_per_sm": 0, "fuse_export": 4}
 for st in a.sets:
     opts = dict(DEFAULTS)
     if st != "base":
