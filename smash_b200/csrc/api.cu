@@ -1121,6 +1121,14 @@ extern "C" int smash_b200_forward(const SmashSetup *setup, const SmashMesh *mesh
         TRY(jreg_device(*pl, setup, mesh, par, par_bgd, st, st_bgd, 0.0f, &jreg, planes));
         CU(cudaStreamSynchronize(pl->stream));
     }
+    if (setup->denormalize_forward) {
+        // the reference normalises the caller's planes around Jreg and denormalises them again (mwd_cost.f90:284-303): the
+        // float32 round trip is a visible side effect on the caller's arrays, so it is reproduced
+        normalize_planes(par->v, SMASH_B200_GNP, nc, setup->lb_parameters, setup->ub_parameters, false);
+        normalize_planes(st->v, SMASH_B200_GNS, nc, setup->lb_states, setup->ub_states, false);
+        normalize_planes(par->v, SMASH_B200_GNP, nc, setup->lb_parameters, setup->ub_parameters, true);
+        normalize_planes(st->v, SMASH_B200_GNS, nc, setup->lb_states, setup->ub_states, true);
+    }
     const float c = jobs + setup->wjreg * jreg;
     if (out) { out->cost = c; out->cost_jobs = jobs; out->cost_jreg = jreg; }
     if (cost) *cost = c;

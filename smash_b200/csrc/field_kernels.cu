@@ -28,12 +28,12 @@ __device__ __forceinline__ float hyper_z(const float *h, const float *d, int nd,
         const float a = poly ? h[2 * j - 1] : h[j];
         if (a == 0.0f) continue;
         const float p = poly ? powf(d[j - 1], h[2 * j]) : d[j - 1];
-        z = z + a * p;
+        z = __fadd_rn(z, __fmul_rn(a, p));                               // no FMA contraction: the reference has none
     }
     return z;
 }
 __device__ __forceinline__ float sigmoid_map(float z, float lb, float ub) {
-    return (ub - lb) * (1.0f / (1.0f + expf(-z))) + lb;                   // :352-356
+    return __fadd_rn(__fmul_rn(ub - lb, 1.0f / (1.0f + expf(-z))), lb);   // :352-356
 }
 
 // ---- hyper_parameters_to_parameters + hyper_states_to_states straight into the plan's [field][npad] planes -----------
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) hyper_reduce_kernel(const HyperArgs a, co
             d[k - 1] = a.desc[(size_t)(k - 1) * a.ncell + c];
             p[k - 1] = a.poly ? powf(d[k - 1], h[2 * k]) : d[k - 1];
             const float ak = a.poly ? h[2 * k - 1] : h[k];
-            if (ak != 0.0f) z = z + ak * p[k - 1];
+            if (ak != 0.0f) z = __fadd_rn(z, __fmul_rn(ak, p[k - 1]));
         }
         const float e = expf(-z);
         const float t = e + 1.0f;
