@@ -107,6 +107,11 @@ struct SplitState {
     size_t tape_rows = 0;
     SplitTopo topo{};
     DBuf<uint8_t> d_deep;          // graph of the deep cells only: SplitTopo::deep
+    // checkpointed gradient runs (adjoint_checkpoint): the tape, hr and w rows hold ONE routing window; the states at every
+    // window start are kept and the window is replayed with the tape on before its reverse sweep
+    bool ckpt = false;
+    DBuf<float> d_ckpt;            // [nwin][5][npad]: hp, hft, hlr of the source cells (fstates), hcar, q at the step before
+    DBuf<float> d_rows_seg, d_wnext, d_qprev;
 };
 
 // window pass (window_kernels.cu) + chain scans over the deep cells only: forward runs of large domains
@@ -424,6 +429,17 @@ static int window_build(SmashPlan &pl, const SmashMesh *mesh) {
 }
 
 // ---- split engine: build -------------------------------------------------------------------------
+// Gradient runs keep a tape of 24 bytes per cell-step (hp0, hft0, hr_imd, w, the q rows and their padding).  Beyond
+// "tape_budget_mb" (default 16 GB) -- or always with option adjoint_checkpoint = 1 -- the reverse sweep runs window by window
+// from checkpointed states instead (256-step windows), so that the tape holds one window.
+static bool checkpoint_wanted(int ncells, int T) {
+    const long long mode = option("adjoint_checkpoint", -1);
+    if (mode == 0) return false;
+    if (mode == 1) return T > 256;
+    const double tape = 24.0 * (double)ncells * (double)T;
+    return T > 256 && tape > (double)option("tape_budget_mb", 16384) * 1048576.0;
+}
+
 static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, bool *unsupported) {
     SplitState &sp = pl.sp;
     RouteGraph &rg = sp.rg;
@@ -444,7 +460,8 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     tp.sparse_k.assign(rg.npad, -1);
     for (int j = 0; j < rg.n; j++) tp.sparse_k[j] = rg.sparse_k[j];
     tp.gauge_slot = rg.gauge_cell;
-    sp.W = split_pick_window(tp.T, &sp.S, &sp.nwin, pl.small_windows);
+    sp.ckpt = checkpoint_wanted(rg.n, tp.T);
+    sp.W = split_pick_window(tp.T, &sp.S, &sp.nwin, pl.small_windows || sp.ckpt);
     sp.Tp = sp.W * sp.nwin;
     CU(cudaStreamCreateWithFlags(&pl.stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&pl.ev0)); CU(cudaEventCreate(&pl.ev1)); CU(cudaEventCreate(&pl.ev2));
@@ -488,22 +505,29 @@ static int split_members(SmashPlan &pl, int nmember, bool save_q, bool save_netp
     if (sp.d_rows.n < nrows) { TRY(sp.d_rows.ensure(nrows)); CU(cudaMemsetAsync(sp.d_rows.p, 0, nrows * sizeof(float), pl.stream)); }
     TRY(sp.d_hcar.ensure(nm * npad));
     TRY(sp.d_done.ensure(std::max<size_t>(1, 2 * nm * sp.rg.ntask)));   // done flags + block counters of the river reaches
-    if (save_q || gradient) TRY(pl.d_qdom.ensure(nm * tp.T * sp.qpitch));
+    if (save_q) TRY(pl.d_qdom.ensure(nm * tp.T * sp.qpitch));
     if (save_netp) TRY(pl.d_netp.ensure(nm * tp.T * sp.qpitch));
     if (gradient) {
-        TRY(sp.d_tape_hp.ensure(nm * tp.T * npad)); TRY(sp.d_tape_hft.ensure(nm * tp.T * npad));
-        if (sp.d_rows_hr.n < nrows) { TRY(sp.d_rows_hr.ensure(nrows)); CU(cudaMemsetAsync(sp.d_rows_hr.p, 0, nrows * sizeof(float), pl.stream)); }
-        if (sp.d_rows_w.n < nrows) { TRY(sp.d_rows_w.ensure(nrows)); CU(cudaMemsetAsync(sp.d_rows_w.p, 0, nrows * sizeof(float), pl.stream)); }
+        const size_t trows = sp.ckpt ? (size_t)sp.W : (size_t)tp.T;     // tape rows per member
+        const size_t nseg = sp.ckpt ? nm * npad * sp.W : nrows;
+        if (sp.ckpt && nm != 1) return fail(SMASH_B200_EUNSUPPORTED, "checkpointed gradient with more than one member");
+        TRY(sp.d_tape_hp.ensure(nm * trows * npad)); TRY(sp.d_tape_hft.ensure(nm * trows * npad));
+        if (sp.d_rows_hr.n < nseg) { TRY(sp.d_rows_hr.ensure(nseg)); CU(cudaMemsetAsync(sp.d_rows_hr.p, 0, nseg * sizeof(float), pl.stream)); }
+        if (sp.d_rows_w.n < nseg) { TRY(sp.d_rows_w.ensure(nseg)); CU(cudaMemsetAsync(sp.d_rows_w.p, 0, nseg * sizeof(float), pl.stream)); }
+        if (sp.ckpt) {
+            if (sp.d_rows_seg.n < nseg) { TRY(sp.d_rows_seg.ensure(nseg)); CU(cudaMemsetAsync(sp.d_rows_seg.p, 0, nseg * sizeof(float), pl.stream)); }
+            TRY(sp.d_ckpt.ensure((size_t)sp.nwin * 5 * npad)); TRY(sp.d_wnext.ensure(npad)); TRY(sp.d_qprev.ensure(npad));
+        }
         TRY(sp.d_gcar.ensure(nm * npad));
         TRY(sp.d_rdone.ensure(std::max<size_t>(1, nm * sp.rg.ntask)));
         TRY(pl.d_qsim_b.ensure(std::max<size_t>(1, nm * tp.T * tp.ng)));
         TRY(pl.d_grad.ensure(nm * NFIELD * npad));
-        if (sp.tape_mapped != sp.d_tape_hp.p || sp.tape_rows != nm * tp.T) {
+        if (sp.tape_mapped != sp.d_tape_hp.p || sp.tape_rows != nm * trows) {
             const char *err = nullptr;
-            if (make_tensor_map_2d(&sp.tm_hp, sp.d_tape_hp.p, npad, nm * tp.T, npad, &err) ||
-                make_tensor_map_2d(&sp.tm_hft, sp.d_tape_hft.p, npad, nm * tp.T, npad, &err))
+            if (make_tensor_map_2d(&sp.tm_hp, sp.d_tape_hp.p, npad, nm * trows, npad, &err) ||
+                make_tensor_map_2d(&sp.tm_hft, sp.d_tape_hft.p, npad, nm * trows, npad, &err))
                 return fail(SMASH_B200_ECUDA, "%s", err);
-            sp.tape_mapped = sp.d_tape_hp.p; sp.tape_rows = nm * tp.T;
+            sp.tape_mapped = sp.d_tape_hp.p; sp.tape_rows = nm * trows;
         }
     }
     pl.nmember = nmember;
@@ -569,6 +593,32 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
     // routing state of window 0 = the hlr field
     CU(cudaMemcpy2DAsync(sp.d_hcar.p, npad * sizeof(float), pl.d_fields.p + (size_t)F_HLR * npad, (size_t)NFIELD * npad * sizeof(float),
                          npad * sizeof(float), (size_t)pl.nmember, cudaMemcpyDeviceToDevice, pl.stream));
+    if (tape && sp.ckpt) {
+        // checkpointed gradient run, pass 1: the plain forward sweep window by window, keeping the states every window starts
+        // from (reservoirs, routing stores, the discharge of the step before).  The tape is written when the window is replayed
+        // right before its reverse sweep (split_reverse).
+        const size_t pb = npad * sizeof(float);
+        a.Tp = sp.W; a.qprev = sp.d_qprev.p;
+        CU(cudaMemsetAsync(sp.d_qprev.p, 0, pb, pl.stream));
+        for (int w = 0; w < sp.nwin; w++) {
+            float *ck = sp.d_ckpt.p + (size_t)w * 5 * npad;
+            if (w == 0) {
+                CU(cudaMemcpyAsync(ck, pl.d_fields.p + (size_t)F_HP * npad, 3 * pb, cudaMemcpyDeviceToDevice, pl.stream));   // hp, hft, hlr
+            } else {
+                CU(cudaMemcpyAsync(ck, pl.d_fstates.p, 3 * pb, cudaMemcpyDeviceToDevice, pl.stream));
+            }
+            CU(cudaMemcpyAsync(ck + 3 * npad, sp.d_hcar.p, pb, cudaMemcpyDeviceToDevice, pl.stream));
+            CU(cudaMemcpyAsync(ck + 4 * npad, sp.d_qprev.p, pb, cudaMemcpyDeviceToDevice, pl.stream));
+            a.t_begin = w * sp.W; a.t_end = std::min(pl.tp.T, (w + 1) * sp.W);
+            a.rows = sp.d_rows_seg.p - (ptrdiff_t)w * sp.W;              // the window buffer holds steps [w W, (w + 1) W)
+            CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), false, pl.stream));
+            CU(launch_route_forward_window(a, w, false, pl.stream));
+            CU(launch_first_step(sp.d_rows_seg.p + (sp.W - 1), sp.W, (int)npad, sp.d_qprev.p, pl.stream));
+            pl.launches += 3 + (sp.rg.npair > 0 ? 1 : 0);
+        }
+        mark(1); mark(2); mark(3);
+        return 0;
+    }
     if (pl.win.on && !tape && pl.nmember == 1 && !pl.ensemble && math_mode() == 1) {
         // window pass: reservoirs of every cell + routing of the shallow cells; then the chain scans over the deep cells
         WindowState &wn = pl.win;
@@ -610,6 +660,30 @@ static int split_reverse(SmashPlan &pl) {
     CU(cudaMemsetAsync(pl.d_grad.p, 0, sizeof(float) * (size_t)pl.nmember * NFIELD * sp.rg.npad, pl.stream));
     auto mark = [&](int i) { pl.kmark[i] = cudaEventRecord(pl.evk[i], pl.stream) == cudaSuccess; };
     mark(4);
+    if (sp.ckpt) {
+        // windows in reverse order: restore the window's start states, replay it with the tape on (one extra forward sweep in
+        // total: recompute factor 2 on the forward side), then its reverse routing sweep and its reverse reservoir sweep.  The
+        // adjoint states travel from window to window in gcar (hlr_b) and the gradient planes (hp_b, hft_b, running sums).
+        const size_t npad = (size_t)sp.rg.npad, pb = npad * sizeof(float);
+        a.Tp = sp.W; a.wnext = sp.d_wnext.p; a.qprev = sp.d_qprev.p;
+        for (int w = sp.nwin - 1; w >= 0; w--) {
+            const float *ck = sp.d_ckpt.p + (size_t)w * 5 * npad;
+            CU(cudaMemcpyAsync(pl.d_fstates.p, ck, 3 * pb, cudaMemcpyDeviceToDevice, pl.stream));
+            CU(cudaMemcpyAsync(sp.d_hcar.p, ck + 3 * npad, pb, cudaMemcpyDeviceToDevice, pl.stream));
+            CU(cudaMemcpyAsync(sp.d_qprev.p, ck + 4 * npad, pb, cudaMemcpyDeviceToDevice, pl.stream));
+            a.t_begin = w * sp.W; a.t_end = std::min(pl.tp.T, (w + 1) * sp.W); a.tape_t0 = w * sp.W;
+            const ptrdiff_t off = (ptrdiff_t)w * sp.W;
+            a.rows = sp.d_rows_seg.p - off; a.rows_hr = sp.d_rows_hr.p - off; a.rows_w = sp.d_rows_w.p - off;
+            CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), true, pl.stream));
+            CU(launch_route_forward_window(a, w, true, pl.stream, true));
+            CU(launch_route_adjoint_window(a, w, pl.stream));
+            CU(launch_vertical_adjoint(a, sp.tm_prcp, sp.tm_pet, sp.tm_hp, sp.tm_hft, math_mode(), pl.stream));
+            CU(launch_first_step(sp.d_rows_w.p, sp.W, (int)npad, sp.d_wnext.p, pl.stream));
+            pl.launches += 5 + (sp.rg.npair > 0 ? 1 : 0);
+        }
+        mark(5); mark(6);
+        return 0;
+    }
     CU(launch_route_adjoint(a, pl.stream));
     mark(5);
     CU(launch_vertical_adjoint(a, sp.tm_prcp, sp.tm_pet, sp.tm_hp, sp.tm_hft, math_mode(), pl.stream));
@@ -913,7 +987,7 @@ static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **
     char key[192];
     snprintf(key, sizeof key, "%016llx:%d:%d:%g:%g:%lld:%d:%d:%d:%lld", (unsigned long long)h, dev, setup->ntime_step, (double)setup->dt,
              (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0, small ? 1 : 0,
-             option("river_wave", 0) + 16 * option("route_order", 0));
+             option("river_wave", 0) + 16 * option("route_order", 0) + 64 * option("adjoint_checkpoint", -1) + 1024 * option("tape_budget_mb", 16384));
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
         std::unique_ptr<SmashPlan> pl(new SmashPlan());

@@ -214,8 +214,9 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_forward_kernel(const _
     float *row = a.rows + ((size_t)m * npad + j) * a.Tp;
     float *qd = (a.save_q && src && valid) ? a.qdom + (size_t)m * T * qpitch + j : nullptr;
     float *np_ = (a.save_netp && valid) ? a.netp + (size_t)m * T * qpitch + j : nullptr;
-    float *thp = TAPE ? a.tape_hp + (size_t)m * T * npad + j : nullptr;
-    float *thft = TAPE ? a.tape_hft + (size_t)m * T * npad + j : nullptr;
+    const long long tape_row0 = (long long)m * T - a.tape_t0;             // tape row of time step 0 (checkpointed runs tape one window)
+    float *thp = TAPE ? a.tape_hp + tape_row0 * npad + j : nullptr;
+    float *thft = TAPE ? a.tape_hft + tape_row0 * npad + j : nullptr;
     float *qsim = a.qsim + (size_t)m * T * a.tp.ng;
     const int ng = a.tp.ng;
     const float c0 = k.c0, E = k.E, inv_cp = k.inv_cp;
@@ -439,7 +440,8 @@ __device__ __noinline__ void route_pair(const SplitArgs &a, int m, const int4 re
     ld_row<S>(rows_lane + (size_t)jB * a.Tp, qB);
     const RouteConst cA = route_const(a, m, jA, a.hcar), cB = route_const(a, m, jB, a.hcar);
     float hA = cA.h0, hB = cB.h0;
-    float qBp = (w > 0) ? a.rows[((size_t)m * npad + jB) * a.Tp + (size_t)w * a.W - 1] : 0.0f;
+    float qBp = 0.0f;                                                     // q_B of the step before the window
+    if (w > 0) qBp = a.qprev ? a.qprev[(size_t)m * npad + jB] : a.rows[((size_t)m * npad + jB) * a.Tp + (size_t)w * a.W - 1];
 #pragma unroll 1
     for (int L = 0; L < 32; L++) {
         float sA = hA, sB = hB, sq = qBp;
@@ -1465,7 +1467,8 @@ __device__ __noinline__ void route_pair_b(const SplitArgs &a, int m, int jA, int
     const RouteConst cA = route_const(a, m, jA, a.gcar), cB = route_const(a, m, jB, a.gcar);
     const float kA = cA.fa1 * cA.c0, kB = cB.fa1 * cB.c0;
     float GA = cA.h0, GB = cB.h0;
-    float wAn = (w < a.nwin - 1) ? a.rows_w[((size_t)m * npad + jA) * a.Tp + (size_t)(w + 1) * a.W] : 0.0f;   // w_A(t + 1)
+    float wAn = 0.0f;                                                     // w_A(t + 1) at the last step of the window
+    if (w < a.nwin - 1) wAn = a.wnext ? a.wnext[(size_t)m * npad + jA] : a.rows_w[((size_t)m * npad + jA) * a.Tp + (size_t)(w + 1) * a.W];
     float lrA = 0.0f, lrB = 0.0f;
 #pragma unroll 1
     for (int L = 31; L >= 0; L--) {
@@ -1561,7 +1564,7 @@ __global__ void __launch_bounds__(128) route_adjoint_kernel(const SplitArgs a, c
                 if (meta & 2) add_seeds<S>(a, m, j, t_first, qb);
                 const RouteConst cc = shfl_const(ci, c);
                 route_cell_b<S>(a, cc, m, j, w, lane, t_first, qb, hr, wv);
-                if ((++ndone & 7) == 0) publish_flag(rdone + task, (epoch << 16) | ndone, lane);   // tributaries may start
+                if ((++ndone & 7) == 0) publish_flag(rdone + task, (epoch << 16) | min(ndone, 0xfffe), lane);   // tributaries may start
             }
         }
         publish_flag(rdone + task, (epoch << 16) | 0xffff, lane);
@@ -1590,9 +1593,11 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const _
     if (j0 >= n) return;
     const int j = j0 + lane;
     const bool valid = j < n;
-    const int nst = (T + VT_TK - 1) / VT_TK;
+    const int t_begin = a.t_begin, t_end = a.t_end;                      // whole run: 0, T; checkpointed runs: one window
+    const int st_lo = t_begin / VT_TK;
+    const int nst = (t_end + VT_TK - 1) / VT_TK - st_lo;
     constexpr uint32_t STAGE_BYTES = sizeof(BwdStage);
-    const int yb = m * T;   // tape rows of member m
+    const int yb = m * T - a.tape_t0;   // tape row of time step 0 of member m
 
     auto issue = [&](int slot, int st) {
         mbar_expect_tx(&bars[slot], STAGE_BYTES);
@@ -1604,7 +1609,7 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const _
     if (lane == 0) {
         for (int s = 0; s < VB_NST; s++) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int s = 0; s < VB_NST && s < nst; s++) issue(s, nst - 1 - s);
+        for (int s = 0; s < VB_NST && s < nst; s++) issue(s, st_lo + nst - 1 - s);
     }
     __syncwarp();
 
@@ -1620,6 +1625,12 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const _
     const float *sb = a.qsim_b + (size_t)m * T * a.tp.ng;
     const int ng = a.tp.ng;
     float hp_b = 0.0f, hft_b = 0.0f, cp_b = 0.0f, cft_b = 0.0f, exc_b = 0.0f;
+    if (valid && t_end < T) {                                            // a later window ran already: its adjoint states and sums
+        const float *g = a.grad + (size_t)m * NFIELD * npad + j;
+        cp_b = g[(size_t)F_CP * npad]; cft_b = g[(size_t)F_CFT * npad]; exc_b = g[(size_t)F_EXC * npad];
+        hp_b = g[(size_t)F_HP * npad]; hft_b = g[(size_t)F_HFT * npad];
+    }
+    const float wnx = (d >= 0 && dlag && a.wnext && t_end < T) ? a.wnext[(size_t)m * npad + d] : 0.0f;
     const bool all_valid = j0 + 32 <= n;
     const bool exc_on = __any_sync(FULL, k.exc != 0.0f);
     const float inv_cft2 = k.inv_cft * k.inv_cft, inv_cp2 = k.inv_cp * k.inv_cp;
@@ -1634,22 +1645,25 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const _
 #pragma unroll
                 for (int i = 0; i < VT_TK; i++) {
                     const int t = st * VT_TK + i + 1;
-                    v[i] = (t < T) ? __ldcg(wrow + t) : 0.0f;
+                    float x = 0.0f;
+                    if (t < t_end) x = __ldcg(wrow + t);
+                    else if (t < T) x = a.wnext ? wnx : __ldcg(wrow + t);     // first step of the next window
+                    v[i] = x;
                 }
             }
         }
     };
     float wn[VT_TK];
-    load_w(nst - 1, wn);
+    load_w(st_lo + nst - 1, wn);
     uint32_t parity = 0;
     int slot = 0;
 #pragma unroll 1
     for (int it = 0; it < nst; it++) {
-        const int st = nst - 1 - it;
+        const int st = st_lo + nst - 1 - it;
         float wq[VT_TK];
 #pragma unroll
         for (int i = 0; i < VT_TK; i++) wq[i] = wn[i];
-        if (st > 0) load_w(st - 1, wn);
+        if (st > st_lo) load_w(st - 1, wn);
         mbar_wait(&bars[slot], parity);
         float pv[VT_TK], ev[VT_TK], hpv[VT_TK], hfv[VT_TK];
 #pragma unroll
@@ -1667,7 +1681,7 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const _
             hmx = fmaxf(hmx, hpv[i]);
         }
         const float xm = mx * k.inv_cp;
-        const bool lean = FAST && all_valid && (st + 1) * VT_TK <= T &&      // warp-uniform part first: every lane votes
+        const bool lean = FAST && all_valid && (st + 1) * VT_TK <= t_end &&  // warp-uniform part first: every lane votes
                           __all_sync(FULL, gfirst < 0 && mn >= 0.0f && xm < 0.25f && hmx + xm < 15.0f);
         if (lean) {
 #pragma unroll
@@ -1680,7 +1694,7 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const _
 #pragma unroll
         for (int i = VT_TK - 1; i >= 0; i--) {
             const int t = st * VT_TK + i;
-            if (valid && t < T) {
+            if (valid && t < t_end) {
                 float q_b = wq[i];
                 if (gfirst >= 0)
                     for (int g = gfirst; g >= 0; g = a.tp.gauge_next[g]) q_b += sb[(size_t)t * ng + g];
@@ -1855,9 +1869,9 @@ cudaError_t launch_route_members(const SplitArgs &a, bool tape, cudaStream_t s) 
     return e;
 }
 
-static cudaError_t route_forward_range(const SplitArgs &a, bool tape, cudaStream_t s, int w_begin, int w_end) {
+static cudaError_t route_forward_range(const SplitArgs &a, bool tape, cudaStream_t s, int w_begin, int w_end, bool reset = false) {
     if (a.tp.ntask == 0) return cudaSuccess;
-    if (w_begin == 0) {
+    if (w_begin == 0 || reset) {
         cudaError_t e = cudaMemsetAsync(a.done, 0, 2 * sizeof(int) * (size_t)a.tp.ntask * a.nmember, s);   // flags + block counters
         if (e != cudaSuccess) return e;
     }
@@ -1869,18 +1883,18 @@ static cudaError_t route_forward_range(const SplitArgs &a, bool tape, cudaStream
     }
 }
 cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s) { return route_forward_range(a, tape, s, 0, a.nwin); }
-cudaError_t launch_route_forward_window(const SplitArgs &a, int w, bool tape, cudaStream_t s) {
-    return route_forward_range(a, tape, s, w, w + 1);
+cudaError_t launch_route_forward_window(const SplitArgs &a, int w, bool tape, cudaStream_t s, bool reset) {
+    return route_forward_range(a, tape, s, w, w + 1, reset);
 }
 
-template <int S> static cudaError_t route_adjoint_windows(const SplitArgs &a, cudaStream_t s) {
+template <int S> static cudaError_t route_adjoint_windows(const SplitArgs &a, cudaStream_t s, int w_hi, int w_lo) {
     int blocks = 0;
     cudaError_t e = persistent_grid(route_adjoint_kernel<S>, &blocks);
     if (e != cudaSuccess) return e;
     const long long total = (long long)a.tp.ntask * a.nmember;
     const int need = (int)((total + 3) / 4);
     if (blocks > need) blocks = need > 0 ? need : 1;
-    for (int w = a.nwin - 1; w >= 0; w--) {
+    for (int w = w_hi; w >= w_lo; w--) {
         e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), s);
         if (e != cudaSuccess) return e;
         route_adjoint_kernel<S><<<blocks, 128, 0, s>>>(a, w);
@@ -1890,18 +1904,31 @@ template <int S> static cudaError_t route_adjoint_windows(const SplitArgs &a, cu
     return cudaSuccess;
 }
 
-cudaError_t launch_route_adjoint(const SplitArgs &a, cudaStream_t s) {
+static cudaError_t route_adjoint_range(const SplitArgs &a, cudaStream_t s, int w_hi, int w_lo) {
     if (a.tp.ntask == 0) return cudaSuccess;
-    cudaError_t e = cudaMemsetAsync(a.rdone, 0, sizeof(int) * (size_t)a.tp.ntask * a.nmember, s);
-    if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(a.gcar, 0, sizeof(float) * (size_t)a.tp.npad * a.nmember, s);
-    if (e != cudaSuccess) return e;
-    switch (a.W / 32) {
-        case 8: return route_adjoint_windows<8>(a, s);
-        case 16: return route_adjoint_windows<16>(a, s);
-        case 24: return route_adjoint_windows<24>(a, s);
-        default: return route_adjoint_windows<32>(a, s);
+    if (w_hi == a.nwin - 1) {
+        cudaError_t e = cudaMemsetAsync(a.rdone, 0, sizeof(int) * (size_t)a.tp.ntask * a.nmember, s);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(a.gcar, 0, sizeof(float) * (size_t)a.tp.npad * a.nmember, s);
+        if (e != cudaSuccess) return e;
     }
+    switch (a.W / 32) {
+        case 8: return route_adjoint_windows<8>(a, s, w_hi, w_lo);
+        case 16: return route_adjoint_windows<16>(a, s, w_hi, w_lo);
+        case 24: return route_adjoint_windows<24>(a, s, w_hi, w_lo);
+        default: return route_adjoint_windows<32>(a, s, w_hi, w_lo);
+    }
+}
+cudaError_t launch_route_adjoint(const SplitArgs &a, cudaStream_t s) { return route_adjoint_range(a, s, a.nwin - 1, 0); }
+cudaError_t launch_route_adjoint_window(const SplitArgs &a, int w, cudaStream_t s) { return route_adjoint_range(a, s, w, w); }
+
+__global__ void first_step_kernel(const float *rows, int pitch, int npad, float *out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < npad) out[j] = rows[(size_t)j * pitch];
+}
+cudaError_t launch_first_step(const float *rows, int pitch, int npad, float *out, cudaStream_t s) {
+    first_step_kernel<<<(npad + 255) / 256, 256, 0, s>>>(rows, pitch, npad, out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_rows_to_domain(const SplitArgs &a, cudaStream_t s) {

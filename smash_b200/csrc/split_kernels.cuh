@@ -47,7 +47,12 @@ struct SplitTopo {
 struct SplitArgs {
     SplitTopo tp;
     int T, Tp, W, nwin;          // time steps, row pitch (= nwin * W), steps per window (= 32 * S), windows
-    int t_begin, t_end;          // time range of this launch of the per-cell forward pass / the export (multiples of 8; whole run: 0, T)
+    int t_begin, t_end;          // time range of this launch of the per-cell passes / the export (multiples of 8; whole run: 0, T)
+    int tape_t0;                 // time step held by row 0 of tape_hp / tape_hft (0: whole-run tape; checkpointed runs: the window start)
+    const float *qprev;          // checkpointed runs: q of every cell at the last step of the PREVIOUS window (pit pairs read it at the
+                                 // first step of a window); nullptr: rows holds every window
+    const float *wnext;          // checkpointed runs: rows_w of every cell at the first step of the NEXT window (the window buffers
+                                 // are reused), read across a window boundary by the pit pairs; nullptr: rows_w holds every window
     int first_routed;            // smallest cell index with flwacc > 1
     int nmember;
     float dt, dx;
@@ -131,11 +136,16 @@ cudaError_t launch_vertical_forward(const SplitArgs &a, const CUtensorMap &prcp,
                                     cudaStream_t s);
 cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s);      // all windows
 // one window (streamed runs: window w is routed as soon as its forcing has arrived); w = 0 resets the flags
-cudaError_t launch_route_forward_window(const SplitArgs &a, int w, bool tape, cudaStream_t s);
+// reset: clear the done flags first (checkpointed runs replay the windows in reverse order)
+cudaError_t launch_route_forward_window(const SplitArgs &a, int w, bool tape, cudaStream_t s, bool reset = false);
 // ensembles on small meshes without pit pairs: lane = member, strictly sequential arithmetic (nrouted <= 12000)
 cudaError_t launch_route_members(const SplitArgs &a, bool tape, cudaStream_t s);     // all windows
 cudaError_t launch_rows_to_domain(const SplitArgs &a, cudaStream_t s);
 cudaError_t launch_route_adjoint(const SplitArgs &a, cudaStream_t s);                // all windows, reverse order
+// one window of the reverse routing sweep (checkpointed runs); w = nwin - 1 resets the flags and the carried adjoint state
+cudaError_t launch_route_adjoint_window(const SplitArgs &a, int w, cudaStream_t s);
+// out[j] = rows[j * pitch] (the first step of a window buffer), j < npad
+cudaError_t launch_first_step(const float *rows, int pitch, int npad, float *out, cudaStream_t s);
 cudaError_t launch_vertical_adjoint(const SplitArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, const CUtensorMap &hp,
                                     const CUtensorMap &hft, int math_mode, cudaStream_t s);
 

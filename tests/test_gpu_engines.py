@@ -301,3 +301,55 @@ def test_window_pass_against_oracle():
     qa, qc = np.asarray(a.output.sparse_qsim_domain, np.float64), np.asarray(c.output.sparse_qsim_domain, np.float64)
     assert np.all(np.abs(qa - qc) <= 1e-4 + 2e-3 * np.abs(qc)), float(np.abs(qa - qc).max())
     assert np.all(np.abs(np.asarray(a.output.qsim, np.float64) - c.output.qsim) <= 1e-4 + 2e-3 * np.abs(c.output.qsim))
+
+
+def _gradient_with(opts, make):
+    lib = L.lib()
+    defaults = {"adjoint_checkpoint": -1, "stream_min_mb": 256, "tape_budget_mb": 16384}
+    for k, v in opts.items():
+        lib.smash_b200_set_option(k.encode(), v)
+    lib.smash_b200_clear_cache()
+    try:
+        m = make()
+        pb, sb = ParametersDT(m.mesh), StatesDT(m.mesh)
+        smash_b200.forward_b(m.setup, m.mesh, m.input_data, m.parameters, pb, m.parameters.copy(), None, m.states, sb,
+                             m.states.copy(), None, m.output, None)
+        return m, pb, sb
+    finally:
+        for k in opts:
+            lib.smash_b200_set_option(k.encode(), defaults[k])
+        lib.smash_b200_clear_cache()
+
+
+@pytest.mark.parametrize("case", ["france", "cance"])
+def test_checkpointed_adjoint_equals_store_all(case):
+    # adjoint_checkpoint = 1: the reverse sweep runs window by window (256 steps) from the states kept at every window start;
+    # each window is replayed with the tape on right before its reverse sweep, so the tape holds one window instead of the
+    # whole run.  Same windows, same arithmetic: the gradient must equal the store-all one (stream_min_mb = 0 gives the
+    # store-all run the same 256-step routing windows).  France window: 600 steps = 2 full windows + 88 steps, pit pairs
+    # across window boundaries included (the 700 x 700 crop holds several of the mesh's 2-cycles).
+    if case == "france":
+        def make():
+            m = cases.france(T=600, sub=(200, 900, 200, 900), ngauge=3)
+            random_fields(m, seed=21)
+            return m
+    else:
+        def make():
+            m = cases.cance(sparse=True, T=1440)
+            random_fields(m, seed=22)
+            return m
+    a, pa, sa = _gradient_with({"adjoint_checkpoint": 1, "stream_min_mb": 0}, make)
+    b, pb, sb = _gradient_with({"adjoint_checkpoint": 0, "stream_min_mb": 0}, make)
+    assert np.isclose(float(a.output.cost), float(b.output.cost), rtol=1e-6)
+    for g1, g2, names in ((pa, pb, ("cp", "cft", "exc", "lr")), (sa, sb, ("hp", "hft", "hlr"))):
+        for n in names:
+            x, y = np.asarray(getattr(g1, n), np.float64), np.asarray(getattr(g2, n), np.float64)
+            scale = np.abs(y).max()
+            assert np.abs(x - y).max() <= 1e-5 * scale + 1e-30, (n, float(np.abs(x - y).max()), float(scale))
+    if case == "cance":
+        import oracle
+        c = make()
+        pc, sc = ParametersDT(c.mesh), StatesDT(c.mesh)
+        oracle.forward_b(c.setup, c.mesh, c.input_data, c.parameters, pc, c.parameters.copy(), c.states, sc, c.states.copy(), c.output)
+        check_grad(pa, pc, ("cp", "cft", "exc", "lr"))
+        check_grad(sa, sc, ("hp", "hft", "hlr"))
