@@ -209,7 +209,9 @@ int smash_b200_plan_checksum(SmashPlan *plan, double *sum_q);
 /* device time (ms, CUDA events on the plan's stream) of the kernels of the last run: [0] vertical_forward,
  * [1] route_forward, [2] rows_to_domain, [3] route_adjoint, [4] vertical_adjoint; -1 where a kernel did not run */
 int smash_b200_plan_kernel_times(SmashPlan *plan, float ms[5]);
-/* named facts about a plan: "engine" (0 fused, 1 split), "routed_cells", "source_cells", "inflow_edges"; -1 if unknown */
+/* named facts about a plan: "engine" (0 fused, 1 split), "routed_cells", "source_cells", "inflow_edges", "checkpoint" (1: the
+ * adjoint runs window by window from checkpoints), "route_window" (steps), "route_windows", "tape_bytes" (what a gradient
+ * run keeps between its sweeps, after the first gradient run), "window_pass", "deep_cells", "shallow_cells"; -1 if unknown */
 double smash_b200_plan_stat(const SmashPlan *plan, const char *name);
 /* topology facts: [0]=ncell_active [1]=nblocks [2]=block_size [3]=max in-block skew [4]=total ticks over blocks
  * [5]=cross-block edges [6]=pit pairs [7]=kernel launches of the last run_* call [8]=critical path over blocks in

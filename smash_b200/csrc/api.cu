@@ -1722,6 +1722,17 @@ extern "C" double smash_b200_plan_stat(const SmashPlan *plan, const char *name) 
         if (n == "routed_cells") return (double)(rg.n - rg.nsrc);
         if (n == "source_cells") return (double)rg.nsrc;
         if (n == "inflow_edges") return (double)rg.up.size();
+        const SplitState &sp = plan->sp;
+        if (n == "checkpoint") return sp.ckpt ? 1.0 : 0.0;
+        if (n == "route_window") return (double)sp.W;
+        if (n == "route_windows") return (double)sp.nwin;
+        // bytes a gradient run keeps between its sweeps: tape (hp0, hft0), hr and w rows, q rows, checkpoints
+        if (n == "tape_bytes")
+            return 4.0 * ((double)sp.d_tape_hp.n + sp.d_tape_hft.n + sp.d_rows_hr.n + sp.d_rows_w.n + (sp.ckpt ? (double)sp.d_rows_seg.n : (double)sp.d_rows.n) +
+                          sp.d_ckpt.n);
+        if (n == "window_pass") return plan->win.on ? 1.0 : 0.0;
+        if (n == "deep_cells") return plan->win.on ? (double)plan->win.host.ndeep : -1.0;
+        if (n == "shallow_cells") return plan->win.on ? (double)plan->win.host.nshallow : -1.0;
     }
     return -1.0;
 }

@@ -44,8 +44,41 @@ def _farray(shape, value, dtype=np.float32):
     return np.full(shape, value, dtype=dtype, order="F")
 
 
+def _coerce(cur, value):
+    """What an f90wrap property setter does to ``value`` given the Fortran type behind the attribute: scalars are converted
+    to the component's type (``setup._ntime_step = 1440.0`` stores the integer 1440), an array component keeps its type
+    and -- when the right-hand side is a scalar -- its storage (``parameters.lr = 5`` fills the plane).
+    An array of another shape replaces the component (the Python mirror has no fixed allocation)."""
+    if isinstance(cur, (bool, np.bool_)):
+        return bool(value), False
+    if isinstance(cur, (int, np.integer)) and not isinstance(value, (str, bytes)):
+        return int(value), False
+    if isinstance(cur, (np.floating, float)) and not isinstance(value, (str, bytes)) and np.ndim(value) == 0:
+        return type(cur)(value), False
+    if isinstance(cur, np.ndarray) and not isinstance(value, (str, bytes)):
+        arr = np.asarray(value)
+        if arr.shape == cur.shape:
+            if cur.dtype.kind in "iuf" and arr.dtype != cur.dtype:
+                return np.asfortranarray(arr, dtype=cur.dtype), False
+            return value if isinstance(value, np.ndarray) else np.asfortranarray(arr), False
+        if arr.ndim == 0 and cur.dtype.kind in "iuf" and arr.dtype.kind in "iufb":
+            cur[...] = arr
+            return cur, True
+        return value, False
+    return value, False
+
+
 class _DT:
-    """copy() mirrors the f90wrap ``copy`` methods added by finalize_f90wrap.py."""
+    """copy() mirrors the f90wrap ``copy`` methods added by finalize_f90wrap.py; attribute assignment follows the typed
+    f90wrap setters (_coerce)."""
+
+    def __setattr__(self, name, value):
+        cur = self.__dict__.get(name)
+        if cur is not None:
+            value, done = _coerce(cur, value)
+            if done:
+                return
+        object.__setattr__(self, name, value)
 
     def copy(self):
         return _copy.deepcopy(self)

@@ -158,7 +158,7 @@ def synthetic_forcing(nac, T, seed=0, gap_fraction=0.0):
     return prcp.T, np.ascontiguousarray(pet, dtype=np.float32).T
 
 
-def france(T=24, seed=0, sub=None, ngauge=0, nd=0):
+def france(T=24, seed=0, sub=None, ngauge=0, nd=0, qobs_from_oracle=True):
     """France 1 km mesh (mesh_France.hdf5) with synthetic sparse forcing; `sub=(r0,r1,c0,c1)` crops a window
     (flow directions leaving the window simply drain nowhere, as at the domain edge); `ngauge` puts synthetic gauges
     on the cells with the largest flow accumulation (the shipped France mesh has none)."""
@@ -201,7 +201,12 @@ def france(T=24, seed=0, sub=None, ngauge=0, nd=0):
     out = OutputDT(setup, mesh)
     set_optimize(setup, mesh, jobs_fun=("nse",) if ngauge else (), gauge="all")
     model = Model(setup, mesh, inp, par, st, out)
-    if ngauge > 0:
+    if ngauge > 0 and not qobs_from_oracle:
+        # long runs (the oracle would need minutes): positive synthetic observations of a plausible magnitude
+        area = flwacc[gr, gc].astype(np.float64) * float(mesh.dx) ** 2
+        base = (0.05e-3 / 3600.0) * area                                     # 0.05 mm/h over the drained area, m3/s
+        inp.qobs = np.asfortranarray((base[:, None] * np.random.default_rng(seed + 17).gamma(2.0, 0.5, (ngauge, T))).astype(np.float32))
+    elif ngauge > 0:
         # "observations" = a run of the CPU oracle with perturbed parameters, +-5 % multiplicative noise
         import oracle
         truth = model.copy()

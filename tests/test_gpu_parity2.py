@@ -334,3 +334,59 @@ def test_run_to_run_determinism():
     for m in (a, b):
         smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
     assert np.array_equal(a.output.qsim, b.output.qsim)
+
+
+def test_scalar_product_test_on_gpu():
+    # the reference's scalar product test (optimize/mw_adjoint_test.f90:26-105) through the shim module, both sides on the
+    # GPU: <dY*, dY> from central differences of forward along dk = 1, <dk*, dk> from forward_b
+    from smash_b200.solver import _mw_adjoint_test as A
+    c = cases.cance(T=480)
+    cases.set_optimize(c.setup, c.mesh, jobs_fun=("nse",))
+    random_fields(c)
+    sp1, sp2 = A.scalar_product_test(c.setup, c.mesh, c.input_data, c.parameters, c.states, c.output, verbose=False)
+    print("scalar product test: sp1 = %.6e sp2 = %.6e rel %.2e" % (sp1, sp2, abs(sp1 - sp2) / abs(sp1)))
+    assert sp1 != 0.0 and abs(sp1 - sp2) <= 2e-2 * abs(sp1), (sp1, sp2)
+
+
+def test_gpu_adjoint_against_gpu_finite_differences():
+    # CUDA-only self-check of forward_b: for every control field, 5 random directions d on the active cells; the
+    # directional derivative <forward_b, d> against (J(x + h d) - J(x - h d)) / 2h of the CUDA forward.  Everything is
+    # float32, so the difference quotient carries the rounding noise of J (about 2e-7 J / h): directions whose derivative
+    # is below ten times that noise are reported but not judged; the others must agree to 3 %.
+    m = cases.cance(T=720)
+    cases.set_optimize(m.setup, m.mesh, jobs_fun=("nse",))
+    random_fields(m, seed=31)
+    act = m.mesh.active_cell == 1
+    pg, sg = ParametersDT(m.mesh), StatesDT(m.mesh)
+    a = m.copy()
+    smash_b200.forward_b(a.setup, a.mesh, a.input_data, a.parameters, pg, a.parameters.copy(), None, a.states, sg,
+                         a.states.copy(), None, a.output, None)
+    J0 = float(a.output.cost)
+
+    def cost(field, is_state, delta):
+        b = m.copy()
+        obj = b.states if is_state else b.parameters
+        getattr(obj, field)[...] = (np.asarray(getattr(obj, field), np.float64) + delta).astype(np.float32)
+        smash_b200.forward(b.setup, b.mesh, b.input_data, b.parameters, b.parameters.copy(), b.states, b.states.copy(), b.output)
+        return float(b.output.cost)
+
+    rng = np.random.default_rng(7)
+    steps = dict(cp=2.0, cft=2.0, exc=0.05, lr=0.05, hp=2e-3, hft=2e-3, hlr=2e-7)
+    judged, worst = 0, 0.0
+    for field, h in steps.items():
+        is_state = field in ("hp", "hft", "hlr")
+        g = np.asarray(getattr(sg if is_state else pg, field), np.float64)
+        for k in range(5):
+            d = np.zeros(act.shape)
+            d[act] = rng.uniform(-1.0, 1.0, int(act.sum()))
+            fd = (cost(field, is_state, h * d) - cost(field, is_state, -h * d)) / (2.0 * h)
+            ad = float((g * d).sum())
+            noise = 2e-7 * abs(J0) / h
+            rel = abs(fd - ad) / max(abs(fd), 1e-300)
+            print("%-4s dir %d: adjoint %.5e fd %.5e rel %.2e%s" % (field, k, ad, fd, rel, "" if abs(fd) > 10 * noise else "  (below the FD noise floor)"))
+            if abs(fd) > 10 * noise:
+                judged += 1
+                worst = max(worst, rel)
+                assert rel <= 3e-2, (field, k, ad, fd)
+    assert judged >= 15, judged
+    print("judged %d directions, worst relative difference %.2e" % (judged, worst))
