@@ -45,16 +45,14 @@ def _farray(shape, value, dtype=np.float32):
 
 
 def _coerce(cur, value):
-    """What an f90wrap property setter does to ``value`` given the Fortran type behind the attribute: scalars are converted
-    to the component's type (``setup._ntime_step = 1440.0`` stores the integer 1440), an array component keeps its type
+    """What an f90wrap property setter does to ``value`` given the Fortran type behind the attribute: integer and logical scalars are
+    converted to the component's type (``setup._ntime_step = 1440.0`` stores the integer 1440), an array component keeps its type
     and -- when the right-hand side is a scalar -- its storage (``parameters.lr = 5`` fills the plane).
     An array of another shape replaces the component (the Python mirror has no fixed allocation)."""
     if isinstance(cur, (bool, np.bool_)):
         return bool(value), False
     if isinstance(cur, (int, np.integer)) and not isinstance(value, (str, bytes)):
         return int(value), False
-    if isinstance(cur, (np.floating, float)) and not isinstance(value, (str, bytes)) and np.ndim(value) == 0:
-        return type(cur)(value), False
     if isinstance(cur, np.ndarray) and not isinstance(value, (str, bytes)):
         arr = np.asarray(value)
         if arr.shape == cur.shape:
