@@ -161,9 +161,16 @@ __global__ void __launch_bounds__(WF_WARPS * 32, MINB) window_forward_kernel(con
         // ---- per-cell records of this ticket (L2-resident planes)
         const int meta = tp.meta[j];
         const float4 c4 = a.cc[j];
-        float hp = fs[j], hft = fs[(size_t)npad + j];
+        // the states were left by whichever warp ran this tile's previous window: wait for it (a lower ticket), and read
+        // them from L2 -- this SM's L1 may still hold the line from an earlier window
+        if (w > a.w_begin || w > 0) {
+            if (lane == 0)
+                while (ld_acquire(a.prog + tile) < w) __nanosleep(64);
+            __syncwarp();
+        }
+        float hp = __ldcg(fs + j), hft = __ldcg(fs + (size_t)npad + j);
         const int cls = meta & 3;
-        float hlr = (cls != 2) ? fs[(size_t)2 * npad + j] : 0.0f;
+        float hlr = (cls != 2) ? __ldcg(fs + (size_t)2 * npad + j) : 0.0f;
         const int nup = (cls == 1) ? (meta >> 8 & 15) : 0;
         int us[WF_MAXUP];
         if (nup > 0) {
