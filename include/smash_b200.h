@@ -239,6 +239,23 @@ int smash_b200_mesh_order(const SmashSetup *setup, const SmashMesh *mesh, int32_
 int smash_b200_mesh_chains(const SmashMesh *mesh, int64_t info[8], int32_t *cell, int32_t *task_of, int32_t *pos_of,
                            int32_t *down_of);
 
+/* ---- the one collective of the path ----------------------------------------------------
+ * One process per GPU.  The reference has no distributed layer; the regionalised multi-catchment calibration (shared
+ * hyper-parameters, catchments spread over the GPUs) sums (cost, gradient) -- a few hundred values -- over the ranks once per
+ * evaluation, and a sharded ensemble gathers its per-member costs.  NCCL (libnccl.so.2, opened at run time) over NVLink /
+ * NVSwitch; the 128-byte unique id is created by rank 0 and handed to the other ranks by the caller. */
+typedef struct SmashComm SmashComm;
+int smash_b200_comm_unique_id(char id[128]);
+int smash_b200_comm_create(const char id[128], int32_t rank, int32_t world, SmashComm **comm);
+void smash_b200_comm_destroy(SmashComm *comm);
+/* in-place on a host vector; kind: 0 float32, 1 float64, 2 int32; op: 0 sum, 2 max, 3 min */
+int smash_b200_comm_allreduce(SmashComm *comm, void *host, int64_t count, int32_t kind, int32_t op);
+/* recv holds world * count values in rank order */
+int smash_b200_comm_allgather(SmashComm *comm, const void *send, void *recv, int64_t count, int32_t kind);
+int smash_b200_comm_rank(const SmashComm *comm);
+int smash_b200_comm_world(const SmashComm *comm);
+const char *smash_b200_comm_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,17 +1,101 @@
-"""Multi-GPU plumbing for the two places the path shards, one process per GPU:
+"""Multi-GPU plumbing for the places the path shards, one process per GPU:
 
 * ensembles (``compute_multiple_run``, mw_multiple_run.f90:96-117: members are independent) -- contiguous blocks of
   members per rank, no data-path collective; the per-member costs / hydrographs are gathered afterwards;
 * multi-catchment regionalised calibration -- every rank evaluates ``hyper_forward_b`` on its own catchment(s) and the
-  shared hyper-parameter gradient (a few hundred floats) is summed with ONE all-reduce.
+  shared hyper-parameter gradient (a few hundred floats) is summed with ONE all-reduce;
+* one large domain split by drainage basin -- no exchange on the data path.
 
-``torch.distributed`` is used for the process group only (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+The collective is NCCL over NVLink, called through the library's own communicator (``smash_b200_comm_*``: libnccl.so.2
+opened at run time; no PyTorch anywhere in the package).  Every function takes a ``comm`` object with ``rank``,
+``world``, ``allreduce(array, op)`` (in place) and ``allgather(array)``; ``None`` means the process-wide ``NcclComm``
+built from the launcher's environment (RANK / WORLD_SIZE / LOCAL_RANK, as set by torchrun).  The CPU tests pass a
+gloo-backed object with the same four members (tests/gloo_comm.py)."""
 from __future__ import annotations
+
+import atexit
+import ctypes as C
+import os
+import time
 
 import numpy as np
 
 PARAM_NAMES = ("ci", "cp", "beta", "cft", "cst", "alpha", "exc", "b", "cusl1", "cusl2", "clsl", "ks", "ds", "dsm", "ws", "lr")
 STATE_NAMES = ("hi", "hp", "hft", "hst", "husl1", "husl2", "hlsl", "hlr")
+
+_KIND = {np.dtype(np.float32): 0, np.dtype(np.float64): 1, np.dtype(np.int32): 2}
+_OP = {"sum": 0, "max": 2, "min": 3}
+
+
+class NcclComm:
+    """One communicator per process: rank 0 creates the NCCL unique id and leaves it in a file named after the launcher's
+    process id and port (all ranks of one node share both), the other ranks pick it up."""
+
+    def __init__(self, rank=None, world=None, device=None, id_file=None, timeout_s=120.0):
+        from . import _lib as L
+        self._L = L
+        lib = L.lib()
+        self.rank = int(os.environ.get("RANK", "0")) if rank is None else int(rank)
+        self.world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else int(world)
+        device = int(os.environ.get("LOCAL_RANK", str(self.rank))) if device is None else int(device)
+        L.check(lib.smash_b200_set_device(device))
+        if id_file is None:
+            id_file = os.environ.get("SMASH_B200_COMM_ID_FILE") or os.path.join(
+                "/tmp", "smash_b200_comm_%d_%s.id" % (os.getppid(), os.environ.get("MASTER_PORT", "0")))
+        uid = C.create_string_buffer(128)
+        if self.rank == 0:
+            self._check(lib.smash_b200_comm_unique_id(uid))
+            tmp = id_file + ".tmp%d" % os.getpid()
+            with open(tmp, "wb") as f:
+                f.write(uid.raw)
+            os.replace(tmp, id_file)
+            atexit.register(lambda: os.path.exists(id_file) and os.remove(id_file))
+        else:
+            t0 = time.time()
+            while not (os.path.exists(id_file) and os.path.getsize(id_file) == 128):
+                if time.time() - t0 > timeout_s:
+                    raise RuntimeError(f"NCCL unique id file {id_file} did not appear")
+                time.sleep(0.01)
+            with open(id_file, "rb") as f:
+                uid.raw = f.read(128)
+        self._h = C.c_void_p()
+        self._check(lib.smash_b200_comm_create(uid, self.rank, self.world, C.byref(self._h)))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("smash_b200 communicator: " + self._L.lib().smash_b200_comm_last_error().decode())
+
+    def allreduce(self, a, op="sum"):
+        """In place on a C-contiguous float32 / float64 / int32 array."""
+        assert a.flags["C_CONTIGUOUS"] or a.flags["F_CONTIGUOUS"]
+        self._check(self._L.lib().smash_b200_comm_allreduce(self._h, a.ctypes.data_as(C.c_void_p), a.size, _KIND[a.dtype], _OP[op]))
+        return a
+
+    def allgather(self, a):
+        """(world, a.size) array, row r = rank r's contribution."""
+        a = np.ascontiguousarray(a)
+        out = np.empty((self.world, a.size), dtype=a.dtype)
+        self._check(self._L.lib().smash_b200_comm_allgather(self._h, a.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                                            a.size, _KIND[a.dtype]))
+        return out
+
+    def barrier(self):
+        self.allreduce(np.zeros(1, np.int32))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.lib().smash_b200_comm_destroy(self._h)
+            self._h = None
+
+
+_default = None
+
+
+def default_comm():
+    global _default
+    if _default is None:
+        _default = NcclComm()
+    return _default
 
 
 def member_slice(ns: int, rank: int, world: int) -> slice:
@@ -21,26 +105,14 @@ def member_slice(ns: int, rank: int, world: int) -> slice:
     return slice(start, start + base + (1 if rank < extra else 0))
 
 
-def _dist():
-    import torch.distributed as dist
-    return dist
-
-
-def _device(group=None):
-    import torch
-    dist = _dist()
-    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-
-
 def multiple_run_sharded(setup, mesh, input_data, parameters, states, output, sample, ind_parameters_states, res_cost,
-                         res_qsim, group=None, compute=None):
-    """``compute_multiple_run`` with the members split over the ranks of ``group``; every rank ends with the full
+                         res_qsim, comm=None, compute=None):
+    """``compute_multiple_run`` with the members split over the ranks of ``comm``; every rank ends with the full
     ``res_cost`` (and ``res_qsim`` when it is not size-0)."""
-    import torch
-    dist = _dist()
+    comm = comm or default_comm()
     if compute is None:
         from .solver._mw_multiple_run import compute_multiple_run as compute
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = comm.rank, comm.world
     sample = np.asfortranarray(sample, dtype=np.float32)
     ns = sample.shape[1]
     sl = member_slice(ns, rank, world)
@@ -52,30 +124,26 @@ def multiple_run_sharded(setup, mesh, input_data, parameters, states, output, sa
     if n_loc:
         compute(setup, mesh, input_data, parameters, states, output, np.asfortranarray(sample[:, sl]), ind_parameters_states,
                 cost_loc, q_loc)
-    dev = _device(group)
     nmax = -(-ns // world)
     width = 1 + (nq if want_q else 0)
-    buf = torch.zeros((nmax, width), dtype=torch.float32)
-    buf[:n_loc, 0] = torch.from_numpy(cost_loc)
+    buf = np.zeros((nmax, width), dtype=np.float32)
+    buf[:n_loc, 0] = cost_loc
     if want_q and n_loc:
-        buf[:n_loc, 1:] = torch.from_numpy(np.ascontiguousarray(q_loc.reshape(nq, n_loc, order="F").T))
-    buf = buf.to(dev)
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf, group=group)
+        buf[:n_loc, 1:] = q_loc.reshape(nq, n_loc, order="F").T
+    out = comm.allgather(buf).reshape(world, nmax, width)
     for r in range(world):
         s = member_slice(ns, r, world)
-        part = out[r][: s.stop - s.start].cpu().numpy()
+        part = out[r][: s.stop - s.start]
         res_cost[s] = part[:, 0]
         if want_q:
             res_qsim[:, :, s] = part[:, 1:].T.reshape(mesh.ng, setup._ntime_step, s.stop - s.start, order="F")
     return res_cost
 
 
-def allreduce_shared_gradient(cost, hyper_parameters_b, hyper_states_b, group=None):
+def allreduce_shared_gradient(cost, hyper_parameters_b, hyper_states_b, comm=None):
     """Sum over ranks of (cost, d cost / d hyper-parameters, d cost / d hyper-states): the one collective of the
     multi-catchment regionalised calibration.  Updates the *_b objects in place and returns the summed cost."""
-    import torch
-    dist = _dist()
+    comm = comm or default_comm()
     parts = [np.asarray([cost], np.float32)]
     refs = []
     for obj, names in ((hyper_parameters_b, PARAM_NAMES), (hyper_states_b, STATE_NAMES)):
@@ -84,9 +152,8 @@ def allreduce_shared_gradient(cost, hyper_parameters_b, hyper_states_b, group=No
             if a is not None:
                 refs.append((obj, n, a.shape))
                 parts.append(np.asarray(a, np.float32).ravel(order="F"))
-    flat = torch.from_numpy(np.concatenate(parts)).to(_device(group))
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    flat = flat.cpu().numpy()
+    flat = np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+    comm.allreduce(flat, "sum")
     k = 1
     for obj, n, shp in refs:
         size = int(np.prod(shp))
@@ -95,27 +162,21 @@ def allreduce_shared_gradient(cost, hyper_parameters_b, hyper_states_b, group=No
     return np.float32(flat[0])
 
 
-def optimize_hyper_lbfgsb_sharded(catchments, group=None, solver=None):
-    """Regionalised multi-catchment calibration with the catchments spread over the ranks of ``group``: every rank passes
+def optimize_hyper_lbfgsb_sharded(catchments, comm=None, solver=None):
+    """Regionalised multi-catchment calibration with the catchments spread over the ranks of ``comm``: every rank passes
     its own ``(setup, mesh, input_data, parameters, states, output)`` tuples, the summed cost and shared hyper-parameter
     gradient travel in ONE all-reduce of ``1 + n_control * nhyper`` values per evaluation (plus one min / max all-reduce
     of the descriptor extrema at the start), and every rank walks the same L-BFGS-B path
     (``smash_b200.solver._mw_optimize.optimize_hyper_lbfgsb_multi``)."""
-    import torch
     from .solver._mw_optimize import optimize_hyper_lbfgsb_multi
-    dist = _dist()
-    dev = _device(group)
+    comm = comm or default_comm()
 
     def reduce_sum(vec):
-        t = torch.from_numpy(np.asarray(vec, dtype=np.float64)).to(dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-        return t.cpu().numpy()
+        return comm.allreduce(np.ascontiguousarray(vec, dtype=np.float64), "sum")
 
     def reduce_minmax(mins, maxs):
-        lo, hi = torch.from_numpy(np.asarray(mins, np.float32)).to(dev), torch.from_numpy(np.asarray(maxs, np.float32)).to(dev)
-        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
-        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
-        return lo.cpu().numpy(), hi.cpu().numpy()
+        lo, hi = np.ascontiguousarray(mins, dtype=np.float32), np.ascontiguousarray(maxs, dtype=np.float32)
+        return comm.allreduce(lo, "min"), comm.allreduce(hi, "max")
 
     return optimize_hyper_lbfgsb_multi(catchments, solver=solver, reduce_sum=reduce_sum, reduce_minmax=reduce_minmax)
 
@@ -162,15 +223,14 @@ def basin_masks(mesh, world, setup=None):
     return [np.asfortranarray((own == r).astype(np.int32)) for r in range(world)], load
 
 
-def forward_sharded_by_basin(model, group=None, gather=True, solver=None):
-    """One forward run of a large domain with its basins spread over the ranks of ``group``: every rank computes the cells
+def forward_sharded_by_basin(model, comm=None, gather=True, solver=None):
+    """One forward run of a large domain with its basins spread over the ranks of ``comm``: every rank computes the cells
     of its basins only (``local_active_cell``), there is no exchange on the data path.  With ``gather`` the domain series
     (``sparse_qsim_domain`` / ``qsim_domain``) and ``qsim`` of all ranks are combined by one all-reduce afterwards."""
-    import torch
-    dist = _dist()
+    comm = comm or default_comm()
     if solver is None:
         from .solver import _mw_forward as solver
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rank, world = comm.rank, comm.world
     masks, _ = basin_masks(model.mesh, world, model.setup)
     keep = model.mesh._local_active_cell
     model.mesh._local_active_cell = masks[rank]
@@ -184,7 +244,6 @@ def forward_sharded_by_basin(model, group=None, gather=True, solver=None):
         if hasattr(model.mesh, "_b200_cache"):
             del model.mesh._b200_cache
     if gather:
-        dev = _device(group)
         mine = masks[rank] == 1
         for name in ("sparse_qsim_domain", "qsim_domain"):
             a = getattr(model.output, name, None)
@@ -197,14 +256,13 @@ def forward_sharded_by_basin(model, group=None, gather=True, solver=None):
                 part = np.where(own[:, None], a, np.float32(0.0))
             else:
                 part = np.where(mine[:, :, None], a, np.float32(0.0))
-            t = torch.from_numpy(np.ascontiguousarray(part, dtype=np.float32)).to(dev)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-            a[...] = t.cpu().numpy()
+            t = np.ascontiguousarray(part, dtype=np.float32)
+            comm.allreduce(t, "sum")
+            a[...] = t
         if model.mesh.ng > 0:
             gp = np.asarray(model.mesh.gauge_pos)
             own_g = mine[gp[:, 0], gp[:, 1]]
-            t = torch.from_numpy(np.ascontiguousarray(np.where(own_g[:, None], model.output.qsim, np.float32(0.0)),
-                                                      dtype=np.float32)).to(dev)
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-            model.output.qsim[...] = t.cpu().numpy()
+            t = np.ascontiguousarray(np.where(own_g[:, None], model.output.qsim, np.float32(0.0)), dtype=np.float32)
+            comm.allreduce(t, "sum")
+            model.output.qsim[...] = t
     return masks[rank]

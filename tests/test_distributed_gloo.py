@@ -1,4 +1,5 @@
-"""world_size-2 gloo test (CPU) of the N>1 path: member sharding + gather of the ensemble results, and the single
+"""world_size-2 gloo test (CPU) of the N>1 path (the product talks NCCL through its own communicator; here a gloo-backed
+object with the same interface, tests/gloo_comm.py, stands in): member sharding + gather of the ensemble results, and the single
 all-reduce of the shared hyper-parameter gradient.  The per-rank compute is replaced by a deterministic stand-in so
 that only the host-side plumbing is exercised here; the GPU arithmetic is covered by the -m gpu tests."""
 import os
@@ -27,13 +28,15 @@ def _worker(rank, world, port, ns, ret):
     sample = np.asfortranarray(rng.uniform(0, 1, (4, ns)).astype(np.float32))
     cost = np.zeros(ns, np.float32)
     qsim = np.zeros((m.mesh.ng, 12, ns), np.float32, order="F")
+    from gloo_comm import GlooComm
+    comm = GlooComm()
     D.multiple_run_sharded(m.setup, m.mesh, m.input_data, m.parameters, m.states, m.output, sample, cases.IND_CP_CFT_EXC_LR,
-                           cost, qsim, compute=_fake_compute)
+                           cost, qsim, comm=comm, compute=_fake_compute)
     cases.set_optimize(m.setup, m.mesh, mapping="hyper-linear")
     hpb, hsb = Hyper_ParametersDT(m.setup), Hyper_StatesDT(m.setup)
     hpb.cp[...] = rank + 1.0
     hsb.hlr[...] = 10.0 * (rank + 1)
-    total = D.allreduce_shared_gradient(np.float32(0.5 + rank), hpb, hsb)
+    total = D.allreduce_shared_gradient(np.float32(0.5 + rank), hpb, hsb, comm=comm)
     if rank == 0:
         ret["cost"], ret["qsim"], ret["sample"] = cost, qsim, sample
         ret["total"], ret["cp"], ret["hlr"] = float(total), hpb.cp.copy(), hsb.hlr.copy()
@@ -89,7 +92,8 @@ def _regional_worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     m = _catchment(rank)
-    D.optimize_hyper_lbfgsb_sharded([_as_tuple(m)], solver=oracle_solver)
+    from gloo_comm import GlooComm
+    D.optimize_hyper_lbfgsb_sharded([_as_tuple(m)], comm=GlooComm(), solver=oracle_solver)
     ret[rank] = (float(m.output.cost), m.parameters.cp.copy(), m.parameters.lr.copy())
     dist.destroy_process_group()
 
@@ -127,7 +131,8 @@ def _basin_worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     m = cases.france(T=24, sub=(400, 520, 400, 520), ngauge=2)
-    mask = D.forward_sharded_by_basin(m, solver=oracle_solver)
+    from gloo_comm import GlooComm
+    mask = D.forward_sharded_by_basin(m, comm=GlooComm(), solver=oracle_solver)
     ret[rank] = (m.output.sparse_qsim_domain.copy(), m.output.qsim.copy(), int(mask.sum()))
     dist.destroy_process_group()
 
