@@ -1,24 +1,29 @@
 #!/usr/bin/env python
-"""bench.py -- forward / adjoint solver throughput on B200 (contract: see the task statement, section 4).
+"""bench.py -- forward / adjoint solver throughput on B200 (contract: the task statement, section 4).
 
-Headline workload (BASELINE.json configs[3], the configuration the HBM-roofline metric is quoted on):
-France 1 km flow-direction mesh (906 044 active cells, mesh_France.hdf5 -> tests/golden/france_mesh.npz),
-T = 720 synthetic hourly steps (SURVEY.md 8d recipe), gr-a, default parameters, save_qsim_domain as in
-setup_France.yaml.  One "step" = one forward run over the whole mesh and all T time steps.
+N = 1 (the configuration BASELINE.json's HBM-roofline metric is quoted on, configs[3]):
+  France 1 km flow-direction mesh (906 044 active cells, mesh_France.hdf5 -> tests/golden/france_mesh.npz), T = 720
+  synthetic hourly steps (SURVEY.md 8d recipe), gr-a, default parameters, save_qsim_domain as in setup_France.yaml.
+  One "step" = one forward run over the whole mesh and all T time steps.
+    value     active-cell-timesteps/s, forcing resident in HBM (plan API), kernel launches only, result stays in HBM
+    e2e       the same metric through the drop-in call smash_b200.forward(...) with HOST arrays: per step the forcing
+              (5.2 GB) goes host->device and the domain discharge (2.6 GB) comes back
+    roofline  the WHOLE STEP against SURVEY 8(d): 12 algorithmic bytes per active cell-step (prcp + pet read, q written)
+              over the CUDA-event step time; per-kernel rows (time, share of the step, DRAM traffic from the committed
+              ncu capture) under roofline.kernels
+    gradient  fwd + adjoint gradient on the same mesh (evals/s, fraction of the 40 B per cell-step roofline)
+    ensemble  32 768-member Cance ensemble on this one GPU (the sharded headline of N > 1, here for the scaling ratio)
+    cpu_baseline  the C oracle (restatement of the Fortran solver, oracle/) on one host core, bounded sample
+    parity    measured max errors of the device path against the oracle on small cases (not pass / fail)
 
-  value   active-cell-timesteps/s, forcing already resident in HBM (plan API), kernel launches only; the result
-          (domain discharge in the reference's sparse layout [t][k]) stays in HBM
-  e2e     same metric through the drop-in call smash_b200.forward(...) with HOST arrays: per step the forcing
-          (5.2 GB) goes host->device and the domain discharge (2.6 GB) comes back
-  roofline  the longest kernel of the step (split engine: vertical_forward / route_forward / rows_to_domain), its
-          algorithmic bytes / its CUDA-event time; "step" = the whole forward step against the
-          12 B per active cell-step of SURVEY.md 8(d) (prcp + pet read, q written)
-  cpu_baseline  the C oracle (restatement of the Fortran solver, oracle/) on one host core, bounded sample
-  extra   fwd+adjoint gradient on the same mesh, Cance gradient latency, 4096-member Cance ensemble
+N > 1 (torchrun, one process per GPU; BASELINE.json configs[2]): the 32 768-member Cance ensemble
+  (compute_multiple_run) with contiguous member blocks per rank -- fixed total work, "scaling": "strong", no data-path
+  collective; one all-gather of the costs afterwards.  Secondary first-class keys: the regionalised multi-catchment
+  calibration (one all-reduce per evaluation) and one France run split by drainage basin.  The collective is NCCL through
+  the library's own communicator (no PyTorch).
 
-N > 1 (torchrun): every rank runs the same-size France domain with its own forcing seed (independent regions,
-no data-path collective) -> weak scaling; time = max over ranks.
---impl reference: the oracle port timed on the host (the reference's forward is single-threaded for one run).
+--impl reference: the oracle port timed on the host: the France sample on one thread at N = 1 (a single forward run of the
+reference is single-threaded), the ensemble sample on all host threads (OpenMP over members, mw_multiple_run.f90:96) at N > 1.
 """
 from __future__ import annotations
 
@@ -38,8 +43,11 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 import numpy as np  # noqa: E402
 
-METRIC = "forward active-cell-timesteps/s (France 1km mesh, gr-a); extra: fwd+adjoint gradient evals/s; % HBM roofline"
+METRIC_FRANCE = "forward active-cell-timesteps/s (France 1km mesh, gr-a); gradient: fwd+adjoint evals/s; % HBM roofline"
+METRIC_ENS = "forward active-cell-timesteps/s (32768-member Cance ensemble, compute_multiple_run, members sharded over the GPUs)"
 UNIT = "cell-timesteps/s"
+ENS_MEMBERS = 32768
+CANCE_CELLS, CANCE_T = 383, 1440
 
 
 def measured_peaks():
@@ -51,7 +59,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe), every 10 ms."""
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
@@ -60,9 +68,11 @@ class ClockSampler:
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "10",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            time.sleep(0.25)                      # nvidia-smi needs ~0.2 s before its first line
+            self.skip = len(self.rows)            # lines printed before the timed region
         except Exception:
             self.proc = None
 
@@ -72,38 +82,61 @@ class ClockSampler:
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.05)
         self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        rows = self.rows[self.skip:] or self.rows[-1:]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        reasons = sorted({n for r in rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}
 
 
-def build_france(T, seed):
-    import cases
-    t0 = time.time()
-    m = cases.france(T=T, seed=seed)
-    return m, time.time() - t0
+def ensemble_sample(ns):
+    rng = np.random.RandomState(99)
+    bounds = [(1e-6, 1e3), (1e-6, 1e3), (-50.0, 50.0), (1e-6, 1e3)]                 # generate_samples.py:357-364
+    return np.asfortranarray(np.stack([rng.uniform(lo, hi, ns) for lo, hi in bounds]).astype(np.float32))
 
 
+# ------------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """--impl reference: the oracle port of the Fortran solver on the host, bounded sample per step."""
     if rank != 0:
         return
     import cases
     import oracle
-    Ts = args.ref_steps
-    m = cases.france(T=Ts, seed=0)
-    m.setup.save_qsim_domain = False
-    units = m.mesh.nac * Ts
+    if args.gpus <= 1:
+        Ts = args.ref_steps
+        m = cases.france(T=Ts, seed=0)                     # save_qsim_domain = True, as the device arm
+        units = m.mesh.nac * Ts
+        cores = 1
 
-    def step():
-        oracle.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
+        def step():
+            oracle.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
 
+        metric = METRIC_FRANCE
+        workload = (f"France 1km mesh forward gr-a, nac=906044, T={args.T}, save_qsim_domain (reference arm: bounded sample, "
+                    f"the first {Ts} time steps per step)")
+        sample = (f"France mesh, {Ts} of {args.T} time steps per step ({units} cell-steps), save_qsim_domain, 1 thread (a single "
+                  "forward run of the reference is single-threaded)")
+    else:
+        ns = args.ref_members
+        cores = os.cpu_count() or 1
+        m = cases.cance()
+        smp = ensemble_sample(ns)
+        cost, q0 = np.zeros(ns, np.float32), np.zeros((0,), np.float32)
+        units = ns * CANCE_CELLS * CANCE_T
+
+        def step():
+            oracle.compute_multiple_run(m.setup, m.mesh, m.input_data, m.parameters, m.states, m.output, smp,
+                                        cases.IND_CP_CFT_EXC_LR, cost, q0, nthreads=cores)
+
+        metric = METRIC_ENS
+        workload = f"Cance {ENS_MEMBERS}-member ensemble (reference arm: bounded sample of {ns} members per step)"
+        sample = f"{ns} of {ENS_MEMBERS} members per step ({units} cell-steps), OpenMP over members, {cores} threads"
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -111,25 +144,125 @@ def run_reference(args, rank, world):
         step()
     dt = (time.perf_counter() - t0) / args.steps
     v = units / dt
-    sample = f"France mesh, {Ts} of {args.T} time steps per step ({units} cell-steps), 1 thread (a single forward run of the reference is single-threaded)"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"France 1km mesh forward gr-a, nac=906044, T={args.T} (reference arm: bounded sample)"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak" if args.gpus <= 1 else "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": workload},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+# ------------------------------------------------------------------------------------------------
+# ensemble (configs[2]): device-resident value + e2e through compute_multiple_run
+# ------------------------------------------------------------------------------------------------
+def bench_ensemble(lib, L, smash_b200, cases, comm, rank, world, steps, warmup, sampler=None):
+    from smash_b200 import distributed as sdist
+    m = cases.cance()
+    m.input_data._forcing_version = 1
+    smp = ensemble_sample(ENS_MEMBERS)
+    sl = sdist.member_slice(ENS_MEMBERS, rank, world)
+    n_loc = sl.stop - sl.start
+    units = ENS_MEMBERS * CANCE_CELLS * CANCE_T
+    chunk = min(n_loc, 8192)
+    pk = L.Packed()
+    s_, m_, i_ = L.pack_setup(m.setup, m.mesh, pk), L.pack_mesh(m.mesh, m.setup, pk), L.pack_input(m.input_data, m.setup, m.mesh, pk)
+    p_, st_ = L.pack_parameters(m.parameters, pk), L.pack_states(m.states, pk)
+    plan = C.c_void_p()
+    L.check(lib.smash_b200_plan_create(C.byref(s_), C.byref(m_), chunk, C.byref(plan)))
+    L.check(lib.smash_b200_plan_set_forcing(plan, C.byref(s_), C.byref(i_)))
+    ind = np.ascontiguousarray(cases.IND_CP_CFT_EXC_LR, dtype=np.int32)
+    loc = np.asfortranarray(smp[:, sl])
+    chunks = [np.asfortranarray(loc[:, k:k + chunk]) for k in range(0, n_loc, chunk)]
+    if chunks and chunks[-1].shape[1] < chunk:                       # pad the last chunk (a plan has a fixed member count)
+        pad = np.repeat(chunks[-1][:, -1:], chunk - chunks[-1].shape[1], axis=1)
+        chunks[-1] = np.asfortranarray(np.concatenate([chunks[-1], pad], axis=1))
+    ms = C.c_float(0.0)
+    kt = (C.c_float * 5)()
+
+    def dev_step():
+        tot, kk = 0.0, np.zeros(2)
+        for ch in chunks:
+            L.check(lib.smash_b200_plan_set_fields(plan, C.byref(p_), C.byref(st_), L._fp(ch), L._ip(ind), 4))
+            L.check(lib.smash_b200_plan_run_forward(plan, C.byref(ms)))
+            tot += ms.value
+            L.check(lib.smash_b200_plan_kernel_times(plan, kt))
+            kk += [kt[0], kt[1]]
+        return tot, kk
+
+    for _ in range(warmup):
+        dev_step()
+    if sampler:
+        sampler.start()
+    comm_barrier(comm)
+    t0 = time.perf_counter()
+    dev_ms, kks = [], []
+    for _ in range(steps):
+        t, kk = dev_step()
+        dev_ms.append(t)
+        kks.append(kk)
+    comm_barrier(comm)
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    info = (C.c_int64 * 12)()
+    lib.smash_b200_plan_info(plan, info)
+    launches = int(info[7]) * len(chunks)
+    lib.smash_b200_plan_destroy(plan)
+    dms = comm_max(comm, float(np.mean(dev_ms)))                     # CUDA-event time of the kernels, max over ranks
+    wall = comm_max(comm, wall)
+    kk = np.mean(np.array(kks), axis=0)
+    # e2e: the drop-in call with host arrays (sample in, costs out; the forcing of the mesh is resident after the first call)
+    cost, q0 = np.zeros(ENS_MEMBERS, np.float32), np.zeros((0,), np.float32)
+
+    def e2e_step():
+        if world > 1:
+            sdist.multiple_run_sharded(m.setup, m.mesh, m.input_data, m.parameters, m.states, m.output, smp,
+                                       cases.IND_CP_CFT_EXC_LR, cost, q0, comm=comm)
+        else:
+            smash_b200.compute_multiple_run(m.setup, m.mesh, m.input_data, m.parameters, m.states, m.output, smp,
+                                            cases.IND_CP_CFT_EXC_LR, cost, q0)
+
+    e2e_step()
+    comm_barrier(comm)
+    ne = max(1, min(3, steps))
+    t0 = time.perf_counter()
+    for _ in range(ne):
+        e2e_step()
+    comm_barrier(comm)
+    e2e_wall = comm_max(comm, time.perf_counter() - t0) / ne
+    return {
+        "units": units, "device_ms": dms, "wall_ms_per_step": wall / steps * 1e3, "value": units / (dms * 1e-3),
+        "members": ENS_MEMBERS, "members_per_rank": n_loc, "members_per_launch": chunk, "launches_per_step": launches,
+        "kernels_ms": {"vertical_forward_kernel": float(kk[0]), "route_members_kernel": float(kk[1])},
+        "e2e": {"value": units / e2e_wall, "unit": UNIT, "ms_per_step": e2e_wall * 1e3,
+                "h2d_bytes_per_step": int(smp.nbytes // world), "d2h_bytes_per_step": int(4 * n_loc)},
+        "cost_checksum": float(np.sum(cost[np.isfinite(cost)], dtype=np.float64)), "clocks": clocks,
+    }
+
+
+def comm_barrier(comm):
+    if comm is not None:
+        comm.barrier()
+
+
+def comm_max(comm, x):
+    if comm is None:
+        return x
+    a = np.array([x], dtype=np.float64)
+    comm.allreduce(a, "max")
+    return float(a[0])
+
+
+# ------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)   # 200 forward runs ~ 1 s: long enough for clock samples
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--T", type=int, default=720, help="time steps of the France workload")
-    ap.add_argument("--ref-steps", type=int, default=8, help="time steps per reference-arm step")
+    ap.add_argument("--ref-steps", type=int, default=8, help="France time steps per reference-arm step")
+    ap.add_argument("--ref-members", type=int, default=128, help="ensemble members per reference-arm step (N > 1)")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     args = ap.parse_args()
@@ -142,37 +275,114 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import cases
     import smash_b200
     from smash_b200 import _lib as L
     lib = L.lib()
     if lib.smash_b200_device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: smash_b200 has no CPU fallback")
     L.check(lib.smash_b200_set_device(local_rank))
-
-    dist = None
+    comm = None
     if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        from smash_b200 import distributed as sdist
+        comm = sdist.NcclComm(rank=rank, world=world, device=local_rank)
+    peak, peak_src = measured_peaks()
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+    if world > 1:
+        bench_sharded(args, lib, L, smash_b200, cases, comm, rank, world, local_rank, peak, peak_src)
+        comm.close()
+        return
+    bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src)
 
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
 
+# ------------------------------------------------------------------------------------------------
+# N > 1: the sharded ensemble as the headline, regional calibration and basin-split France next to it
+# ------------------------------------------------------------------------------------------------
+def bench_sharded(args, lib, L, smash_b200, cases, comm, rank, world, local_rank, peak, peak_src):
+    from smash_b200 import distributed as sdist
+    ens = bench_ensemble(lib, L, smash_b200, cases, comm, rank, world, args.steps, args.warmup, ClockSampler(local_rank))
+    out = {
+        "metric": METRIC_ENS, "value": ens["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ens["device_ms"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"Cance {ENS_MEMBERS}-member ensemble, T={CANCE_T}, nac={CANCE_CELLS}, generate_samples(random_state=99) parameter sets",
+                   "members_per_rank": ens["members_per_rank"], "members_per_launch": ens["members_per_launch"],
+                   "l2": "inputs larger than L2: the members' row buffers (2.4 MB per member) stream through HBM; the shared "
+                         "forcing (4.4 MB) is L2-resident by nature of the workload",
+                   "parallelism": f"members sharded over {world} ranks, no data-path collective, one all-gather of the costs",
+                   "wall_ms_per_step": ens["wall_ms_per_step"], "cost_checksum": ens["cost_checksum"]},
+        "roofline": {"bound": "hbm", "achieved": 8.0 * ens["units"] / (ens["device_ms"] * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                     "frac": 8.0 * ens["units"] / (ens["device_ms"] * 1e-3) / 1e9 / peak / world, "traffic": None, "peak_source": peak_src,
+                     "note": "per GPU, against 8 B per member cell-step (SURVEY 8d); the forcing is shared by the members and "
+                             "L2-resident, so this configuration is bound by instruction issue and the row traffic of the split "
+                             "passes, not by algorithmic HBM bytes", "kernels_ms": ens["kernels_ms"]},
+        "cpu_baseline": None, "e2e": ens["e2e"], "gpu_launches": args.steps * ens["launches_per_step"], "clocks": ens["clocks"],
+    }
+    if not args.no_extra:
+        # configs[4]: regionalised calibration, 8 Cance-sized catchments per rank (different periods / observations), shared
+        # hyper-polynomial mapping, ONE all-reduce of (cost, gradient) per evaluation
+        def catchments():
+            cs = []
+            for k in range(8):
+                mk = cases.cance(T=1440 - 24 * ((rank * 8 + k) % 5))
+                mk.input_data.qobs = np.asfortranarray(mk.input_data.qobs * np.float32(1.0 + 0.01 * (rank * 8 + k)))
+                mk.input_data._forcing_version = 100 + rank * 8 + k
+                cases.set_optimize(mk.setup, mk.mesh, jobs_fun=("nse",), mapping="hyper-polynomial")
+                mk.setup._optimize.optim_parameters[[1, 3, 6, 15]] = 1
+                mk.setup._optimize.maxiter = 5
+                mk.setup._optimize.verbose = False
+                cs.append((mk.setup, mk.mesh, mk.input_data, mk.parameters, mk.states, mk.output))
+            return cs
+        sdist.optimize_hyper_lbfgsb_sharded(catchments(), comm=comm)
+        cs = catchments()
+        comm_barrier(comm)
+        t0 = time.perf_counter()
+        sdist.optimize_hyper_lbfgsb_sharded(cs, comm=comm)
+        comm_barrier(comm)
+        dtr = comm_max(comm, time.perf_counter() - t0)
+        out["regional_calibration"] = {"catchments": 8 * world, "catchments_per_rank": 8, "iterations": 5, "wall_s": dtr,
+                                       "s_per_iteration": dtr / 5, "scaling": "weak",
+                                       "collective": "NCCL all-reduce of 1 + 4 x 5 float64 per evaluation (library communicator)",
+                                       "rank0_cost": float(cs[0][5].cost)}
+        # ONE France run with its 3 434 drainage basins spread over the ranks (whole basins per rank, no exchange)
+        model = cases.france(T=args.T, seed=0)
+        units = int(model.mesh.nac) * args.T
+        masks, load = sdist.basin_masks(model.mesh, world, model.setup)
+        model.mesh._local_active_cell = masks[rank]
+        pkb = L.Packed()
+        sb_, mb_, ib_ = L.pack_setup(model.setup, model.mesh, pkb), L.pack_mesh(model.mesh, model.setup, pkb), L.pack_input(model.input_data, model.setup, model.mesh, pkb)
+        pb_, stb_ = L.pack_parameters(model.parameters, pkb), L.pack_states(model.states, pkb)
+        planb = C.c_void_p()
+        L.check(lib.smash_b200_plan_create(C.byref(sb_), C.byref(mb_), 1, C.byref(planb)))
+        L.check(lib.smash_b200_plan_set_forcing(planb, C.byref(sb_), C.byref(ib_)))
+        L.check(lib.smash_b200_plan_set_fields(planb, C.byref(pb_), C.byref(stb_), None, None, 0))
+        msb = C.c_float(0.0)
+        for _ in range(3):
+            L.check(lib.smash_b200_plan_run_forward(planb, C.byref(msb)))
+        comm_barrier(comm)
+        nrep, tot = 20, 0.0
+        for _ in range(nrep):
+            L.check(lib.smash_b200_plan_run_forward(planb, C.byref(msb)))
+            tot += msb.value
+        dtb = comm_max(comm, tot / nrep)
+        lib.smash_b200_plan_destroy(planb)
+        out["france_split_by_basin"] = {"cell_timesteps_per_s": units / (dtb * 1e-3), "device_ms_per_run": dtb, "scaling": "strong",
+                                        "cells_per_rank": [int(x) for x in load], "collective": "none",
+                                        "frac_of_12B_roofline_all_gpus": 12.0 * units / (dtb * 1e-3) / 1e9 / (peak * world)}
+    if rank == 0:
+        print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# N = 1: France forward (headline), gradient, ensemble, e2e, CPU baseline, parity numbers
+# ------------------------------------------------------------------------------------------------
+def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
     T = args.T
-    model, t_build = build_france(T, seed=rank)
+    t0 = time.time()
+    model = cases.france(T=T, seed=0)
+    t_build = time.time() - t0
     nac = int(model.mesh.nac)
     units = nac * T
-
     pk = L.Packed()
     s_, m_, i_ = L.pack_setup(model.setup, model.mesh, pk), L.pack_mesh(model.mesh, model.setup, pk), L.pack_input(model.input_data, model.setup, model.mesh, pk)
     p_, st_ = L.pack_parameters(model.parameters, pk), L.pack_states(model.states, pk)
@@ -182,14 +392,12 @@ def main():
     L.check(lib.smash_b200_plan_set_fields(plan, C.byref(p_), C.byref(st_), None, None, 0))
     info = (C.c_int64 * 12)()
     lib.smash_b200_plan_info(plan, info)
-
     ms = C.c_float(0.0)
     kt = (C.c_float * 5)()
     for _ in range(args.warmup):
         L.check(lib.smash_b200_plan_run_forward(plan, C.byref(ms)))
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
     kernel_ms, per_kernel = [], []
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -197,217 +405,149 @@ def main():
         kernel_ms.append(ms.value)
         L.check(lib.smash_b200_plan_kernel_times(plan, kt))           # events recorded inside the run, read after it
         per_kernel.append([kt[i] for i in range(5)])
-    barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
-    wall = max_over_ranks(wall)
-    kms = max_over_ranks(float(np.mean(kernel_ms)))
-    value = world * units * args.steps / wall
+    kms = float(np.mean(kernel_ms))
+    value = units * args.steps / wall
     chk = C.c_double(0.0)
     L.check(lib.smash_b200_plan_checksum(plan, C.byref(chk)))
+    lib.smash_b200_plan_info(plan, info)
+    launches_per_step = int(info[7])
 
-    # ---- roofline (device events on the launching stream, average over the timed launches)
-    peak, peak_src = measured_peaks()
-    split = int(info[11]) == -1
-    step_bytes = 12.0 * units
-    roofline_step = {"achieved": step_bytes / (kms * 1e-3) / 1e9, "frac": step_bytes / (kms * 1e-3) / 1e9 / peak,
-                     "algorithmic_bytes_per_step": step_bytes, "device_ms": kms}
+    # ---- roofline: the whole step against 12 B per cell-step; kernels with their time, share and measured DRAM traffic
     traffic = {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             traffic = json.load(f)
     except Exception:
         pass
-    if split:
-        pk_ms = np.mean(np.array(per_kernel), axis=0)
-        nrt, nedge = float(lib.smash_b200_plan_stat(plan, b"routed_cells")), float(lib.smash_b200_plan_stat(plan, b"inflow_edges"))
-        names = ["vertical_forward_kernel", "route_forward_kernel", "rows_to_domain_kernel"]
-        # algorithmic bytes per launch: reservoir pass 8 B forcing + 4 B series per cell-step;
-        # routing 4 B per routed cell-step in and out + 4 B per inflow edge-step; export 8 B per routed cell-step
-        kbytes = [12.0 * units, 4.0 * T * (2.0 * nrt + nedge), 8.0 * T * nrt]
-        fused_export = pk_ms[2] < 0.02                # option fuse_export: the routing warps write qsim_domain themselves
-        ktraffic = [traffic.get(n) for n in names]
-        if fused_export:
-            kbytes[1] += kbytes[2]                    # (profiles/ncu_traffic.json holds the traffic of the fused kernel)
-        kernels = {names[i]: {"ms": float(pk_ms[i]), "share": float(pk_ms[i] / kms), "algorithmic_bytes": kbytes[i],
-                              "achieved_gbs": kbytes[i] / (pk_ms[i] * 1e-3) / 1e9, "frac": kbytes[i] / (pk_ms[i] * 1e-3) / 1e9 / peak,
-                              "traffic": ktraffic[i]} for i in range(3) if pk_ms[i] > 0 and not (i == 2 and fused_export)}
-        if fused_export:
-            kernels[names[1]]["includes"] = "export of the routed cells' series to [t][cell] (8 B per routed cell-step)"
-        top = max(kernels, key=lambda k: kernels[k]["ms"])
-        roofline = {"bound": "hbm", "achieved": kernels[top]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                    "frac": kernels[top]["frac"], "traffic": kernels[top]["traffic"], "peak_source": peak_src, "kernel": top,
-                    "kernel_ms": kernels[top]["ms"], "algorithmic_bytes_per_launch": kernels[top]["algorithmic_bytes"],
-                    "kernels": kernels, "step": roofline_step}
-        lib.smash_b200_plan_info(plan, info)
-        launches_per_step = int(info[7])             # kernels launched by the last plan_run_forward (counted by the library)
-    else:
-        roofline = {"bound": "hbm", "achieved": roofline_step["achieved"], "peak": peak, "unit": "GB/s",
-                    "frac": roofline_step["frac"], "traffic": traffic.get("forward_kernel"), "peak_source": peak_src,
-                    "kernel": "forward_kernel", "kernel_ms": kms, "algorithmic_bytes_per_launch": step_bytes,
-                    "step": roofline_step}
-        launches_per_step = 1
+    step_bytes = 12.0 * units
+    pk_ms = np.mean(np.array(per_kernel), axis=0)
+    window_pass = lib.smash_b200_plan_stat(plan, b"window_pass") == 1.0
+    names = ["window_forward_kernel" if window_pass else "vertical_forward_kernel", "route_forward_kernel", "rows_to_domain_kernel"]
+    kernels = {names[i]: {"ms": float(pk_ms[i]), "share": float(pk_ms[i] / kms), "dram_traffic_bytes": traffic.get(names[i])}
+               for i in range(3) if pk_ms[i] > 0.02}
+    tr = [k["dram_traffic_bytes"] for k in kernels.values()]
+    roofline = {"bound": "hbm", "achieved": step_bytes / (kms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": step_bytes / (kms * 1e-3) / 1e9 / peak, "traffic": float(sum(tr)) if tr and all(t is not None for t in tr) else None,
+                "peak_source": peak_src, "scope": "whole forward step (all kernels), SURVEY 8(d): 12 B per active cell-step",
+                "algorithmic_bytes_per_step": step_bytes, "device_ms": kms, "kernels": kernels}
 
-    extra = {}
+    # ---- gradient (first class): forward sweep with the tape + cost + reverse sweeps
+    gradient = None
     if not args.no_extra:
-        # fwd + adjoint gradient on the same mesh (store-all tape in HBM): 48 B per cell-step moved by design
         f_ms, r_ms = C.c_float(0), C.c_float(0)
         L.check(lib.smash_b200_plan_run_gradient(plan, C.byref(f_ms), C.byref(r_ms)))
-        gms = []
-        for _ in range(max(2, args.steps // 3)):
+        gms, gk = [], []
+        for _ in range(max(3, args.steps // 5)):
             L.check(lib.smash_b200_plan_run_gradient(plan, C.byref(f_ms), C.byref(r_ms)))
             gms.append((f_ms.value, r_ms.value))
+            L.check(lib.smash_b200_plan_kernel_times(plan, kt))
+            gk.append([kt[i] for i in range(5)])
         gf, gr = float(np.mean([g[0] for g in gms])), float(np.mean([g[1] for g in gms]))
-        extra["france_gradient"] = {"evals_per_s": 1e3 / (gf + gr), "cell_timesteps_per_s": units / ((gf + gr) * 1e-3),
-                                    "forward_tape_ms": gf, "reverse_ms": gr,
-                                    "hbm_frac_vs_40B": 40.0 * units / ((gf + gr) * 1e-3) / 1e9 / peak}
+        gk = np.mean(np.array(gk), axis=0)
+        ck = lib.smash_b200_plan_stat(plan, b"checkpoint") == 1.0
+        gradient = {"evals_per_s": 1e3 / (gf + gr), "cell_timesteps_per_s": units / ((gf + gr) * 1e-3), "ms_per_eval": gf + gr,
+                    "forward_tape_ms": gf, "reverse_ms": gr, "frac_of_40B_roofline": 40.0 * units / ((gf + gr) * 1e-3) / 1e9 / peak,
+                    "tape": "checkpointed, 256-step windows (forward sweeps: 2)" if ck else "store-all in HBM (forward sweeps: 1)",
+                    "tape_gb": lib.smash_b200_plan_stat(plan, b"tape_bytes") / 1e9,
+                    "kernels_ms": {"vertical_forward_kernel(tape)": float(gk[0]), "route_forward_kernel(tape)": float(gk[1]),
+                                   "route_adjoint_kernel": float(gk[3]), "vertical_adjoint_kernel": float(gk[4])}}
     lib.smash_b200_plan_destroy(plan)
 
     # ---- e2e through the drop-in call with host buffers
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     model.input_data._forcing_version = 0
-    # the forcing / output arrays live until clear_cache() below: let the library page-lock them in place (opt-in option)
-    lib.smash_b200_set_option(b"pin_host", 1)
-
-    par_bgd, sta_bgd = model.parameters.copy(), model.states.copy()     # the background never changes between calls
+    lib.smash_b200_set_option(b"pin_host", 1)      # the forcing / output arrays live until clear_cache() below
+    par_bgd, sta_bgd = model.parameters.copy(), model.states.copy()
 
     def e2e_step():
-        smash_b200.forward(model.setup, model.mesh, model.input_data, model.parameters, par_bgd, model.states, sta_bgd,
-                           model.output)
+        smash_b200.forward(model.setup, model.mesh, model.input_data, model.parameters, par_bgd, model.states, sta_bgd, model.output)
 
+    t0 = time.perf_counter()
     e2e_step()
-    barrier()
+    first_call_s = time.perf_counter() - t0
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         e2e_step()
-    barrier()
-    e2e_wall = max_over_ranks(time.perf_counter() - t0)
+    e2e_wall = time.perf_counter() - t0
     h2d = 2 * nac * T * 4 + 7 * model.mesh.nrow * model.mesh.ncol * 4
     d2h = nac * T * 4 + 3 * int(info[1]) * int(info[2]) * 4 + 4
-    e2e = {"value": world * units * e2e_steps / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-           "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
+    e2e = {"value": units * e2e_steps / e2e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3, "first_call_ms_incl_page_locking": first_call_s * 1e3,
            "host_buffers": "caller's NumPy arrays, page-locked in place by the library (option pin_host=1) during the untimed first call",
            "streamed": "256-step windows: upload, kernels and download overlap on three streams"}
     lib.smash_b200_clear_cache()
     lib.smash_b200_set_option(b"pin_host", 0)
 
-    cpu = None
-    if rank == 0 and world == 1:
-        import cases
-        import oracle
-        Ts = 64                                  # ~10 s of single-thread CPU work
-        mc = cases.france(T=Ts, seed=0)
-        mc.setup.save_qsim_domain = False
-        t0 = time.perf_counter()
-        oracle.forward(mc.setup, mc.mesh, mc.input_data, mc.parameters, mc.parameters.copy(), mc.states, mc.states.copy(), mc.output)
-        dtc = time.perf_counter() - t0
-        cpu = {"value": nac * Ts / dtc, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"France mesh, first {Ts} of {T} steps ({nac * Ts} cell-steps, {dtc:.1f} s), C oracle -O3, 1 thread "
-                         "(a single forward of the reference is single-threaded)"}
-        if not args.no_extra:
-            extra.update(cance_extras(lib, L, smash_b200, oracle, cases))
-    if world > 1 and not args.no_extra:
-        # configs[2]: the 4096-member Cance ensemble split over the ranks (contiguous member blocks, no data-path collective;
-        # one all-gather of the costs afterwards) -- total work fixed, i.e. strong scaling of this extra
-        import cases
-        from smash_b200 import distributed as sdist
-        mc = cases.cance()
-        mc.input_data._forcing_version = 1
-        ns = 4096
-        rng = np.random.RandomState(99)
-        bounds = [(1e-6, 1e3), (1e-6, 1e3), (-50.0, 50.0), (1e-6, 1e3)]
-        smp = np.asfortranarray(np.stack([rng.uniform(lo, hi, ns) for lo, hi in bounds]).astype(np.float32))
-        cost, q0 = np.zeros(ns, np.float32), np.zeros((0,), np.float32)
+    # ---- CPU baseline: the oracle on one host core, same configuration, bounded sample
+    import oracle
+    Ts = 64
+    mc = cases.france(T=Ts, seed=0)
+    t0 = time.perf_counter()
+    oracle.forward(mc.setup, mc.mesh, mc.input_data, mc.parameters, mc.parameters.copy(), mc.states, mc.states.copy(), mc.output)
+    dtc = time.perf_counter() - t0
+    cpu = {"value": nac * Ts / dtc, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"France mesh, first {Ts} of {T} steps ({nac * Ts} cell-steps, {dtc:.1f} s), save_qsim_domain, C oracle -O3 "
+                     "-march=x86-64-v3, 1 thread (a single forward of the reference is single-threaded)"}
 
-        def ens():
-            sdist.multiple_run_sharded(mc.setup, mc.mesh, mc.input_data, mc.parameters, mc.states, mc.output, smp,
-                                       cases.IND_CP_CFT_EXC_LR, cost, q0)
+    out = {
+        "metric": METRIC_FRANCE, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"France 1km mesh forward gr-a, nac={nac}, T={T}, save_qsim_domain (setup_France.yaml)",
+                   "engine": "split: " + ("window pass (reservoirs + shallow routing) + chain scans over the deep cells" if window_pass
+                                          else "reservoir pass per cell + routing scan per heavy-path chain"),
+                   "pit_pairs": int(info[6]), "l2": "inputs larger than L2 (5.2 GB forcing streamed once per step)",
+                   "parallelism": "1 GPU", "checksum_q": chk.value, "model_build_s": t_build},
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
+        "gradient": gradient,
+    }
+    if not args.no_extra:
+        ens = bench_ensemble(lib, L, smash_b200, cases, None, 0, 1, max(2, min(5, args.steps)), 1)
+        ens.pop("clocks")
+        ens["cell_timesteps_per_s"] = ens.pop("value")
+        out["ensemble"] = ens
+        out["parity"] = parity_numbers(smash_b200, oracle, cases)
+        out["extra"] = cance_extras(lib, L, smash_b200, oracle, cases)
+    print(json.dumps(out))
 
-        ens()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(3):
-            ens()
-        barrier()
-        dte = max_over_ranks(time.perf_counter() - t0) / 3
-        # configs[4]: regionalised calibration, one Cance-sized catchment per rank, shared hyper-polynomial mapping,
-        # one all-reduce of (cost, gradient) per evaluation
-        def catchment():
-            mk = cases.cance()
-            mk.input_data.qobs = np.asfortranarray(mk.input_data.qobs * np.float32(1.0 + 0.05 * rank))
-            mk.input_data._forcing_version = 100 + rank
-            cases.set_optimize(mk.setup, mk.mesh, jobs_fun=("nse",), mapping="hyper-polynomial")
-            mk.setup._optimize.optim_parameters[[1, 3, 6, 15]] = 1
-            mk.setup._optimize.maxiter = 10
-            mk.setup._optimize.verbose = False
-            return mk
-        mk = catchment()
-        sdist.optimize_hyper_lbfgsb_sharded([(mk.setup, mk.mesh, mk.input_data, mk.parameters, mk.states, mk.output)])
-        mk = catchment()
-        barrier()
-        t0 = time.perf_counter()
-        sdist.optimize_hyper_lbfgsb_sharded([(mk.setup, mk.mesh, mk.input_data, mk.parameters, mk.states, mk.output)])
-        barrier()
-        dtr = max_over_ranks(time.perf_counter() - t0)
-        extra["regional_hyper_polynomial_lbfgsb"] = {"catchments": world, "iterations": 10, "wall_s": dtr,
-                                                     "s_per_iteration": dtr / 10, "collective": "all-reduce of 21 float64 per evaluation",
-                                                     "rank0_cost": float(mk.output.cost)}
-        # ONE France run with its 3 434 drainage basins spread over the ranks (whole basins per rank, no exchange):
-        # strong scaling of a single domain, bounded by the largest basin (the Loire, 15 % of the cells)
-        masks, load = sdist.basin_masks(model.mesh, world, model.setup)
-        keep_mask = model.mesh._local_active_cell
-        model.mesh._local_active_cell = masks[rank]
-        if hasattr(model.mesh, "_b200_cache"):
-            del model.mesh._b200_cache
-        pkb = L.Packed()
-        sb_, mb_, ib_ = L.pack_setup(model.setup, model.mesh, pkb), L.pack_mesh(model.mesh, model.setup, pkb), L.pack_input(model.input_data, model.setup, model.mesh, pkb)
-        planb = C.c_void_p()
-        L.check(lib.smash_b200_plan_create(C.byref(sb_), C.byref(mb_), 1, C.byref(planb)))
-        L.check(lib.smash_b200_plan_set_forcing(planb, C.byref(sb_), C.byref(ib_)))
-        L.check(lib.smash_b200_plan_set_fields(planb, C.byref(p_), C.byref(st_), None, None, 0))
-        msb = C.c_float(0.0)
-        for _ in range(3):
-            L.check(lib.smash_b200_plan_run_forward(planb, C.byref(msb)))
-        barrier()
-        tb0 = time.perf_counter()
-        nrep = 20
-        for _ in range(nrep):
-            L.check(lib.smash_b200_plan_run_forward(planb, C.byref(msb)))
-        barrier()
-        dtb = max_over_ranks(time.perf_counter() - tb0) / nrep
-        lib.smash_b200_plan_destroy(planb)
-        model.mesh._local_active_cell = keep_mask
-        if hasattr(model.mesh, "_b200_cache"):
-            del model.mesh._b200_cache
-        extra["france_one_domain_split_by_basin"] = {"cell_timesteps_per_s": units / dtb, "ms_per_run": dtb * 1e3, "scaling": "strong",
-                                                     "cells_per_rank": [int(x) for x in load], "collective": "none"}
-        extra["cance_ensemble_4096_sharded"] = {"cell_timesteps_per_s_e2e": ns * 383 * 1440 / dte, "ms_per_call": dte * 1e3,
-                                                "members_per_rank": ns // world, "scaling": "strong",
-                                                "cost_checksum": float(np.sum(cost[np.isfinite(cost)], dtype=np.float64))}
 
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"France 1km mesh forward gr-a, nac={nac}, T={T}, save_qsim_domain (setup_France.yaml)",
-                       "engine": "split (reservoir pass per cell + routing scan per heavy-path chain)" if split else "fused tick wavefront",
-                       "ctas": int(info[1]), "cta_size": int(info[2]),
-                       **({"chains": int(info[5]), "routing_tasks": int(info[10]), "chain_dependency_height": int(info[3]),
-                           "longest_dependency_path_cells": int(info[8])} if split else
-                          {"max_skew": int(info[3]), "cross_block_edges": int(info[5])}),
-                       "pit_pairs": int(info[6]),
-                       "l2": "inputs larger than L2 (5.2 GB forcing streamed once per step)",
-                       "parallelism": f"{world} independent domain replica(s), no collective", "checksum_q": chk.value,
-                       "model_build_s": t_build},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks, "extra": extra,
-        }))
-    if dist is not None:
-        dist.destroy_process_group()
+def parity_numbers(smash_b200, oracle, cases):
+    """Measured differences of the device path to the float32 oracle (and of the float32 oracle to the float64 one, the
+    noise floor of the model in the reference's real kind) -- numbers, not pass / fail."""
+    from smash_b200.solver._derived_types import ParametersDT, StatesDT
+    out = {}
+
+    def rel(a, b):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        m = np.abs(b) > 1e-2
+        return float((np.abs(a - b)[m] / np.abs(b)[m]).max()) if m.any() else 0.0
+
+    a, b, c = cases.cance(), cases.cance(), cases.cance()
+    for m in (a, b, c):
+        rng = np.random.default_rng(1)
+        act = m.mesh.active_cell == 1
+        for name, lo, hi in (("cp", 50, 600), ("cft", 50, 800), ("exc", -5, 5), ("lr", 1, 30)):
+            getattr(m.parameters, name)[act] = rng.uniform(lo, hi, int(act.sum())).astype(np.float32)
+    pa, sa, pb, sb = ParametersDT(a.mesh), StatesDT(a.mesh), ParametersDT(b.mesh), StatesDT(b.mesh)
+    smash_b200.forward_b(a.setup, a.mesh, a.input_data, a.parameters, pa, a.parameters.copy(), None, a.states, sa, a.states.copy(),
+                         None, a.output, None)
+    oracle.forward_b(b.setup, b.mesh, b.input_data, b.parameters, pb, b.parameters.copy(), b.states, sb, b.states.copy(), b.output)
+    oracle.forward(c.setup, c.mesh, c.input_data, c.parameters, c.parameters.copy(), c.states, c.states.copy(), c.output, precision="f64")
+    out["cance_T1440_qsim_max_rel_gpu_vs_f32_oracle"] = rel(a.output.qsim, b.output.qsim)
+    out["cance_T1440_qsim_max_rel_gpu_vs_f64_oracle"] = rel(a.output.qsim, c.output.qsim)
+    out["cance_T1440_qsim_max_rel_f32_oracle_vs_f64_oracle"] = rel(b.output.qsim, c.output.qsim)
+    out["cance_T1440_cost_abs_diff"] = abs(float(a.output.cost) - float(b.output.cost))
+    for n in ("cp", "cft", "exc", "lr"):
+        x, y = np.asarray(getattr(pa, n), np.float64), np.asarray(getattr(pb, n), np.float64)
+        out[f"cance_gradient_{n}_max_err_over_inf_norm"] = float(np.abs(x - y).max() / np.abs(y).max())
+        out[f"cance_gradient_{n}_cosine"] = float((x * y).sum() / np.sqrt((x * x).sum() * (y * y).sum()))
+    return out
 
 
 def cance_extras(lib, L, smash_b200, oracle, cases):
-    """Cance (383 cells, T=1440): single gradient latency and the 4096-member ensemble (configs[1], configs[2])."""
+    """Cance (383 cells, T = 1440): single gradient latency and the variational calibration loop (configs[1])."""
     from smash_b200.solver._derived_types import ParametersDT, StatesDT
     out = {}
     m = cases.cance()
@@ -431,37 +571,8 @@ def cance_extras(lib, L, smash_b200, oracle, cases):
     oracle.forward_b(mo.setup, mo.mesh, mo.input_data, mo.parameters, po, mo.parameters.copy(), mo.states, so, mo.states.copy(), mo.output)
     dto = time.perf_counter() - t0
     out["cance_gradient"] = {"evals_per_s": 1.0 / dt, "ms_per_eval_e2e": dt * 1e3, "cpu_port_ms_per_eval": dto * 1e3, "cpu_cores": 1}
-    # ensemble
-    ns = 4096
-    rng = np.random.RandomState(99)
-    bounds = [(1e-6, 1e3), (1e-6, 1e3), (-50.0, 50.0), (1e-6, 1e3)]
-    smp = np.asfortranarray(np.stack([rng.uniform(lo, hi, ns) for lo, hi in bounds]).astype(np.float32))
-    cost = np.zeros(ns, np.float32)
-    q0 = np.zeros((0,), np.float32)
-
-    def ens():
-        smash_b200.compute_multiple_run(m.setup, m.mesh, m.input_data, m.parameters, m.states, m.output, smp,
-                                        cases.IND_CP_CFT_EXC_LR, cost, q0)
-
-    ens()
-    t0 = time.perf_counter()
-    for _ in range(3):
-        ens()
-    dte = (time.perf_counter() - t0) / 3
-    nthreads = os.cpu_count() or 1
-    nso = 64
-    co = np.zeros(nso, np.float32)
-    t0 = time.perf_counter()
-    oracle.compute_multiple_run(mo.setup, mo.mesh, mo.input_data, mo.parameters, mo.states, mo.output, smp[:, :nso],
-                                cases.IND_CP_CFT_EXC_LR, co, q0, nthreads=nthreads)
-    dtoe = time.perf_counter() - t0
-    cs = 383 * 1440
-    out["cance_ensemble_4096"] = {"cell_timesteps_per_s_e2e": ns * cs / dte, "ms_per_call": dte * 1e3,
-                                  "cpu_port_cell_timesteps_per_s": nso * cs / dtoe, "cpu_cores": nthreads,
-                                  "cpu_sample": f"{nso} members, OpenMP over members"}
     # configs[1]: distributed-mapping variational calibration, L-BFGS-B driven by the adjoint gradient (mw_optimize.f90:484-676)
     from smash_b200 import simulation
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_solver                                  # the CPU port behind the solver signatures (checker / baseline only)
     iters = 20
     simulation.optimize(cases.cance(), mapping="distributed", options={"maxiter": 2})            # warm-up (plan, forcing)
