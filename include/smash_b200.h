@@ -156,28 +156,24 @@ const char *smash_b200_version(void);
 int smash_b200_device_count(void);           /* number of CUDA devices, 0 if none / no driver */
 int smash_b200_set_device(int device);       /* device used by subsequent calls of this thread */
 void smash_b200_clear_cache(void);           /* drop cached mesh plans and device-resident forcing */
-/* tuning knobs (also readable from the environment as SMASH_B200_<NAME>): "math" 1 (default) = MUFU
- * reciprocal / rsqrt with the cancellation-free transfer formula (closer to the float64 solution than the
- * reference's own float32 arithmetic), 0 = IEEE division / sqrt + libm tanhf in the reference's
- * statement order; "block" = cells per CTA (0 = automatic);
- * "member_budget_mb" = device memory per ensemble launch; "engine" 1 = split engine (reservoir pass per cell + routing
- * scan per chain, default with math = 1), 0 = fused tick wavefront; "ensemble_engine" the same choice for
- * compute_multiple_run (split engine: routing with lane = member); "pin_host" 1 = page-lock large caller-owned host
- * arrays in place on first use (PCIe-speed copies) -- the caller must then call smash_b200_clear_cache() before freeing
- * them; off by default; "river_wave" 1 = the longest chains are cut into reaches of at most 128 cells, one CTA per reach,
- * routed as pipelined tick wavefronts (thread = cell, strictly sequential arithmetic) instead of a window scan per cell
- * (experimental: slower than the default on the France mesh); "stream" 1 (default) = forward runs
- * whose sparse forcing is at least "stream_min_mb" (256) megabytes are cut into 256-step windows so that the forcing upload,
- * the kernels and the download of sparse_qsim_domain overlap on three streams (effective with page-locked arrays);
- * "fuse_export" (default 4) = warps per routing CTA that, once every chain has been claimed, also write the routed cells'
- * series to the [t][cell] domain layout as the chains owning a tile of 32 cells finish, in the shadow of the serial walks
- * down the main rivers; 0 = separate rows_to_domain kernel after the routing pass; "route_dynamic" 1 (default) = the
- * ticketed chains of the routing pass are handed out from ready queues (a chain is queued when its last tributary chain has
- * finished; one queue per basin of a long river, longest first, "route_queues" of them, plus one for the rest), 0 = static
- * ticket order with done-flag waits; "route_order" = static ticket order: 0 by topological level (default), 1 by distance
- * to the outlet, 2 basin by basin (both measured slower); diagnostics: "route_ctas_per_sm" (1 / 2:
- * fewer routing CTAs per SM than fit), "plan_small_windows" (256-step routing windows in plans of the plan API),
- * "dbg_prof" (per-river-chain cycle counts on stderr). */
+/* options (also readable from the environment as SMASH_B200_<NAME>):
+ *   "math"  1 (default) = MUFU reciprocal / rsqrt with the cancellation-free transfer formula (closer to the float64 solution
+ *           than the reference's own float32 arithmetic); 0 = IEEE division / sqrt + libm tanhf in the
+ *           reference's statement order (runs on the fused engine)
+ *   "engine" / "ensemble_engine"  1 = split engine (default with math = 1), 0 = fused tick wavefront; the second name is the
+ *           same choice for compute_multiple_run
+ *   "member_budget_mb"  device memory per ensemble launch (default 16384)
+ *   "pin_host"  1 = page-lock large caller-owned host arrays in place on first use (PCIe-speed copies); the caller must then
+ *           call smash_b200_clear_cache() before freeing them; off by default
+ *   "stream" (default 1), "stream_min_mb" (256)  forward runs with at least that much sparse forcing are cut into 256-step
+ *           windows so that upload, kernels and the download of sparse_qsim_domain overlap on three streams
+ *   "adjoint_checkpoint"  -1 (default) = gradient runs whose store-all tape would exceed "tape_budget_mb" (16384) run their
+ *           reverse sweep window by window from checkpointed states (one forward replay per 256-step window); 1 = always,
+ *           0 = never
+ *   "window_pass" (default 0), "shallow_acc" (32)  experimental forward path for large domains: reservoirs and the routing of
+ *           the cells with flwacc <= shallow_acc in one pass over 8-step windows (window_kernels.cu), chain scans over the rest
+ *   "fuse_export" (default 4)  warps per routing CTA that also write the routed cells' series to the [t][cell] layout
+ * Build-time options are part of the plan cache key: changing one makes a new plan. */
 int smash_b200_set_option(const char *name, long long value);
 
 /* ---- device-resident plan API (bench / advanced callers) --------------------------------------
@@ -188,7 +184,8 @@ typedef struct SmashPlan SmashPlan;
 
 int smash_b200_plan_create(const SmashSetup *setup, const SmashMesh *mesh, int32_t nmember, SmashPlan **plan);
 void smash_b200_plan_destroy(SmashPlan *plan);
-/* upload + re-layout forcing ([block][tick][prcp|pet][cell]); qobs too if present */
+/* forcing to the device (sparse [t][k] arrays whose order is the cell order are used in place, anything else is packed to
+ * [t][cell] once); qobs too if present */
 int smash_b200_plan_set_forcing(SmashPlan *plan, const SmashSetup *setup, const SmashInputData *input_data);
 /* member-major parameter / state values: uniform_sample F(nvar,nmember) applied on top of the planes */
 int smash_b200_plan_set_fields(SmashPlan *plan, const SmashParameters *parameters, const SmashStates *states,

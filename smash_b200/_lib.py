@@ -149,6 +149,10 @@ def pack_setup(setup, mesh, pk: Packed) -> SmashSetup:
     s = SmashSetup()
     if setup.structure not in STRUCTURES:
         raise ValueError(f"unknown structure {setup.structure!r}")
+    if setup.structure != "gr-a":
+        # the device kernels cover gr-a (md_forward_structure.f90:30-214); fail before any packing or upload work
+        raise NotImplementedError(f"structure {setup.structure!r}: smash_b200 implements 'gr-a' only "
+                                  "(gr-b, gr-c, gr-d, vic-a are listed as next in DESIGN.md section 7); there is no CPU fallback")
     s.structure = STRUCTURES[setup.structure]
     s.dt = float(setup.dt)
     s.ntime_step = int(setup._ntime_step)
@@ -191,9 +195,14 @@ def pack_mesh(mesh, setup, pk: Packed) -> SmashMesh:
     m = SmashMesh()
     m.dx = float(mesh.dx)
     m.nrow, m.ncol, m.ng, m.nac = int(mesh.nrow), int(mesh.ncol), int(mesh.ng), int(mesh.nac)
+    # The converted arrays are cached on the mesh object.  The key holds the source arrays themselves (identity compared, and
+    # kept alive so that an id cannot be recycled); rebinding any of them -- e.g. mesh._local_active_cell for a basin shard --
+    # makes a new image.  In-place edits of a keyed array are not seen: rebind or delete mesh._b200_cache.
     cache = getattr(mesh, "_b200_cache", None)
-    key = (id(mesh.flwdir), id(mesh.flwacc), id(mesh.path), id(mesh.active_cell))
-    if cache is None or cache[0] != key:
+    srcs = (mesh.flwdir, mesh.flwacc, mesh.path, mesh.active_cell, getattr(mesh, "_local_active_cell", None),
+            getattr(mesh, "gauge_pos", None), getattr(mesh, "area", None))
+    key = tuple(srcs)
+    if cache is None or len(cache[0]) != len(key) or any(x is not y for x, y in zip(cache[0], key)):
         arrs = {}
         arrs["flwdir"] = np.asfortranarray(mesh.flwdir, dtype=np.int32)
         arrs["flwacc"] = np.asfortranarray(mesh.flwacc, dtype=np.int32)

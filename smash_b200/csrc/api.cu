@@ -445,8 +445,7 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     RouteGraph &rg = sp.rg;
     std::string err = build_route_graph(rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
                                         mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
-                                        (int)option("route_ded_max", option("river_wave", 0) ? 224 : 64),
-                                        option("river_wave", 0) ? 128 : 0, (int)option("route_order", 0));
+                                        (int)option("route_ded_max", 64), 0, 0);
     if (!err.empty()) {
         *unsupported = err.rfind("unsupported", 0) == 0;
         return fail(SMASH_B200_EINVAL, "%s", err.c_str());
@@ -569,9 +568,7 @@ static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp, SplitSta
         a.dbg_prof = dp;
     }
     a.save_q = save_q ? 1 : 0; a.save_netp = save_netp ? 1 : 0;
-    a.river_wave = (int)option("river_wave", 0);
     a.fuse_export = 0;
-    a.route_ctas_per_sm = (int)option("route_ctas_per_sm", 0);
     a.dyn = (option("route_dynamic", 1) != 0 && pl.nmember == 1 && gr.rg.nchain > gr.rg.nded) ? 1 : 0;
     a.dyn_nq = gr.dyn_nq; a.qctl = gr.d_qctl.p; a.queue = gr.d_queue.p; a.ndep = gr.d_ndep.p; a.cons = gr.d_cons.p; a.qid = gr.d_qid.p;
     a.qoff = gr.d_qoff.p; a.qctl0 = gr.d_qctl0.p; a.queue0 = gr.d_queue0.p; a.ndep0 = gr.d_ndep0.p;
@@ -987,7 +984,9 @@ static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **
     char key[192];
     snprintf(key, sizeof key, "%016llx:%d:%d:%g:%g:%lld:%d:%d:%d:%lld", (unsigned long long)h, dev, setup->ntime_step, (double)setup->dt,
              (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0, small ? 1 : 0,
-             option("river_wave", 0) + 16 * option("route_order", 0) + 64 * option("adjoint_checkpoint", -1) + 1024 * option("tape_budget_mb", 16384));
+             option("route_ded_min", 96) + 1024 * option("route_ded_max", 64) + (option("route_queues", 12) << 20) +
+                 ((option("adjoint_checkpoint", -1) + 1) << 26) + (option("tape_budget_mb", 16384) << 28) +
+                 (option("window_pass", 0) << 48) + (option("shallow_acc", 32) << 50));
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
         std::unique_ptr<SmashPlan> pl(new SmashPlan());

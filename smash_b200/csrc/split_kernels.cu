@@ -892,233 +892,6 @@ __device__ __forceinline__ void route_chain_cta(const SplitArgs &a, ChainShared<
     }
 }
 
-// Tick wavefront for a dedicated chain (a river reach of at most 128 cells; route_graph.cpp cuts the long chains into
-// such reaches): thread = cell, the threads are skewed by one block of 8 time steps -- at tick tau thread i routes block
-// tau - i of its cell, strictly sequentially in time and in the reference's summation order (no scan), and hands the
-// discharge block to thread i + 1 through shared memory.  A reach of L cells costs T/8 + L ticks of 8 dependent
-// cell-steps instead of L whole-window passes.  The last cell publishes a block counter, and a reach that gathers the
-// tail of another dedicated reach (the next reach of the same river, or a large tributary) consumes it block by block
-// ("streamed" inflow) instead of waiting for the whole series: the reaches of a river form one pipeline across CTAs.
-// A thread awaits its other tributaries at its first tick, so the upper part of a reach runs while tributaries further
-// down are still being routed.  The next block of the cell's own row and of its first two tributaries travels to
-// registers while the current block is routed.
-constexpr int WAVE_CAP = 128;             // cells per reach = threads of the CTA
-struct WaveShared {
-    float hand[2][128][8];                // [tick parity][thread]: discharge block of the thread's cell
-    int2 ent[128][8];                     // inflow entries of the thread's cell: x = producer cell, y = code (below)
-};
-// entry code: bits 0-1 kind (0 chain predecessor, 1 / 2 register slot, 3 read at use), bit 2 streamed, bits 3.. producer task
-__device__ __forceinline__ void wave_wait_block(const int *prog, int want, bool prof, long long &t_swait) {
-    if (ld_acquire(prog) >= want) return;
-    const long long t = prof ? clock64() : 0;
-    while (ld_acquire(prog) < want) {}
-    if (prof) t_swait += clock64() - t;
-}
-
-template <int TAPE>
-__device__ __forceinline__ void route_chain_wave(const SplitArgs &a, WaveShared &sh, int m, int task, int w, int epoch) {
-    const SplitTopo &tp = a.tp;
-    const int tid = threadIdx.x;
-    const int cb = tp.task_begin[task], L = tp.task_begin[task + 1] - cb;
-    const int t0 = w * a.W, tend = min(a.T, (w + 1) * a.W), tcap = tend - 1;
-    const int nb = (tend - t0 + 7) >> 3;
-    const int pbase = w << 16;                                           // block counters never decrease across windows
-    const size_t npad = tp.npad;
-    int *done = a.done + (size_t)m * tp.ntask;
-    int *prog = a.done + ((size_t)a.nmember + m) * tp.ntask;             // second half of the flag buffer: blocks finished per task
-    float *rows = a.rows + (size_t)m * npad * a.Tp;
-    float *qsim = a.qsim + (size_t)m * a.T * tp.ng;
-    const float c0 = a.dx * a.dx * 0.001f / a.dt;                         // md_forward_structure.f90:155
-    const bool active = tid < L;
-    int j = 0, meta = 0, nup = 0;
-    float s_q = 0.0f, E = 0.0f, fa1 = 0.0f, h = 0.0f;
-    int lsrc[2] = {-1, -1}, lprog[2] = {-1, -1};                          // register slots: producer cell, producer task if streamed
-    __syncthreads();                                                     // shared memory of the previous member is free
-    if (active) {
-        const int4 rec = tp.tcell[cb + tid];
-        j = rec.x; meta = rec.y;
-        if (meta & 1) {
-            const RouteConst ci = route_const(a, m, j, a.hcar);
-            s_q = ci.s_q; E = ci.E; fa1 = ci.fa1; h = ci.h0;
-            nup = min(8, meta >> 8);
-            int nslot = 0;
-            for (int e = 0; e < nup; e++) {
-                const int2 u = tp.tup[rec.z + e];
-                int code;
-                if (u.y <= UP_HEAVY) code = 0;
-                else {
-                    const bool streamed = u.y >= tp.nchain - tp.nded && u.y < tp.nchain &&
-                                          tp.task_begin[u.y + 1] - tp.task_begin[u.y] <= WAVE_CAP;   // a wavefront reach
-                    const int kind = nslot < 2 ? 1 + nslot : 3;
-                    if (nslot < 2) { lsrc[nslot] = u.x; lprog[nslot] = streamed ? u.y : -1; }
-                    nslot++;
-                    code = kind | (streamed ? 4 : 0) | (max(u.y, 0) << 3);
-                    if (u.y >= 0 && !streamed) code |= 1 << 31;          // whole-series tributary of another task: await its flag
-                }
-                sh.ent[tid][e] = make_int2(u.x, code);
-            }
-        }
-    }
-    float *row = rows + (size_t)j * a.Tp + t0;
-    float *row_hr = TAPE ? a.rows_hr + ((size_t)m * npad + j) * a.Tp + t0 : nullptr;
-    const float *lrow[2] = {rows + (size_t)max(lsrc[0], 0) * a.Tp + t0, rows + (size_t)max(lsrc[1], 0) * a.Tp + t0};
-    float nxt[3][8];                                                     // next block: own row, slot 1, slot 2
-    bool have[2] = {false, false};                                       // streamed slot: its next block is already in nxt
-    int known[2] = {0, 0};                                               // streamed slot: last block counter seen (polled only when it falls short)
-    // Start-up of a thread: its whole-series tributaries are done, their first lines are asked from DRAM and block 0 of
-    // the cell's own row and of the register slots is loaded.  Tried without blocking every 16 ticks ahead of the thread's
-    // first tick, so that the loaded-DRAM latency of a start-up is paid off the tick path whenever the tributaries are
-    // early (the usual case); blocking at the first tick otherwise.
-    bool started = !active;
-    const bool prof = a.dbg_prof != nullptr;
-    long long t_wait = 0, t_swait = 0;
-    const long long t_start = prof ? clock64() : 0;
-    if (prof && tid == 0) { a.dbg_prof[8 * (size_t)(task - (tp.nchain - tp.nded)) + 2] = 0ull; a.dbg_prof[8 * (size_t)(task - (tp.nchain - tp.nded)) + 4] = 0ull; }
-    __syncthreads();
-    auto start_up = [&](bool blocking) {
-        for (int e = 0; e < nup; e++) {
-            const int2 u = sh.ent[tid][e];
-            if (u.y < 0) {
-                const int *flag = done + ((u.y & 0x7fffffff) >> 3);
-                if (blocking) {
-                    const long long tw = prof ? clock64() : 0;
-                    while (ld_acquire(flag) < epoch) __nanosleep(64);
-                    if (prof) t_wait += clock64() - tw;
-                } else if (ld_acquire(flag) < epoch) return;
-            }
-        }
-        ld8(row, nxt[0]);
-#pragma unroll
-        for (int k = 0; k < 2; k++)
-            if (lsrc[k] >= 0 && lprog[k] < 0) {
-                ld8(lrow[k], nxt[1 + k]);
-                prefetch_l2(lrow[k] + 32); prefetch_l2(lrow[k] + 64);
-            }
-        prefetch_l2(row + 32); prefetch_l2(row + 64);
-        for (int e = 0; e < nup; e++) {
-            const int2 u = sh.ent[tid][e];
-            if ((u.y & 7) == 3) { const float *p = rows + (size_t)u.x * a.Tp + t0; prefetch_l2(p); prefetch_l2(p + 32); prefetch_l2(p + 64); }
-        }
-        started = true;
-    };
-    const int nticks = nb + L - 1;
-#pragma unroll 1
-    for (int tau = 0; tau < nticks; tau++) {
-        const int b = tau - tid;
-        if (!started && b < 0 && (tau & 15) == 0) start_up(false);
-        if (active && b >= 0 && b < nb) {
-            if (b == 0) {
-                if (!started) start_up(true);
-#pragma unroll
-                for (int k = 0; k < 2; k++)
-                    if (lsrc[k] >= 0 && lprog[k] >= 0) {                 // first block of a streamed inflow
-                        wave_wait_block(prog + lprog[k], pbase + 1, prof, t_swait);
-                        known[k] = pbase + 1;
-                        ld8(lrow[k], nxt[1 + k]);
-                    }
-            }
-            float cur[3][8];
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-#pragma unroll
-                for (int s = 0; s < 8; s++) cur[k][s] = nxt[k][s];
-#pragma unroll
-            for (int k = 0; k < 2; k++)                                  // a streamed block that was not ready one tick ago
-                if (b > 0 && lprog[k] >= 0 && !have[k]) {
-                    wave_wait_block(prog + lprog[k], pbase + b + 1, prof, t_swait);
-                    known[k] = pbase + b + 1;
-                    ld8(lrow[k] + 8 * b, cur[1 + k]);
-                }
-            if (b + 1 < nb) {                                            // block b + 1 travels while block b is routed
-                ld8(row + 8 * (b + 1), nxt[0]);
-#pragma unroll
-                for (int k = 0; k < 2; k++)
-                    if (lsrc[k] >= 0) {
-                        if (lprog[k] >= 0 && known[k] < pbase + b + 2) known[k] = ld_acquire(prog + lprog[k]);
-                        have[k] = lprog[k] < 0 || known[k] >= pbase + b + 2;
-                        if (have[k]) ld8(lrow[k] + 8 * (b + 1), nxt[1 + k]);
-                    }
-                if ((b & 3) == 3 && 8 * (b + 1) + 64 < a.W) {            // every fourth block: the 128-byte lines two lines ahead
-                    prefetch_l2(row + 8 * (b + 1) + 64);
-                    if (lsrc[0] >= 0 && lprog[0] < 0) prefetch_l2(lrow[0] + 8 * (b + 1) + 64);
-                    if (lsrc[1] >= 0 && lprog[1] < 0) prefetch_l2(lrow[1] + 8 * (b + 1) + 64);
-                    for (int e = 0; e < nup; e++) {
-                        const int2 u = sh.ent[tid][e];
-                        if ((u.y & 7) == 3) prefetch_l2(rows + (size_t)u.x * a.Tp + t0 + 8 * (b + 1) + 64);
-                    }
-                }
-            }
-            float q[8];
-            if (meta & 1) {
-                float x[8];
-#pragma unroll
-                for (int s = 0; s < 8; s++) x[s] = 0.0f;
-#pragma unroll 1
-                for (int e = 0; e < nup; e++) {                         // md_routing_operator.f90:37-53, same order
-                    const int2 u = sh.ent[tid][e];
-                    const int kind = u.y & 3;
-                    if (kind == 0) {
-                        const float4 lo = *reinterpret_cast<const float4 *>(&sh.hand[(tau - 1) & 1][tid - 1][0]);
-                        const float4 hi = *reinterpret_cast<const float4 *>(&sh.hand[(tau - 1) & 1][tid - 1][4]);
-                        x[0] += lo.x; x[1] += lo.y; x[2] += lo.z; x[3] += lo.w; x[4] += hi.x; x[5] += hi.y; x[6] += hi.z; x[7] += hi.w;
-                    } else if (kind == 1) {
-#pragma unroll
-                        for (int s = 0; s < 8; s++) x[s] = x[s] + cur[1][s];
-                    } else if (kind == 2) {
-#pragma unroll
-                        for (int s = 0; s < 8; s++) x[s] = x[s] + cur[2][s];
-                    } else {
-                        float v[8];
-                        if (u.y & 4) wave_wait_block(prog + ((u.y & 0x7fffffff) >> 3), pbase + b + 1, prof, t_swait);
-                        ld8(rows + (size_t)u.x * a.Tp + t0 + 8 * b, v);
-#pragma unroll
-                        for (int s = 0; s < 8; s++) x[s] = x[s] + v[s];
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < 8; s++) {
-                    const float hr = h + x[s] * s_q;                     // md_routing_operator.f90:55-56, :73
-                    const float hn = hr * E;                             // :75
-                    q[s] = fmaf(hr - hn, fa1, cur[0][s]) * c0;           // :77, md_forward_structure.f90:155
-                    x[s] = hr;
-                    if (t0 + 8 * b + s <= tcap) h = hn;                  // steps beyond T only pad the row
-                }
-                st8(row + 8 * b, q);
-                if (TAPE) st8(row_hr + 8 * b, x);
-                if (b == nb - 1) {
-                    a.hcar[(size_t)m * npad + j] = h;
-                    if (w == a.nwin - 1) a.fstates[((size_t)m * 3 + 2) * npad + j] = h;
-                }
-                if (meta & 2)
-                    for (int g = tp.gauge_first[j]; g >= 0; g = tp.gauge_next[g])
-#pragma unroll
-                        for (int s = 0; s < 8; s++)
-                            if (t0 + 8 * b + s < a.T) qsim[(size_t)(t0 + 8 * b + s) * tp.ng + g] = q[s];   // :206-210
-            } else {
-#pragma unroll
-                for (int s = 0; s < 8; s++) q[s] = cur[0][s];            // source cell at the chain head: already final
-            }
-            *reinterpret_cast<float4 *>(&sh.hand[tau & 1][tid][0]) = make_float4(q[0], q[1], q[2], q[3]);
-            *reinterpret_cast<float4 *>(&sh.hand[tau & 1][tid][4]) = make_float4(q[4], q[5], q[6], q[7]);
-            // this thread wrote the blocks: its release orders them.  Every fourth block only: a release waits for the
-            // thread's outstanding stores, which the whole CTA would feel at the tick barrier
-            if (tid == L - 1 && ((b & 3) == 3 || b == nb - 1)) st_release(prog + task, pbase + b + 1);
-        }
-        __syncthreads();
-    }
-    if (tid == 0) { st_release(done + task, epoch); notify_consumer(a, task); }   // every thread's row stores precede the last barrier
-    if (prof) {
-        unsigned long long *o = a.dbg_prof + 8 * (size_t)(task - (tp.nchain - tp.nded));
-        if (t_wait) atomicAdd(o + 2, (unsigned long long)t_wait);
-        if (t_swait) atomicAdd(o + 4, (unsigned long long)t_swait);
-        if (tid == 0) {
-            unsigned long long gt;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-            o[0] = (unsigned long long)L; o[1] = (unsigned long long)(clock64() - t_start); o[3] = gt; o[5] = (unsigned long long)nticks;
-        }
-    }
-}
-
 // Export of a tile of 32 consecutive cells to the domain layout qdom[t][cell], done by a routing warp once the chains that
 // own the tile's cells have finished this window (fuse_export): the transposition runs in the shadow of the serial walks
 // down the main rivers instead of in a kernel of its own.  Source cells were written by the reservoir pass already.
@@ -1174,7 +947,6 @@ __global__ void __launch_bounds__(128, 3) route_forward_kernel(const SplitArgs a
     union Shared {
         RowStage<S> warp_stage[4];
         ChainShared<S / 4> cta;
-        WaveShared wave;
     };
     __shared__ __align__(16) Shared sh;
     const SplitTopo &tp = a.tp;
@@ -1182,11 +954,7 @@ __global__ void __launch_bounds__(128, 3) route_forward_kernel(const SplitArgs a
     if ((int)blockIdx.x < ded_blocks) {
         const int t_first = w * a.W + threadIdx.x * (S / 4);
         const int task = tp.nchain - tp.nded + blockIdx.x;
-        const bool wave = a.river_wave && tp.task_begin[task + 1] - tp.task_begin[task] <= WAVE_CAP;
-        for (int m = 0; m < a.nmember; m++) {
-            if (wave) route_chain_wave<TAPE>(a, sh.wave, m, task, w, epoch);
-            else route_chain_cta<S / 4, TAPE>(a, sh.cta, m, task, w, t_first, epoch);
-        }
+        for (int m = 0; m < a.nmember; m++) route_chain_cta<S / 4, TAPE>(a, sh.cta, m, task, w, t_first, epoch);
         return;
     }
     const int lane = threadIdx.x & 31;
@@ -1813,12 +1581,6 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
     int blocks = 0;
     cudaError_t e = tape ? persistent_grid(route_forward_kernel<S, 1>, &blocks) : persistent_grid(route_forward_kernel<S, 0>, &blocks);
     if (e != cudaSuccess) return e;
-    if (a.route_ctas_per_sm > 0) {
-        int dev = 0, sms = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        blocks = std::min(blocks, sms * a.route_ctas_per_sm);
-    }
     const int ded_blocks = a.tp.nded;                      // one CTA per dedicated chain (route_graph.cpp keeps nded small)
     const long long total = (long long)(a.tp.nchain - a.tp.nded) * a.nmember;
     const long long need = (total + 3) / 4 + ded_blocks;

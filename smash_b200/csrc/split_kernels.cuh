@@ -57,9 +57,7 @@ struct SplitArgs {
     int nmember;
     float dt, dx;
     int save_q, save_netp;
-    int route_ctas_per_sm;       // 0: as many routing CTAs per SM as fit (3); 1 / 2: fewer ticket warps, less DRAM pressure on the river walks
     int fuse_export;             // 1: the routing warps also write the routed cells' series to qdom ([t][cell]) once their chains are done
-    int river_wave;              // 1: dedicated chains run the tick wavefront (thread = cells), 0: whole-window scan per cell
     unsigned long long *dbg_prof;  // diagnostics: per dedicated chain [cells, cycles, cycles waiting for tributaries, end time ns], or nullptr
     const float *fields;         // [m][NFIELD][npad]
     float *fstates;              // [m][3][npad]

@@ -43,36 +43,6 @@ def test_split_and_fused_engines_agree():
     check_grad(sa, sb, ("hp", "hft", "hlr"))
 
 
-def test_river_reaches_wavefront_agrees():
-    # option river_wave = 1: the longest chains are cut into reaches of <= 128 cells that run as pipelined tick wavefronts
-    # (strictly sequential arithmetic) instead of a window scan per cell; same discharge, cost and gradient.  The 600 x 600
-    # window holds chains of more than 128 cells, so reaches stream into each other.
-    def run(wave):
-        lib = L.lib()
-        lib.smash_b200_set_option(b"river_wave", wave)
-        lib.smash_b200_clear_cache()
-        try:
-            m = cases.france(T=96, sub=(300, 900, 300, 900), ngauge=4)
-            random_fields(m, seed=5)
-            pb, sb = ParametersDT(m.mesh), StatesDT(m.mesh)
-            smash_b200.forward_b(m.setup, m.mesh, m.input_data, m.parameters, pb, m.parameters.copy(), None, m.states, sb,
-                                 m.states.copy(), None, m.output, None)
-            return m, pb, sb
-        finally:
-            lib.smash_b200_set_option(b"river_wave", 0)
-            lib.smash_b200_clear_cache()
-    a, pa, sa = run(1)
-    b, pb, sb = run(0)
-    qa, qb = np.asarray(a.output.qsim, np.float64), np.asarray(b.output.qsim, np.float64)
-    assert np.all(np.abs(qa - qb) <= 1e-6 + 1e-4 * np.abs(qb)), float(np.abs(qa - qb).max())
-    da = np.asarray(a.output.sparse_qsim_domain, np.float64)
-    db = np.asarray(b.output.sparse_qsim_domain, np.float64)
-    assert np.all(np.abs(da - db) <= 1e-6 + 1e-4 * np.abs(db)), float(np.abs(da - db).max())
-    assert np.isclose(float(a.output.cost), float(b.output.cost), rtol=1e-4)
-    check_grad(pa, pb, ("cp", "cft", "exc", "lr"))
-    check_grad(sa, sb, ("hp", "hft", "hlr"))
-
-
 def test_streamed_forward_agrees():
     # large host-resident sparse forcing: the ABI forward streams 256-step windows (upload, kernels, download overlapped).
     # Same run with streaming off (one 640-step window): discharge, domain series, final states and cost must agree to the
