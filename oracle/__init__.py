@@ -27,7 +27,8 @@ GNP, GNS = 16, 8
 PARAM_NAMES = ("ci", "cp", "beta", "cft", "cst", "alpha", "exc", "b", "cusl1", "cusl2", "clsl", "ks", "ds", "dsm",
                "ws", "lr")
 STATE_NAMES = ("hi", "hp", "hft", "hst", "husl1", "husl2", "hlsl", "hlr")
-JOBS_FUN = {"nse": 1, "kge": 2, "kge2": 3, "se": 4, "rmse": 5, "logarithmic": 6}
+JOBS_FUN = {"nse": 1, "kge": 2, "kge2": 3, "se": 4, "rmse": 5, "logarithmic": 6, "Crc": 7, "Cfp2": 8, "Cfp10": 9, "Cfp50": 10,
+            "Cfp90": 11, "Erc": 12, "Elt": 13, "Epf": 14}
 JREG_FUN = {"prior": 1, "smoothing": 2, "hard_smoothing": 3}
 MAPPING = {"hyper-linear": 1, "hyper-polynomial": 2}
 
@@ -73,6 +74,7 @@ def _make_struct(real):
             ("denormalize_forward", C.c_int), ("optimize_start_step", C.c_int), ("mapping", C.c_int), ("nhyper", C.c_int),
             ("optim_parameters", ip), ("optim_states", ip),
             ("lb_parameters", rp), ("ub_parameters", rp), ("lb_states", rp), ("ub_states", rp), ("wgauge", rp),
+            ("mean_prcp", rp), ("mask_event", ip),
         ]
 
     return OProblem
@@ -145,6 +147,9 @@ def _problem(ctx: _Ctx, setup, mesh, input_data):
     P.optim_parameters, P.optim_states = ctx.i(o.optim_parameters), ctx.i(o.optim_states)
     P.lb_parameters, P.ub_parameters = ctx.r(o.lb_parameters), ctx.r(o.ub_parameters)
     P.lb_states, P.ub_states = ctx.r(o.lb_states), ctx.r(o.ub_states)
+    if any(JOBS_FUN[x] >= 7 for x in jf) and mesh.ng > 0:                   # signature objectives (mwd_cost.f90:117-122)
+        P.mean_prcp = ctx.r(input_data.mean_prcp)
+        P.mask_event = ctx.i(o.mask_event)
     return P
 
 

@@ -27,6 +27,7 @@
 #define EXP exp
 #define SQRT sqrt
 #define LOG log
+#define FABS fabs
 #else
 #define R(x) x##f
 #define POW powf
@@ -34,6 +35,7 @@
 #define EXP expf
 #define SQRT sqrtf
 #define LOG logf
+#define FABS fabsf
 #endif
 
 typedef OSYM(OProblem) Prob;
@@ -616,6 +618,73 @@ static oreal quantile_half(const oreal *dat, int n, int *lo, int *hi, oreal *fra
     return res;
 }
 
+
+/* quantile (mwd_cost.f90:675-720) of dat(1:n): heap_sort (:594-673) is replaced by qsort (same sorted result) */
+static oreal quantile_p(const oreal *dat, int n, oreal p) {
+    oreal res;
+    if (n <= 0) return 0;
+    if (n == 1) return dat[0];
+    oreal *s = (oreal *)malloc(n * sizeof(oreal));
+    memcpy(s, dat, n * sizeof(oreal));
+    qsort(s, n, sizeof(oreal), cmp_oreal);
+    oreal frac = (n - 1) * p + 1;
+    if (frac <= 1) res = s[0];
+    else if (frac >= n) res = s[n - 1];
+    else { oreal q1 = s[(int)frac - 1], q2 = s[(int)frac]; res = q1 + (q2 - q1) * (frac - (int)frac); }
+    free(s);
+    return res;
+}
+/* flow_percentile (mwd_cost.f90:722-768): quantiles over the steps where both series are non-negative */
+static void flow_percentile(const oreal *qo, const oreal *qs, int n, oreal p, oreal *num, oreal *den) {
+    oreal *a = (oreal *)malloc((size_t)(n > 0 ? n : 1) * 2 * sizeof(oreal)), *b = a + n;
+    int j = 0;
+    for (int i = 0; i < n; i++) if (qo[i] >= 0 && qs[i] >= 0) { a[j] = qo[i]; b[j] = qs[i]; j++; }
+    *num = quantile_p(b, j, p);
+    *den = quantile_p(a, j, p);
+    free(a);
+}
+/* signature (mwd_cost.f90:770-970): |s(qs) / s(qo) - 1| for one signature; event-based ones are averaged over the events
+ * of mask_event.  num / den keep their previous values when a case does not set them, as in the Fortran function where
+ * they are uninitialised locals: they start at 0 here (den = 0 adds nothing). */
+static oreal signature(const oreal *po, const oreal *qo, const oreal *qs, const int *mask, int mstride, int n, int stype) {
+    oreal res = 0, num = 0, den = 0;
+    if (stype == OJ_ERC || stype == OJ_ELT || stype == OJ_EPF) {
+        int n_event = 0;
+        for (int i = n - 1; i >= 0; i--) if (mask[(size_t)i * mstride] > 0) { n_event = mask[(size_t)i * mstride]; break; }
+        for (int ev = 1; ev <= n_event; ev++) {
+            int start = -1, cnt = 0;
+            for (int j = 0; j < n; j++) if (mask[(size_t)j * mstride] == ev) { if (start < 0) start = j; cnt++; }
+            if (start < 0) start = 0;          /* Fortran: start_event keeps its previous value; an event number always occurs */
+            oreal sum_qo = 0, sum_qs = 0, sum_po = 0, max_qo = 0, max_qs = 0, max_po = 0;
+            int imax_qo = 0, imax_qs = 0, imax_po = 0;
+            for (int j = start; j < start + cnt && j < n; j++) {
+                if (qo[j] >= 0 && po[j] >= 0) {
+                    sum_qo += qo[j]; sum_qs += qs[j]; sum_po += po[j];
+                    if (qo[j] > max_qo) { max_qo = qo[j]; imax_qo = j + 1; }
+                    if (qs[j] > max_qs) { max_qs = qs[j]; imax_qs = j + 1; }
+                    if (po[j] > max_po) { max_po = po[j]; imax_po = j + 1; }
+                }
+            }
+            if (stype == OJ_EPF) { num = max_qs; den = max_qo; }
+            else if (stype == OJ_ELT) { num = (oreal)(imax_qs - imax_po); den = (oreal)(imax_qo - imax_po); }
+            else if (sum_po > 0) { num = sum_qs / sum_po; den = sum_qo / sum_po; }
+            if (den > 0) res = res + FABS(num / den - 1);
+        }
+        if (n_event > 0) res = res / n_event;
+    } else {
+        if (stype == OJ_CRC) {
+            oreal sum_qo = 0, sum_qs = 0, sum_po = 0;
+            for (int i = 0; i < n; i++) if (qo[i] >= 0 && po[i] >= 0) { sum_qo += qo[i]; sum_qs += qs[i]; sum_po += po[i]; }
+            if (sum_po > 0) { num = sum_qs / sum_po; den = sum_qo / sum_po; }
+        } else {
+            const oreal p = stype == OJ_CFP2 ? R(0.02) : stype == OJ_CFP10 ? R(0.1) : stype == OJ_CFP50 ? R(0.5) : R(0.9);
+            flow_percentile(qo, qs, n, p, &num, &den);
+        }
+        if (den > 0) res = FABS(num / den - 1);
+    }
+    return res;
+}
+
 /* compute_jobs (mwd_cost.f90:37-156) and COMPUTE_JOBS_B (forward_db.f90:2553-2715).
  * If qsim_b != NULL the adjoint seed jobs_b is propagated into qsim_b (which is first zeroed, :2660). */
 static oreal compute_jobs(const Prob *P, const oreal *qsim, oreal *qsim_b, oreal jobs_b) {
@@ -623,8 +692,8 @@ static oreal compute_jobs(const Prob *P, const oreal *qsim, oreal *qsim_b, oreal
     const int n = P->ntime_step - s0;
     const int ng = P->ng;
     oreal jobs = 0;
-    oreal *qo = (oreal *)malloc((size_t)(n > 0 ? n : 1) * sizeof(oreal) * 3);
-    oreal *qs = qo + n, *qs_b = qs + n;
+    oreal *qo = (oreal *)malloc((size_t)(n > 0 ? n : 1) * sizeof(oreal) * 4);
+    oreal *qs = qo + n, *qs_b = qs + n, *po = qs_b + n;
     oreal *arr = (oreal *)calloc(ng > 0 ? ng : 1, sizeof(oreal));
     oreal *gjobs_b = (oreal *)calloc(ng > 0 ? ng : 1, sizeof(oreal));
     int *arr_g = (int *)malloc((ng > 0 ? ng : 1) * sizeof(int));
@@ -650,7 +719,12 @@ static oreal compute_jobs(const Prob *P, const oreal *qsim, oreal *qsim_b, oreal
                         case OJ_SE: j_imd = se(qo, qs, n); break;
                         case OJ_RMSE: j_imd = rmse(qo, qs, n); break;
                         case OJ_LOGARITHMIC: j_imd = logarithmic(qo, qs, n); break;
-                        default: break;
+                        default:
+                            if (P->jobs_fun[j] >= OJ_CRC && P->jobs_fun[j] <= OJ_EPF && P->mean_prcp && P->mask_event) {
+                                for (int i = 0; i < n; i++) po[i] = P->mean_prcp[g + (size_t)ng * (s0 + i)];
+                                j_imd = signature(po, qo, qs, P->mask_event + g + (size_t)ng * s0, ng, n, P->jobs_fun[j]);
+                            }
+                            break;
                     }
                 }
                 gauge_jobs = gauge_jobs + P->wjobs_fun[j] * j_imd;

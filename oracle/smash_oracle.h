@@ -46,7 +46,9 @@ enum { OP_CI = 0, OP_CP, OP_BETA, OP_CFT, OP_CST, OP_ALPHA, OP_EXC, OP_B, OP_CUS
 enum { OS_HI = 0, OS_HP, OS_HFT, OS_HST, OS_HUSL1, OS_HUSL2, OS_HLSL, OS_HLR };
 
 /* jobs_fun codes (mwd_cost.f90:98-131) */
-enum { OJ_NSE = 1, OJ_KGE = 2, OJ_KGE2 = 3, OJ_SE = 4, OJ_RMSE = 5, OJ_LOGARITHMIC = 6 };
+enum { OJ_NSE = 1, OJ_KGE = 2, OJ_KGE2 = 3, OJ_SE = 4, OJ_RMSE = 5, OJ_LOGARITHMIC = 6,
+       /* signatures (mwd_cost.f90:117-122, 772-970): continuous Crc, Cfp2/10/50/90; event-based Erc, Elt, Epf */
+       OJ_CRC = 7, OJ_CFP2 = 8, OJ_CFP10 = 9, OJ_CFP50 = 10, OJ_CFP90 = 11, OJ_ERC = 12, OJ_ELT = 13, OJ_EPF = 14 };
 /* jreg_fun codes (mwd_cost.f90:200-240) */
 enum { OR_PRIOR = 1, OR_SMOOTHING = 2, OR_HARD_SMOOTHING = 3 };
 /* mapping codes (mwd_parameters_manipulation.f90:330-342) */
@@ -79,6 +81,9 @@ typedef struct {
     const oreal *lb_parameters, *ub_parameters; /* (16) */
     const oreal *lb_states, *ub_states;         /* (8) */
     const oreal *wgauge;                        /* (ng) */
+    /* signature objectives only (may be NULL otherwise) */
+    const oreal *mean_prcp;                     /* Input_DataDT%mean_prcp (ng,T) */
+    const int *mask_event;                      /* Optimize_SetupDT%mask_event (ng,T): event number of every step, 0 = none */
 } OSYM(OProblem);
 
 #ifdef __cplusplus
