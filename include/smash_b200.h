@@ -38,7 +38,10 @@ enum { SMASH_STRUCTURE_GR_A = 1, SMASH_STRUCTURE_GR_B = 2, SMASH_STRUCTURE_GR_C 
        SMASH_STRUCTURE_VIC_A = 5 };
 /* setup%optimize%jobs_fun(:) (optimize/mwd_cost.f90:98-131) */
 enum { SMASH_JOBS_NSE = 1, SMASH_JOBS_KGE = 2, SMASH_JOBS_KGE2 = 3, SMASH_JOBS_SE = 4, SMASH_JOBS_RMSE = 5,
-       SMASH_JOBS_LOGARITHMIC = 6 };
+       SMASH_JOBS_LOGARITHMIC = 6,
+       /* signature-based objectives (optimize/mwd_cost.f90:117-122, 770-970); forward only: forward_b rejects them */
+       SMASH_JOBS_CRC = 7, SMASH_JOBS_CFP2 = 8, SMASH_JOBS_CFP10 = 9, SMASH_JOBS_CFP50 = 10, SMASH_JOBS_CFP90 = 11,
+       SMASH_JOBS_ERC = 12, SMASH_JOBS_ELT = 13, SMASH_JOBS_EPF = 14 };
 /* setup%optimize%jreg_fun(:) (optimize/mwd_cost.f90:200-240) */
 enum { SMASH_JREG_PRIOR = 1, SMASH_JREG_SMOOTHING = 2, SMASH_JREG_HARD_SMOOTHING = 3 };
 /* setup%optimize%mapping (routine/mwd_parameters_manipulation.f90:330-342) */
@@ -73,6 +76,7 @@ typedef struct SmashSetup {
     float lb_parameters[SMASH_B200_GNP], ub_parameters[SMASH_B200_GNP];
     float lb_states[SMASH_B200_GNS], ub_states[SMASH_B200_GNS];
     const float *wgauge; /* (ng) */
+    const int32_t *mask_event; /* (ng,T) setup%optimize%mask_event: event number of every step, 0 = none; signature objectives only */
 } SmashSetup;
 
 /* MeshDT (derived_type/mwd_mesh.f90:45-72) */
@@ -97,6 +101,8 @@ typedef struct SmashInputData {
      * calls).  Non-zero = caller's promise that (pointer, version) identifies immutable content,
      * so the device-resident [block][tick][cell] copy is reused. */
     uint64_t forcing_version;
+    const float *mean_prcp;               /* (ng,T) catchment-mean precipitation (routine/mw_forcing_statistic.f90:18-75); signature
+                                           * objectives only */
 } SmashInputData;
 
 /* ParametersDT / StatesDT (derived_type/mwd_parameters.f90:58-78, mwd_states.f90:49-60): one

@@ -18,7 +18,8 @@ c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int32)
 
 STRUCTURES = {"gr-a": 1, "gr-b": 2, "gr-c": 3, "gr-d": 4, "vic-a": 5}
-JOBS_FUN = {"nse": 1, "kge": 2, "kge2": 3, "se": 4, "rmse": 5, "logarithmic": 6}
+JOBS_FUN = {"nse": 1, "kge": 2, "kge2": 3, "se": 4, "rmse": 5, "logarithmic": 6, "Crc": 7, "Cfp2": 8, "Cfp10": 9, "Cfp50": 10,
+            "Cfp90": 11, "Erc": 12, "Elt": 13, "Epf": 14}
 JREG_FUN = {"prior": 1, "smoothing": 2, "hard_smoothing": 3}
 MAPPING = {"hyper-linear": 1, "hyper-polynomial": 2}
 
@@ -34,7 +35,7 @@ class SmashSetup(C.Structure):
         ("optim_parameters", C.c_int32 * GNP), ("optim_states", C.c_int32 * GNS),
         ("lb_parameters", C.c_float * GNP), ("ub_parameters", C.c_float * GNP),
         ("lb_states", C.c_float * GNS), ("ub_states", C.c_float * GNS),
-        ("wgauge", c_float_p),
+        ("wgauge", c_float_p), ("mask_event", c_int_p),
     ]
 
 
@@ -49,7 +50,7 @@ class SmashMesh(C.Structure):
 class SmashInputData(C.Structure):
     _fields_ = [
         ("qobs", c_float_p), ("prcp", c_float_p), ("pet", c_float_p), ("sparse_prcp", c_float_p),
-        ("sparse_pet", c_float_p), ("descriptor", c_float_p), ("forcing_version", C.c_uint64),
+        ("sparse_pet", c_float_p), ("descriptor", c_float_p), ("forcing_version", C.c_uint64), ("mean_prcp", c_float_p),
     ]
 
 
@@ -164,7 +165,7 @@ def pack_setup(setup, mesh, pk: Packed) -> SmashSetup:
     jf = [str(x).strip() for x in np.atleast_1d(o.jobs_fun)][: int(o.njf)]
     for name in jf:
         if name not in JOBS_FUN:
-            raise RuntimeError(f"jobs_fun {name!r}: signature-based objectives are not implemented by smash_b200")
+            raise RuntimeError(f"jobs_fun {name!r} is not implemented by smash_b200")
     jfc = _i32(np.array([JOBS_FUN[x] for x in jf], dtype=np.int32), pk.keep)
     wjf = _f32(np.atleast_1d(o.wjobs_fun)[: len(jf)], pk.keep)
     s.njf, s.jobs_fun, s.wjobs_fun = len(jf), _ip(jfc), _fp(wjf)
@@ -180,6 +181,8 @@ def pack_setup(setup, mesh, pk: Packed) -> SmashSetup:
     s.denormalize_forward = int(bool(o.denormalize_forward))
     s.nhyper = int(o.nhyper)
     s.optimize_start_step = int(o.optimize_start_step)
+    if any(JOBS_FUN[x] >= 7 for x in jf) and mesh.ng > 0:                   # signature objectives read the event mask
+        s.mask_event = _ip(_i32(o.mask_event, pk.keep))
     s.optim_parameters[:] = [int(x) for x in o.optim_parameters]
     s.optim_states[:] = [int(x) for x in o.optim_states]
     s.lb_parameters[:] = [float(x) for x in o.lb_parameters]
@@ -241,6 +244,8 @@ def pack_input(input_data, setup, mesh, pk: Packed) -> SmashInputData:
     if setup._nd > 0 and getattr(input_data, "descriptor", None) is not None:
         i.descriptor = _fp(_f32(input_data.descriptor, pk.keep))
     i.forcing_version = int(getattr(input_data, "_forcing_version", 0))
+    if mesh.ng > 0 and getattr(input_data, "mean_prcp", None) is not None:
+        i.mean_prcp = _fp(_f32(input_data.mean_prcp, pk.keep))
     return i
 
 

@@ -188,7 +188,8 @@ struct SmashPlan {
     // data
     DBuf<float> d_forcing, d_raw_prcp, d_raw_pet, d_planes, d_fields, d_fstates, d_qsim, d_qdom, d_netp, d_tape, d_qsim_b,
         d_wdom, d_grad, d_cost_jobs, d_qobs, d_area, d_wgauge, d_sample, d_out;
-    DBuf<int32_t> d_gauge_flwacc, d_sample_field;
+    DBuf<int32_t> d_gauge_flwacc, d_sample_field, d_mask_event;
+    DBuf<float> d_mean_prcp, d_sig_scratch;
     DBuf<int> d_prog, d_rprog;
     DBuf<unsigned int> d_ticket;
     DBuf<double> d_sum;
@@ -817,7 +818,8 @@ static int plan_set_fields(SmashPlan &pl, const SmashParameters *par, const Smas
 }
 
 // ---- cost ---------------------------------------------------------------------------------------
-static int make_cost_args(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, float jobs_b, bool adjoint, CostArgs &c) {
+static int make_cost_args(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, float jobs_b, bool adjoint, CostArgs &c,
+                          const SmashInputData *in = nullptr) {
     c = CostArgs{};
     c.T = pl.tp.T; c.ng = mesh->ng; c.nmember = pl.nmember; c.start = setup->optimize_start_step - 1;
     if (c.start < 0 || c.start >= c.T) return fail(SMASH_B200_EINVAL, "optimize_start_step %d out of range", setup->optimize_start_step);
@@ -827,14 +829,28 @@ static int make_cost_args(SmashPlan &pl, const SmashSetup *setup, const SmashMes
     if (c.njf > 8) return fail(SMASH_B200_EUNSUPPORTED, "more than 8 objective functions");
     for (int j = 0; j < c.njf; j++) {
         c.jobs_fun[j] = setup->jobs_fun[j]; c.wjobs_fun[j] = setup->wjobs_fun[j];
-        if (c.jobs_fun[j] < SMASH_JOBS_NSE || c.jobs_fun[j] > SMASH_JOBS_LOGARITHMIC)
-            return fail(SMASH_B200_EUNSUPPORTED, "jobs_fun code %d (signature-based objectives are host-side, not implemented)", c.jobs_fun[j]);
+        if (c.jobs_fun[j] < SMASH_JOBS_NSE || c.jobs_fun[j] > SMASH_JOBS_EPF)
+            return fail(SMASH_B200_EUNSUPPORTED, "jobs_fun code %d is not implemented", c.jobs_fun[j]);
+        if (c.jobs_fun[j] >= SMASH_JOBS_CRC) {
+            // signature objectives (mwd_cost.f90:770-970): catchment-mean precipitation and the event mask on the device
+            if (adjoint) return fail(SMASH_B200_EUNSUPPORTED, "forward_b with a signature-based objective (jobs_fun code %d)", c.jobs_fun[j]);
+            if (!in || !in->mean_prcp || !setup->mask_event)
+                return fail(SMASH_B200_EINVAL, "signature-based objective: input_data.mean_prcp / setup.optimize.mask_event missing");
+            if (!c.mean_prcp) {
+                const size_t nq = (size_t)mesh->ng * c.T;
+                TRY(pl.d_mean_prcp.ensure(nq)); TRY(pl.d_mask_event.ensure(nq)); TRY(pl.d_sig_scratch.ensure((size_t)pl.nmember * 2 * nq));
+                CU(cudaMemcpyAsync(pl.d_mean_prcp.p, in->mean_prcp, nq * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+                CU(cudaMemcpyAsync(pl.d_mask_event.p, setup->mask_event, nq * sizeof(int32_t), cudaMemcpyHostToDevice, pl.stream));
+                c.mean_prcp = pl.d_mean_prcp.p; c.mask_event = pl.d_mask_event.p; c.scratch = pl.d_sig_scratch.p;
+            }
+        }
     }
     c.jobs_b = jobs_b; c.cost_jobs = pl.d_cost_jobs.p; c.qsim_b = adjoint ? pl.d_qsim_b.p : nullptr;
     return 0;
 }
 
-static int run_cost(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, float jobs_b, bool adjoint) {
+static int run_cost(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, float jobs_b, bool adjoint,
+                    const SmashInputData *in = nullptr) {
     if (mesh->ng <= 0) {
         CU(cudaMemsetAsync(pl.d_cost_jobs.p, 0, sizeof(float) * pl.nmember, pl.stream));
         return 0;
@@ -844,7 +860,7 @@ static int run_cost(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mes
     std::vector<float> wg(setup->wgauge, setup->wgauge + mesh->ng);
     TRY(pl.d_wgauge.upload(wg, pl.stream));
     CostArgs c;
-    TRY(make_cost_args(pl, setup, mesh, jobs_b, adjoint, c));
+    TRY(make_cost_args(pl, setup, mesh, jobs_b, adjoint, c, in));
     CU(launch_cost(c, pl.stream));
     pl.launches++;
     return 0;
@@ -1148,7 +1164,7 @@ static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const 
         if (!fields_ready) TRY(plan_set_fields(*pl, par, st, nullptr, nullptr, 0, 1));
         TRY(run_forward_engine(*pl, save_q, save_n, false));
     }
-    TRY(run_cost(*pl, setup, mesh, 0.0f, false));
+    TRY(run_cost(*pl, setup, mesh, 0.0f, false, in));
     std::vector<float> fs((size_t)3 * pl->ncols);
     float jobs = 0.0f;
     TRY(download(*pl, fs.data(), pl->d_fstates.p, fs.size() * sizeof(float)));
@@ -1406,7 +1422,7 @@ extern "C" int smash_b200_compute_multiple_run(const SmashSetup *setup, const Sm
         TRY(plan_members(*pl, nm, false, false, false));
         TRY(plan_set_fields(*pl, par, st, sample + (size_t)m0 * nvar, ind, nvar, nm));
         TRY(run_forward_engine(*pl, false, false, false));
-        TRY(run_cost(*pl, setup, mesh, 0.0f, false));
+        TRY(run_cost(*pl, setup, mesh, 0.0f, false, in));
         TRY(download(*pl, jobs.data(), pl->d_cost_jobs.p, (size_t)nm * sizeof(float)));
         if (res_qsim && nq) TRY(download(*pl, res_qsim + (size_t)m0 * nq, pl->d_qsim.p, (size_t)nm * nq * sizeof(float)));
         CU(cudaStreamSynchronize(pl->stream));

@@ -499,6 +499,103 @@ __device__ Kge kge_of(const Moments &m) {            // mwd_cost.f90:403-490
 
 // One CTA per member, one thread per gauge for the order-dependent sums.  The element-wise part (unit conversion with
 // its IEEE divisions) is done by the whole CTA into shared memory, chunk by chunk, so the sequential part is adds only.
+// ---- signature objectives (mwd_cost.f90:770-970): |s(qs) / s(qo) - 1| per gauge, one thread per gauge, straight from
+// global memory (a few thousand steps).  Forward only.
+struct SigSeries {           // qo / qs / po of one gauge from step `start` on (mwd_cost.f90:82-92)
+    const float *qsim, *qobs, *mprcp;
+    const int32_t *mask;
+    int ng, g, start;
+    float dt, area, dden;
+    __device__ float qs(int i) const { return FM(FD(FM(qsim[(size_t)(start + i) * ng + g], dt), area), 1e3f); }
+    __device__ float qo(int i) const { return FM(FD(FM(qobs[(size_t)(start + i) * ng + g], dt), dden), 1e3f); }
+    __device__ float po(int i) const { return mprcp[(size_t)(start + i) * ng + g]; }
+    __device__ int ev(int i) const { return mask[(size_t)(start + i) * ng + g]; }
+};
+__device__ void sig_heap_sort(float *a, int n) {             // heap_sort, mwd_cost.f90:594-673 (any correct sort gives the same array)
+    for (int start = n / 2 - 1; start >= 0; start--) {
+        int root = start;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= n) break;
+            if (child + 1 < n && a[child] < a[child + 1]) child++;
+            if (a[root] >= a[child]) break;
+            const float t = a[root]; a[root] = a[child]; a[child] = t;
+            root = child;
+        }
+    }
+    for (int end = n - 1; end > 0; end--) {
+        const float t0 = a[0]; a[0] = a[end]; a[end] = t0;
+        int root = 0;
+        for (;;) {
+            int child = 2 * root + 1;
+            if (child >= end) break;
+            if (child + 1 < end && a[child] < a[child + 1]) child++;
+            if (a[root] >= a[child]) break;
+            const float t = a[root]; a[root] = a[child]; a[child] = t;
+            root = child;
+        }
+    }
+}
+__device__ float sig_quantile(float *dat, int n, float p) {  // quantile, mwd_cost.f90:675-720 (sorts dat in place)
+    if (n <= 0) return 0.0f;
+    if (n == 1) return dat[0];
+    sig_heap_sort(dat, n);
+    const float frac = FA(FM((float)(n - 1), p), 1.0f);
+    if (frac <= 1.0f) return dat[0];
+    if (frac >= (float)n) return dat[n - 1];
+    const float q1 = dat[(int)frac - 1], q2 = dat[(int)frac];
+    return FA(q1, FM(FS(q2, q1), FS(frac, (float)(int)frac)));
+}
+__device__ float signature_dev(const SigSeries &S, int n, int stype, float *scratch /* 2 * n floats */) {
+    float res = 0.0f, num = 0.0f, den = 0.0f;
+    if (stype >= 12) {                                       // Erc, Elt, Epf: per event of mask_event (:799-893)
+        int n_event = 0;
+        for (int i = n - 1; i >= 0; i--) if (S.ev(i) > 0) { n_event = S.ev(i); break; }
+        for (int e = 1; e <= n_event; e++) {
+            int start = -1, cnt = 0;
+            for (int j = 0; j < n; j++) if (S.ev(j) == e) { if (start < 0) start = j; cnt++; }
+            if (start < 0) start = 0;
+            float sum_qo = 0.f, sum_qs = 0.f, sum_po = 0.f, max_qo = 0.f, max_qs = 0.f, max_po = 0.f;
+            int imax_qo = 0, imax_qs = 0, imax_po = 0;
+            for (int j = start; j < start + cnt && j < n; j++) {
+                const float qo = S.qo(j), qs = S.qs(j), po = S.po(j);
+                if (qo >= 0.0f && po >= 0.0f) {
+                    sum_qo = FA(sum_qo, qo); sum_qs = FA(sum_qs, qs); sum_po = FA(sum_po, po);
+                    if (qo > max_qo) { max_qo = qo; imax_qo = j + 1; }
+                    if (qs > max_qs) { max_qs = qs; imax_qs = j + 1; }
+                    if (po > max_po) { max_po = po; imax_po = j + 1; }
+                }
+            }
+            if (stype == 14) { num = max_qs; den = max_qo; }
+            else if (stype == 13) { num = (float)(imax_qs - imax_po); den = (float)(imax_qo - imax_po); }
+            else if (sum_po > 0.0f) { num = FD(sum_qs, sum_po); den = FD(sum_qo, sum_po); }
+            if (den > 0.0f) res = FA(res, fabsf(FS(FD(num, den), 1.0f)));
+        }
+        if (n_event > 0) res = FD(res, (float)n_event);
+    } else {
+        if (stype == 7) {                                    // Crc (:897-918)
+            float sum_qo = 0.f, sum_qs = 0.f, sum_po = 0.f;
+            for (int i = 0; i < n; i++) {
+                const float qo = S.qo(i), po = S.po(i);
+                if (qo >= 0.0f && po >= 0.0f) { sum_qo = FA(sum_qo, qo); sum_qs = FA(sum_qs, S.qs(i)); sum_po = FA(sum_po, po); }
+            }
+            if (sum_po > 0.0f) { num = FD(sum_qs, sum_po); den = FD(sum_qo, sum_po); }
+        } else if (scratch) {                                // Cfp2 / 10 / 50 / 90: flow_percentile (:722-768)
+            const float p = stype == 8 ? 0.02f : stype == 9 ? 0.1f : stype == 10 ? 0.5f : 0.9f;
+            float *a = scratch, *b = scratch + n;
+            int j = 0;
+            for (int i = 0; i < n; i++) {
+                const float qo = S.qo(i), qs = S.qs(i);
+                if (qo >= 0.0f && qs >= 0.0f) { a[j] = qo; b[j] = qs; j++; }
+            }
+            num = sig_quantile(b, j, p);
+            den = sig_quantile(a, j, p);
+        }
+        if (den > 0.0f) res = fabsf(FS(FD(num, den), 1.0f));
+    }
+    return res;
+}
+
 __global__ void cost_kernel(const CostArgs c, const int CH) {
     extern __shared__ float sh[];            // [ng] gauge_jobs, [ng] gauge_jobs_b, [ng][7] adjoint coefficients, [ng][CH] x, [ng][CH] y
     float *gj = sh, *gjb = sh + c.ng, *coef = sh + 2 * c.ng, *xs = sh + 9 * c.ng, *ys = xs + (size_t)c.ng * CH;
@@ -534,7 +631,13 @@ __global__ void cost_kernel(const CostArgs c, const int CH) {
                         case 4: j_imd = mo.se; break;
                         case 5: j_imd = sqrtf(FD(mo.se, (float)mo.n)); break;
                         case 6: j_imd = mo.lg; break;
-                        default: break;
+                        default:
+                            if (c.jobs_fun[j] >= 7 && c.jobs_fun[j] <= 14 && c.mean_prcp && c.mask_event) {
+                                const SigSeries S{qsim, c.qobs, c.mean_prcp, c.mask_event, c.ng, g, c.start, c.dt, c.area[g],
+                                                  FM(FM((float)c.gauge_flwacc[g], c.dx), c.dx)};
+                                j_imd = signature_dev(S, n, c.jobs_fun[j], c.scratch ? c.scratch + ((size_t)m * c.ng + g) * 2 * c.T : nullptr);
+                            }
+                            break;
                     }
                 }
                 gauge_jobs = FA(gauge_jobs, FM(c.wjobs_fun[j], j_imd));

@@ -62,6 +62,10 @@ struct CostArgs {
     float jobs_b;                       // adjoint seed (cost_b); qsim_b written iff qsim_b != nullptr
     float *cost_jobs;                   // [m]
     float *qsim_b;                      // [m][T][ng] or nullptr
+    // signature objectives (mwd_cost.f90:770-970), forward only
+    const float *mean_prcp;             // [T][ng] (= F(ng,T)) or nullptr
+    const int32_t *mask_event;          // [T][ng] or nullptr
+    float *scratch;                     // [m][ng][2][T] sort space of the flow percentiles, or nullptr
 };
 
 // math_mode: 0 = IEEE division / sqrt + libm tanhf ; 1 = reciprocal / rsqrt approximations

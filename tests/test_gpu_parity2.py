@@ -472,3 +472,40 @@ def test_math0_against_the_relative_gate(T):
     excess = np.abs(qa - qb) - 1e-4 * np.abs(qb)
     print("math = 0, T = %d: max(|dq| - 1e-4 |q|) = %.3e, max |dq| = %.3e" % (T, excess.max(), np.abs(qa - qb).max()))
     assert np.all(np.abs(qa - qb) <= 1e-5 + 1e-4 * np.abs(qb)), float(excess.max())
+
+
+def test_signature_objectives_against_oracle():
+    # signature-based objectives (mwd_cost.f90:770-970): continuous (Crc, flow percentiles) and event-based (Erc, Elt, Epf)
+    # with an event mask of two events, mixed with nse; the device cost kernel against the oracle, gauge by gauge
+    from smash_b200.solver._mw_forcing_statistic import compute_mean_forcing
+    names = ["nse", "Crc", "Cfp2", "Cfp10", "Cfp50", "Cfp90", "Erc", "Elt", "Epf"]
+    for k, gauge in enumerate(("downstream", "all")):
+        a, b = cases.cance(), cases.cance()
+        for m in (a, b):
+            random_fields(m, seed=51)
+            cases.set_optimize(m.setup, m.mesh, jobs_fun=tuple(names), wjobs_fun=[1, 2, 2, 2, 2, 2, 2, 2, 2], gauge=gauge)
+            me = m.setup._optimize.mask_event
+            me[:, 100:220] = 1
+            me[:, 700:900] = 2
+            compute_mean_forcing(m.setup, m.mesh, m.input_data)
+        smash_b200.forward(a.setup, a.mesh, a.input_data, a.parameters, a.parameters.copy(), a.states, a.states.copy(), a.output)
+        oracle.forward(b.setup, b.mesh, b.input_data, b.parameters, b.parameters.copy(), b.states, b.states.copy(), b.output)
+        print("signature cost (%s): gpu %.7f oracle %.7f" % (gauge, float(a.output.cost), float(b.output.cost)))
+        assert float(b.output.cost) > 0.5
+        assert abs(float(a.output.cost) - float(b.output.cost)) <= 2e-3 * abs(float(b.output.cost))
+    # one signature at a time on the downstream gauge
+    for name in names[1:]:
+        a, b = cases.cance(T=960), cases.cance(T=960)
+        for m in (a, b):
+            cases.set_optimize(m.setup, m.mesh, jobs_fun=(name,))
+            m.setup._optimize.mask_event[:, 100:220] = 1
+            m.setup._optimize.mask_event[:, 700:900] = 2
+            compute_mean_forcing(m.setup, m.mesh, m.input_data)
+        smash_b200.forward(a.setup, a.mesh, a.input_data, a.parameters, a.parameters.copy(), a.states, a.states.copy(), a.output)
+        oracle.forward(b.setup, b.mesh, b.input_data, b.parameters, b.parameters.copy(), b.states, b.states.copy(), b.output)
+        assert abs(float(a.output.cost) - float(b.output.cost)) <= 1e-5 + 2e-3 * abs(float(b.output.cost)), (name, float(a.output.cost), float(b.output.cost))
+    # the adjoint of a signature objective is not provided: loud failure
+    pb, sb = ParametersDT(a.mesh), StatesDT(a.mesh)
+    with pytest.raises(RuntimeError, match="signature"):
+        smash_b200.forward_b(a.setup, a.mesh, a.input_data, a.parameters, pb, a.parameters.copy(), None, a.states, sb, a.states.copy(),
+                             None, a.output, None)

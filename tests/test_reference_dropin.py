@@ -122,6 +122,9 @@ def test_model_multiple_run(ref_smash, golden):
     ("optimize.hyper-linear_l-bfgs-b.cost", dict(mapping="hyper-linear", algorithm="l-bfgs-b", options={"maxiter": 1})),
     ("optimize.hyper-polynomial_l-bfgs-b.cost", dict(mapping="hyper-polynomial", algorithm="l-bfgs-b", options={"maxiter": 1})),
     ("optimize.uniform_sbs_mtg.cost", dict(gauge="all", wgauge="median", options={"maxiter": 1})),
+    ("optimize.uniform_nelder-mead.cost",
+     dict(mapping="uniform", algorithm="nelder-mead", jobs_fun=["nse", "Crc", "Cfp10", "Cfp50", "Epf", "Elt"],
+          wjobs_fun=[1, 2, 2, 2, 2, 2], event_seg={"peak_quant": 0.99}, options={"maxiter": 10})),
     ("optimize.distributed_l-bfgs-b_reg_fast.cost",
      dict(mapping="distributed", control_vector=["cp", "cft", "lr"],
           options={"maxiter": 2, "jreg_fun": ["prior", "smoothing"], "wjreg_fun": [1.0, 2.0], "auto_wjreg": "fast"})),
