@@ -826,7 +826,7 @@ static int make_cost_args(SmashPlan &pl, const SmashSetup *setup, const SmashMes
     c.dt = setup->dt; c.dx = mesh->dx;
     c.qsim = pl.d_qsim.p; c.qobs = pl.d_qobs.p; c.area = pl.d_area.p; c.wgauge = pl.d_wgauge.p; c.gauge_flwacc = pl.d_gauge_flwacc.p;
     c.njf = setup->njf;
-    if (c.njf > 8) return fail(SMASH_B200_EUNSUPPORTED, "more than 8 objective functions");
+    if (c.njf > 32) return fail(SMASH_B200_EUNSUPPORTED, "more than 32 objective functions");
     for (int j = 0; j < c.njf; j++) {
         c.jobs_fun[j] = setup->jobs_fun[j]; c.wjobs_fun[j] = setup->wjobs_fun[j];
         if (c.jobs_fun[j] < SMASH_JOBS_NSE || c.jobs_fun[j] > SMASH_JOBS_EPF)

@@ -57,8 +57,8 @@ struct CostArgs {
     const float *area, *wgauge;         // [ng]
     const int32_t *gauge_flwacc;        // [ng] flwacc at the gauge cell
     int njf;
-    int jobs_fun[8];
-    float wjobs_fun[8];
+    int jobs_fun[32];
+    float wjobs_fun[32];
     float jobs_b;                       // adjoint seed (cost_b); qsim_b written iff qsim_b != nullptr
     float *cost_jobs;                   // [m]
     float *qsim_b;                      // [m][T][ng] or nullptr

