@@ -241,6 +241,13 @@ int smash_b200_mesh_order(const SmashSetup *setup, const SmashMesh *mesh, int32_
  * Returns SMASH_B200_EUNSUPPORTED when the mesh needs the fused engine. */
 int smash_b200_mesh_chains(const SmashMesh *mesh, int64_t info[8], int32_t *cell, int32_t *task_of, int32_t *pos_of,
                            int32_t *down_of);
+/* Host-only: the ticket schedule of the tick pass (tick_kernels.cu) for this mesh, dealt to nwarp warps and replayed on the
+ * host the way the device walks it.  info: [0] cells [1] tiles [2] reaches [3] largest stage [4] shallow routed cells
+ * [5] deep cells [6] pit cells [7] units per warp [8] longest deep chain [9] tickets replayed [10] 1 = the schedule is
+ * consistent (every ticket only reads smaller keys, the replay completes) [11] cells that publish an exchange block.
+ * Replaces nothing in the reference (the time x space loop of md_forward_structure.f90:82-214 is sequential); test aid. */
+int smash_b200_mesh_tick_schedule(const SmashMesh *mesh, int32_t shallow_acc, int32_t nwarp, int32_t nwin, int64_t info[12],
+                                  int32_t *unit_of, int32_t *sigma_of);
 
 /* ---- the one collective of the path ----------------------------------------------------
  * One process per GPU.  The reference has no distributed layer; the regionalised multi-catchment calibration (shared

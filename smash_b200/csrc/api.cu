@@ -114,18 +114,18 @@ struct SplitState {
     DBuf<float> d_rows_seg, d_wnext, d_qprev;
 };
 
-// window pass (window_kernels.cu) + chain scans over the deep cells only: forward runs of large domains
+// tick pass (tick_kernels.cu): forward runs of large domains; the pit pairs are routed afterwards from rows
 struct WindowState {
     bool on = false;
-    WindowTopoHost host;
-    SplitState deep;               // route graph of the deep cells and its device image (graph members only)
-    DBuf<int32_t> d_meta, d_upoff, d_ups;
+    TickTopoHost host;
+    SplitState deep;               // route graph of the pit pairs and its device image (graph members only)
+    DBuf<int32_t> d_meta, d_upoff, d_ups, d_reach, d_wunits, d_cons1, d_cons2, d_need;
     DBuf<uint8_t> d_rounds;
     DBuf<float4> d_cc;
     DBuf<float> d_X;
-    DBuf<int> d_prog;
-    int nx = 2;
-    WfTopo topo{};
+    DBuf<int> d_cnt, d_err;
+    int nwarp = 0, maxu = 0, variant = 8;
+    TkTopo topo{};
 };
 
 // Opt-in (option "pin_host" = 1): large caller-owned host arrays (forcing in, domain series out) are page-locked in place
@@ -179,6 +179,7 @@ struct SmashPlan {
     cudaEvent_t evk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // per-kernel marks
     int kmark[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 1: evk[i] was recorded in the last run
     int launches = 0;
+    bool tick_ran = false;          // the last forward sweep was the tick pass: its error word is checked at the next synchronisation
     // topology on device
     DBuf<int32_t> d_cell, d_off, d_flwacc, d_up_begin, d_down_kind, d_down_lane, d_gfirst, d_gnext, d_hmax, d_sparse_k;
     DBuf<uint8_t> d_late, d_early, d_bflags;
@@ -396,34 +397,47 @@ static int upload_route_graph(SplitState &sp, int ng, cudaStream_t s) {
     return 0;
 }
 
-// ---- window pass: classes, deep-cell graph, exchange buffer ---------------------------------------
-// Forward runs of large domains (no tape, one member): window_kernels.cu routes the shallow cells inside the reservoir pass,
-// the chain scans then only see the deep cells.  Not eligible (tiny domain, option off, unsupported mesh): win.on stays false
-// and the run uses the row-based passes.
+// ---- tick pass: classes, reaches, stages, units per warp ------------------------------------------
+// Forward runs of large domains (no tape, one member, math = 1): tick_kernels.cu computes reservoirs and routing of the whole
+// domain in one kernel.  Not eligible (small domain, option off, unsupported mesh): win.on stays false and the run uses the
+// row-based passes.
 static int window_build(SmashPlan &pl, const SmashMesh *mesh) {
     WindowState &wn = pl.win;
     const RouteGraph &rg = pl.sp.rg;
     wn.on = false;
-    if (!option("window_pass", 0) || rg.n < option("window_min_cells", 65536)) return 0;
-    if (!build_window_topo(rg, (int)option("shallow_acc", 32), wn.host).empty()) return 0;
-    std::string err = build_route_graph(wn.deep.rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
-                                        mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
-                                        (int)option("route_ded_max", 64), 0, 0, wn.host.deep.data());
-    if (!err.empty() || wn.deep.rg.n != rg.n) return 0;
+    if (!option("tick_pass", 0) || rg.n < option("tick_min_cells", 65536)) return 0;
+    wn.variant = (int)option("tick_variant", 6);
+    CU(tick_grid_warps(wn.variant, (int)option("tick_ctas_per_sm", 0), &wn.nwarp));
+    // stages with at least a quarter of a unit per warp run two ticks after their producers (option tick_slack = 0: one tick)
+    const int slack = option("tick_slack", 1) ? std::max(1, wn.nwarp / (int)std::max<long long>(1, option("tick_slack_div", 4))) : 0;
+    if (!build_tick_topo(rg, (int)option("shallow_acc", 32), wn.host, slack).empty()) return 0;
+    std::vector<int32_t> wunits;
+    deal_tick_units(wn.host, wn.nwarp, wunits, wn.maxu);
+    if (wn.maxu > tick_max_units()) return 0;                         // a mesh too large for one resident grid: row-based passes
     cudaStream_t s = pl.stream;
     const size_t npad = (size_t)rg.npad, ntile = npad / 32;
-    TRY(upload_route_graph(wn.deep, mesh->ng, s));
-    TRY(wn.deep.d_deep.upload(wn.host.deep, s));
-    wn.deep.topo.deep = wn.deep.d_deep.p;
-    TRY(wn.deep.d_done.ensure(std::max<size_t>(1, 2 * (size_t)wn.deep.rg.ntask)));
+    if (wn.host.npair_cells > 0) {
+        std::string err = build_route_graph(wn.deep.rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
+                                            mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
+                                            (int)option("route_ded_max", 64), 0, 0, wn.host.pair.data());
+        if (!err.empty() || wn.deep.rg.n != rg.n || wn.deep.rg.nchain != 0) return 0;
+        TRY(upload_route_graph(wn.deep, mesh->ng, s));
+        std::vector<uint8_t> mask(npad, 0);
+        std::copy(wn.host.pair.begin(), wn.host.pair.end(), mask.begin());
+        TRY(wn.deep.d_deep.upload(mask, s));
+        wn.deep.topo.deep = wn.deep.d_deep.p;
+        TRY(wn.deep.d_done.ensure(std::max<size_t>(1, 2 * (size_t)wn.deep.rg.ntask)));
+    }
     TRY(wn.d_meta.upload(wn.host.meta, s)); TRY(wn.d_upoff.upload(wn.host.upoff, s)); TRY(wn.d_ups.upload(wn.host.ups, s));
     TRY(wn.d_rounds.upload(wn.host.tile_rounds, s));
-    wn.nx = (int)std::min<long long>(2, std::max<long long>(1, option("window_nx", 2)));
-    TRY(wn.d_cc.ensure(npad)); TRY(wn.d_X.ensure((size_t)wn.nx * npad * WF_W)); TRY(wn.d_prog.ensure(ntile));
-    CU(cudaMemsetAsync(wn.d_X.p, 0, (size_t)wn.nx * npad * WF_W * sizeof(float), s));
-    WfTopo &t = wn.topo;
-    t.n = rg.n; t.npad = (int)npad; t.ntile = (int)ntile; t.ng = mesh->ng;
-    t.meta = wn.d_meta.p; t.upoff = wn.d_upoff.p; t.ups = wn.d_ups.p; t.down = pl.sp.d_down.p; t.tile_rounds = wn.d_rounds.p;
+    if (wn.host.nreach > 0) TRY(wn.d_reach.upload(wn.host.reach_cells, s));
+    TRY(wn.d_wunits.upload(wunits, s));
+    TRY(wn.d_cons1.upload(wn.host.cons1, s)); TRY(wn.d_cons2.upload(wn.host.cons2, s)); TRY(wn.d_need.upload(wn.host.need, s));
+    TRY(wn.d_cc.ensure(npad)); TRY(wn.d_err.ensure(1));
+    TkTopo &t = wn.topo;
+    t.n = rg.n; t.npad = (int)npad; t.ntile = (int)ntile; t.nreach = wn.host.nreach; t.ng = mesh->ng;
+    t.meta = wn.d_meta.p; t.upoff = wn.d_upoff.p; t.ups = wn.d_ups.p; t.tile_rounds = wn.d_rounds.p; t.reach_cells = wn.d_reach.p;
+    t.cons1 = wn.d_cons1.p; t.cons2 = wn.d_cons2.p; t.need = wn.d_need.p;
     t.gauge_first = pl.sp.d_gfirst.p; t.gauge_next = pl.sp.d_gnext.p;
     wn.on = true;
     return 0;
@@ -618,23 +632,44 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
         return 0;
     }
     if (pl.win.on && !tape && pl.nmember == 1 && !pl.ensemble && math_mode() == 1) {
-        // window pass: reservoirs of every cell + routing of the shallow cells; then the chain scans over the deep cells
+        // tick pass: reservoirs + routing of every cell but the pit pairs; those are routed from rows afterwards
         WindowState &wn = pl.win;
-        WfArgs wa{};
-        wa.tp = wn.topo; wa.T = pl.tp.T; wa.Tp = sp.Tp; wa.w_begin = 0; wa.w_end = (pl.tp.T + WF_W - 1) / WF_W; wa.nx = wn.nx;
+        TkArgs wa{};
+        wa.tp = wn.topo; wa.T = pl.tp.T; wa.Tp = sp.Tp; wa.nwin = (pl.tp.T + TK_W - 1) / TK_W;
+        wa.nwarp = wn.nwarp; wa.maxu = wn.maxu; wa.wunits = wn.d_wunits.p;
         wa.dt = pl.dt; wa.dx = pl.dx; wa.save_q = save_q ? 1 : 0; wa.save_netp = save_netp ? 1 : 0;
+        const size_t nx = (size_t)wa.nwin * npad * TK_W;
+        if (wn.d_X.n < nx) TRY(wn.d_X.ensure(nx));
+        wa.nb = (int)std::max<long long>(1, option("tick_nb", 2));
+        const size_t ncnt = (size_t)((wa.nwin + wa.nb - 1) / wa.nb) * (wn.topo.ntile + wn.topo.nreach);
+        if (wn.d_cnt.n < ncnt) TRY(wn.d_cnt.ensure(ncnt));
         wa.cc = wn.d_cc.p; wa.fstates = pl.d_fstates.p; wa.X = wn.d_X.p; wa.rows = sp.d_rows.p; wa.qdom = pl.d_qdom.p;
-        wa.netp = pl.d_netp.p; wa.qpitch = sp.qpitch; wa.qsim = pl.d_qsim.p; wa.prog = wn.d_prog.p;
-        CU(launch_window_forward(wa, pl.d_fields.p, sp.tm_prcp, sp.tm_pet, pl.stream, (int)option("window_ctas_per_sm", 0),
-                                 (int)option("window_variant", 8)));
+        wa.netp = pl.d_netp.p; wa.qpitch = sp.qpitch; wa.qsim = pl.d_qsim.p; wa.cnt = wn.d_cnt.p; wa.err = wn.d_err.p;
+        if (option("tick_dbg", 0)) {
+            static unsigned long long *dp = nullptr;
+            if (!dp) CU(cudaMalloc(&dp, 1025 * sizeof(unsigned long long)));
+            std::vector<unsigned long long> hv(1025);
+            CU(cudaMemcpy(hv.data(), dp, 1025 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            if (hv[1024] != 0 && hv[1024] != ~0ull) {
+                fprintf(stderr, "[tick_dbg] previous run: tick -> ms since start:");
+                for (int kk = 0; kk < 1024; kk++) if (hv[kk]) fprintf(stderr, " %d:%.3f", kk, (hv[kk] - hv[1024]) * 1e-6);
+                fprintf(stderr, "\n");
+            }
+            CU(cudaMemset(dp, 0, 1024 * sizeof(unsigned long long)));
+            CU(cudaMemset(dp + 1024, 0xff, sizeof(unsigned long long)));
+            wa.dbg = dp;
+        }
+        CU(launch_tick_forward(wa, pl.d_fields.p, sp.tm_prcp, sp.tm_pet, pl.stream, wn.variant));
         mark(1);
-        SplitArgs b = split_args(pl, save_q, save_netp, &wn.deep);
-        b.fuse_export = save_q ? (int)option("fuse_export", 4) : 0;
-        CU(launch_route_forward(b, false, pl.stream));
-        mark(2);
-        pl.launches += 2 + sp.nwin * (1 + (wn.deep.rg.npair > 0 ? 1 : 0));
-        if (save_q && !b.fuse_export) { CU(launch_rows_to_domain(b, pl.stream)); pl.launches++; }
-        mark(3);
+        pl.launches += 2;
+        if (wn.host.npair_cells > 0) {
+            SplitArgs b = split_args(pl, save_q, save_netp, &wn.deep);
+            b.fuse_export = save_q ? 1 : 0;                                 // route_pair writes the pit cells' series to qdom itself
+            CU(launch_route_forward(b, false, pl.stream));
+            pl.launches += sp.nwin * 2;
+        }
+        mark(2); mark(3);
+        pl.tick_ran = true;
         return 0;
     }
     CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), tape, pl.stream));
@@ -1002,7 +1037,7 @@ static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **
              (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0, small ? 1 : 0,
              option("route_ded_min", 96) + 1024 * option("route_ded_max", 64) + (option("route_queues", 12) << 20) +
                  ((option("adjoint_checkpoint", -1) + 1) << 26) + (option("tape_budget_mb", 16384) << 28) +
-                 (option("window_pass", 0) << 48) + (option("shallow_acc", 32) << 50));
+                 (option("tick_pass", 0) << 48) + (option("tick_slack", 1) << 49) + (option("shallow_acc", 32) << 50));
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
         std::unique_ptr<SmashPlan> pl(new SmashPlan());
@@ -1122,7 +1157,19 @@ static int forward_streamed(SmashPlan &pl, const SmashSetup *setup, const SmashM
     return 0;
 }
 
+// after a synchronisation of the plan's stream: a wait of the tick pass that did not end leaves 1 + unit in its error word
+static int tick_check(SmashPlan &pl) {
+    if (!pl.tick_ran) return 0;
+    pl.tick_ran = false;
+    int h = 0;
+    CU(cudaMemcpyAsync(&h, pl.win.d_err.p, sizeof(int), cudaMemcpyDeviceToHost, pl.stream));
+    CU(cudaStreamSynchronize(pl.stream));
+    if (h != 0) return fail(SMASH_B200_ECUDA, "tick pass: a wait for unit %d did not end (results invalid)", h - 1);
+    return 0;
+}
+
 static int run_forward_engine(SmashPlan &pl, bool save_q, bool save_netp, bool tape) {
+    pl.tick_ran = false;
     if (pl.engine == 1) return split_forward(pl, save_q, save_netp, tape);
     SolverArgs a = solver_args(pl, save_q, save_netp, tape);
     CU(launch_forward(a, math_mode(), pl.stream));
@@ -1180,6 +1227,7 @@ static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const 
             if (out->fstates.v[i] && st->v[i]) memcpy(out->fstates.v[i], st->v[i], nc * sizeof(float));
     CU(cudaStreamSynchronize(pl->stream));
     if (streamed) CU(cudaStreamSynchronize(pl->s_out));
+    TRY(tick_check(*pl));
     for (int f = 0; f < 3; f++) {
         float *dst = restore_states ? (out ? out->fstates.v[FIELD_STATE[f]] : nullptr) : st->v[FIELD_STATE[f]];
         if (dst) scatter_sorted(*pl, fs.data() + (size_t)f * pl->ncols, dst);
@@ -1538,6 +1586,7 @@ extern "C" int smash_b200_plan_run_forward(SmashPlan *plan, float *elapsed_ms) {
     CU(cudaEventRecord(plan->ev1, plan->stream));
     CU(cudaEventSynchronize(plan->ev1));
     if (elapsed_ms) CU(cudaEventElapsedTime(elapsed_ms, plan->ev0, plan->ev1));
+    TRY(tick_check(*plan));
     return 0;
 }
 
@@ -1714,6 +1763,38 @@ extern "C" int smash_b200_mesh_chains(const SmashMesh *mesh, int64_t info[8], in
     return 0;
 }
 
+// host-only: the schedule of the tick pass (used by the CPU test-suite).  Builds classes, reaches, stages and the deal of the
+// units to `nwarp` warps, then replays the tickets the way the kernel's warps would -- every warp in its own key order,
+// a ticket runs only when everything it reads has been published -- and reports whether the replay completes.
+// info: [0] cells [1] tiles [2] reaches [3] largest stage [4] shallow routed cells [5] deep cells [6] pit cells [7] units per
+// warp [8] longest deep chain [9] tickets replayed [10] 1 = every dependency points to a smaller key and the replay completed
+// unit_of / sigma_of (per cell, or NULL): the unit that publishes the cell's discharge and its stage
+extern "C" int smash_b200_mesh_tick_schedule(const SmashMesh *mesh, int32_t shallow_acc, int32_t nwarp, int32_t nwin, int64_t info[12],
+                                             int32_t *unit_of, int32_t *sigma_of) {
+    if (!mesh || !info || nwarp < 1 || nwin < 1) return fail(SMASH_B200_EINVAL, "bad argument");
+    RouteGraph rg;
+    std::string err = build_route_graph(rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
+                                        mesh->local_active_cell, mesh->path, mesh->gauge_pos);
+    if (!err.empty()) return fail(err.rfind("unsupported", 0) == 0 ? SMASH_B200_EUNSUPPORTED : SMASH_B200_EINVAL, "%s", err.c_str());
+    TickTopoHost tk;
+    err = build_tick_topo(rg, shallow_acc, tk, option("tick_slack", 1) ? std::max(1, nwarp / 4) : 0);   // as window_build does
+    if (!err.empty()) return fail(err.rfind("unsupported", 0) == 0 ? SMASH_B200_EUNSUPPORTED : SMASH_B200_EINVAL, "%s", err.c_str());
+    std::vector<int32_t> pub;
+    long long done = 0;
+    int maxu = 0;
+    const bool ok = replay_tick_schedule(rg, tk, nwarp, nwin, pub, done, maxu);
+    const int ntile = tk.ntile;
+    const long long total = (long long)(ntile + tk.nreach) * nwin;
+    info[0] = rg.n; info[1] = ntile; info[2] = tk.nreach; info[3] = tk.max_sigma; info[4] = tk.nshallow; info[5] = tk.ndeep;
+    info[6] = tk.npair_cells; info[7] = maxu; info[8] = tk.max_chain; info[9] = done; info[10] = (ok && done == total) ? 1 : 0;
+    info[11] = tk.nx_cells;
+    for (int j = 0; j < rg.n; j++) {
+        if (unit_of) unit_of[j] = pub[j];
+        if (sigma_of) sigma_of[j] = pub[j] >= 0 ? tk.sigma[pub[j]] : -1;
+    }
+    return 0;
+}
+
 // device time of the kernels of the last plan run (split engine), milliseconds, -1 where a kernel did not run:
 // [0] vertical_forward, [1] route_forward, [2] rows_to_domain, [3] route_adjoint, [4] vertical_adjoint
 extern "C" int smash_b200_plan_kernel_times(SmashPlan *plan, float ms[5]) {
@@ -1745,7 +1826,10 @@ extern "C" double smash_b200_plan_stat(const SmashPlan *plan, const char *name) 
         if (n == "tape_bytes")
             return 4.0 * ((double)sp.d_tape_hp.n + sp.d_tape_hft.n + sp.d_rows_hr.n + sp.d_rows_w.n + (sp.ckpt ? (double)sp.d_rows_seg.n : (double)sp.d_rows.n) +
                           sp.d_ckpt.n);
-        if (n == "window_pass") return plan->win.on ? 1.0 : 0.0;
+        if (n == "tick_pass") return plan->win.on ? 1.0 : 0.0;
+        if (n == "tick_stages") return plan->win.on ? (double)plan->win.host.max_sigma : -1.0;
+        if (n == "tick_reaches") return plan->win.on ? (double)plan->win.host.nreach : -1.0;
+        if (n == "tick_units_per_warp") return plan->win.on ? (double)plan->win.maxu : -1.0;
         if (n == "deep_cells") return plan->win.on ? (double)plan->win.host.ndeep : -1.0;
         if (n == "shallow_cells") return plan->win.on ? (double)plan->win.host.nshallow : -1.0;
     }

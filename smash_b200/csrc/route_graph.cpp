@@ -305,51 +305,256 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
 }
 
 // ------------------------------------------------------------------------------------------------
-// Classes of the window pass (window_kernels.cu) from the full route graph.  Cells are visited in path order, which is a
-// topological order of every non-lagged edge: a cell is deep when its flow accumulation exceeds shallow_acc, when it sits in
-// a pit pair, or when one of its inflows is deep or lagged; every other gathering cell is shallow and routed inside the
-// window pass.
+// Topology of the tick pass (tick_kernels.cu) from the full route graph.
+//
+// Cells are visited in path order, which is a topological order of every non-lagged edge.  Classes: S source (flwacc == 1),
+// R shallow routed cell (flwacc <= shallow_acc, no inflow from a deep / pit cell, at most 8 dependency rounds inside its
+// tile), P cell of a pit pair, D every other gathering cell.  The D cells are cut into heavy-path chains (heavy inflow = the
+// D inflow with the largest flwacc) and the chains into reaches of at most 32 cells.
+//
+// Units: tile b (cells 32 b .. 32 b + 31) and reach r (unit ntile + r).  Stage sigma of a unit = 1 + the largest stage among
+// the units that produce one of its inputs; ticket (unit, window w) has key sigma + w and only reads what tickets with a
+// smaller key wrote.
 // ------------------------------------------------------------------------------------------------
-std::string build_window_topo(const RouteGraph &g, int shallow_acc, WindowTopoHost &out) {
+std::string build_tick_topo(const RouteGraph &g, int shallow_acc, TickTopoHost &out, int slack_units) {
     const int n = g.n, npad = g.npad, ntile = npad / 32;
-    out = WindowTopoHost();
-    out.meta.assign(npad, 0); out.upoff.assign(npad, 0); out.deep.assign(npad, 0); out.tile_rounds.assign(ntile, 0);
+    out = TickTopoHost();
+    out.ntile = ntile;
+    out.meta.assign(npad, 0); out.upoff.assign(npad, 0); out.tile_rounds.assign(ntile, 0); out.pair.assign(n, 0);
+    out.cons1.assign(npad, -1); out.cons2.assign(npad, -1);
     std::vector<uint8_t> cls(n, 0), round(n, 0);
     for (int j = 0; j < n; j++) {
-        const int nup = g.up_begin[j + 1] - g.up_begin[j];
         if (g.flwacc[j] <= 1) { cls[j] = 0; continue; }
         // flwacc > 1 without a computed inflow: still routed (qup = 0, md_forward_structure.f90:146-156)
-        bool deep = g.flwacc[j] > shallow_acc || nup > 8 || (g.flwacc[j] - 1) >= (1 << 19);
+        bool pair = false, deep = g.flwacc[j] > shallow_acc;
         int r = 0;
-        for (int e = g.up_begin[j]; e < g.up_begin[j + 1] && !deep; e++) {
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) {
             const int s = g.up[e].src;
-            if (g.up[e].task == UP_PARTNER || s >= j || cls[s] == 2) { deep = true; break; }
-            if (cls[s] == 1 && (s >> 5) == (j >> 5)) r = std::max(r, round[s] + 1);
+            if (g.up[e].task == UP_PARTNER) { pair = true; break; }
+            if (s >= j) return "unsupported: lagged inflow outside a pit pair";
+            if (cls[s] >= 2) deep = true;
+            else if (cls[s] == 1 && (s >> 5) == (j >> 5)) r = std::max(r, round[s] + 1);
         }
-        if (!deep && r > 7) deep = true;
-        cls[j] = deep ? 2 : 1;
-        round[j] = deep ? 0 : (uint8_t)r;
+        if (r > 7) deep = true;
+        cls[j] = pair ? 2 : deep ? 3 : 1;
+        round[j] = cls[j] == 1 ? (uint8_t)r : 0;
+        if (pair) { out.pair[j] = 1; out.npair_cells++; }
+    }
+    for (int j = 0; j < n; j++)
+        if (cls[j] == 2 && g.down[j] >= 0 && cls[g.down[j]] != 2) return "unsupported: a pit pair drains into another cell";
+
+    // ---- heavy-path chains of the D cells, cut into reaches
+    std::vector<int32_t> heavy(n, -1), next(n, -1), reach_of(n, -1), lane_of(n, -1);
+    for (int j = 0; j < n; j++) {
+        if (cls[j] != 3) continue;
+        int best = -1, best_fa = -1;
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) {
+            const int s = g.up[e].src;
+            if (cls[s] == 3 && g.flwacc[s] > best_fa) { best_fa = g.flwacc[s]; best = s; }
+        }
+        if (best >= 0) { heavy[j] = best; next[best] = j; }
     }
     for (int j = 0; j < n; j++) {
-        const int nup = (cls[j] == 1) ? g.up_begin[j + 1] - g.up_begin[j] : 0;
+        if (cls[j] != 3 || heavy[j] >= 0) continue;                      // chain heads
+        int len = 0;
+        for (int c = j; c >= 0; c = next[c], len++) {
+            if (len % 32 == 0) { out.reach_cells.resize(out.reach_cells.size() + 32, -1); out.nreach++; }
+            reach_of[c] = out.nreach - 1; lane_of[c] = len % 32;
+            out.reach_cells[(size_t)(out.nreach - 1) * 32 + len % 32] = c;
+            out.ndeep++;
+        }
+        out.max_chain = std::max(out.max_chain, len);
+    }
+    auto owner = [&](int s) { return cls[s] == 3 ? ntile + reach_of[s] : (s >> 5); };
+
+    // ---- inflow lists (reference summation order) and per-cell records
+    for (int j = 0; j < n; j++) {
         const int d = g.down[j];
-        const bool want_x = d >= 0 && cls[d] == 1, want_row = d >= 0 && cls[d] == 2 && cls[j] != 2;
         out.upoff[j] = (int32_t)out.ups.size();
-        for (int e = 0; e < nup; e++) out.ups.push_back(g.up[g.up_begin[j] + e].src);
+        int nup = 0;
+        if (cls[j] == 1 || cls[j] == 3)
+            for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) {
+                const int s = g.up[e].src;
+                // the previous cell of the same reach hands its discharge over inside the warp
+                if (cls[j] == 3 && s == heavy[j] && reach_of[s] == reach_of[j]) continue;
+                out.ups.push_back(s);
+                nup++;
+            }
+        if (nup > 15) return "unsupported: more than 15 inflows";
+        const bool chained = cls[j] == 3 && heavy[j] >= 0 && reach_of[heavy[j]] == reach_of[j];
+        // who reads this cell's discharge from memory: a shallow cell or a reach reads the exchange blocks, a pit cell reads rows
+        const bool handed = d >= 0 && cls[j] == 3 && cls[d] == 3 && heavy[d] == j && reach_of[d] == reach_of[j];
+        const bool want_x = d >= 0 && !handed && (cls[d] == 1 || cls[d] == 3);
+        const bool want_row = d >= 0 && cls[d] == 2 && cls[j] != 2;
+        if (g.flwacc[j] - 1 >= (1 << 19)) return "unsupported: flow accumulation above 2^19";
         out.meta[j] = cls[j] | (want_x ? 4 : 0) | (want_row ? 8 : 0) | (g.gauge_first[j] >= 0 ? 16 : 0) | (round[j] << 5) | (nup << 8) |
-                      (std::min(g.flwacc[j] - 1, (1 << 19) - 1) << 12);
-        out.deep[j] = cls[j] == 2;
+                      (chained ? 4096 : 0) | (std::max(0, g.flwacc[j] - 1) << 13);
+        // the unit that reads the block a tile ticket writes for this cell (a D cell: its own reach reads the runoff), and the
+        // unit that reads the block its reach ticket writes
+        if (cls[j] == 3) {
+            out.cons1[j] = ntile + reach_of[j];
+            if (want_x) out.cons2[j] = owner(d);
+        } else if (want_x && owner(d) != (j >> 5)) {
+            out.cons1[j] = owner(d);
+        }
         if (cls[j] == 1) {
             out.nshallow++;
             out.tile_rounds[j >> 5] = std::max<uint8_t>(out.tile_rounds[j >> 5], (uint8_t)(round[j] + 1));
-            out.max_round = std::max(out.max_round, (int)round[j]);
         }
-        if (cls[j] == 2) out.ndeep++;
-        if (want_row) out.nrow++;
         if (want_x) out.nx_cells++;
+        if (want_row) out.nrow_cells++;
     }
-    if (out.ups.empty()) out.ups.push_back(-1);
+    if (out.ups.empty()) out.ups.push_back(0);
+
+    // ---- stages
+    const int nunit = ntile + out.nreach;
+    out.sigma.assign(nunit, 0);
+    for (int j = 0; j < n; j++) {                                         // tiles: path order visits every producer tile first
+        if (cls[j] != 1) continue;
+        int &sg = out.sigma[j >> 5];
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) {
+            const int s = g.up[e].src;
+            if ((s >> 5) != (j >> 5)) sg = std::max(sg, out.sigma[s >> 5] + 1);
+        }
+    }
+    // reaches by their last cell (the largest index of the reach: flwacc grows downstream), so every producer reach comes first
+    std::vector<int32_t> order(out.nreach);
+    std::vector<int32_t> last(out.nreach, -1);
+    for (int r = 0; r < out.nreach; r++) {
+        order[r] = r;
+        for (int l = 0; l < 32; l++) last[r] = std::max(last[r], out.reach_cells[(size_t)r * 32 + l]);
+    }
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return last[x] < last[y]; });
+    for (int r : order) {
+        int sg = 0;
+        for (int l = 0; l < 32; l++) {
+            const int c = out.reach_cells[(size_t)r * 32 + l];
+            if (c < 0) continue;
+            sg = std::max(sg, out.sigma[c >> 5] + 1);                   // its own runoff block
+            for (int e = g.up_begin[c]; e < g.up_begin[c + 1]; e++) {
+                const int s = g.up[e].src;
+                if (cls[s] == 3 && reach_of[s] == r) continue;
+                const int o = owner(s);
+                if (o >= ntile && last[o - ntile] >= last[r]) return "internal: reach order violates a dependency";
+                sg = std::max(sg, out.sigma[o] + 1);
+            }
+        }
+        out.sigma[ntile + r] = sg;
+    }
+    for (int u = 0; u < nunit; u++) out.max_sigma = std::max(out.max_sigma, out.sigma[u]);
+    // blocks a unit waits for per window = arrivals counted by its producers
+    out.need.assign(nunit, 0);
+    for (int j = 0; j < n; j++) {
+        if (out.cons1[j] >= 0) out.need[out.cons1[j]]++;
+        if (out.cons2[j] >= 0) out.need[out.cons2[j]]++;
+    }
+    // ticket key of a stage: consumers of a crowded stage start two ticks after their producers (a whole tick of slack, so
+    // that nobody waits for a producer that is still being worked on); the sparse deep stages follow one tick apart
+    std::vector<int32_t> count(out.max_sigma + 1, 0);
+    for (int u = 0; u < nunit; u++) count[out.sigma[u]]++;
+    out.key.assign(out.max_sigma + 1, 0);
+    for (int sg = 1; sg <= out.max_sigma; sg++) out.key[sg] = out.key[sg - 1] + ((slack_units > 0 && count[sg] >= slack_units) ? 2 : 1);
+    // blocks read `far_ticks` or more ticks after they were written are not worth keeping in L2 (bit 30 of the entries)
+    auto reader = [&](int j) { return cls[j] == 3 ? ntile + reach_of[j] : (j >> 5); };
+    const int far_ticks = 4;
+    for (int j = 0; j < n; j++) {
+        if (cls[j] != 1 && cls[j] != 3) continue;
+        const int kj = out.key[out.sigma[reader(j)]];
+        const int nup = out.meta[j] >> 8 & 15;
+        for (int e = 0; e < nup; e++) {
+            const int s = out.ups[out.upoff[j] + e];
+            if (kj - out.key[out.sigma[owner(s)]] >= far_ticks) out.ups[out.upoff[j] + e] = s | (1 << 30);
+        }
+    }
+    for (int j = 0; j < n; j++) {
+        if (out.cons1[j] >= 0 && out.key[out.sigma[out.cons1[j]]] - out.key[out.sigma[j >> 5]] >= far_ticks) out.cons1[j] |= 1 << 30;
+        if (out.cons2[j] >= 0 && out.key[out.sigma[out.cons2[j]]] - out.key[out.sigma[reader(j)]] >= far_ticks) out.cons2[j] |= 1 << 30;
+    }
     return "";
+}
+
+// Units dealt to the warps of a resident grid: sorted by stage, round-robin, so every warp holds the same mix of stages.
+void deal_tick_units(const TickTopoHost &t, int nwarp, std::vector<int32_t> &wunits, int &maxu) {
+    const int nunit = t.ntile + t.nreach;
+    std::vector<int32_t> order(nunit);
+    for (int u = 0; u < nunit; u++) order[u] = u;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return t.sigma[x] < t.sigma[y]; });
+    maxu = (nunit + nwarp - 1) / nwarp;
+    wunits.assign((size_t)nwarp * maxu * 2, -1);
+    for (int i = 0; i < nunit; i++) {
+        const int g = i % nwarp, k = i / nwarp;
+        wunits[((size_t)g * maxu + k) * 2] = order[i];
+        wunits[((size_t)g * maxu + k) * 2 + 1] = t.key[t.sigma[order[i]]];
+    }
+}
+
+// Host replay of the tick pass (tests): every warp walks its tickets in key order, a ticket runs only when everything it reads
+// has been published.  pub[j] = unit that publishes cell j's discharge.  Returns true when every dependency points to a
+// smaller stage and the replay completes; done = tickets replayed.
+bool replay_tick_schedule(const RouteGraph &rg, const TickTopoHost &tk, int nwarp, int nwin, std::vector<int32_t> &pub, long long &done,
+                          int &maxu) {
+    std::vector<int32_t> wunits;
+    deal_tick_units(tk, nwarp, wunits, maxu);
+    const int ntile = tk.ntile, nunit = ntile + tk.nreach;
+    std::vector<std::vector<int32_t>> need(nunit);
+    pub.assign(rg.npad, -1);
+    bool ok = true;
+    for (int r = 0; r < tk.nreach; r++)
+        for (int l = 0; l < 32; l++) {
+            const int c = tk.reach_cells[(size_t)r * 32 + l];
+            if (c >= 0) pub[c] = ntile + r;
+        }
+    for (int j = 0; j < rg.n; j++) {
+        const int cls = tk.meta[j] & 3;
+        if (cls <= 1) pub[j] = j >> 5;
+        if (cls == 3 && pub[j] < 0) return false;
+    }
+    for (int j = 0; j < rg.n; j++) {
+        const int cls = tk.meta[j] & 3;
+        if (cls != 1 && cls != 3) continue;
+        const int unit = pub[j];
+        if (cls == 3) need[unit].push_back(j >> 5);
+        for (int e = 0; e < (tk.meta[j] >> 8 & 15); e++) {
+            const int src = tk.ups[tk.upoff[j] + e] & ~(1 << 30);
+            if (src < 0 || src >= rg.n || pub[src] < 0) return false;
+            const int own = pub[src];
+            if (own != unit) { need[unit].push_back(own); if (tk.key[tk.sigma[own]] >= tk.key[tk.sigma[unit]]) ok = false; }
+        }
+    }
+    // the arrival counts the device waits for must equal the blocks each unit reads from other units
+    for (int u = 0; u < nunit; u++)
+        if ((int)need[u].size() != tk.need[u]) ok = false;
+    // own[u]: windows the owner has finished; seen[u]: windows it has published (a warp publishes when it leaves a tick)
+    std::vector<int32_t> own(nunit, 0), seen(nunit, 0), cur_k(nwarp, 0), cur_i(nwarp, 0), nu(nwarp, 0);
+    for (int g = 0; g < nwarp; g++) {
+        while (nu[g] < maxu && wunits[((size_t)g * maxu + nu[g]) * 2] >= 0) nu[g]++;
+        cur_k[g] = nu[g] ? wunits[(size_t)g * maxu * 2 + 1] : 0;
+    }
+    done = 0;
+    const long long total = (long long)nunit * nwin;
+    bool moved = true;
+    while (moved && done < total) {
+        moved = false;
+        for (int g = 0; g < nwarp; g++) {
+            if (!nu[g]) continue;
+            const int kmax = wunits[((size_t)g * maxu + nu[g] - 1) * 2 + 1] + nwin - 1;
+            while (cur_k[g] <= kmax) {
+                const int u = wunits[((size_t)g * maxu + cur_i[g]) * 2], ky = wunits[((size_t)g * maxu + cur_i[g]) * 2 + 1];
+                const int w = cur_k[g] - ky;
+                if (w >= 0 && w < nwin) {
+                    bool ready = own[u] == w;
+                    for (int p_ : need[u]) if (seen[p_] <= w) { ready = false; break; }
+                    if (!ready) break;
+                    own[u] = w + 1; done++; moved = true;
+                }
+                if (++cur_i[g] == nu[g]) {
+                    cur_i[g] = 0; cur_k[g]++;
+                    for (int q = 0; q < nu[g]; q++) seen[wunits[((size_t)g * maxu + q) * 2]] = own[wunits[((size_t)g * maxu + q) * 2]];
+                }
+            }
+        }
+    }
+    return ok && done == total;
 }
 
 }  // namespace smash

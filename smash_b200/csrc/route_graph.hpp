@@ -79,14 +79,33 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
 // pass, at most ded_max CTAs.  reach > 0: those chains are cut into reaches of at most `reach` cells, one CTA per reach
 // (tick wavefront, the reaches of a river pipelined); reach = 0: one CTA per whole chain (window scan per cell).
 
-// host side of the window pass topology (WfTopo, split_kernels.cuh)
-struct WindowTopoHost {
-    std::vector<int32_t> meta, upoff, ups;
-    std::vector<uint8_t> tile_rounds, deep;
-    int nshallow = 0, ndeep = 0, nrow = 0, nx_cells = 0, max_round = 0;
+// host side of the tick pass topology (TkTopo, split_kernels.cuh; kernels in tick_kernels.cu)
+struct TickTopoHost {
+    int ntile = 0, nreach = 0;
+    std::vector<int32_t> meta;          // [npad] bits 0-1 class (0 S source, 1 R shallow routed, 2 P pit pair, 3 D deep), bit 2: a
+                                        // shallow cell or a reach reads the cell's exchange block, bit 3: a pit cell reads its row,
+                                        // bit 4 gauge, bits 5-7 round inside the tile (R), bits 8-11 inflow entries in `ups`,
+                                        // bit 12 (D): the previous lane of the reach holds the heavy inflow, bits 13-31 flwacc - 1
+    std::vector<int32_t> upoff;         // [npad] first inflow entry (pairs of int32 in ups)
+    std::vector<int32_t> ups;           // (producer cell, unit that publishes it) in the reference's summation order
+    std::vector<uint8_t> tile_rounds;   // [ntile] dependency rounds inside the tile (0: no R cell)
+    std::vector<uint8_t> pair;          // [n] 1 = cell of a pit pair (routed afterwards by route_pairs_kernel from rows)
+    std::vector<int32_t> reach_cells;   // [nreach][32] cells of a reach, upstream -> downstream, -1 = unused lane
+    std::vector<int32_t> cons1;         // [npad] unit that reads the block the cell's TILE ticket writes (S / R: the consumer's unit when
+                                        // it is another unit; D: the cell's own reach, which reads the runoff), or -1
+    std::vector<int32_t> cons2;         // [npad] D cells: unit that reads the block the cell's REACH ticket writes, or -1
+    std::vector<int32_t> need;          // [ntile + nreach] blocks of other units a ticket of the unit reads
+    std::vector<int32_t> sigma;         // [ntile + nreach] stage of every unit
+    std::vector<int32_t> key;           // [max_sigma + 1] ticket key of a stage (ticket (unit, w) runs at key[sigma] + w)
+    int max_sigma = 0, nshallow = 0, ndeep = 0, npair_cells = 0, nx_cells = 0, nrow_cells = 0, max_chain = 0;
 };
-// Classes of the window pass from the full route graph; shallow_acc = largest flwacc routed inside the window pass.
-// Returns "" or "unsupported: ...".
-std::string build_window_topo(const RouteGraph &g, int shallow_acc, WindowTopoHost &out);
+// shallow_acc = largest flwacc routed inside the tile tickets.  Returns "" or "unsupported: ...".
+// slack_units: stages with at least that many units start two ticks after the stage before (0: always one tick)
+std::string build_tick_topo(const RouteGraph &g, int shallow_acc, TickTopoHost &out, int slack_units = 0);
+// wunits[warp][k] = (unit, key of its stage), k < maxu, -1 = none; a warp's units are sorted by stage
+void deal_tick_units(const TickTopoHost &t, int nwarp, std::vector<int32_t> &wunits, int &maxu);
+// host replay of the ticket walk (tests): true = consistent and complete
+bool replay_tick_schedule(const RouteGraph &rg, const TickTopoHost &tk, int nwarp, int nwin, std::vector<int32_t> &pub, long long &done,
+                          int &maxu);
 
 }  // namespace smash

@@ -90,42 +90,50 @@ struct SplitArgs {
     int *rdone;                  // [m][ntask]
 };
 
-// ---- window pass (window_kernels.cu): reservoirs of every cell + routing of the shallow cells, 8 steps at a time ----------
-constexpr int WF_W = 8;          // time steps per window = one TMA box = one 32-byte sector of a row
+// ---- tick pass (tick_kernels.cu): reservoirs + routing of the whole domain, 8 steps at a time ------------------------------
+constexpr int TK_W = 8;          // time steps per window = one TMA box = one 32-byte sector per cell
 
-struct WfTopo {
-    int n, npad, ntile, ng;
-    const int32_t *meta;         // [npad] bits 0-1 class (0 source, 1 shallow routed, 2 deep), bit 2: the consumer reads the exchange
-                                 // buffer, bit 3: the consumer is a deep cell (the series is also written as a row), bit 4: gauge,
-                                 // bits 5-7: round inside the tile, bits 8-11: inflows, bits 12-: flwacc - 1
-    const int32_t *upoff;        // [npad] first inflow entry of a shallow routed cell
-    const int32_t *ups;          // producer cells, reference summation order (md_routing_operator.f90:37-53)
-    const int32_t *down;         // [npad] consumer cell or -1
-    const uint8_t *tile_rounds;  // [ntile] dependency rounds inside the tile (0: no shallow routed cell)
+struct TkTopo {
+    int n, npad, ntile, nreach, ng;
+    const int32_t *meta;         // [npad] TickTopoHost::meta (route_graph.hpp)
+    const int32_t *upoff;        // [npad] first inflow entry of an R or D cell
+    const int32_t *ups;          // producer cells in the reference's summation order (md_routing_operator.f90:37-53); bit 30: the
+                                 // block was written many ticks before it is read
+    const int32_t *cons1, *cons2;  // [npad] TickTopoHost::cons1 / cons2; bit 30: the reader runs many ticks later
+    const int32_t *need;         // [ntile + nreach] blocks of other units a ticket reads
+    const uint8_t *tile_rounds;  // [ntile] dependency rounds inside the tile (0: no R cell)
+    const int32_t *reach_cells;  // [nreach][32]
     const int32_t *gauge_first;  // [npad]
     const int32_t *gauge_next;   // [ng]
 };
 
-struct WfArgs {
-    WfTopo tp;
-    int T, Tp;                   // time steps; pitch of the deep rows
-    int w_begin, w_end;          // windows of this launch
-    int nx;                      // slots of the exchange buffer (windows a block stays readable): 1 or 2
+struct TkArgs {
+    TkTopo tp;
+    int T, Tp, nwin;             // time steps; pitch of the pit rows; windows = ceil(T / 8)
+    int nb;                      // windows per visit: a ticket is (unit, visit), key = key of the stage + visit
+    int nwarp, maxu;             // warps of the resident grid; columns of wunits
+    const int32_t *wunits;       // [nwarp][maxu] (unit, ticket key of its stage), sorted by stage, -1 = none
     float dt, dx;
     int save_q, save_netp;
     float4 *cc;                  // [npad] cp, cft, exc, exp(-dt / (60 lr))
     float *fstates;              // [3][npad] reservoir and routing states carried from window to window; final states
-    float *X;                    // [nx][npad][WF_W] discharge blocks handed from producer to consumer (L2-resident)
-    float *rows;                 // [npad][Tp] qt of the deep cells, q of the cells that flow into a deep cell
+    float *X;                    // [nwin][npad][TK_W] discharge blocks handed from producer to consumer
+    float *rows;                 // [npad][Tp] runoff of the pit cells, discharge of the cells that flow into a pit cell
     float *qdom, *netp;          // [T][qpitch]
     int64_t qpitch;
     float *qsim;                 // [T][ng]
-    int *prog;                   // [ntile] windows finished
+    int *cnt;                    // [visits][ntile + nreach] cells whose blocks have arrived for ticket (unit, visit)
+    int *err;                    // set to 1 + unit when a wait did not end (the results are then invalid)
+    unsigned long long *dbg;     // diagnostics (option tick_dbg) or nullptr: [k] time the last warp left tick k, [1024] start
 };
 
-// all windows [w_begin, w_end); w_begin == 0 also prepares the per-cell constants and the carried states from `fields`
-cudaError_t launch_window_forward(const WfArgs &a, const float *fields, const CUtensorMap &prcp, const CUtensorMap &pet, cudaStream_t s,
-                                  int ctas_per_sm = 0, int variant = 8);
+size_t tick_smem_bytes();
+int tick_max_units();
+// warps of the fully resident grid (variant: 8 / 6 / 4 CTAs per SM aimed at; ctas_per_sm > 0 caps it)
+cudaError_t tick_grid_warps(int variant, int ctas_per_sm, int *nwarp);
+// the whole run: per-cell constants and carried states from `fields`, then every ticket
+cudaError_t launch_tick_forward(const TkArgs &a, const float *fields, const CUtensorMap &prcp, const CUtensorMap &pet,
+                                cudaStream_t s, int variant = 8);
 
 // 2-D tensor map over a [rows][pitch] float array, box = 8 rows x 32 columns.  cols = valid columns (the rest reads 0).
 int make_tensor_map_2d(CUtensorMap *tm, const float *base, uint64_t cols, uint64_t rows, uint64_t pitch_elems, const char **err);

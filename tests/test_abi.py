@@ -172,6 +172,41 @@ def test_chains_france():
     assert info[3] <= 16 and info[5] <= 820
 
 
+def tick_schedule(m, shallow_acc, nwarp, nwin):
+    pk = L.Packed()
+    me = L.pack_mesh(m.mesh, m.setup, pk)
+    info = (C.c_int64 * 12)()
+    n = int(((m.mesh.active_cell == 1) & (m.mesh._local_active_cell == 1)).sum())
+    unit, sigma = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    L.check(L.lib().smash_b200_mesh_tick_schedule(C.byref(me), shallow_acc, nwarp, nwin, info, L._ip(unit), L._ip(sigma)))
+    return list(info), unit, sigma
+
+
+@pytest.mark.parametrize("shallow_acc,nwarp", [(4, 7), (32, 64), (1, 3)])
+def test_tick_schedule_cance(shallow_acc, nwarp):
+    # the ticket order of the tick pass (tick_kernels.cu): every ticket only reads smaller keys and the host replay of the
+    # warps' in-order walks completes (no deadlock), whatever the number of warps
+    m = cases.cance(T=24)
+    info, unit, sigma = tick_schedule(m, shallow_acc, nwarp, 5)
+    assert info[0] == 383 and info[10] == 1 and info[9] == (info[1] + info[2]) * 5
+    cell, task, pos, down, _ = mesh_chains(m)
+    has = (down >= 0) & (unit >= 0) & (unit[np.maximum(down, 0)] >= 0)
+    diff = unit[down[has]] != unit[has]
+    assert np.all(sigma[down[has]][diff] > sigma[has][diff])                 # a consumer's stage lies above its producer's
+
+
+def test_tick_schedule_france():
+    m = cases.france(T=8)
+    info, unit, sigma = tick_schedule(m, 32, 4736, 3)
+    assert info[0] == 906044 and info[6] == 100 and info[10] == 1 and info[9] == (info[1] + info[2]) * 3
+    cell, task, pos, down, ci = mesh_chains(m)
+    assert info[4] + info[5] + info[6] == 906044 - ci[6]                     # every gathering cell has a class
+    assert info[3] <= 96 and info[7] <= 24 and info[8] >= 700               # stages stay shallow: the Loire is a pipeline of reaches
+    has = (down >= 0) & (unit >= 0) & (unit[np.maximum(down, 0)] >= 0)
+    diff = unit[down[has]] != unit[has]
+    assert np.all(sigma[down[has]][diff] > sigma[has][diff])
+
+
 def test_basin_masks_partition_the_domain():
     # a France run shards by basin -- whole basins per rank, nothing gathered across ranks
     from smash_b200 import distributed as D

@@ -227,18 +227,18 @@ def _run_window(m, opts):
         return m
     finally:
         for k in opts:
-            lib.smash_b200_set_option(k.encode(), {"window_pass": 0, "shallow_acc": 32, "window_nx": 2, "window_variant": 8,
-                                                   "window_min_cells": 65536}[k])
+            lib.smash_b200_set_option(k.encode(), {"tick_pass": 0, "shallow_acc": 32, "tick_variant": 8, "tick_min_cells": 65536,
+                                                   "tick_ctas_per_sm": 0}[k])
         lib.smash_b200_clear_cache()
 
 
-@pytest.mark.parametrize("opts", [{"shallow_acc": 32}, {"shallow_acc": 3, "window_nx": 1}, {"shallow_acc": 100000, "window_variant": 6},
-                                  {"shallow_acc": 200, "window_variant": 4}])
-def test_window_pass_agrees_with_row_passes(opts):
-    # forward runs of large domains: the window pass (reservoirs + routing of the shallow cells, 8 steps at a time, discharge
-    # blocks handed over through the L2-resident exchange buffer) followed by the chain scans over the deep cells, against the
-    # row-based passes (window_pass = 0).  T = 100 ends in a partial window; shallow_acc moves the class boundary from
-    # "almost everything deep" to "everything shallow" (then the pit pairs are the only deep cells).
+@pytest.mark.parametrize("opts", [{"shallow_acc": 32}, {"shallow_acc": 3}, {"shallow_acc": 100000, "tick_variant": 6},
+                                  {"shallow_acc": 200, "tick_variant": 4}, {"shallow_acc": 1, "tick_ctas_per_sm": 2}])
+def test_tick_pass_agrees_with_row_passes(opts):
+    # forward runs of large domains: the tick pass (reservoirs + routing of every cell in one kernel, 8 steps at a time:
+    # tile tickets route the shallow cells, reach tickets the deep chains, discharge blocks handed from producer to consumer)
+    # against the row-based passes (tick_pass = 0).  T = 100 ends in a partial window; shallow_acc moves the class boundary
+    # from "every gathering cell sits in a reach" to "everything the tile rounds allow is shallow"; the crop holds pit pairs.
     def model():
         m = cases.france(T=100, sub=(250, 900, 250, 900), ngauge=4)
         random_fields(m, seed=11)
@@ -246,10 +246,10 @@ def test_window_pass_agrees_with_row_passes(opts):
         m.output = type(m.output)(m.setup, m.mesh)
         return m
     o = dict(opts)
-    o["window_min_cells"] = 1000
-    o["window_pass"] = 1
+    o["tick_min_cells"] = 1000
+    o["tick_pass"] = 1
     a = _run_window(model(), o)
-    b = _run_window(model(), {"window_pass": 0})
+    b = _run_window(model(), {"tick_pass": 0})
     assert a.mesh.nac > 100000
     for name, x, y in (("qsim", a.output.qsim, b.output.qsim), ("qdom", a.output.sparse_qsim_domain, b.output.sparse_qsim_domain),
                        ("netp", a.output.sparse_net_prcp_domain, b.output.sparse_net_prcp_domain),
@@ -260,13 +260,33 @@ def test_window_pass_agrees_with_row_passes(opts):
     assert np.isclose(float(a.output.cost), float(b.output.cost), rtol=1e-5)
 
 
-def test_window_pass_against_oracle():
+@pytest.mark.parametrize("acc", [16, 2])
+def test_tick_pass_against_oracle(acc):
     import oracle
     m = cases.france(T=50, sub=(400, 700, 400, 700), ngauge=3)
     random_fields(m, seed=13)
     c = m.copy()
     c.output = type(m.output)(m.setup, m.mesh)
-    a = _run_window(m, {"window_pass": 1, "window_min_cells": 1000, "shallow_acc": 16})
+    a = _run_window(m, {"tick_pass": 1, "tick_min_cells": 1000, "shallow_acc": acc})
+    oracle.forward(c.setup, c.mesh, c.input_data, c.parameters, c.parameters.copy(), c.states, c.states.copy(), c.output)
+    qa, qc = np.asarray(a.output.sparse_qsim_domain, np.float64), np.asarray(c.output.sparse_qsim_domain, np.float64)
+    assert np.all(np.abs(qa - qc) <= 1e-4 + 2e-3 * np.abs(qc)), float(np.abs(qa - qc).max())
+    assert np.all(np.abs(np.asarray(a.output.qsim, np.float64) - c.output.qsim) <= 1e-4 + 2e-3 * np.abs(c.output.qsim))
+    for name in ("hp", "hft", "hlr"):
+        x, y = np.asarray(getattr(a.output.fstates, name), np.float64), np.asarray(getattr(c.output.fstates, name), np.float64)
+        assert np.all(np.abs(x - y) <= 1e-5 + 2e-3 * np.abs(y)), (name, float(np.abs(x - y).max()))
+
+
+def test_tick_pass_cance_against_oracle():
+    # the whole Cance catchment through the tick pass (383 cells: 12 tiles and a few reaches), T = 1440, against the oracle
+    import oracle
+    m = cases.cance(sparse=True, T=1440)
+    random_fields(m, seed=14)
+    m.setup.save_qsim_domain = True
+    m.output = type(m.output)(m.setup, m.mesh)
+    c = m.copy()
+    c.output = type(m.output)(m.setup, m.mesh)
+    a = _run_window(m, {"tick_pass": 1, "tick_min_cells": 0, "shallow_acc": 8})
     oracle.forward(c.setup, c.mesh, c.input_data, c.parameters, c.parameters.copy(), c.states, c.states.copy(), c.output)
     qa, qc = np.asarray(a.output.sparse_qsim_domain, np.float64), np.asarray(c.output.sparse_qsim_domain, np.float64)
     assert np.all(np.abs(qa - qc) <= 1e-4 + 2e-3 * np.abs(qc)), float(np.abs(qa - qc).max())

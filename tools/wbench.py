@@ -1,4 +1,4 @@
-"""Window-pass experiments on the France mesh through the plan API: one model, several option sets.
+"""Tick-pass experiments on the France mesh through the plan API: one model, several option sets.
 usage: python tools/wbench.py [--T N] [--reps R] set1 set2 ...   with set = name=value[,name=value...] ('base' = defaults)"""
 import argparse, ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -13,7 +13,7 @@ ap.add_argument("sets", nargs="*", default=["base"])
 a = ap.parse_args()
 lib = L.lib()
 m = cases.france(T=a.T)
-DEFAULTS = {"window_pass": 0, "shallow_acc": 32, "window_nx": 2, "window_variant": 8, "window_ctas_per_sm": 0, "fuse_export": 4}
+DEFAULTS = {"tick_pass": 1, "tick_nb": 2, "tick_slack": 1, "tick_dbg": 0, "shallow_acc": 32, "tick_variant": 8, "tick_ctas_per_sm": 0, "fuse_export": 4}
 for st in a.sets:
     opts = dict(DEFAULTS)
     if st != "base":
