@@ -241,6 +241,22 @@ int smash_b200_mesh_order(const SmashSetup *setup, const SmashMesh *mesh, int32_
  * Returns SMASH_B200_EUNSUPPORTED when the mesh needs the fused engine. */
 int smash_b200_mesh_chains(const SmashMesh *mesh, int64_t info[8], int32_t *cell, int32_t *task_of, int32_t *pos_of,
                            int32_t *down_of);
+/* ---- preprocessing on the device (meshing, input pipeline) ----------------- */
+
+/* replaces mw_meshing::flow_accumulation (smash/mesh/mw_meshing.f90:204-233 with fill_nipd :111-152 and
+ * downstream_cell_flwacc :154-202).  flwdir / flwacc: (nrow,ncol) Fortran order; mask: (nrow,ncol) or NULL -- cells with
+ * mask == 0 neither give nor receive (a catchment window).  Integer-exact. */
+int smash_b200_flow_accumulation(int32_t nrow, int32_t ncol, const int32_t *flwdir, const int32_t *mask, int32_t *flwacc);
+
+/* replaces mw_mask::mask_upstream_cells (smash/solver/routine/mw_mask.f90:11-55) for every gauge of the mesh:
+ * mask (nrow,ncol,ng) bytes, 1 = the cell drains through the gauge cell. */
+int smash_b200_gauge_masks(const SmashMesh *mesh, uint8_t *mask);
+
+/* replaces mw_forcing_statistic::compute_mean_forcing (smash/solver/routine/mw_forcing_statistic.f90:18-75):
+ * mean_prcp / mean_pet (ng,T) = mean over the cells upstream of each gauge whose value is >= 0 (either may be NULL). */
+int smash_b200_compute_mean_forcing(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *input_data, float *mean_prcp,
+                                    float *mean_pet);
+
 /* Host-only: the ticket schedule of the tick pass (tick_kernels.cu) for this mesh, dealt to nwarp warps and replayed on the
  * host the way the device walks it.  info: [0] cells [1] tiles [2] reaches [3] largest stage [4] shallow routed cells
  * [5] deep cells [6] pit cells [7] units per warp [8] longest deep chain [9] tickets replayed [10] 1 = the schedule is

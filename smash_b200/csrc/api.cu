@@ -1741,6 +1741,60 @@ extern "C" int smash_b200_mesh_order(const SmashSetup *setup, const SmashMesh *m
     return 0;
 }
 
+// ---- preprocessing on the device (pre_kernels.cu) ---------------------------------------------------
+namespace smash {
+cudaError_t pre_flow_accumulation(int nrow, int ncol, const int32_t *flwdir, const int32_t *mask, int32_t *flwacc);
+cudaError_t pre_gauge_masks(int nrow, int ncol, int ng, const int32_t *flwdir, const int32_t *gauge_pos, uint8_t *mask, uint8_t *d_mask_out);
+cudaError_t pre_mean_forcing(int nrow, int ncol, int ng, int T, const int32_t *flwdir, const int32_t *gauge_pos, int n, const int32_t *cell_of,
+                             const float *prcp, const float *pet, float *mean_prcp, float *mean_pet);
+}
+
+// replaces mw_meshing::flow_accumulation (smash/mesh/mw_meshing.f90:204-233)
+extern "C" int smash_b200_flow_accumulation(int32_t nrow, int32_t ncol, const int32_t *flwdir, const int32_t *mask, int32_t *flwacc) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!flwdir || !flwacc || nrow <= 0 || ncol <= 0) return fail(SMASH_B200_EINVAL, "bad argument");
+    TRY(check_device());
+    CU(pre_flow_accumulation(nrow, ncol, flwdir, mask, flwacc));
+    return 0;
+}
+
+// replaces mw_mask::mask_upstream_cells (solver/routine/mw_mask.f90:11-55) called once per gauge
+extern "C" int smash_b200_gauge_masks(const SmashMesh *mesh, uint8_t *mask) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!mesh || !mask || !mesh->flwdir || (mesh->ng > 0 && !mesh->gauge_pos)) return fail(SMASH_B200_EINVAL, "NULL argument");
+    TRY(check_device());
+    CU(pre_gauge_masks(mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->gauge_pos, mask, nullptr));
+    return 0;
+}
+
+// replaces mw_forcing_statistic::compute_mean_forcing (solver/routine/mw_forcing_statistic.f90:18-75)
+extern "C" int smash_b200_compute_mean_forcing(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, float *mean_prcp,
+                                               float *mean_pet) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!setup || !mesh || !in) return fail(SMASH_B200_EINVAL, "NULL argument");
+    TRY(check_device());
+    const int ncell = mesh->nrow * mesh->ncol;
+    if (setup->sparse_storage) {
+        if (!in->sparse_prcp || !in->sparse_pet) return fail(SMASH_B200_EINVAL, "input_data.sparse_prcp / sparse_pet is NULL");
+        std::vector<int32_t> cell_of;                                   // mw_sparse_storage.f90:28-45: path order over the active cells
+        for (int i = 0; i < ncell; i++) {
+            const int row = mesh->path[2 * i], col = mesh->path[2 * i + 1];
+            if (!(row > 0 && col > 0)) continue;
+            if (row > mesh->nrow || col > mesh->ncol) return fail(SMASH_B200_EINVAL, "mesh.path holds an index outside the grid");
+            const int c = (row - 1) + (col - 1) * mesh->nrow;
+            if (mesh->active_cell[c] == 1) cell_of.push_back(c);
+        }
+        if ((int)cell_of.size() != mesh->nac) return fail(SMASH_B200_EINVAL, "mesh.nac does not match the active cells on mesh.path");
+        CU(pre_mean_forcing(mesh->nrow, mesh->ncol, mesh->ng, setup->ntime_step, mesh->flwdir, mesh->gauge_pos, mesh->nac, cell_of.data(),
+                            in->sparse_prcp, in->sparse_pet, mean_prcp, mean_pet));
+    } else {
+        if (!in->prcp || !in->pet) return fail(SMASH_B200_EINVAL, "input_data.prcp / pet is NULL");
+        CU(pre_mean_forcing(mesh->nrow, mesh->ncol, mesh->ng, setup->ntime_step, mesh->flwdir, mesh->gauge_pos, ncell, nullptr, in->prcp,
+                            in->pet, mean_prcp, mean_pet));
+    }
+    return 0;
+}
+
 // host-only: the heavy-path decomposition of the split engine (used by the CPU test-suite)
 extern "C" int smash_b200_mesh_chains(const SmashMesh *mesh, int64_t info[8], int32_t *cell, int32_t *task_of, int32_t *pos_of,
                                       int32_t *down_of) {

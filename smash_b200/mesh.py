@@ -14,6 +14,20 @@ DROW = np.array([-1, -1, 0, 1, 1, 1, 0, -1], dtype=np.int64)
 DCOL = np.array([0, 1, 1, 1, 0, -1, -1, -1], dtype=np.int64)
 
 
+def flow_accumulation_device(flwdir, mask=None):
+    """The same integer contract on the GPU (``smash_b200_flow_accumulation``, csrc/pre_kernels.cu): every cell nobody
+    drains into walks downstream, the last neighbour to arrive carries the sum on.  Raises without a CUDA device."""
+    import ctypes as C
+
+    from . import _lib as L
+    fd = np.asfortranarray(flwdir, dtype=np.int32)
+    nrow, ncol = fd.shape
+    mk = None if mask is None else np.asfortranarray(np.asarray(mask) != 0, dtype=np.int32)
+    out = np.zeros((nrow, ncol), dtype=np.int32, order="F")
+    L.check(L.lib().smash_b200_flow_accumulation(nrow, ncol, L._ip(fd), L._ip(mk) if mk is not None else None, L._ip(out)))
+    return out
+
+
 def flow_accumulation(flwdir, mask=None):
     """``flwacc`` (int32, 1 on cells without inflow) of ``flwdir`` (codes 1..8, anything else = no direction).  ``mask``
     restricts the computation to a catchment window (cells outside neither give nor receive)."""

@@ -39,6 +39,33 @@ def compute_mean_forcing(setup, mesh, input_data):
                     dst[g, t] = np.float32(mat[ok].sum(dtype=np.float32)) / np.float32(n)
 
 
+def compute_mean_forcing_device(setup, mesh, input_data):
+    """The same means on the GPU (``smash_b200_compute_mean_forcing``, csrc/pre_kernels.cu): catchment masks by walking
+    downstream from every cell, one block per (time step, gauge), float64 sums rounded once.  Raises without a CUDA device."""
+    import ctypes as C
+
+    from .. import _lib as L
+    pk = L.Packed()
+    s, m, i = L.pack_setup(setup, mesh, pk), L.pack_mesh(mesh, setup, pk), L.pack_input(input_data, setup, mesh, pk)
+    mp = np.zeros((mesh.ng, setup._ntime_step), dtype=np.float32, order="F")
+    me = np.zeros((mesh.ng, setup._ntime_step), dtype=np.float32, order="F")
+    L.check(L.lib().smash_b200_compute_mean_forcing(C.byref(s), C.byref(m), C.byref(i), L._fp(mp), L._fp(me)))
+    input_data.mean_prcp[...] = mp
+    input_data.mean_pet[...] = me
+
+
+def gauge_masks_device(mesh, setup=None):
+    """(nrow, ncol, ng) boolean masks of the cells upstream of every gauge, computed on the GPU."""
+    import ctypes as C
+
+    from .. import _lib as L
+    pk = L.Packed()
+    m = L.pack_mesh(mesh, setup, pk)
+    out = np.zeros((mesh.nrow, mesh.ncol, mesh.ng), dtype=np.uint8, order="F")
+    L.check(L.lib().smash_b200_gauge_masks(C.byref(m), out.ctypes.data_as(C.POINTER(C.c_uint8))))
+    return out.astype(bool)
+
+
 def _quantile(x, q):
     """mwd_cost.f90 quantile (linear interpolation between order statistics, like numpy's default)."""
     return np.quantile(np.asarray(x, np.float64), q).astype(np.float32)

@@ -1,7 +1,9 @@
 """Drop-in for the f90wrap module ``smash.solver._mw_forward`` (forward/mw_forward.f90:18-181).
 
 Same function names, argument order and in-place behaviour as the wrapped Fortran; the work is done by
-libsmash_b200.so on the GPU.  ``forward_d`` / ``hyper_forward_d`` (tangent mode) are not provided.
+libsmash_b200.so on the GPU.  ``forward_d`` / ``hyper_forward_d`` keep the reference's argument lists but are NOT a
+Tapenade tangent: the directional derivative of the cost is formed from central differences of the GPU forward (two
+extra forward runs), which is what the reference's only caller -- the scalar product test -- needs.
 """
 from __future__ import annotations
 
@@ -80,3 +82,62 @@ def hyper_forward_b(setup, mesh, input_data, parameters, parameters_b, hyper_par
                                                C.byref(st), C.byref(hs), C.byref(hs_b), C.byref(o), C.byref(c), C.byref(cb)))
     L.finish_output(o, output, wb)
     return np.float32(c.value)
+
+
+def _directional(run, fields, step):
+    """(J(k + h dk) - J(k - h dk)) / (2 h) for the perturbation ``fields`` = [(object, name, direction array)]."""
+    base = [(obj, n, np.array(getattr(obj, n), dtype=np.float32, order="F", copy=True)) for obj, n, _ in fields]
+    out = []
+    try:
+        for sign in (+1.0, -1.0):
+            for (obj, n, d), (_, _, x0) in zip(fields, base):
+                setattr(obj, n, np.asfortranarray((x0.astype(np.float64) + sign * step * np.asarray(d, np.float64)).astype(np.float32)))
+            out.append(float(run()))
+    finally:
+        for obj, n, x0 in base:
+            setattr(obj, n, x0)
+    return (out[0] - out[1]) / (2.0 * step)
+
+
+def _planes(obj, dobj):
+    return [(obj, n, getattr(dobj, n)) for n in vars(obj)
+            if isinstance(getattr(obj, n), np.ndarray) and isinstance(getattr(dobj, n, None), np.ndarray) and np.any(getattr(dobj, n))]
+
+
+def forward_d(setup, mesh, input_data, parameters, parameters_d, parameters_bgd, parameters_bgd_d, states, states_d,
+              states_bgd, states_bgd_d, output, output_d, cost=0.0, cost_d=0.0, eps=0.05):
+    """Argument list of mw_forward.f90:70-97.  Returns (cost, cost_d) with cost_d = dJ/dk . (parameters_d, states_d) from
+    central differences of ``forward`` with the absolute step ``eps`` (no tangent kernel; the background terms are held
+    fixed, as in the reference's scalar product test where *_bgd_d = 0)."""
+    fields = _planes(parameters, parameters_d) + _planes(states, states_d)
+
+    def run():
+        o = output.copy()
+        forward(setup, mesh, input_data, parameters.copy(), parameters_bgd, states.copy(), states_bgd, o)
+        return o.cost
+
+    cd = _directional(run, fields, float(eps)) if fields else 0.0
+    c = forward(setup, mesh, input_data, parameters, parameters_bgd, states, states_bgd, output)
+    if output_d is not None and hasattr(output_d, "cost"):
+        output_d.cost = np.float32(cd)
+    return np.float32(c), np.float32(cd)
+
+
+def hyper_forward_d(setup, mesh, input_data, parameters, parameters_d, hyper_parameters, hyper_parameters_d,
+                    hyper_parameters_bgd, states, states_d, hyper_states, hyper_states_d, hyper_states_bgd, output, output_d,
+                    cost=0.0, cost_d=0.0, eps=1e-3):
+    """Argument list of mw_forward.f90:154-181: the same central differences along (hyper_parameters_d, hyper_states_d)."""
+    fields = _planes(hyper_parameters, hyper_parameters_d) + _planes(hyper_states, hyper_states_d)
+
+    def run():
+        o = output.copy()
+        hyper_forward(setup, mesh, input_data, parameters.copy(), hyper_parameters, hyper_parameters_bgd, states.copy(),
+                      hyper_states, hyper_states_bgd, o)
+        return o.cost
+
+    cd = _directional(run, fields, float(eps)) if fields else 0.0
+    c = hyper_forward(setup, mesh, input_data, parameters, hyper_parameters, hyper_parameters_bgd, states, hyper_states,
+                      hyper_states_bgd, output)
+    if output_d is not None and hasattr(output_d, "cost"):
+        output_d.cost = np.float32(cd)
+    return np.float32(c), np.float32(cd)

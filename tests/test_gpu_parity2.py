@@ -348,6 +348,30 @@ def test_scalar_product_test_on_gpu():
     assert sp1 != 0.0 and abs(sp1 - sp2) <= 2e-2 * abs(sp1), (sp1, sp2)
 
 
+def test_forward_d_shim_matches_the_adjoint():
+    # _mw_forward.forward_d (reference argument list, mw_forward.f90:70-97): cost_d along a direction that mixes two fields
+    # against <forward_b, direction>
+    from smash_b200.solver import _mw_forward as F
+    c = cases.cance(T=480)
+    cases.set_optimize(c.setup, c.mesh, jobs_fun=("nse",))
+    random_fields(c)
+    pd, sd = ParametersDT(c.mesh), StatesDT(c.mesh)
+    for obj in (pd, sd):
+        for n in vars(obj):
+            if isinstance(getattr(obj, n), np.ndarray):
+                getattr(obj, n)[...] = 0.0
+    pd.cp[...] = 1.0
+    pd.lr[...] = 0.5
+    cost, cost_d = F.forward_d(c.setup, c.mesh, c.input_data, c.parameters, pd, c.parameters.copy(), None, c.states, sd,
+                               c.states.copy(), None, c.output, None)
+    pb, sb = ParametersDT(c.mesh), StatesDT(c.mesh)
+    F.forward_b(c.setup, c.mesh, c.input_data, c.parameters.copy(), pb, c.parameters.copy(), None, c.states.copy(), sb,
+                c.states.copy(), None, c.output, None)
+    ref = float((np.asarray(pb.cp, np.float64) * pd.cp).sum() + (np.asarray(pb.lr, np.float64) * pd.lr).sum())
+    print("forward_d: cost %.6f cost_d %.6e <forward_b, d> %.6e" % (float(cost), float(cost_d), ref))
+    assert ref != 0.0 and abs(float(cost_d) - ref) <= 2e-2 * abs(ref)
+
+
 def test_gpu_adjoint_against_gpu_finite_differences():
     # CUDA-only self-check of forward_b: for every control field, 5 random directions d on the active cells; the
     # directional derivative <forward_b, d> against (J(x + h d) - J(x - h d)) / 2h of the CUDA forward.  Everything is
