@@ -187,6 +187,8 @@ std::string build_route_graph(RouteGraph &g, int nrow, int ncol, int ng, const i
             g.max_chain = std::max(g.max_chain, (int)chains[ci].size());
         }
     }
+    // the reverse sweep publishes the cells a chain has finished in the low 16 bits of its progress word (split_kernels.cu)
+    if (g.max_chain >= 0xfff0) return "unsupported: a heavy-path chain of 65520 cells or more";
     // Task order: by the topological level of the chain's last cell (level = cells on the longest path from a source to the
     // cell).  A chain's tributaries end at a lower level than the cell they join, so this is a dependency order, and it is
     // the order in which the serial walks down the rivers need their tributaries: what joins the upper reaches comes first.

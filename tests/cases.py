@@ -221,5 +221,44 @@ def france(T=24, seed=0, sub=None, ngauge=0, nd=0, qobs_from_oracle=True):
     return model
 
 
+def from_flwdir(flwdir, T=24, seed=0, ngauge=0, dx=1000.0):
+    """A model on an arbitrary D8 raster (codes 1..8, anything else = not a cell): flow accumulation by the host restatement
+    of the meshing step, path = stable argsort of flwacc (meshing.py:216-218), sparse synthetic forcing, gauges on the cells
+    with the largest flow accumulation."""
+    from smash_b200.mesh import flow_accumulation
+    flwdir = np.asarray(flwdir, dtype=np.int32)
+    nrow, ncol = flwdir.shape
+    active = ((flwdir >= 1) & (flwdir <= 8)).astype(np.int32)
+    flwacc = flow_accumulation(flwdir, mask=active == 1)
+    order = np.argsort(np.where(active == 1, flwacc, np.iinfo(np.int32).max).ravel(), kind="stable")[: int(active.sum())]
+    pr, pc = np.unravel_index(order, flwdir.shape)
+    setup = SetupDT(nd=0, ng=ngauge)
+    setup.sparse_storage = True
+    setup._ntime_step = int(T)
+    setup.save_qsim_domain = True
+    mesh = MeshDT(setup, nrow, ncol, ngauge)
+    mesh.dx = np.float32(dx)
+    mesh.flwdir = np.asfortranarray(flwdir)
+    mesh.flwacc = np.asfortranarray(flwacc)
+    mesh.active_cell = np.asfortranarray(active)
+    mesh._local_active_cell = np.asfortranarray(active.copy())
+    full = np.full((2, nrow * ncol), -100, dtype=np.int32)
+    full[0, :pr.size], full[1, :pr.size] = pr, pc
+    mesh.path = np.asfortranarray(full)
+    mesh.nac = int(active.sum())
+    compute_rowcol_to_ind_sparse(mesh)
+    if ngauge > 0:
+        fa = np.where(active == 1, flwacc, 0)
+        flat = np.argsort(fa.ravel(), kind="stable")[::-1][:ngauge]
+        gr, gc = np.unravel_index(flat, fa.shape)
+        mesh.gauge_pos = np.asfortranarray(np.stack([gr, gc], axis=1).astype(np.int32))
+        mesh.area = (flwacc[gr, gc].astype(np.float32) * mesh.dx * mesh.dx).astype(np.float32)
+    inp = Input_DataDT(setup, mesh)
+    inp.sparse_prcp, inp.sparse_pet = synthetic_forcing(mesh.nac, T, seed)
+    par, st, out = ParametersDT(mesh), StatesDT(mesh), OutputDT(setup, mesh)
+    set_optimize(setup, mesh, jobs_fun=(), gauge="all")
+    return Model(setup, mesh, inp, par, st, out)
+
+
 def hyper_objects(model):
     return Hyper_ParametersDT(model.setup), Hyper_StatesDT(model.setup)

@@ -141,3 +141,29 @@ def test_errors_at_the_boundary():
     with pytest.raises(RuntimeError):
         smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
     L.lib().smash_b200_clear_cache()
+
+
+@pytest.mark.parametrize("shape", ["channel", "comb"])
+def test_meshes_whose_chains_are_all_long(shape):
+    # a straight 1 x 200 channel (one heavy-path chain of 199 routed cells: every chain is a "dedicated" one, no ticketed
+    # chain at all) and a comb of such channels joined by a trunk; domain discharge, gauge series and final states against
+    # the oracle.  The routing pass must keep a CTA for the export tiles when every chain has a CTA of its own.
+    if shape == "channel":
+        fd = np.full((1, 200), 3, dtype=np.int32)                        # code 3: east
+    else:
+        fd = np.full((150, 120), 3, dtype=np.int32)                      # every row flows east into the last column ...
+        fd[:, -1] = 5                                                    # ... which flows south
+        fd[::2, :] = 0                                                   # every other row is not a cell
+        fd[:, -1] = 5
+    a, b = cases.from_flwdir(fd, T=96, seed=4, ngauge=2), cases.from_flwdir(fd, T=96, seed=4, ngauge=2)
+    for m in (a, b):
+        random_fields(m, seed=8)
+    smash_b200.forward(a.setup, a.mesh, a.input_data, a.parameters, a.parameters.copy(), a.states, a.states.copy(), a.output)
+    oracle.forward(b.setup, b.mesh, b.input_data, b.parameters, b.parameters.copy(), b.states, b.states.copy(), b.output)
+    assert float(np.abs(b.output.sparse_qsim_domain).max()) > 0
+    assert close_q(a.output.sparse_qsim_domain, b.output.sparse_qsim_domain)
+    assert close_q(a.output.qsim, b.output.qsim)
+    for n in ("hp", "hft", "hlr"):
+        x, y = np.asarray(getattr(a.output.fstates, n), np.float64), np.asarray(getattr(b.output.fstates, n), np.float64)
+        assert np.all(np.abs(x - y) <= 1e-5 + 2e-3 * np.abs(y)), n
+    L.lib().smash_b200_clear_cache()
