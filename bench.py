@@ -423,8 +423,8 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
         pass
     step_bytes = 12.0 * units
     pk_ms = np.mean(np.array(per_kernel), axis=0)
-    window_pass = lib.smash_b200_plan_stat(plan, b"window_pass") == 1.0
-    names = ["window_forward_kernel" if window_pass else "vertical_forward_kernel", "route_forward_kernel", "rows_to_domain_kernel"]
+    window_pass = lib.smash_b200_plan_stat(plan, b"tick_pass") == 1.0
+    names = ["tick_forward_kernel" if window_pass else "vertical_forward_kernel", "route_forward_kernel", "rows_to_domain_kernel"]
     kernels = {names[i]: {"ms": float(pk_ms[i]), "share": float(pk_ms[i] / kms), "dram_traffic_bytes": traffic.get(names[i])}
                for i in range(3) if pk_ms[i] > 0.02}
     tr = [k["dram_traffic_bytes"] for k in kernels.values()]
@@ -454,6 +454,31 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
                     "kernels_ms": {"vertical_forward_kernel(tape)": float(gk[0]), "route_forward_kernel(tape)": float(gk[1]),
                                    "route_adjoint_kernel": float(gk[3]), "vertical_adjoint_kernel": float(gk[4])}}
     lib.smash_b200_plan_destroy(plan)
+
+    # ---- the measured alternative: the tick pass (one kernel for reservoirs + routing, opt-in), same workload
+    if not args.no_extra:
+        lib.smash_b200_set_option(b"tick_pass", 1)
+        try:
+            plan2 = C.c_void_p()
+            L.check(lib.smash_b200_plan_create(C.byref(s_), C.byref(m_), 1, C.byref(plan2)))
+            L.check(lib.smash_b200_plan_set_forcing(plan2, C.byref(s_), C.byref(i_)))
+            L.check(lib.smash_b200_plan_set_fields(plan2, C.byref(p_), C.byref(st_), None, None, 0))
+            tms = []
+            for k in range(args.warmup + 5):
+                L.check(lib.smash_b200_plan_run_forward(plan2, C.byref(ms)))
+                if k >= args.warmup:
+                    tms.append(ms.value)
+            chk2 = C.c_double(0.0)
+            L.check(lib.smash_b200_plan_checksum(plan2, C.byref(chk2)))
+            on = lib.smash_b200_plan_stat(plan2, b"tick_pass") == 1.0
+            lib.smash_b200_plan_destroy(plan2)
+            roofline["alternatives"] = {"tick_pass": {
+                "ran": bool(on), "ms_per_step": float(np.mean(tms)), "frac": step_bytes / (float(np.mean(tms)) * 1e-3) / 1e9 / peak,
+                "dram_traffic_bytes": traffic.get("tick_forward_kernel"), "checksum_q": chk2.value,
+                "note": "opt-in (option tick_pass): every cell advances 8 steps per ticket, discharge blocks handed from producer to "
+                        "consumer; bound by the latency of a ticket, see DESIGN.md section 3b"}}
+        finally:
+            lib.smash_b200_set_option(b"tick_pass", 0)
 
     # ---- e2e through the drop-in call with host buffers
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
@@ -496,7 +521,7 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
         "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"France 1km mesh forward gr-a, nac={nac}, T={T}, save_qsim_domain (setup_France.yaml)",
-                   "engine": "split: " + ("window pass (reservoirs + shallow routing) + chain scans over the deep cells" if window_pass
+                   "engine": "split: " + ("tick pass (reservoirs + routing in one kernel)" if window_pass
                                           else "reservoir pass per cell + routing scan per heavy-path chain"),
                    "pit_pairs": int(info[6]), "l2": "inputs larger than L2 (5.2 GB forcing streamed once per step)",
                    "parallelism": "1 GPU", "checksum_q": chk.value, "model_build_s": t_build},
