@@ -257,6 +257,17 @@ int smash_b200_gauge_masks(const SmashMesh *mesh, uint8_t *mask);
 int smash_b200_compute_mean_forcing(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *input_data, float *mean_prcp,
                                     float *mean_pet);
 
+/* ---- the ANN mapping's Dense layers on the tensor cores --------------------- */
+
+/* replaces Net._forward_pass (smash/core/net.py:281-299) for a chain of Dense (+ Activation) layers (net.py:579-688, 458-498):
+ * y = act_L(... act_1(x W_1 + b_1) ...) with every contraction a TF32 tcgen05 GEMM (float32 accumulation) and bias + activation
+ * fused into its epilogue; the whole chain stays on the device.
+ * x (nrows, sizes[0]) row-major host array; weight[l] (sizes[l], sizes[l+1]) row-major; bias[l] (sizes[l+1]);
+ * activation[l]: 0 none, 1 relu, 2 sigmoid, 3 tanh, 4 leaky_relu(0.2), 5 elu(0.1), 6 selu, 7 softplus; y (nrows, sizes[nlayer]).
+ * ms / flops (may be NULL): device time of the layers and 2 x multiply-adds. */
+int smash_b200_mlp_forward(int64_t nrows, int32_t nlayer, const int32_t *sizes, const float *x, const float *const *weight,
+                           const float *const *bias, const int32_t *activation, float *y, float *ms, double *flops);
+
 /* Host-only: the ticket schedule of the tick pass (tick_kernels.cu) for this mesh, dealt to nwarp warps and replayed on the
  * host the way the device walks it.  info: [0] cells [1] tiles [2] reaches [3] largest stage [4] shallow routed cells
  * [5] deep cells [6] pit cells [7] units per warp [8] longest deep chain [9] tickets replayed [10] 1 = the schedule is

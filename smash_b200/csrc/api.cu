@@ -1795,6 +1795,23 @@ extern "C" int smash_b200_compute_mean_forcing(const SmashSetup *setup, const Sm
     return 0;
 }
 
+// ---- the network's Dense layers on the tensor cores (dense_tc.cu) -----------------------------------
+namespace smash {
+const char *mlp_forward_device(int64_t M, int nlayer, const int32_t *sizes, const float *x, const float *const *W, const float *const *b,
+                               const int32_t *act, float *y, float *ms, double *flops);
+}
+
+// replaces the forward pass of Net (smash/core/net.py:281-299, Dense :664-670, Activation :478-482) for Dense (+ activation) chains
+extern "C" int smash_b200_mlp_forward(int64_t nrows, int32_t nlayer, const int32_t *sizes, const float *x, const float *const *weight,
+                                      const float *const *bias, const int32_t *activation, float *y, float *ms, double *flops) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!sizes || !x || !weight || !bias || !activation || !y) return fail(SMASH_B200_EINVAL, "NULL argument");
+    TRY(check_device());
+    const char *err = mlp_forward_device(nrows, nlayer, sizes, x, weight, bias, activation, y, ms, flops);
+    if (err) return fail(SMASH_B200_ECUDA, "%s", err);
+    return 0;
+}
+
 // host-only: the heavy-path decomposition of the split engine (used by the CPU test-suite)
 extern "C" int smash_b200_mesh_chains(const SmashMesh *mesh, int64_t info[8], int32_t *cell, int32_t *task_of, int32_t *pos_of,
                                       int32_t *down_of) {
