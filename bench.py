@@ -480,6 +480,36 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
         finally:
             lib.smash_b200_set_option(b"tick_pass", 0)
 
+    # ---- the ANN mapping's forward pass at France scale: the graph of _ann_optimize.py:143-168 for nd = 6 descriptors
+    ann = None
+    if not args.no_extra:
+        from smash_b200.net import Net
+        nd_, n1 = 6, int(round(np.sqrt(nac * 6) * 2 / 3))
+        net = Net()
+        net.add("dense", {"input_shape": (nd_,), "neurons": n1, "kernel_initializer": "glorot_uniform"})
+        net.add("activation", {"name": "relu"})
+        net.add("dense", {"neurons": round(n1 / 2), "kernel_initializer": "glorot_uniform"})
+        net.add("activation", {"name": "relu"})
+        net.add("dense", {"neurons": 4, "kernel_initializer": "glorot_uniform"})
+        net.add("activation", {"name": "sigmoid"})
+        net.compile("adam", {"learning_rate": 0.003}, random_state=11)
+        xd = np.random.default_rng(3).uniform(0.0, 1.0, (nac, nd_)).astype(np.float32)
+        tm, best = {}, None
+        for _ in range(3):
+            yd = net._predict_device(xd, timing=tm)
+            best = dict(tm) if best is None or tm["ms"] < best["ms"] else best
+        ref = net._predict(xd[:2000].astype(np.float64))
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                bf16 = float(json.load(f)["bf16_tflops"])
+        except Exception:
+            bf16 = 2250.0
+        ann = {"rows": nac, "graph": [nd_, n1, round(n1 / 2), 4], "device_ms": best["ms"], "tflops": best["tflops"], "dtype": "tf32 (f32 accumulate)",
+               "frac_of_tf32_peak": best["tflops"] / (bf16 / 2.0), "tf32_peak_tflops": bf16 / 2.0,
+               "peak_source": "half the measured dense bf16 rate of MEASURED_PEAKS.json (TF32 runs at half the bf16 rate)",
+               "max_abs_err_vs_numpy_f64": float(np.abs(yd[:2000] - ref).max()),
+               "kernel": "CUTLASS sm100 collective (TMA + tcgen05.mma kind::tf32, accumulators in TMEM), bias + activation fused"}
+
     # ---- e2e through the drop-in call with host buffers
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     model.input_data._forcing_version = 0
@@ -526,7 +556,7 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
                    "pit_pairs": int(info[6]), "l2": "inputs larger than L2 (5.2 GB forcing streamed once per step)",
                    "parallelism": "1 GPU", "checksum_q": chk.value, "model_build_s": t_build},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
-        "gradient": gradient,
+        "gradient": gradient, "ann_dense": ann,
     }
     if not args.no_extra:
         ens = bench_ensemble(lib, L, smash_b200, cases, None, 0, 1, max(2, min(5, args.steps)), 1)

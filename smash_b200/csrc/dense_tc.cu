@@ -43,8 +43,14 @@ struct DenseGemm {
     static constexpr int Align = 4;                                       // 16 bytes: what TMA needs of every leading dimension
     using Arch = cutlass::arch::Sm100;
     using OpClass = cutlass::arch::OpClassTensorOp;
-    using TileShape = Shape<_128, _128, _32>;                             // one tcgen05 tile per CTA, 128 bytes of K per stage
-    using ClusterShape = Shape<_1, _1, _1>;
+#ifndef DENSE_TILE_M
+#define DENSE_TILE_M _256
+#define DENSE_TILE_N _128
+#define DENSE_TILE_K _32
+#define DENSE_CLUSTER_M _2
+#endif
+    using TileShape = Shape<DENSE_TILE_M, DENSE_TILE_N, DENSE_TILE_K>;    // 256 x 128: one tcgen05.mma.cta_group::2 tile per CTA pair
+    using ClusterShape = Shape<DENSE_CLUSTER_M, _1, _1>;
     using Fusion = cutlass::epilogue::fusion::LinCombPerColBiasEltAct<Act, Element, float, float>;
     using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
         Arch, OpClass, TileShape, ClusterShape, cutlass::epilogue::collective::EpilogueTileAuto, float, float, Element, LayoutC, Align,
