@@ -268,6 +268,19 @@ int smash_b200_compute_mean_forcing(const SmashSetup *setup, const SmashMesh *me
 int smash_b200_mlp_forward(int64_t nrows, int32_t nlayer, const int32_t *sizes, const float *x, const float *const *weight,
                            const float *const *bias, const int32_t *activation, float *y, float *ms, double *flops);
 
+/* The same chain kept on the device between the forward and the backward pass of a training epoch (Net._fit_d2p,
+ * smash/core/net.py:353-415).  run_forward: x may be NULL after the first call (the rows stay on the device); y may be NULL.
+ * run_backward replaces Net._backward_pass (net.py:301-303) for the chain: from grad_y = d loss / d y (nrows, sizes[nlayer]) it
+ * returns grad_weight[l] (sizes[l], sizes[l+1]) = a_l^T g and grad_bias[l] (sizes[l+1]) = column sums of g
+ * (Dense._backward_pass net.py:672-685; the optimiser update stays with the caller), g being pushed back through the
+ * activations and W^T layer by layer; both contractions are TF32 tensor-core GEMMs. */
+typedef struct SmashMlp SmashMlp;
+int smash_b200_mlp_create(int64_t nrows, int32_t nlayer, const int32_t *sizes, const int32_t *activation, SmashMlp **mlp);
+void smash_b200_mlp_destroy(SmashMlp *mlp);
+int smash_b200_mlp_run_forward(SmashMlp *mlp, const float *x, const float *const *weight, const float *const *bias, float *y, float *ms,
+                               double *flops);
+int smash_b200_mlp_run_backward(SmashMlp *mlp, const float *grad_y, float *const *grad_weight, float *const *grad_bias, float *ms);
+
 /* Host-only: the ticket schedule of the tick pass (tick_kernels.cu) for this mesh, dealt to nwarp warps and replayed on the
  * host the way the device walks it.  info: [0] cells [1] tiles [2] reaches [3] largest stage [4] shallow routed cells
  * [5] deep cells [6] pit cells [7] units per warp [8] longest deep chain [9] tickets replayed [10] 1 = the schedule is

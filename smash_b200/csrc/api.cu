@@ -1797,6 +1797,11 @@ extern "C" int smash_b200_compute_mean_forcing(const SmashSetup *setup, const Sm
 
 // ---- the network's Dense layers on the tensor cores (dense_tc.cu) -----------------------------------
 namespace smash {
+struct Mlp;
+const char *mlp_create(int64_t M, int nlayer, const int32_t *sizes, const int32_t *act, Mlp **out);
+void mlp_destroy(Mlp *m);
+const char *mlp_forward(Mlp &m, const float *x, const float *const *W, const float *const *b, float *y, float *ms, double *flops);
+const char *mlp_backward(Mlp &m, const float *gy, float *const *gW, float *const *gb, float *ms);
 const char *mlp_forward_device(int64_t M, int nlayer, const int32_t *sizes, const float *x, const float *const *W, const float *const *b,
                                const int32_t *act, float *y, float *ms, double *flops);
 }
@@ -1808,6 +1813,34 @@ extern "C" int smash_b200_mlp_forward(int64_t nrows, int32_t nlayer, const int32
     if (!sizes || !x || !weight || !bias || !activation || !y) return fail(SMASH_B200_EINVAL, "NULL argument");
     TRY(check_device());
     const char *err = mlp_forward_device(nrows, nlayer, sizes, x, weight, bias, activation, y, ms, flops);
+    if (err) return fail(SMASH_B200_ECUDA, "%s", err);
+    return 0;
+}
+
+// the same chain kept on the device between the forward and the backward pass of a training epoch (Net._fit_d2p net.py:353-415)
+extern "C" int smash_b200_mlp_create(int64_t nrows, int32_t nlayer, const int32_t *sizes, const int32_t *activation, SmashMlp **mlp) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!sizes || !activation || !mlp) return fail(SMASH_B200_EINVAL, "NULL argument");
+    TRY(check_device());
+    Mlp *m = nullptr;
+    const char *err = mlp_create(nrows, nlayer, sizes, activation, &m);
+    if (err) return fail(SMASH_B200_ECUDA, "%s", err);
+    *mlp = reinterpret_cast<SmashMlp *>(m);
+    return 0;
+}
+extern "C" void smash_b200_mlp_destroy(SmashMlp *mlp) { mlp_destroy(reinterpret_cast<Mlp *>(mlp)); }
+extern "C" int smash_b200_mlp_run_forward(SmashMlp *mlp, const float *x, const float *const *weight, const float *const *bias, float *y,
+                                          float *ms, double *flops) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!mlp || !weight || !bias) return fail(SMASH_B200_EINVAL, "NULL argument");
+    const char *err = mlp_forward(*reinterpret_cast<Mlp *>(mlp), x, weight, bias, y, ms, flops);
+    if (err) return fail(SMASH_B200_ECUDA, "%s", err);
+    return 0;
+}
+extern "C" int smash_b200_mlp_run_backward(SmashMlp *mlp, const float *grad_y, float *const *grad_weight, float *const *grad_bias, float *ms) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!mlp || !grad_y || !grad_weight || !grad_bias) return fail(SMASH_B200_EINVAL, "NULL argument");
+    const char *err = mlp_backward(*reinterpret_cast<Mlp *>(mlp), grad_y, grad_weight, grad_bias, ms);
     if (err) return fail(SMASH_B200_ECUDA, "%s", err);
     return 0;
 }

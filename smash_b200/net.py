@@ -357,6 +357,19 @@ class Net:
     def _predict(self, x):
         return self._forward_pass(x, training=False)
 
+    def _device_chain(self):
+        """The leading Dense (+ Activation) layers that smash_b200_mlp_* can run: [(dense, activation layer or None, code)],
+        and the index of the first layer after the chain."""
+        chain, i = [], 0
+        while i < len(self.layers) and isinstance(self.layers[i], Dense):
+            code, actl = 0, None
+            nxt = self.layers[i + 1] if i + 1 < len(self.layers) else None
+            if isinstance(nxt, Activation) and type(nxt._f).__name__ in self._DEVICE_ACT:
+                code, actl = self._DEVICE_ACT[type(nxt._f).__name__], nxt
+            chain.append((self.layers[i], actl, code))
+            i += 2 if code else 1
+        return chain, i
+
     # activation codes of smash_b200_mlp_forward (include/smash_b200.h)
     _DEVICE_ACT = {"_ReLU": 1, "_Sigmoid": 2, "_TanH": 3, "_LeakyReLU": 4, "_ELU": 5, "_SELU": 6, "_SoftPlus": 7}
 
@@ -369,14 +382,8 @@ class Net:
         import ctypes as C
 
         from . import _lib as L
-        chain, i = [], 0
-        while i < len(self.layers) and isinstance(self.layers[i], Dense):
-            act = 0
-            nxt = self.layers[i + 1] if i + 1 < len(self.layers) else None
-            if isinstance(nxt, Activation) and type(nxt._f).__name__ in self._DEVICE_ACT:
-                act = self._DEVICE_ACT[type(nxt._f).__name__]
-            chain.append((self.layers[i], act))
-            i += 2 if act else 1
+        chain3, i = self._device_chain()
+        chain = [(d, c) for d, _, c in chain3]
         if not chain:
             return self._predict(x)
         x32 = np.ascontiguousarray(x, dtype=np.float32)
@@ -397,13 +404,15 @@ class Net:
         return out
 
     def _fit_d2p(self, x_train, instance, control_vector, mask, parameters_bgd, states_bgd, epochs, early_stopping, verbose,
-                 solver=None):
-        """net.py:353-415"""
+                 solver=None, device=False):
+        """net.py:353-415.  device = True: the Dense / Activation chain runs on the GPU's tensor cores (DeviceChain), forward and
+        backward; meant for domain-sized inputs."""
         if not self._compiled:
             raise ValueError("The network has not been compiled yet")
         loss_opt = 0
+        dev = DeviceChain(self, x_train) if device else None
         for epo in range(epochs):
-            y_pred = self._forward_pass(x_train)
+            y_pred = dev.forward() if dev else self._forward_pass(x_train)
             loss_grad = _hcost_prime(y_pred, control_vector, mask, instance, parameters_bgd, states_bgd, solver)
             loss = instance.output.cost
             if early_stopping and (loss_opt > loss or epo == 0):
@@ -411,14 +420,93 @@ class Net:
                 for layer in self.layers:
                     if hasattr(layer, "_initialize"):
                         layer._weight, layer._bias = np.copy(layer.weight), np.copy(layer.bias)
-            self._backward_pass(loss_grad)
+            if dev:
+                dev.backward(loss_grad)
+            else:
+                self._backward_pass(loss_grad)
             if verbose:
                 print(f"    At epoch    {epo + 1:3}    J ={loss:10.6f}    |proj g| ={np.amax(np.abs(loss_grad)):10.6f}")
             self.history["loss_train"].append(loss)
+        if dev:
+            dev.close()
         if early_stopping:
             for layer in self.layers:
                 if hasattr(layer, "_initialize"):
                     layer.weight, layer.bias = np.copy(layer._weight), np.copy(layer._bias)
+
+
+class DeviceChain:
+    """The network's leading Dense (+ Activation) layers resident on the GPU for a training run (``smash_b200_mlp_create`` /
+    ``run_forward`` / ``run_backward``, csrc/dense_tc.cu): the rows go up once, every epoch uploads the weights, runs the
+    forward pass on the tensor cores, and -- from the gradient of the loss with respect to the chain's output -- returns
+    grad_weight / grad_bias of every Dense layer; the optimiser update stays on the host (Dense._backward_pass, net.py:672-685).
+    TF32 operands with float32 accumulation: gradients agree with the float64 NumPy backward pass to about 1e-3 of their
+    scale (tests/test_gpu_dense.py)."""
+
+    def __init__(self, net, x):
+        import ctypes as C
+
+        from . import _lib as L
+        self._C, self._L = C, L
+        self.net = net
+        self.chain, self.after = net._device_chain()
+        if not self.chain:
+            raise ValueError("the network does not start with a Dense layer")
+        self.x = np.ascontiguousarray(x, dtype=np.float32)
+        self.sizes = np.array([self.x.shape[1]] + [d.neurons for d, _, _ in self.chain], dtype=np.int32)
+        self.acts = np.array([c for _, _, c in self.chain], dtype=np.int32)
+        self.h = C.c_void_p()
+        L.check(L.lib().smash_b200_mlp_create(C.c_int64(self.x.shape[0]), len(self.chain), L._ip(self.sizes), L._ip(self.acts), C.byref(self.h)))
+        self._first = True
+        self.ms_forward = self.ms_backward = 0.0
+
+    def close(self):
+        if self.h:
+            self._L.lib().smash_b200_mlp_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ptrs(self, arrays):
+        return (self._C.POINTER(self._C.c_float) * len(arrays))(*[self._L._fp(a) for a in arrays])
+
+    def forward(self):
+        C, L = self._C, self._L
+        ws = [np.ascontiguousarray(d.weight, dtype=np.float32) for d, _, _ in self.chain]
+        bs = [np.ascontiguousarray(np.ravel(d.bias), dtype=np.float32) for d, _, _ in self.chain]
+        y = np.empty((self.x.shape[0], int(self.sizes[-1])), dtype=np.float32)
+        ms, fl = C.c_float(0.0), C.c_double(0.0)
+        L.check(L.lib().smash_b200_mlp_run_forward(self.h, L._fp(self.x) if self._first else None, self._ptrs(ws), self._ptrs(bs), L._fp(y),
+                                                   C.byref(ms), C.byref(fl)))
+        self._first = False
+        self.ms_forward = float(ms.value)
+        out = y.astype(np.float64)
+        for layer in self.net.layers[self.after:]:
+            out = layer._forward_pass(out, True)
+        return out
+
+    def backward(self, loss_grad):
+        """Net._backward_pass (net.py:301-303): the layers after the chain on the host, the chain on the device, then the
+        optimiser updates in the reference's order (last layer first)."""
+        C, L = self._C, self._L
+        g = loss_grad
+        for layer in reversed(self.net.layers[self.after:]):
+            g = layer._backward_pass(g)
+        gy = np.ascontiguousarray(g, dtype=np.float32)
+        gws = [np.zeros((int(self.sizes[l]), int(self.sizes[l + 1])), dtype=np.float32) for l in range(len(self.chain))]
+        gbs = [np.zeros(int(self.sizes[l + 1]), dtype=np.float32) for l in range(len(self.chain))]
+        ms = C.c_float(0.0)
+        L.check(L.lib().smash_b200_mlp_run_backward(self.h, L._fp(gy), self._ptrs(gws), self._ptrs(gbs), C.byref(ms)))
+        self.ms_backward = float(ms.value)
+        for (dense, _, _), gw, gb in reversed(list(zip(self.chain, gws, gbs))):
+            if dense.trainable:
+                dense.weight = dense._weight_opt.update(dense.weight, gw.astype(np.float64))
+                dense.bias = dense._bias_opt.update(dense.bias, gb.astype(np.float64)[None, :])
+        return gws, gbs
 
 
 def _hcost_prime(y, control_vector, mask, instance, parameters_bgd, states_bgd, solver=None):

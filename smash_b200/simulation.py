@@ -571,9 +571,10 @@ def bayes_optimize(model, sample=None, alpha=4, n=1000, random_state=None, de_bw
 
 def ann_optimize(model, net=None, optimizer="adam", learning_rate=0.003, control_vector=None, bounds=None, jobs_fun="nse",
                  wjobs_fun=None, gauge="downstream", wgauge="mean", ost_step=0, epochs=400, early_stopping=False,
-                 random_state=None, verbose=False, inplace=False, return_net=False, solver=None):
+                 random_state=None, verbose=False, inplace=False, return_net=False, solver=None, device_net=False):
     """Model.ann_optimize (model.py:1223-1420, simulation/_ann_optimize.py:20-254): a network maps the normalised
-    descriptors of the active cells to the control fields; every epoch is one ``forward_b`` on the GPU."""
+    descriptors of the active cells to the control fields; every epoch is one ``forward_b`` on the GPU.  ``device_net``: the
+    network's Dense / Activation layers run on the GPU's tensor cores too (net.DeviceChain), for domain-sized inputs."""
     from .net import Net
     inst = model if inplace else model.copy()
     _, cv = _setup_optimize(inst, "uniform", "sbs", control_vector, bounds, jobs_fun, wjobs_fun, gauge, wgauge, ost_step, verbose)
@@ -612,7 +613,8 @@ def ann_optimize(model, net=None, optimizer="adam", learning_rate=0.003, control
         if net.layers[-1].output_shape()[0] != cv.size:
             raise ValueError(f"Inconsistent value between the number of output layer ({net.layers[-1].output_shape()}) and "
                              f"the number of control vectors ({cv.size})")
-    net._fit_d2p(x_train, inst, cv, active, parameters_bgd, states_bgd, epochs, early_stopping, verbose, solver=solver)
+    net._fit_d2p(x_train, inst, cv, active, parameters_bgd, states_bgd, epochs, early_stopping, verbose, solver=solver,
+                 device=device_net)
     y = net._predict(x_inactive)                                         # predicted maps on the inactive cells
     for i, name in enumerate(cv):
         getattr(inst.parameters if name in GPARAMETERS_NAME else inst.states, name)[inactive] = y[:, i]

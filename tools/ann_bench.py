@@ -22,3 +22,15 @@ for _ in range(3):
     print("rows %d graph 6-%d-%d-4: %.3f ms, %.1f TFLOP/s" % (rows, n1, round(n1 / 2), t["ms"], t["tflops"]), flush=True)
 ref = net._predict(x[:2000].astype(np.float64))
 print("max abs err vs numpy f64 (first 2000 rows):", float(np.abs(y[:2000] - ref).max()))
+
+# one training step with the chain resident on the device: forward + backward (grad_weight, grad_bias of every Dense layer)
+from smash_b200.net import DeviceChain
+dev = DeviceChain(net, x)
+gy = np.random.default_rng(4).uniform(0.5, 1.5, (rows, 4)).astype(np.float32) * 1e-6
+for _ in range(3):
+    dev.forward()
+    dev.backward(gy)
+    fl = 2.0 * rows * (6 * n1 + n1 * round(n1 / 2) + round(n1 / 2) * 4)
+    print("training step: forward %.3f ms, backward %.3f ms (%.1f TFLOP/s over 2 contractions per layer)" %
+          (dev.ms_forward, dev.ms_backward, 2 * fl / dev.ms_backward * 1e-9), flush=True)
+dev.close()
