@@ -128,6 +128,22 @@ struct WindowState {
     TkTopo topo{};
 };
 
+// subtree engine (sub_kernels.cu): one pass over the forcing with the engine's own cell order; pit pairs afterwards from rows
+struct SubState {
+    bool on = false, have_forcing = false;
+    SubTopoHost host;
+    SplitState pits;               // route graph of the pit pairs and its device image
+    int npad2 = 0;
+    DBuf<int32_t> d_cell, d_rec, d_xout, d_extoff, d_extlist, d_idx_raw, d_pit_to_engine;
+    DBuf<uint32_t> d_child;
+    DBuf<uint8_t> d_kmax, d_ext;
+    DBuf<float> d_X, d_pk_prcp, d_pk_pet, d_qdom, d_netp;
+    DBuf<int> d_err;
+    CUtensorMap tm_prcp, tm_pet;
+    std::vector<int32_t> idx_sparse, idx_dense;   // raw forcing column of every engine column (-1 on empty lanes)
+    SbTopo topo{};
+};
+
 // Opt-in (option "pin_host" = 1): large caller-owned host arrays (forcing in, domain series out) are page-locked in place
 // the first time they are seen (cudaHostRegister), so that the copies run at PCIe speed; the registration is remembered
 // by address until smash_b200_clear_cache().  The caller promises not to free such an array before clearing the cache
@@ -164,6 +180,8 @@ struct SmashPlan {
     bool ensemble = false;          // plan made for compute_multiple_run / a multi-member plan: lane = member routing
     SplitState sp;
     WindowState win;
+    SubState sub;
+    bool sub_ran = false;           // the last forward sweep was the subtree engine: its error word is checked at the next synchronisation
     std::vector<int32_t> col_cell;  // per device column (slot / cell j): flat rect index or -1 on padding
     int ncols = 0;                  // columns of the per-cell device arrays (fields, fstates, grad)
     int nmember = 0;
@@ -443,6 +461,49 @@ static int window_build(SmashPlan &pl, const SmashMesh *mesh) {
     return 0;
 }
 
+// ---- subtree engine: tiles, exchange slots, pit-pair graph --------------------------------------------
+// Forward runs of large domains (no tape, one member, math = 1), option sub_engine.  Not eligible: sub.on stays false.
+static int sub_build(SmashPlan &pl, const SmashMesh *mesh) {
+    SubState &sb = pl.sub;
+    const RouteGraph &rg = pl.sp.rg;
+    sb.on = false;
+    if (!option("sub_engine", 0) || rg.n < option("sub_min_cells", 65536)) return 0;
+    if (!build_sub_topo(rg, 8, sb.host).empty()) return 0;
+    cudaStream_t s = pl.stream;
+    const size_t npad = (size_t)rg.npad;
+    sb.npad2 = sb.host.ntile * 32;
+    if (sb.host.pair_cells > 0) {
+        std::string err = build_route_graph(sb.pits.rg, mesh->nrow, mesh->ncol, mesh->ng, mesh->flwdir, mesh->flwacc, mesh->active_cell,
+                                            mesh->local_active_cell, mesh->path, mesh->gauge_pos, (int)option("route_ded_min", 96),
+                                            (int)option("route_ded_max", 64), 0, 0, sb.host.pair.data());
+        if (!err.empty() || sb.pits.rg.n != rg.n || sb.pits.rg.nchain != 0) return 0;
+        TRY(upload_route_graph(sb.pits, mesh->ng, s));
+        std::vector<uint8_t> mask(npad, 0);
+        std::copy(sb.host.pair.begin(), sb.host.pair.end(), mask.begin());
+        TRY(sb.pits.d_deep.upload(mask, s));
+        sb.pits.topo.deep = sb.pits.d_deep.p;
+        TRY(sb.pits.d_done.ensure(std::max<size_t>(1, 2 * (size_t)sb.pits.rg.ntask)));
+    }
+    sb.idx_sparse.assign(sb.npad2, -1); sb.idx_dense.assign(sb.npad2, -1);
+    std::vector<int32_t> pit_to_engine(npad, -1);
+    for (int jp = 0; jp < sb.npad2; jp++) {
+        const int j = sb.host.cell[jp];
+        if (j < 0) continue;
+        sb.idx_sparse[jp] = rg.sparse_k[j]; sb.idx_dense[jp] = rg.cell[j];
+        if (sb.host.pair[j]) pit_to_engine[j] = jp;
+    }
+    TRY(sb.d_cell.upload(sb.host.cell, s)); TRY(sb.d_rec.upload(sb.host.rec, s)); TRY(sb.d_child.upload(sb.host.child, s));
+    TRY(sb.d_xout.upload(sb.host.xout, s)); TRY(sb.d_extoff.upload(sb.host.extoff, s)); TRY(sb.d_extlist.upload(sb.host.extlist, s));
+    TRY(sb.d_kmax.upload(sb.host.tile_kmax, s)); TRY(sb.d_ext.upload(sb.host.tile_ext, s)); TRY(sb.d_pit_to_engine.upload(pit_to_engine, s));
+    TRY(sb.d_err.ensure(1));
+    SbTopo &t = sb.topo;
+    t.ntile = sb.host.ntile; t.ng = mesh->ng; t.nslot = sb.host.nslot; t.dmax = sb.host.dmax;
+    t.cell = sb.d_cell.p; t.rec = sb.d_rec.p; t.child = reinterpret_cast<const uint2 *>(sb.d_child.p); t.xout = sb.d_xout.p;
+    t.extoff = sb.d_extoff.p; t.extlist = sb.d_extlist.p; t.tile_kmax = sb.d_kmax.p; t.tile_ext = sb.d_ext.p;
+    sb.on = true;
+    return 0;
+}
+
 // ---- split engine: build -------------------------------------------------------------------------
 // Gradient runs keep a tape of 24 bytes per cell-step (hp0, hft0, hr_imd, w, the q rows and their padding).  Beyond
 // "tape_budget_mb" (default 16 GB) -- or always with option adjoint_checkpoint = 1 -- the reverse sweep runs window by window
@@ -500,6 +561,7 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
     }
     TRY(pl.d_planes.ensure((size_t)NFIELD * ncell));
     TRY(window_build(pl, mesh));
+    TRY(sub_build(pl, mesh));
     CU(cudaStreamSynchronize(s));
     pl.col_cell = cell;
     pl.ncols = npad;
@@ -629,6 +691,41 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
             pl.launches += 3 + (sp.rg.npair > 0 ? 1 : 0);
         }
         mark(1); mark(2); mark(3);
+        return 0;
+    }
+    if (pl.sub.on && pl.sub.have_forcing && !tape && pl.nmember == 1 && !pl.ensemble && math_mode() == 1) {
+        // subtree engine: one pass over the forcing; the results are in engine order (column j' = tile * 32 + lane)
+        SubState &sb = pl.sub;
+        SbArgs sa{};
+        sa.tp = sb.topo; sa.T = pl.tp.T; sa.Tp = sp.Tp; sa.nwin = (pl.tp.T + SB_W - 1) / SB_W; sa.npad = (int)npad;
+        sa.dt = pl.dt; sa.dx = pl.dx; sa.save_q = save_q ? 1 : 0; sa.save_netp = save_netp ? 1 : 0;
+        sa.fields = pl.d_fields.p; sa.flwacc = sp.d_flwacc.p; sa.gauge_first = sp.d_gfirst.p; sa.gauge_next = sp.d_gnext.p;
+        sa.fstates = pl.d_fstates.p; sa.rows = sp.d_rows.p; sa.qpitch = sb.npad2; sa.qsim = pl.d_qsim.p; sa.err = sb.d_err.p;
+        sa.nowait = (int)option("sub_nowait", 0);
+        const size_t nx = (size_t)std::max(1, sb.host.nslot) * sa.nwin * SB_W, nq = (size_t)pl.tp.T * sb.npad2;
+        if (sb.d_X.n < nx) TRY(sb.d_X.ensure(nx));
+        if (save_q && sb.d_qdom.n < nq) { TRY(sb.d_qdom.ensure(nq)); CU(cudaMemsetAsync(sb.d_qdom.p, 0, nq * sizeof(float), pl.stream)); }
+        if (save_netp && sb.d_netp.n < nq) { TRY(sb.d_netp.ensure(nq)); CU(cudaMemsetAsync(sb.d_netp.p, 0, nq * sizeof(float), pl.stream)); }
+        sa.X = sb.d_X.p; sa.qdom = sb.d_qdom.p; sa.netp = sb.d_netp.p;
+        CU(launch_sub_forward(sa, sb.tm_prcp, sb.tm_pet, pl.stream));
+        mark(1);
+        pl.launches += 1;
+        const bool scatter = option("sub_scatter", 1) != 0;               // results also in cell order j (what the exports read)
+        if (scatter) {
+            if (save_q) CU(launch_scatter_columns(sb.d_qdom.p, sb.npad2, sb.d_cell.p, sb.npad2, pl.tp.T, sp.qpitch, pl.d_qdom.p, pl.stream));
+            if (save_netp) CU(launch_scatter_columns(sb.d_netp.p, sb.npad2, sb.d_cell.p, sb.npad2, pl.tp.T, sp.qpitch, pl.d_netp.p, pl.stream));
+            pl.launches += (save_q ? 1 : 0) + (save_netp ? 1 : 0);
+        }
+        if (sb.host.pair_cells > 0) {
+            SplitArgs b = split_args(pl, save_q, save_netp, &sb.pits);
+            b.fuse_export = save_q ? 1 : 0;                                 // route_pair writes the pit cells' series to qdom (cell order) itself
+            CU(launch_route_forward(b, false, pl.stream));
+            pl.launches += sp.nwin * 2;
+            // the pit cells' columns into the engine-order arrays too
+            if (save_q) CU(launch_scatter_columns(pl.d_qdom.p, sp.qpitch, sb.d_pit_to_engine.p, sp.rg.n, pl.tp.T, sb.npad2, sb.d_qdom.p, pl.stream));
+        }
+        mark(2); mark(3);
+        pl.sub_ran = true;
         return 0;
     }
     if (pl.win.on && !tape && pl.nmember == 1 && !pl.ensemble && math_mode() == 1) {
@@ -804,6 +901,20 @@ static int plan_set_forcing(SmashPlan &pl, const SmashSetup *setup, const SmashM
         CU(launch_relayout_forcing(pl.dtp, sparse ? pl.d_sparse_k.p : pl.d_cell.p, pl.d_raw_prcp.p, pl.d_raw_pet.p, stride,
                                    pl.d_forcing.p, pl.stream));
         pl.launches++;
+    }
+    if (pl.engine == 1 && pl.sub.on) {
+        // the subtree engine reads the forcing in its own column order: packed once per forcing
+        SubState &sb = pl.sub;
+        const size_t npk = (size_t)sb.npad2 * tp.T;
+        TRY(sb.d_pk_prcp.ensure(npk)); TRY(sb.d_pk_pet.ensure(npk));
+        TRY(sb.d_idx_raw.upload(sparse ? sb.idx_sparse : sb.idx_dense, pl.stream));
+        CU(launch_pack_columns(pl.d_raw_prcp.p, stride, sb.d_idx_raw.p, sb.npad2, sb.npad2, tp.T, sb.d_pk_prcp.p, pl.stream));
+        CU(launch_pack_columns(pl.d_raw_pet.p, stride, sb.d_idx_raw.p, sb.npad2, sb.npad2, tp.T, sb.d_pk_pet.p, pl.stream));
+        const char *err = nullptr;
+        if (make_tensor_map_2d(&sb.tm_prcp, sb.d_pk_prcp.p, (uint64_t)sb.npad2, (uint64_t)tp.T, (uint64_t)sb.npad2, &err) ||
+            make_tensor_map_2d(&sb.tm_pet, sb.d_pk_pet.p, (uint64_t)sb.npad2, (uint64_t)tp.T, (uint64_t)sb.npad2, &err))
+            return fail(SMASH_B200_ECUDA, "%s", err);
+        sb.have_forcing = true;
     }
     pl.have_forcing = true; pl.forcing_ptr = prcp; pl.forcing_version = in->forcing_version; pl.forcing_sparse = (int)sparse;
     if (mesh->ng > 0 && in->qobs) {
@@ -1037,7 +1148,7 @@ static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **
              (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0, small ? 1 : 0,
              option("route_ded_min", 96) + 1024 * option("route_ded_max", 64) + (option("route_queues", 12) << 20) +
                  ((option("adjoint_checkpoint", -1) + 1) << 26) + (option("tape_budget_mb", 16384) << 28) +
-                 (option("tick_pass", 0) << 48) + (option("tick_slack", 1) << 49) + (option("shallow_acc", 32) << 50));
+                 (option("tick_pass", 0) << 48) + (option("tick_slack", 1) << 49) + (option("shallow_acc", 32) << 50) + (option("sub_engine", 0) << 58));
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
         std::unique_ptr<SmashPlan> pl(new SmashPlan());
@@ -1159,6 +1270,13 @@ static int forward_streamed(SmashPlan &pl, const SmashSetup *setup, const SmashM
 
 // after a synchronisation of the plan's stream: a wait of the tick pass that did not end leaves 1 + unit in its error word
 static int tick_check(SmashPlan &pl) {
+    if (pl.sub_ran) {
+        pl.sub_ran = false;
+        int h = 0;
+        CU(cudaMemcpyAsync(&h, pl.sub.d_err.p, sizeof(int), cudaMemcpyDeviceToHost, pl.stream));
+        CU(cudaStreamSynchronize(pl.stream));
+        if (h != 0) return fail(SMASH_B200_ECUDA, "subtree engine: tile %d waited for an inflow block that never came (results invalid)", h - 1);
+    }
     if (!pl.tick_ran) return 0;
     pl.tick_ran = false;
     int h = 0;
@@ -1169,7 +1287,7 @@ static int tick_check(SmashPlan &pl) {
 }
 
 static int run_forward_engine(SmashPlan &pl, bool save_q, bool save_netp, bool tape) {
-    pl.tick_ran = false;
+    pl.tick_ran = false; pl.sub_ran = false;
     if (pl.engine == 1) return split_forward(pl, save_q, save_netp, tape);
     SolverArgs a = solver_args(pl, save_q, save_netp, tape);
     CU(launch_forward(a, math_mode(), pl.stream));
@@ -1681,7 +1799,9 @@ extern "C" int smash_b200_plan_get_gradient(SmashPlan *plan, SmashParameters *pa
 extern "C" int smash_b200_plan_checksum(SmashPlan *plan, double *sum_q) {
     if (!plan || !sum_q) return fail(SMASH_B200_EINVAL, "NULL argument");
     if (!plan->d_qdom.p) return fail(SMASH_B200_EINVAL, "plan keeps no domain discharge");
-    if (plan->engine == 1) CU(launch_sum_domain(plan->d_qdom.p, plan->sp.qpitch, plan->sp.rg.n, plan->tp.T, plan->d_sum.p, plan->stream));
+    if (plan->engine == 1 && plan->sub.on && plan->sub.d_qdom.p && !option("sub_scatter", 1))
+        CU(launch_sum_domain(plan->sub.d_qdom.p, plan->sub.npad2, plan->sub.npad2, plan->tp.T, plan->d_sum.p, plan->stream));
+    else if (plan->engine == 1) CU(launch_sum_domain(plan->d_qdom.p, plan->sp.qpitch, plan->sp.rg.n, plan->tp.T, plan->d_sum.p, plan->stream));
     else CU(launch_checksum(plan->dtp, plan->d_qdom.p, plan->d_sum.p, plan->stream));
     CU(cudaMemcpyAsync(sum_q, plan->d_sum.p, sizeof(double), cudaMemcpyDeviceToHost, plan->stream));
     CU(cudaStreamSynchronize(plan->stream));
@@ -1930,6 +2050,10 @@ extern "C" double smash_b200_plan_stat(const SmashPlan *plan, const char *name) 
         if (n == "tape_bytes")
             return 4.0 * ((double)sp.d_tape_hp.n + sp.d_tape_hft.n + sp.d_rows_hr.n + sp.d_rows_w.n + (sp.ckpt ? (double)sp.d_rows_seg.n : (double)sp.d_rows.n) +
                           sp.d_ckpt.n);
+        if (n == "sub_engine") return plan->sub.on ? 1.0 : 0.0;
+        if (n == "sub_tiles") return plan->sub.on ? (double)plan->sub.host.ntile : -1.0;
+        if (n == "sub_slots") return plan->sub.on ? (double)plan->sub.host.nslot : -1.0;
+        if (n == "sub_levels") return plan->sub.on ? (double)plan->sub.host.nlevel : -1.0;
         if (n == "tick_pass") return plan->win.on ? 1.0 : 0.0;
         if (n == "tick_stages") return plan->win.on ? (double)plan->win.host.max_sigma : -1.0;
         if (n == "tick_reaches") return plan->win.on ? (double)plan->win.host.nreach : -1.0;

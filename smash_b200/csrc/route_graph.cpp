@@ -559,4 +559,168 @@ bool replay_tick_schedule(const RouteGraph &rg, const TickTopoHost &tk, int nwar
     return ok && done == total;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Subtree tiles (route_graph.hpp).  Cells are visited in path order (inflows first): a cell keeps the open subtrees of its
+// inflows, heaviest first, while the union holds at most 32 cells and dmax + 1 cells of depth; an inflow that does not fit is
+// closed and becomes the root of a component.
+// ------------------------------------------------------------------------------------------------
+std::string build_sub_topo(const RouteGraph &g, int dmax, SubTopoHost &out) {
+    const int n = g.n;
+    out = SubTopoHost();
+    if (dmax < 1 || dmax > 15) return "internal: dmax out of range";
+    out.dmax = dmax;
+    out.pair.assign(n, 0);
+    out.cells = n;
+    // ---- pit cells; tree over the other cells
+    for (int j = 0; j < n; j++)
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) {
+            if (g.up[e].task == UP_PARTNER) out.pair[j] = 1;
+            else if (g.up[e].src >= j) return "unsupported: lagged inflow outside a pit pair";
+        }
+    std::vector<int32_t> parent(n, -1);
+    for (int j = 0; j < n; j++) {
+        if (out.pair[j]) { out.pair_cells++; continue; }
+        const int d = g.down[j];
+        if (d >= 0 && !out.pair[d]) parent[j] = d;
+    }
+    for (int j = 0; j < n; j++)
+        if (out.pair[j] && g.down[j] >= 0 && !out.pair[g.down[j]]) return "unsupported: a pit pair drains into another cell";
+    // ---- open subtrees
+    std::vector<int32_t> osize(n, 1), oheight(n, 1);
+    std::vector<uint8_t> closed(n, 0);
+    std::vector<int32_t> kids;
+    for (int j = 0; j < n; j++) {
+        if (out.pair[j]) { closed[j] = 1; continue; }
+        kids.clear();
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) kids.push_back(g.up[e].src);
+        if (kids.size() > 8) return "unsupported: more than 8 inflows";
+        std::stable_sort(kids.begin(), kids.end(), [&](int x, int y) { return g.flwacc[x] > g.flwacc[y]; });
+        int size = 1, height = 1;
+        for (int c : kids) {
+            if (size + osize[c] <= 32 && oheight[c] + 1 <= dmax + 1) { size += osize[c]; height = std::max(height, oheight[c] + 1); }
+            else closed[c] = 1;
+        }
+        osize[j] = size; oheight[j] = height;
+        if (parent[j] < 0) closed[j] = 1;
+    }
+    // ---- components (root = closed cell), their levels
+    std::vector<int32_t> comp(n, -1);
+    for (int j = n - 1; j >= 0; j--) comp[j] = closed[j] ? j : comp[parent[j]];
+    std::vector<int32_t> level(n, 0);                                     // per component root
+    for (int c = 0; c < n; c++)                                           // ascending: a component's root is its largest cell
+        if (closed[c] && !out.pair[c] && parent[c] >= 0) {
+            const int cr = comp[parent[c]];
+            level[cr] = std::max(level[cr], level[c] + 1);
+        }
+    // ---- tiles: first fit decreasing inside a level
+    std::vector<int32_t> roots;
+    for (int c = 0; c < n; c++) if (closed[c]) roots.push_back(c);
+    out.ncomp = (int)roots.size();
+    std::stable_sort(roots.begin(), roots.end(), [&](int x, int y) {
+        if (level[x] != level[y]) return level[x] < level[y];
+        return osize[x] > osize[y];
+    });
+    std::vector<int32_t> tile_of_comp(n, -1), tile_fill;
+    {
+        size_t i = 0;
+        while (i < roots.size()) {
+            size_t k = i;
+            while (k < roots.size() && level[roots[k]] == level[roots[i]]) k++;
+            const int first_tile = (int)tile_fill.size();
+            // bins with free room, indexed by free lanes: a component goes to the fullest bin it fits
+            std::vector<std::vector<int32_t>> by_free(33);
+            for (size_t r = i; r < k; r++) {
+                const int sz = osize[roots[r]];
+                int t = -1;
+                for (int f = sz; f <= 32 && t < 0; f++)
+                    if (!by_free[f].empty()) { t = by_free[f].back(); by_free[f].pop_back(); }
+                if (t < 0) { t = (int)tile_fill.size(); tile_fill.push_back(0); }
+                tile_of_comp[roots[r]] = t;
+                tile_fill[t] += sz;
+                if (tile_fill[t] < 32) by_free[32 - tile_fill[t]].push_back(t);
+            }
+            (void)first_tile;
+            out.nlevel = std::max(out.nlevel, level[roots[i]] + 1);
+            i = k;
+        }
+    }
+    out.ntile = (int)tile_fill.size();
+    const size_t np2 = (size_t)out.ntile * 32;
+    out.cell.assign(np2, -1); out.jprime.assign(n, -1); out.rec.assign(np2, 0); out.child.assign(np2 * 2, 0u);
+    out.xout.assign(np2, -1); out.extoff.assign(np2, 0); out.tile_kmax.assign(out.ntile, 0); out.tile_ext.assign(out.ntile, 0);
+    // ---- lanes: components in the order of `roots`, cells of a component in path order (descending so that parents come first
+    // is not needed: a lane only needs its delay and the lanes of its inflows)
+    // breadth first from the root of every component, so that the in-tile inflows of a cell sit in consecutive lanes, in the
+    // reference's summation order: the warp sums them with a segmented scan
+    std::vector<int32_t> next_lane(out.ntile, 0), delay(n, 0), segpos(n, 0), lastc(n, -1);
+    {
+        std::vector<int32_t> queue;
+        for (int r : roots) {
+            const int t = tile_of_comp[r];
+            queue.clear();
+            queue.push_back(r);
+            for (size_t q = 0; q < queue.size(); q++) {
+                const int j = queue[q];
+                const int lane = next_lane[t]++;
+                out.jprime[j] = t * 32 + lane;
+                out.cell[(size_t)t * 32 + lane] = j;
+                if (out.pair[j]) continue;
+                int pos = 0;
+                for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) {
+                    const int c = g.up[e].src;
+                    if (closed[c]) continue;
+                    segpos[c] = pos++;
+                    lastc[j] = c;
+                    queue.push_back(c);
+                }
+            }
+        }
+    }
+    for (int j = n - 1; j >= 0; j--) delay[j] = closed[j] ? oheight[j] - 1 : delay[parent[j]] - 1;
+    // ---- exchange slots: one per closed root that flows into another component
+    std::vector<int32_t> slot(n, -1);
+    for (int c = 0; c < n; c++)
+        if (closed[c] && !out.pair[c] && parent[c] >= 0) slot[c] = out.nslot++;
+    for (int j = 0; j < n; j++) {
+        const size_t jp = (size_t)out.jprime[j];
+        const int t = (int)(jp >> 5);
+        int rec = 1, nch = 0, next = 0;
+        out.extoff[jp] = (int32_t)out.extlist.size();
+        if (out.pair[j]) rec |= 2;
+        else {
+            if (delay[j] < 0 || delay[j] > dmax) return "internal: lane delay out of range";
+            for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) {
+                const int c = g.up[e].src;
+                if (closed[c]) { out.extlist.push_back(slot[c]); next++; if (slot[c] < 0) return "internal: inflow without a slot"; }
+                else {
+                    const int cl = out.jprime[c] & 31;
+                    if ((out.jprime[c] >> 5) != t || delay[c] != delay[j] - 1) return "internal: in-tile inflow off the wavefront";
+                    if (nch < 6) out.child[jp * 2] |= (uint32_t)cl << (5 * nch);
+                    else out.child[jp * 2 + 1] |= (uint32_t)cl << (5 * (nch - 6));
+                    nch++;
+                }
+            }
+            if (slot[j] >= 0) { rec |= 4; out.xout[jp] = slot[j]; }
+            const int d = g.down[j];
+            if (d >= 0 && out.pair[d]) rec |= 8;
+            rec |= delay[j] << 8;
+        }
+        if (g.gauge_first[j] >= 0) rec |= 16;
+        rec |= (nch << 12) | (next << 16) | (segpos[j] << 20) | ((lastc[j] >= 0 ? (out.jprime[lastc[j]] & 31) : 0) << 23);
+        if (lastc[j] >= 0 && (out.jprime[lastc[j]] >> 5) != t) return "internal: inflow lanes outside the tile";
+        out.rec[jp] = rec;
+        out.tile_kmax[t] = std::max<uint8_t>(out.tile_kmax[t], (uint8_t)nch);
+        if (next) out.tile_ext[t] = 1;
+        out.kmax = std::max(out.kmax, nch);
+    }
+    if (out.extlist.empty()) out.extlist.push_back(0);
+    // a tile only reads slots written by lower tiles
+    for (int j = 0; j < n; j++)
+        for (int e = g.up_begin[j]; e < g.up_begin[j + 1]; e++) {
+            const int c = g.up[e].src;
+            if (!out.pair[j] && closed[c] && (out.jprime[c] >> 5) >= (out.jprime[j] >> 5)) return "internal: tile order violates a dependency";
+        }
+    return "";
+}
+
 }  // namespace smash

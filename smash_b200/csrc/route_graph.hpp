@@ -108,4 +108,31 @@ void deal_tick_units(const TickTopoHost &t, int nwarp, std::vector<int32_t> &wun
 bool replay_tick_schedule(const RouteGraph &rg, const TickTopoHost &tk, int nwarp, int nwin, std::vector<int32_t> &pub, long long &done,
                           int &maxu);
 
+// ---- subtree engine (sub_kernels.cu): the engine owns the cell order -------------------------------------------------
+// The drainage forest (pit pairs aside) is cut into connected subtrees ("components") of at most 32 cells and at most
+// dmax + 1 cells of depth; components of the same level (1 + the largest level among the components that flow into them) are
+// packed into tiles of 32 lanes.  Inside a tile a cell's inflows are lanes of the same warp (delay of a lane = delay of its
+// parent - 1, so every in-tile edge spans exactly one micro-tick of the warp's wavefront); only the roots of the components
+// hand their series to another tile, through exchange slots.  Tiles are numbered by level: a tile only reads lower tiles.
+struct SubTopoHost {
+    int ntile = 0, nslot = 0, dmax = 0, nlevel = 0, ncomp = 0, kmax = 0;
+    std::vector<int32_t> cell;       // [ntile * 32] cell j (path order) of engine column j', -1 = empty lane
+    std::vector<int32_t> jprime;     // [n] engine column of cell j
+    std::vector<int32_t> rec;        // [ntile * 32] bit 0 valid, 1 pit cell (reservoirs only), 2 writes an exchange slot, 3 a pit cell
+                                     // reads its row, 4 gauge, bits 8-11 delay, 12-15 in-tile inflows (they sit in consecutive lanes),
+                                     // 16-19 exchange slots read, 20-22 position among the in-tile inflows of its parent, 23-27 lane of
+                                     // the last in-tile inflow
+    std::vector<uint32_t> child;     // [ntile * 32][2] lanes of the in-tile inflows, 5 bits each (6 in word 0, 2 in word 1),
+                                     // reference summation order
+    std::vector<int32_t> xout;       // [ntile * 32] exchange slot written by the lane, or -1
+    std::vector<int32_t> extoff;     // [ntile * 32] first entry of the lane in extlist
+    std::vector<int32_t> extlist;    // exchange slots read
+    std::vector<uint8_t> tile_kmax;  // [ntile] largest number of in-tile inflows of a lane
+    std::vector<uint8_t> tile_ext;   // [ntile] 1 = some lane reads an exchange slot
+    std::vector<uint8_t> pair;       // [n] 1 = cell of a pit pair
+    int64_t cells = 0, pair_cells = 0;
+};
+// Returns "" or "unsupported: ...".
+std::string build_sub_topo(const RouteGraph &g, int dmax, SubTopoHost &out);
+
 }  // namespace smash

@@ -135,6 +135,41 @@ cudaError_t tick_grid_warps(int variant, int ctas_per_sm, int *nwarp);
 cudaError_t launch_tick_forward(const TkArgs &a, const float *fields, const CUtensorMap &prcp, const CUtensorMap &pet,
                                 cudaStream_t s, int variant = 8);
 
+// ---- subtree engine (sub_kernels.cu): one pass over the forcing, the engine owns the cell order --------------------------
+constexpr int SB_W = 8;          // time steps per forcing box / exchange block
+
+struct SbTopo {
+    int ntile, ng, nslot, dmax;
+    const int32_t *cell;         // [ntile * 32] SubTopoHost::cell (route_graph.hpp)
+    const int32_t *rec;          // [ntile * 32]
+    const uint2 *child;          // [ntile * 32]
+    const int32_t *xout;         // [ntile * 32]
+    const int32_t *extoff;       // [ntile * 32]
+    const int32_t *extlist;
+    const uint8_t *tile_kmax, *tile_ext;   // [ntile]
+};
+
+struct SbArgs {
+    SbTopo tp;
+    int T, Tp, nwin, npad;       // time steps; pitch of the pit rows; windows = ceil(T / 8); columns of fields / fstates (cell order j)
+    float dt, dx;
+    int save_q, save_netp;
+    const float *fields;         // [NFIELD][npad] cell order j
+    const int32_t *flwacc;       // [npad]
+    const int32_t *gauge_first;  // [npad]
+    const int32_t *gauge_next;   // [ng]
+    float *fstates;              // [3][npad] final states, cell order j
+    float *X;                    // [nslot][nwin][8] exchange blocks (NaN = not written yet)
+    float *rows;                 // [npad][Tp] runoff of the pit cells, discharge of the cells that flow into a pit cell
+    float *qdom, *netp;          // [T][qpitch] ENGINE order (column j' = tile * 32 + lane), qpitch = ntile * 32
+    int64_t qpitch;
+    float *qsim;                 // [T][ng]
+    int *err;                    // set to 1 + tile when a wait did not end
+    int nowait;                  // diagnostics: do not wait for the exchange blocks (wrong results; shows the dependency-free time)
+};
+size_t sub_smem_bytes();
+cudaError_t launch_sub_forward(const SbArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, cudaStream_t s);
+
 // 2-D tensor map over a [rows][pitch] float array, box = 8 rows x 32 columns.  cols = valid columns (the rest reads 0).
 int make_tensor_map_2d(CUtensorMap *tm, const float *base, uint64_t cols, uint64_t rows, uint64_t pitch_elems, const char **err);
 

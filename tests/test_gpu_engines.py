@@ -228,7 +228,7 @@ def _run_window(m, opts):
     finally:
         for k in opts:
             lib.smash_b200_set_option(k.encode(), {"tick_pass": 0, "shallow_acc": 32, "tick_variant": 8, "tick_min_cells": 65536,
-                                                   "tick_ctas_per_sm": 0}[k])
+                                                   "tick_ctas_per_sm": 0, "sub_engine": 0, "sub_min_cells": 65536, "sub_scatter": 1}[k])
         lib.smash_b200_clear_cache()
 
 
@@ -343,3 +343,47 @@ def test_checkpointed_adjoint_equals_store_all(case):
         oracle.forward_b(c.setup, c.mesh, c.input_data, c.parameters, pc, c.parameters.copy(), c.states, sc, c.states.copy(), c.output)
         check_grad(pa, pc, ("cp", "cft", "exc", "lr"))
         check_grad(sa, sc, ("hp", "hft", "hlr"))
+
+
+def test_sub_engine_agrees_with_row_passes():
+    # the subtree engine (sub_kernels.cu: the engine's own cell order, routing inside the warp as a wavefront, only subtree
+    # roots hand their series to other tiles) against the row-based passes on a 650 x 650 France crop with pit pairs; T = 100
+    # ends in a partial window
+    def model():
+        m = cases.france(T=100, sub=(250, 900, 250, 900), ngauge=4)
+        random_fields(m, seed=11)
+        m.setup.save_net_prcp_domain = True
+        m.output = type(m.output)(m.setup, m.mesh)
+        return m
+    a = _run_window(model(), {"sub_engine": 1, "sub_min_cells": 1000})
+    b = _run_window(model(), {"sub_engine": 0})
+    assert a.mesh.nac > 100000
+    for name, x, y in (("qsim", a.output.qsim, b.output.qsim), ("qdom", a.output.sparse_qsim_domain, b.output.sparse_qsim_domain),
+                       ("netp", a.output.sparse_net_prcp_domain, b.output.sparse_net_prcp_domain),
+                       ("hlr", a.output.fstates.hlr, b.output.fstates.hlr), ("hp", a.output.fstates.hp, b.output.fstates.hp),
+                       ("hft", a.output.fstates.hft, b.output.fstates.hft)):
+        x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+        assert np.all(np.abs(x - y) <= 1e-7 + 1e-5 * np.abs(y)), (name, float(np.abs(x - y).max()))
+    assert np.isclose(float(a.output.cost), float(b.output.cost), rtol=1e-5)
+
+
+@pytest.mark.parametrize("case", ["france", "cance"])
+def test_sub_engine_against_oracle(case):
+    import oracle
+    if case == "france":
+        m = cases.france(T=50, sub=(400, 700, 400, 700), ngauge=3)
+    else:
+        m = cases.cance(sparse=True, T=1440)
+        m.setup.save_qsim_domain = True
+        m.output = type(m.output)(m.setup, m.mesh)
+    random_fields(m, seed=13)
+    c = m.copy()
+    c.output = type(m.output)(m.setup, m.mesh)
+    a = _run_window(m, {"sub_engine": 1, "sub_min_cells": 0})
+    oracle.forward(c.setup, c.mesh, c.input_data, c.parameters, c.parameters.copy(), c.states, c.states.copy(), c.output)
+    qa, qc = np.asarray(a.output.sparse_qsim_domain, np.float64), np.asarray(c.output.sparse_qsim_domain, np.float64)
+    assert np.all(np.abs(qa - qc) <= 1e-4 + 2e-3 * np.abs(qc)), float(np.abs(qa - qc).max())
+    assert np.all(np.abs(np.asarray(a.output.qsim, np.float64) - c.output.qsim) <= 1e-4 + 2e-3 * np.abs(c.output.qsim))
+    for name in ("hp", "hft", "hlr"):
+        x, y = np.asarray(getattr(a.output.fstates, name), np.float64), np.asarray(getattr(c.output.fstates, name), np.float64)
+        assert np.all(np.abs(x - y) <= 1e-5 + 2e-3 * np.abs(y)), (name, float(np.abs(x - y).max()))
