@@ -455,30 +455,40 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
                                    "route_adjoint_kernel": float(gk[3]), "vertical_adjoint_kernel": float(gk[4])}}
     lib.smash_b200_plan_destroy(plan)
 
-    # ---- the measured alternative: the tick pass (one kernel for reservoirs + routing, opt-in), same workload
+    # ---- the measured alternatives (opt-in engines that trade DRAM traffic against instructions), same workload
     if not args.no_extra:
-        lib.smash_b200_set_option(b"tick_pass", 1)
-        try:
-            plan2 = C.c_void_p()
-            L.check(lib.smash_b200_plan_create(C.byref(s_), C.byref(m_), 1, C.byref(plan2)))
-            L.check(lib.smash_b200_plan_set_forcing(plan2, C.byref(s_), C.byref(i_)))
-            L.check(lib.smash_b200_plan_set_fields(plan2, C.byref(p_), C.byref(st_), None, None, 0))
-            tms = []
-            for k in range(args.warmup + 5):
-                L.check(lib.smash_b200_plan_run_forward(plan2, C.byref(ms)))
-                if k >= args.warmup:
-                    tms.append(ms.value)
-            chk2 = C.c_double(0.0)
-            L.check(lib.smash_b200_plan_checksum(plan2, C.byref(chk2)))
-            on = lib.smash_b200_plan_stat(plan2, b"tick_pass") == 1.0
-            lib.smash_b200_plan_destroy(plan2)
-            roofline["alternatives"] = {"tick_pass": {
-                "ran": bool(on), "ms_per_step": float(np.mean(tms)), "frac": step_bytes / (float(np.mean(tms)) * 1e-3) / 1e9 / peak,
-                "dram_traffic_bytes": traffic.get("tick_forward_kernel"), "checksum_q": chk2.value,
-                "note": "opt-in (option tick_pass): every cell advances 8 steps per ticket, discharge blocks handed from producer to "
-                        "consumer; bound by the latency of a ticket, see DESIGN.md section 3b"}}
-        finally:
-            lib.smash_b200_set_option(b"tick_pass", 0)
+        roofline["alternatives"] = {}
+        notes = {"tick_pass": "opt-in (option tick_pass): every cell advances 8 steps per ticket, discharge blocks handed from producer "
+                              "to consumer; bound by the latency of a ticket, DESIGN.md section 3b",
+                 "sub_engine": "opt-in (option sub_engine): the engine's own cell order, subtrees of the drainage forest routed inside "
+                               "the warp, only subtree roots exchange series; DRAM traffic 1.16 x algorithmic, bound by instruction "
+                               "issue, DESIGN.md section 3e"}
+        kern = {"tick_pass": "tick_forward_kernel", "sub_engine": "sub_forward_kernel"}
+        for name in ("tick_pass", "sub_engine"):
+            lib.smash_b200_set_option(name.encode(), 1)
+            lib.smash_b200_set_option(b"sub_scatter", 0)                     # results stay in engine order
+            try:
+                plan2 = C.c_void_p()
+                L.check(lib.smash_b200_plan_create(C.byref(s_), C.byref(m_), 1, C.byref(plan2)))
+                L.check(lib.smash_b200_plan_set_forcing(plan2, C.byref(s_), C.byref(i_)))
+                L.check(lib.smash_b200_plan_set_fields(plan2, C.byref(p_), C.byref(st_), None, None, 0))
+                tms = []
+                for k in range(args.warmup + 5):
+                    L.check(lib.smash_b200_plan_run_forward(plan2, C.byref(ms)))
+                    if k >= args.warmup:
+                        tms.append(ms.value)
+                chk2 = C.c_double(0.0)
+                L.check(lib.smash_b200_plan_checksum(plan2, C.byref(chk2)))
+                on = lib.smash_b200_plan_stat(plan2, name.encode()) == 1.0
+                lib.smash_b200_plan_destroy(plan2)
+                tr2 = traffic.get(kern[name])
+                roofline["alternatives"][name] = {
+                    "ran": bool(on), "ms_per_step": float(np.mean(tms)), "frac": step_bytes / (float(np.mean(tms)) * 1e-3) / 1e9 / peak,
+                    "dram_traffic_bytes": tr2, "traffic_over_algorithmic": (tr2 / step_bytes) if tr2 else None,
+                    "checksum_q": chk2.value, "note": notes[name]}
+            finally:
+                lib.smash_b200_set_option(name.encode(), 0)
+                lib.smash_b200_set_option(b"sub_scatter", 1)
 
     # ---- the ANN mapping's forward pass at France scale: the graph of _ann_optimize.py:143-168 for nd = 6 descriptors
     ann = None

@@ -90,7 +90,7 @@ __device__ __forceinline__ float sub_step_lean(const CellConst &k, float prcp, f
 }
 
 template <int DUMMY>
-__global__ void __launch_bounds__(SB_WARPS * 32, 8) sub_forward_kernel(const __grid_constant__ CUtensorMap tm_prcp,
+__global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __grid_constant__ CUtensorMap tm_prcp,
                                                                        const __grid_constant__ CUtensorMap tm_pet, const SbArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
