@@ -57,6 +57,12 @@ __device__ __forceinline__ void sb_ld8(const float *p, float *v) {       // stra
                  : "memory");
 }
 
+// shared-memory accesses through addresses kept in registers: left to itself the compiler rebuilds every address from the
+// thread index (about ten instructions per access at this register budget)
+__device__ __forceinline__ uint32_t sb_opaque(uint32_t x) { uint32_t y; asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x)); return y; }
+__device__ __forceinline__ float sb_lds(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sb_sts(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
 // gr-a cell-step without forcing gap, tanh argument below 0.25 and hp_imd <= 15: the statements of vertical_step_nogap
 // (cell_math.cuh) with those branches resolved by the caller.  Same code as vertical_step_lean of split_kernels.cu.
 template <bool EXC>
@@ -152,6 +158,12 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
     const bool save_q = a.save_q != 0 && valid && !pit;
     const bool rare = root_out || want_row || pit || gauge;
     const float inv_cp = k.inv_cp;
+    // lane flags in one register the compiler cannot rebuild from the kernel arguments every tick
+    const uint32_t fl = sb_opaque((save_q ? 1u : 0u) | (rare ? 2u : 0u) | ((tile_ext && next > 0) ? 4u : 0u) | (nch > 0 ? 8u : 0u) |
+                                  (tile_ext ? 16u : 0u));
+    const uint32_t qcol = sb_opaque(smem_u32(&qr[0][lane]));             // this lane's column of the runoff / discharge ring (rows 128 bytes apart)
+    const uint32_t ecol = sb_opaque(smem_u32(&extv[0][lane]));
+    const uint32_t pcol = sb_opaque(smem_u32(&ring_p[0][0][lane]));       // prcp boxes of this warp; the pet boxes lie SB_WARPS * SB_NST boxes further
 
     const int ngroup = (T + dmax + SB_W - 1) / SB_W;                      // groups of 8 micro-ticks
     uint32_t parity = 0;
@@ -163,10 +175,11 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
             mbar_wait(&bars[slot], parity);
             float pv[SB_W], ev[SB_W];
             float mn = 0.0f, mx = 0.0f;
+            const uint32_t pbox = pcol + (uint32_t)slot * (uint32_t)sizeof(SbBox), ebox = pbox + (uint32_t)(sizeof(SbBox) * SB_WARPS * SB_NST);
 #pragma unroll
             for (int i = 0; i < SB_W; i++) {
-                pv[i] = ring_p[slot][i][lane];
-                ev[i] = ring_e[slot][i][lane];
+                pv[i] = sb_lds(pbox + 128 * i);
+                ev[i] = sb_lds(ebox + 128 * i);
                 mn = fminf(mn, fminf(pv[i], ev[i]));
                 mx = fmaxf(mx, fmaxf(pv[i], ev[i]));
             }
@@ -181,14 +194,14 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
             const bool full = tb + SB_W <= T;                             // empty lanes carry default parameters and zero forcing
             const float xm = mx * inv_cp;
             const bool lean = full && __all_sync(FULLM, mn >= 0.0f && xm < 0.25f && fmaf(8.0f, xm, hp) < 15.0f);
-            float (*row)[32] = qr + (tb & (SB_DL - 1));                   // 8 consecutive rows: tb is a multiple of 8
+            const uint32_t row = qcol + ((uint32_t)(tb & (SB_DL - 1)) << 7);      // 8 consecutive rows: tb is a multiple of 8
             if (lean) {
                 if (exc_on) {
 #pragma unroll
-                    for (int i = 0; i < SB_W; i++) row[i][lane] = sub_step_lean<true>(k, pv[i], ev[i], hp, hft);
+                    for (int i = 0; i < SB_W; i++) sb_sts(row + 128 * i, sub_step_lean<true>(k, pv[i], ev[i], hp, hft));
                 } else {
 #pragma unroll
-                    for (int i = 0; i < SB_W; i++) row[i][lane] = sub_step_lean<false>(k, pv[i], ev[i], hp, hft);
+                    for (int i = 0; i < SB_W; i++) sb_sts(row + 128 * i, sub_step_lean<false>(k, pv[i], ev[i], hp, hft));
                 }
             } else {
 #pragma unroll
@@ -199,13 +212,13 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
                     if (__all_sync(FULLM, gapless)) qt = vertical_step_nogap(k, pv[i], ev[i], hp_n, hft_n);
                     else qt = vertical_step<1>(k, pv[i], ev[i], hp_n, hft_n).qt;
                     if (act) { hp = hp_n; hft = hft_n; }
-                    row[i][lane] = qt;
+                    sb_sts(row + 128 * i, qt);
                 }
             }
             if (save_netp) {
 #pragma unroll
                 for (int i = 0; i < SB_W; i++)
-                    if (tb + i < T) __stcs(np_ + (size_t)(tb + i) * pitch, row[i][lane]);
+                    if (tb + i < T) __stcs(np_ + (size_t)(tb + i) * pitch, sb_lds(row + 128 * i));
             }
         }
         // ================= routing, micro-ticks 8 kb .. 8 kb + 7: lane l is at time step t = m - delay(l)
@@ -215,8 +228,8 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
             const int t = m - delay;
             const bool active = valid && (unsigned)t < (unsigned)T;
             // ---- inflow blocks of other tiles: once per window of this lane
-            if (tile_ext) {
-                if (active && next > 0 && (t & 7) == 0) {
+            if (fl & 16u) {
+                if (active && (fl & 4u) && (t & 7) == 0) {
                     float acc[SB_W];
 #pragma unroll
                     for (int i = 0; i < SB_W; i++) acc[i] = 0.0f;
@@ -235,7 +248,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
                         for (int i = 0; i < SB_W; i++) acc[i] = acc[i] + v[i];
                     }
 #pragma unroll
-                    for (int i = 0; i < SB_W; i++) extv[i][lane] = acc[i];
+                    for (int i = 0; i < SB_W; i++) sb_sts(ecol + 128 * i, acc[i]);
                 }
                 __syncwarp();
             }
@@ -246,17 +259,18 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
             v = __shfl_up_sync(FULLM, x, 2); x = segpos >= 2 ? x + v : x;
             v = __shfl_up_sync(FULLM, x, 4); x = segpos >= 4 ? x + v : x;
             v = __shfl_sync(FULLM, x, lastc);
-            float qup = nch > 0 ? v : 0.0f;
-            if (tile_ext && next > 0) qup += extv[t & 7][lane];
-            const float qt = qr[t & (SB_DL - 1)][lane];
+            float qup = (fl & 8u) ? v : 0.0f;
+            if (fl & 4u) qup += sb_lds(ecol + ((uint32_t)(t & 7) << 7));
+            const uint32_t qcell = qcol + ((uint32_t)(t & (SB_DL - 1)) << 7);
+            const float qt = sb_lds(qcell);
             const float hr = hlr + qup * s_q;                             // :55-56, :73
             const float hn = hr * E;                                      // :75
             const float q = fmaf(hr - hn, fa1, qt) * c0;                  // :77, md_forward_structure.f90:155
             hlr = active ? hn : hlr;
             qprev = active ? q : 0.0f;
             if (active) {
-                qr[t & (SB_DL - 1)][lane] = q;
-                if (rare) {
+                sb_sts(qcell, q);
+                if (fl & 2u) {
                     if (root_out) xo[t] = q;
                     if (rowp) rowp[t] = q;
                     if (gauge && !pit)
@@ -265,7 +279,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
             }
             // the row of time step m - dmax is complete: one coalesced row of the domain series
             const int tt = m - dmax;
-            if (save_q && (unsigned)tt < (unsigned)T) { __stcs(qd, qr[tt & (SB_DL - 1)][lane]); qd += pitch; }
+            if ((fl & 1u) && (unsigned)tt < (unsigned)T) { __stcs(qd, sb_lds(qcol + ((uint32_t)(tt & (SB_DL - 1)) << 7))); qd += pitch; }
         }
     }
     // the reader of an exchange block waits for 8 numbers: fill what lies beyond the last time step
