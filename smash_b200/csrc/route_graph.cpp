@@ -645,6 +645,46 @@ std::string build_sub_topo(const RouteGraph &g, int dmax, SubTopoHost &out) {
         }
     }
     out.ntile = (int)tile_fill.size();
+    {
+        // ---- dispatch order of the tiles: a topological order of the tile graph that starts the longest pipelines first
+        // (list scheduling by the length of the longest chain of tiles downstream), so that the river tiles run under the
+        // bulk of the domain instead of forming a tail.  A tile still only reads tiles with a smaller number.
+        const int nt = out.ntile;
+        std::vector<std::vector<int32_t>> cons(nt);
+        std::vector<int32_t> indeg(nt, 0), dl(nt, 1), tlevel(nt, 0);
+        for (int c = 0; c < n; c++)
+            if (closed[c] && !out.pair[c] && parent[c] >= 0) {
+                const int a = tile_of_comp[c], b2 = tile_of_comp[comp[parent[c]]];
+                if (a == b2) return "internal: a tile reads itself";
+                cons[a].push_back(b2);
+            }
+        for (int r : roots) tlevel[tile_of_comp[r]] = level[r];           // all components of a tile share the level
+        for (int t = 0; t < nt; t++) {
+            std::sort(cons[t].begin(), cons[t].end());
+            cons[t].erase(std::unique(cons[t].begin(), cons[t].end()), cons[t].end());
+            for (int b2 : cons[t]) indeg[b2]++;
+        }
+        std::vector<int32_t> bylevel(nt);
+        for (int t = 0; t < nt; t++) bylevel[t] = t;
+        std::stable_sort(bylevel.begin(), bylevel.end(), [&](int x, int y) { return tlevel[x] > tlevel[y]; });
+        for (int t : bylevel)                                             // consumers (higher level) first
+            for (int b2 : cons[t]) dl[t] = std::max(dl[t], dl[b2] + 1);
+        std::vector<std::pair<int32_t, int32_t>> heap;                    // (downstream length, -tile): longest first, then the old order
+        for (int t = 0; t < nt; t++) if (indeg[t] == 0) heap.push_back({dl[t], -t});
+        std::make_heap(heap.begin(), heap.end());
+        std::vector<int32_t> newid(nt, -1);
+        int next_id = 0;
+        while (!heap.empty()) {
+            std::pop_heap(heap.begin(), heap.end());
+            const int t = -heap.back().second;
+            heap.pop_back();
+            newid[t] = next_id++;
+            for (int b2 : cons[t])
+                if (--indeg[b2] == 0) { heap.push_back({dl[b2], -b2}); std::push_heap(heap.begin(), heap.end()); }
+        }
+        if (next_id != nt) return "internal: the tile graph has a cycle";
+        for (int r : roots) tile_of_comp[r] = newid[tile_of_comp[r]];
+    }
     const size_t np2 = (size_t)out.ntile * 32;
     out.cell.assign(np2, -1); out.jprime.assign(n, -1); out.rec.assign(np2, 0); out.child.assign(np2 * 2, 0u);
     out.xout.assign(np2, -1); out.extoff.assign(np2, 0); out.tile_kmax.assign(out.ntile, 0); out.tile_ext.assign(out.ntile, 0);
