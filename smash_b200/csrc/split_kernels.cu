@@ -1605,10 +1605,12 @@ template <int S> static cudaError_t route_forward_windows(const SplitArgs &a, bo
             if (e == cudaSuccess) e = cudaMemcpyAsync(a.qctl, a.qctl0, 32 * sizeof(unsigned int), cudaMemcpyDeviceToDevice, s);
             if (e != cudaSuccess) return e;
         }
-        if (tape) route_forward_kernel<S, 1><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
-        else route_forward_kernel<S, 0><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
+        if (a.tp.nchain > 0 || a.fuse_export > 1) {                       // a graph of pit pairs only has nothing for this kernel
+            if (tape) route_forward_kernel<S, 1><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
+            else route_forward_kernel<S, 0><<<blocks, 128, 0, s>>>(a, w, ded_blocks);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return e;
+        }
         if (npair > 0) {
             if (tape) route_pairs_kernel<S, 1><<<(npair + 3) / 4, 128, 0, s>>>(a, w);
             else route_pairs_kernel<S, 0><<<(npair + 3) / 4, 128, 0, s>>>(a, w);

@@ -23,6 +23,7 @@
 #include "split_kernels.cuh"
 
 #include <algorithm>
+#include <type_traits>
 
 #include "cell_math.cuh"
 
@@ -159,8 +160,8 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
     const bool rare = root_out || want_row || pit || gauge;
     const float inv_cp = k.inv_cp;
     // lane flags in one register the compiler cannot rebuild from the kernel arguments every tick
-    const uint32_t fl = sb_opaque((save_q ? 1u : 0u) | (rare ? 2u : 0u) | ((tile_ext && next > 0) ? 4u : 0u) | (nch > 0 ? 8u : 0u) |
-                                  (tile_ext ? 16u : 0u));
+    const uint32_t fl = sb_opaque((save_q ? 1u : 0u) | ((want_row || pit || gauge) ? 2u : 0u) | ((tile_ext && next > 0) ? 4u : 0u) |
+                                  (nch > 0 ? 8u : 0u) | (root_out ? 32u : 0u));
     const uint32_t qcol = sb_opaque(smem_u32(&qr[0][lane]));             // this lane's column of the runoff / discharge ring (rows 128 bytes apart)
     const uint32_t ecol = sb_opaque(smem_u32(&extv[0][lane]));
     const uint32_t pcol = sb_opaque(smem_u32(&ring_p[0][0][lane]));       // prcp boxes of this warp; the pet boxes lie SB_WARPS * SB_NST boxes further
@@ -221,36 +222,33 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
                     if (tb + i < T) __stcs(np_ + (size_t)(tb + i) * pitch, sb_lds(row + 128 * i));
             }
         }
-        // ================= routing, micro-ticks 8 kb .. 8 kb + 7: lane l is at time step t = m - delay(l)
-#pragma unroll 1
-        for (int mi = 0; mi < SB_W; mi++) {
-            const int m = kb * SB_W + mi;
+        // ================= routing, micro-ticks 8 kb .. 8 kb + 7: lane l is at time step t = m - delay(l).  In the interior groups
+        // every lane is inside [0, T) at every tick and the guards fall away.
+        auto tick = [&](const int m, auto guarded_t) {
+            constexpr bool GUARDED = decltype(guarded_t)::value;
             const int t = m - delay;
-            const bool active = valid && (unsigned)t < (unsigned)T;
-            // ---- inflow blocks of other tiles: once per window of this lane
-            if (fl & 16u) {
-                if (active && (fl & 4u) && (t & 7) == 0) {
-                    float acc[SB_W];
+            const bool active = GUARDED ? (valid && (unsigned)t < (unsigned)T) : true;
+            // ---- inflow blocks of other tiles: once per window of this lane (the lane's column of extv is its own)
+            if ((fl & 4u) && active && (t & 7) == 0) {
+                float acc[SB_W];
 #pragma unroll
-                    for (int i = 0; i < SB_W; i++) acc[i] = 0.0f;
-                    for (int e = 0; e < next; e++) {                      // md_routing_operator.f90:37-53 (inflows of other tiles first)
-                        const float *blk = a.X + ((size_t)tp.extlist[eoff + e] * nwin + (t >> 3)) * SB_W;
-                        float v[SB_W];
-                        int spins = 0;
-                        for (;;) {
-                            sb_ld8(blk, v);
-                            const float chk = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
-                            if (chk == chk || a.nowait) break;            // a NaN anywhere makes the sum a NaN
-                            __nanosleep(100);
-                            if (++spins > (1 << 21)) { atomicExch(a.err, 1 + tile); break; }
-                        }
-#pragma unroll
-                        for (int i = 0; i < SB_W; i++) acc[i] = acc[i] + v[i];
+                for (int i = 0; i < SB_W; i++) acc[i] = 0.0f;
+                for (int e = 0; e < next; e++) {                          // md_routing_operator.f90:37-53 (inflows of other tiles first)
+                    const float *blk = a.X + ((size_t)tp.extlist[eoff + e] * nwin + (t >> 3)) * SB_W;
+                    float v[SB_W];
+                    int spins = 0;
+                    for (;;) {
+                        sb_ld8(blk, v);
+                        const float chk = ((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]));
+                        if (chk == chk || a.nowait) break;                // a NaN anywhere makes the sum a NaN
+                        __nanosleep(100);
+                        if (++spins > (1 << 21)) { atomicExch(a.err, 1 + tile); break; }
                     }
 #pragma unroll
-                    for (int i = 0; i < SB_W; i++) sb_sts(ecol + 128 * i, acc[i]);
+                    for (int i = 0; i < SB_W; i++) acc[i] = acc[i] + v[i];
                 }
-                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < SB_W; i++) sb_sts(ecol + 128 * i, acc[i]);
             }
             // ---- the in-tile inflows sit in consecutive lanes: segmented sum of last micro-tick's discharge, then the parent reads
             // the lane of its last inflow (md_routing_operator.f90:37-53)
@@ -266,12 +264,12 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
             const float hr = hlr + qup * s_q;                             // :55-56, :73
             const float hn = hr * E;                                      // :75
             const float q = fmaf(hr - hn, fa1, qt) * c0;                  // :77, md_forward_structure.f90:155
-            hlr = active ? hn : hlr;
-            qprev = active ? q : 0.0f;
+            if (GUARDED) { hlr = active ? hn : hlr; qprev = active ? q : 0.0f; }
+            else { hlr = hn; qprev = q; }
             if (active) {
                 sb_sts(qcell, q);
+                if (fl & 32u) xo[t] = q;                                  // the root of a subtree: its series goes to another tile
                 if (fl & 2u) {
-                    if (root_out) xo[t] = q;
                     if (rowp) rowp[t] = q;
                     if (gauge && !pit)
                         for (int g = a.gauge_first[j]; g >= 0; g = a.gauge_next[g]) a.qsim[(size_t)t * ng + g] = q;   // :206-210
@@ -279,7 +277,15 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
             }
             // the row of time step m - dmax is complete: one coalesced row of the domain series
             const int tt = m - dmax;
-            if ((fl & 1u) && (unsigned)tt < (unsigned)T) { __stcs(qd, sb_lds(qcol + ((uint32_t)(tt & (SB_DL - 1)) << 7))); qd += pitch; }
+            if ((fl & 1u) && (!GUARDED || (unsigned)tt < (unsigned)T)) { __stcs(qd, sb_lds(qcol + ((uint32_t)(tt & (SB_DL - 1)) << 7))); qd += pitch; }
+        };
+        const int m0 = kb * SB_W;
+        if (m0 >= dmax && m0 + SB_W <= T) {
+#pragma unroll 1
+            for (int mi = 0; mi < SB_W; mi++) tick(m0 + mi, std::false_type());
+        } else {
+#pragma unroll 1
+            for (int mi = 0; mi < SB_W; mi++) tick(m0 + mi, std::true_type());
         }
     }
     // the reader of an exchange block waits for 8 numbers: fill what lies beyond the last time step
