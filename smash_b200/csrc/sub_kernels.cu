@@ -166,6 +166,11 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
     const uint32_t ecol = sb_opaque(smem_u32(&extv[0][lane]));
     const uint32_t pcol = sb_opaque(smem_u32(&ring_p[0][0][lane]));       // prcp boxes of this warp; the pet boxes lie SB_WARPS * SB_NST boxes further
 
+    // per-lane clock of the routing wavefront: time step, its row of the ring (byte offset), the row that completes this tick
+    int t = -delay;
+    uint32_t toff = ((uint32_t)(-delay) & (SB_DL - 1)) << 7;
+    const int ttshift = delay - dmax;
+    const uint32_t ttadd = ((uint32_t)(delay - dmax) & (SB_DL - 1)) << 7;
     const int ngroup = (T + dmax + SB_W - 1) / SB_W;                      // groups of 8 micro-ticks
     uint32_t parity = 0;
     int slot = 0;
@@ -224,12 +229,11 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
         }
         // ================= routing, micro-ticks 8 kb .. 8 kb + 7: lane l is at time step t = m - delay(l).  In the interior groups
         // every lane is inside [0, T) at every tick and the guards fall away.
-        auto tick = [&](const int m, auto guarded_t) {
+        auto tick = [&](auto guarded_t) {
             constexpr bool GUARDED = decltype(guarded_t)::value;
-            const int t = m - delay;
             const bool active = GUARDED ? (valid && (unsigned)t < (unsigned)T) : true;
             // ---- inflow blocks of other tiles: once per window of this lane (the lane's column of extv is its own)
-            if ((fl & 4u) && active && (t & 7) == 0) {
+            if ((fl & 4u) && active && (toff & 0x380u) == 0u) {
                 float acc[SB_W];
 #pragma unroll
                 for (int i = 0; i < SB_W; i++) acc[i] = 0.0f;
@@ -258,8 +262,8 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
             v = __shfl_up_sync(FULLM, x, 4); x = segpos >= 4 ? x + v : x;
             v = __shfl_sync(FULLM, x, lastc);
             float qup = (fl & 8u) ? v : 0.0f;
-            if (fl & 4u) qup += sb_lds(ecol + ((uint32_t)(t & 7) << 7));
-            const uint32_t qcell = qcol + ((uint32_t)(t & (SB_DL - 1)) << 7);
+            if (fl & 4u) qup += sb_lds(ecol + (toff & 0x380u));
+            const uint32_t qcell = qcol + toff;
             const float qt = sb_lds(qcell);
             const float hr = hlr + qup * s_q;                             // :55-56, :73
             const float hn = hr * E;                                      // :75
@@ -275,17 +279,21 @@ __global__ void __launch_bounds__(SB_WARPS * 32, 7) sub_forward_kernel(const __g
                         for (int g = a.gauge_first[j]; g >= 0; g = a.gauge_next[g]) a.qsim[(size_t)t * ng + g] = q;   // :206-210
                 }
             }
-            // the row of time step m - dmax is complete: one coalesced row of the domain series
-            const int tt = m - dmax;
-            if ((fl & 1u) && (!GUARDED || (unsigned)tt < (unsigned)T)) { __stcs(qd, sb_lds(qcol + ((uint32_t)(tt & (SB_DL - 1)) << 7))); qd += pitch; }
+            // the row of time step m - dmax = t + delay - dmax is complete: one coalesced row of the domain series
+            if ((fl & 1u) && (!GUARDED || (unsigned)(t + ttshift) < (unsigned)T)) {
+                __stcs(qd, sb_lds(qcol + ((toff + ttadd) & (SB_DL * 128u - 1u))));
+                qd += pitch;
+            }
+            t++;
+            toff = (toff + 128u) & (SB_DL * 128u - 1u);
         };
         const int m0 = kb * SB_W;
         if (m0 >= dmax && m0 + SB_W <= T) {
 #pragma unroll 1
-            for (int mi = 0; mi < SB_W; mi++) tick(m0 + mi, std::false_type());
+            for (int mi = 0; mi < SB_W; mi++) tick(std::false_type());
         } else {
 #pragma unroll 1
-            for (int mi = 0; mi < SB_W; mi++) tick(m0 + mi, std::true_type());
+            for (int mi = 0; mi < SB_W; mi++) tick(std::true_type());
         }
     }
     // the reader of an exchange block waits for 8 numbers: fill what lies beyond the last time step
