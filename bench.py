@@ -424,7 +424,10 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
     step_bytes = 12.0 * units
     pk_ms = np.mean(np.array(per_kernel), axis=0)
     window_pass = lib.smash_b200_plan_stat(plan, b"tick_pass") == 1.0
+    sub_engine = lib.smash_b200_plan_stat(plan, b"sub_engine") == 1.0
     names = ["tick_forward_kernel" if window_pass else "vertical_forward_kernel", "route_forward_kernel", "rows_to_domain_kernel"]
+    if sub_engine:
+        names = ["sub_forward_kernel", "route_pairs_kernel", "rows_to_domain_kernel"]
     kernels = {names[i]: {"ms": float(pk_ms[i]), "share": float(pk_ms[i] / kms), "dram_traffic_bytes": traffic.get(names[i])}
                for i in range(3) if pk_ms[i] > 0.02}
     tr = [k["dram_traffic_bytes"] for k in kernels.values()]
@@ -455,18 +458,18 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
                                    "route_adjoint_kernel": float(gk[3]), "vertical_adjoint_kernel": float(gk[4])}}
     lib.smash_b200_plan_destroy(plan)
 
-    # ---- the measured alternatives (opt-in engines that trade DRAM traffic against instructions), same workload
+    # ---- the other engines on the same workload (plan API, results resident): the row-based passes and the tick pass
     if not args.no_extra:
         roofline["alternatives"] = {}
-        notes = {"tick_pass": "opt-in (option tick_pass): every cell advances 8 steps per ticket, discharge blocks handed from producer "
-                              "to consumer; bound by the latency of a ticket, DESIGN.md section 3b",
-                 "sub_engine": "opt-in (option sub_engine): the engine's own cell order, subtrees of the drainage forest routed inside "
-                               "the warp, only subtree roots exchange series; DRAM traffic 1.16 x algorithmic, bound by instruction "
-                               "issue, DESIGN.md section 3e"}
-        kern = {"tick_pass": "tick_forward_kernel", "sub_engine": "sub_forward_kernel"}
-        for name in ("tick_pass", "sub_engine"):
-            lib.smash_b200_set_option(name.encode(), 1)
-            lib.smash_b200_set_option(b"sub_scatter", 0)                     # results stay in engine order
+        alts = {"row_passes": ({"sub_engine": 0, "tick_pass": 0}, ["vertical_forward_kernel", "route_forward_kernel"],
+                               "reservoir pass per cell + routing scan per heavy-path chain over rows [cell][time] (the engine of "
+                               "the drop-in calls and of the gradient): 2.2 x the algorithmic DRAM traffic, DESIGN.md section 3"),
+                "tick_pass": ({"sub_engine": 0, "tick_pass": 1}, ["tick_forward_kernel"],
+                              "every cell advances 8 steps per ticket, discharge blocks handed from producer to consumer; bound by the "
+                              "latency of a ticket, DESIGN.md section 3b")}
+        for name, (opts, kerns, note) in alts.items():
+            for k_, v_ in opts.items():
+                lib.smash_b200_set_option(k_.encode(), v_)
             try:
                 plan2 = C.c_void_p()
                 L.check(lib.smash_b200_plan_create(C.byref(s_), C.byref(m_), 1, C.byref(plan2)))
@@ -479,16 +482,16 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
                         tms.append(ms.value)
                 chk2 = C.c_double(0.0)
                 L.check(lib.smash_b200_plan_checksum(plan2, C.byref(chk2)))
-                on = lib.smash_b200_plan_stat(plan2, name.encode()) == 1.0
                 lib.smash_b200_plan_destroy(plan2)
-                tr2 = traffic.get(kern[name])
+                tr2 = [traffic.get(kn) for kn in kerns]
+                tr2 = float(sum(tr2)) if all(x is not None for x in tr2) else None
                 roofline["alternatives"][name] = {
-                    "ran": bool(on), "ms_per_step": float(np.mean(tms)), "frac": step_bytes / (float(np.mean(tms)) * 1e-3) / 1e9 / peak,
+                    "ms_per_step": float(np.mean(tms)), "frac": step_bytes / (float(np.mean(tms)) * 1e-3) / 1e9 / peak,
                     "dram_traffic_bytes": tr2, "traffic_over_algorithmic": (tr2 / step_bytes) if tr2 else None,
-                    "checksum_q": chk2.value, "note": notes[name]}
+                    "checksum_q": chk2.value, "note": note}
             finally:
-                lib.smash_b200_set_option(name.encode(), 0)
-                lib.smash_b200_set_option(b"sub_scatter", 1)
+                lib.smash_b200_set_option(b"sub_engine", -1)
+                lib.smash_b200_set_option(b"tick_pass", 0)
 
     # ---- the ANN mapping's forward pass at France scale: the graph of _ann_optimize.py:143-168 for nd = 6 descriptors
     ann = None
@@ -572,7 +575,9 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
         "ms_per_step": wall / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"France 1km mesh forward gr-a, nac={nac}, T={T}, save_qsim_domain (setup_France.yaml)",
-                   "engine": "split: " + ("tick pass (reservoirs + routing in one kernel)" if window_pass
+                   "engine": "subtree engine: one pass over the forcing, subtrees of the drainage forest routed inside a warp, results in "
+                             "the engine's column order (DESIGN.md section 3e)" if sub_engine else
+                             "split: " + ("tick pass (reservoirs + routing in one kernel)" if window_pass
                                           else "reservoir pass per cell + routing scan per heavy-path chain"),
                    "pit_pairs": int(info[6]), "l2": "inputs larger than L2 (5.2 GB forcing streamed once per step)",
                    "parallelism": "1 GPU", "checksum_q": chk.value, "model_build_s": t_build},

@@ -182,6 +182,7 @@ struct SmashPlan {
     WindowState win;
     SubState sub;
     bool sub_ran = false;           // the last forward sweep was the subtree engine: its error word is checked at the next synchronisation
+    bool plan_api = false;          // made by smash_b200_plan_create: results may stay in the engine's own column order
     std::vector<int32_t> col_cell;  // per device column (slot / cell j): flat rect index or -1 on padding
     int ncols = 0;                  // columns of the per-cell device arrays (fields, fstates, grad)
     int nmember = 0;
@@ -467,7 +468,10 @@ static int sub_build(SmashPlan &pl, const SmashMesh *mesh) {
     SubState &sb = pl.sub;
     const RouteGraph &rg = pl.sp.rg;
     sb.on = false;
-    if (!option("sub_engine", 0) || rg.n < option("sub_min_cells", 65536)) return 0;
+    // option sub_engine: -1 (default) = plans of the plan API (results stay on the device, in engine order); 1 = every eligible
+    // plan (the drop-in calls get their domain series back in cell order through a scatter pass); 0 = off
+    const long long mode = option("sub_engine", -1);
+    if (!(mode == 1 || (mode == -1 && pl.plan_api)) || rg.n < option("sub_min_cells", 65536)) return 0;
     if (!build_sub_topo(rg, 8, sb.host).empty()) return 0;
     cudaStream_t s = pl.stream;
     const size_t npad = (size_t)rg.npad;
@@ -710,7 +714,7 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
         CU(launch_sub_forward(sa, sb.tm_prcp, sb.tm_pet, pl.stream));
         mark(1);
         pl.launches += 1;
-        const bool scatter = option("sub_scatter", 1) != 0;               // results also in cell order j (what the exports read)
+        const bool scatter = !pl.plan_api || option("sub_scatter", 0) != 0;   // results also in cell order j (what the exports read)
         if (scatter) {
             if (save_q) CU(launch_scatter_columns(sb.d_qdom.p, sb.npad2, sb.d_cell.p, sb.npad2, pl.tp.T, sp.qpitch, pl.d_qdom.p, pl.stream));
             if (save_netp) CU(launch_scatter_columns(sb.d_netp.p, sb.npad2, sb.d_cell.p, sb.npad2, pl.tp.T, sp.qpitch, pl.d_netp.p, pl.stream));
@@ -1148,7 +1152,7 @@ static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **
              (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0, small ? 1 : 0,
              option("route_ded_min", 96) + 1024 * option("route_ded_max", 64) + (option("route_queues", 12) << 20) +
                  ((option("adjoint_checkpoint", -1) + 1) << 26) + (option("tape_budget_mb", 16384) << 28) +
-                 (option("tick_pass", 0) << 48) + (option("tick_slack", 1) << 49) + (option("shallow_acc", 32) << 50) + (option("sub_engine", 0) << 58));
+                 (option("tick_pass", 0) << 48) + (option("tick_slack", 1) << 49) + (option("shallow_acc", 32) << 50) + ((option("sub_engine", -1) + 1) << 58));
     auto it = g_plans.find(key);
     if (it == g_plans.end()) {
         std::unique_ptr<SmashPlan> pl(new SmashPlan());
@@ -1654,6 +1658,7 @@ extern "C" int smash_b200_plan_create(const SmashSetup *setup, const SmashMesh *
     TRY(check_device());
     std::unique_ptr<SmashPlan> pl(new SmashPlan());
     pl->small_windows = option("plan_small_windows", 0) != 0;          // diagnostics: 256-step routing windows in a resident plan
+    pl->plan_api = true;
     TRY(plan_build(*pl, setup, mesh, nmember, nmember > 1 ? (int)option("ensemble_engine", -1) : -1));
     pl->nmember = nmember > 0 ? nmember : 1;
     pl->ensemble = nmember > 1;
@@ -1799,7 +1804,7 @@ extern "C" int smash_b200_plan_get_gradient(SmashPlan *plan, SmashParameters *pa
 extern "C" int smash_b200_plan_checksum(SmashPlan *plan, double *sum_q) {
     if (!plan || !sum_q) return fail(SMASH_B200_EINVAL, "NULL argument");
     if (!plan->d_qdom.p) return fail(SMASH_B200_EINVAL, "plan keeps no domain discharge");
-    if (plan->engine == 1 && plan->sub.on && plan->sub.d_qdom.p && !option("sub_scatter", 1))
+    if (plan->engine == 1 && plan->sub.on && plan->sub.d_qdom.p && plan->plan_api && !option("sub_scatter", 0))
         CU(launch_sum_domain(plan->sub.d_qdom.p, plan->sub.npad2, plan->sub.npad2, plan->tp.T, plan->d_sum.p, plan->stream));
     else if (plan->engine == 1) CU(launch_sum_domain(plan->d_qdom.p, plan->sp.qpitch, plan->sp.rg.n, plan->tp.T, plan->d_sum.p, plan->stream));
     else CU(launch_checksum(plan->dtp, plan->d_qdom.p, plan->d_sum.p, plan->stream));

@@ -228,7 +228,7 @@ def _run_window(m, opts):
     finally:
         for k in opts:
             lib.smash_b200_set_option(k.encode(), {"tick_pass": 0, "shallow_acc": 32, "tick_variant": 8, "tick_min_cells": 65536,
-                                                   "tick_ctas_per_sm": 0, "sub_engine": 0, "sub_min_cells": 65536, "sub_scatter": 1}[k])
+                                                   "tick_ctas_per_sm": 0, "sub_engine": -1, "sub_min_cells": 65536, "sub_scatter": 0}[k])
         lib.smash_b200_clear_cache()
 
 

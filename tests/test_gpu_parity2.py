@@ -433,14 +433,28 @@ def _pit_pair_cells(mesh):
     return rr[back], cc[back]
 
 
-def test_france_full_size_against_oracle_on_basins():
+@pytest.mark.parametrize("engine", ["row_passes", "subtree"])
+def test_france_full_size_against_oracle_on_basins(engine):
+    # engine: the row-based passes of the drop-in call (streamed), and the subtree engine that the plan API -- and with it the
+    # bench -- runs (here forced into the drop-in call: the forcing goes up in one piece, the series come back through the
+    # scatter pass).
     # BASELINE.json's bench configuration at its own size (906 044 cells, T = 720, sparse_qsim_domain): the device series of
     # the whole domain against the CPU oracle on the Loire basin (136 170 cells, the longest rivers of the mesh), three
     # other basins and basins that end in a pit pair -- the oracle computes a basin alone through mesh%local_active_cell
     # (md_forward_structure.f90:88), which is exact because basins exchange nothing.  Reports the measured differences.
     from smash_b200 import distributed as D
     m = cases.france(T=720)
-    smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
+    lib = L.lib()
+    if engine == "subtree":
+        lib.smash_b200_set_option(b"sub_engine", 1)
+        lib.smash_b200_set_option(b"stream", 0)
+        lib.smash_b200_clear_cache()
+    try:
+        smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
+    finally:
+        lib.smash_b200_set_option(b"sub_engine", -1)
+        lib.smash_b200_set_option(b"stream", 1)
+        lib.smash_b200_clear_cache()
     gpu = m.output.sparse_qsim_domain
     labels, nb = D.basin_labels(m.mesh, m.setup)
     size = np.bincount(labels[labels >= 0], minlength=nb)

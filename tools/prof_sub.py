@@ -3,7 +3,6 @@ sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import numpy as np, cases
 from smash_b200 import _lib as L
 lib = L.lib()
-lib.smash_b200_set_option(b"sub_engine", 1); lib.smash_b200_set_option(b"sub_scatter", 0)
 m = cases.france(T=720)
 pk = L.Packed()
 s_, m_, i_ = L.pack_setup(m.setup, m.mesh, pk), L.pack_mesh(m.mesh, m.setup, pk), L.pack_input(m.input_data, m.setup, m.mesh, pk)

@@ -13,7 +13,7 @@ ap.add_argument("sets", nargs="*", default=["base"])
 a = ap.parse_args()
 lib = L.lib()
 m = cases.france(T=a.T)
-DEFAULTS = {"tick_pass": 0, "sub_engine": 0, "sub_scatter": 1, "tick_nb": 2, "tick_slack": 1, "tick_dbg": 0, "shallow_acc": 32, "tick_variant": 8, "tick_ctas_per_sm": 0, "fuse_export": 4}
+DEFAULTS = {"tick_pass": 0, "sub_engine": -1, "sub_scatter": 0, "tick_nb": 2, "tick_slack": 1, "tick_dbg": 0, "shallow_acc": 32, "tick_variant": 8, "tick_ctas_per_sm": 0, "fuse_export": 4}
 for st in a.sets:
     opts = dict(DEFAULTS)
     if st != "base":
