@@ -134,7 +134,8 @@ struct SubState {
     SubTopoHost host;
     SplitState pits;               // route graph of the pit pairs and its device image
     int npad2 = 0;
-    DBuf<int32_t> d_cell, d_rec, d_xout, d_extoff, d_extlist, d_idx_raw, d_pit_to_engine;
+    DBuf<int32_t> d_cell, d_rec, d_xout, d_extoff, d_extlist, d_idx_raw, d_pit_j, d_pit_jp;
+    int npit = 0;
     DBuf<uint32_t> d_child;
     DBuf<uint8_t> d_kmax, d_ext;
     DBuf<float> d_X, d_pk_prcp, d_pk_pet, d_qdom, d_netp;
@@ -489,16 +490,19 @@ static int sub_build(SmashPlan &pl, const SmashMesh *mesh) {
         TRY(sb.pits.d_done.ensure(std::max<size_t>(1, 2 * (size_t)sb.pits.rg.ntask)));
     }
     sb.idx_sparse.assign(sb.npad2, -1); sb.idx_dense.assign(sb.npad2, -1);
-    std::vector<int32_t> pit_to_engine(npad, -1);
+    std::vector<int32_t> pit_j, pit_jp;                                   // the pit cells: cell order j and engine column j'
     for (int jp = 0; jp < sb.npad2; jp++) {
         const int j = sb.host.cell[jp];
         if (j < 0) continue;
         sb.idx_sparse[jp] = rg.sparse_k[j]; sb.idx_dense[jp] = rg.cell[j];
-        if (sb.host.pair[j]) pit_to_engine[j] = jp;
+        if (sb.host.pair[j]) { pit_j.push_back(j); pit_jp.push_back(jp); }
     }
+    sb.npit = (int)pit_j.size();
+    if (pit_j.empty()) { pit_j.push_back(0); pit_jp.push_back(0); }
     TRY(sb.d_cell.upload(sb.host.cell, s)); TRY(sb.d_rec.upload(sb.host.rec, s)); TRY(sb.d_child.upload(sb.host.child, s));
     TRY(sb.d_xout.upload(sb.host.xout, s)); TRY(sb.d_extoff.upload(sb.host.extoff, s)); TRY(sb.d_extlist.upload(sb.host.extlist, s));
-    TRY(sb.d_kmax.upload(sb.host.tile_kmax, s)); TRY(sb.d_ext.upload(sb.host.tile_ext, s)); TRY(sb.d_pit_to_engine.upload(pit_to_engine, s));
+    TRY(sb.d_kmax.upload(sb.host.tile_kmax, s)); TRY(sb.d_ext.upload(sb.host.tile_ext, s));
+    TRY(sb.d_pit_j.upload(pit_j, s)); TRY(sb.d_pit_jp.upload(pit_jp, s));
     TRY(sb.d_err.ensure(1));
     SbTopo &t = sb.topo;
     t.ntile = sb.host.ntile; t.ng = mesh->ng; t.nslot = sb.host.nslot; t.dmax = sb.host.dmax;
@@ -726,7 +730,7 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
             CU(launch_route_forward(b, false, pl.stream));
             pl.launches += sp.nwin * 2;
             // the pit cells' columns into the engine-order arrays too
-            if (save_q) CU(launch_scatter_columns(pl.d_qdom.p, sp.qpitch, sb.d_pit_to_engine.p, sp.rg.n, pl.tp.T, sb.npad2, sb.d_qdom.p, pl.stream));
+            if (save_q) CU(launch_copy_columns(pl.d_qdom.p, sp.qpitch, sb.d_pit_j.p, sb.d_pit_jp.p, sb.npit, pl.tp.T, sb.npad2, sb.d_qdom.p, pl.stream));
         }
         mark(2); mark(3);
         pl.sub_ran = true;

@@ -1732,6 +1732,20 @@ cudaError_t launch_scatter_columns(const float *src, int64_t pitch, const int32_
     scatter_columns_kernel<<<grid, 256, 0, s>>>(src, pitch, idx, n, T, stride, out);
     return cudaGetLastError();
 }
+// out[t * stride + didx[i]] = src[t * pitch + sidx[i]], i < n: a handful of columns from one layout into another
+__global__ void copy_columns_kernel(const float *src, int64_t pitch, const int32_t *sidx, const int32_t *didx, int n, int T, int64_t stride,
+                                    float *out) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    const int a = sidx[i], b = didx[i];
+    for (int t = threadIdx.x; t < T; t += blockDim.x) out[(int64_t)t * stride + b] = src[(int64_t)t * pitch + a];
+}
+cudaError_t launch_copy_columns(const float *src, int64_t pitch, const int32_t *sidx, const int32_t *didx, int n, int T, int64_t stride,
+                                float *out, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    copy_columns_kernel<<<n, 256, 0, s>>>(src, pitch, sidx, didx, n, T, stride, out);
+    return cudaGetLastError();
+}
 cudaError_t launch_sum_domain(const float *src, int64_t pitch, int n, int T, double *out, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), s);
     if (e != cudaSuccess) return e;

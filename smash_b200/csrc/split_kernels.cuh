@@ -196,6 +196,9 @@ cudaError_t launch_pack_columns(const float *raw, int64_t stride, const int32_t 
 // out[t * stride + idx[j]] = src[t * pitch + j]
 cudaError_t launch_scatter_columns(const float *src, int64_t pitch, const int32_t *idx, int n, int T, int64_t stride, float *out,
                                    cudaStream_t s);
+// out[t * stride + didx[i]] = src[t * pitch + sidx[i]], i < n
+cudaError_t launch_copy_columns(const float *src, int64_t pitch, const int32_t *sidx, const int32_t *didx, int n, int T, int64_t stride,
+                                float *out, cudaStream_t s);
 // sum over t < T, j < n of a [T][pitch] array (double accumulation)
 cudaError_t launch_sum_domain(const float *src, int64_t pitch, int n, int T, double *out, cudaStream_t s);
 
