@@ -58,6 +58,9 @@ def _lib(precision: str):
     return _libs[precision]
 
 
+STRUCTURES = {"gr-a": 1, "gr-b": 2, "gr-c": 3, "gr-d": 4, "vic-a": 5}   # OST_* of smash_oracle.h
+
+
 def _make_struct(real):
     rp, ip = C.POINTER(real), C.POINTER(C.c_int32)
 
@@ -74,7 +77,7 @@ def _make_struct(real):
             ("denormalize_forward", C.c_int), ("optimize_start_step", C.c_int), ("mapping", C.c_int), ("nhyper", C.c_int),
             ("optim_parameters", ip), ("optim_states", ip),
             ("lb_parameters", rp), ("ub_parameters", rp), ("lb_states", rp), ("ub_states", rp), ("wgauge", rp),
-            ("mean_prcp", rp), ("mask_event", ip),
+            ("mean_prcp", rp), ("mask_event", ip), ("structure", C.c_int),
         ]
 
     return OProblem
@@ -112,6 +115,7 @@ class _Ctx:
 def _problem(ctx: _Ctx, setup, mesh, input_data):
     o = setup._optimize
     P = ctx.S()
+    P.structure = STRUCTURES[str(getattr(setup, "structure", "gr-a")).strip()]   # forward.f90:43
     P.ntime_step, P.nd, P.dt = int(setup._ntime_step), int(setup._nd), float(setup.dt)
     P.sparse_storage = int(bool(setup.sparse_storage))
     P.save_qsim_domain, P.save_net_prcp_domain = int(bool(setup.save_qsim_domain)), int(bool(setup.save_net_prcp_domain))

@@ -226,6 +226,173 @@ static void gr_a_forward(const Prob *P, const oreal *par, oreal *st, oreal *qsim
 }
 
 /* ============================================================================================
+ * The other structures -- forward/md_forward_structure.f90:216-931, operator/md_gr_operator.f90:20-34,
+ * operator/md_vic_operator.f90.  Forward only (the reference's tests and golden file hold no vector of
+ * these structures: parity of this part is UNPINNED, see the header).
+ * ========================================================================================== */
+
+/* md_gr_operator.f90:20-34 */
+static void gr_interception(oreal prcp, oreal pet, oreal ci, oreal *hi, oreal *pn, oreal *ei) {
+    *ei = fmin(pet, prcp + (*hi) * ci);
+    *pn = fmax(R(0.0), prcp - ci * (R(1.0) - (*hi)) - (*ei));
+    *hi = (*hi) + (prcp - (*ei) - (*pn)) / ci;
+}
+
+/* md_vic_operator.f90:21-77 */
+static void vic_infiltration(oreal prcp, oreal cusl1, oreal cusl2, oreal b, oreal *husl1, oreal *husl2, oreal *runoff) {
+    oreal bp1 = b + R(1.0), ifl;
+    if (prcp <= R(0.0)) {
+        ifl = R(0.0);
+    } else {
+        oreal cusl = cusl1 + cusl2;
+        oreal wusl = (*husl1) * cusl1 + (*husl2) * cusl2;
+        wusl = fmax(R(1.e-6), wusl);
+        wusl = fmin(cusl - R(1e-6), wusl);
+        oreal iflm = cusl * bp1;
+        oreal iflc = iflm * (R(1.0) - POW(R(1.0) - (wusl / cusl), R(1.0) / bp1));
+        if (iflc + prcp >= iflm) ifl = cusl - wusl;
+        else ifl = (cusl - wusl) - cusl * POW(R(1.0) - ((iflc + prcp) / iflm), bp1);
+        ifl = fmin(prcp, ifl);
+    }
+    oreal ifl_usl1 = fmin((R(1.0) - (*husl1)) * cusl1, ifl);
+    ifl = ifl - ifl_usl1;
+    oreal ifl_usl2 = fmin((R(1.0) - (*husl2)) * cusl2, ifl);
+    ifl = ifl - ifl_usl2;
+    *husl1 = (*husl1) + ifl_usl1 / cusl1;
+    *husl2 = (*husl2) + ifl_usl2 / cusl2;
+    *runoff = prcp - (ifl_usl1 + ifl_usl2);
+}
+
+/* md_vic_operator.f90:165-183, called with residual = 0, porosity = 1, lambda = 1 (:88, :92) */
+static oreal brooks_and_corey_flow(oreal ks, oreal residual, oreal porosity, oreal lambda, oreal c_upper, oreal c_lower,
+                                   oreal h_upper, oreal h_lower) {
+    oreal flow = ks * POW((h_upper - residual) / (porosity - residual), lambda);
+    oreal w_upper = h_upper * c_upper * porosity;
+    oreal w_lower = h_lower * c_lower * porosity;
+    oreal max_flow = fmin(w_upper, c_lower - w_lower);
+    return fmin(max_flow, flow);
+}
+
+/* md_vic_operator.f90:185-200 */
+static oreal linear_evapotranspiration(oreal e, oreal c, oreal h) { return fmin(c * h, e * h); }
+
+/* md_vic_operator.f90:79-114 */
+static void vic_vertical_transfer(oreal pet, oreal cusl1, oreal cusl2, oreal clsl, oreal ks, oreal *husl1, oreal *husl2,
+                                  oreal *hlsl) {
+    oreal fbc = brooks_and_corey_flow(ks, R(0.0), R(1.0), R(1.0), cusl1, cusl2, *husl1, *husl2);
+    *husl1 = (*husl1) - fbc / cusl1;
+    *husl2 = (*husl2) + fbc / cusl2;
+    fbc = brooks_and_corey_flow(ks, R(0.0), R(1.0), R(1.0), cusl2, clsl, *husl2, *hlsl);
+    *husl2 = (*husl2) - fbc / cusl2;
+    *hlsl = (*hlsl) + fbc / clsl;
+    oreal fe = linear_evapotranspiration(pet, cusl1, *husl1);
+    *husl1 = (*husl1) - fe / cusl1;
+    oreal pet_remain = fmax(R(0.0), pet - fe);
+    fe = linear_evapotranspiration(pet_remain, cusl2, *husl2);
+    *husl2 = (*husl2) - fe / cusl2;
+    pet_remain = fmax(R(0.0), pet_remain - fe);
+    fe = linear_evapotranspiration(pet_remain, clsl, *hlsl);
+    *hlsl = (*hlsl) - fe / clsl;
+}
+
+/* md_vic_operator.f90:116-135 */
+static void vic_interflow(oreal n, oreal cusl2, oreal *husl2, oreal *qi) {
+    oreal nm1 = n - R(1.0), d1pnm1 = R(1.0) / nm1, h0 = *husl2;
+    *husl2 = POW(POW(h0 * cusl2, -nm1) + POW(cusl2, -nm1), -d1pnm1) / cusl2;
+    *qi = (h0 - (*husl2)) * cusl2;
+}
+
+/* md_vic_operator.f90:137-163 */
+static void vic_baseflow(oreal clsl, oreal ds, oreal dsm, oreal ws, oreal *hlsl, oreal *qb) {
+    if ((*hlsl) <= ws) *qb = (ds * dsm) / ws * (*hlsl);
+    else *qb = dsm * (R(1.0) - ds / ws) * ((*hlsl) - ws) / (R(1.0) - ws);
+    *qb = fmin(clsl * (*hlsl), *qb);
+    *hlsl = (*hlsl) - (*qb) / clsl;
+}
+
+/* gr_b_forward :216-398, gr_c_forward :400-587, gr_d_forward :589-760, vic_a_forward :762-931: the loop skeleton of
+ * gr_a_forward with another runoff-production part (the lines cited per branch); routing and stores are the same */
+static void structure_forward(const Prob *P, const oreal *par, oreal *st, oreal *qsim, oreal *qdom, oreal *netp) {
+    const size_t ncell = (size_t)P->nrow * P->ncol;
+    const oreal *ci = par + OP_CI * ncell, *cp = par + OP_CP * ncell, *cft = par + OP_CFT * ncell, *cst = par + OP_CST * ncell,
+                *exc = par + OP_EXC * ncell, *lr = par + OP_LR * ncell, *b = par + OP_B * ncell, *cusl1 = par + OP_CUSL1 * ncell,
+                *cusl2 = par + OP_CUSL2 * ncell, *clsl = par + OP_CLSL * ncell, *ks = par + OP_KS * ncell, *ds = par + OP_DS * ncell,
+                *dsm = par + OP_DSM * ncell, *ws = par + OP_WS * ncell;
+    oreal *hi = st + OS_HI * ncell, *hp = st + OS_HP * ncell, *hft = st + OS_HFT * ncell, *hst = st + OS_HST * ncell,
+          *husl1 = st + OS_HUSL1 * ncell, *husl2 = st + OS_HUSL2 * ncell, *hlsl = st + OS_HLSL * ncell, *hlr = st + OS_HLR * ncell;
+    oreal *q = (oreal *)calloc(ncell, sizeof(oreal));
+    const int S = P->structure;
+
+    for (int t = 0; t < P->ntime_step; t++) {
+        for (size_t i = 0; i < ncell; i++) {
+            int row = P->path[2 * i], col = P->path[2 * i + 1];
+            if (!(row > 0 && col > 0)) continue;
+            size_t c = IDX(P, row, col);
+            if (!(P->active_cell[c] == 1 && (!P->local_active_cell || P->local_active_cell[c] == 1))) continue;
+            oreal prcp, pet, qt, qup = 0, qrout = 0;
+            read_forcing(P, row, col, t, &prcp, &pet);
+            const int nogap = (prcp >= 0 && pet >= 0);
+            if (S == OST_VIC_A) {
+                oreal runoff = 0, qi = 0, qb = 0;                                    /* :797-804 */
+                if (nogap) {
+                    vic_infiltration(prcp, cusl1[c], cusl2[c], b[c], &husl1[c], &husl2[c], &runoff);          /* :843 */
+                    vic_vertical_transfer(pet, cusl1[c], cusl2[c], clsl[c], ks[c], &husl1[c], &husl2[c], &hlsl[c]); /* :851 */
+                }
+                vic_interflow(R(5.0), cusl2[c], &husl2[c], &qi);                    /* :861 */
+                vic_baseflow(clsl[c], ds[c], dsm[c], ws[c], &hlsl[c], &qb);         /* :863 */
+                qt = (runoff + qi + qb);                                            /* :866 */
+            } else {
+                oreal ei, pn = 0, en = 0, pr = 0, perc = 0, l = 0, prr, prl, prd, qr = 0, ql = 0, qd;
+                if (nogap) {
+                    if (S == OST_GR_D) {
+                        ei = fmin(pet, prcp);                                       /* :666 */
+                        pn = fmax(R(0.0), prcp - ei);                               /* :668 */
+                    } else {
+                        gr_interception(prcp, pet, ci[c], &hi[c], &pn, &ei);        /* :298, :482 */
+                    }
+                    en = pet - ei;
+                    gr_production(pn, en, cp[c], R(1000.0), &hp[c], &pr, &perc);    /* :306, :490, :676 */
+                    if (S != OST_GR_D) gr_exchange(exc[c], hft[c], &l);             /* :313, :497 */
+                }
+                if (S == OST_GR_B) {
+                    prr = R(0.9) * (pr + perc) + l;                                 /* :321 */
+                    prd = R(0.1) * (pr + perc);                                     /* :322 */
+                    gr_transfer(R(5.0), prcp, prr, cft[c], &hft[c], &qr);           /* :324 */
+                    qd = fmax(R(0.0), prd + l);                                     /* :326 */
+                    qt = (qr + qd);                                                 /* :328 */
+                } else if (S == OST_GR_C) {
+                    prr = R(0.9) * R(0.6) * (pr + perc) + l;                        /* :505 */
+                    prl = R(0.9) * R(0.4) * (pr + perc);                            /* :506 */
+                    prd = R(0.1) * (pr + perc);                                     /* :507 */
+                    gr_transfer(R(5.0), prcp, prr, cft[c], &hft[c], &qr);           /* :509 */
+                    gr_transfer(R(5.0), prcp, prl, cst[c], &hst[c], &ql);           /* :511 */
+                    qd = fmax(R(0.0), prd + l);                                     /* :513 */
+                    qt = (qr + ql + qd);                                            /* :515 */
+                } else {
+                    prr = pr + perc;                                                /* :685 */
+                    gr_transfer(R(5.0), prcp, prr, cft[c], &hft[c], &qr);           /* :687 */
+                    qt = qr;                                                        /* :689 */
+                }
+            }
+            upstream_discharge(P, row, col, q, &qup);
+            linear_routing(P->dt, qup, lr[c], &hlr[c], &qrout);
+            q[c] = (qt + qrout * (oreal)(P->flwacc[c] - 1)) * P->dx * P->dx * R(0.001) / P->dt;
+            if (netp) {
+                if (P->sparse_storage) netp[(size_t)P->rowcol_to_ind_sparse[c] - 1 + (size_t)P->nac * t] = qt;
+                else netp[c + ncell * t] = qt;
+            }
+            if (qdom) {
+                if (P->sparse_storage) qdom[(size_t)P->rowcol_to_ind_sparse[c] - 1 + (size_t)P->nac * t] = q[c];
+                else qdom[c + ncell * t] = q[c];
+            }
+        }
+        for (int g = 0; g < P->ng; g++)
+            qsim[g + (size_t)P->ng * t] = q[IDX(P, P->gauge_pos[g], P->gauge_pos[g + P->ng])];
+    }
+    free(q);
+}
+
+/* ============================================================================================
  * Operator adjoints -- forward/forward_db.f90
  * ========================================================================================== */
 
@@ -925,6 +1092,12 @@ static oreal compute_cost(const Prob *P, oreal *par, const oreal *par_bgd, oreal
     return cost;
 }
 
+/* select case (trim(setup%structure)) forward.f90:43-65, :120-142 */
+static void run_structure(const Prob *P, const oreal *par, oreal *st, oreal *qsim, oreal *qdom, oreal *netp) {
+    if (P->structure <= OST_GR_A) gr_a_forward(P, par, st, qsim, qdom, netp, NULL);
+    else structure_forward(P, par, st, qsim, qdom, netp);
+}
+
 /* ============================================================================================
  * base_forward -- forward/forward.f90:1-80
  * ========================================================================================== */
@@ -938,8 +1111,8 @@ int OSYM(oracle_forward)(const Prob *P, oreal *parameters, const oreal *paramete
     }
     oreal *states_imd = (oreal *)malloc(O_GNS * ncell * sizeof(oreal));
     memcpy(states_imd, states, O_GNS * ncell * sizeof(oreal)); /* :41 */
-    gr_a_forward(P, parameters, states, qsim, P->save_qsim_domain ? qsim_domain : NULL,
-                 P->save_net_prcp_domain ? net_prcp_domain : NULL, NULL); /* :47 */
+    run_structure(P, parameters, states, qsim, P->save_qsim_domain ? qsim_domain : NULL,
+                  P->save_net_prcp_domain ? net_prcp_domain : NULL);   /* :43-65 */
     if (fstates) memcpy(fstates, states, O_GNS * ncell * sizeof(oreal));     /* :71 */
     memcpy(states, states_imd, O_GNS * ncell * sizeof(oreal));              /* :72 */
     free(states_imd);
@@ -954,6 +1127,7 @@ int OSYM(oracle_forward_b)(const Prob *P, oreal *parameters, oreal *parameters_b
                            oreal *states, oreal *states_b, const oreal *states_bgd, oreal *qsim, oreal *out_cost) {
     const size_t ncell = (size_t)P->nrow * P->ncol;
     const oreal cost_b = R(1.0);
+    if (P->structure > OST_GR_A) return 2;               /* only GR_A_FORWARD_B is restated */
     if (P->denormalize_forward) {                       /* :10697-10703 */
         denormalize(P, parameters, O_GNP, P->lb_parameters, P->ub_parameters);
         denormalize(P, states, O_GNS, P->lb_states, P->ub_states);
@@ -1069,7 +1243,7 @@ int OSYM(oracle_hyper_forward)(const Prob *P, oreal *parameters, const oreal *hy
     const size_t ncell = (size_t)P->nrow * P->ncol;
     hyper_to_field(P, hyper_parameters, parameters, O_GNP, P->lb_parameters, P->ub_parameters);
     hyper_to_field(P, hyper_states, states, O_GNS, P->lb_states, P->ub_states);
-    gr_a_forward(P, parameters, states, qsim, NULL, NULL, NULL);
+    run_structure(P, parameters, states, qsim, NULL, NULL);
     if (fstates) memcpy(fstates, states, O_GNS * ncell * sizeof(oreal));
     oreal jobs = compute_jobs(P, qsim, NULL, 0); /* hyper_compute_cost mwd_cost.f90:309-348 */
     if (out_cost) { out_cost[0] = jobs + P->wjreg * R(0.0); out_cost[1] = jobs; out_cost[2] = 0; }
@@ -1081,6 +1255,7 @@ int OSYM(oracle_hyper_forward_b)(const Prob *P, oreal *parameters, const oreal *
                                  oreal *hyper_parameters_b, oreal *states, const oreal *hyper_states,
                                  oreal *hyper_states_b, oreal *qsim, oreal *out_cost) {
     const size_t ncell = (size_t)P->nrow * P->ncol;
+    if (P->structure > OST_GR_A) return 2;
     hyper_to_field(P, hyper_parameters, parameters, O_GNP, P->lb_parameters, P->ub_parameters);
     hyper_to_field(P, hyper_states, states, O_GNS, P->lb_states, P->ub_states);
     oreal *st0 = (oreal *)malloc(O_GNS * ncell * sizeof(oreal));

@@ -45,6 +45,9 @@ enum { OP_CI = 0, OP_CP, OP_BETA, OP_CFT, OP_CST, OP_ALPHA, OP_EXC, OP_B, OP_CUS
 /* state planes (md_constant.f90:57-69) */
 enum { OS_HI = 0, OS_HP, OS_HFT, OS_HST, OS_HUSL1, OS_HUSL2, OS_HLSL, OS_HLR };
 
+/* setup%structure (mwd_setup.f90:113, _constant.py STRUCTURE_PARAMETERS) */
+enum { OST_GR_A = 1, OST_GR_B = 2, OST_GR_C = 3, OST_GR_D = 4, OST_VIC_A = 5 };
+
 /* jobs_fun codes (mwd_cost.f90:98-131) */
 enum { OJ_NSE = 1, OJ_KGE = 2, OJ_KGE2 = 3, OJ_SE = 4, OJ_RMSE = 5, OJ_LOGARITHMIC = 6,
        /* signatures (mwd_cost.f90:117-122, 772-970): continuous Crc, Cfp2/10/50/90; event-based Erc, Elt, Epf */
@@ -84,6 +87,7 @@ typedef struct {
     /* signature objectives only (may be NULL otherwise) */
     const oreal *mean_prcp;                     /* Input_DataDT%mean_prcp (ng,T) */
     const int *mask_event;                      /* Optimize_SetupDT%mask_event (ng,T): event number of every step, 0 = none */
+    int structure;                              /* OST_* (0 = gr-a); the adjoint and multiple_run entry points take gr-a only */
 } OSYM(OProblem);
 
 #ifdef __cplusplus

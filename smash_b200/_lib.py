@@ -154,10 +154,8 @@ def pack_setup(setup, mesh, pk: Packed) -> SmashSetup:
     s = SmashSetup()
     if setup.structure not in STRUCTURES:
         raise ValueError(f"unknown structure {setup.structure!r}")
-    if setup.structure != "gr-a":
-        # the device kernels cover gr-a (md_forward_structure.f90:30-214); fail before any packing or upload work
-        raise NotImplementedError(f"structure {setup.structure!r}: smash_b200 implements 'gr-a' only "
-                                  "(gr-b, gr-c, gr-d, vic-a are listed as next in DESIGN.md section 7); there is no CPU fallback")
+    # gr-a: every entry point.  gr-b, gr-c, gr-d, vic-a (md_forward_structure.f90:216-931): forward runs (forward,
+    # compute_multiple_run, the plan API); the library answers SMASH_B200_EUNSUPPORTED to their adjoint and descriptor mappings
     s.structure = STRUCTURES[setup.structure]
     s.dt = float(setup.dt)
     s.ntime_step = int(setup._ntime_step)

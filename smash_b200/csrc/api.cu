@@ -183,6 +183,7 @@ struct SmashPlan {
     WindowState win;
     SubState sub;
     bool sub_ran = false;           // the last forward sweep was the subtree engine: its error word is checked at the next synchronisation
+    int structure = SMASH_STRUCTURE_GR_A;   // setup%structure; the others run forward only, on the row passes (struct_kernels.cu)
     bool plan_api = false;          // made by smash_b200_plan_create: results may stay in the engine's own column order
     std::vector<int32_t> col_cell;  // per device column (slot / cell j): flat rect index or -1 on padding
     int ncols = 0;                  // columns of the per-cell device arrays (fields, fstates, grad)
@@ -207,6 +208,8 @@ struct SmashPlan {
     DBuf<ExtRef> d_ext, d_rext;
     DBuf<int64_t> d_tick_base;
     // data
+    DBuf<float> d_splanes, d_sfields, d_sfstates;   // structures other than gr-a: [24][ncell], [m][24][npad], [m][8][npad]
+    DBuf<int32_t> d_sample_plane;
     DBuf<float> d_forcing, d_raw_prcp, d_raw_pet, d_planes, d_fields, d_fstates, d_qsim, d_qdom, d_netp, d_tape, d_qsim_b,
         d_wdom, d_grad, d_cost_jobs, d_qobs, d_area, d_wgauge, d_sample, d_out;
     DBuf<int32_t> d_gauge_flwacc, d_sample_field, d_mask_event;
@@ -276,8 +279,9 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
 
 static int plan_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, int nmember, int engine = -1) {
     if (!setup || !mesh) return fail(SMASH_B200_EINVAL, "setup / mesh is NULL");
-    if (setup->structure != SMASH_STRUCTURE_GR_A)
-        return fail(SMASH_B200_EUNSUPPORTED, "structure %d: only gr-a is implemented on the device", setup->structure);
+    if (setup->structure < SMASH_STRUCTURE_GR_A || setup->structure > SMASH_STRUCTURE_VIC_A)
+        return fail(SMASH_B200_EINVAL, "unknown structure %d", setup->structure);
+    pl.structure = setup->structure;
     if (!mesh->flwdir || !mesh->flwacc || !mesh->active_cell || !mesh->path) return fail(SMASH_B200_EINVAL, "mesh arrays missing");
     if (mesh->ng > 0 && (!mesh->gauge_pos || !mesh->area)) return fail(SMASH_B200_EINVAL, "mesh.gauge_pos / area missing");
     // count computed cells to pick the block size
@@ -287,11 +291,14 @@ static int plan_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *m
         if (mesh->active_cell[c] == 1 && (!mesh->local_active_cell || mesh->local_active_cell[c] == 1)) nact++;
     pl.sparse = setup->sparse_storage ? 1 : 0;
     pl.engine = pick_engine(engine);
+    if (pl.structure != SMASH_STRUCTURE_GR_A) pl.engine = 1;   // their reservoir pass belongs to the row passes
     if (pl.engine == 1) {
         bool unsupported = false;
         const int rc = split_build(pl, setup, mesh, &unsupported);
         if (rc == 0) return 0;
         if (!unsupported) return rc;
+        if (pl.structure != SMASH_STRUCTURE_GR_A)
+            return fail(SMASH_B200_EUNSUPPORTED, "structure %d on a mesh the row passes do not handle: %s", pl.structure, g_err.c_str());
         pl.engine = 0;   // mesh shape the split engine does not handle: fused engine
         pl.sp = SplitState();
     }
@@ -568,8 +575,10 @@ static int split_build(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *
         TRY(pl.d_gauge_flwacc.upload(pl.gauge_flwacc, s));
     }
     TRY(pl.d_planes.ensure((size_t)NFIELD * ncell));
-    TRY(window_build(pl, mesh));
-    TRY(sub_build(pl, mesh));
+    if (pl.structure == SMASH_STRUCTURE_GR_A) {
+        TRY(window_build(pl, mesh));
+        TRY(sub_build(pl, mesh));
+    }
     CU(cudaStreamSynchronize(s));
     pl.col_cell = cell;
     pl.ncols = npad;
@@ -583,6 +592,11 @@ static int split_members(SmashPlan &pl, int nmember, bool save_q, bool save_netp
     const size_t nm = (size_t)nmember, npad = (size_t)sp.rg.npad;
     TRY(pl.d_fields.ensure(nm * NFIELD * npad));
     TRY(pl.d_fstates.ensure(nm * 3 * npad));
+    if (pl.structure != SMASH_STRUCTURE_GR_A) {
+        if (gradient) return fail(SMASH_B200_EUNSUPPORTED, "structure %d: the adjoint is implemented for gr-a only", pl.structure);
+        TRY(pl.d_sfields.ensure(nm * (SMASH_B200_GNP + SMASH_B200_GNS) * npad));
+        TRY(pl.d_sfstates.ensure(nm * SMASH_B200_GNS * npad));
+    }
     TRY(pl.d_qsim.ensure(std::max<size_t>(1, nm * tp.T * tp.ng)));
     TRY(pl.d_cost_jobs.ensure(nm));
     const size_t nrows = nm * npad * sp.Tp;
@@ -657,6 +671,7 @@ static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp, SplitSta
     a.dyn = (option("route_dynamic", 1) != 0 && pl.nmember == 1 && gr.rg.nchain > gr.rg.nded) ? 1 : 0;
     a.dyn_nq = gr.dyn_nq; a.qctl = gr.d_qctl.p; a.queue = gr.d_queue.p; a.ndep = gr.d_ndep.p; a.cons = gr.d_cons.p; a.qid = gr.d_qid.p;
     a.qoff = gr.d_qoff.p; a.qctl0 = gr.d_qctl0.p; a.queue0 = gr.d_queue0.p; a.ndep0 = gr.d_ndep0.p;
+    a.sfields = pl.d_sfields.p; a.sfstates = pl.d_sfstates.p;
     a.fields = pl.d_fields.p; a.fstates = pl.d_fstates.p; a.rows = sp.d_rows.p; a.qdom = pl.d_qdom.p; a.netp = pl.d_netp.p;
     a.qpitch = sp.qpitch; a.qsim = pl.d_qsim.p; a.tape_hp = sp.d_tape_hp.p; a.tape_hft = sp.d_tape_hft.p; a.rows_hr = sp.d_rows_hr.p;
     a.hcar = sp.d_hcar.p; a.done = graph ? gr.d_done.p : sp.d_done.p; a.ticket = pl.d_ticket.p; a.qsim_b = pl.d_qsim_b.p; a.rows_w = sp.d_rows_w.p;
@@ -777,7 +792,12 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
         pl.tick_ran = true;
         return 0;
     }
-    CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), tape, pl.stream));
+    if (pl.structure != SMASH_STRUCTURE_GR_A) {
+        if (tape) return fail(SMASH_B200_EUNSUPPORTED, "structure %d: the adjoint is implemented for gr-a only", pl.structure);
+        CU(launch_vertical_struct(a, sp.tm_prcp, sp.tm_pet, pl.structure, math_mode(), pl.stream));
+    } else {
+        CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), tape, pl.stream));
+    }
     mark(1);
     // ensembles on a small mesh: lane = member, exact sequential routing; otherwise the per-chain scan
     const bool by_member = pl.ensemble && sp.rg.npair == 0 && a.tp.nrouted <= 12000;   // whatever the size of this launch
@@ -945,14 +965,54 @@ static int stacked_to_field(int ind1) {
     return -1;
 }
 
+// planes a structure reads and updates (the reference's STRUCTURE_PARAMETERS / STRUCTURE_STATES, smash/core/_constant.py:20-33)
+struct StructurePlanes { bool par[SMASH_B200_GNP]; bool st[SMASH_B200_GNS]; };
+static const StructurePlanes &structure_planes(int structure) {
+    static StructurePlanes tab[6];
+    static bool init = false;
+    if (!init) {
+        auto set = [&](int s, std::initializer_list<int> p, std::initializer_list<int> h) {
+            for (int k : p) tab[s].par[k] = true;
+            for (int k : h) tab[s].st[k] = true;
+        };
+        set(SMASH_STRUCTURE_GR_A, {SMASH_P_CP, SMASH_P_CFT, SMASH_P_EXC, SMASH_P_LR}, {SMASH_S_HP, SMASH_S_HFT, SMASH_S_HLR});
+        set(SMASH_STRUCTURE_GR_B, {SMASH_P_CI, SMASH_P_CP, SMASH_P_CFT, SMASH_P_EXC, SMASH_P_LR}, {SMASH_S_HI, SMASH_S_HP, SMASH_S_HFT, SMASH_S_HLR});
+        set(SMASH_STRUCTURE_GR_C, {SMASH_P_CI, SMASH_P_CP, SMASH_P_CFT, SMASH_P_CST, SMASH_P_EXC, SMASH_P_LR},
+            {SMASH_S_HI, SMASH_S_HP, SMASH_S_HFT, SMASH_S_HST, SMASH_S_HLR});
+        set(SMASH_STRUCTURE_GR_D, {SMASH_P_CP, SMASH_P_CFT, SMASH_P_LR}, {SMASH_S_HP, SMASH_S_HFT, SMASH_S_HLR});
+        set(SMASH_STRUCTURE_VIC_A, {SMASH_P_B, SMASH_P_CUSL1, SMASH_P_CUSL2, SMASH_P_CLSL, SMASH_P_KS, SMASH_P_DS, SMASH_P_DSM, SMASH_P_WS, SMASH_P_LR},
+            {SMASH_S_HUSL1, SMASH_S_HUSL2, SMASH_S_HLSL, SMASH_S_HLR});
+        init = true;
+    }
+    return tab[structure];
+}
+
 static int plan_set_fields(SmashPlan &pl, const SmashParameters *par, const SmashStates *st, const float *sample,
                            const int32_t *ind, int nvar, int nmember) {
     const size_t nc = (size_t)pl.ncell;
+    const bool other = pl.structure != SMASH_STRUCTURE_GR_A;
+    if (other) {
+        // every plane the structure reads (STRUCTURE_PARAMETERS / STRUCTURE_STATES of the reference's _constant.py:20-33)
+        TRY(pl.d_splanes.ensure((size_t)(SMASH_B200_GNP + SMASH_B200_GNS) * nc));
+        const StructurePlanes &need = structure_planes(pl.structure);
+        for (int k = 0; k < SMASH_B200_GNP + SMASH_B200_GNS; k++) {
+            const float *src = k < SMASH_B200_GNP ? par->v[k] : st->v[k - SMASH_B200_GNP];
+            float *dst = pl.d_splanes.p + (size_t)k * nc;
+            const bool used = k < SMASH_B200_GNP ? need.par[k] : need.st[k - SMASH_B200_GNP];
+            if (src) CU(cudaMemcpyAsync(dst, src, nc * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
+            else if (used) return fail(SMASH_B200_EINVAL, "%s plane %d is NULL", k < SMASH_B200_GNP ? "parameters" : "states",
+                                       k < SMASH_B200_GNP ? k : k - SMASH_B200_GNP);
+            else CU(cudaMemsetAsync(dst, 0, nc * sizeof(float), pl.stream));
+        }
+    }
     for (int f = 0; f < 4; f++) {
+        // the routing passes read lr / hlr from here; the gr-a reservoir planes are placeholders for the other structures
+        if (other) { CU(cudaMemcpyAsync(pl.d_planes.p + f * nc, pl.d_splanes.p + (size_t)FIELD_PARAM[f] * nc, nc * sizeof(float), cudaMemcpyDeviceToDevice, pl.stream)); continue; }
         if (!par->v[FIELD_PARAM[f]]) return fail(SMASH_B200_EINVAL, "parameters plane %d is NULL", FIELD_PARAM[f]);
         CU(cudaMemcpyAsync(pl.d_planes.p + f * nc, par->v[FIELD_PARAM[f]], nc * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
     }
     for (int f = 0; f < 3; f++) {
+        if (other) { CU(cudaMemcpyAsync(pl.d_planes.p + (4 + f) * nc, pl.d_splanes.p + (size_t)(SMASH_B200_GNP + FIELD_STATE[f]) * nc, nc * sizeof(float), cudaMemcpyDeviceToDevice, pl.stream)); continue; }
         if (!st->v[FIELD_STATE[f]]) return fail(SMASH_B200_EINVAL, "states plane %d is NULL", FIELD_STATE[f]);
         CU(cudaMemcpyAsync(pl.d_planes.p + (4 + f) * nc, st->v[FIELD_STATE[f]], nc * sizeof(float), cudaMemcpyHostToDevice, pl.stream));
     }
@@ -968,6 +1028,16 @@ static int plan_set_fields(SmashPlan &pl, const SmashParameters *par, const Smas
     CU(launch_gather_fields(pl.dtp, nmember, pl.d_planes.p, (int64_t)nc, nv ? pl.d_sample.p : nullptr, pl.d_sample_field.p, nv,
                             pl.d_fields.p, pl.stream));
     pl.launches++;
+    if (other) {
+        if (nv) {
+            std::vector<int32_t> spl(nvar);
+            for (int j = 0; j < nvar; j++) spl[j] = ind[j] - 1;             // stacked index: 16 parameters then 8 states
+            TRY(pl.d_sample_plane.upload(spl, pl.stream));
+        }
+        CU(launch_gather_struct_fields(pl.d_cell.p, pl.ncols, nmember, pl.d_splanes.p, (int64_t)nc, nv ? pl.d_sample.p : nullptr,
+                                       pl.d_sample_plane.p, nv, pl.d_sfields.p, pl.stream));
+        pl.launches++;
+    }
     return 0;
 }
 
@@ -1152,8 +1222,8 @@ static int get_plan(const SmashSetup *setup, const SmashMesh *mesh, SmashPlan **
     const bool small = option("stream", 1) != 0 && setup->sparse_storage &&
                        (size_t)mesh->nac * setup->ntime_step * 8 >= ((size_t)option("stream_min_mb", 256) << 20);
     char key[192];
-    snprintf(key, sizeof key, "%016llx:%d:%d:%g:%g:%lld:%d:%d:%d:%lld", (unsigned long long)h, dev, setup->ntime_step, (double)setup->dt,
-             (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0, small ? 1 : 0,
+    snprintf(key, sizeof key, "%016llx:%d:%d:%d:%g:%g:%lld:%d:%d:%d:%lld", (unsigned long long)h, dev, setup->structure, setup->ntime_step,
+             (double)setup->dt, (double)mesh->dx, option("block", 0), pick_engine(engine), setup->sparse_storage ? 1 : 0, small ? 1 : 0,
              option("route_ded_min", 96) + 1024 * option("route_ded_max", 64) + (option("route_queues", 12) << 20) +
                  ((option("adjoint_checkpoint", -1) + 1) << 26) + (option("tape_budget_mb", 16384) << 28) +
                  (option("tick_pass", 0) << 48) + (option("tick_slack", 1) << 49) + (option("shallow_acc", 32) << 50) + ((option("sub_engine", -1) + 1) << 58));
@@ -1229,7 +1299,7 @@ static void scatter_sorted(const SmashPlan &pl, const float *sorted, float *plan
 // is uploaded on s_in while window w - 1 is computed on the plan's stream and window w - 2 travels back on s_out: both PCIe
 // directions and the kernels overlap, and the run costs about as long as the larger of the two transfers.
 static bool can_stream(const SmashPlan &pl, const SmashSetup *setup) {
-    return pl.engine == 1 && pl.small_windows && pl.sp.nwin > 1 && setup->sparse_storage && pl.sp.rg.direct && pl.tp.nactive % 4 == 0 &&
+    return pl.engine == 1 && pl.structure == SMASH_STRUCTURE_GR_A && pl.small_windows && pl.sp.nwin > 1 && setup->sparse_storage && pl.sp.rg.direct && pl.tp.nactive % 4 == 0 &&
            option("stream", 1) != 0;
 }
 static int forward_streamed(SmashPlan &pl, const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, SmashOutput *out,
@@ -1338,9 +1408,14 @@ static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const 
         TRY(run_forward_engine(*pl, save_q, save_n, false));
     }
     TRY(run_cost(*pl, setup, mesh, 0.0f, false, in));
-    std::vector<float> fs((size_t)3 * pl->ncols);
+    std::vector<float> fs((size_t)3 * pl->ncols), sfs;
     float jobs = 0.0f;
     TRY(download(*pl, fs.data(), pl->d_fstates.p, fs.size() * sizeof(float)));
+    const bool other = pl->structure != SMASH_STRUCTURE_GR_A;
+    if (other) {
+        sfs.resize((size_t)SMASH_B200_GNS * pl->ncols);
+        TRY(download(*pl, sfs.data(), pl->d_sfstates.p, sfs.size() * sizeof(float)));
+    }
     TRY(download(*pl, &jobs, pl->d_cost_jobs.p, sizeof(float)));
     if (out && out->qsim && mesh->ng > 0) TRY(download(*pl, out->qsim, pl->d_qsim.p, (size_t)mesh->ng * tp.T * sizeof(float)));
     if (save_q && !streamed) TRY(export_domain(*pl, setup, mesh, pl->d_qdom.p, out->qsim_domain, out->sparse_qsim_domain));
@@ -1354,10 +1429,16 @@ static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const 
     CU(cudaStreamSynchronize(pl->stream));
     if (streamed) CU(cudaStreamSynchronize(pl->s_out));
     TRY(tick_check(*pl));
-    for (int f = 0; f < 3; f++) {
-        float *dst = restore_states ? (out ? out->fstates.v[FIELD_STATE[f]] : nullptr) : st->v[FIELD_STATE[f]];
-        if (dst) scatter_sorted(*pl, fs.data() + (size_t)f * pl->ncols, dst);
-        if (!restore_states && out && out->fstates.v[FIELD_STATE[f]]) memcpy(out->fstates.v[FIELD_STATE[f]], st->v[FIELD_STATE[f]], nc * sizeof(float));
+    const StructurePlanes &used = structure_planes(pl->structure);
+    for (int k = 0; k < SMASH_B200_GNS; k++) {
+        if (!used.st[k]) continue;
+        // gr-a: hp, hft, hlr from the engine's three planes; the other structures: hlr from there, the rest from their own block
+        const float *src = nullptr;
+        if (other && k != SMASH_S_HLR) src = sfs.data() + (size_t)k * pl->ncols;
+        else for (int f = 0; f < 3; f++) if (FIELD_STATE[f] == k) src = fs.data() + (size_t)f * pl->ncols;
+        float *dst = restore_states ? (out ? out->fstates.v[k] : nullptr) : st->v[k];
+        if (dst) scatter_sorted(*pl, src, dst);
+        if (!restore_states && out && out->fstates.v[k]) memcpy(out->fstates.v[k], st->v[k], nc * sizeof(float));
     }
     *jobs_out = jobs;
     return 0;
@@ -1492,6 +1573,8 @@ extern "C" int smash_b200_forward_b(const SmashSetup *setup, const SmashMesh *me
 // hyper_forward / hyper_forward_b
 // ------------------------------------------------------------------------------------------------
 static int hyper_check(const SmashSetup *setup, const SmashInputData *in) {
+    if (setup->structure != SMASH_STRUCTURE_GR_A)
+        return fail(SMASH_B200_EUNSUPPORTED, "structure %d: the descriptor mappings are implemented for gr-a only", setup->structure);
     if (setup->mapping != SMASH_MAPPING_HYPER_LINEAR && setup->mapping != SMASH_MAPPING_HYPER_POLYNOMIAL)
         return fail(SMASH_B200_EINVAL, "hyper_forward needs mapping hyper-linear or hyper-polynomial");
     const int want = setup->mapping == SMASH_MAPPING_HYPER_LINEAR ? 1 + setup->nd : 1 + 2 * setup->nd;

@@ -61,6 +61,8 @@ struct SplitArgs {
     unsigned long long *dbg_prof;  // diagnostics: per dedicated chain [cells, cycles, cycles waiting for tributaries, end time ns], or nullptr
     const float *fields;         // [m][NFIELD][npad]
     float *fstates;              // [m][3][npad]
+    const float *sfields;        // [m][16 + 8][npad] every parameter and state plane (structures other than gr-a), or nullptr
+    float *sfstates;             // [m][8][npad]      final stores of those structures (hlr: fstates)
     float *rows;                 // [m][npad][Tp]   qt of every cell after vertical_forward, q after route_forward
     float *qdom;                 // [m][T][qpitch]  domain discharge, cell order j
     float *netp;                 // [m][T][qpitch]  qt (save_net_prcp_domain)
@@ -173,6 +175,11 @@ cudaError_t launch_sub_forward(const SbArgs &a, const CUtensorMap &prcp, const C
 // 2-D tensor map over a [rows][pitch] float array, box = 8 rows x 32 columns.  cols = valid columns (the rest reads 0).
 int make_tensor_map_2d(CUtensorMap *tm, const float *base, uint64_t cols, uint64_t rows, uint64_t pitch_elems, const char **err);
 
+// structures other than gr-a (struct_kernels.cu): the reservoir pass of gr-b / gr-c / gr-d / vic-a, whole run, forward only
+cudaError_t launch_vertical_struct(const SplitArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, int structure, int math_mode,
+                                   cudaStream_t s);
+cudaError_t launch_gather_struct_fields(const int32_t *cell, int npad, int nmember, const float *planes, int64_t ncell, const float *sample,
+                                        const int32_t *sample_plane, int nvar, float *sfields, cudaStream_t s);
 cudaError_t launch_vertical_forward(const SplitArgs &a, const CUtensorMap &prcp, const CUtensorMap &pet, int math_mode, bool tape,
                                     cudaStream_t s);
 cudaError_t launch_route_forward(const SplitArgs &a, bool tape, cudaStream_t s);      // all windows

@@ -15,8 +15,20 @@ from .solver import _mw_forward, _mw_multiple_run, _mw_optimize
 from .solver._derived_types import GPARAMETERS_NAME, GSTATES_NAME, Optimize_SetupDT
 
 # smash/core/_constant.py:15-45
-STRUCTURE_PARAMETERS = {"gr-a": ["cp", "cft", "exc", "lr"]}
-STRUCTURE_STATES = {"gr-a": ["hp", "hft", "hlr"]}
+STRUCTURE_PARAMETERS = {
+    "gr-a": ["cp", "cft", "exc", "lr"],
+    "gr-b": ["cp", "cft", "exc", "lr"],
+    "gr-c": ["cp", "cft", "cst", "exc", "lr"],
+    "gr-d": ["cp", "cft", "lr"],
+    "vic-a": ["b", "cusl1", "cusl2", "clsl", "ks", "ds", "dsm", "ws", "lr"],
+}
+STRUCTURE_STATES = {
+    "gr-a": ["hp", "hft", "hlr"],
+    "gr-b": ["hi", "hp", "hft", "hlr"],
+    "gr-c": ["hi", "hp", "hft", "hst", "hlr"],
+    "gr-d": ["hp", "hft", "hlr"],
+    "vic-a": ["husl1", "husl2", "hlsl"],
+}
 MAPPING = ("uniform", "distributed", "hyper-linear", "hyper-polynomial")
 JOBS_FUN = ("nse", "kge", "kge2", "se", "rmse", "logarithmic")
 
