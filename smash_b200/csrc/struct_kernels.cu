@@ -38,17 +38,33 @@ __device__ __forceinline__ void st_st8(float *p, const float *v) {
 // parameters and stores of one cell; which members are live depends on the structure
 struct SPar {
     float ci, cp, inv_cp, cft, cst, exc, b, cusl1, cusl2, clsl, ks, ds, dsm, ws;
+    // reciprocals of the capacities (fast math mode: a division by a per-cell constant becomes a product)
+    float inv_ci, inv_cft, inv_cst, inv_cusl1, inv_cusl2, inv_clsl;
 };
+// a / b with b a per-cell constant whose reciprocal is at hand
+template <int FAST> __device__ __forceinline__ float cdiv(float a, float b, float inv_b) { return FAST ? a * inv_b : a / b; }
+// the two powers of vic_infiltration are subtracted from 1 (from cusl - wusl) right away: the result keeps two to three digits fewer
+// than the power, so libm's powf stays in the fast math mode too (__powf moved the France checksum by 7e-4)
 struct SSto {
     float hi, hp, hft, hst, husl1, husl2, hlsl;
 };
 
 // gr_production md_gr_operator.f90:36-67 (beta = 1000)
 template <int FAST> __device__ __forceinline__ void d_production(float pn, float en, float cp, float inv_cp, float &hp, float &pr, float &perc) {
-    const float tp = ftanh<FAST>(pn * inv_cp), te = ftanh<FAST>(en * inv_cp);
-    const float ps = fdiv<FAST>((cp * (1.0f - hp * hp)) * tp, 1.0f + hp * tp);               // :52
-    const float es = fdiv<FAST>(((hp * cp) * (2.0f - hp)) * te, 1.0f + (1.0f - hp) * te);    // :55
-    const float hp_imd = hp + (ps - es) * inv_cp;                                            // :58
+    float hp_imd;
+    if (FAST && !(pn > 0.0f && en > 0.0f)) {
+        // one of pn, en is zero (always so behind gr_interception and the gr-d statements): tanh(0) = 0 leaves one of ps, es
+        const bool wet = pn > 0.0f;
+        const float th = ftanh<FAST>((wet ? pn : en) * inv_cp);
+        const float num = (wet ? cp * (1.0f - hp * hp) : (hp * cp) * (2.0f - hp)) * th;     // :52, :55
+        const float r = __fdividef(num, fmaf(wet ? hp : 1.0f - hp, th, 1.0f));
+        hp_imd = fmaf(wet ? r : -r, inv_cp, hp);                                             // :58
+    } else {
+        const float tp = ftanh<FAST>(pn * inv_cp), te = ftanh<FAST>(en * inv_cp);
+        const float ps = fdiv<FAST>((cp * (1.0f - hp * hp)) * tp, 1.0f + hp * tp);           // :52
+        const float es = fdiv<FAST>(((hp * cp) * (2.0f - hp)) * te, 1.0f + (1.0f - hp) * te);    // :55
+        hp_imd = hp + (ps - es) * inv_cp;                                                    // :58
+    }
     pr = (pn > 0.0f) ? pn - (hp_imd - hp) * cp : 0.0f;                                       // :60-62
     const float w = 1.0f + pow4(hp_imd * 0.001f);                                            // :64
     const float pw = (w == 1.0f) ? 1.0f : pow_m025<FAST>(w);
@@ -61,7 +77,7 @@ template <int FAST> __device__ __forceinline__ void d_production(float pn, float
 template <int FAST> __device__ __forceinline__ float d_power_store(float h_imd, float c, float &h_new) {
     if (FAST) {
         const float z = pow4(h_imd);
-        const float s2 = sqrtf(1.0f + z), s1 = sqrtf(s2);
+        const float s2 = fsqrt_fast(1.0f + z), s1 = fsqrt_fast(s2);
         const float rel = h_imd * __fdividef(z, s1 * (s1 + 1.0f) * (s2 + 1.0f));
         h_new = h_imd - rel;
         return rel * c;
@@ -72,13 +88,13 @@ template <int FAST> __device__ __forceinline__ float d_power_store(float h_imd, 
 }
 
 // gr_transfer(n = 5) md_gr_operator.f90:81-110
-template <int FAST> __device__ __forceinline__ float d_transfer(float prcp, float pr, float ct, float &ht) {
+template <int FAST> __device__ __forceinline__ float d_transfer(float prcp, float pr, float ct, float inv_ct, float &ht) {
     float pr_imd = pr;
     if (prcp < 0.0f) {                                                                       // :95-96 forcing gap: emptying
         const float x = ht * ct;
         pr_imd = 1.0f / sqrtf(sqrtf(1.0f / pow4(x) - 1.0f / pow4(ct))) - x;
     }
-    const float ht_imd = fmaxf(1.e-6f, FAST ? fmaf(pr_imd, __frcp_rn(ct), ht) : ht + pr_imd / ct);   // :102
+    const float ht_imd = fmaxf(1.e-6f, FAST ? fmaf(pr_imd, inv_ct, ht) : ht + pr_imd / ct);   // :102
     float ht_new;
     const float q = d_power_store<FAST>(ht_imd, ct, ht_new);
     ht = ht_new;
@@ -86,8 +102,9 @@ template <int FAST> __device__ __forceinline__ float d_transfer(float prcp, floa
 }
 
 // vic_infiltration md_vic_operator.f90:21-77
-__device__ __forceinline__ float d_vic_infiltration(float prcp, float cusl1, float cusl2, float b, float &husl1, float &husl2) {
-    const float bp1 = b + 1.0f;
+template <int FAST> __device__ __forceinline__ float d_vic_infiltration(float prcp, const SPar &p, float &husl1, float &husl2) {
+    const float cusl1 = p.cusl1, cusl2 = p.cusl2;
+    const float bp1 = p.b + 1.0f;
     float ifl;
     if (prcp <= 0.0f) {
         ifl = 0.0f;
@@ -97,16 +114,16 @@ __device__ __forceinline__ float d_vic_infiltration(float prcp, float cusl1, flo
         wusl = fmaxf(1.e-6f, wusl);
         wusl = fminf(cusl - 1e-6f, wusl);
         const float iflm = cusl * bp1;
-        const float iflc = iflm * (1.0f - powf(1.0f - (wusl / cusl), 1.0f / bp1));
+        const float iflc = iflm * (1.0f - powf(1.0f - fdiv<FAST>(wusl, cusl), fdiv<FAST>(1.0f, bp1)));
         if (iflc + prcp >= iflm) ifl = cusl - wusl;
-        else ifl = (cusl - wusl) - cusl * powf(1.0f - ((iflc + prcp) / iflm), bp1);
+        else ifl = (cusl - wusl) - cusl * powf(1.0f - fdiv<FAST>(iflc + prcp, iflm), bp1);
         ifl = fminf(prcp, ifl);
     }
     const float ifl_usl1 = fminf((1.0f - husl1) * cusl1, ifl);
     ifl = ifl - ifl_usl1;
     const float ifl_usl2 = fminf((1.0f - husl2) * cusl2, ifl);
-    husl1 = husl1 + ifl_usl1 / cusl1;
-    husl2 = husl2 + ifl_usl2 / cusl2;
+    husl1 = husl1 + cdiv<FAST>(ifl_usl1, cusl1, p.inv_cusl1);
+    husl2 = husl2 + cdiv<FAST>(ifl_usl2, cusl2, p.inv_cusl2);
     return prcp - (ifl_usl1 + ifl_usl2);
 }
 
@@ -118,30 +135,30 @@ __device__ __forceinline__ float d_brooks_corey(float ks, float c_upper, float c
 }
 
 // vic_vertical_transfer md_vic_operator.f90:79-114 (linear_evapotranspiration :185-200 inlined: min(c h, e h))
-__device__ __forceinline__ void d_vic_vertical_transfer(float pet, const SPar &p, float &husl1, float &husl2, float &hlsl) {
+template <int FAST> __device__ __forceinline__ void d_vic_vertical_transfer(float pet, const SPar &p, float &husl1, float &husl2, float &hlsl) {
     float fbc = d_brooks_corey(p.ks, p.cusl1, p.cusl2, husl1, husl2);
-    husl1 = husl1 - fbc / p.cusl1;
-    husl2 = husl2 + fbc / p.cusl2;
+    husl1 = husl1 - cdiv<FAST>(fbc, p.cusl1, p.inv_cusl1);
+    husl2 = husl2 + cdiv<FAST>(fbc, p.cusl2, p.inv_cusl2);
     fbc = d_brooks_corey(p.ks, p.cusl2, p.clsl, husl2, hlsl);
-    husl2 = husl2 - fbc / p.cusl2;
-    hlsl = hlsl + fbc / p.clsl;
+    husl2 = husl2 - cdiv<FAST>(fbc, p.cusl2, p.inv_cusl2);
+    hlsl = hlsl + cdiv<FAST>(fbc, p.clsl, p.inv_clsl);
     float fe = fminf(p.cusl1 * husl1, pet * husl1);
-    husl1 = husl1 - fe / p.cusl1;
+    husl1 = husl1 - cdiv<FAST>(fe, p.cusl1, p.inv_cusl1);
     float pet_remain = fmaxf(0.0f, pet - fe);
     fe = fminf(p.cusl2 * husl2, pet_remain * husl2);
-    husl2 = husl2 - fe / p.cusl2;
+    husl2 = husl2 - cdiv<FAST>(fe, p.cusl2, p.inv_cusl2);
     pet_remain = fmaxf(0.0f, pet_remain - fe);
     fe = fminf(p.clsl * hlsl, pet_remain * hlsl);
-    hlsl = hlsl - fe / p.clsl;
+    hlsl = hlsl - cdiv<FAST>(fe, p.clsl, p.inv_clsl);
 }
 
 // vic_baseflow md_vic_operator.f90:137-163
-__device__ __forceinline__ float d_vic_baseflow(const SPar &p, float &hlsl) {
+template <int FAST> __device__ __forceinline__ float d_vic_baseflow(const SPar &p, float &hlsl) {
     float qb;
-    if (hlsl <= p.ws) qb = (p.ds * p.dsm) / p.ws * hlsl;
-    else qb = p.dsm * (1.0f - p.ds / p.ws) * (hlsl - p.ws) / (1.0f - p.ws);
+    if (hlsl <= p.ws) qb = fdiv<FAST>(p.ds * p.dsm, p.ws) * hlsl;
+    else qb = fdiv<FAST>(p.dsm * (1.0f - fdiv<FAST>(p.ds, p.ws)) * (hlsl - p.ws), 1.0f - p.ws);
     qb = fminf(p.clsl * hlsl, qb);
-    hlsl = hlsl - qb / p.clsl;
+    hlsl = hlsl - cdiv<FAST>(qb, p.clsl, p.inv_clsl);
     return qb;
 }
 
@@ -151,13 +168,13 @@ template <int ST, int FAST> __device__ __forceinline__ float struct_step(const S
     if (ST == SMASH_STRUCTURE_VIC_A) {
         float runoff = 0.0f;
         if (nogap) {
-            runoff = d_vic_infiltration(prcp, p.cusl1, p.cusl2, p.b, s.husl1, s.husl2);      // md_forward_structure.f90:843
-            d_vic_vertical_transfer(pet, p, s.husl1, s.husl2, s.hlsl);                       // :851
+            runoff = d_vic_infiltration<FAST>(prcp, p, s.husl1, s.husl2);            // md_forward_structure.f90:843
+            d_vic_vertical_transfer<FAST>(pet, p, s.husl1, s.husl2, s.hlsl);                       // :851
         }
         float h2;
         const float qi = d_power_store<FAST>(s.husl2, p.cusl2, h2);                          // :861
         s.husl2 = h2;
-        const float qb = d_vic_baseflow(p, s.hlsl);                                          // :863
+        const float qb = d_vic_baseflow<FAST>(p, s.hlsl);                                          // :863
         return runoff + qi + qb;                                                             // :866
     }
     float pr = 0.0f, perc = 0.0f, l = 0.0f;
@@ -169,7 +186,7 @@ template <int ST, int FAST> __device__ __forceinline__ float struct_step(const S
         } else {                                                                             // gr_interception md_gr_operator.f90:20-34
             ei = fminf(pet, prcp + s.hi * p.ci);
             pn = fmaxf(0.0f, prcp - p.ci * (1.0f - s.hi) - ei);
-            s.hi = s.hi + (prcp - ei - pn) / p.ci;
+            s.hi = s.hi + cdiv<FAST>(prcp - ei - pn, p.ci, p.inv_ci);
         }
         const float en = pet - ei;
         d_production<FAST>(pn, en, p.cp, p.inv_cp, s.hp, pr, perc);                          // :306, :490, :676
@@ -178,18 +195,18 @@ template <int ST, int FAST> __device__ __forceinline__ float struct_step(const S
     if (ST == SMASH_STRUCTURE_GR_B) {
         const float prr = 0.9f * (pr + perc) + l;                                            // :321
         const float prd = 0.1f * (pr + perc);                                                // :322
-        const float qr = d_transfer<FAST>(prcp, prr, p.cft, s.hft);                          // :324
+        const float qr = d_transfer<FAST>(prcp, prr, p.cft, p.inv_cft, s.hft);                          // :324
         return qr + fmaxf(0.0f, prd + l);                                                    // :326-328
     }
     if (ST == SMASH_STRUCTURE_GR_C) {
         const float prr = 0.9f * 0.6f * (pr + perc) + l;                                     // :505
         const float prl = 0.9f * 0.4f * (pr + perc);                                         // :506
         const float prd = 0.1f * (pr + perc);                                                // :507
-        const float qr = d_transfer<FAST>(prcp, prr, p.cft, s.hft);                          // :509
-        const float ql = d_transfer<FAST>(prcp, prl, p.cst, s.hst);                          // :511
+        const float qr = d_transfer<FAST>(prcp, prr, p.cft, p.inv_cft, s.hft);                          // :509
+        const float ql = d_transfer<FAST>(prcp, prl, p.cst, p.inv_cst, s.hst);                          // :511
         return (qr + ql) + fmaxf(0.0f, prd + l);                                             // :513-515
     }
-    return d_transfer<FAST>(prcp, pr + perc, p.cft, s.hft);                                  // gr-d :685-689
+    return d_transfer<FAST>(prcp, pr + perc, p.cft, p.inv_cft, s.hft);                                  // gr-d :685-689
 }
 
 template <int ST, int FAST>
@@ -220,7 +237,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32) vertical_struct_kernel(const __
     __syncwarp();
 
     // padding lanes run on the reference's default values (mwd_parameters.f90:150-167, mwd_states.f90:117-126)
-    SPar p{1e-6f, 200.0f, 0.005f, 500.0f, 500.0f, 0.0f, 0.3f, 100.0f, 500.0f, 2000.0f, 20.0f, 0.02f, 0.33f, 0.8f};
+    SPar p{1e-6f, 200.0f, 0.005f, 500.0f, 500.0f, 0.0f, 0.3f, 100.0f, 500.0f, 2000.0f, 20.0f, 0.02f, 0.33f, 0.8f, 1e6f, 0.002f, 0.002f, 0.01f,
+           0.002f, 0.0005f};
     SSto s{0.01f, 0.01f, 0.01f, 0.01f, 0.01f, 0.01f, 0.01f};
     float hlr = 0.0f, E = 0.0f;
     int fa = 1;
@@ -232,6 +250,8 @@ __global__ void __launch_bounds__(ST_WARPS * 32) vertical_struct_kernel(const __
         p.ci = P(SMASH_P_CI); p.cp = P(SMASH_P_CP); p.inv_cp = 1.0f / p.cp; p.cft = P(SMASH_P_CFT); p.cst = P(SMASH_P_CST);
         p.exc = P(SMASH_P_EXC); p.b = P(SMASH_P_B); p.cusl1 = P(SMASH_P_CUSL1); p.cusl2 = P(SMASH_P_CUSL2); p.clsl = P(SMASH_P_CLSL);
         p.ks = P(SMASH_P_KS); p.ds = P(SMASH_P_DS); p.dsm = P(SMASH_P_DSM); p.ws = P(SMASH_P_WS);
+        p.inv_ci = 1.0f / p.ci; p.inv_cft = 1.0f / p.cft; p.inv_cst = 1.0f / p.cst;
+        p.inv_cusl1 = 1.0f / p.cusl1; p.inv_cusl2 = 1.0f / p.cusl2; p.inv_clsl = 1.0f / p.clsl;
         s.hi = S(SMASH_S_HI); s.hp = S(SMASH_S_HP); s.hft = S(SMASH_S_HFT); s.hst = S(SMASH_S_HST);
         s.husl1 = S(SMASH_S_HUSL1); s.husl2 = S(SMASH_S_HUSL2); s.hlsl = S(SMASH_S_HLSL);
         hlr = S(SMASH_S_HLR);

@@ -9,10 +9,14 @@ from smash_b200 import _lib as L
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--T", type=int, default=720); ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--structure", default="gr-a")
 ap.add_argument("sets", nargs="*", default=["base"])
 a = ap.parse_args()
 lib = L.lib()
 m = cases.france(T=a.T)
+m.setup.structure = a.structure
+if a.structure in ("gr-b", "gr-c"):
+    m.parameters.ci[...] = 2.0
 DEFAULTS = {"tick_pass": 0, "sub_engine": -1, "sub_scatter": 0, "tick_nb": 2, "tick_slack": 1, "tick_dbg": 0, "shallow_acc": 32, "tick_variant": 8, "tick_ctas_per_sm": 0, "fuse_export": 4}
 for st in a.sets:
     opts = dict(DEFAULTS)
