@@ -493,6 +493,41 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
                 lib.smash_b200_set_option(b"sub_engine", -1)
                 lib.smash_b200_set_option(b"tick_pass", 0)
 
+    # ---- the other structures on the same mesh and forcing (forward only; reservoir pass of struct_kernels.cu + the routing passes)
+    structures = None
+    if not args.no_extra:
+        structures = {}
+        for name in ("gr-b", "gr-c", "gr-d", "vic-a"):
+            model.setup.structure = name
+            model.parameters.ci[...] = 2.0 if name in ("gr-b", "gr-c") else 1e-6
+            try:
+                pk2 = L.Packed()
+                s2 = L.pack_setup(model.setup, model.mesh, pk2)
+                p2, st2 = L.pack_parameters(model.parameters, pk2), L.pack_states(model.states, pk2)
+                plan2 = C.c_void_p()
+                L.check(lib.smash_b200_plan_create(C.byref(s2), C.byref(m_), 1, C.byref(plan2)))
+                L.check(lib.smash_b200_plan_set_forcing(plan2, C.byref(s2), C.byref(i_)))
+                L.check(lib.smash_b200_plan_set_fields(plan2, C.byref(p2), C.byref(st2), None, None, 0))
+                tms = []
+                for k in range(args.warmup + 3):
+                    L.check(lib.smash_b200_plan_run_forward(plan2, C.byref(ms)))
+                    if k >= args.warmup:
+                        tms.append(ms.value)
+                kt = (C.c_float * 5)()
+                lib.smash_b200_plan_kernel_times(plan2, kt)
+                chk2 = C.c_double(0.0)
+                L.check(lib.smash_b200_plan_checksum(plan2, C.byref(chk2)))
+                lib.smash_b200_plan_destroy(plan2)
+                structures[name] = {"ms_per_step": float(np.mean(tms)), "cell_timesteps_per_s": units / (float(np.mean(tms)) * 1e-3),
+                                    "frac_of_12B_roofline": step_bytes / (float(np.mean(tms)) * 1e-3) / 1e9 / peak,
+                                    "kernels_ms": {"vertical_struct_kernel": float(kt[0]), "route_forward_kernel": float(kt[1])},
+                                    "checksum_q": chk2.value}
+            finally:
+                model.setup.structure = "gr-a"
+                model.parameters.ci[...] = 1e-6
+        structures["note"] = ("forward runs of md_forward_structure.f90:216-931 on the row passes; same 12 B per cell-step of algorithmic "
+                              "traffic as gr-a; the reservoir pass is instruction-bound (divisions, powf of vic_infiltration)")
+
     # ---- the ANN mapping's forward pass at France scale: the graph of _ann_optimize.py:143-168 for nd = 6 descriptors
     ann = None
     if not args.no_extra:
@@ -582,7 +617,7 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
                    "pit_pairs": int(info[6]), "l2": "inputs larger than L2 (5.2 GB forcing streamed once per step)",
                    "parallelism": "1 GPU", "checksum_q": chk.value, "model_build_s": t_build},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": args.steps * launches_per_step, "clocks": clocks,
-        "gradient": gradient, "ann_dense": ann,
+        "gradient": gradient, "ann_dense": ann, "structures": structures,
     }
     if not args.no_extra:
         ens = bench_ensemble(lib, L, smash_b200, cases, None, 0, 1, max(2, min(5, args.steps)), 1)

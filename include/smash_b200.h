@@ -16,7 +16,9 @@
  *
  * Return value: 0 on success, non-zero on error (message via smash_b200_last_error()).  There is
  * no CPU fallback: without a CUDA device every compute entry point fails with SMASH_B200_ENODEV.
- * Only the gr-a structure is implemented (the structure named by BASELINE.json's configs).
+ * Structures: gr-a (the structure named by BASELINE.json's configs) behind every entry point; gr-b, gr-c, gr-d and vic-a
+ * (forward/md_forward_structure.f90:216-931) behind smash_b200_forward, smash_b200_compute_multiple_run and the plan API's forward
+ * run -- their adjoint and descriptor mappings answer SMASH_B200_EUNSUPPORTED.
  */
 #ifndef SMASH_B200_H
 #define SMASH_B200_H

@@ -2,7 +2,8 @@
  * smash_oracle.c -- CPU ORACLE (test infrastructure, NOT the product; see smash_oracle.h).
  *
  * Restates, statement by statement and in the same floating-point evaluation order, the
- * reference's gr-a forward solver, its cost function and the Tapenade reverse sweep.
+ * reference's gr-a forward solver, its cost function and the Tapenade reverse sweep, and the
+ * forward solvers of gr-b, gr-c, gr-d and vic-a (parity of those four: UNPINNED, see smash_oracle.h).
  * Each function cites the reference file:line it follows (paths relative to
  * /root/reference/smash/solver/).  Compile with -ffp-contract=off so that no FMA is formed
  * that the scalar Fortran would not have formed.

@@ -14,6 +14,10 @@
  * SURVEY.md 8c); the float32 build is checked against the reference's own golden file
  * smash/tests/baseline.hdf5 (run.cost, multiple_run.{cost,qsim}, mutiple_run.slc_*,
  * optimize.* after one L-BFGS-B iteration) through tests/golden/cance_golden.npz.
+ * Exception -- parity UNPINNED: the forward restatement of the structures gr-b, gr-c, gr-d and
+ * vic-a (structure_forward in smash_oracle.c).  The reference's tests and golden file run gr-a
+ * only, so there is no vector to pin them to; what is checked instead (tests/test_oracle_structures.py):
+ * gr-b with ci -> 0 reproduces the pinned gr-a run, float32 against float64 builds, forward.f90's bookkeeping.
  *
  * All arrays use the reference's memory layout: Fortran order, 1-based index VALUES.
  *   (nrow,ncol)      -> a[row-1 + (col-1)*nrow]
