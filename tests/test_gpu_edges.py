@@ -129,9 +129,16 @@ def test_sparse_layout_needing_the_gather_pass():
 
 def test_errors_at_the_boundary():
     m = cases.cance(T=24)
-    m.setup.structure = "gr-b"
-    with pytest.raises(RuntimeError, match="gr-a"):
+    m.setup.structure = "gr-e"                                                # not one of the five structures
+    with pytest.raises((RuntimeError, ValueError), match="structure"):
         smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
+    m = cases.cance(T=24)
+    m.setup.structure = "gr-b"                                                # forward only: the mappings over descriptors are gr-a's
+    cases.normalize_descriptor(m)
+    cases.set_optimize(m.setup, m.mesh, jobs_fun=("nse",), mapping="hyper-linear")
+    hp, hs = cases.hyper_objects(m)
+    with pytest.raises(RuntimeError, match="gr-a only"):
+        smash_b200.hyper_forward(m.setup, m.mesh, m.input_data, m.parameters, hp, hp.copy(), m.states, hs, hs.copy(), m.output)
     m = cases.cance(T=24)
     cases.set_optimize(m.setup, m.mesh, jobs_fun=("no_such_objective",))
     with pytest.raises((RuntimeError, ValueError, KeyError)):
