@@ -259,6 +259,14 @@ int smash_b200_gauge_masks(const SmashMesh *mesh, uint8_t *mask);
 int smash_b200_compute_mean_forcing(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *input_data, float *mean_prcp,
                                     float *mean_pet);
 
+/* replaces mw_interception_store::adjust_interception_store (smash/solver/routine/mw_interception_store.f90:19-160), the
+ * calibration of the interception capacity of gr-b / gr-c on sub-daily runs: ci (nrow,ncol) of every computed cell := the value
+ * among 0.1, 0.2 .. 4.9 mm whose cumulated sub-daily interception evaporation is closest to the cumulated daily one.
+ * day_index (ntime_step): day number of every step; nday >= the number of days it holds.  Other cells of ci are left untouched.
+ * kernel_ms (may be NULL): device time of the search. */
+int smash_b200_adjust_interception_store(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *input_data, int32_t nday,
+                                         const int32_t *day_index, float *ci, float *kernel_ms);
+
 /* ---- the ANN mapping's Dense layers on the tensor cores --------------------- */
 
 /* replaces Net._forward_pass (smash/core/net.py:281-299) for a chain of Dense (+ Activation) layers (net.py:579-688, 458-498):

@@ -309,6 +309,17 @@ def compute_multiple_run(setup, mesh, input_data, parameters, states, output, sa
         res_qsim[...] = rq
 
 
+def adjust_interception_store(setup, mesh, input_data, parameters, nday, day_index, precision="f32"):
+    """adjust_interception_store (routine/mw_interception_store.f90:19-160): sets parameters.ci on the computed cells."""
+    ctx = _Ctx(precision)
+    P = _problem(ctx, setup, mesh, input_data)
+    ci = np.asfortranarray(parameters.ci, dtype=ctx.dtype).copy(order="F")
+    di = np.ascontiguousarray(day_index, dtype=np.int32)
+    rc = ctx.fn("oracle_adjust_interception_store")(C.byref(P), int(nday), di.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(ctx, ci))
+    assert rc == 0
+    parameters.ci[...] = ci
+
+
 def nse(x, y, precision="f32"):
     ctx = _Ctx(precision)
     f = ctx.fn("oracle_nse")

@@ -1093,6 +1093,55 @@ static oreal compute_cost(const Prob *P, oreal *par, const oreal *par_bgd, oreal
     return cost;
 }
 
+/* ============================================================================================
+ * adjust_interception_store -- routine/mw_interception_store.f90:19-160 (UNPINNED like the structures that use ci).
+ * ci of every computed cell := the capacity among 0.1, 0.2 .. 4.9 mm (arange_r, m_array_creation.f90:41-54) whose
+ * cumulated sub-daily interception evaporation is closest to the cumulated daily one.  The reference loops candidate ->
+ * time -> cell; cells are independent, so cell -> candidate -> time below forms the same sums in the same order.
+ * ========================================================================================== */
+int OSYM(oracle_adjust_interception_store)(const Prob *P, int nday, const int *day_index, oreal *ci) {
+    const oreal stt = R(0.1), stp = R(5.0), step = R(0.1);
+    const int ncand = (int)ceil((double)((stp - stt) / step));           /* :33 */
+    if (ncand <= 0 || ncand > 64 || nday <= 0) return 1;
+    oreal cmax[64];
+    for (int i = 0; i < ncand; i++) cmax[i] = stt + (oreal)i * step;      /* m_array_creation.f90:50 */
+    oreal *daily_p = (oreal *)malloc((size_t)nday * sizeof(oreal)), *daily_e = (oreal *)malloc((size_t)nday * sizeof(oreal));
+    for (int col = 1; col <= P->ncol; col++) {
+        for (int row = 1; row <= P->nrow; row++) {
+            size_t c = IDX(P, row, col);
+            if (!(P->active_cell[c] == 1 && (!P->local_active_cell || P->local_active_cell[c] == 1))) continue; /* :100, :138 */
+            for (int d = 0; d < nday; d++) daily_p[d] = daily_e[d] = 0;
+            int n = 0;
+            for (int t = 0; t < P->ntime_step; t++) {                     /* :44-75 */
+                if (t > 0 && day_index[t] != day_index[t - 1]) n++;
+                if (n >= nday) { free(daily_p); free(daily_e); return 1; }
+                oreal prcp, pet;
+                read_forcing(P, row, col, t, &prcp, &pet);
+                daily_p[n] = daily_p[n] + prcp;
+                daily_e[n] = daily_e[n] + pet;
+            }
+            oreal daily_cumulated = 0;
+            for (int d = 0; d < nday; d++) daily_cumulated = daily_cumulated + fmin(daily_p[d], daily_e[d]); /* :79-91 */
+            int best = 0;
+            oreal best_diff = 0;
+            for (int i = 0; i < ncand; i++) {                              /* :95-131 */
+                oreal h = 0, sub = 0, pth, ec;
+                for (int t = 0; t < P->ntime_step; t++) {
+                    oreal prcp, pet;
+                    read_forcing(P, row, col, t, &prcp, &pet);
+                    gr_interception(prcp, pet, cmax[i], &h, &pth, &ec);   /* :117 */
+                    sub = sub + ec;
+                }
+                oreal diff = FABS(sub - daily_cumulated);
+                if (i == 0 || diff < best_diff) { best = i; best_diff = diff; }   /* minloc: first smallest, :142 */
+            }
+            ci[c] = cmax[best];                                           /* :143 */
+        }
+    }
+    free(daily_p); free(daily_e);
+    return 0;
+}
+
 /* select case (trim(setup%structure)) forward.f90:43-65, :120-142 */
 static void run_structure(const Prob *P, const oreal *par, oreal *st, oreal *qsim, oreal *qdom, oreal *netp) {
     if (P->structure <= OST_GR_A) gr_a_forward(P, par, st, qsim, qdom, netp, NULL);

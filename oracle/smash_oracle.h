@@ -127,6 +127,8 @@ int OSYM(oracle_multiple_run)(const OSYM(OProblem) *P, const oreal *parameters, 
                               oreal *res_qsim, int nthreads);
 
 /* Pieces exported for unit tests. */
+/* adjust_interception_store (mw_interception_store.f90:19-160): ci (nrow,ncol) is updated on the computed cells only */
+int OSYM(oracle_adjust_interception_store)(const OSYM(OProblem) *P, int nday, const int *day_index, oreal *ci);
 void OSYM(oracle_gr_production)(oreal pn, oreal en, oreal cp, oreal beta, oreal *hp, oreal *pr, oreal *perc);
 void OSYM(oracle_gr_transfer)(oreal n, oreal prcp, oreal pr, oreal ct, oreal *ht, oreal *q);
 oreal OSYM(oracle_nse)(const oreal *x, const oreal *y, int n);

@@ -79,7 +79,7 @@ EXPORTS = [
     "smash_b200_plan_run_forward", "smash_b200_plan_run_gradient", "smash_b200_plan_run_hyper_gradient", "smash_b200_plan_get_qsim",
     "smash_b200_plan_get_gradient", "smash_b200_plan_checksum", "smash_b200_plan_info", "smash_b200_plan_order",
     "smash_b200_mesh_order", "smash_b200_mesh_chains", "smash_b200_mesh_tick_schedule", "smash_b200_flow_accumulation",
-    "smash_b200_gauge_masks", "smash_b200_compute_mean_forcing", "smash_b200_mlp_forward", "smash_b200_mlp_create", "smash_b200_mlp_destroy",
+    "smash_b200_gauge_masks", "smash_b200_compute_mean_forcing", "smash_b200_adjust_interception_store", "smash_b200_mlp_forward", "smash_b200_mlp_create", "smash_b200_mlp_destroy",
     "smash_b200_mlp_run_forward", "smash_b200_mlp_run_backward", "smash_b200_plan_kernel_times", "smash_b200_plan_stat",
     "smash_b200_comm_unique_id", "smash_b200_comm_create", "smash_b200_comm_destroy", "smash_b200_comm_allreduce",
     "smash_b200_comm_allgather", "smash_b200_comm_rank", "smash_b200_comm_world", "smash_b200_comm_last_error",

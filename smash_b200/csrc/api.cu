@@ -1959,6 +1959,8 @@ cudaError_t pre_flow_accumulation(int nrow, int ncol, const int32_t *flwdir, con
 cudaError_t pre_gauge_masks(int nrow, int ncol, int ng, const int32_t *flwdir, const int32_t *gauge_pos, uint8_t *mask, uint8_t *d_mask_out);
 cudaError_t pre_mean_forcing(int nrow, int ncol, int ng, int T, const int32_t *flwdir, const int32_t *gauge_pos, int n, const int32_t *cell_of,
                              const float *prcp, const float *pet, float *mean_prcp, float *mean_pet);
+cudaError_t pre_interception(int n, int T, const int64_t *src_index, int64_t slab, const float *prcp, const float *pet, const int32_t *day_index,
+                             float *ci_out, float *ms);
 }
 
 // replaces mw_meshing::flow_accumulation (smash/mesh/mw_meshing.f90:204-233)
@@ -2004,6 +2006,42 @@ extern "C" int smash_b200_compute_mean_forcing(const SmashSetup *setup, const Sm
         CU(pre_mean_forcing(mesh->nrow, mesh->ncol, mesh->ng, setup->ntime_step, mesh->flwdir, mesh->gauge_pos, ncell, nullptr, in->prcp,
                             in->pet, mean_prcp, mean_pet));
     }
+    return 0;
+}
+
+// replaces mw_interception_store::adjust_interception_store (solver/routine/mw_interception_store.f90:19-160)
+extern "C" int smash_b200_adjust_interception_store(const SmashSetup *setup, const SmashMesh *mesh, const SmashInputData *in, int32_t nday,
+                                                    const int32_t *day_index, float *ci, float *kernel_ms) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!setup || !mesh || !in || !day_index || !ci) return fail(SMASH_B200_EINVAL, "NULL argument");
+    if (!mesh->active_cell) return fail(SMASH_B200_EINVAL, "mesh.active_cell is NULL");
+    const int T = setup->ntime_step;
+    int days = 1;
+    for (int t = 1; t < T; t++) days += day_index[t] != day_index[t - 1];
+    if (nday < days) return fail(SMASH_B200_EINVAL, "nday = %d but day_index holds %d days", nday, days);
+    TRY(check_device());
+    const int ncell = mesh->nrow * mesh->ncol;
+    const float *prcp = setup->sparse_storage ? in->sparse_prcp : in->prcp, *pet = setup->sparse_storage ? in->sparse_pet : in->pet;
+    if (!prcp || !pet) return fail(SMASH_B200_EINVAL, "input_data forcing arrays are NULL");
+    if (setup->sparse_storage && !mesh->rowcol_to_ind_sparse) return fail(SMASH_B200_EINVAL, "mesh.rowcol_to_ind_sparse is NULL");
+    std::vector<int64_t> src;
+    std::vector<int32_t> cell;
+    for (int c = 0; c < ncell; c++) {                                    // :100, :138 the computed cells
+        if (!(mesh->active_cell[c] == 1 && (!mesh->local_active_cell || mesh->local_active_cell[c] == 1))) continue;
+        int64_t k = c;
+        if (setup->sparse_storage) {
+            k = (int64_t)mesh->rowcol_to_ind_sparse[c] - 1;
+            if (k < 0 || k >= mesh->nac) return fail(SMASH_B200_EINVAL, "mesh.rowcol_to_ind_sparse holds an index outside 1..nac");
+        }
+        src.push_back(k);
+        cell.push_back(c);
+    }
+    std::vector<float> out(src.size());
+    float ms = 0.0f;
+    CU(pre_interception((int)src.size(), T, src.data(), setup->sparse_storage ? (int64_t)mesh->nac : (int64_t)ncell, prcp, pet, day_index,
+                        out.data(), &ms));
+    for (size_t i = 0; i < cell.size(); i++) ci[cell[i]] = out[i];
+    if (kernel_ms) *kernel_ms = ms;
     return 0;
 }
 

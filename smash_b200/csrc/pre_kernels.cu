@@ -198,4 +198,90 @@ cudaError_t pre_mean_forcing(int nrow, int ncol, int ng, int T, const int32_t *f
     return cudaSuccess;
 }
 
+// ------------------------------------------------------------------------------------------------
+// adjust_interception_store (solver/routine/mw_interception_store.f90:19-160): the capacity ci of gr-b / gr-c, cell by cell.
+// Thread (cell, group): one pass over the cell's forcing series forms the daily sums (:44-91) and, for the group's seven
+// capacities of cmax = 0.1, 0.2 .. 4.9 (arange_r, m_array_creation.f90:41-54), the cumulated interception evaporation of
+// gr_interception (operator/md_gr_operator.f90:20-34; :95-131).  |sub-daily - daily| and the candidate index are packed into
+// one 64-bit key (a non-negative float orders like its bit pattern), atomicMin over the seven groups = minloc's first smallest
+// (:142).  Every statement is a single rounded operation (no contraction), like the scalar Fortran.
+// ------------------------------------------------------------------------------------------------
+constexpr int CI_NCAND = 49, CI_GROUP = 7;
+
+__global__ void __launch_bounds__(128) interception_kernel(int n, int T, const int64_t *src_index, int64_t slab, const float *prcp, const float *pet,
+                                                           const uint8_t *newday, unsigned long long *best) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c0 = blockIdx.y * CI_GROUP;
+    float ci[CI_GROUP], h[CI_GROUP], sub[CI_GROUP];
+#pragma unroll
+    for (int k = 0; k < CI_GROUP; k++) {
+        ci[k] = __fadd_rn(0.1f, __fmul_rn((float)(c0 + k), 0.1f));       // res(i) = stt + (i - 1)*step
+        h[k] = 0.0f; sub[k] = 0.0f;
+    }
+    const float *pp = prcp + src_index[i], *pe = pet + src_index[i];
+    float dp = 0.0f, de = 0.0f, cum = 0.0f;
+    for (int t = 0; t < T; t++) {
+        const float p = pp[(int64_t)t * slab], e = pe[(int64_t)t * slab];
+        if (newday[t]) {                                                  // :46 a new day starts: close the previous one (:79-91)
+            cum = __fadd_rn(cum, fminf(dp, de));
+            dp = 0.0f; de = 0.0f;
+        }
+        dp = __fadd_rn(dp, p); de = __fadd_rn(de, e);
+#pragma unroll
+        for (int k = 0; k < CI_GROUP; k++) {
+            const float ei = fminf(e, __fadd_rn(p, __fmul_rn(h[k], ci[k])));
+            const float pn = fmaxf(0.0f, __fsub_rn(__fsub_rn(p, __fmul_rn(ci[k], __fsub_rn(1.0f, h[k]))), ei));
+            h[k] = __fadd_rn(h[k], __fdiv_rn(__fsub_rn(__fsub_rn(p, ei), pn), ci[k]));
+            sub[k] = __fadd_rn(sub[k], ei);
+        }
+    }
+    cum = __fadd_rn(cum, fminf(dp, de));
+    unsigned long long key = ~0ull;
+#pragma unroll
+    for (int k = 0; k < CI_GROUP; k++) {
+        const float d = fabsf(__fsub_rn(sub[k], cum));
+        const unsigned long long kk = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)(c0 + k);
+        key = kk < key ? kk : key;
+    }
+    atomicMin(&best[i], key);
+}
+
+// n computed cells; src_index[i] = offset of cell i inside one time slab of prcp / pet (host arrays of slab * T floats);
+// ci_out[i] = the chosen capacity
+cudaError_t pre_interception(int n, int T, const int64_t *src_index, int64_t slab, const float *prcp, const float *pet, const int32_t *day_index,
+                             float *ci_out, float *ms) {
+    if (n <= 0 || T <= 0) return cudaSuccess;
+    Dev<int64_t> d_idx;
+    Dev<float> d_p, d_e;
+    Dev<uint8_t> d_new;
+    Dev<unsigned long long> d_best;
+    cudaError_t e;
+    std::vector<uint8_t> newday(T, 0);
+    for (int t = 1; t < T; t++) newday[t] = day_index[t] != day_index[t - 1];
+    if ((e = d_idx.alloc(n)) || (e = d_p.alloc((size_t)slab * T)) || (e = d_e.alloc((size_t)slab * T)) || (e = d_new.alloc(T)) ||
+        (e = d_best.alloc(n)))
+        return e;
+    if ((e = cudaMemcpy(d_idx.p, src_index, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice))) return e;
+    if ((e = cudaMemcpy(d_p.p, prcp, (size_t)slab * T * sizeof(float), cudaMemcpyHostToDevice))) return e;
+    if ((e = cudaMemcpy(d_e.p, pet, (size_t)slab * T * sizeof(float), cudaMemcpyHostToDevice))) return e;
+    if ((e = cudaMemcpy(d_new.p, newday.data(), (size_t)T, cudaMemcpyHostToDevice))) return e;
+    if ((e = cudaMemset(d_best.p, 0xff, (size_t)n * sizeof(unsigned long long)))) return e;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0);
+    interception_kernel<<<dim3((unsigned)((n + 127) / 128), CI_NCAND / CI_GROUP), 128>>>(n, T, d_idx.p, slab, d_p.p, d_e.p, d_new.p, d_best.p);
+    cudaEventRecord(e1);
+    if ((e = cudaGetLastError())) return e;
+    std::vector<unsigned long long> best(n);
+    if ((e = cudaMemcpy(best.data(), d_best.p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost))) return e;
+    if (ms) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (int i = 0; i < n; i++) {
+        const int c = (int)(best[i] & 0xffffffffu);
+        ci_out[i] = 0.1f + (float)c * 0.1f;
+    }
+    return cudaSuccess;
+}
+
 }  // namespace smash

@@ -81,3 +81,58 @@ def test_adjoint_is_gr_a_only():
     pb, sb = ParametersDT(m.mesh), StatesDT(m.mesh)
     with pytest.raises(AssertionError):
         oracle.forward_b(m.setup, m.mesh, m.input_data, m.parameters, pb, m.parameters.copy(), m.states, sb, m.states.copy(), m.output)
+
+
+# ---- adjust_interception_store (mw_interception_store.f90:19-160) ---------------------------------------------------------
+
+def _day_index(T, steps_per_day=24):
+    return (np.arange(T) // steps_per_day + 1).astype(np.int32)
+
+
+def _one_cell_by_hand(prcp, pet, day_index):
+    """The routine for one cell in NumPy float32 scalars, written from the Fortran text: daily sums, 49 capacities, minloc."""
+    f = np.float32
+    days = {}
+    for p, e, d in zip(prcp, pet, day_index):
+        a, b = days.get(d, (f(0), f(0)))
+        days[d] = (f(a + p), f(b + e))
+    daily = f(0)
+    for d in sorted(days):
+        daily = f(daily + min(days[d][0], days[d][1]))
+    best, best_diff = None, None
+    for i in range(49):
+        ci = f(f(0.1) + f(f(i) * f(0.1)))
+        h, sub = f(0), f(0)
+        for p, e in zip(prcp, pet):
+            ei = min(e, f(p + f(h * ci)))
+            pn = max(f(0), f(f(p - f(ci * f(f(1) - h))) - ei))
+            h = f(h + f(f(f(p - ei) - pn) / ci))
+            sub = f(sub + ei)
+        diff = abs(f(sub - daily))
+        if best is None or diff < best_diff:
+            best, best_diff = ci, diff
+    return best
+
+
+def test_interception_store_against_a_hand_restatement():
+    m = cases.cance(T=240)
+    m.setup.structure = "gr-b"
+    di = _day_index(240)
+    oracle.adjust_interception_store(m.setup, m.mesh, m.input_data, m.parameters, 10, di)
+    ci = np.asarray(m.parameters.ci)
+    act = m.mesh.active_cell == 1
+    assert np.all(ci[~act] == np.float32(1e-6))                              # untouched outside the computed cells
+    assert ci[act].min() >= np.float32(0.1) and ci[act].max() <= np.float32(4.9) + 1e-6
+    rr, cc = np.nonzero(act)
+    for k in (0, 57, 191, len(rr) - 1):
+        r, c = rr[k], cc[k]
+        want = _one_cell_by_hand(m.input_data.prcp[r, c, :], m.input_data.pet[r, c, :], di)
+        assert ci[r, c] == want, (k, ci[r, c], want)
+
+
+def test_interception_store_without_rain_takes_the_first_capacity():
+    m = cases.cance(T=96, sparse=True)
+    m.input_data.sparse_prcp[...] = 0.0
+    oracle.adjust_interception_store(m.setup, m.mesh, m.input_data, m.parameters, 4, _day_index(96))
+    act = m.mesh.active_cell == 1
+    assert np.all(np.asarray(m.parameters.ci)[act] == np.float32(0.1))       # every diff is 0: minloc returns the first
