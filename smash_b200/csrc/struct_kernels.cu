@@ -163,8 +163,9 @@ template <int FAST> __device__ __forceinline__ float d_vic_baseflow(const SPar &
 }
 
 // one cell-step of the runoff-production part; returns qt
-template <int ST, int FAST> __device__ __forceinline__ float struct_step(const SPar &p, float prcp, float pet, SSto &s) {
-    const bool nogap = (prcp >= 0.0f) && (pet >= 0.0f);
+// NOGAP: the caller has checked that no lane of the warp has a forcing gap in this box (the usual case)
+template <int ST, int FAST, bool NOGAP = false> __device__ __forceinline__ float struct_step(const SPar &p, float prcp, float pet, SSto &s) {
+    const bool nogap = NOGAP || ((prcp >= 0.0f) && (pet >= 0.0f));
     if (ST == SMASH_STRUCTURE_VIC_A) {
         float runoff = 0.0f;
         if (nogap) {
@@ -190,7 +191,8 @@ template <int ST, int FAST> __device__ __forceinline__ float struct_step(const S
         }
         const float en = pet - ei;
         d_production<FAST>(pn, en, p.cp, p.inv_cp, s.hp, pr, perc);                          // :306, :490, :676
-        if (ST != SMASH_STRUCTURE_GR_D) l = (p.exc == 0.0f) ? 0.0f : p.exc * pow_3p5(s.hft); // gr_exchange :313, :497
+        if (ST != SMASH_STRUCTURE_GR_D)                                                      // gr_exchange :313, :497
+            l = FAST ? p.exc * ((s.hft * s.hft) * s.hft * fsqrt_fast(s.hft)) : ((p.exc == 0.0f) ? 0.0f : p.exc * pow_3p5(s.hft));
     }
     if (ST == SMASH_STRUCTURE_GR_B) {
         const float prr = 0.9f * (pr + perc) + l;                                            // :321
@@ -258,6 +260,7 @@ __global__ void __launch_bounds__(ST_WARPS * 32) vertical_struct_kernel(const __
         E = expf(-a.dt / (P(SMASH_P_LR) * 60.0f));                         // md_routing_operator.f90:75
     }
     const bool src = fa <= 1;
+    const bool all_valid = j0 + 32 <= n;
     const int gfirst = valid ? a.tp.gauge_first[j] : -1;
     const size_t qpitch = (size_t)a.qpitch;
     float *row = a.rows + ((size_t)m * npad + j) * a.Tp;
@@ -285,6 +288,30 @@ __global__ void __launch_bounds__(ST_WARPS * 32) vertical_struct_kernel(const __
             st_tma_load_2d(&stage[slot][1][0][0], &tm_pet, j0, (st + ST_NST) * ST_TK, &bars[slot]);
         }
         const int tb = st * ST_TK;
+        float mn = 0.0f;
+#pragma unroll
+        for (int i = 0; i < ST_TK; i++) mn = fminf(mn, fminf(pv[i], ev[i]));
+        if (FAST && all_valid && tb + ST_TK <= T && __all_sync(FULLM, mn >= 0.0f)) {
+            // whole box, every lane a cell, no forcing gap in the warp: no per-step guards, the stores are updated in place
+#pragma unroll
+            for (int i = 0; i < ST_TK; i++) {
+                const int t = tb + i;
+                const float qt = struct_step<ST, FAST, true>(p, pv[i], ev[i], s);
+                float q = qt;
+                if (np_) np_[(size_t)t * qpitch] = qt;
+                if (src) {
+                    q = qt * c0;
+                    hlr = (hlr + 0.0f) * E;
+                    if (qd) qd[(size_t)t * qpitch] = q;
+                    if (gfirst >= 0)
+                        for (int g = gfirst; g >= 0; g = a.tp.gauge_next[g]) qsim[(size_t)t * ng + g] = q;
+                }
+                qv[i] = q;
+            }
+            st_st8(row + (size_t)tb, qv);
+            if (++slot == ST_NST) { slot = 0; parity ^= 1u; }
+            continue;
+        }
 #pragma unroll
         for (int i = 0; i < ST_TK; i++) {
             const int t = tb + i;

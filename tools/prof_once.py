@@ -1,5 +1,5 @@
 """One run of a configuration for ncu captures (no warm-up: ncu replays every kernel).
-usage: python tools/prof_once.py france_fwd | france_grad | ensemble | hyper"""
+usage: python tools/prof_once.py france_fwd | france_grad | ensemble | hyper | struct:<gr-b|gr-c|gr-d|vic-a>"""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -7,6 +7,9 @@ import numpy as np
 import cases
 from smash_b200 import _lib as L
 what = sys.argv[1]
+structure = "gr-a"
+if what.startswith("struct:"):
+    structure, what = what.split(":")[1], "france_fwd"
 lib = L.lib()
 if what == "ensemble":
     m = cases.cance(sparse=True)
@@ -14,6 +17,9 @@ if what == "ensemble":
 else:
     m = cases.france(T=720, ngauge=4 if what in ("france_grad", "hyper") else 0, nd=6 if what == "hyper" else 0, qobs_from_oracle=False)
     members = 1
+m.setup.structure = structure
+if structure in ("gr-b", "gr-c"):
+    m.parameters.ci[...] = 2.0
 if what == "hyper":
     from test_gpu_parity2 import _hyper_objects
     cases.set_optimize(m.setup, m.mesh, jobs_fun=("nse",), mapping="hyper-polynomial", gauge="all")
