@@ -249,3 +249,53 @@ def test_net_init_golden(golden):
         layer = net.layers[3 * i]
         assert np.allclose(layer.weight, golden[f"net_init.weight_layer_{i + 1}"], atol=1e-6)
         assert np.allclose(layer.bias, golden[f"net_init.bias_layer_{i + 1}"], atol=1e-6)
+
+
+# ---- the other structures under the derivative-free driver (their adjoint is not built: l-bfgs-b is refused) ---------------------
+
+OTHER_STRUCTURES = ("gr-b", "gr-c", "gr-d", "vic-a")
+
+
+def _sbs_other(structure, solver):
+    m = cases.cance(T=480)
+    m.setup.structure = structure
+    m.parameters.ci[...] = 2.0
+    before = m.copy()
+    run = oracle_solver if solver is not None else __import__("smash_b200")
+    run.forward(before.setup, before.mesh, before.input_data, before.parameters, before.parameters.copy(), before.states,
+                before.states.copy(), before.output)
+    inst = simulation.optimize(m, algorithm="sbs", options={"maxiter": 2}, solver=solver)
+    return before, inst
+
+
+@pytest.mark.parametrize("structure", OTHER_STRUCTURES)
+def test_sbs_other_structures_cpu(structure):
+    # default control vector = STRUCTURE_PARAMETERS[structure] (_constant.py:13-19), uniform mapping, two sbs iterations
+    before, inst = _sbs_other(structure, oracle_solver)
+    assert float(inst.output.cost) < float(before.output.cost)
+    moved = [n for n in simulation.STRUCTURE_PARAMETERS[structure]
+             if not np.array_equal(getattr(inst.parameters, n), getattr(before.parameters, n))]
+    assert moved, "no parameter of the control vector moved"
+    untouched = set(simulation.GPARAMETERS_NAME) - set(simulation.STRUCTURE_PARAMETERS[structure])
+    for n in untouched:
+        assert np.array_equal(getattr(inst.parameters, n), getattr(before.parameters, n)), n
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("structure", OTHER_STRUCTURES)
+def test_sbs_other_structures_gpu(structure):
+    # the same search through libsmash_b200.so: same path through the parameter space, same cost to the device tolerance
+    _, cpu = _sbs_other(structure, oracle_solver)
+    _, gpu = _sbs_other(structure, None)
+    assert abs(float(gpu.output.cost) - float(cpu.output.cost)) < (5e-4 if structure == "vic-a" else COST_ATOL_GPU * 5)
+    for n in simulation.STRUCTURE_PARAMETERS[structure]:
+        a, b = getattr(gpu.parameters, n), getattr(cpu.parameters, n)
+        assert np.allclose(a, b, rtol=2e-2, atol=1e-3), (n, float(a.max()), float(b.max()))
+
+
+@pytest.mark.gpu
+def test_lbfgsb_is_refused_for_other_structures():
+    m = cases.cance(T=48)
+    m.setup.structure = "gr-d"
+    with pytest.raises(RuntimeError, match="gr-a only"):
+        simulation.optimize(m, mapping="distributed", algorithm="l-bfgs-b", options={"maxiter": 1})
