@@ -170,8 +170,10 @@ static inline void read_forcing(const Prob *P, int row, int col, int t, oreal *p
     }
 }
 
-static void gr_a_forward(const Prob *P, const oreal *par, oreal *st, oreal *qsim, oreal *qdom, oreal *netp,
-                         Tape *tape) {
+/* grd != 0: the statements of gr_d_forward instead (md_forward_structure.f90:589-760: no exchange, prr = pr + perc :685,
+ * qt = qr :689) -- the same loop, taped for GR_D_FORWARD_B */
+static void gr_ad_forward(const Prob *P, const oreal *par, oreal *st, oreal *qsim, oreal *qdom, oreal *netp,
+                          Tape *tape, int grd) {
     const size_t ncell = (size_t)P->nrow * P->ncol;
     const oreal *cp = par + OP_CP * ncell, *cft = par + OP_CFT * ncell, *exc = par + OP_EXC * ncell,
                 *lr = par + OP_LR * ncell;
@@ -196,18 +198,28 @@ static void gr_a_forward(const Prob *P, const oreal *par, oreal *st, oreal *qsim
                 pn = fmax(R(0.0), prcp - ei);          /* :114 */
                 en = pet - ei;                         /* :116 */
                 gr_production(pn, en, cp[c], R(1000.0), &hp[c], &pr, &perc); /* :122 */
-                gr_exchange(exc[c], hft[c], &l);       /* :129 */
+                if (!grd) gr_exchange(exc[c], hft[c], &l); /* :129 */
             }
-            prr = R(0.9) * (pr + perc) + l;            /* :137 */
-            prd = R(0.1) * (pr + perc);                /* :138 */
+            if (grd) {
+                prr = pr + perc;                       /* :685 */
+                prd = R(0.0);
+            } else {
+                prr = R(0.9) * (pr + perc) + l;        /* :137 */
+                prd = R(0.1) * (pr + perc);            /* :138 */
+            }
             if (tape) { tape->pn[tp] = pn; tape->en[tp] = en; tape->prr[tp] = prr; tape->hft0[tp] = hft[c]; }
-            gr_transfer(R(5.0), prcp, prr, cft[c], &hft[c], &qr); /* :140 */
-            qd = fmax(R(0.0), prd + l);                /* :142 */
-            qt = (qr + qd);                            /* :144 */
+            gr_transfer(R(5.0), prcp, prr, cft[c], &hft[c], &qr); /* :140, :687 */
+            if (grd) {
+                qd = R(0.0);
+                qt = qr;                               /* :689 */
+            } else {
+                qd = fmax(R(0.0), prd + l);            /* :142 */
+                qt = (qr + qd);                        /* :144 */
+            }
             upstream_discharge(P, row, col, q, &qup);  /* :150 */
             if (tape) {
                 tape->qup[tp] = qup; tape->hlr0[tp] = hlr[c];
-                tape->flags[tp] = (unsigned char)((nogap ? 1 : 0) | ((R(0.0) < prd + l) ? 2 : 0));
+                tape->flags[tp] = (unsigned char)((nogap ? 1 : 0) | ((!grd && R(0.0) < prd + l) ? 2 : 0));
             }
             linear_routing(P->dt, qup, lr[c], &hlr[c], &qrout); /* :153 */
             q[c] = (qt + qrout * (oreal)(P->flwacc[c] - 1)) * P->dx * P->dx * R(0.001) / P->dt; /* :155 */
@@ -224,6 +236,10 @@ static void gr_a_forward(const Prob *P, const oreal *par, oreal *st, oreal *qsim
             qsim[g + (size_t)P->ng * t] = q[IDX(P, P->gauge_pos[g], P->gauge_pos[g + P->ng])];
     }
     free(q);
+}
+
+static void gr_a_forward(const Prob *P, const oreal *par, oreal *st, oreal *qsim, oreal *qdom, oreal *netp, Tape *tape) {
+    gr_ad_forward(P, par, st, qsim, qdom, netp, tape, 0);
 }
 
 /* ============================================================================================
@@ -555,14 +571,17 @@ static void upstream_discharge_b(const Prob *P, int row, int col, oreal *q_b, or
 
 /* GR_A_FORWARD_B forward_db.f90:7954-8175: taped forward sweep then reverse sweep.
  * qsim_b is consumed (zeroed) like output_b%qsim (:8107). */
+/* GR_A_FORWARD_B forward_db.f90:7954-8175; with grd != 0 GR_D_FORWARD_B :9604-9797 (qr_b = qt_b :9763, pr_b = perc_b = prr_b
+ * :9770-9771, no exchange, parameters_b%exc untouched) */
 static void gr_a_forward_b(const Prob *P, const oreal *par, oreal *par_b, oreal *st, oreal *st_b, oreal *qsim,
                            oreal *qsim_b) {
+    const int grd = P->structure == OST_GR_D;
     const size_t ncell = (size_t)P->nrow * P->ncol;
     Tape tape;
     tape_alloc(&tape, P);
     oreal *st0 = (oreal *)malloc(O_GNS * ncell * sizeof(oreal));
     memcpy(st0, st, O_GNS * ncell * sizeof(oreal));
-    gr_a_forward(P, par, st, qsim, NULL, NULL, &tape);
+    gr_ad_forward(P, par, st, qsim, NULL, NULL, &tape, grd);
     memcpy(st, st0, O_GNS * ncell * sizeof(oreal)); /* the POPREAL4s leave the initial states */
     free(st0);
 
@@ -598,11 +617,11 @@ static void gr_a_forward_b(const Prob *P, const oreal *par, oreal *par_b, oreal 
             else { l_b = R(0.0); prd_b = R(0.0); }
             oreal prr_b = R(0.0);
             gr_transfer_b(R(5.0), prcp, tape.prr[tp], &prr_b, cft[c], &cft_b[c], tape.hft0[tp], &hft_b[c], qr_b);
-            oreal pr_b = R(0.1) * prd_b + R(0.9) * prr_b;    /* :8143 */
-            oreal perc_b = R(0.1) * prd_b + R(0.9) * prr_b;
+            oreal pr_b = grd ? prr_b : R(0.1) * prd_b + R(0.9) * prr_b;    /* :8143, :9770 */
+            oreal perc_b = grd ? prr_b : R(0.1) * prd_b + R(0.9) * prr_b;  /* :8144, :9771 */
             l_b = l_b + prr_b;
-            if (tape.flags[tp] & 1) {                        /* :8148-8165 */
-                gr_exchange_b(exc[c], &exc_b[c], tape.hft0[tp], &hft_b[c], l_b);
+            if (tape.flags[tp] & 1) {                        /* :8148-8165, :9773-9787 */
+                if (!grd) gr_exchange_b(exc[c], &exc_b[c], tape.hft0[tp], &hft_b[c], l_b);
                 gr_production_b(tape.pn[tp], tape.en[tp], cp[c], &cp_b[c], R(1000.0), tape.hp0[tp], &hp_b[c], pr_b,
                                 perc_b);
             }
@@ -1177,7 +1196,7 @@ int OSYM(oracle_forward_b)(const Prob *P, oreal *parameters, oreal *parameters_b
                            oreal *states, oreal *states_b, const oreal *states_bgd, oreal *qsim, oreal *out_cost) {
     const size_t ncell = (size_t)P->nrow * P->ncol;
     const oreal cost_b = R(1.0);
-    if (P->structure > OST_GR_A) return 2;               /* only GR_A_FORWARD_B is restated */
+    if (P->structure > OST_GR_A && P->structure != OST_GR_D) return 2;   /* GR_A_FORWARD_B and GR_D_FORWARD_B are restated */
     if (P->denormalize_forward) {                       /* :10697-10703 */
         denormalize(P, parameters, O_GNP, P->lb_parameters, P->ub_parameters);
         denormalize(P, states, O_GNS, P->lb_states, P->ub_states);
@@ -1186,7 +1205,7 @@ int OSYM(oracle_forward_b)(const Prob *P, oreal *parameters, oreal *parameters_b
     oreal *st0 = (oreal *)malloc(O_GNS * ncell * sizeof(oreal));
     memcpy(par0, parameters, O_GNP * ncell * sizeof(oreal));
     memcpy(st0, states, O_GNS * ncell * sizeof(oreal));
-    gr_a_forward(P, parameters, states, qsim, NULL, NULL, NULL);       /* :10713 */
+    run_structure(P, parameters, states, qsim, NULL, NULL);            /* :10713 */
     memcpy(states, st0, O_GNS * ncell * sizeof(oreal));                /* :10770 */
     compute_cost(P, parameters, parameters_bgd, states, states_bgd, qsim, out_cost); /* :10821 */
     memcpy(parameters, par0, O_GNP * ncell * sizeof(oreal));           /* POPREAL4ARRAYs :10823-10868 */
@@ -1305,12 +1324,12 @@ int OSYM(oracle_hyper_forward_b)(const Prob *P, oreal *parameters, const oreal *
                                  oreal *hyper_parameters_b, oreal *states, const oreal *hyper_states,
                                  oreal *hyper_states_b, oreal *qsim, oreal *out_cost) {
     const size_t ncell = (size_t)P->nrow * P->ncol;
-    if (P->structure > OST_GR_A) return 2;
+    if (P->structure > OST_GR_A && P->structure != OST_GR_D) return 2;
     hyper_to_field(P, hyper_parameters, parameters, O_GNP, P->lb_parameters, P->ub_parameters);
     hyper_to_field(P, hyper_states, states, O_GNS, P->lb_states, P->ub_states);
     oreal *st0 = (oreal *)malloc(O_GNS * ncell * sizeof(oreal));
     memcpy(st0, states, O_GNS * ncell * sizeof(oreal));
-    gr_a_forward(P, parameters, states, qsim, NULL, NULL, NULL);
+    run_structure(P, parameters, states, qsim, NULL, NULL);
     oreal jobs = compute_jobs(P, qsim, NULL, 0);
     if (out_cost) { out_cost[0] = jobs; out_cost[1] = jobs; out_cost[2] = 0; }
     oreal *qsim_b = (oreal *)calloc((size_t)(P->ng > 0 ? P->ng : 1) * P->ntime_step, sizeof(oreal));

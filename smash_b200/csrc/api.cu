@@ -244,6 +244,10 @@ struct SmashPlan {
     }
 };
 
+// gr-b, gr-c, vic-a: their own reservoir pass (struct_kernels.cu), forward only.  gr-d runs on gr-a's kernels (forward, tape and
+// reverse sweep) with the shares 1 / 0 and exc = 0 (SplitArgs::grd), which makes every statement gr_d_forward's / GR_D_FORWARD_B's.
+static bool struct_pass(const SmashPlan &pl) { return pl.structure != SMASH_STRUCTURE_GR_A && pl.structure != SMASH_STRUCTURE_GR_D; }
+
 static std::mutex g_mu;
 static std::map<std::string, std::unique_ptr<SmashPlan>> g_plans;
 
@@ -593,7 +597,8 @@ static int split_members(SmashPlan &pl, int nmember, bool save_q, bool save_netp
     TRY(pl.d_fields.ensure(nm * NFIELD * npad));
     TRY(pl.d_fstates.ensure(nm * 3 * npad));
     if (pl.structure != SMASH_STRUCTURE_GR_A) {
-        if (gradient) return fail(SMASH_B200_EUNSUPPORTED, "structure %d: the adjoint is implemented for gr-a only", pl.structure);
+        if (gradient && struct_pass(pl))
+            return fail(SMASH_B200_EUNSUPPORTED, "structure %d: the adjoint is implemented for gr-a and gr-d only", pl.structure);
         TRY(pl.d_sfields.ensure(nm * (SMASH_B200_GNP + SMASH_B200_GNS) * npad));
         TRY(pl.d_sfstates.ensure(nm * SMASH_B200_GNS * npad));
     }
@@ -672,6 +677,7 @@ static SplitArgs split_args(SmashPlan &pl, bool save_q, bool save_netp, SplitSta
     a.dyn_nq = gr.dyn_nq; a.qctl = gr.d_qctl.p; a.queue = gr.d_queue.p; a.ndep = gr.d_ndep.p; a.cons = gr.d_cons.p; a.qid = gr.d_qid.p;
     a.qoff = gr.d_qoff.p; a.qctl0 = gr.d_qctl0.p; a.queue0 = gr.d_queue0.p; a.ndep0 = gr.d_ndep0.p;
     a.sfields = pl.d_sfields.p; a.sfstates = pl.d_sfstates.p;
+    a.grd = pl.structure == SMASH_STRUCTURE_GR_D ? 1 : 0;
     a.fields = pl.d_fields.p; a.fstates = pl.d_fstates.p; a.rows = sp.d_rows.p; a.qdom = pl.d_qdom.p; a.netp = pl.d_netp.p;
     a.qpitch = sp.qpitch; a.qsim = pl.d_qsim.p; a.tape_hp = sp.d_tape_hp.p; a.tape_hft = sp.d_tape_hft.p; a.rows_hr = sp.d_rows_hr.p;
     a.hcar = sp.d_hcar.p; a.done = graph ? gr.d_done.p : sp.d_done.p; a.ticket = pl.d_ticket.p; a.qsim_b = pl.d_qsim_b.p; a.rows_w = sp.d_rows_w.p;
@@ -792,8 +798,8 @@ static int split_forward(SmashPlan &pl, bool save_q, bool save_netp, bool tape) 
         pl.tick_ran = true;
         return 0;
     }
-    if (pl.structure != SMASH_STRUCTURE_GR_A) {
-        if (tape) return fail(SMASH_B200_EUNSUPPORTED, "structure %d: the adjoint is implemented for gr-a only", pl.structure);
+    if (struct_pass(pl)) {
+        if (tape) return fail(SMASH_B200_EUNSUPPORTED, "structure %d: the adjoint is implemented for gr-a and gr-d only", pl.structure);
         CU(launch_vertical_struct(a, sp.tm_prcp, sp.tm_pet, pl.structure, math_mode(), pl.stream));
     } else {
         CU(launch_vertical_forward(a, sp.tm_prcp, sp.tm_pet, math_mode(), tape, pl.stream));
@@ -1411,7 +1417,7 @@ static int forward_common(const SmashSetup *setup, const SmashMesh *mesh, const 
     std::vector<float> fs((size_t)3 * pl->ncols), sfs;
     float jobs = 0.0f;
     TRY(download(*pl, fs.data(), pl->d_fstates.p, fs.size() * sizeof(float)));
-    const bool other = pl->structure != SMASH_STRUCTURE_GR_A;
+    const bool other = struct_pass(*pl);
     if (other) {
         sfs.resize((size_t)SMASH_B200_GNS * pl->ncols);
         TRY(download(*pl, sfs.data(), pl->d_sfstates.p, sfs.size() * sizeof(float)));

@@ -105,6 +105,8 @@ __device__ __forceinline__ float fsqrt_fast(float x) { return x * mufu_rsq(x); }
 struct CellConst {
     float cp, inv_cp, cft, inv_cft, cft_m4, exc, lr, E, fa1, den;  // den = 0.001*dx*dx*(flwacc-1)
     float s_q, c0;                                                  // dt/den (0 for sources) and dx*dx*0.001/dt
+    float kr, kd;   // shares of pr + perc that go to the transfer store / to the direct branch: 0.9, 0.1 (md_forward_structure.f90:137-138);
+                    // 1, 0 with exc = 0 turns every statement into gr_d_forward's (:685-689) and the reverse sweep into GR_D_FORWARD_B
 };
 
 // One gr-a cell-step WITHOUT routing (md_forward_structure.f90:106-144).  Updates hp, hft; returns qt and
@@ -138,8 +140,8 @@ __device__ __forceinline__ StepOut vertical_step(const CellConst &k, float prcp,
         // gr_exchange md_gr_operator.f90:69-79
         l = (k.exc == 0.0f) ? 0.0f : k.exc * pow_3p5(hft);
     }
-    o.prr = 0.9f * (pr + perc) + l;                                  // :137
-    o.prd = 0.1f * (pr + perc);                                      // :138
+    o.prr = k.kr * (pr + perc) + l;                                  // :137
+    o.prd = k.kd * (pr + perc);                                      // :138
     o.l = l;
     // gr_transfer(n = 5) md_gr_operator.f90:81-110
     float pr_imd;
@@ -173,8 +175,10 @@ __device__ __forceinline__ StepOut vertical_step(const CellConst &k, float prcp,
     return o;
 }
 
-__device__ __forceinline__ CellConst make_const(float cp, float cft, float exc, float lr, int flwacc, float dt, float dx) {
+__device__ __forceinline__ CellConst make_const(float cp, float cft, float exc, float lr, int flwacc, float dt, float dx, bool grd = false) {
     CellConst k;
+    if (grd) exc = 0.0f;
+    k.kr = grd ? 1.0f : 0.9f; k.kd = grd ? 0.0f : 0.1f;
     k.cp = cp; k.inv_cp = 1.0f / cp;                                  // md_gr_operator.f90:47
     k.cft = cft; k.inv_cft = 1.0f / cft; k.cft_m4 = 1.0f / pow4(cft);
     k.exc = exc; k.lr = lr;
@@ -216,8 +220,8 @@ __device__ __forceinline__ float vertical_step_nogap(const CellConst &k, float p
     }
     hp = hp_imd - perc * k.inv_cp;                                       // :68
     const float l = k.exc * ((hft * hft) * hft * fsqrt_fast(hft));       // md_gr_operator.f90:77
-    const float prr = fmaf(0.9f, pr + perc, l);                          // md_forward_structure.f90:137
-    const float prd = 0.1f * (pr + perc);                                // :138
+    const float prr = fmaf(k.kr, pr + perc, l);                          // md_forward_structure.f90:137
+    const float prd = k.kd * (pr + perc);                                // :138
     const float u = fmaxf(1.e-6f, fmaf(prr, k.inv_cft, hft));            // md_gr_operator.f90:102
     const float z = pow4(u);
     const float s2 = fsqrt_fast(1.0f + z), s1 = fsqrt_fast(s2);
@@ -252,8 +256,8 @@ __device__ __forceinline__ void vertical_step_b(const CellConst &k, float prcp, 
         perc = hp_imd * k.cp * (1.0f - pwr1);
         l = (k.exc == 0.0f) ? 0.0f : k.exc * pow_3p5(hft0);
     }
-    const float prr = 0.9f * (pr + perc) + l;
-    const float prd = 0.1f * (pr + perc);
+    const float prr = k.kr * (pr + perc) + l;
+    const float prd = k.kd * (pr + perc);
     const float qr_b = qt_b, qd_b = qt_b;
     float prd_b = 0.0f, l_b = 0.0f;
     if (0.0f < prd + l) { prd_b = qd_b; l_b = qd_b; }                     // :8128-8137
@@ -299,7 +303,7 @@ __device__ __forceinline__ void vertical_step_b(const CellConst &k, float prcp, 
         }
         hft_b = htb;
     }
-    const float pr_b = 0.1f * prd_b + 0.9f * prr_b;                       // :8143
+    const float pr_b = k.kd * prd_b + k.kr * prr_b;                       // :8143
     float perc_b = pr_b;
     l_b += prr_b;
     if (nogap) {

@@ -62,8 +62,8 @@ __device__ __forceinline__ float vertical_step_lean(const CellConst &k, float pr
     const float pr = wet ? pn - (hp_imd - hp) * k.cp : 0.0f;             // :60-62
     hp = hp_imd;                                                         // perc == 0 (:66-68)
     const float l = EXC ? k.exc * ((hft * hft) * hft * fsqrt_fast(hft)) : 0.0f;             // :77
-    const float prr = fmaf(0.9f, pr, l);                                 // md_forward_structure.f90:137
-    const float prd = 0.1f * pr;                                         // :138
+    const float prr = fmaf(k.kr, pr, l);                                 // md_forward_structure.f90:137
+    const float prd = k.kd * pr;                                         // :138
     const float u = fmaxf(1.e-6f, fmaf(prr, k.inv_cft, hft));            // md_gr_operator.f90:102
     const float z = pow4(u);
     const float s2 = fsqrt_fast(1.0f + z), s1 = fsqrt_fast(s2);
@@ -103,8 +103,8 @@ __device__ __forceinline__ void vertical_step_b_lean(const CellConst &k, float i
     const float pr = wet ? pn - (hp_imd - hp) * k.cp : 0.0f;          // :60-62
     const float h25 = (ht * ht) * fsqrt_fast(ht);                     // hft^2.5
     const float l = EXC ? k.exc * (h25 * ht) : 0.0f;                  // :77
-    const float prr = fmaf(0.9f, pr, l);
-    const float prd = 0.1f * pr;
+    const float prr = fmaf(k.kr, pr, l);
+    const float prd = k.kd * pr;
     // reverse
     const float qr_b = qt_b;
     const bool qd_on = 0.0f < prd + l;                                // forward_db.f90:8128-8137
@@ -130,7 +130,7 @@ __device__ __forceinline__ void vertical_step_b_lean(const CellConst &k, float i
     const float prr_b = first ? ht_imd_b * ict : 0.0f;
     if (first) cft_b -= (prr * ht_imd_b) * inv_cft2;
     hft_b = first ? ht_imd_b : 0.0f;
-    const float pr_b = fmaf(0.9f, prr_b, 0.1f * prd_b);               // :8143
+    const float pr_b = fmaf(k.kr, prr_b, k.kd * prd_b);               // :8143
     l_b += prr_b;
     exc_b = fmaf(h25 * ht, l_b, exc_b);                               // GR_EXCHANGE_B (pre-transfer hft); exc_b is fed even where exc == 0
     if (EXC) hft_b = fmaf(3.5f * h25 * k.exc, l_b, hft_b);
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_forward_kernel(const _
     if (valid) {
         fa = a.tp.flwacc[j];
         k = make_const(fld[(size_t)F_CP * npad], fld[(size_t)F_CFT * npad], fld[(size_t)F_EXC * npad], fld[(size_t)F_LR * npad], fa,
-                       a.dt, a.dx);
+                       a.dt, a.dx, a.grd != 0);
         hp = fld[(size_t)F_HP * npad]; hft = fld[(size_t)F_HFT * npad]; hlr = fld[(size_t)F_HLR * npad];
         if (t_begin > 0) {                                               // a later window: the states the previous one left
             const float *fs = a.fstates + (size_t)m * 3 * npad + j;
@@ -1386,7 +1386,7 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const _
     int d = -1, dlag = 0, gfirst = -1;
     if (valid) {
         k = make_const(fld[(size_t)F_CP * npad], fld[(size_t)F_CFT * npad], fld[(size_t)F_EXC * npad], fld[(size_t)F_LR * npad],
-                       a.tp.flwacc[j], a.dt, a.dx);
+                       a.tp.flwacc[j], a.dt, a.dx, a.grd != 0);
         d = a.tp.down[j]; dlag = a.tp.down_lag[j]; gfirst = a.tp.gauge_first[j];
     }
     const float *wrow = (d >= 0) ? a.rows_w + ((size_t)m * npad + d) * a.Tp : nullptr;
@@ -1474,7 +1474,8 @@ __global__ void __launch_bounds__(VT_WARPS * 32) vertical_adjoint_kernel(const _
     }
     if (valid) {
         float *g = a.grad + (size_t)m * NFIELD * npad + j;
-        g[(size_t)F_CP * npad] = cp_b; g[(size_t)F_CFT * npad] = cft_b; g[(size_t)F_EXC * npad] = exc_b;
+        g[(size_t)F_CP * npad] = cp_b; g[(size_t)F_CFT * npad] = cft_b;
+        g[(size_t)F_EXC * npad] = a.grd ? 0.0f : exc_b;                       // gr-d has no exchange: parameters_b%exc stays 0 (forward_db.f90:9604-9797)
         g[(size_t)F_HP * npad] = hp_b; g[(size_t)F_HFT * npad] = hft_b;
     }
 }

@@ -57,6 +57,7 @@ struct SplitArgs {
     int nmember;
     float dt, dx;
     int save_q, save_netp;
+    int grd;                     // 1: the gr-a kernels run gr-d's statements (shares 1 / 0, no exchange; cell_math.cuh CellConst::kr, kd)
     int fuse_export;             // 1: the routing warps also write the routed cells' series to qdom ([t][cell]) once their chains are done
     unsigned long long *dbg_prof;  // diagnostics: per dedicated chain [cells, cycles, cycles waiting for tributaries, end time ns], or nullptr
     const float *fields;         // [m][NFIELD][npad]

@@ -137,7 +137,7 @@ def test_forward_forcing_gaps(structure):
     check_states(a, b, structure)
 
 
-@pytest.mark.parametrize("structure", ["gr-b", "vic-a"])
+@pytest.mark.parametrize("structure", ["gr-b", "gr-d", "vic-a"])
 def test_forward_france_crop_vs_oracle(structure):
     # a France crop with pit pairs and long rivers: the routing passes behind the new reservoir pass, sparse storage
     def make():
@@ -170,13 +170,31 @@ def test_multiple_run_gr_c_vs_oracle():
     assert close_q(qsim, want_q, ref_q)
 
 
-@pytest.mark.parametrize("structure", STRUCTURES)
+@pytest.mark.parametrize("jobs", [("nse",), ("kge",)])
+def test_gr_d_gradient_vs_oracle(jobs):
+    # gr-d runs on gr-a's kernels with the shares 1 / 0 and no exchange (SplitArgs::grd): forward tape + reverse sweep against the
+    # oracle's restatement of GR_D_FORWARD_B (forward_db.f90:9604-9797), tolerances of test_gpu_parity.py
+    from test_gpu_parity import check_grad, gradients, random_fields
+    a, b = cases.cance(), cases.cance()
+    for m in (a, b):
+        m.setup.structure = "gr-d"
+        cases.set_optimize(m.setup, m.mesh, jobs_fun=jobs, gauge="all")
+        random_fields(m)
+    pa, sa = gradients(a, "gpu")
+    pb, sb = gradients(b, "cpu")
+    check_grad(pa, pb, ("cp", "cft", "lr"))
+    check_grad(sa, sb, ("hp", "hft", "hlr"))
+    assert not np.any(pa.exc) and not np.any(pb.exc)                           # exc is not a parameter of gr-d
+    assert abs(float(a.output.cost) - float(b.output.cost)) < 1e-5
+
+
+@pytest.mark.parametrize("structure", ["gr-b", "gr-c", "vic-a"])
 def test_adjoint_is_refused(structure):
-    # only GR_A_FORWARD_B is built: the library says so instead of returning a gr-a gradient
+    # GR_A_FORWARD_B and GR_D_FORWARD_B are built: for the others the library says so instead of returning a gr-a gradient
     m = cases.cance(T=48)
     m.setup.structure = structure
     pb, sb = ParametersDT(m.mesh), StatesDT(m.mesh)
-    with pytest.raises(RuntimeError, match="gr-a only"):
+    with pytest.raises(RuntimeError, match="gr-a and gr-d only"):
         smash_b200.forward_b(m.setup, m.mesh, m.input_data, m.parameters, pb, m.parameters.copy(), None, m.states, sb, m.states.copy(),
                              None, m.output, None)
 

@@ -150,3 +150,42 @@ def test_hyper_adjoint_vs_finite_differences(mapping):
                 vals.append(J(h2))
             fd = (vals[0] - vals[1]) / (2 * eps)
             assert np.isclose(fd, float(getattr(hpb, n)[k, 0]), rtol=5e-4, atol=1e-9), (n, k, fd, float(getattr(hpb, n)[k, 0]))
+
+
+def test_gr_d_adjoint_vs_finite_differences():
+    # GR_D_FORWARD_B (forward_db.f90:9604-9797) restated as the gr-d mode of the taped loop: directional derivatives against
+    # central differences of the INDEPENDENT forward restatement (structure_forward), double precision
+    m = make(("nse",))
+    m.setup.structure = "gr-d"
+    pb, sb = grad(m)
+    rng = np.random.default_rng(9)
+    act = (m.mesh.active_cell == 1)
+    for obj, g, name, eps in ((m.parameters, pb, "cp", 1e-4), (m.parameters, pb, "cft", 1e-4), (m.parameters, pb, "lr", 1e-5),
+                              (m.states, sb, "hp", 1e-7), (m.states, sb, "hft", 1e-7)):
+        direction = rng.standard_normal(act.shape) * act
+        base = np.array(getattr(obj, name), dtype=np.float64)
+        vals = []
+        for sgn in (+1, -1):
+            c = m.copy()
+            tgt = c.parameters if obj is m.parameters else c.states
+            setattr(tgt, name, np.asfortranarray(base + sgn * eps * direction))
+            vals.append(float(oracle.forward(c.setup, c.mesh, c.input_data, c.parameters, m.parameters.copy(), c.states,
+                                             m.states.copy(), c.output, precision="f64")))
+        fd = (vals[0] - vals[1]) / (2 * eps)
+        ad = float((np.asarray(getattr(g, name), np.float64) * direction).sum())
+        assert np.isclose(fd, ad, rtol=2e-4, atol=1e-10), (name, fd, ad)
+    assert not np.any(pb.exc)                                                 # exc is not a parameter of gr-d
+    # the cost the adjoint run reports is the forward run's
+    c = m.copy()
+    pb2, sb2 = ParametersDT(m.mesh), StatesDT(m.mesh)
+    cb = oracle.forward_b(c.setup, c.mesh, c.input_data, c.parameters, pb2, m.parameters.copy(), c.states, sb2, m.states.copy(), c.output,
+                          precision="f64")
+    assert cb is None or np.isclose(float(c.output.cost), cost(m), rtol=1e-12)
+
+
+def test_other_adjoints_are_refused():
+    for s in ("gr-b", "gr-c", "vic-a"):
+        m = make(("nse",))
+        m.setup.structure = s
+        with pytest.raises(AssertionError):
+            grad(m)
