@@ -18,7 +18,8 @@
  * no CPU fallback: without a CUDA device every compute entry point fails with SMASH_B200_ENODEV.
  * Structures: gr-a (the structure named by BASELINE.json's configs) behind every entry point; gr-b, gr-c, gr-d and vic-a
  * (forward/md_forward_structure.f90:216-931) behind smash_b200_forward, smash_b200_compute_multiple_run and the plan API's forward
- * run -- their adjoint and descriptor mappings answer SMASH_B200_EUNSUPPORTED.
+ * run; gr-d also behind smash_b200_forward_b (GR_D_FORWARD_B, forward_db.f90:9604-9797).  The adjoint of gr-b / gr-c / vic-a and the
+ * descriptor mappings of the four answer SMASH_B200_EUNSUPPORTED.
  */
 #ifndef SMASH_B200_H
 #define SMASH_B200_H
