@@ -520,13 +520,15 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
                 lib.smash_b200_plan_destroy(plan2)
                 structures[name] = {"ms_per_step": float(np.mean(tms)), "cell_timesteps_per_s": units / (float(np.mean(tms)) * 1e-3),
                                     "frac_of_12B_roofline": step_bytes / (float(np.mean(tms)) * 1e-3) / 1e9 / peak,
-                                    "kernels_ms": {"vertical_struct_kernel": float(kt[0]), "route_forward_kernel": float(kt[1])},
+                                    "kernels_ms": {("vertical_forward_kernel (gr-d mode)" if name == "gr-d" else "vertical_struct_kernel"): float(kt[0]),
+                                                   "route_forward_kernel": float(kt[1])},
                                     "checksum_q": chk2.value}
             finally:
                 model.setup.structure = "gr-a"
                 model.parameters.ci[...] = 1e-6
         structures["note"] = ("forward runs of md_forward_structure.f90:216-931 on the row passes; same 12 B per cell-step of algorithmic "
-                              "traffic as gr-a; the reservoir pass is instruction-bound (divisions, powf of vic_infiltration)")
+                              "traffic as gr-a; the reservoir pass is instruction-bound (divisions, powf of vic_infiltration); gr-d runs on "
+                              "gr-a's kernels with the shares 1 / 0 and no exchange (DESIGN.md section 3f)")
 
     # ---- the ANN mapping's forward pass at France scale: the graph of _ann_optimize.py:143-168 for nd = 6 descriptors
     ann = None
