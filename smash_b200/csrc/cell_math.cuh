@@ -105,7 +105,7 @@ __device__ __forceinline__ float fsqrt_fast(float x) { return x * mufu_rsq(x); }
 struct CellConst {
     float cp, inv_cp, cft, inv_cft, cft_m4, exc, lr, E, fa1, den;  // den = 0.001*dx*dx*(flwacc-1)
     float s_q, c0;                                                  // dt/den (0 for sources) and dx*dx*0.001/dt
-    float kr, kd;   // shares of pr + perc that go to the transfer store / to the direct branch: 0.9, 0.1 (md_forward_structure.f90:137-138);
+    float kr = 0.9f, kd = 0.1f;   // shares of pr + perc that go to the transfer store / to the direct branch: 0.9, 0.1 (md_forward_structure.f90:137-138);
                     // 1, 0 with exc = 0 turns every statement into gr_d_forward's (:685-689) and the reverse sweep into GR_D_FORWARD_B
 };
 

@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(TK_WARPS * 32, MINB) tick_forward_kernel(const
                 CellConst kc;
                 kc.cp = c4.x; kc.inv_cp = __frcp_rn(c4.x);                 // md_gr_operator.f90:47
                 kc.cft = c4.y; kc.inv_cft = __frcp_rn(c4.y); kc.cft_m4 = __frcp_rn(pow4(c4.y));
-                kc.exc = c4.z; kc.lr = 0.0f; kc.E = c4.w;
+                kc.exc = c4.z; kc.lr = 0.0f; kc.E = c4.w; kc.kr = 0.9f; kc.kd = 0.1f;
                 kc.fa1 = (float)((unsigned)meta >> 13); kc.den = 0.0f; kc.c0 = c0;
                 kc.s_q = (cls == 1) ? __fdiv_rn(a.dt, d0 * kc.fa1) : 0.0f; // dt / (0.001 dx^2 (flwacc - 1)), md_routing_operator.f90:56
                 const bool far = cons >= 0 && (cons & (1 << 30)) != 0;
