@@ -32,6 +32,32 @@ def test_version_and_no_device_is_loud():
         with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
             smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(),
                                m.output)
+        # the other structures and the interception search are device-only as well: same loud failure, no host path
+        m.setup.structure = "vic-a"
+        with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+            smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(),
+                               m.output)
+        from smash_b200.solver import _mw_interception_store as ics
+        with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+            ics.adjust_interception_store(m.setup, m.mesh, m.input_data, m.parameters, 1, np.ones(24, np.int32))
+
+
+def test_interception_store_argument_checks():
+    # argument errors are reported before the device is needed
+    from smash_b200.solver import _mw_interception_store as ics
+    m = cases.cance(T=48)
+    with pytest.raises(ValueError, match="day_index"):
+        ics.adjust_interception_store(m.setup, m.mesh, m.input_data, m.parameters, 2, np.ones(24, np.int32))
+    with pytest.raises(RuntimeError, match="nday"):
+        ics.adjust_interception_store(m.setup, m.mesh, m.input_data, m.parameters, 1, (np.arange(48) // 24 + 1).astype(np.int32))
+
+
+def test_unknown_structure_is_refused_on_the_host():
+    import smash_b200
+    m = cases.cance(T=24)
+    m.setup.structure = "gr-z"
+    with pytest.raises(ValueError, match="unknown structure"):
+        smash_b200.forward(m.setup, m.mesh, m.input_data, m.parameters, m.parameters.copy(), m.states, m.states.copy(), m.output)
 
 
 def mesh_order(m, block=0):
