@@ -489,6 +489,8 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
                     "ms_per_step": float(np.mean(tms)), "frac": step_bytes / (float(np.mean(tms)) * 1e-3) / 1e9 / peak,
                     "dram_traffic_bytes": tr2, "traffic_over_algorithmic": (tr2 / step_bytes) if tr2 else None,
                     "checksum_q": chk2.value, "note": note}
+            except Exception as exc:                      # a secondary block never costs the headline line
+                roofline["alternatives"][name] = {"error": str(exc), "note": note}
             finally:
                 lib.smash_b200_set_option(b"sub_engine", -1)
                 lib.smash_b200_set_option(b"tick_pass", 0)
@@ -523,6 +525,8 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
                                     "kernels_ms": {("vertical_forward_kernel (gr-d mode)" if name == "gr-d" else "vertical_struct_kernel"): float(kt[0]),
                                                    "route_forward_kernel": float(kt[1])},
                                     "checksum_q": chk2.value}
+            except Exception as exc:                      # a secondary block never costs the headline line
+                structures[name] = {"error": str(exc)}
             finally:
                 model.setup.structure = "gr-a"
                 model.parameters.ci[...] = 1e-6
