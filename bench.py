@@ -537,43 +537,46 @@ def bench_france(args, lib, L, smash_b200, cases, local_rank, peak, peak_src):
     # ---- the ANN mapping's forward pass at France scale: the graph of _ann_optimize.py:143-168 for nd = 6 descriptors
     ann = None
     if not args.no_extra:
-        from smash_b200.net import Net
-        nd_, n1 = 6, int(round(np.sqrt(nac * 6) * 2 / 3))
-        net = Net()
-        net.add("dense", {"input_shape": (nd_,), "neurons": n1, "kernel_initializer": "glorot_uniform"})
-        net.add("activation", {"name": "relu"})
-        net.add("dense", {"neurons": round(n1 / 2), "kernel_initializer": "glorot_uniform"})
-        net.add("activation", {"name": "relu"})
-        net.add("dense", {"neurons": 4, "kernel_initializer": "glorot_uniform"})
-        net.add("activation", {"name": "sigmoid"})
-        net.compile("adam", {"learning_rate": 0.003}, random_state=11)
-        xd = np.random.default_rng(3).uniform(0.0, 1.0, (nac, nd_)).astype(np.float32)
-        tm, best = {}, None
-        for _ in range(3):
-            yd = net._predict_device(xd, timing=tm)
-            best = dict(tm) if best is None or tm["ms"] < best["ms"] else best
-        from smash_b200.net import DeviceChain
-        dev = DeviceChain(net, xd)                       # one training step with the chain resident on the device
-        gyd = np.random.default_rng(4).uniform(0.5, 1.5, (nac, 4)).astype(np.float32) * np.float32(1e-6)
-        for _ in range(2):
-            dev.forward()
-            dev.backward(gyd)
-        train_ms = (dev.ms_forward, dev.ms_backward)
-        dev.close()
-        ref = net._predict(xd[:2000].astype(np.float64))
         try:
-            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-                bf16 = float(json.load(f)["bf16_tflops"])
-        except Exception:
-            bf16 = 2250.0
-        ann = {"rows": nac, "graph": [nd_, n1, round(n1 / 2), 4], "device_ms": best["ms"], "tflops": best["tflops"], "dtype": "tf32 (f32 accumulate)",
-               "frac_of_tf32_peak": best["tflops"] / (bf16 / 2.0), "tf32_peak_tflops": bf16 / 2.0,
-               "peak_source": "half the measured dense bf16 rate of MEASURED_PEAKS.json (TF32 runs at half the bf16 rate)",
-               "max_abs_err_vs_numpy_f64": float(np.abs(yd[:2000] - ref).max()),
-               "training_step_ms": {"forward": train_ms[0], "backward": train_ms[1],
-                                    "note": "backward = activation derivatives, column sums, grad_weight = a^T g (stream-K over the rows) and "
-                                            "g W^T per layer, all on the device; the optimiser update stays on the host"},
-               "kernel": "CUTLASS sm100 collective (TMA + tcgen05.mma kind::tf32, accumulators in TMEM), bias + activation fused"}
+            from smash_b200.net import Net
+            nd_, n1 = 6, int(round(np.sqrt(nac * 6) * 2 / 3))
+            net = Net()
+            net.add("dense", {"input_shape": (nd_,), "neurons": n1, "kernel_initializer": "glorot_uniform"})
+            net.add("activation", {"name": "relu"})
+            net.add("dense", {"neurons": round(n1 / 2), "kernel_initializer": "glorot_uniform"})
+            net.add("activation", {"name": "relu"})
+            net.add("dense", {"neurons": 4, "kernel_initializer": "glorot_uniform"})
+            net.add("activation", {"name": "sigmoid"})
+            net.compile("adam", {"learning_rate": 0.003}, random_state=11)
+            xd = np.random.default_rng(3).uniform(0.0, 1.0, (nac, nd_)).astype(np.float32)
+            tm, best = {}, None
+            for _ in range(3):
+                yd = net._predict_device(xd, timing=tm)
+                best = dict(tm) if best is None or tm["ms"] < best["ms"] else best
+            from smash_b200.net import DeviceChain
+            dev = DeviceChain(net, xd)                       # one training step with the chain resident on the device
+            gyd = np.random.default_rng(4).uniform(0.5, 1.5, (nac, 4)).astype(np.float32) * np.float32(1e-6)
+            for _ in range(2):
+                dev.forward()
+                dev.backward(gyd)
+            train_ms = (dev.ms_forward, dev.ms_backward)
+            dev.close()
+            ref = net._predict(xd[:2000].astype(np.float64))
+            try:
+                with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                    bf16 = float(json.load(f)["bf16_tflops"])
+            except Exception:
+                bf16 = 2250.0
+            ann = {"rows": nac, "graph": [nd_, n1, round(n1 / 2), 4], "device_ms": best["ms"], "tflops": best["tflops"], "dtype": "tf32 (f32 accumulate)",
+                   "frac_of_tf32_peak": best["tflops"] / (bf16 / 2.0), "tf32_peak_tflops": bf16 / 2.0,
+                   "peak_source": "half the measured dense bf16 rate of MEASURED_PEAKS.json (TF32 runs at half the bf16 rate)",
+                   "max_abs_err_vs_numpy_f64": float(np.abs(yd[:2000] - ref).max()),
+                   "training_step_ms": {"forward": train_ms[0], "backward": train_ms[1],
+                                        "note": "backward = activation derivatives, column sums, grad_weight = a^T g (stream-K over the rows) and "
+                                                "g W^T per layer, all on the device; the optimiser update stays on the host"},
+                   "kernel": "CUTLASS sm100 collective (TMA + tcgen05.mma kind::tf32, accumulators in TMEM), bias + activation fused"}
+        except Exception as exc:                          # a secondary block never costs the headline line
+            ann = {"error": str(exc)}
 
     # ---- e2e through the drop-in call with host buffers
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
